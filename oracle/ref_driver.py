@@ -1,0 +1,114 @@
+"""oracle/ref_driver.py -- TEST INFRASTRUCTURE (never imported by the product path).
+
+ctypes driver for the UNMODIFIED reference built by oracle/Makefile.ref into
+oracle/_ref/libliggghts_ref.so.  It speaks the reference's own C API
+(/root/reference/src/library.h:59-74) plus the read-only accessors of
+oracle/ref_shim.cpp.  Used (a) in this container to generate tests/golden/*.npz and to pin
+oracle/dem_oracle.c, (b) on the GPU box as the `--impl reference` CPU arm of bench.py.
+The reference calls exit(1) on errors (error.cpp:160-186), so decks are trusted input.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_ref", "libliggghts_ref.so")
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+class Ref:
+    def __init__(self, log=None):
+        self.lib = C.CDLL(LIB)
+        L = self.lib
+        L.lammps_open_no_mpi.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
+        L.lammps_close.argtypes = [C.c_void_p]
+        L.lammps_command.argtypes = [C.c_void_p, C.c_char_p]
+        L.lammps_command.restype = C.c_void_p
+        L.lammps_extract_atom.argtypes = [C.c_void_p, C.c_char_p]
+        L.lammps_extract_atom.restype = C.c_void_p
+        L.lammps_extract_fix.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.lammps_extract_fix.restype = C.c_void_p
+        L.lammps_get_natoms.argtypes = [C.c_void_p]
+        for f in ("ref_nlocal", "ref_nghost", "ref_neigh_ncalls"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.ref_ntimestep.argtypes = [C.c_void_p]
+        L.ref_ntimestep.restype = C.c_long
+        L.ref_pairlist_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_pairlist_dump.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        args = [b"liggghts", b"-screen", b"none", b"-log", (log or "none").encode(), b"-echo", b"none"]
+        argv = (C.c_char_p * len(args))(*args)
+        self.h = C.c_void_p()
+        L.lammps_open_no_mpi(len(args), argv, C.byref(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.lammps_close(self.h)
+            self.h = None
+
+    def cmd(self, text):
+        for line in text.strip().splitlines():
+            line = line.strip()
+            if line and not line.startswith("#"):
+                self.lib.lammps_command(self.h, line.encode())
+
+    @property
+    def nlocal(self):
+        return self.lib.ref_nlocal(self.h)
+
+    @property
+    def neigh_builds(self):
+        return self.lib.ref_neigh_ncalls(self.h)
+
+    def _vec(self, name, n, ctype, cols):
+        p = self.lib.lammps_extract_atom(self.h, name.encode())
+        if cols == 1:
+            arr = C.cast(p, C.POINTER(ctype))
+            return np.array([arr[i] for i in range(n)])
+        rows = C.cast(p, C.POINTER(C.POINTER(ctype)))
+        # rows of a contiguous block (memory.h create2d): copy through the first row pointer
+        base = C.cast(rows[0], C.POINTER(ctype * (n * cols)))
+        return np.array(base.contents, dtype=np.float64).reshape(n, cols).copy()
+
+    def atoms(self):
+        """per-particle state sorted by tag"""
+        n = self.nlocal
+        out = {"tag": self._vec("id", n, C.c_int, 1).astype(np.int32)}
+        out["type"] = self._vec("type", n, C.c_int, 1).astype(np.int32)
+        for k in ("x", "v", "f", "omega", "torque"):
+            out[k] = self._vec(k, n, C.c_double, 3)
+        for k in ("radius", "rmass", "density"):
+            out[k] = self._vec(k, n, C.c_double, 1).astype(np.float64)
+        o = np.argsort(out["tag"], kind="stable")
+        return {k: v[o] for k, v in out.items()}
+
+    def fix_peratom_array(self, fix_id, ncols):
+        """per-atom array of a fix (e.g. primitive-wall history 'history_<wallid>'), by tag"""
+        n = self.nlocal
+        tag = self._vec("id", n, C.c_int, 1)
+        p = self.lib.lammps_extract_fix(self.h, fix_id.encode(), 1, 2, 0, 0)
+        rows = C.cast(p, C.POINTER(C.POINTER(C.c_double)))
+        a = np.array([[rows[i][c] for c in range(ncols)] for i in range(n)], dtype=np.float64).reshape(n, ncols)
+        return a[np.argsort(tag, kind="stable")]
+
+    def pairs(self):
+        """granular half list: canonical (tag_lo, tag_hi) sorted, flag, history rows with the
+        sign convention of the (tag_lo -> first) orientation (all our history values are
+        newtonflag=1 vectors: they flip sign when the pair is viewed from the other side,
+        fix_contact_history.cpp:406-409)."""
+        dn = C.c_int(0)
+        n = self.lib.ref_pairlist_count(self.h, C.byref(dn))
+        dnum = dn.value
+        ti = np.zeros(n, np.int32); tj = np.zeros(n, np.int32)
+        ii = np.zeros(n, np.int32); jj = np.zeros(n, np.int32)
+        fl = np.zeros(n, np.int32); hist = np.zeros((n, max(dnum, 1)), np.float64)
+        self.lib.ref_pairlist_dump(self.h, ti.ctypes.data, tj.ctypes.data, ii.ctypes.data, jj.ctypes.data,
+                                   fl.ctypes.data, hist.ctypes.data if dnum else None)
+        hist = hist[:, :dnum]
+        swap = ti > tj
+        lo = np.where(swap, tj, ti); hi = np.where(swap, ti, tj)
+        hist = np.where(swap[:, None], -hist, hist)
+        o = np.lexsort((hi, lo))
+        return {"lo": lo[o], "hi": hi[o], "flag": fl[o], "hist": hist[o], "dnum": dnum}
