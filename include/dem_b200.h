@@ -1,0 +1,126 @@
+/* dem_b200.h -- C ABI of libdem_b200.so: the B200-native DEM timestep engine.
+ *
+ * This is the drop-in boundary for the per-timestep particle hot path of
+ * LIGGGHTS-INL.  One dem_engine == one GPU == one rank.
+ * Every entry point cites the reference interface it replaces (paths relative to
+ * the reference tree).  Plain pointers and sizes only; the caller owns every host
+ * buffer, the engine owns all device memory, streams and communicators.
+ *
+ * Error model: every call returns 0 on success or a negative dem_status; the
+ * message is available through dem_last_error().  Nothing aborts or throws across
+ * the boundary (the reference prints and exit(1)s: src/error.cpp:160-186).
+ *
+ * There is NO CPU fallback: dem_create fails when no sm_100 device is usable.
+ */
+#ifndef DEM_B200_H
+#define DEM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dem_engine dem_engine;
+
+enum dem_status {
+  DEM_OK = 0,
+  DEM_ERR_ARG = -1,         /* bad argument / unknown keyword                           */
+  DEM_ERR_UNSUPPORTED = -2, /* valid reference syntax that is outside the hot-path scope */
+  DEM_ERR_STATE = -3,       /* call order violated (e.g. run before setup)               */
+  DEM_ERR_CUDA = -4,        /* CUDA / NCCL runtime failure                               */
+  DEM_ERR_OVERFLOW = -5     /* a capacity the engine could not grow                      */
+};
+
+/* ---- life cycle ---------------------------------------------------------------------
+ * replaces: lammps_open_no_mpi / lammps_close           src/library.h:60-61
+ * device   CUDA ordinal; rank/nranks = position in the spatial brick of GPUs;
+ * nccl_id  128-byte ncclUniqueId shared by all ranks (NULL when nranks == 1);
+ * stream   cudaStream_t to launch on (NULL = legacy default stream).                  */
+int dem_create(dem_engine **out, int device, int rank, int nranks, const void *nccl_id, void *stream);
+void dem_destroy(dem_engine *e);
+const char *dem_last_error(const dem_engine *e);
+const char *dem_version(void);
+
+/* ---- deck-level settings (same vocabulary as the input script) --------------------- */
+/* `units si|cgs|micro`                                   src/update.cpp:160-260        */
+int dem_set_units(dem_engine *e, const char *style);
+/* `region block` + `create_box` + `boundary p|f|m`       src/domain.cpp, create_box.cpp */
+int dem_set_box(dem_engine *e, const double lo[3], const double hi[3], const int periodic[3]);
+/* number of atom types of `create_box N`                                                */
+int dem_set_ntypes(dem_engine *e, int ntypes);
+/* `processors Px Py Pz` (brick of GPUs; product must equal nranks) src/procmap.cpp      */
+int dem_set_processors(dem_engine *e, int px, int py, int pz);
+/* `neighbor <skin> bin` + `neigh_modify delay D every E check yes|no`
+ *                                                        src/neighbor.cpp:1362-1376     */
+int dem_set_neighbor(dem_engine *e, double skin, int every, int delay, int check);
+/* `timestep dt`                                                                         */
+int dem_set_timestep(dem_engine *e, double dt);
+/* `fix ID all property/global <name> scalar|peratomtype|peratomtypepair v...`
+ *                                  src/fix_property_global.cpp, global_properties.cpp   */
+int dem_set_property(dem_engine *e, const char *name, const char *kind, const double *values, int n);
+/* `pair_style gran model hertz|hooke tangential history [cohesion ...]
+ *  [rolling_friction cdt|epsd|epsd2] [key on|off ...]` (argv starts at "model")
+ *                          src/contact_models.cpp:158-260, src/pair_gran.cpp:229-558    */
+int dem_set_pair_style(dem_engine *e, int argc, const char *const *argv);
+/* `fix ID all wall/gran model ... primitive type T xplane|yplane|zplane P |
+ *  xcylinder|ycylinder|zcylinder R c1 c2 [shear x|y|z v]` (argv starts at "model")
+ *                                                        src/fix_wall_gran.cpp:171-330  */
+int dem_add_wall_primitive(dem_engine *e, const char *id, int argc, const char *const *argv);
+/* `fix ID all gravity g vector x y z`                    src/fix_gravity.cpp:301-383    */
+int dem_set_gravity(dem_engine *e, double magnitude, const double dir[3]);
+/* `fix ID <group> freeze` : particles whose mask has any bit of groupbit
+ *                                                        src/fix_freeze.cpp:121-144     */
+int dem_set_freeze(dem_engine *e, int groupbit);
+/* `fix ID <group> nve/sphere` : group integrated (default: bit 1 = all)
+ *                                                        src/fix_nve_sphere.cpp:134-244 */
+int dem_set_integrate(dem_engine *e, int groupbit);
+
+/* ---- particles ------------------------------------------------------------------------
+ * replaces: read_data rows `id type diameter density x y z` + velocities
+ *           src/atom_vec_sphere.cpp:1055-1083 ; lammps_scatter_atoms src/library.h:72
+ * mask may be NULL (all particles in group bit 1), v/omega may be NULL (zero).
+ * With nranks > 1 every rank passes the FULL set; each keeps what its brick owns.     */
+int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask,
+                         const double *x, const double *v, const double *omega,
+                         const double *radius, const double *density);
+
+/* ---- run --------------------------------------------------------------------------------
+ * dem_setup  == Verlet::setup  (forces with shearupdate = 0)   src/verlet.cpp:134-199
+ * dem_run(n) == Verlet::run(n)                                 src/verlet.cpp:264-391   */
+int dem_setup(dem_engine *e);
+int dem_run(dem_engine *e, long nsteps);
+
+/* ---- read-back (rows ordered by ascending tag over the particles THIS rank owns) ------
+ * replaces: lammps_extract_atom / lammps_gather_atoms          src/library.h:66,71
+ * field in {"tag","type","mask"} -> int32 x count ; {"radius","rmass","density"} ->
+ * double x count ; {"x","v","f","omega","torque"} -> double x 3*count.                  */
+long dem_nlocal(const dem_engine *e);
+int dem_download(dem_engine *e, const char *field, void *out, long count);
+/* granular pair list as the reference's half list: one row per unordered pair whose
+ * lower-tag particle is owned by this rank, sorted by (tag_lo,tag_hi); flag != 0 iff the
+ * pair holds contact history; hist has dnum doubles per row in the orientation
+ * "lower tag is i" (reference: NeighList::firstneigh/firstdouble of listgranhistory,
+ * src/neigh_gran.cpp:560-620, src/pair_gran_base.h:213-215).                             */
+int dem_pair_count(dem_engine *e, long *npairs, int *dnum);
+int dem_download_pairs(dem_engine *e, int *tag_lo, int *tag_hi, int *flag, double *hist);
+/* per-particle history of one primitive wall (reference: fix property/atom
+ * "history_<wallid>", src/fix_wall_gran.cpp:479-503); rows by ascending tag.            */
+int dem_download_wall_history(dem_engine *e, const char *wall_id, double *out, long count);
+
+typedef struct dem_stats {
+  long ntimestep;      /* steps taken since setup                                  */
+  long nbuilds;        /* neighbour list builds (reference: neighbor->ncalls)      */
+  long nlocal, nghost; /* owned / ghost particles on this rank                     */
+  long npairs_full;    /* entries in the full list (both directions)               */
+  long ncontacts_full; /* touching entries at the last step (both directions)      */
+  long kernel_launches;/* CUDA kernels launched by the engine so far               */
+  int maxneigh;        /* ELLPACK width in use                                     */
+  int dnum;            /* history doubles per pair                                 */
+  double step_kernel_ms;   /* device time of the fused step kernel, last dem_run  */
+  long step_kernel_calls;  /* launches that time covers                           */
+} dem_stats;
+int dem_get_stats(dem_engine *e, dem_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEM_B200_H */

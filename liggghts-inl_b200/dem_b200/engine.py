@@ -1,0 +1,185 @@
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+# every symbol declared in include/dem_b200.h
+ABI_SYMBOLS = [
+    "dem_create", "dem_destroy", "dem_last_error", "dem_version", "dem_set_units", "dem_set_box",
+    "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_property",
+    "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
+    "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
+    "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
+]
+
+
+class DemError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("ntimestep", C.c_long), ("nbuilds", C.c_long), ("nlocal", C.c_long), ("nghost", C.c_long),
+                ("npairs_full", C.c_long), ("ncontacts_full", C.c_long), ("kernel_launches", C.c_long),
+                ("maxneigh", C.c_int), ("dnum", C.c_int), ("step_kernel_ms", C.c_double),
+                ("step_kernel_calls", C.c_long)]
+
+
+def library_path():
+    return os.path.join(_ROOT, "libdem_b200.so")
+
+
+def load_library(path=None):
+    path = path or library_path()
+    if not os.path.exists(path):
+        raise DemError("libdem_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    return C.CDLL(path)
+
+
+def _strv(args):
+    arr = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
+    return len(args), arr
+
+
+class Engine:
+    """One DEM engine on one GPU.  `lib`/`prefix` exist so the test-suite can drive the CPU
+    oracle (tests only) through the very same call sequence."""
+
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None, stream=None, lib=None, prefix="dem_"):
+        self._lib = lib if lib is not None else load_library()
+        self._p = prefix
+        self._h = C.c_void_p()
+        f = self._fn("create")
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        idbuf = C.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
+        rc = f(C.byref(self._h), device, rank, nranks, idbuf, C.c_void_p(stream or 0))
+        if rc != 0 or not self._h:
+            msg = self._err() if self._h else "engine creation failed (no usable sm_100 GPU?)"
+            raise DemError(msg)
+
+    # -- plumbing -----------------------------------------------------------------------
+    def _fn(self, name):
+        return getattr(self._lib, self._p + name)
+
+    def _err(self):
+        f = self._fn("last_error"); f.restype = C.c_char_p; f.argtypes = [C.c_void_p]
+        return (f(self._h) or b"").decode()
+
+    def _call(self, name, argtypes, *args):
+        f = self._fn(name); f.argtypes = [C.c_void_p] + argtypes; f.restype = C.c_int
+        rc = f(self._h, *args)
+        if rc != 0:
+            raise DemError("%s%s failed (%d): %s" % (self._p, name, rc, self._err()))
+
+    def close(self):
+        if self._h:
+            f = self._fn("destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+            f(self._h); self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- deck vocabulary ----------------------------------------------------------------
+    def units(self, style):
+        self._call("set_units", [C.c_char_p], style.encode())
+
+    def box(self, lo, hi, periodic=(0, 0, 0)):
+        self._call("set_box", [C.POINTER(C.c_double)] * 2 + [C.POINTER(C.c_int)],
+                   (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_int * 3)(*[int(p) for p in periodic]))
+
+    def ntypes(self, n):
+        self._call("set_ntypes", [C.c_int], n)
+
+    def processors(self, px, py, pz):
+        self._call("set_processors", [C.c_int] * 3, px, py, pz)
+
+    def neighbor(self, skin, every=1, delay=0, check=True):
+        self._call("set_neighbor", [C.c_double, C.c_int, C.c_int, C.c_int], skin, every, delay, int(check))
+
+    def timestep(self, dt):
+        self._call("set_timestep", [C.c_double], dt)
+
+    def property_global(self, name, kind, values):
+        v = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).ravel()
+        self._call("set_property", [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int],
+                   name.encode(), kind.encode(), v.ctypes.data, v.size)
+
+    def pair_style(self, text):
+        """text as in the deck after `pair_style gran`, e.g. 'model hertz tangential history'"""
+        n, a = _strv(text.split())
+        self._call("set_pair_style", [C.c_int, C.POINTER(C.c_char_p)], n, a)
+
+    def wall_primitive(self, wall_id, text):
+        """text as in the deck after `fix ID all wall/gran`"""
+        n, a = _strv(text.split())
+        self._call("add_wall_primitive", [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)], wall_id.encode(), n, a)
+
+    def gravity(self, magnitude, direction):
+        self._call("set_gravity", [C.c_double, C.POINTER(C.c_double)], magnitude, (C.c_double * 3)(*direction))
+
+    def freeze(self, groupbit):
+        self._call("set_freeze", [C.c_int], groupbit)
+
+    def integrate(self, groupbit=1):
+        self._call("set_integrate", [C.c_int], groupbit)
+
+    # -- particles ----------------------------------------------------------------------
+    def upload(self, tag, type, x, radius, density, v=None, omega=None, mask=None):
+        n = len(tag)
+        self._keep = [np.ascontiguousarray(tag, np.int32), np.ascontiguousarray(type, np.int32),
+                      None if mask is None else np.ascontiguousarray(mask, np.int32),
+                      np.ascontiguousarray(x, np.float64), None if v is None else np.ascontiguousarray(v, np.float64),
+                      None if omega is None else np.ascontiguousarray(omega, np.float64),
+                      np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
+        ptr = [a.ctypes.data if a is not None else None for a in self._keep]
+        self._call("upload_particles", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
+
+    def setup(self):
+        self._call("setup", [])
+
+    def run(self, nsteps):
+        self._call("run", [C.c_long], int(nsteps))
+
+    # -- read-back ----------------------------------------------------------------------
+    @property
+    def nlocal(self):
+        f = self._fn("nlocal"); f.argtypes = [C.c_void_p]; f.restype = C.c_long
+        return f(self._h)
+
+    def download(self, field):
+        n = self.nlocal
+        if field in ("tag", "type", "mask"):
+            out = np.zeros(n, np.int32)
+        elif field in ("radius", "rmass", "density"):
+            out = np.zeros(n, np.float64)
+        else:
+            out = np.zeros((n, 3), np.float64)
+        self._call("download", [C.c_char_p, C.c_void_p, C.c_long], field.encode(), out.ctypes.data, n)
+        return out
+
+    def atoms(self, fields=("tag", "type", "x", "v", "f", "omega", "torque", "radius", "rmass")):
+        return {k: self.download(k) for k in fields}
+
+    def pairs(self):
+        npairs = C.c_long(0); dnum = C.c_int(0)
+        self._call("pair_count", [C.POINTER(C.c_long), C.POINTER(C.c_int)], C.byref(npairs), C.byref(dnum))
+        n, d = npairs.value, dnum.value
+        lo = np.zeros(n, np.int32); hi = np.zeros(n, np.int32); fl = np.zeros(n, np.int32)
+        hist = np.zeros((n, max(d, 1)), np.float64)
+        self._call("download_pairs", [C.c_void_p] * 4, lo.ctypes.data, hi.ctypes.data, fl.ctypes.data, hist.ctypes.data)
+        return {"lo": lo, "hi": hi, "flag": fl, "hist": hist[:, :d], "dnum": d}
+
+    def wall_history(self, wall_id, dnum):
+        n = self.nlocal
+        out = np.zeros((n, max(dnum, 1)), np.float64)
+        self._call("download_wall_history", [C.c_char_p, C.c_void_p, C.c_long], wall_id.encode(), out.ctypes.data, n)
+        return out[:, :dnum]
+
+    def stats(self):
+        s = Stats()
+        self._call("get_stats", [C.POINTER(Stats)], C.byref(s))
+        return s

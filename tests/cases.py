@@ -1,0 +1,141 @@
+"""Seeded test cases shared by the golden generator (reference), the oracle and the CUDA
+engine.  A case is a plain dict; `to_deck` renders it as a LIGGGHTS input script + data
+file for the unmodified reference, `apply` replays it on an Engine-like object (the CUDA
+engine or, in tests only, the CPU oracle) through the C ABI."""
+import numpy as np
+
+SEED = 20261017
+
+
+def lattice(n3, pitch, origin, jitter, rng):
+    nx, ny, nz = n3
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3)
+    return np.asarray(origin) + g * pitch + rng.uniform(-jitter, jitter, (len(g), 3))
+
+
+def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdt", seed=SEED,
+             poly=False, periodic=(0, 0, 0), ntypes=1, hooke=False, frozen=0, cyl=False, shear=False, name="box",
+             settings=""):
+    """particles on a jittered lattice falling under gravity onto a floor inside side walls"""
+    rng = np.random.default_rng(seed)
+    rad = 0.0025
+    pitch = 2.05 * rad if not poly else 2.05 * 0.003
+    L = max(n3[0], n3[1]) * pitch
+    lo = [0.0, 0.0, 0.0]; hi = [L, L, 4 * n3[2] * pitch + 0.02]
+    if cyl:  # the cylinder (radius 0.64 L about the box centre) reaches outside the lattice footprint
+        lo = [-0.2 * L, -0.2 * L, 0.0]; hi = [1.2 * L, 1.2 * L, hi[2]]
+    x = lattice(n3, pitch, [0.5 * pitch, 0.5 * pitch, 0.6 * pitch], 0.04 * rad, rng)
+    n = len(x)
+    radius = rng.uniform(0.0015, 0.003, n) if poly else np.full(n, rad)
+    typ = (np.arange(n) % ntypes + 1).astype(np.int32)
+    v = np.tile([0.0, 0.0, -0.5], (n, 1)) + rng.uniform(-0.3, 0.3, (n, 3))
+    mask = np.ones(n, np.int32)
+    if frozen:
+        mask[:frozen] |= 2
+        v[:frozen] = 0.0
+    T = ntypes
+    props = [("youngsModulus", "peratomtype", [5e6, 7e6, 9e6][:T]),
+             ("poissonsRatio", "peratomtype", [0.45, 0.3, 0.25][:T]),
+             ("coefficientRestitution", "peratomtypepair", (0.3 + 0.1 * np.add.outer(np.arange(T), np.arange(T))).ravel()),
+             ("coefficientFriction", "peratomtypepair", (0.5 - 0.05 * np.add.outer(np.arange(T), np.arange(T))).ravel()),
+             ("coefficientRollingFriction", "peratomtypepair", (0.1 + 0.02 * np.add.outer(np.arange(T), np.arange(T))).ravel())]
+    if "epsd " in model + " ":
+        props.append(("coefficientRollingViscousDamping", "peratomtypepair", np.full(T * T, 0.3)))
+    if "hooke" in model:
+        props.append(("characteristicVelocity", "scalar", [2.0]))
+    # wall/gran keyword order: model selection, wall keywords, then on/off settings (fix_wall_gran.cpp:150-342)
+    st = (" " + settings) if settings else ""
+    walls = [("zw", model + " primitive type %d zplane 0.0" % T + (" shear x 0.2" if shear else "") + st)]
+    if cyl:
+        walls.append(("cw", model + " primitive type 1 zcylinder %.17g %.17g %.17g" % (0.64 * L, 0.5 * L, 0.5 * L)
+                      + (" shear z 0.3" if shear else "") + st))
+    else:
+        if not periodic[0]:
+            walls += [("x0", model + " primitive type 1 xplane 0.0" + st), ("x1", model + " primitive type 1 xplane %.17g" % L
+                       + (" shear y 0.2" if shear else "") + st)]
+        if not periodic[1]:
+            walls += [("y0", model + " primitive type 1 yplane 0.0" + st), ("y1", model + " primitive type 1 yplane %.17g" % L + st)]
+    return dict(name=name, lo=lo, hi=hi, periodic=list(periodic), ntypes=T, skin=0.001, dt=1e-5, props=props,
+                pair=model + st, walls=walls, gravity=(9.81, [0.0, 0.0, -1.0]), freeze=2 if frozen else 0,
+                tag=np.arange(1, n + 1, dtype=np.int32), type=typ, mask=mask, x=x, v=v,
+                omega=rng.uniform(-5, 5, (n, 3)) * (0 if frozen else 1) + 0.0, radius=radius, density=np.full(n, 2500.0))
+
+
+def to_deck(c, datafile):
+    """LIGGGHTS deck + data file text for the reference (grammar: SURVEY.md 8b)"""
+    n = len(c["tag"])
+    data = ["synthetic case %s" % c["name"], "", "%d atoms" % n, "%d atom types" % c["ntypes"], "",
+            "%.17g %.17g xlo xhi" % (c["lo"][0], c["hi"][0]), "%.17g %.17g ylo yhi" % (c["lo"][1], c["hi"][1]),
+            "%.17g %.17g zlo zhi" % (c["lo"][2], c["hi"][2]), "", "Atoms", ""]
+    for i in range(n):
+        data.append("%d %d %.17g %.17g %.17g %.17g %.17g" % (c["tag"][i], c["type"][i], 2 * c["radius"][i],
+                                                           c["density"][i], *c["x"][i]))
+    data += ["", "Velocities", ""]
+    for i in range(n):
+        data.append("%d %.17g %.17g %.17g %.17g %.17g %.17g" % (c["tag"][i], *c["v"][i], *c["omega"][i]))
+    b = " ".join("p" if p else "f" for p in c["periodic"])
+    deck = ["units si", "atom_style sphere", "atom_modify map array sort 0 0", "boundary " + b, "newton off",
+            "communicate single vel yes", "read_data " + datafile, "neighbor %.17g bin" % c["skin"],
+            "neigh_modify delay 0"]
+    for k, (name, kind, vals) in enumerate(c["props"]):
+        extra = " %d" % c["ntypes"] if kind == "peratomtypepair" else ""
+        deck.append("fix m%d all property/global %s %s%s %s" % (k, name, kind, extra, " ".join("%.17g" % v for v in vals)))
+    deck += ["pair_style gran " + c["pair"], "pair_coeff * *"]
+    if c["gravity"]:
+        deck.append("fix grav all gravity %.17g vector %g %g %g" % (c["gravity"][0], *c["gravity"][1]))
+    for wid, text in c["walls"]:
+        deck.append("fix %s all wall/gran %s" % (wid, text))
+    if c["freeze"]:
+        ids = " ".join(str(t) for t in c["tag"][(c["mask"] & c["freeze"]) != 0])
+        deck += ["group frozen id " + ids, "fix frz frozen freeze"]
+    deck += ["fix integr all nve/sphere", "timestep %.17g" % c["dt"]]
+    return "\n".join(deck), "\n".join(data) + "\n"
+
+
+def apply(c, eng):
+    """replay the case on an Engine (C ABI call sequence == deck order)"""
+    eng.units("si")
+    eng.box(c["lo"], c["hi"], c["periodic"])
+    eng.ntypes(c["ntypes"])
+    eng.neighbor(c["skin"], every=1, delay=0, check=True)
+    for name, kind, vals in c["props"]:
+        eng.property_global(name, kind, vals)
+    eng.pair_style(c["pair"])
+    if c["gravity"]:
+        eng.gravity(*c["gravity"])
+    for wid, text in c["walls"]:
+        eng.wall_primitive(wid, text)
+    if c["freeze"]:
+        eng.freeze(c["freeze"])
+    eng.integrate(1)
+    eng.timestep(c["dt"])
+    eng.upload(c["tag"], c["type"], c["x"], c["radius"], c["density"], v=c["v"], omega=c["omega"], mask=c["mask"])
+    return eng
+
+
+GOLDEN_CASES = {
+    "box_hertz_cdt": dict(kw=dict(n3=(4, 4, 4)), checkpoints=[0, 1, 2, 10, 400, 2500]),
+    "poly_hooke_epsd_cyl": dict(kw=dict(n3=(4, 4, 5), model="model hooke tangential history rolling_friction epsd",
+                                        poly=True, ntypes=2, cyl=True, shear=True, frozen=6),
+                                checkpoints=[0, 1, 2, 10, 400, 2500]),
+    "periodic_epsd2": dict(kw=dict(n3=(5, 5, 4), model="model hertz tangential history rolling_friction epsd2", settings="limitForce on",
+                                   poly=True, periodic=(1, 1, 0), ntypes=2, shear=True), checkpoints=[0, 1, 2, 10, 400, 2500]),
+    "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
+                                         poly=True), checkpoints=[0, 1, 300, 1500]),
+}
+
+
+def make_case(name):
+    g = GOLDEN_CASES[name]
+    return case_box(name=name, **g["kw"])
+
+
+def snapshot(eng, c):
+    """state + bookkeeping of an Engine-like object as a flat dict of arrays"""
+    out = dict(eng.atoms(("x", "v", "f", "omega", "torque")))
+    p = eng.pairs()
+    out.update(pair_lo=p["lo"], pair_hi=p["hi"], pair_flag=(p["flag"] != 0).astype(np.int32), pair_hist=p["hist"])
+    for wid, text in c["walls"]:
+        dn = 3 + (3 if ("epsd" in text) else 0)
+        out["wall_" + wid] = eng.wall_history(wid, dn)
+    return out

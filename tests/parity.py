@@ -1,0 +1,78 @@
+"""Parity helpers (tests only).  Tolerances: SURVEY.md 8d / BASELINE.json north_star --
+pair sets and history bookkeeping bit-exact; forces/torques rel. err <= 1e-10 (fp64)."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+FTOL = 1e-10
+
+
+def oracle_lib():
+    """build (if needed) and load the CPU restatement -- the checker, never the product"""
+    src = os.path.join(ROOT, "oracle", "dem_oracle.c")
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True, capture_output=True)
+    return ctypes.CDLL(ORACLE_SO)
+
+
+def oracle_engine():
+    import dem_b200
+    return dem_b200.Engine(lib=oracle_lib(), prefix="orc_")
+
+
+def unique_pairs(lo, hi, flag, hist):
+    """the reference lists an owned/periodic-ghost pair on both sides: keep one row per pair"""
+    key = lo.astype(np.int64) * (1 << 32) + hi.astype(np.int64)
+    _, idx = np.unique(key, return_index=True)
+    return lo[idx], hi[idx], flag[idx], hist[idx]
+
+
+def rel_err(a, b, floor):
+    """max |a-b| / max(|b|_row, floor): per-particle vector error with an absolute floor"""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    den = np.maximum(np.linalg.norm(b.reshape(len(b), -1), axis=1), floor)
+    return float(np.max(np.linalg.norm((a - b).reshape(len(b), -1), axis=1) / den)) if len(b) else 0.0
+
+
+def compare_snapshot(got, ref, rmass, tol=FTOL, tol_state=None, hist_tol=None, label=""):
+    """got/ref: dicts with x,v,f,omega,torque,pair_lo,pair_hi,pair_flag,pair_hist,(wall_*)"""
+    tol_state = tol if tol_state is None else tol_state
+    hist_tol = tol if hist_tol is None else hist_tol
+    mg = rmass * 9.81
+    glo, ghi, gfl, gh = unique_pairs(got["pair_lo"], got["pair_hi"], got["pair_flag"], got["pair_hist"])
+    rlo, rhi, rfl, rh = unique_pairs(ref["pair_lo"], ref["pair_hi"], ref["pair_flag"], ref["pair_hist"])
+    assert len(glo) == len(rlo) and np.array_equal(glo, rlo) and np.array_equal(ghi, rhi), label + ": pair set differs"
+    assert np.array_equal(gfl != 0, rfl != 0), label + ": contact flags differ"
+    errs = {}
+    if rh.size:
+        scale = max(np.abs(rh).max(), 1e-300)
+        errs["hist"] = float(np.abs(gh - rh).max() / scale)
+        assert errs["hist"] <= hist_tol, "%s: history rel err %.3e" % (label, errs["hist"])
+    errs["f"] = rel_err(got["f"], ref["f"], 1e-12 * mg)
+    rad_t = 1e-12 * mg * 1e-3
+    errs["torque"] = rel_err(got["torque"], ref["torque"], np.maximum(rad_t, 1e-6 * np.linalg.norm(ref["f"], axis=1) * 1e-3))
+    assert errs["f"] <= tol, "%s: force rel err %.3e" % (label, errs["f"])
+    assert errs["torque"] <= tol, "%s: torque rel err %.3e" % (label, errs["torque"])
+    for k, fl in (("x", 1e-3), ("v", 1e-3), ("omega", 1e-2)):
+        errs[k] = rel_err(got[k], ref[k], fl)
+        assert errs[k] <= tol_state, "%s: %s rel err %.3e" % (label, k, errs[k])
+    for k in ref:
+        if k.startswith("wall_") and k in got:
+            scale = max(np.abs(ref[k]).max(), 1e-300)
+            errs[k] = float(np.abs(got[k] - ref[k]).max() / scale)
+            tiny = 1e-12 * scale  # projections leave 1e-40-size residues: "zeroed" means far below scale
+            assert np.array_equal(np.abs(got[k]) > tiny, np.abs(ref[k]) > tiny), "%s: %s bookkeeping differs" % (label, k)
+            assert errs[k] <= hist_tol, "%s: %s rel err %.3e" % (label, k, errs[k])
+    return errs
+
+
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+
+def golden_at(g, cp):
+    pre = "s%d_" % cp
+    return {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
