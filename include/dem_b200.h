@@ -40,6 +40,10 @@ void dem_destroy(dem_engine *e);
 const char *dem_last_error(const dem_engine *e);
 const char *dem_version(void);
 
+/* engine tuning knobs that have no deck equivalent: "time_kernels" (0/1: CUDA-event timing of the
+ * step kernel, reported by dem_get_stats), "maxneigh" (initial ELLPACK width), "morton" (0/1).  */
+int dem_set_option(dem_engine *e, const char *name, double value);
+
 /* ---- deck-level settings (same vocabulary as the input script) --------------------- */
 /* `units si|cgs|micro`                                   src/update.cpp:160-260        */
 int dem_set_units(dem_engine *e, const char *style);

@@ -1,0 +1,30 @@
+"""Builds libdem_b200.so (hand-written CUDA for sm_100a + C ABI) in-tree with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "dem_engine.cu")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("dem_engine.cu", "dem_kernels.cuh", "dem_contact.cuh", "dem_types.h")] + \
+       [os.path.join(os.path.dirname(HERE), "include", "dem_b200.h")]
+OUT = os.path.join(HERE, "libdem_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static"]
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libdem_b200.so")
+    if verbose:
+        print(r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))

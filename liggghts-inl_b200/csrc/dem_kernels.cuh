@@ -1,0 +1,496 @@
+// dem_kernels.cuh -- hand-written sm_100a kernels of the DEM timestep engine.
+//
+// Design (B200-first, not a port of the reference loops):
+//  * 32-byte particle records (x|r, v|m, omega|type+mask) so that one neighbour gather is
+//    exactly one DRAM sector; records are double-buffered so that the whole timestep
+//    (pair forces + walls + gravity + freeze + final_integrate(n) + initial_integrate(n+1) +
+//    rebuild trigger) is ONE kernel with no force array round trip through HBM.
+//  * FULL neighbour list in transposed ELLPACK layout, every pair evaluated by both owners
+//    in one canonical orientation (lower tag first) -> no atomics, bit-reproducible runs,
+//    and both copies of a pair's history stay bit-identical.
+//  * contact history is valid only when the NBR_HIST bit of the neighbour word is set
+//    (== the reference's contact_flag != 0), so untouched pairs cost no history traffic.
+// Reference behaviour followed: see dem_contact.cuh and the per-kernel notes below.
+#pragma once
+#include "dem_contact.cuh"
+
+namespace dem {
+
+__device__ __forceinline__ double sq3_rn(double a, double b, double c)
+{  // a*a+b*b+c*c exactly as the un-contracted CPU expression (predicates must be bit-exact)
+  return __dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c));
+}
+__device__ __forceinline__ int rec_type(double w) { return (int)(__double_as_longlong(w) & 0xff); }
+__device__ __forceinline__ int rec_mask(double w) { return (int)((__double_as_longlong(w) >> 8) & 0xffffffffLL); }
+__host__ __device__ __forceinline__ long long pack_bits(int type, int mask) { return ((long long)(unsigned)mask << 8) | (long long)(type & 0xff); }
+
+// sphere/wall contact with the wall's own model selection (uniform run-time switch)
+__device__ __noinline__ void wall_chain(const StepP &P, const ModelP &M, const Contact &c, double *h, bool su, ContactOut &o)
+{
+  const int key = M.normal * 4 + M.rolling;
+  switch (key) {
+    case N_HERTZ * 4 + R_OFF: contact_chain<N_HERTZ, R_OFF, true>(P, M, c, h, su, o); break;
+    case N_HERTZ * 4 + R_CDT: contact_chain<N_HERTZ, R_CDT, true>(P, M, c, h, su, o); break;
+    case N_HERTZ * 4 + R_EPSD: contact_chain<N_HERTZ, R_EPSD, true>(P, M, c, h, su, o); break;
+    case N_HERTZ * 4 + R_EPSD2: contact_chain<N_HERTZ, R_EPSD2, true>(P, M, c, h, su, o); break;
+    case N_HOOKE * 4 + R_OFF: contact_chain<N_HOOKE, R_OFF, true>(P, M, c, h, su, o); break;
+    case N_HOOKE * 4 + R_CDT: contact_chain<N_HOOKE, R_CDT, true>(P, M, c, h, su, o); break;
+    case N_HOOKE * 4 + R_EPSD: contact_chain<N_HOOKE, R_EPSD, true>(P, M, c, h, su, o); break;
+    default: contact_chain<N_HOOKE, R_EPSD2, true>(P, M, c, h, su, o); break;
+  }
+}
+
+// primitive walls of one particle: fix_wall_gran.cpp:988-1121, fix_wall_gran_base.h:159-367,
+// primitive_wall_definitions.h:128-203
+__device__ __forceinline__ void walls_of_particle(const StepP &P, int i, const double4 &xi, const double4 &vi,
+                                                  const double4 &wi, int itype, bool su, double *F, double *T)
+{
+  const double4 xh = P.xh[i];
+  const unsigned wbits = (unsigned)(__double_as_longlong(xh.w) & 0xffffffffLL);
+  const unsigned cand = wbits & 0xffffu;
+  unsigned valid = wbits >> 16;
+  const unsigned valid0 = valid;
+  const double pos[3] = {xi.x, xi.y, xi.z};
+  const double r = xi.w;
+  for (int w = 0; w < P.nwalls; w++) {
+    if (!((cand >> w) & 1u)) continue;
+    const WallP &W = P.walls[w];
+    double delta[3] = {0., 0., 0.}, deltan;
+    if (W.wtype < 3) {
+      const int d = W.wtype;
+      const double p = W.param[0];
+      delta[d] = p - pos[d];
+      deltan = pos[d] > p ? pos[d] - p - r : p - pos[d] - r;
+    } else {
+      const int dd = W.wtype - 3, iy = (dd + 1) % 3, iz = (dd + 2) % 3;
+      const double R = W.param[0];
+      const double dy = pos[iy] - W.param[1], dz = pos[iz] - W.param[2];
+      const double dist = sqrt(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dz, dz)));
+      if (dist == 0.0) deltan = 0.0;
+      else if (dist > R) { deltan = dist - R - r; const double fact = (dist - R) / dist; delta[iy] = -dy * fact; delta[iz] = -dz * fact; }
+      else { deltan = R - dist - r; const double fact = (R - dist) / dist; delta[iy] = dy * fact; delta[iz] = dz * fact; }
+    }
+    if (deltan > P.cutneighmax) continue;
+    const int wd = W.m.dnum;
+    if (deltan <= 0 || deltan < (P.cdf - 1.0) * r) {
+      if (deltan <= 0) {
+        Contact c;
+        c.dx = -delta[0]; c.dy = -delta[1]; c.dz = -delta[2];
+        c.radi = r; c.radj = 0.0; c.radsum = r; c.deltan_in = -deltan;
+        c.r = c.radi - c.deltan_in; c.rinv = 1.0 / c.r;
+        c.meff = vi.w; c.mi = vi.w; c.mj = 0.0;
+        c.vi[0] = vi.x; c.vi[1] = vi.y; c.vi[2] = vi.z;
+        c.wi[0] = wi.x; c.wi[1] = wi.y; c.wi[2] = wi.z;
+        c.vj[0] = c.vj[1] = c.vj[2] = 0.0; c.wj[0] = c.wj[1] = c.wj[2] = 0.0;
+        if (W.shear) {
+          if (W.shearAxis >= 0) {
+            const int dd = W.wtype - 3;
+            double rd[3] = {0., 0., 0.};
+            rd[(dd + 1) % 3] = pos[(dd + 1) % 3] - W.param[1];
+            rd[(dd + 2) % 3] = pos[(dd + 2) % 3] - W.param[2];
+            c.vj[0] = W.axisVec[1] * rd[2] - W.axisVec[2] * rd[1];
+            c.vj[1] = W.axisVec[2] * rd[0] - W.axisVec[0] * rd[2];
+            c.vj[2] = W.axisVec[0] * rd[1] - W.axisVec[1] * rd[0];
+          } else c.vj[W.shearDim] = W.vshear;
+        }
+        c.itype = itype; c.jtype = W.atom_type;
+        double h[6] = {0., 0., 0., 0., 0., 0.};
+        if ((valid >> w) & 1u)
+          for (int d = 0; d < wd; d++) h[d] = P.whist[(size_t)(W.hist_row + d) * P.cap + i];
+        ContactOut o;
+        wall_chain(P, W.m, c, h, su, o);
+        F[0] += o.F[0]; F[1] += o.F[1]; F[2] += o.F[2];
+        T[0] += o.Ti[0]; T[1] += o.Ti[1]; T[2] += o.Ti[2];
+        if (su && wd) {
+          for (int d = 0; d < wd; d++) P.whist[(size_t)(W.hist_row + d) * P.cap + i] = h[d];
+          valid |= (1u << w);
+        }
+      } else valid &= ~(1u << w);  // surfacesClose: history zeroed (tangential_model_history.h:428-440)
+    } else valid &= ~(1u << w);  // candidate but apart: history zeroed (fix_wall_gran.cpp:1117-1119)
+  }
+  if (valid != valid0) {
+    const long long nb = (long long)(cand | (valid << 16));
+    P.xh[i].w = __longlong_as_double(nb);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// THE hot kernel: one launch == one timestep of the owned particles of this GPU.
+//   verlet.cpp:264-391 (order of operations), pair_gran_base.h:257-496 (pair loop),
+//   fix_gravity.cpp:331-339, fix_freeze.cpp:132-144, fix_nve_sphere.cpp:134-244,
+//   neighbor.cpp:1425-1466 (rebuild trigger)
+template <int NORMAL, int ROLLING>
+__global__ void __launch_bounds__(128) k_step(const StepP P)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool trig = false;
+  unsigned ncont = 0;
+  if (i < P.nlocal) {
+    const double4 xi = P.xr[i], vi = P.vm[i], wi = P.wt[i];
+    const int itype = rec_type(wi.w), imask = rec_mask(wi.w);
+    const bool su = (P.mode != MODE_SETUP);
+    double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
+    if (P.have_pair) {
+      const int nn = P.numneigh[i];
+      const int dnum = P.pm.dnum;
+      for (int k = 0; k < nn; k++) {
+        const unsigned w = P.nbr[(size_t)k * P.lcap + i];
+        const int j = (int)(w & NBR_IDX);
+        const double4 xj = P.xr[j];
+        const bool jfirst = (w & NBR_JFIRST) != 0;
+        // first - second, exact negation keeps both copies of a pair identical
+        const double dx = jfirst ? xj.x - xi.x : xi.x - xj.x;
+        const double dy = jfirst ? xj.y - xi.y : xi.y - xj.y;
+        const double dz = jfirst ? xj.z - xi.z : xi.z - xj.z;
+        const double rsq = sq3_rn(dx, dy, dz);
+        const double radsum = xi.w + xj.w;
+        const double rs2 = __dmul_rn(radsum, radsum);
+        if (rsq < rs2) {
+          const double4 vj = P.vm[j], wj = P.wt[j];
+          const int jtype = rec_type(wj.w), jmask = rec_mask(wj.w);
+          Contact c;
+          c.dx = dx; c.dy = dy; c.dz = dz;
+          c.r = sqrt(rsq); c.rinv = 1.0 / c.r; c.radsum = radsum; c.deltan_in = 0.0;
+          const double4 &xa = jfirst ? xj : xi, &xb = jfirst ? xi : xj;
+          const double4 &va = jfirst ? vj : vi, &vb = jfirst ? vi : vj;
+          const double4 &wa = jfirst ? wj : wi, &wb = jfirst ? wi : wj;
+          c.radi = xa.w; c.radj = xb.w; c.mi = va.w; c.mj = vb.w;
+          c.vi[0] = va.x; c.vi[1] = va.y; c.vi[2] = va.z; c.vj[0] = vb.x; c.vj[1] = vb.y; c.vj[2] = vb.z;
+          c.wi[0] = wa.x; c.wi[1] = wa.y; c.wi[2] = wa.z; c.wj[0] = wb.x; c.wj[1] = wb.y; c.wj[2] = wb.z;
+          c.itype = jfirst ? jtype : itype; c.jtype = jfirst ? itype : jtype;
+          double meff = c.mi * c.mj / (c.mi + c.mj);
+          if ((jfirst ? jmask : imask) & P.freezebit) meff = c.mj;  // pair_gran_base.h:389-393
+          if ((jfirst ? imask : jmask) & P.freezebit) meff = c.mi;
+          c.meff = meff;
+          double h[6] = {0., 0., 0., 0., 0., 0.};
+          const bool had = (w & NBR_HIST) != 0;
+          if (had)
+            for (int d = 0; d < dnum; d++) h[d] = P.hist[(size_t)(k * dnum + d) * P.lcap + i];
+          ContactOut o;
+          contact_chain<NORMAL, ROLLING, false>(P, P.pm, c, h, su, o);
+          if (jfirst) {
+            F[0] -= o.F[0]; F[1] -= o.F[1]; F[2] -= o.F[2];
+            T[0] += o.Tj[0]; T[1] += o.Tj[1]; T[2] += o.Tj[2];
+          } else {
+            F[0] += o.F[0]; F[1] += o.F[1]; F[2] += o.F[2];
+            T[0] += o.Ti[0]; T[1] += o.Ti[1]; T[2] += o.Ti[2];
+          }
+          if (dnum && (su || !had))
+            for (int d = 0; d < dnum; d++) P.hist[(size_t)(k * dnum + d) * P.lcap + i] = h[d];
+          if (!had) P.nbr[(size_t)k * P.lcap + i] = w | NBR_HIST;
+          ncont++;
+        } else if (P.cdf > 1.0 && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) {
+          // surfacesClose: tangential/rolling history zeroed, flag stays (normal bit), pair_gran_base.h:420-423
+          for (int d = 0; d < dnum; d++) P.hist[(size_t)(k * dnum + d) * P.lcap + i] = 0.0;
+        }
+      }
+    }
+    if (P.have_g && (imask & 1)) { F[0] += vi.w * P.g[0]; F[1] += vi.w * P.g[1]; F[2] += vi.w * P.g[2]; }
+    if (P.nwalls) walls_of_particle(P, i, xi, vi, wi, itype, su, F, T);
+    if (imask & P.freezebit) { F[0] = F[1] = F[2] = 0.0; T[0] = T[1] = T[2] = 0.0; }
+
+    if (P.mode != MODE_STEP) {  // forces are only materialised when somebody will read them
+      P.f[i] = F[0]; P.f[P.cap + i] = F[1]; P.f[2 * (size_t)P.cap + i] = F[2];
+      P.tq[i] = T[0]; P.tq[P.cap + i] = T[1]; P.tq[2 * (size_t)P.cap + i] = T[2];
+    }
+    if (P.mode != MODE_SETUP) {
+      double4 xo = xi, vo = vi, wo = wi;
+      if (imask & P.integbit) {
+        const double dtfm = P.dtf / vi.w;
+        const double dtir = P.dtfrot / (xi.w * xi.w * vi.w);
+        // final_integrate of this step
+        vo.x += dtfm * F[0]; vo.y += dtfm * F[1]; vo.z += dtfm * F[2];
+        wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
+        if (P.mode == MODE_STEP) {  // initial_integrate of the next step
+          vo.x += dtfm * F[0]; vo.y += dtfm * F[1]; vo.z += dtfm * F[2];
+          xo.x += P.dtv * vo.x; xo.y += P.dtv * vo.y; xo.z += P.dtv * vo.z;
+          wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
+        }
+      }
+      P.xr_o[i] = xo; P.vm_o[i] = vo; P.wt_o[i] = wo;
+      if (P.mode == MODE_STEP) {
+        const double4 xh = P.xh[i];
+        trig = sq3_rn(xo.x - xh.x, xo.y - xh.y, xo.z - xh.z) > P.trigsq;
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
+  if (P.ncontact) {
+    for (int o = 16; o; o >>= 1) ncont += __shfl_down_sync(0xffffffffu, ncont, o);
+    if ((threadIdx.x & 31) == 0 && ncont) atomicAdd(P.ncontact, (unsigned long long)ncont);
+  }
+}
+
+// first half step of a run from the stored force arrays: fix_nve_sphere.cpp:134-183
+__global__ void __launch_bounds__(256) k_initial_integrate(const StepP P)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool trig = false;
+  if (i < P.nlocal) {
+    const double4 xi = P.xr[i], vi = P.vm[i], wi = P.wt[i];
+    double4 xo = xi, vo = vi, wo = wi;
+    if (rec_mask(wi.w) & P.integbit) {
+      const double dtfm = P.dtf / vi.w;
+      const double dtir = P.dtfrot / (xi.w * xi.w * vi.w);
+      vo.x += dtfm * P.f[i]; vo.y += dtfm * P.f[P.cap + i]; vo.z += dtfm * P.f[2 * (size_t)P.cap + i];
+      xo.x += P.dtv * vo.x; xo.y += P.dtv * vo.y; xo.z += P.dtv * vo.z;
+      wo.x += dtir * P.tq[i]; wo.y += dtir * P.tq[P.cap + i]; wo.z += dtir * P.tq[2 * (size_t)P.cap + i];
+    }
+    P.xr_o[i] = xo; P.vm_o[i] = vo; P.wt_o[i] = wo;
+    const double4 xh = P.xh[i];
+    trig = sq3_rn(xo.x - xh.x, xo.y - xh.y, xo.z - xh.z) > P.trigsq;
+  }
+  if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
+}
+
+// ghost refresh (== forward_comm of x,v,omega: comm_brick.cpp:563-645, atom_vec_sphere.cpp:283-293)
+struct GhostP {
+  int nghost, nlocal;
+  const int *src;      // owned source index
+  const int *shift;    // 3 small ints per ghost (periodic image offsets)
+  double prd[3];
+  double4 *xr, *vm, *wt;
+  int with_static;  // also copy radius/mass/type (at rebuild)
+};
+__global__ void __launch_bounds__(256) k_ghost_update(const GhostP G, int g0, int g1)
+{
+  const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= g1) return;
+  const int s = G.src[g];
+  double4 x = G.xr[s];
+  const int sx = G.shift[3 * g], sy = G.shift[3 * g + 1], sz = G.shift[3 * g + 2];
+  if (sx) x.x += sx * G.prd[0];
+  if (sy) x.y += sy * G.prd[1];
+  if (sz) x.z += sz * G.prd[2];
+  G.xr[G.nlocal + g] = x;
+  G.vm[G.nlocal + g] = G.vm[s];
+  G.wt[G.nlocal + g] = G.wt[s];
+}
+
+// ------------------------------------------------------------------ rebuild kernels
+struct GridP {
+  double org[3], inv[3];
+  int nc[3];
+  int morton;
+};
+__device__ __forceinline__ unsigned spread10(unsigned v)
+{
+  v &= 0x3ff; v = (v | (v << 16)) & 0x030000FF; v = (v | (v << 8)) & 0x0300F00F;
+  v = (v | (v << 4)) & 0x030C30C3; v = (v | (v << 2)) & 0x09249249; return v;
+}
+__device__ __forceinline__ void cell_of(const GridP &G, const double4 &x, int &cx, int &cy, int &cz)
+{
+  cx = (int)floor((x.x - G.org[0]) * G.inv[0]); cy = (int)floor((x.y - G.org[1]) * G.inv[1]); cz = (int)floor((x.z - G.org[2]) * G.inv[2]);
+  cx = min(max(cx, 0), G.nc[0] - 1); cy = min(max(cy, 0), G.nc[1] - 1); cz = min(max(cz, 0), G.nc[2] - 1);
+}
+__device__ __forceinline__ int lin_cell(const GridP &G, int cx, int cy, int cz) { return (cz * G.nc[1] + cy) * G.nc[0] + cx; }
+__device__ __forceinline__ unsigned key_of(const GridP &G, int cx, int cy, int cz)
+{
+  return G.morton ? (spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2)) : (unsigned)lin_cell(G, cx, cy, cz);
+}
+
+// Domain::pbc (domain.cpp:550-640) + sort key of the owned particles
+struct BoxP { double lo[3], hi[3], prd[3]; int periodic[3]; };
+__global__ void __launch_bounds__(256) k_wrap_key(int n, double4 *xr, const GridP G, const BoxP B, unsigned *keys, int *vals)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 x = xr[i];
+  {
+    double c[3] = {x.x, x.y, x.z};
+    bool ch = false;
+    for (int d = 0; d < 3; d++) if (B.periodic[d]) {
+      if (c[d] < B.lo[d]) { c[d] += B.prd[d]; ch = true; }
+      if (c[d] >= B.hi[d]) { c[d] -= B.prd[d]; c[d] = fmax(c[d], B.lo[d]); ch = true; }
+    }
+    if (ch) { x.x = c[0]; x.y = c[1]; x.z = c[2]; xr[i] = x; }
+  }
+  int cx, cy, cz; cell_of(G, x, cx, cy, cz);
+  keys[i] = key_of(G, cx, cy, cz); vals[i] = i;
+}
+
+__global__ void __launch_bounds__(256) k_gather4(int n, const int *perm, const double4 *a, double4 *ao, const double4 *b, double4 *bo,
+                                                 const double4 *c, double4 *co)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = perm[i];
+  ao[i] = a[p]; bo[i] = b[p]; co[i] = c[p];
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_rows(int n, int nrows, size_t stride_in, size_t stride_out, const int *perm, const T *a, T *ao)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = perm[i];
+  for (int r = 0; r < nrows; r++) ao[r * stride_out + i] = a[r * stride_in + p];
+}
+
+// cell ranges of a cell-sorted index range [base, base+n)
+__global__ void __launch_bounds__(256) k_cell_ranges(int n, int base, const double4 *xr, const GridP G, int *cstart, int *cend)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int cx, cy, cz;
+  cell_of(G, xr[base + p], cx, cy, cz);
+  const int c = lin_cell(G, cx, cy, cz);
+  int cp = -1, cn = -1;
+  if (p > 0) { cell_of(G, xr[base + p - 1], cx, cy, cz); cp = lin_cell(G, cx, cy, cz); }
+  if (p < n - 1) { cell_of(G, xr[base + p + 1], cx, cy, cz); cn = lin_cell(G, cx, cy, cz); }
+  if (c != cp) cstart[c] = base + p;
+  if (c != cn) cend[c] = base + p + 1;
+}
+
+// border candidates of one dimension: comm_brick.cpp:884-1117 (slab test; ghosts of earlier dims included)
+__global__ void __launch_bounds__(256) k_border_flag(int n, const double4 *xr, int dim, double lo_cut, double hi_cut, int *flo, int *fhi)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double4 x = xr[p];
+  const double c = dim == 0 ? x.x : dim == 1 ? x.y : x.z;
+  flo[p] = c < lo_cut;    // image at +prd
+  fhi[p] = c >= hi_cut;   // image at -prd
+}
+__global__ void __launch_bounds__(256) k_border_scatter(int n, int nlocal, int dim, const int *flo, const int *slo, const int *fhi, const int *shi,
+                                                        int nlo_total, int gbase, int *gsrc, int *gshift)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  for (int side = 0; side < 2; side++) {
+    const int fl = side ? fhi[p] : flo[p];
+    if (!fl) continue;
+    const int g = gbase + (side ? nlo_total + shi[p] : slo[p]);
+    int s = p, sh[3] = {0, 0, 0};
+    if (p >= nlocal) { const int gp = p - nlocal; s = gsrc[gp]; sh[0] = gshift[3 * gp]; sh[1] = gshift[3 * gp + 1]; sh[2] = gshift[3 * gp + 2]; }
+    sh[dim] += side ? -1 : 1;
+    gsrc[g] = s; gshift[3 * g] = sh[0]; gshift[3 * g + 1] = sh[1]; gshift[3 * g + 2] = sh[2];
+  }
+}
+__global__ void __launch_bounds__(256) k_ghost_keys(int n, int nlocal, const double4 *xr, const GridP G, unsigned *keys, int *vals)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  int cx, cy, cz; cell_of(G, xr[nlocal + g], cx, cy, cz);
+  keys[g] = key_of(G, cx, cy, cz); vals[g] = g;
+}
+__global__ void __launch_bounds__(256) k_ghost_permute(int n, const int *perm, const int *src, const int *shift, int *src_o, int *shift_o,
+                                                       const int *tag, int *gtag, int nlocal)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int p = perm[g];
+  src_o[g] = src[p]; shift_o[3 * g] = shift[3 * p]; shift_o[3 * g + 1] = shift[3 * p + 1]; shift_o[3 * g + 2] = shift[3 * p + 2];
+  gtag[nlocal + g] = tag[src[p]];
+}
+
+// Verlet-skin FULL list + history remap: neigh_gran.cpp:560-625 (predicates), fix_contact_history.cpp:351
+struct BuildP {
+  int nlocal, cap, maxk, dnum;
+  const double4 *xr;
+  const int *tag;
+  GridP G;
+  const int *ocs, *oce, *gcs, *gce;  // owned / ghost cell ranges
+  double cdf, skin;
+  unsigned *nbr; int *numneigh; int *ptag; double *hist;
+  // previous list (rows addressed through perm: new i <- old perm[i])
+  int have_old, cap_old, dnum_old;
+  const int *perm; const unsigned *nbr_old; const int *numneigh_old; const int *ptag_old; const double *hist_old;
+  int *overflow;
+};
+__global__ void __launch_bounds__(128) k_build_list(const BuildP B)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.nlocal) return;
+  const double4 xi = B.xr[i];
+  const int tagi = B.tag[i];
+  int cx, cy, cz; cell_of(B.G, xi, cx, cy, cz);
+  const int oi = B.have_old ? B.perm[i] : 0;
+  const int nold = B.have_old ? B.numneigh_old[oi] : 0;
+  int n = 0;
+  for (int dz = -1; dz <= 1; dz++) {
+    const int z = cz + dz; if (z < 0 || z >= B.G.nc[2]) continue;
+    for (int dy = -1; dy <= 1; dy++) {
+      const int y = cy + dy; if (y < 0 || y >= B.G.nc[1]) continue;
+      for (int dx = -1; dx <= 1; dx++) {
+        const int x = cx + dx; if (x < 0 || x >= B.G.nc[0]) continue;
+        const int c = lin_cell(B.G, x, y, z);
+        for (int pass = 0; pass < 2; pass++) {
+          const int s = pass ? B.gcs[c] : B.ocs[c], e = pass ? B.gce[c] : B.oce[c];
+          for (int j = s; j < e; j++) {
+            if (j == i) continue;
+            const double4 xj = B.xr[j];
+            const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+            const double radsum = __dmul_rn(xi.w + xj.w, B.cdf);
+            const double rc = radsum + B.skin;
+            if (rsq <= __dmul_rn(rc, rc)) {
+              if (n < B.maxk) {
+                const int tagj = B.tag[j];
+                unsigned w = (unsigned)j | (tagj < tagi ? NBR_JFIRST : 0u);
+                if (nold && rsq < __dmul_rn(radsum, radsum)) {
+                  for (int m = 0; m < nold; m++) {
+                    if (B.ptag_old[(size_t)m * B.cap_old + oi] == tagj && (B.nbr_old[(size_t)m * B.cap_old + oi] & NBR_HIST)) {
+                      w |= NBR_HIST;
+                      for (int d = 0; d < B.dnum; d++)
+                        B.hist[(size_t)(n * B.dnum + d) * B.cap + i] = B.hist_old[(size_t)(m * B.dnum + d) * B.cap_old + oi];
+                      break;
+                    }
+                  }
+                }
+                B.nbr[(size_t)n * B.cap + i] = w;
+                B.ptag[(size_t)n * B.cap + i] = tagj;
+              }
+              n++;
+            }
+          }
+        }
+      }
+    }
+  }
+  B.numneigh[i] = min(n, B.maxk);
+  if (n > B.maxk) atomicMax(B.overflow, n);
+}
+
+// positions at build time (neighbor.cpp:1486-1510) + primitive-wall candidate bits (primitive_wall.h:129-138)
+__global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 *xh, const unsigned *valid_in, const WallP *walls, int nwalls, double skin)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 x = xr[i];
+  unsigned cand = 0;
+  const double pos[3] = {x.x, x.y, x.z};
+  for (int w = 0; w < nwalls; w++) {
+    const WallP &W = walls[w];
+    bool in;
+    const double dMax = x.w + skin;
+    if (W.wtype < 3) {
+      const double dist = pos[W.wtype] - W.param[0];
+      in = ((dist > 0.0) ? dist : -dist) <= dMax;
+    } else {
+      const int dd = W.wtype - 3;
+      const double dy = pos[(dd + 1) % 3] - W.param[1], dz = pos[(dd + 2) % 3] - W.param[2];
+      const double dist = sqrt(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dz, dz))) - W.param[0];
+      in = (dMax < dist || -dMax < dist);
+    }
+    if (in) cand |= 1u << w;
+  }
+  const unsigned valid = valid_in ? valid_in[i] : 0u;
+  double4 o; o.x = x.x; o.y = x.y; o.z = x.z; o.w = __longlong_as_double((long long)(cand | (valid << 16)));
+  xh[i] = o;
+}
+__global__ void __launch_bounds__(256) k_extract_valid(int n, const int *perm, const double4 *xh, unsigned *valid)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  valid[i] = ((unsigned)(__double_as_longlong(xh[perm ? perm[i] : i].w) & 0xffffffffLL)) >> 16;
+}
+
+__global__ void __launch_bounds__(256) k_count_pairs(int n, const int *numneigh, const unsigned *nbr, int cap, unsigned long long *out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long a = 0, b = 0;
+  if (i < n) { const int nn = numneigh[i]; a = nn; for (int k = 0; k < nn; k++) b += (nbr[(size_t)k * cap + i] & NBR_HIST) ? 1 : 0; }
+  for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(out, a); if (b) atomicAdd(out + 1, b); }
+}
+
+}  // namespace dem

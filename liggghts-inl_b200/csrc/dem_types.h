@@ -1,0 +1,64 @@
+// dem_types.h -- plain structs shared by host orchestration and device kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dem {
+
+enum { N_OFF = 0, N_HERTZ = 1, N_HOOKE = 2 };
+enum { R_OFF = 0, R_CDT = 1, R_EPSD = 2, R_EPSD2 = 3 };
+// per-type-pair tables, each (ntypes+1)^2 doubles, concatenated in this order
+enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_COUNT };
+
+#define DEM_MAXW 16  // primitive walls per engine (candidate + valid bits share one 32-bit word)
+
+// neighbour word: [31] partner is the "first" body of the pair (partner tag < own tag)
+//                 [30] pair holds contact history (== reference contact_flag != 0)
+//                 [29:0] partner index (owned or ghost), cf. NEIGHMASK lmptype.h:86
+#define NBR_JFIRST 0x80000000u
+#define NBR_HIST 0x40000000u
+#define NBR_IDX 0x3FFFFFFFu
+
+struct ModelP {
+  int normal, tangential, rolling;
+  int tdamp, limitForce, torsion, ktToKn;
+  int dnum, off_shear, off_roll;
+};
+
+struct WallP {
+  ModelP m;
+  int wtype;  // 0..2 plane x,y,z ; 3..5 cylinder x,y,z
+  int atom_type;
+  int shear, shearDim, shearAxis;
+  int hist_row;  // first row of this wall in the whist array
+  double param[3];
+  double vshear, axisVec[3];
+};
+
+enum { MODE_SETUP = 0, MODE_STEP = 1, MODE_LAST = 2 };
+
+struct StepP {
+  int nlocal, nall, cap, maxk;
+  int lcap;  // row stride of the ELLPACK arrays (nbr, hist)
+  // particle records, 32 B each: (x,y,z,radius) (vx,vy,vz,mass) (wx,wy,wz,bits(type|mask<<8))
+  const double4 *xr, *vm, *wt;
+  double4 *xr_o, *vm_o, *wt_o;
+  double4 *xh;  // (xhold, bits(wall candidate | wall-history-valid << 16))
+  unsigned *nbr;
+  const int *numneigh;
+  double *hist;   // [maxk*dnum][cap]
+  double *whist;  // [sum wall dnum][cap]
+  double *f, *tq; // [3][cap]
+  const WallP *walls;
+  int nwalls;
+  ModelP pm;
+  const double *tab;
+  int nt1;  // ntypes+1
+  double dt, dtv, dtf, dtfrot, nktv2p, charVel, cdf, cdfsq, trigsq, cutneighmax;
+  double g[3];
+  int have_g, have_pair, freezebit, integbit;
+  int mode;
+  int *flag;  // rebuild trigger (mapped host memory)
+  unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
+};
+
+}  // namespace dem

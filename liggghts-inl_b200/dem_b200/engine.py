@@ -7,7 +7,7 @@ _ROOT = os.path.dirname(_HERE)
 
 # every symbol declared in include/dem_b200.h
 ABI_SYMBOLS = [
-    "dem_create", "dem_destroy", "dem_last_error", "dem_version", "dem_set_units", "dem_set_box",
+    "dem_create", "dem_destroy", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
     "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_property",
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
@@ -82,6 +82,10 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def option(self, name, value):
+        if self._p == "dem_":
+            self._call("set_option", [C.c_char_p, C.c_double], name.encode(), float(value))
 
     # -- deck vocabulary ----------------------------------------------------------------
     def units(self, style):
