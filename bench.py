@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the DEM hot path on BASELINE.json configs[1]:
+4 194 304 polydisperse spheres, Hertz/history + rolling friction (cdt), settled bed on a floor,
+periodic in x,y (a 16 384-sphere tile settled by the reference, bench_data/, replicated 16x16).
+
+  python bench.py --gpus 1 --steps K --warmup W            -> own arm (CUDA engine through the C ABI)
+  python bench.py --impl reference --gpus 1 --steps K ...  -> reference arm: the UNMODIFIED reference
+         (oracle/_ref) on all host cores, one independent replica of the tile per core (the image
+         has no MPI; SURVEY.md 8d "P-replica proxy")
+One JSON line on stdout (rank 0)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "liggghts-inl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "particle-steps/s (Hertz/history, 4M spheres)"
+MODEL = "model hertz tangential history rolling_friction cdt"
+PROPS = [("youngsModulus", "peratomtype", [5e6]), ("poissonsRatio", "peratomtype", [0.45]),
+         ("coefficientRestitution", "peratomtypepair", [0.3]), ("coefficientFriction", "peratomtypepair", [0.5]),
+         ("coefficientRollingFriction", "peratomtypepair", [0.1])]
+
+
+def load_tile():
+    t = np.load(os.path.join(ROOT, "bench_data", "tile16k.npz"))
+    return {k: t[k] for k in t.files}
+
+
+def bed_case(tiles_x, tiles_y, name="bed"):
+    """the settled tile replicated tiles_x x tiles_y (the reference's `replicate` idea)"""
+    t = load_tile()
+    n0 = len(t["radius"])
+    Lx, Ly = t["hi"][0] - t["lo"][0], t["hi"][1] - t["lo"][1]
+    nt = tiles_x * tiles_y
+    x = np.empty((nt * n0, 3)); k = 0
+    for ix in range(tiles_x):
+        for iy in range(tiles_y):
+            x[k * n0:(k + 1) * n0] = t["x"] + np.array([ix * Lx, iy * Ly, 0.0]); k += 1
+    rep = lambda a: np.tile(a, (nt,) + (1,) * (a.ndim - 1))
+    n = nt * n0
+    return dict(name=name, lo=[t["lo"][0], t["lo"][1], t["lo"][2]], hi=[t["lo"][0] + tiles_x * Lx, t["lo"][1] + tiles_y * Ly, t["hi"][2]],
+                periodic=[1, 1, 0], ntypes=1, skin=0.001, dt=1e-5, props=PROPS, pair=MODEL,
+                walls=[("floor", MODEL + " primitive type 1 zplane 0.0")], gravity=(9.81, [0.0, 0.0, -1.0]), freeze=0,
+                tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32), mask=np.ones(n, np.int32), x=x,
+                v=rep(t["v"]), omega=rep(t["omega"]), radius=rep(t["radius"]), density=rep(t["density"]))
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate(); self.p.wait()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [s.strip() for s in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+def ref_worker(tiles, steps, out):
+    """one reference process: `tiles x tiles` tile bed, `run steps`; prints loop seconds"""
+    import cases
+    import ref_driver
+    c = bed_case(tiles, tiles, name="cpu")
+    tmp = tempfile.mkdtemp()
+    deck, data = cases.to_deck(c, os.path.join(tmp, "bed.data"))
+    open(os.path.join(tmp, "bed.data"), "w").write(data)
+    r = ref_driver.Ref()
+    r.cmd(deck)
+    r.cmd("run 0")
+    t0 = time.perf_counter()
+    r.cmd("run %d" % steps)
+    dt = time.perf_counter() - t0
+    json.dump({"seconds": dt, "n": len(c["tag"]), "steps": steps}, open(out, "w"))
+
+
+def run_reference_procs(nproc, tiles, steps):
+    outs, procs = [], []
+    for k in range(nproc):
+        out = tempfile.mktemp(suffix=".json")
+        outs.append(out)
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", str(tiles), str(steps), out],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for p in procs:
+        p.wait()
+    res = [json.load(open(o)) for o in outs if os.path.exists(o)]
+    for o in outs:
+        if os.path.exists(o):
+            os.unlink(o)
+    if not res:
+        return None
+    total = sum(r["n"] * r["steps"] for r in res)
+    return total / max(r["seconds"] for r in res), len(res), res[0]["n"]
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ref_driver
+    cfg = {"workload": "4,194,304-sphere settled polydisperse bed (16x16 replicas of bench_data/tile16k), hertz/history/cdt, floor + periodic xy",
+           "inputs": "reference arm runs one 16,384-sphere tile of the same bed per host core"}
+    if not ref_driver.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libliggghts_ref.so missing (build: make -C oracle ref)"}))
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: each step of this arm = `sample_steps` reference steps of one tile per core
+    sample_steps = 150
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v = run_reference_procs(cores, 1, sample_steps)
+        if v is None:
+            print(json.dumps({"impl": "reference", "unavailable": "reference worker failed"})); return
+        if it >= args.warmup:
+            vals.append(v[0])
+    value = float(np.mean(vals))
+    n_tile = 16384
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores * n_tile * sample_steps / value,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": cfg,
+                      "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "reference",
+                                       "sample": "%d independent serial reference processes (no MPI in the image), each one 16,384-sphere tile x %d steps" % (cores, sample_steps)},
+                      "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------------------------
+def own_arm(args):
+    import torch
+    import dem_b200
+    import cases
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU brick decomposition is not enabled in this build yet")
+    torch.cuda.set_device(local)
+    tiles = args.tiles
+    c = bed_case(tiles, tiles)
+    n = len(c["tag"])
+    eng = cases.apply(c, dem_b200.Engine(device=local))
+    eng.option("time_kernels", 1)
+    eng.setup()
+    eng.run(max(args.warmup, 3))
+    st0 = eng.stats()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run(args.steps)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    st = eng.stats()
+    value = n * args.steps / (ms * 1e-3)
+    # roofline of the dominant (fused step) kernel
+    K_half = st.npairs_full / 2.0 / n
+    C_half = st.ncontacts_full / 2.0 / n
+    dnum = st.dnum
+    bytes_per_ps = 192.0 + 4.0 * K_half + (16.0 * dnum + 8.0) * C_half
+    kms = st.step_kernel_ms / max(st.step_kernel_calls, 1)
+    peak, peak_src = peaks()
+    achieved = bytes_per_ps * n / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("k_step_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_step<hertz,cdt> (fused pair+wall+gravity+integrate step)", "kernel_ms": kms, "peak_source": peak_src,
+                "bytes_per_particle_step": bytes_per_ps, "halflist_per_particle": K_half, "contacts_per_particle": C_half,
+                "kernel_share_of_step": kms * st.step_kernel_calls / ms if ms > 0 else None}
+    launches = st.kernel_launches - st0.kernel_launches
+    nbuilds = st.nbuilds
+
+    # end-to-end through the public API with host buffers: upload -> setup -> run(K) -> download
+    ke = max(args.steps // 4, 10)
+    eng.close()
+    t0 = time.perf_counter()
+    eng2 = cases.apply(c, dem_b200.Engine(device=local))
+    eng2.setup()
+    eng2.run(ke)
+    xo = eng2.download("x"); vo = eng2.download("v")
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    h2d = n * (3 * 32 + 4 + 8)
+    d2h = xo.nbytes + vo.nbytes + 2 * n * 4
+    e2e = {"value": n * ke / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / ke, "d2h_bytes_per_step": d2h / ke,
+           "job": "create + upload(host arrays) + setup + run(%d) + download x,v; %.3f s" % (ke, t_e2e)}
+    eng2.close()
+
+    # CPU baseline: the unmodified reference, 1 core, one tile of the same bed
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        import ref_driver
+        if ref_driver.available():
+            steps_cpu = 1500
+            r = run_reference_procs(1, 1, steps_cpu)
+            if r:
+                cpu = {"value": r[0], "unit": "particle-steps/s", "cores": 1, "kind": "reference",
+                       "sample": "one 16,384-sphere tile of the bed x %d steps, serial reference build (oracle/_ref)" % steps_cpu}
+    out = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": "%d-sphere settled polydisperse bed (%dx%d replicas of bench_data/tile16k, radii U[1.5,3] mm), "
+                                  "hertz/history/cdt, floor + periodic xy, dt 1e-5, skin 1 mm" % (n, tiles, tiles),
+                      "particles": n, "l2_policy": "inputs (%.1f GB of state + lists) exceed the 126 MB L2" % (n * 600 / 1e9),
+                      "rebuilds_in_timed_region": int(nbuilds), "parallelism": "1 GPU"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--ref-worker":
+        ref_worker(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]); return
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="own")
+    ap.add_argument("--tiles", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        own_arm(args)
+
+
+if __name__ == "__main__":
+    main()
