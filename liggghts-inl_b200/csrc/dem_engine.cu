@@ -42,7 +42,7 @@ struct ListSet {  // one ELLPACK neighbour list + history (two sets ping-pong ac
   DevBuf<unsigned> nbr;
   DevBuf<int> ptag, numneigh;
   DevBuf<double> hist;
-  int cap = 0, maxk = 0, dnum = 0, valid = 0;
+  int cap = 0, maxk = 0, dnum = 0, hslots = 0, valid = 0;
 };
 
 struct WallHost { std::string id; WallP p; };
@@ -147,8 +147,8 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
     e->device = device; e->rank = rank; e->nranks = nranks; e->stream = (cudaStream_t)stream;
     if (nranks != 1) dem_fail(e, DEM_ERR_UNSUPPORTED, "multi-rank bricks are not enabled in this build yet");
     (void)nccl_id;
-    CK(cudaHostAlloc((void **)&e->hflag, sizeof(int), cudaHostAllocMapped));
-    *e->hflag = 0;
+    CK(cudaHostAlloc((void **)&e->hflag, 4 * sizeof(int), cudaHostAllocMapped));
+    e->hflag[0] = e->hflag[1] = 0;
     e->pm.tdamp = 1;
   } catch (const DemFail &f) { return f.code; }
   return DEM_OK;
@@ -241,7 +241,10 @@ extern "C" int dem_set_property(dem_engine *e, const char *name, const char *kin
     double(*dst)[MAXT + 1] = nm == "coefficientRestitution" ? e->cor : nm == "coefficientFriction" ? e->mu
                             : nm == "coefficientRollingFriction" ? e->rmu : nm == "coefficientRollingViscousDamping" ? e->rvisc : nullptr;
     if (!dst) dem_fail(e, DEM_ERR_UNSUPPORTED, "peratomtypepair property %s not on the hot path", name);
-    for (int i = 0; i < T; i++) for (int j = 0; j < T; j++) dst[i + 1][j + 1] = v[i * T + j];
+    for (int i = 0; i < T; i++) for (int j = 0; j < T; j++) {
+      if (v[i * T + j] != v[j * T + i]) dem_fail(e, DEM_ERR_ARG, "%s: per-atomtype property matrix must be symmetric", name);
+      dst[i + 1][j + 1] = v[i * T + j];
+    }
   } else dem_fail(e, DEM_ERR_ARG, "unknown property kind %s", kind);
   e->have_prop[nm] = 1;
   API_END
@@ -464,6 +467,7 @@ static void derive_tables(dem_engine *E)
       at(T_BETA) = at(T_CORLOG) / sqrt(pow(at(T_CORLOG), 2.) + pow(3.14159265358979323846, 2.));
     }
     at(T_MU) = E->mu[i][j]; at(T_RMU) = E->rmu[i][j]; at(T_RVISC) = E->rvisc[i][j];
+    if (hertz || hooke) { at(T_SQ2Y) = sqrt(2. * at(T_YEFF)); at(T_SQ8G) = sqrt(8. * at(T_GEFF)); at(T_INV8G) = 1. / (8. * at(T_GEFF)); }
   }
   E->tab.ensure(E, t.size());
   CK(cudaMemcpyAsync(E->tab.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
@@ -526,13 +530,13 @@ static void ghost_update(dem_engine *E, int g0, int g1)
   E->launches++;
 }
 
-static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum)
+static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum, int hslots)
 {
-  if (L.cap != cap || L.maxk < maxk || L.dnum != dnum) {
+  if (L.cap != cap || L.maxk < maxk || L.dnum != dnum || L.hslots < hslots) {
     L.nbr.release(); L.ptag.release(); L.hist.release(); L.numneigh.release();
-    L.cap = cap; L.maxk = maxk; L.dnum = dnum;
+    L.cap = cap; L.maxk = maxk; L.dnum = dnum; L.hslots = hslots;
     L.nbr.ensure(E, (size_t)maxk * cap); L.ptag.ensure(E, (size_t)maxk * cap); L.numneigh.ensure(E, cap);
-    if (dnum) L.hist.ensure(E, (size_t)maxk * dnum * cap);
+    if (dnum) L.hist.ensure(E, (size_t)hslots * dnum * cap);
   }
 }
 
@@ -544,7 +548,7 @@ static void rebuild(dem_engine *E)
   const int dnum = E->have_pair ? E->pm.dnum : 0;
   ensure_cub(E, (size_t)E->cap);
   E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->perm.ensure(E, E->cap);
-  E->overflow.ensure(E, 1);
+  E->overflow.ensure(E, 2);
   BoxP B;
   for (int d = 0; d < 3; d++) { B.lo[d] = E->lo[d]; B.hi[d] = E->hi[d]; B.prd[d] = E->prd[d]; B.periodic[d] = E->periodic[d]; }
   int c = E->cur;
@@ -628,11 +632,12 @@ static void rebuild(dem_engine *E)
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
+  int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : 16));
   for (int attempt = 0; attempt < 6 && n; attempt++) {
-    ensure_list(E, Lnew, E->cap, maxk, dnum);
-    CK(cudaMemsetAsync(E->overflow.p, 0, sizeof(int), st));
+    ensure_list(E, Lnew, E->cap, maxk, dnum, hslots);
+    CK(cudaMemsetAsync(E->overflow.p, 0, 2 * sizeof(int), st));
     BuildP P;
-    P.nlocal = n; P.cap = Lnew.cap; P.maxk = Lnew.maxk; P.dnum = dnum; P.xr = E->xr[c].p; P.tag = E->tag.p; P.G = E->grid;
+    P.nlocal = n; P.cap = Lnew.cap; P.maxk = Lnew.maxk; P.dnum = dnum; P.hslots = Lnew.hslots; P.xr = E->xr[c].p; P.tag = E->tag.p; P.G = E->grid;
     P.ocs = E->ocs.p; P.oce = E->oce.p; P.gcs = E->gcs.p; P.gce = E->gce.p; P.cdf = E->cdf; P.skin = E->skin;
     P.nbr = Lnew.nbr.p; P.numneigh = Lnew.numneigh.p; P.ptag = Lnew.ptag.p; P.hist = Lnew.hist.p;
     P.have_old = (Lold.valid && dnum && Lold.dnum == dnum) ? 1 : 0; P.cap_old = Lold.cap; P.dnum_old = Lold.dnum;
@@ -640,12 +645,14 @@ static void rebuild(dem_engine *E)
     P.overflow = E->overflow.p;
     k_build_list<<<GRID(n, 128), 128, 0, st>>>(P);
     E->launches++;
-    int ov = 0;
-    CK(cudaMemcpyAsync(&ov, E->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int ov[2] = {0, 0};
+    CK(cudaMemcpyAsync(ov, E->overflow.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (ov == 0) break;
-    if (attempt == 5) dem_fail(E, DEM_ERR_OVERFLOW, "neighbour list overflow (%d neighbours)", ov);
-    maxk = ov + 4;
+    if (ov[0] == 0 && ov[1] == 0) break;
+    if (attempt == 5) dem_fail(E, DEM_ERR_OVERFLOW, "neighbour list overflow (%d neighbours, %d history partners)", ov[0], ov[1]);
+    if (ov[0]) maxk = ov[0] + 4;
+    if (ov[1]) hslots = ov[1] + 12;
+    if (maxk > 0xffff || hslots > NBR_MAXSLOTS) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d neighbours / %d history partners", ov[0], ov[1]);
   }
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
@@ -668,7 +675,7 @@ static StepP step_params(dem_engine *E, int mode)
   P.nlocal = (int)E->nlocal; P.nall = (int)(E->nlocal + E->nghost); P.cap = E->cap; P.maxk = L.maxk; P.lcap = L.cap;
   P.xr = E->xr[c].p; P.vm = E->vm[c].p; P.wt = E->wt[c].p;
   P.xr_o = E->xr[c ^ 1].p; P.vm_o = E->vm[c ^ 1].p; P.wt_o = E->wt[c ^ 1].p;
-  P.xh = E->xh.p; P.nbr = L.nbr.p; P.numneigh = L.numneigh.p; P.hist = L.hist.p;
+  P.xh = E->xh.p; P.nbr = L.nbr.p; P.numneigh = L.numneigh.p; P.hist = L.hist.p; P.hslots = L.hslots;
   P.whist = E->whist.p; P.f = E->f.p; P.tq = E->tq.p; P.walls = E->dwalls.p; P.nwalls = (int)E->walls.size();
   P.pm = E->pm; P.tab = E->tab.p; P.nt1 = E->ntypes + 1;
   P.dt = E->dt; P.dtv = E->dt; P.dtf = 0.5 * E->dt * E->ftm2v; P.dtfrot = P.dtf / 0.4;  // fix_nve.cpp:86, fix_nve_sphere.cpp:69,150
@@ -781,6 +788,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   collect_timing(e);
+  if (e->hflag[1]) { e->hflag[1] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;
   API_END
 }
@@ -842,18 +850,20 @@ static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector
   std::vector<int> tags(n), nn(n);
   CK(cudaMemcpy(tags.data(), E->tag.p, n * sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(nn.data(), L.numneigh.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  for (long i = 0; i < n; i++) nn[i] &= 0xffff;
   int kmax = 0; for (long i = 0; i < n; i++) kmax = std::max(kmax, nn[i]);
   std::vector<unsigned> nbr((size_t)kmax * L.cap); std::vector<int> ptag((size_t)kmax * L.cap);
   if (kmax) {
     CK(cudaMemcpy(nbr.data(), L.nbr.p, nbr.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ptag.data(), L.ptag.p, ptag.size() * sizeof(int), cudaMemcpyDeviceToHost));
   }
-  hist.assign((size_t)kmax * dnum * L.cap, 0.0);
+  hist.assign((size_t)L.hslots * dnum * L.cap, 0.0);
   if (kmax && dnum) CK(cudaMemcpy(hist.data(), L.hist.p, hist.size() * sizeof(double), cudaMemcpyDeviceToHost));
   for (long i = 0; i < n; i++) for (int k = 0; k < nn[i]; k++) {
     const unsigned w = nbr[(size_t)k * L.cap + i];
     const int tj = ptag[(size_t)k * L.cap + i];
-    if (tags[i] < tj) rows.push_back(PairRow{tags[i], tj, (w & NBR_HIST) ? 1 : 0, (long)k * L.cap + i});
+    const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+    if (tags[i] < tj) rows.push_back(PairRow{tags[i], tj, slot >= 0 ? 1 : 0, (long)std::max(slot, 0) * L.cap + i});
   }
   std::sort(rows.begin(), rows.end(), [](const PairRow &a, const PairRow &b) { return a.lo != b.lo ? a.lo < b.lo : a.hi < b.hi; });
 }

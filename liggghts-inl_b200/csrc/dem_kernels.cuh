@@ -20,29 +20,41 @@ __device__ __forceinline__ double sq3_rn(double a, double b, double c)
 {  // a*a+b*b+c*c exactly as the un-contracted CPU expression (predicates must be bit-exact)
   return __dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c));
 }
+// 256-bit record access (sm_100: LDG.E.256 / STG.E.256): one instruction per 32-byte particle record
+__device__ __forceinline__ double4 ldg4(const double4 *p)
+{
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st4(double4 *p, const double4 &v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int rec_type(double w) { return (int)(__double_as_longlong(w) & 0xff); }
 __device__ __forceinline__ int rec_mask(double w) { return (int)((__double_as_longlong(w) >> 8) & 0xffffffffLL); }
 __host__ __device__ __forceinline__ long long pack_bits(int type, int mask) { return ((long long)(unsigned)mask << 8) | (long long)(type & 0xff); }
 
 // sphere/wall contact with the wall's own model selection (uniform run-time switch)
-__device__ __noinline__ void wall_chain(const StepP &P, const ModelP &M, const Contact &c, double *h, bool su, ContactOut &o)
+__device__ __noinline__ void wall_chain(const StepP &P, const ModelP &M, const Contact &c, double (&h)[3], double (&g)[3], bool su, ContactOut &o)
 {
   const int key = M.normal * 4 + M.rolling;
   switch (key) {
-    case N_HERTZ * 4 + R_OFF: contact_chain<N_HERTZ, R_OFF, true>(P, M, c, h, su, o); break;
-    case N_HERTZ * 4 + R_CDT: contact_chain<N_HERTZ, R_CDT, true>(P, M, c, h, su, o); break;
-    case N_HERTZ * 4 + R_EPSD: contact_chain<N_HERTZ, R_EPSD, true>(P, M, c, h, su, o); break;
-    case N_HERTZ * 4 + R_EPSD2: contact_chain<N_HERTZ, R_EPSD2, true>(P, M, c, h, su, o); break;
-    case N_HOOKE * 4 + R_OFF: contact_chain<N_HOOKE, R_OFF, true>(P, M, c, h, su, o); break;
-    case N_HOOKE * 4 + R_CDT: contact_chain<N_HOOKE, R_CDT, true>(P, M, c, h, su, o); break;
-    case N_HOOKE * 4 + R_EPSD: contact_chain<N_HOOKE, R_EPSD, true>(P, M, c, h, su, o); break;
-    default: contact_chain<N_HOOKE, R_EPSD2, true>(P, M, c, h, su, o); break;
+    case N_HERTZ * 4 + R_OFF: contact_chain<N_HERTZ, R_OFF, true>(P, M, c, h, g, su, o); break;
+    case N_HERTZ * 4 + R_CDT: contact_chain<N_HERTZ, R_CDT, true>(P, M, c, h, g, su, o); break;
+    case N_HERTZ * 4 + R_EPSD: contact_chain<N_HERTZ, R_EPSD, true>(P, M, c, h, g, su, o); break;
+    case N_HERTZ * 4 + R_EPSD2: contact_chain<N_HERTZ, R_EPSD2, true>(P, M, c, h, g, su, o); break;
+    case N_HOOKE * 4 + R_OFF: contact_chain<N_HOOKE, R_OFF, true>(P, M, c, h, g, su, o); break;
+    case N_HOOKE * 4 + R_CDT: contact_chain<N_HOOKE, R_CDT, true>(P, M, c, h, g, su, o); break;
+    case N_HOOKE * 4 + R_EPSD: contact_chain<N_HOOKE, R_EPSD, true>(P, M, c, h, g, su, o); break;
+    default: contact_chain<N_HOOKE, R_EPSD2, true>(P, M, c, h, g, su, o); break;
   }
 }
 
 // primitive walls of one particle: fix_wall_gran.cpp:988-1121, fix_wall_gran_base.h:159-367,
 // primitive_wall_definitions.h:128-203
-__device__ __forceinline__ void walls_of_particle(const StepP &P, int i, const double4 &xi, const double4 &vi,
+__device__ __noinline__ void walls_of_particle(const StepP &P, int i, const double4 &xi, const double4 &vi,
                                                   const double4 &wi, int itype, bool su, double *F, double *T)
 {
   const double4 xh = P.xh[i];
@@ -94,15 +106,24 @@ __device__ __forceinline__ void walls_of_particle(const StepP &P, int i, const d
           } else c.vj[W.shearDim] = W.vshear;
         }
         c.itype = itype; c.jtype = W.atom_type;
-        double h[6] = {0., 0., 0., 0., 0., 0.};
-        if ((valid >> w) & 1u)
-          for (int d = 0; d < wd; d++) h[d] = P.whist[(size_t)(W.hist_row + d) * P.cap + i];
+        double h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
+        if ((valid >> w) & 1u) {
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            if (W.m.tangential) h[d] = P.whist[(size_t)(W.hist_row + W.m.off_shear + d) * P.cap + i];
+            if (W.m.off_roll >= 0) g[d] = P.whist[(size_t)(W.hist_row + W.m.off_roll + d) * P.cap + i];
+          }
+        }
         ContactOut o;
-        wall_chain(P, W.m, c, h, su, o);
+        wall_chain(P, W.m, c, h, g, su, o);
         F[0] += o.F[0]; F[1] += o.F[1]; F[2] += o.F[2];
         T[0] += o.Ti[0]; T[1] += o.Ti[1]; T[2] += o.Ti[2];
         if (su && wd) {
-          for (int d = 0; d < wd; d++) P.whist[(size_t)(W.hist_row + d) * P.cap + i] = h[d];
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            if (W.m.tangential) P.whist[(size_t)(W.hist_row + W.m.off_shear + d) * P.cap + i] = h[d];
+            if (W.m.off_roll >= 0) P.whist[(size_t)(W.hist_row + W.m.off_roll + d) * P.cap + i] = g[d];
+          }
           valid |= (1u << w);
         }
       } else valid &= ~(1u << w);  // surfacesClose: history zeroed (tangential_model_history.h:428-440)
@@ -114,76 +135,106 @@ __device__ __forceinline__ void walls_of_particle(const StepP &P, int i, const d
   }
 }
 
+template <int NORMAL, int ROLLING>
+__device__ __forceinline__ void pair_contact(const StepP &P, int i, int k, const double4 &xi, const double4 &vi, const double4 &wi,
+                                             int itype, int imask, bool su, int &nh, double *F, double *T)
+{
+  const int dnum = P.pm.dnum;
+  const unsigned w = P.nbr[(size_t)k * P.lcap + i];
+  const int j = (int)(w & NBR_IDX);
+  const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
+  const double sgn = (w & NBR_JFIRST) ? -1.0 : 1.0;
+  int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+  const bool had = slot >= 0;
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  double h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
+  if (had) {
+    const double *hp = P.hist + (size_t)(slot * dnum) * P.lcap + i;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (P.pm.tangential) h[d] = sgn * hp[(size_t)(P.pm.off_shear + d) * P.lcap];
+      if (HAS_ROLL_HIST) g[d] = sgn * hp[(size_t)(P.pm.off_roll + d) * P.lcap];
+    }
+  }
+  const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+  const double rsq = sq3_rn(dx, dy, dz);
+  pair_chain<NORMAL, ROLLING>(P, P.pm, xi, vi, wi, xj, vj, wj, itype, rec_type(wj.w), imask, rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
+  if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
+    if (nh < P.hslots) { slot = nh++; P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); }
+    else ((volatile int *)P.flag)[1] = 1;
+  }
+  if (dnum && slot >= 0 && (su || !had)) {
+    double *hp = P.hist + (size_t)(slot * dnum) * P.lcap + i;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (P.pm.tangential) hp[(size_t)(P.pm.off_shear + d) * P.lcap] = sgn * h[d];
+      if (HAS_ROLL_HIST) hp[(size_t)(P.pm.off_roll + d) * P.lcap] = sgn * g[d];
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // THE hot kernel: one launch == one timestep of the owned particles of this GPU.
 //   verlet.cpp:264-391 (order of operations), pair_gran_base.h:257-496 (pair loop),
 //   fix_gravity.cpp:331-339, fix_freeze.cpp:132-144, fix_nve_sphere.cpp:134-244,
 //   neighbor.cpp:1425-1466 (rebuild trigger)
+// Two phases per particle: (1) stream the row, gather the partner positions with several
+// independent loads in flight and build a bit mask of touching slots; (2) pop the set bits,
+// so the lanes of a warp walk their c-th CONTACT together instead of idling through the
+// non-touching slots of their neighbours.
+#ifndef DEM_STEP_MINBLOCKS
+#define DEM_STEP_MINBLOCKS 4
+#endif
 template <int NORMAL, int ROLLING>
-__global__ void __launch_bounds__(128) k_step(const StepP P)
+__global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool trig = false;
-  unsigned ncont = 0;
   if (i < P.nlocal) {
-    const double4 xi = P.xr[i], vi = P.vm[i], wi = P.wt[i];
+    const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
     const int itype = rec_type(wi.w), imask = rec_mask(wi.w);
     const bool su = (P.mode != MODE_SETUP);
     double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
     if (P.have_pair) {
-      const int nn = P.numneigh[i];
-      const int dnum = P.pm.dnum;
-      for (int k = 0; k < nn; k++) {
-        const unsigned w = P.nbr[(size_t)k * P.lcap + i];
-        const int j = (int)(w & NBR_IDX);
-        const double4 xj = P.xr[j];
-        const bool jfirst = (w & NBR_JFIRST) != 0;
-        // first - second, exact negation keeps both copies of a pair identical
-        const double dx = jfirst ? xj.x - xi.x : xi.x - xj.x;
-        const double dy = jfirst ? xj.y - xi.y : xi.y - xj.y;
-        const double dz = jfirst ? xj.z - xi.z : xi.z - xj.z;
-        const double rsq = sq3_rn(dx, dy, dz);
-        const double radsum = xi.w + xj.w;
-        const double rs2 = __dmul_rn(radsum, radsum);
-        if (rsq < rs2) {
-          const double4 vj = P.vm[j], wj = P.wt[j];
-          const int jtype = rec_type(wj.w), jmask = rec_mask(wj.w);
-          Contact c;
-          c.dx = dx; c.dy = dy; c.dz = dz;
-          c.r = sqrt(rsq); c.rinv = 1.0 / c.r; c.radsum = radsum; c.deltan_in = 0.0;
-          const double4 &xa = jfirst ? xj : xi, &xb = jfirst ? xi : xj;
-          const double4 &va = jfirst ? vj : vi, &vb = jfirst ? vi : vj;
-          const double4 &wa = jfirst ? wj : wi, &wb = jfirst ? wi : wj;
-          c.radi = xa.w; c.radj = xb.w; c.mi = va.w; c.mj = vb.w;
-          c.vi[0] = va.x; c.vi[1] = va.y; c.vi[2] = va.z; c.vj[0] = vb.x; c.vj[1] = vb.y; c.vj[2] = vb.z;
-          c.wi[0] = wa.x; c.wi[1] = wa.y; c.wi[2] = wa.z; c.wj[0] = wb.x; c.wj[1] = wb.y; c.wj[2] = wb.z;
-          c.itype = jfirst ? jtype : itype; c.jtype = jfirst ? itype : jtype;
-          double meff = c.mi * c.mj / (c.mi + c.mj);
-          if ((jfirst ? jmask : imask) & P.freezebit) meff = c.mj;  // pair_gran_base.h:389-393
-          if ((jfirst ? imask : jmask) & P.freezebit) meff = c.mi;
-          c.meff = meff;
-          double h[6] = {0., 0., 0., 0., 0., 0.};
-          const bool had = (w & NBR_HIST) != 0;
-          if (had)
-            for (int d = 0; d < dnum; d++) h[d] = P.hist[(size_t)(k * dnum + d) * P.lcap + i];
-          ContactOut o;
-          contact_chain<NORMAL, ROLLING, false>(P, P.pm, c, h, su, o);
-          if (jfirst) {
-            F[0] -= o.F[0]; F[1] -= o.F[1]; F[2] -= o.F[2];
-            T[0] += o.Tj[0]; T[1] += o.Tj[1]; T[2] += o.Tj[2];
-          } else {
-            F[0] += o.F[0]; F[1] += o.F[1]; F[2] += o.F[2];
-            T[0] += o.Ti[0]; T[1] += o.Ti[1]; T[2] += o.Ti[2];
+      const int nnw = P.numneigh[i];
+      const int nn = nnw & 0xffff;
+      int nh = (nnw >> 16) & 0xffff;
+      const int nh0 = nh;
+      for (int k0 = 0; k0 < nn; k0 += 64) {
+        const int kn = min(64, nn - k0);
+        unsigned long long touch = 0ull, close = 0ull;
+#pragma unroll 4
+        for (int kk = 0; kk < kn; kk++) {
+          const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+          const double4 xj = ldg4(P.xr + (w & NBR_IDX));
+          const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+          const double radsum = xi.w + xj.w;
+          if (rsq < __dmul_rn(radsum, radsum)) {
+            touch |= 1ull << kk;
+            // phase 2 will need the partner's v|m and omega|type records and this pair's history rows:
+            // start those DRAM accesses now, without holding registers for them
+            prefetch_l1(P.vm + (w & NBR_IDX)); prefetch_l1(P.wt + (w & NBR_IDX));
+            if (w & NBR_HIST) {
+              const double *hp = P.hist + (size_t)((((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1) * P.pm.dnum) * P.lcap + i;
+              for (int d = 0; d < P.pm.dnum; d++) prefetch_l1(hp + (size_t)d * P.lcap);
+            }
           }
-          if (dnum && (su || !had))
-            for (int d = 0; d < dnum; d++) P.hist[(size_t)(k * dnum + d) * P.lcap + i] = h[d];
-          if (!had) P.nbr[(size_t)k * P.lcap + i] = w | NBR_HIST;
-          ncont++;
-        } else if (P.cdf > 1.0 && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) {
-          // surfacesClose: tangential/rolling history zeroed, flag stays (normal bit), pair_gran_base.h:420-423
-          for (int d = 0; d < dnum; d++) P.hist[(size_t)(k * dnum + d) * P.lcap + i] = 0.0;
+          else if (P.cdf > 1.0 && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) close |= 1ull << kk;
+        }
+        while (touch) {
+          const int kk = __ffsll((long long)touch) - 1;
+          touch &= touch - 1;
+          pair_contact<NORMAL, ROLLING>(P, i, k0 + kk, xi, vi, wi, itype, imask, su, nh, F, T);
+        }
+        while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
+          const int kk = __ffsll((long long)close) - 1;
+          close &= close - 1;
+          const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+          const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+          for (int d = 0; d < P.pm.dnum; d++) P.hist[(size_t)(slot * P.pm.dnum + d) * P.lcap + i] = 0.0;
         }
       }
+      if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
     }
     if (P.have_g && (imask & 1)) { F[0] += vi.w * P.g[0]; F[1] += vi.w * P.g[1]; F[2] += vi.w * P.g[2]; }
     if (P.nwalls) walls_of_particle(P, i, xi, vi, wi, itype, su, F, T);
@@ -207,7 +258,7 @@ __global__ void __launch_bounds__(128) k_step(const StepP P)
           wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
         }
       }
-      P.xr_o[i] = xo; P.vm_o[i] = vo; P.wt_o[i] = wo;
+      st4(P.xr_o + i, xo); st4(P.vm_o + i, vo); st4(P.wt_o + i, wo);
       if (P.mode == MODE_STEP) {
         const double4 xh = P.xh[i];
         trig = sq3_rn(xo.x - xh.x, xo.y - xh.y, xo.z - xh.z) > P.trigsq;
@@ -215,10 +266,6 @@ __global__ void __launch_bounds__(128) k_step(const StepP P)
     }
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
-  if (P.ncontact) {
-    for (int o = 16; o; o >>= 1) ncont += __shfl_down_sync(0xffffffffu, ncont, o);
-    if ((threadIdx.x & 31) == 0 && ncont) atomicAdd(P.ncontact, (unsigned long long)ncont);
-  }
 }
 
 // first half step of a run from the stored force arrays: fix_nve_sphere.cpp:134-183
@@ -385,7 +432,7 @@ __global__ void __launch_bounds__(256) k_ghost_permute(int n, const int *perm, c
 
 // Verlet-skin FULL list + history remap: neigh_gran.cpp:560-625 (predicates), fix_contact_history.cpp:351
 struct BuildP {
-  int nlocal, cap, maxk, dnum;
+  int nlocal, cap, maxk, dnum, hslots;
   const double4 *xr;
   const int *tag;
   GridP G;
@@ -405,8 +452,8 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
   const int tagi = B.tag[i];
   int cx, cy, cz; cell_of(B.G, xi, cx, cy, cz);
   const int oi = B.have_old ? B.perm[i] : 0;
-  const int nold = B.have_old ? B.numneigh_old[oi] : 0;
-  int n = 0;
+  const int nold = B.have_old ? (B.numneigh_old[oi] & 0xffff) : 0;
+  int n = 0, nh = 0;
   for (int dz = -1; dz <= 1; dz++) {
     const int z = cz + dz; if (z < 0 || z >= B.G.nc[2]) continue;
     for (int dy = -1; dy <= 1; dy++) {
@@ -428,10 +475,15 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
                 unsigned w = (unsigned)j | (tagj < tagi ? NBR_JFIRST : 0u);
                 if (nold && rsq < __dmul_rn(radsum, radsum)) {
                   for (int m = 0; m < nold; m++) {
-                    if (B.ptag_old[(size_t)m * B.cap_old + oi] == tagj && (B.nbr_old[(size_t)m * B.cap_old + oi] & NBR_HIST)) {
-                      w |= NBR_HIST;
-                      for (int d = 0; d < B.dnum; d++)
-                        B.hist[(size_t)(n * B.dnum + d) * B.cap + i] = B.hist_old[(size_t)(m * B.dnum + d) * B.cap_old + oi];
+                    const unsigned wo = B.nbr_old[(size_t)m * B.cap_old + oi];
+                    if ((wo & NBR_HIST) && B.ptag_old[(size_t)m * B.cap_old + oi] == tagj) {
+                      const int so = (int)((wo & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+                      if (nh < B.hslots) {
+                        w |= (unsigned)(nh + 1) << NBR_SLOT_SHIFT;
+                        for (int d = 0; d < B.dnum; d++)
+                          B.hist[(size_t)(nh * B.dnum + d) * B.cap + i] = B.hist_old[(size_t)(so * B.dnum + d) * B.cap_old + oi];
+                      }
+                      nh++;
                       break;
                     }
                   }
@@ -446,8 +498,9 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
       }
     }
   }
-  B.numneigh[i] = min(n, B.maxk);
+  B.numneigh[i] = min(n, B.maxk) | (min(nh, B.hslots) << 16);
   if (n > B.maxk) atomicMax(B.overflow, n);
+  if (nh + 8 > B.hslots) atomicMax(B.overflow + 1, nh);
 }
 
 // positions at build time (neighbor.cpp:1486-1510) + primitive-wall candidate bits (primitive_wall.h:129-138)
@@ -488,7 +541,7 @@ __global__ void __launch_bounds__(256) k_count_pairs(int n, const int *numneigh,
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long a = 0, b = 0;
-  if (i < n) { const int nn = numneigh[i]; a = nn; for (int k = 0; k < nn; k++) b += (nbr[(size_t)k * cap + i] & NBR_HIST) ? 1 : 0; }
+  if (i < n) { const int nn = numneigh[i] & 0xffff; a = nn; for (int k = 0; k < nn; k++) b += (nbr[(size_t)k * cap + i] & NBR_HIST) ? 1 : 0; }
   for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
   if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(out, a); if (b) atomicAdd(out + 1, b); }
 }

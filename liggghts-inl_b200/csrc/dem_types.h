@@ -7,16 +7,20 @@ namespace dem {
 enum { N_OFF = 0, N_HERTZ = 1, N_HOOKE = 2 };
 enum { R_OFF = 0, R_CDT = 1, R_EPSD = 2, R_EPSD2 = 3 };
 // per-type-pair tables, each (ntypes+1)^2 doubles, concatenated in this order
-enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_COUNT };
+enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_SQ2Y, T_SQ8G, T_INV8G, T_COUNT };
 
 #define DEM_MAXW 16  // primitive walls per engine (candidate + valid bits share one 32-bit word)
 
-// neighbour word: [31] partner is the "first" body of the pair (partner tag < own tag)
-//                 [30] pair holds contact history (== reference contact_flag != 0)
-//                 [29:0] partner index (owned or ghost), cf. NEIGHMASK lmptype.h:86
+// neighbour word: [31]    partner is the "first" body of the pair (partner tag < own tag)
+//                 [30:25] history slot + 1 of this pair in the particle's compact history rows;
+//                         0 = pair holds no history (== reference contact_flag == 0)
+//                 [24:0]  partner index (owned or ghost), cf. NEIGHMASK lmptype.h:86
+// numneigh word:  [15:0] list length, [31:16] history slots in use by this particle
 #define NBR_JFIRST 0x80000000u
-#define NBR_HIST 0x40000000u
-#define NBR_IDX 0x3FFFFFFFu
+#define NBR_HIST 0x7E000000u
+#define NBR_SLOT_SHIFT 25
+#define NBR_IDX 0x01FFFFFFu
+#define NBR_MAXSLOTS 62
 
 struct ModelP {
   int normal, tangential, rolling;
@@ -44,8 +48,9 @@ struct StepP {
   double4 *xr_o, *vm_o, *wt_o;
   double4 *xh;  // (xhold, bits(wall candidate | wall-history-valid << 16))
   unsigned *nbr;
-  const int *numneigh;
-  double *hist;   // [maxk*dnum][cap]
+  int *numneigh;
+  double *hist;   // [hslots*dnum][lcap], slot-major: contact c of particle i at rows c*dnum..c*dnum+dnum-1
+  int hslots;
   double *whist;  // [sum wall dnum][cap]
   double *f, *tq; // [3][cap]
   const WallP *walls;
@@ -57,7 +62,7 @@ struct StepP {
   double g[3];
   int have_g, have_pair, freezebit, integbit;
   int mode;
-  int *flag;  // rebuild trigger (mapped host memory)
+  int *flag;  // [0] rebuild trigger, [1] history-slot overflow (mapped host memory)
   unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
 };
 

@@ -27,7 +27,7 @@ class Stats(C.Structure):
 
 
 def library_path():
-    return os.path.join(_ROOT, "libdem_b200.so")
+    return os.environ.get("DEM_B200_LIB", os.path.join(_ROOT, "libdem_b200.so"))
 
 
 def load_library(path=None):
