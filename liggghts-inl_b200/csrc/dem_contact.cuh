@@ -33,6 +33,12 @@ __device__ __forceinline__ double tabv(const StepP &P, int which, int it, int jt
 {
   return __ldg(P.tab + (which * P.nt1 + it) * P.nt1 + jt);
 }
+// ONE = single atom type: the material constants are kernel parameters (uniform), no per-thread loads
+template <bool ONE>
+__device__ __forceinline__ double tabp(const StepP &P, int which, int tij)
+{
+  return ONE ? P.t1[which] : __ldg(P.tab + which * P.nt1 * P.nt1 + tij);
+}
 
 // shear / ch: the tangential shear vector and the rolling spring torque of this pair's history row
 // (fixed-size so that they live in registers; the caller maps them to rows off_shear.. / off_roll..)
@@ -210,12 +216,13 @@ __device__ __forceinline__ void sqrt_rsqrt_fast(double x, double &s, double &rs)
 // forces are equal and opposite to the last bit and the two history copies stay exact negatives,
 // without selecting operands into a canonical order.  shear/ch are in MY orientation.
 // Adds the force / torque acting on me to F / T.
-template <int NORMAL, int ROLLING>
+template <int NORMAL, int ROLLING, bool ONE>
 __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, const double4 &xi, const double4 &vi, const double4 &wi,
                                            const double4 &xj, const double4 &vj, const double4 &wj, int itype, int jtype,
                                            int imask, int jmask, double dx, double dy, double dz, double rsq,
                                            double (&shear)[3], double (&ch)[3], bool shearupdate, double *F, double *T)
 {
+  const int tij = itype * P.nt1 + jtype;
   double r, rinv;
   sqrt_rsqrt_fast(rsq, r, rinv);
   const double enx = dx * rinv, eny = dy * rinv, enz = dz * rinv;
@@ -240,19 +247,19 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
   if (jmask & P.freezebit) meff = mi;
   double kn, kt, inv_kt, gamman, gammat;
   if (NORMAL == N_HERTZ) {  // normal_model_hertz.h:205-266
-    const double Y = tabv(P, T_YEFF, itype, jtype), G = tabv(P, T_GEFF, itype, jtype);
-    const double beta = tabv(P, T_BETA, itype, jtype);
+    const double Y = tabp<ONE>(P, T_YEFF, tij), G = tabp<ONE>(P, T_GEFF, tij);
+    const double beta = tabp<ONE>(P, T_BETA, tij);
     double s, inv_s, q, inv_q;
     sqrt_rsqrt_fast(reff * deltan, s, inv_s);
     sqrt_rsqrt_fast(s * meff, q, inv_q);
     kn = 4. / 3. * Y * s; kt = 8. * G * s;
-    inv_kt = tabv(P, T_INV8G, itype, jtype) * inv_s;
+    inv_kt = tabp<ONE>(P, T_INV8G, tij) * inv_s;
     const double c2 = -2. * 0.91287092917527685576161630466800355658790782499663875 * beta * q;
-    gamman = c2 * tabv(P, T_SQ2Y, itype, jtype);          // -2 sqrt(5/6) beta sqrt(Sn meff), Sn = 2 Y s
-    gammat = M.tdamp ? c2 * tabv(P, T_SQ8G, itype, jtype) : 0.0;  // St = 8 G s
+    gamman = c2 * tabp<ONE>(P, T_SQ2Y, tij);          // -2 sqrt(5/6) beta sqrt(Sn meff), Sn = 2 Y s
+    gammat = M.tdamp ? c2 * tabp<ONE>(P, T_SQ8G, tij) : 0.0;  // St = 8 G s
   } else {  // normal_model_hooke.h:230-300
-    const double Y = tabv(P, T_YEFF, itype, jtype);
-    const double lg = tabv(P, T_CORLOG, itype, jtype);
+    const double Y = tabp<ONE>(P, T_YEFF, tij);
+    const double lg = tabp<ONE>(P, T_CORLOG, tij);
     const double sqrtval = sqrt(reff);
     kn = 16. / 15. * sqrtval * Y * pow(15. * meff * P.charVel * P.charVel / (16. * sqrtval * Y), 0.2);
     kt = kn;
@@ -275,7 +282,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
     }
     double shrmag, inv_shr;
     sqrt_rsqrt_fast(shear[0] * shear[0] + shear[1] * shear[1] + shear[2] * shear[2], shrmag, inv_shr);
-    const double xmu = tabv(P, T_MU, itype, jtype);
+    const double xmu = tabp<ONE>(P, T_MU, tij);
     double Ft1 = -(kt * shear[0]), Ft2 = -(kt * shear[1]), Ft3 = -(kt * shear[2]);
     const double Ft_shear = kt * shrmag, Ft_friction = xmu * fabs(Fn);
     if (Ft_shear > Ft_friction) {
@@ -292,7 +299,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
   }
   if (ROLLING != R_OFF) {
     const double a1 = wi.x - wj.x, a2 = wi.y - wj.y, a3 = wi.z - wj.z;
-    const double rmu = tabv(P, T_RMU, itype, jtype);
+    const double rmu = tabp<ONE>(P, T_RMU, tij);
     if (ROLLING == R_CDT) {  // rolling_model_cdt.h:91-167
       double mag, inv_mag;
       sqrt_rsqrt_fast(a1 * a1 + a2 * a2 + a3 * a3, mag, inv_mag);
@@ -325,7 +332,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
         if (ROLLING == R_EPSD) {
           const double ri = mi * radi * radi, rj = mj * radj * radj;
           const double r_inertia = 1.4 * ri * rj * rcp_fast(ri + rj);
-          const double r_coef = tabv(P, T_RVISC, itype, jtype) * 2 * sqrt(r_inertia * kr);
+          const double r_coef = tabp<ONE>(P, T_RVISC, tij) * 2 * sqrt(r_inertia * kr);
           r1 += r_coef * w1; r2 += r_coef * w2; r3 += r_coef * w3;
         }
       }

@@ -41,8 +41,8 @@ struct DevBuf {
 struct ListSet {  // one ELLPACK neighbour list + history (two sets ping-pong across rebuilds)
   DevBuf<unsigned> nbr;
   DevBuf<int> ptag, numneigh;
-  DevBuf<double> hist;
-  int cap = 0, maxk = 0, dnum = 0, hslots = 0, valid = 0;
+  DevBuf<double4> hist;
+  int cap = 0, maxk = 0, dnum = 0, hslots = 0, valid = 0;  // dnum = 32-byte history records per contact
 };
 
 struct WallHost { std::string id; WallP p; };
@@ -75,8 +75,10 @@ struct dem_engine {
   int cur = 0;
   DevBuf<int> tag, tag_tmp;
   DevBuf<double> density, density_tmp, f, tq, whist, whist_tmp, tab;
+  double t1[T_COUNT] = {0};
   DevBuf<WallP> dwalls;
   DevBuf<unsigned> valid_tmp;
+  DevBuf<int> wlist; DevBuf<double> fw; int nwc = 0, nwcap = 0;
   // ghosts
   DevBuf<int> gsrc, gshift, gsrc2, gshift2, flo, fhi, slo, shi;
   // cells / sort
@@ -162,7 +164,7 @@ extern "C" void dem_destroy(dem_engine *e)
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
   e->xh.release(); e->tag.release(); e->tag_tmp.release(); e->density.release(); e->density_tmp.release();
   e->f.release(); e->tq.release(); e->whist.release(); e->whist_tmp.release(); e->tab.release(); e->dwalls.release();
-  e->valid_tmp.release(); e->gsrc.release(); e->gshift.release(); e->gsrc2.release(); e->gshift2.release();
+  e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->gsrc.release(); e->gshift.release(); e->gsrc2.release(); e->gshift2.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
   e->cubtmp.release(); e->overflow.release(); e->counters.release();
@@ -282,9 +284,9 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
   }
   if ((m.rolling == R_EPSD || m.rolling == R_EPSD2) && !m.tangential)
     dem_fail(e, DEM_ERR_ARG, "rolling_friction epsd/epsd2 requires tangential history");
-  m.dnum = 0;
-  if (m.tangential) { m.off_shear = m.dnum; m.dnum += 3; }
-  if (m.rolling == R_EPSD || m.rolling == R_EPSD2) { m.off_roll = m.dnum; m.dnum += 3; }
+  m.dnum = 0; m.hrec = 0; m.rec_shear = m.rec_roll = -1;
+  if (m.tangential) { m.off_shear = m.dnum; m.dnum += 3; m.rec_shear = m.hrec++; }
+  if (m.rolling == R_EPSD || m.rolling == R_EPSD2) { m.off_roll = m.dnum; m.dnum += 3; m.rec_roll = m.hrec++; }
 }
 // trailing `key on|off` settings (Settings::parseArguments)
 static void parse_model_settings(dem_engine *e, int argc, const char *const *a, ModelP &m)
@@ -469,6 +471,7 @@ static void derive_tables(dem_engine *E)
     at(T_MU) = E->mu[i][j]; at(T_RMU) = E->rmu[i][j]; at(T_RVISC) = E->rvisc[i][j];
     if (hertz || hooke) { at(T_SQ2Y) = sqrt(2. * at(T_YEFF)); at(T_SQ8G) = sqrt(8. * at(T_GEFF)); at(T_INV8G) = 1. / (8. * at(T_GEFF)); }
   }
+  for (int w = 0; w < T_COUNT; w++) E->t1[w] = t[((size_t)w * n1 + 1) * n1 + 1];
   E->tab.ensure(E, t.size());
   CK(cudaMemcpyAsync(E->tab.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
   if (!E->walls.empty()) {
@@ -545,7 +548,7 @@ static void rebuild(dem_engine *E)
 {
   cudaStream_t st = E->stream;
   const int n = (int)E->nlocal;
-  const int dnum = E->have_pair ? E->pm.dnum : 0;
+  const int dnum = E->have_pair ? E->pm.hrec : 0;  // history records per contact
   ensure_cub(E, (size_t)E->cap);
   E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->perm.ensure(E, E->cap);
   E->overflow.ensure(E, 2);
@@ -658,8 +661,23 @@ static void rebuild(dem_engine *E)
   E->lcur ^= 1;
   // 6. positions at build time + primitive wall candidate bits
   if (n) {
-    k_hold<<<GRID(n, 256), 256, 0, st>>>(n, E->xr[c].p, E->xh.p, E->valid_tmp.p, E->dwalls.p, (int)E->walls.size(), E->skin);
+    const int nw = (int)E->walls.size();
+    E->flo.ensure(E, n + 1); E->slo.ensure(E, n + 1);
+    k_hold<<<GRID(n, 256), 256, 0, st>>>(n, E->xr[c].p, E->xh.p, E->valid_tmp.p, E->dwalls.p, nw, E->skin, nw ? E->flo.p : nullptr);
     E->launches++;
+    E->nwc = 0;
+    if (nw) {
+      size_t tb = E->cubtmp.n;
+      CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, E->flo.p, E->slo.p, n, st));
+      int last[2];
+      CK(cudaMemcpyAsync(&last[0], E->flo.p + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&last[1], E->slo.p + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      E->nwc = last[0] + last[1];
+      if (E->nwc > E->nwcap) { E->nwcap = E->nwc + E->nwc / 4 + 256; E->wlist.release(); E->fw.release(); E->wlist.ensure(E, E->nwcap); E->fw.ensure(E, 6 * (size_t)E->nwcap); }
+      if (E->nwc) k_wall_index<<<GRID(n, 256), 256, 0, st>>>(n, E->flo.p, E->slo.p, E->wlist.p, E->xh.p);
+      E->launches += 2;
+    }
   }
   CK(cudaGetLastError());
   E->ago = 0;
@@ -676,22 +694,24 @@ static StepP step_params(dem_engine *E, int mode)
   P.xr = E->xr[c].p; P.vm = E->vm[c].p; P.wt = E->wt[c].p;
   P.xr_o = E->xr[c ^ 1].p; P.vm_o = E->vm[c ^ 1].p; P.wt_o = E->wt[c ^ 1].p;
   P.xh = E->xh.p; P.nbr = L.nbr.p; P.numneigh = L.numneigh.p; P.hist = L.hist.p; P.hslots = L.hslots;
-  P.whist = E->whist.p; P.f = E->f.p; P.tq = E->tq.p; P.walls = E->dwalls.p; P.nwalls = (int)E->walls.size();
+  P.whist = E->whist.p; P.f = E->f.p; P.tq = E->tq.p; P.walls = E->dwalls.p; P.nwalls = (int)E->walls.size(); P.nwc = E->nwc; P.nwcap = E->nwcap; P.wlist = E->wlist.p; P.fw = E->fw.p;
   P.pm = E->pm; P.tab = E->tab.p; P.nt1 = E->ntypes + 1;
+  for (int w = 0; w < T_COUNT; w++) P.t1[w] = E->t1[w];
   P.dt = E->dt; P.dtv = E->dt; P.dtf = 0.5 * E->dt * E->ftm2v; P.dtfrot = P.dtf / 0.4;  // fix_nve.cpp:86, fix_nve_sphere.cpp:69,150
   P.nktv2p = E->nktv2p; P.charVel = E->charVel; P.cdf = E->cdf; P.cdfsq = E->cdf * E->cdf;
   P.trigsq = 0.25 * E->skin * E->skin;  // neighbor.cpp:298
   P.cutneighmax = E->cutneighmax;
   for (int d = 0; d < 3; d++) P.g[d] = E->g[d];
   P.have_g = E->have_g; P.have_pair = E->have_pair; P.freezebit = E->freezebit; P.integbit = E->integbit;
-  P.mode = mode; P.flag = E->hflag; P.ncontact = nullptr;
+  P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = E->hflag; P.ncontact = nullptr;
   return P;
 }
 
 template <int N, int R>
 static void launch_step_t(dem_engine *E, const StepP &P)
 {
-  k_step<N, R><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+  if (E->ntypes == 1) k_step<N, R, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+  else k_step<N, R, false><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
 }
 static void launch_step(dem_engine *E, int mode, bool timed)
 {
@@ -702,6 +722,7 @@ static void launch_step(dem_engine *E, int mode, bool timed)
     if ((long)E->ev.size() < 2 * (E->ev_used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); E->ev.push_back(a); E->ev.push_back(b); }
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
   }
+  if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
   switch (key) {
     case N_HERTZ * 4 + R_OFF: launch_step_t<N_HERTZ, R_OFF>(E, P); break;
@@ -839,7 +860,7 @@ extern "C" int dem_download(dem_engine *e, const char *field, void *out, long co
 }
 
 struct PairRow { int lo, hi, flag; long src; };
-static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector<double> &hist, int &dnum)
+static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector<double4> &hist, int &dnum)
 {
   ListSet &L = E->ls[E->lcur];
   dnum = L.dnum;
@@ -857,8 +878,8 @@ static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector
     CK(cudaMemcpy(nbr.data(), L.nbr.p, nbr.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ptag.data(), L.ptag.p, ptag.size() * sizeof(int), cudaMemcpyDeviceToHost));
   }
-  hist.assign((size_t)L.hslots * dnum * L.cap, 0.0);
-  if (kmax && dnum) CK(cudaMemcpy(hist.data(), L.hist.p, hist.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  hist.assign((size_t)L.hslots * dnum * L.cap, make_double4(0., 0., 0., 0.));
+  if (kmax && dnum) CK(cudaMemcpy(hist.data(), L.hist.p, hist.size() * sizeof(double4), cudaMemcpyDeviceToHost));
   for (long i = 0; i < n; i++) for (int k = 0; k < nn[i]; k++) {
     const unsigned w = nbr[(size_t)k * L.cap + i];
     const int tj = ptag[(size_t)k * L.cap + i];
@@ -872,26 +893,32 @@ extern "C" int dem_pair_count(dem_engine *e, long *npairs, int *dnum)
 {
   API_BEGIN
   CK(cudaSetDevice(e->device));
-  std::vector<PairRow> rows; std::vector<double> hist; int dn = 0;
+  std::vector<PairRow> rows; std::vector<double4> hist; int dn = 0;
   collect_pairs(e, rows, hist, dn);
   if (npairs) *npairs = (long)rows.size();
-  if (dnum) *dnum = dn;
+  if (dnum) *dnum = e->have_pair ? e->pm.dnum : 0;
   API_END
 }
 extern "C" int dem_download_pairs(dem_engine *e, int *lo, int *hi, int *flag, double *hist)
 {
   API_BEGIN
   CK(cudaSetDevice(e->device));
-  std::vector<PairRow> rows; std::vector<double> h; int dn = 0;
-  collect_pairs(e, rows, h, dn);
+  std::vector<PairRow> rows; std::vector<double4> h; int nrec = 0;
+  collect_pairs(e, rows, h, nrec);
   ListSet &L = e->ls[e->lcur];
+  const ModelP &M = e->pm;
+  const int dn = e->have_pair ? M.dnum : 0;
   for (size_t r = 0; r < rows.size(); r++) {
     if (lo) lo[r] = rows[r].lo;
     if (hi) hi[r] = rows[r].hi;
     if (flag) flag[r] = rows[r].flag;
     if (hist) {
-      const long k = rows[r].src / L.cap, i = rows[r].src % L.cap;
-      for (int d = 0; d < dn; d++) hist[r * dn + d] = rows[r].flag ? h[(size_t)(k * dn + d) * L.cap + i] : 0.0;
+      const long k = rows[r].src / L.cap, i = rows[r].src % L.cap;  // k = history slot
+      for (int d = 0; d < dn; d++) hist[r * dn + d] = 0.0;
+      if (rows[r].flag) {
+        if (M.rec_shear >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_shear) * L.cap + i]; hist[r * dn + M.off_shear] = v.x; hist[r * dn + M.off_shear + 1] = v.y; hist[r * dn + M.off_shear + 2] = v.z; }
+        if (M.rec_roll >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_roll) * L.cap + i]; hist[r * dn + M.off_roll] = v.x; hist[r * dn + M.off_roll + 1] = v.y; hist[r * dn + M.off_roll + 2] = v.z; }
+      }
     }
   }
   API_END
@@ -930,7 +957,7 @@ extern "C" int dem_get_stats(dem_engine *e, dem_stats *s)
   s->ntimestep = e->ntimestep; s->nbuilds = e->nbuilds; s->nlocal = e->nlocal; s->nghost = e->nghost;
   s->kernel_launches = e->launches;
   ListSet &L = e->ls[e->lcur];
-  s->maxneigh = L.maxk; s->dnum = L.dnum;
+  s->maxneigh = L.maxk; s->dnum = e->have_pair ? e->pm.dnum : 0;
   if (L.valid && e->nlocal) {
     e->counters.ensure(e, 2);
     CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), e->stream));

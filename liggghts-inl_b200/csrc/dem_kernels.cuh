@@ -24,14 +24,17 @@ __device__ __forceinline__ double sq3_rn(double a, double b, double c)
 __device__ __forceinline__ double4 ldg4(const double4 *p)
 {
   double4 v;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  // not volatile: a read-only load the compiler may hoist and batch with its neighbours
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st4(double4 *p, const double4 &v)
 {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+  // volatile (must not be dropped) but no memory clobber: nothing in the same thread reads it back
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w));
 }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int rec_type(double w) { return (int)(__double_as_longlong(w) & 0xff); }
 __device__ __forceinline__ int rec_mask(double w) { return (int)((__double_as_longlong(w) >> 8) & 0xffffffffLL); }
 __host__ __device__ __forceinline__ long long pack_bits(int type, int mask) { return ((long long)(unsigned)mask << 8) | (long long)(type & 0xff); }
@@ -54,9 +57,18 @@ __device__ __noinline__ void wall_chain(const StepP &P, const ModelP &M, const C
 
 // primitive walls of one particle: fix_wall_gran.cpp:988-1121, fix_wall_gran_base.h:159-367,
 // primitive_wall_definitions.h:128-203
-__device__ __noinline__ void walls_of_particle(const StepP &P, int i, const double4 &xi, const double4 &vi,
-                                                  const double4 &wi, int itype, bool su, double *F, double *T)
+// Pre-pass kernel over the compact list of particles that are candidates of at least one primitive
+// wall (a thin layer of the bed): keeps ~200 lines of rarely needed code and its registers out of
+// the hot kernel.  Writes the wall force/torque of candidate c to fw[0..5][c]; k_step adds it.
+__global__ void __launch_bounds__(128) k_walls(const StepP P)
 {
+  const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cidx >= P.nwc) return;
+  const int i = P.wlist[cidx];
+  const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
+  const int itype = rec_type(wi.w);
+  const bool su = (P.mode != MODE_SETUP);
+  double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
   const double4 xh = P.xh[i];
   const unsigned wbits = (unsigned)(__double_as_longlong(xh.w) & 0xffffffffLL);
   const unsigned cand = wbits & 0xffffu;
@@ -130,46 +142,61 @@ __device__ __noinline__ void walls_of_particle(const StepP &P, int i, const doub
     } else valid &= ~(1u << w);  // candidate but apart: history zeroed (fix_wall_gran.cpp:1117-1119)
   }
   if (valid != valid0) {
-    const long long nb = (long long)(cand | (valid << 16));
+    const long long nb = (__double_as_longlong(xh.w) & ~0xffffffffLL) | (long long)(cand | (valid << 16));
     P.xh[i].w = __longlong_as_double(nb);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) { P.fw[(size_t)d * P.nwcap + cidx] = F[d]; P.fw[(size_t)(3 + d) * P.nwcap + cidx] = T[d]; }
+}
+
+#define DEM_CMAX 16  // contacts per particle staged in shared memory (more go through the bit-mask path)
+
+// one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see
+// pair_chain); history records are stored in the canonical orientation "lower tag first" (sign
+// flipped on load/store when the partner is the first body)
+template <int NORMAL, int ROLLING, bool ONE>
+__device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, int nn, const double4 &xi, const double4 &vi,
+                                             const double4 &wi, int itype, int imask, bool su, int &nh, double *F, double *T)
+{
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  const int j = (int)(w & NBR_IDX);
+  int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+  const bool had = slot >= 0;
+  const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
+  double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
+  if (had) {
+    const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
+    if (P.pm.tangential) hs = hp[(size_t)P.pm.rec_shear * P.lcap];
+    if (HAS_ROLL_HIST) hr = hp[(size_t)P.pm.rec_roll * P.lcap];
+  }
+  const double sgn = (w & NBR_JFIRST) ? -1.0 : 1.0;
+  double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
+  const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+  const double rsq = sq3_rn(dx, dy, dz);
+  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, itype, rec_type(wj.w), imask, rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
+  if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
+    if (nh < P.hslots) {
+      slot = nh++;
+      for (int k = 0; k < nn; k++)  // rare path: find the row entry of this partner and tag it with its slot
+        if ((P.nbr[(size_t)k * P.lcap + i] & NBR_IDX) == (unsigned)j) { P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); break; }
+    } else ((volatile int *)P.flag)[1] = 1;
+  }
+  if (P.pm.hrec && slot >= 0 && (su || !had)) {
+    double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
+    if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
+    if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
   }
 }
 
-template <int NORMAL, int ROLLING>
-__device__ __forceinline__ void pair_contact(const StepP &P, int i, int k, const double4 &xi, const double4 &vi, const double4 &wi,
-                                             int itype, int imask, bool su, int &nh, double *F, double *T)
+// start the memory accesses a contact will need one iteration ahead, without holding registers
+__device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w)
 {
-  const int dnum = P.pm.dnum;
-  const unsigned w = P.nbr[(size_t)k * P.lcap + i];
   const int j = (int)(w & NBR_IDX);
-  const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
-  const double sgn = (w & NBR_JFIRST) ? -1.0 : 1.0;
-  int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-  const bool had = slot >= 0;
-  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
-  double h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
-  if (had) {
-    const double *hp = P.hist + (size_t)(slot * dnum) * P.lcap + i;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      if (P.pm.tangential) h[d] = sgn * hp[(size_t)(P.pm.off_shear + d) * P.lcap];
-      if (HAS_ROLL_HIST) g[d] = sgn * hp[(size_t)(P.pm.off_roll + d) * P.lcap];
-    }
-  }
-  const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-  const double rsq = sq3_rn(dx, dy, dz);
-  pair_chain<NORMAL, ROLLING>(P, P.pm, xi, vi, wi, xj, vj, wj, itype, rec_type(wj.w), imask, rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
-  if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
-    if (nh < P.hslots) { slot = nh++; P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); }
-    else ((volatile int *)P.flag)[1] = 1;
-  }
-  if (dnum && slot >= 0 && (su || !had)) {
-    double *hp = P.hist + (size_t)(slot * dnum) * P.lcap + i;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      if (P.pm.tangential) hp[(size_t)(P.pm.off_shear + d) * P.lcap] = sgn * h[d];
-      if (HAS_ROLL_HIST) hp[(size_t)(P.pm.off_roll + d) * P.lcap] = sgn * g[d];
-    }
+  prefetch_l1(P.xr + j); prefetch_l1(P.vm + j); prefetch_l1(P.wt + j);
+  const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+  if (slot >= 0) {
+    const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
+    for (int r = 0; r < P.pm.hrec; r++) prefetch_l1(hp + (size_t)r * P.lcap);
   }
 }
 
@@ -178,17 +205,19 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, int k, const
 //   verlet.cpp:264-391 (order of operations), pair_gran_base.h:257-496 (pair loop),
 //   fix_gravity.cpp:331-339, fix_freeze.cpp:132-144, fix_nve_sphere.cpp:134-244,
 //   neighbor.cpp:1425-1466 (rebuild trigger)
-// Two phases per particle: (1) stream the row, gather the partner positions with several
-// independent loads in flight and build a bit mask of touching slots; (2) pop the set bits,
-// so the lanes of a warp walk their c-th CONTACT together instead of idling through the
-// non-touching slots of their neighbours.
+// Two phases per particle: (1) stream the row with 8 independent position gathers in flight and
+// stage the neighbour words of the TOUCHING entries in shared memory; (2) walk the staged
+// contacts, so the lanes of a warp evaluate their c-th CONTACT together instead of idling
+// through the non-touching slots of their neighbours, prefetching contact c+1 while c computes.
 #ifndef DEM_STEP_MINBLOCKS
 #define DEM_STEP_MINBLOCKS 4
 #endif
-template <int NORMAL, int ROLLING>
+template <int NORMAL, int ROLLING, bool ONE>
 __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
+  __shared__ unsigned s_w[DEM_CMAX][128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = threadIdx.x;
   bool trig = false;
   if (i < P.nlocal) {
     const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
@@ -200,44 +229,59 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       const int nn = nnw & 0xffff;
       int nh = (nnw >> 16) & 0xffff;
       const int nh0 = nh;
-      for (int k0 = 0; k0 < nn; k0 += 64) {
+      int nc = 0;
+      for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += 64) {
         const int kn = min(64, nn - k0);
-        unsigned long long touch = 0ull, close = 0ull;
-#pragma unroll 4
+        unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
+        // (1a) branch-free sweep: 8 neighbour words, then 8 position gathers in flight per thread
+#pragma unroll 8
         for (int kk = 0; kk < kn; kk++) {
           const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
           const double4 xj = ldg4(P.xr + (w & NBR_IDX));
           const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
           const double radsum = xi.w + xj.w;
-          if (rsq < __dmul_rn(radsum, radsum)) {
-            touch |= 1ull << kk;
-            // phase 2 will need the partner's v|m and omega|type records and this pair's history rows:
-            // start those DRAM accesses now, without holding registers for them
-            prefetch_l1(P.vm + (w & NBR_IDX)); prefetch_l1(P.wt + (w & NBR_IDX));
-            if (w & NBR_HIST) {
-              const double *hp = P.hist + (size_t)((((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1) * P.pm.dnum) * P.lcap + i;
-              for (int d = 0; d < P.pm.dnum; d++) prefetch_l1(hp + (size_t)d * P.lcap);
-            }
-          }
-          else if (P.cdf > 1.0 && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) close |= 1ull << kk;
+          const bool t = rsq < __dmul_rn(radsum, radsum);
+          touch |= (unsigned long long)t << kk;
+          if (P.cdf > 1.0) close |= (unsigned long long)(!t && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << kk;
         }
+        // (1b) stage the touching entries; start the partner v|m, omega|type fetches towards L2
         while (touch) {
           const int kk = __ffsll((long long)touch) - 1;
           touch &= touch - 1;
-          pair_contact<NORMAL, ROLLING>(P, i, k0 + kk, xi, vi, wi, itype, imask, su, nh, F, T);
+          const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+          if (nc < DEM_CMAX) s_w[nc++][tid] = w; else extra |= 1ull << kk;
+          prefetch_l2(P.vm + (w & NBR_IDX)); prefetch_l2(P.wt + (w & NBR_IDX));
+        }
+        while (extra) {  // more than DEM_CMAX contacts (rare)
+          const int kk = __ffsll((long long)extra) - 1;
+          extra &= extra - 1;
+          pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + kk) * P.lcap + i], nn, xi, vi, wi, itype, imask, su, nh, F, T);
         }
         while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
           const int kk = __ffsll((long long)close) - 1;
           close &= close - 1;
           const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
           const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-          for (int d = 0; d < P.pm.dnum; d++) P.hist[(size_t)(slot * P.pm.dnum + d) * P.lcap + i] = 0.0;
+          for (int r = 0; r < P.pm.hrec; r++) st4(P.hist + (size_t)(slot * P.pm.hrec + r) * P.lcap + i, make_double4(0., 0., 0., 0.));
         }
+      }
+      if (P.debug & 1) nc = 0;
+      if (nc) prefetch_contact(P, i, s_w[0][tid]);
+      for (int c = 0; c < nc; c++) {
+        const unsigned w = s_w[c][tid];
+        if (c + 1 < nc) prefetch_contact(P, i, s_w[c + 1][tid]);
+        pair_contact<NORMAL, ROLLING, ONE>(P, i, w, nn, xi, vi, wi, itype, imask, su, nh, F, T);
       }
       if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
     }
     if (P.have_g && (imask & 1)) { F[0] += vi.w * P.g[0]; F[1] += vi.w * P.g[1]; F[2] += vi.w * P.g[2]; }
-    if (P.nwalls) walls_of_particle(P, i, xi, vi, wi, itype, su, F, T);
+    if (P.nwc) {  // primitive-wall contacts were evaluated by the k_walls pre-pass
+      const unsigned widx = (unsigned)(__double_as_longlong(P.xh[i].w) >> 32);
+      if (widx) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) { F[d] += P.fw[(size_t)d * P.nwcap + widx - 1]; T[d] += P.fw[(size_t)(3 + d) * P.nwcap + widx - 1]; }
+      }
+    }
     if (imask & P.freezebit) { F[0] = F[1] = F[2] = 0.0; T[0] = T[1] = T[2] = 0.0; }
 
     if (P.mode != MODE_STEP) {  // forces are only materialised when somebody will read them
@@ -438,10 +482,10 @@ struct BuildP {
   GridP G;
   const int *ocs, *oce, *gcs, *gce;  // owned / ghost cell ranges
   double cdf, skin;
-  unsigned *nbr; int *numneigh; int *ptag; double *hist;
+  unsigned *nbr; int *numneigh; int *ptag; double4 *hist;
   // previous list (rows addressed through perm: new i <- old perm[i])
   int have_old, cap_old, dnum_old;
-  const int *perm; const unsigned *nbr_old; const int *numneigh_old; const int *ptag_old; const double *hist_old;
+  const int *perm; const unsigned *nbr_old; const int *numneigh_old; const int *ptag_old; const double4 *hist_old;
   int *overflow;
 };
 __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
@@ -480,7 +524,7 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
                       const int so = (int)((wo & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
                       if (nh < B.hslots) {
                         w |= (unsigned)(nh + 1) << NBR_SLOT_SHIFT;
-                        for (int d = 0; d < B.dnum; d++)
+                        for (int d = 0; d < B.dnum; d++)  // dnum = 32-byte records per contact here
                           B.hist[(size_t)(nh * B.dnum + d) * B.cap + i] = B.hist_old[(size_t)(so * B.dnum + d) * B.cap_old + oi];
                       }
                       nh++;
@@ -504,7 +548,16 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
 }
 
 // positions at build time (neighbor.cpp:1486-1510) + primitive-wall candidate bits (primitive_wall.h:129-138)
-__global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 *xh, const unsigned *valid_in, const WallP *walls, int nwalls, double skin)
+__global__ void __launch_bounds__(256) k_wall_index(int n, const int *flag, const int *scan, int *wlist, double4 *xh)
+{  // compact list of wall candidates + the particle's position in it (upper 32 bits of xh.w, +1)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const int c = scan[i];
+  wlist[c] = i;
+  const long long b = (__double_as_longlong(xh[i].w) & 0xffffffffLL) | ((long long)(c + 1) << 32);
+  xh[i].w = __longlong_as_double(b);
+}
+__global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 *xh, const unsigned *valid_in, const WallP *walls, int nwalls, double skin, int *cflag)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -529,6 +582,7 @@ __global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 
   const unsigned valid = valid_in ? valid_in[i] : 0u;
   double4 o; o.x = x.x; o.y = x.y; o.z = x.z; o.w = __longlong_as_double((long long)(cand | (valid << 16)));
   xh[i] = o;
+  if (cflag) cflag[i] = cand != 0;
 }
 __global__ void __launch_bounds__(256) k_extract_valid(int n, const int *perm, const double4 *xh, unsigned *valid)
 {

@@ -25,7 +25,8 @@ enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_SQ2Y, T_SQ8
 struct ModelP {
   int normal, tangential, rolling;
   int tdamp, limitForce, torsion, ktToKn;
-  int dnum, off_shear, off_roll;
+  int dnum, off_shear, off_roll;  // reference layout of a history row (fix_contact_history)
+  int hrec, rec_shear, rec_roll;   // device layout: hrec 32-byte records per contact, one per sub-model
 };
 
 struct WallP {
@@ -49,19 +50,24 @@ struct StepP {
   double4 *xh;  // (xhold, bits(wall candidate | wall-history-valid << 16))
   unsigned *nbr;
   int *numneigh;
-  double *hist;   // [hslots*dnum][lcap], slot-major: contact c of particle i at rows c*dnum..c*dnum+dnum-1
+  double4 *hist;  // [hslots*hrec][lcap] 32-byte records: contact slot c of particle i at rows c*hrec..
   int hslots;
   double *whist;  // [sum wall dnum][cap]
   double *f, *tq; // [3][cap]
   const WallP *walls;
   int nwalls;
+  int nwc, nwcap;     // primitive-wall candidates (compact list) and row stride of fw
+  const int *wlist;   // [nwc] particle index
+  double *fw;         // [6][nwcap] wall force / torque of candidate c
   ModelP pm;
   const double *tab;
   int nt1;  // ntypes+1
+  double t1[T_COUNT];  // the tables' single entry when ntypes == 1
   double dt, dtv, dtf, dtfrot, nktv2p, charVel, cdf, cdfsq, trigsq, cutneighmax;
   double g[3];
   int have_g, have_pair, freezebit, integbit;
   int mode;
+  int debug;  // profiling aid (option "debug"): bit0 skip contact evaluation, bit1 skip list walk
   int *flag;  // [0] rebuild trigger, [1] history-slot overflow (mapped host memory)
   unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
 };
