@@ -37,6 +37,12 @@ enum dem_status {
  * stream   cudaStream_t to launch on (NULL = legacy default stream).                  */
 int dem_create(dem_engine **out, int device, int rank, int nranks, const void *nccl_id, void *stream);
 void dem_destroy(dem_engine *e);
+/* multi-GPU plumbing: rank 0 creates the 128-byte ncclUniqueId and shares it (e.g. torch.distributed broadcast)
+ * before every rank calls dem_create.  replaces: MPI_Init / MPI_COMM_WORLD of lammps_open  src/library.h:59  */
+int dem_nccl_unique_id(void *out128);
+/* the brick this rank owns (processor grid, grid position, sub-box): Comm::set_proc_grid  src/comm.cpp,
+ * Domain::set_local_box  src/domain.cpp.  Pure host logic, valid after dem_set_box / dem_set_processors.  */
+int dem_decomposition(dem_engine *e, int pgrid[3], int myloc[3], double sublo[3], double subhi[3]);
 const char *dem_last_error(const dem_engine *e);
 const char *dem_version(void);
 

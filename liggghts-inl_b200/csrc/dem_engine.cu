@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "../../include/dem_b200.h"
 #include "dem_kernels.cuh"
 
@@ -21,6 +24,34 @@ using namespace dem;
 #define MAXT 8
 
 struct DemFail { int code; };
+
+// NCCL is bound at run time (dlopen) so that single-GPU use needs no NCCL at all and multi-GPU use
+// shares the copy torch.distributed already loaded into the process.
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load()
+  {
+    if (h) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int k = 0; names[k] && !h; k++) h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+#define NCCL_SYM(f) f = (decltype(f))dlsym(h, "nccl" #f); if (!f) return false;
+    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(Send) NCCL_SYM(Recv) NCCL_SYM(AllReduce)
+    NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
+#undef NCCL_SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
 static void dem_fail(dem_engine *e, int code, const char *fmt, ...);
 
 #define CK(call)                                                                                   \
@@ -79,8 +110,19 @@ struct dem_engine {
   DevBuf<WallP> dwalls;
   DevBuf<unsigned> valid_tmp;
   DevBuf<int> wlist; DevBuf<double> fw; int nwc = 0, nwcap = 0;
-  // ghosts
-  DevBuf<int> gsrc, gshift, gsrc2, gshift2, flo, fhi, slo, shi;
+  // brick decomposition (comm_brick.cpp / procmap.cpp): rank -> (ix,iy,iz), sub-box, 6 neighbours
+  int pgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0}, user_grid = 0;
+  double sublo[3] = {0, 0, 0}, subhi[3] = {1, 1, 1};
+  ncclComm_t comm = nullptr;
+  // ghost swaps, LAMMPS order: for dim 0..2: (send to lo neighbour, send to hi neighbour)
+  struct Swap { int dim = 0, side = 0, peer = -1, self = 0, nsend = 0, nrecv = 0, gfirst = 0; double shift = 0.0; DevBuf<int> list; };
+  Swap swaps[6]; int nswap = 0;
+  DevBuf<double4> sbuf, rbuf_unused;
+  DevBuf<int> sbuf_i, gorder, gone, cnt_dev;
+  DevBuf<double> migs, migr;
+  int *hcnt = nullptr;  // pinned host scratch for counts
+  DevBuf<int> dflag;    // device-side rebuild trigger (multi-rank: all-reduced)
+  DevBuf<int> flo, fhi, slo, shi;
   // cells / sort
   GridP grid = {};
   long ncells = 0;
@@ -122,6 +164,11 @@ void DevBuf<T>::ensure(dem_engine *E, size_t m, size_t keep, cudaStream_t st)
   p = q; n = m;
 }
 
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess) dem_fail(E, DEM_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+  } while (0)
 #define GRID(n, b) (unsigned)(((n) + (b)-1) / (b))
 #define API_BEGIN  if (!e) return DEM_ERR_ARG; dem_engine *E = e; (void)E; try {
 #define API_END    } catch (const DemFail &f) { return f.code; } catch (const std::exception &x) { e->err = x.what(); return DEM_ERR_CUDA; } return DEM_OK;
@@ -147,12 +194,27 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
     if (prop.major < 10) dem_fail(e, DEM_ERR_CUDA, "device %d is sm_%d%d; this library only contains sm_100a code", device, prop.major, prop.minor);
     CK(cudaSetDevice(device));
     e->device = device; e->rank = rank; e->nranks = nranks; e->stream = (cudaStream_t)stream;
-    if (nranks != 1) dem_fail(e, DEM_ERR_UNSUPPORTED, "multi-rank bricks are not enabled in this build yet");
-    (void)nccl_id;
+    if (nranks < 1 || rank < 0 || rank >= nranks) dem_fail(e, DEM_ERR_ARG, "bad rank/nranks %d/%d", rank, nranks);
+    if (nranks > 1) {
+      if (!nccl_id) dem_fail(e, DEM_ERR_ARG, "nranks > 1 needs the shared 128-byte ncclUniqueId (dem_nccl_unique_id on rank 0)");
+      if (!g_nccl.load()) dem_fail(e, DEM_ERR_CUDA, "could not load libnccl.so.2");
+      ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
+      NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+    }
+    CK(cudaHostAlloc((void **)&e->hcnt, 64 * sizeof(int), cudaHostAllocDefault));
     CK(cudaHostAlloc((void **)&e->hflag, 4 * sizeof(int), cudaHostAllocMapped));
     e->hflag[0] = e->hflag[1] = 0;
     e->pm.tdamp = 1;
   } catch (const DemFail &f) { return f.code; }
+  return DEM_OK;
+}
+
+extern "C" int dem_nccl_unique_id(void *out128)
+{
+  if (!out128 || !g_nccl.load()) return DEM_ERR_CUDA;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return DEM_ERR_CUDA;
+  memcpy(out128, &id, sizeof id);
   return DEM_OK;
 }
 
@@ -164,13 +226,15 @@ extern "C" void dem_destroy(dem_engine *e)
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
   e->xh.release(); e->tag.release(); e->tag_tmp.release(); e->density.release(); e->density_tmp.release();
   e->f.release(); e->tq.release(); e->whist.release(); e->whist_tmp.release(); e->tab.release(); e->dwalls.release();
-  e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->gsrc.release(); e->gshift.release(); e->gsrc2.release(); e->gshift2.release();
+  e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
   e->cubtmp.release(); e->overflow.release(); e->counters.release();
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   if (e->hflag) cudaFreeHost(e->hflag);
+  if (e->hcnt) cudaFreeHost(e->hcnt);
+  if (e->comm) g_nccl.CommDestroy(e->comm);
   delete e;
 }
 
@@ -208,6 +272,7 @@ extern "C" int dem_set_processors(dem_engine *e, int px, int py, int pz)
 {
   API_BEGIN
   if (px * py * pz != e->nranks) dem_fail(e, DEM_ERR_ARG, "processors grid %dx%dx%d != nranks %d", px, py, pz, e->nranks);
+  e->pgrid[0] = px; e->pgrid[1] = py; e->pgrid[2] = pz; e->user_grid = 1;
   API_END
 }
 extern "C" int dem_set_neighbor(dem_engine *e, double skin, int every, int delay, int check)
@@ -399,6 +464,44 @@ static void ensure_particle_cap(dem_engine *E, long need, long keep)
   E->cap = (int)ncap;
 }
 
+
+// uniform brick of ranks over the box (procmap.cpp / Comm::set_proc_grid): unless `processors` fixed it,
+// all ranks form slabs along the longest periodic axis (else the longest axis) -- NVSwitch gives every
+// pair of GPUs the same bandwidth, so 1-D slabs minimise the number of messages per step
+static void setup_decomposition(dem_engine *E)
+{
+  if (!E->user_grid) {
+    int best = 0; double bl = -1.0;
+    for (int d = 0; d < 3; d++) { const double l = E->prd[d] * (E->periodic[d] ? 1.0 : 0.999); if (l > bl) { bl = l; best = d; } }
+    E->pgrid[0] = E->pgrid[1] = E->pgrid[2] = 1; E->pgrid[best] = E->nranks;
+  }
+  int r = E->rank;
+  E->myloc[0] = r % E->pgrid[0]; r /= E->pgrid[0];
+  E->myloc[1] = r % E->pgrid[1]; r /= E->pgrid[1];
+  E->myloc[2] = r;
+  for (int d = 0; d < 3; d++) {
+    E->sublo[d] = E->lo[d] + E->prd[d] * E->myloc[d] / E->pgrid[d];
+    E->subhi[d] = (E->myloc[d] == E->pgrid[d] - 1) ? E->hi[d] : E->lo[d] + E->prd[d] * (E->myloc[d] + 1) / E->pgrid[d];
+  }
+}
+static int rank_of(dem_engine *E, int ix, int iy, int iz) { return (iz * E->pgrid[1] + iy) * E->pgrid[0] + ix; }
+static int neighbor_rank(dem_engine *E, int dim, int dir)
+{  // dir -1 / +1; returns -1 when there is no neighbour across a non-periodic face
+  int loc[3] = {E->myloc[0], E->myloc[1], E->myloc[2]};
+  loc[dim] += dir;
+  if (loc[dim] < 0) { if (!E->periodic[dim]) return -1; loc[dim] = E->pgrid[dim] - 1; }
+  if (loc[dim] >= E->pgrid[dim]) { if (!E->periodic[dim]) return -1; loc[dim] = 0; }
+  return rank_of(E, loc[0], loc[1], loc[2]);
+}
+
+extern "C" int dem_decomposition(dem_engine *e, int pgrid[3], int myloc[3], double sublo[3], double subhi[3])
+{
+  API_BEGIN
+  setup_decomposition(e);
+  for (int d = 0; d < 3; d++) { if (pgrid) pgrid[d] = e->pgrid[d]; if (myloc) myloc[d] = e->myloc[d]; if (sublo) sublo[d] = e->sublo[d]; if (subhi) subhi[d] = e->subhi[d]; }
+  API_END
+}
+
 extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
                                     const double *v, const double *omega, const double *radius, const double *density)
 {
@@ -409,8 +512,9 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
   e->cap = 0;  // force fresh allocation
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
   e->xh.release(); e->tag.release(); e->density.release(); e->f.release(); e->tq.release(); e->whist.release();
-  ensure_particle_cap(e, std::max<long>(n + n / 4 + 1024, 1024), 0);
-  std::vector<double4> hx(n), hv(n), hw(n);
+  setup_decomposition(e);
+  std::vector<double4> hx, hv, hw; std::vector<int> htag; std::vector<double> hden;
+  hx.reserve(n / e->nranks + 16); hv.reserve(n / e->nranks + 16); hw.reserve(n / e->nranks + 16);
   double rmax = 0.0;
   for (long i = 0; i < n; i++) {
     if (type[i] < 1 || type[i] > e->ntypes) dem_fail(e, DEM_ERR_ARG, "Invalid atom type in particle %ld", i);
@@ -418,12 +522,30 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     if (tag[i] <= 0) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle %ld", i);
     const double r = radius[i];
     const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * density[i];  // atom_vec_sphere.cpp:1078
-    hx[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
-    hv[i] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
+    rmax = std::max(rmax, r);  // global maximum: every rank sees the full set
+    if (e->nranks > 1) {  // ownership test on the wrapped position (Domain::pbc + sub-box, like read_data)
+      bool mine = true;
+      for (int d = 0; d < 3 && mine; d++) {
+        double c = x[3 * i + d];
+        if (e->periodic[d]) { if (c < e->lo[d]) c += e->prd[d]; if (c >= e->hi[d]) { c -= e->prd[d]; c = std::max(c, e->lo[d]); } }
+        const bool lo_ok = c >= e->sublo[d] || (e->myloc[d] == 0 && !e->periodic[d]);
+        const bool hi_ok = c < e->subhi[d] || (e->myloc[d] == e->pgrid[d] - 1 && !e->periodic[d]);
+        mine = lo_ok && hi_ok;
+      }
+      if (!mine) continue;
+    }
+    hx.push_back(make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r));
+    hv.push_back(make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m));
     const long long bits = pack_bits(type[i], mask ? mask[i] : 1);
     double wb; memcpy(&wb, &bits, 8);
-    hw[i] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0., wb);
-    rmax = std::max(rmax, r);
+    hw.push_back(make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0., wb));
+    htag.push_back(tag[i]); hden.push_back(density[i]);
+  }
+  n = (long)hx.size();
+  tag = htag.data(); density = hden.data();
+  {
+    const double cf = e->opt.count("cap_factor") ? e->opt["cap_factor"] : (e->nranks > 1 ? 1.5 : 1.25);
+    ensure_particle_cap(e, std::max<long>((long)(n * cf) + 1024, 1024), 0);
   }
   e->cur = 0;
   if (n) {
@@ -484,7 +606,7 @@ static void derive_tables(dem_engine *E)
 }
 
 static void setup_grid(dem_engine *E)
-{
+{  // cell grid over this rank's sub-box plus one layer of cells for the ghosts (neighbor.cpp:1647-1812 analogue)
   E->cutneighmax = 2.0 * E->rmax * E->cdf + E->skin;  // pair_gran.cpp:591-603 + neighbor skin
   if (!(E->cutneighmax > 0)) dem_fail(E, DEM_ERR_STATE, "neighbour cutoff is zero (no particles or zero radius)");
   long total = 1;
@@ -492,17 +614,21 @@ static void setup_grid(dem_engine *E)
   for (int pass = 0; pass < 64; pass++) {
     total = 1;
     for (int d = 0; d < 3; d++) {
-      int nc = (int)floor(E->prd[d] / cell); if (nc < 1) nc = 1;
-      const double size = E->prd[d] / nc;
-      E->grid.nc[d] = nc + 2; E->grid.inv[d] = 1.0 / size; E->grid.org[d] = E->lo[d] - size;
+      const double len = E->subhi[d] - E->sublo[d];
+      int nc = (int)floor(len / cell); if (nc < 1) nc = 1;
+      const double size = len / nc;
+      E->grid.nc[d] = nc + 2; E->grid.inv[d] = 1.0 / size; E->grid.org[d] = E->sublo[d] - size;
       total *= (nc + 2);
     }
     if (total <= (1L << 25)) break;
     cell *= 1.3;
   }
-  for (int d = 0; d < 3; d++)
+  for (int d = 0; d < 3; d++) {
     if (E->periodic[d] && E->prd[d] < 2.0 * E->cutneighmax)
       dem_fail(E, DEM_ERR_UNSUPPORTED, "periodic box length in dim %d is below two neighbour cutoffs", d);
+    if (E->pgrid[d] > 1 && E->subhi[d] - E->sublo[d] < 2.0 * E->cutneighmax)
+      dem_fail(E, DEM_ERR_UNSUPPORTED, "sub-box of a rank in dim %d is thinner than two neighbour cutoffs", d);
+  }
   E->grid.morton = (E->grid.nc[0] <= 1024 && E->grid.nc[1] <= 1024 && E->grid.nc[2] <= 1024) ? 1 : 0;
   if (E->opt.count("morton") && E->opt["morton"] == 0) E->grid.morton = 0;
   E->ncells = total;
@@ -517,20 +643,75 @@ static void ensure_cub(dem_engine *E, size_t n)
   E->cubtmp.ensure(E, std::max(b1, b2) + 256);
 }
 
-static GhostP ghost_params(dem_engine *E)
+// exchange `n` ints with the two peers of a swap (either may be -1)
+static void xchg_ints(dem_engine *E, int peer_send, const int *sendv, int peer_recv, int *recvv, int n)
 {
-  GhostP G;
-  G.nghost = (int)E->nghost; G.nlocal = (int)E->nlocal; G.src = E->gsrc.p; G.shift = E->gshift.p;
-  for (int d = 0; d < 3; d++) G.prd[d] = E->prd[d];
-  G.xr = E->xr[E->cur].p; G.vm = E->vm[E->cur].p; G.wt = E->wt[E->cur].p; G.with_static = 1;
-  return G;
+  cudaStream_t st = E->stream;
+  E->cnt_dev.ensure(E, 64);
+  for (int k = 0; k < n; k++) { E->hcnt[k] = sendv[k]; E->hcnt[32 + k] = 0; }
+  CK(cudaMemcpyAsync(E->cnt_dev.p, E->hcnt, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(E->cnt_dev.p + 32, 0, n * sizeof(int), st));
+  NK(g_nccl.GroupStart());
+  if (peer_send >= 0) NK(g_nccl.Send(E->cnt_dev.p, n, ncclInt, peer_send, E->comm, st));
+  if (peer_recv >= 0) NK(g_nccl.Recv(E->cnt_dev.p + 32, n, ncclInt, peer_recv, E->comm, st));
+  NK(g_nccl.GroupEnd());
+  CK(cudaMemcpyAsync(E->hcnt + 32, E->cnt_dev.p + 32, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < n; k++) recvv[k] = E->hcnt[32 + k];
 }
-static void ghost_update(dem_engine *E, int g0, int g1)
+
+// flags -> deterministic compact list; returns the number of set flags
+static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &scan, DevBuf<int> &list)
 {
-  if (g1 <= g0) return;
-  GhostP G = ghost_params(E);
-  k_ghost_update<<<GRID(g1 - g0, 256), 256, 0, E->stream>>>(G, g0, g1);
-  E->launches++;
+  cudaStream_t st = E->stream;
+  if (n <= 0) return 0;
+  size_t tb = E->cubtmp.n;
+  CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, flag.p, scan.p, n, st));
+  CK(cudaMemcpyAsync(&E->hcnt[60], flag.p + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&E->hcnt[61], scan.p + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int cnt = E->hcnt[60] + E->hcnt[61];
+  if (cnt) { list.ensure(E, cnt + 1); k_compact<<<GRID(n, 256), 256, 0, st>>>(n, flag.p, scan.p, list.p); }
+  E->launches += 2;
+  return cnt;
+}
+
+// per-step ghost refresh == CommBrick::forward_comm (comm_brick.cpp:563-645): one pack kernel per swap; periodic
+// images on the same rank are written in place, remote ghosts travel as three NCCL send/recv pairs that land
+// directly in the ghost region of the record arrays.  Swaps run in order so that edge/corner ghosts propagate.
+static void do_swap(dem_engine *E, dem_engine::Swap &W)
+{
+  cudaStream_t st = E->stream;
+  const int c = E->cur;
+  SwapP S;
+  S.n = W.nsend; S.list = W.list.p; S.dim = W.dim; S.shift = W.shift; S.xr = E->xr[c].p; S.vm = E->vm[c].p; S.wt = E->wt[c].p;
+  if (W.self) {
+    if (!W.nsend) return;
+    S.ox = E->xr[c].p + W.gfirst; S.ov = E->vm[c].p + W.gfirst; S.ow = E->wt[c].p + W.gfirst;
+    k_pack_swap<<<GRID(W.nsend, 256), 256, 0, st>>>(S);
+    E->launches++;
+    return;
+  }
+  if (W.nsend) {
+    E->sbuf.ensure(E, 3 * (size_t)W.nsend, 0, st);
+    S.ox = E->sbuf.p; S.ov = E->sbuf.p + W.nsend; S.ow = E->sbuf.p + 2 * (size_t)W.nsend;
+    k_pack_swap<<<GRID(W.nsend, 256), 256, 0, st>>>(S);
+    E->launches++;
+  }
+  const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+  NK(g_nccl.GroupStart());
+  if (peer_send >= 0 && W.nsend)
+    for (int a = 0; a < 3; a++) NK(g_nccl.Send(E->sbuf.p + (size_t)a * W.nsend, 4 * (size_t)W.nsend, ncclDouble, peer_send, E->comm, st));
+  if (peer_recv >= 0 && W.nrecv) {
+    NK(g_nccl.Recv(E->xr[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+    NK(g_nccl.Recv(E->vm[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+    NK(g_nccl.Recv(E->wt[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+  }
+  NK(g_nccl.GroupEnd());
+}
+static void forward_comm(dem_engine *E)
+{
+  for (int q = 0; q < E->nswap; q++) do_swap(E, E->swaps[q]);
 }
 
 static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum, int hslots)
@@ -543,25 +724,104 @@ static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum, 
   }
 }
 
+// particle migration between bricks: CommBrick::exchange (comm_brick.cpp:732-860); runs BEFORE the periodic
+// wrap so that the direction is decided on the unwrapped coordinate (the sender wraps while packing)
+static int migrate(dem_engine *E, int ncur, int &ngone)
+{
+  cudaStream_t st = E->stream;
+  const int c = E->cur;
+  ListSet &Lold = E->ls[E->lcur];
+  const bool hist = Lold.valid && Lold.dnum > 0;
+  const int hrec = hist ? Lold.dnum : 0;
+  ngone = 0;
+  E->gone.ensure(E, E->cap); CK(cudaMemsetAsync(E->gone.p, 0, (size_t)E->cap * sizeof(int), st));
+  for (int d = 0; d < 3; d++) {
+    if (E->pgrid[d] == 1) continue;
+    const int plo = neighbor_rank(E, d, -1), phi = neighbor_rank(E, d, 1);
+    E->flo.ensure(E, ncur + 1); E->fhi.ensure(E, ncur + 1); E->slo.ensure(E, ncur + 1); E->shi.ensure(E, ncur + 1);
+    if (ncur) k_mig_flag<<<GRID(ncur, 256), 256, 0, st>>>(ncur, E->xr[c].p, d, E->sublo[d], E->subhi[d], plo >= 0, phi >= 0, E->flo.p, E->fhi.p, E->gone.p);
+    E->launches++;
+    DevBuf<int> lists[2];
+    int nsend[2] = {compact_flags(E, ncur, E->flo, E->slo, lists[0]), 0};
+    nsend[1] = compact_flags(E, ncur, E->fhi, E->shi, lists[1]);
+    for (int side = 0; side < 2; side++) {
+      const int peer_send = side ? phi : plo, peer_recv = side ? plo : phi;
+      int H = 0;
+      if (hist && nsend[side]) {
+        CK(cudaMemsetAsync(E->overflow.p, 0, sizeof(int), st));
+        k_max_nh<<<GRID(nsend[side], 256), 256, 0, st>>>(nsend[side], lists[side].p, Lold.numneigh.p, E->overflow.p);
+        CK(cudaMemcpyAsync(&E->hcnt[62], E->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        H = E->hcnt[62];
+      }
+      int sv[2] = {nsend[side], H}, rv[2] = {0, 0};
+      xchg_ints(E, peer_send, sv, peer_recv, rv, 2);
+      const int nrecv = rv[0], Hr = rv[1];
+      MigP M;
+      memset(&M, 0, sizeof M);
+      M.nwrows = E->nwrows; M.hrec = hrec; M.cap = E->cap; M.lcap = Lold.cap; M.dim = d;
+      M.periodic = E->periodic[d]; M.wrap_lo = E->lo[d]; M.wrap_hi = E->hi[d]; M.prd = E->prd[d];
+      M.density = E->density.p; M.whist = E->whist.p;
+      if (hist) { M.nbr = Lold.nbr.p; M.numneigh = Lold.numneigh.p; M.ptag = Lold.ptag.p; M.hist = Lold.hist.p; M.hslots = Lold.hslots; M.maxk = Lold.maxk; }
+      const int ss = 16 + E->nwrows + H * (1 + 4 * hrec), sr = 16 + E->nwrows + Hr * (1 + 4 * hrec);
+      if (nsend[side]) {
+        E->migs.ensure(E, (size_t)nsend[side] * ss);
+        M.n = nsend[side]; M.stride = ss; M.hmax = H; M.list = lists[side].p; M.buf = E->migs.p;
+        M.xr = E->xr[c].p; M.vm = E->vm[c].p; M.wt = E->wt[c].p; M.xh = E->xh.p; M.tag = E->tag.p;
+        k_mig_pack<<<GRID(M.n, 128), 128, 0, st>>>(M);
+        E->launches++;
+      }
+      if (nrecv) {
+        if ((long)ncur + nrecv > E->cap) ensure_particle_cap(E, (long)ncur + nrecv, ncur);
+        if (hist && (ncur + nrecv > Lold.cap || Hr > Lold.maxk || Hr > Lold.hslots))
+          dem_fail(E, DEM_ERR_OVERFLOW, "migration does not fit the neighbour rows (raise options cap_factor / maxneigh / histslots)");
+        E->migr.ensure(E, (size_t)nrecv * sr);
+      }
+      NK(g_nccl.GroupStart());
+      if (peer_send >= 0 && nsend[side]) NK(g_nccl.Send(E->migs.p, (size_t)nsend[side] * ss, ncclDouble, peer_send, E->comm, st));
+      if (peer_recv >= 0 && nrecv) NK(g_nccl.Recv(E->migr.p, (size_t)nrecv * sr, ncclDouble, peer_recv, E->comm, st));
+      NK(g_nccl.GroupEnd());
+      if (nrecv) {
+        E->gone.ensure(E, E->cap, ncur, st);
+        CK(cudaMemsetAsync(E->gone.p + ncur, 0, (size_t)nrecv * sizeof(int), st));
+        M.n = nrecv; M.stride = sr; M.hmax = Hr; M.buf = E->migr.p; M.cap = E->cap;
+        M.xr = E->xr[E->cur].p; M.vm = E->vm[E->cur].p; M.wt = E->wt[E->cur].p; M.xh = E->xh.p; M.tag = E->tag.p;
+        M.density = E->density.p; M.whist = E->whist.p;
+        k_mig_unpack<<<GRID(nrecv, 128), 128, 0, st>>>(M, ncur);
+        E->launches++;
+        ncur += nrecv;
+      }
+      ngone += nsend[side];
+    }
+    lists[0].release(); lists[1].release();
+  }
+  return ncur;
+}
+
 // Neighbor rebuild: verlet.cpp:305-328 (pre_exchange .. neighbor->build) re-designed for the GPU.
 static void rebuild(dem_engine *E)
 {
   cudaStream_t st = E->stream;
-  const int n = (int)E->nlocal;
   const int dnum = E->have_pair ? E->pm.hrec : 0;  // history records per contact
   ensure_cub(E, (size_t)E->cap);
-  E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->perm.ensure(E, E->cap);
   E->overflow.ensure(E, 2);
   BoxP B;
   for (int d = 0; d < 3; d++) { B.lo[d] = E->lo[d]; B.hi[d] = E->hi[d]; B.prd[d] = E->prd[d]; B.periodic[d] = E->periodic[d]; }
+  // 0. migration between bricks (multi-rank only)
+  int ncur = (int)E->nlocal, ngone = 0;
+  if (E->nranks > 1) ncur = migrate(E, ncur, ngone);
+  const int n = ncur - ngone;
+  ensure_cub(E, (size_t)E->cap);
+  E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->perm.ensure(E, E->cap);
   int c = E->cur;
-  if (n) {
+  if (ncur) {
     // 1. pbc wrap, cell keys, radix sort, gather the particle records into cell (Morton) order
-    k_wrap_key<<<GRID(n, 256), 256, 0, st>>>(n, E->xr[c].p, E->grid, B, E->keys.p, E->vals.p);
+    k_wrap_key<<<GRID(ncur, 256), 256, 0, st>>>(ncur, E->xr[c].p, E->grid, B, E->keys.p, E->vals.p, E->nranks > 1 ? E->gone.p : nullptr);
     size_t tb = E->cubtmp.n;
-    int endbit = 32;
-    if (E->grid.morton) endbit = 30; else { endbit = 1; while ((1L << endbit) < E->ncells) endbit++; }
-    CK(cub::DeviceRadixSort::SortPairs(E->cubtmp.p, tb, E->keys.p, E->keys2.p, E->vals.p, E->perm.p, n, 0, endbit, st));
+    CK(cub::DeviceRadixSort::SortPairs(E->cubtmp.p, tb, E->keys.p, E->keys2.p, E->vals.p, E->perm.p, ncur, 0, 32, st));
+    E->launches += 2;
+  }
+  if (n) {
     k_gather4<<<GRID(n, 256), 256, 0, st>>>(n, E->perm.p, E->xr[c].p, E->xr[c ^ 1].p, E->vm[c].p, E->vm[c ^ 1].p, E->wt[c].p, E->wt[c ^ 1].p);
     k_gather_rows<int><<<GRID(n, 256), 256, 0, st>>>(n, 1, 0, 0, E->perm.p, E->tag.p, E->tag_tmp.p);
     k_gather_rows<double><<<GRID(n, 256), 256, 0, st>>>(n, 1, 0, 0, E->perm.p, E->density.p, E->density_tmp.p);
@@ -573,75 +833,80 @@ static void rebuild(dem_engine *E)
       E->launches++;
     }
     k_extract_valid<<<GRID(n, 256), 256, 0, st>>>(n, E->perm.p, E->xh.p, E->valid_tmp.p);
-    E->launches += 6;
+    E->launches += 4;
     E->cur = c ^ 1; c = E->cur;
   }
+  E->nlocal = n;
   // 2. owned cell ranges
   CK(cudaMemsetAsync(E->ocs.p, 0, E->ncells * sizeof(int), st)); CK(cudaMemsetAsync(E->oce.p, 0, E->ncells * sizeof(int), st));
   CK(cudaMemsetAsync(E->gcs.p, 0, E->ncells * sizeof(int), st)); CK(cudaMemsetAsync(E->gce.p, 0, E->ncells * sizeof(int), st));
   if (n) { k_cell_ranges<<<GRID(n, 256), 256, 0, st>>>(n, 0, E->xr[c].p, E->grid, E->ocs.p, E->oce.p); E->launches++; }
-  // 3. periodic images (ghosts), one dimension after the other so that edges/corners propagate
-  E->nghost = 0;
-  for (int d = 0; d < 3 && n; d++) {
-    if (!E->periodic[d]) continue;
+  // 3. ghosts: CommBrick::borders (comm_brick.cpp:884-1117).  One dimension after the other, two swaps per
+  // dimension, candidates = owned + ghosts of earlier dimensions, so edges and corners propagate.
+  E->nghost = 0; E->nswap = 0;
+  for (int d = 0; d < 3; d++) {
+    const bool multi = E->pgrid[d] > 1;
+    if (!multi && !E->periodic[d]) continue;
+    if (!multi && n == 0) continue;
+    const int plo = multi ? neighbor_rank(E, d, -1) : E->rank, phi = multi ? neighbor_rank(E, d, 1) : E->rank;
     const int n0 = (int)(E->nlocal + E->nghost);
     E->flo.ensure(E, n0 + 1); E->fhi.ensure(E, n0 + 1); E->slo.ensure(E, n0 + 1); E->shi.ensure(E, n0 + 1);
-    k_border_flag<<<GRID(n0, 256), 256, 0, st>>>(n0, E->xr[c].p, d, E->lo[d] + E->cutneighmax, E->hi[d] - E->cutneighmax, E->flo.p, E->fhi.p);
-    size_t tb = E->cubtmp.n;
-    CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, E->flo.p, E->slo.p, n0, st));
-    tb = E->cubtmp.n;
-    CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, E->fhi.p, E->shi.p, n0, st));
-    int last[4];
-    CK(cudaMemcpyAsync(&last[0], E->flo.p + n0 - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&last[1], E->slo.p + n0 - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&last[2], E->fhi.p + n0 - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&last[3], E->shi.p + n0 - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const int nlo = last[0] + last[1], nhi = last[2] + last[3];
-    E->launches += 3;
-    if (nlo + nhi == 0) continue;
-    ensure_particle_cap(E, (long)n0 + nlo + nhi, n0);
-    const long ng = E->nghost + nlo + nhi;
-    E->gsrc.ensure(E, ng + 1, E->nghost, st); E->gshift.ensure(E, 3 * (ng + 1), 3 * E->nghost, st);
-    k_border_scatter<<<GRID(n0, 256), 256, 0, st>>>(n0, n, d, E->flo.p, E->slo.p, E->fhi.p, E->shi.p, nlo, (int)E->nghost, E->gsrc.p, E->gshift.p);
+    // no neighbour on a side: the flag can never be set (cut beyond the data)
+    const double lo_cut = plo >= 0 ? E->sublo[d] + E->cutneighmax : -1e300, hi_cut = phi >= 0 ? E->subhi[d] - E->cutneighmax : 1e300;
+    if (n0) k_border_flag<<<GRID(n0, 256), 256, 0, st>>>(n0, E->xr[c].p, d, lo_cut, hi_cut, E->flo.p, E->fhi.p);
     E->launches++;
-    const int g0 = (int)E->nghost;
-    E->nghost = ng;
-    ghost_update(E, g0, (int)ng);
+    for (int side = 0; side < 2; side++) {
+      dem_engine::Swap &W = E->swaps[E->nswap];
+      W.dim = d; W.side = side; W.self = multi ? 0 : 1;
+      W.nsend = compact_flags(E, n0, side ? E->fhi : E->flo, side ? E->shi : E->slo, W.list);
+      W.shift = 0.0;
+      if (E->periodic[d] && side == 0 && E->myloc[d] == 0) W.shift = E->prd[d];
+      if (E->periodic[d] && side == 1 && E->myloc[d] == E->pgrid[d] - 1) W.shift = -E->prd[d];
+      const int peer_send = side ? phi : plo, peer_recv = side ? plo : phi;
+      if (multi) { int sv[1] = {W.nsend}, rv[1] = {0}; xchg_ints(E, peer_send, sv, peer_recv, rv, 1); W.nrecv = rv[0]; }
+      else W.nrecv = W.nsend;
+      W.gfirst = (int)(E->nlocal + E->nghost);
+      if (W.gfirst + W.nrecv > E->cap) ensure_particle_cap(E, (long)W.gfirst + W.nrecv, W.gfirst);
+      c = E->cur;
+      // tags of the new ghosts
+      if (W.self) { if (W.nsend) k_pack_int<<<GRID(W.nsend, 256), 256, 0, st>>>(W.nsend, W.list.p, E->tag.p, E->tag.p + W.gfirst); }
+      else {
+        if (W.nsend) { E->sbuf_i.ensure(E, W.nsend); k_pack_int<<<GRID(W.nsend, 256), 256, 0, st>>>(W.nsend, W.list.p, E->tag.p, E->sbuf_i.p); }
+        NK(g_nccl.GroupStart());
+        if (peer_send >= 0 && W.nsend) NK(g_nccl.Send(E->sbuf_i.p, W.nsend, ncclInt, peer_send, E->comm, st));
+        if (peer_recv >= 0 && W.nrecv) NK(g_nccl.Recv(E->tag.p + W.gfirst, W.nrecv, ncclInt, peer_recv, E->comm, st));
+        NK(g_nccl.GroupEnd());
+      }
+      E->launches++;
+      E->nghost += W.nrecv;
+      E->nswap++;
+    }
+    // records of this dimension's new ghosts (the next dimension's flags look at them)
+    do_swap(E, E->swaps[E->nswap - 2]);
+    do_swap(E, E->swaps[E->nswap - 1]);
   }
-  // 4. ghosts into cell order
+  // 4. cell order of the ghosts (storage keeps the swap order so that NCCL can receive in place)
   if (E->nghost) {
     const int ng = (int)E->nghost;
-    E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap);
-    DevBuf<int> &gperm = E->slo;  // reuse
-    gperm.ensure(E, ng);
+    E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->gorder.ensure(E, E->cap);
     ensure_cub(E, (size_t)E->cap);
     k_ghost_keys<<<GRID(ng, 256), 256, 0, st>>>(ng, n, E->xr[c].p, E->grid, E->keys.p, E->vals.p);
     size_t tb = E->cubtmp.n;
-    int endbit = 32;
-    if (E->grid.morton) endbit = 30; else { endbit = 1; while ((1L << endbit) < E->ncells) endbit++; }
-    CK(cub::DeviceRadixSort::SortPairs(E->cubtmp.p, tb, E->keys.p, E->keys2.p, E->vals.p, gperm.p, ng, 0, endbit, st));
-    E->gsrc2.ensure(E, ng); E->gshift2.ensure(E, 3 * (size_t)ng);
-    E->tag.ensure(E, E->cap, E->nlocal, st);
-    k_ghost_permute<<<GRID(ng, 256), 256, 0, st>>>(ng, gperm.p, E->gsrc.p, E->gshift.p, E->gsrc2.p, E->gshift2.p, E->tag.p, E->tag.p, n);
-    std::swap(E->gsrc.p, E->gsrc2.p); std::swap(E->gsrc.n, E->gsrc2.n);
-    std::swap(E->gshift.p, E->gshift2.p); std::swap(E->gshift.n, E->gshift2.n);
+    CK(cub::DeviceRadixSort::SortPairs(E->cubtmp.p, tb, E->keys.p, E->keys2.p, E->vals.p, E->gorder.p, ng, 0, 32, st));
+    k_cell_ranges_idx<<<GRID(ng, 256), 256, 0, st>>>(ng, E->gorder.p, E->xr[c].p, E->grid, E->gcs.p, E->gce.p);
     E->launches += 3;
-    ghost_update(E, 0, ng);
-    k_cell_ranges<<<GRID(ng, 256), 256, 0, st>>>(ng, n, E->xr[c].p, E->grid, E->gcs.p, E->gce.p);
-    E->launches++;
   }
-  // the spare record buffers must be as large as the live ones (ghost growth may have re-allocated)
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
   int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : 16));
-  for (int attempt = 0; attempt < 6 && n; attempt++) {
+  for (int attempt = 0; attempt < 6; attempt++) {
     ensure_list(E, Lnew, E->cap, maxk, dnum, hslots);
+    if (!n) break;
     CK(cudaMemsetAsync(E->overflow.p, 0, 2 * sizeof(int), st));
     BuildP P;
     P.nlocal = n; P.cap = Lnew.cap; P.maxk = Lnew.maxk; P.dnum = dnum; P.hslots = Lnew.hslots; P.xr = E->xr[c].p; P.tag = E->tag.p; P.G = E->grid;
-    P.ocs = E->ocs.p; P.oce = E->oce.p; P.gcs = E->gcs.p; P.gce = E->gce.p; P.cdf = E->cdf; P.skin = E->skin;
+    P.ocs = E->ocs.p; P.oce = E->oce.p; P.gcs = E->gcs.p; P.gce = E->gce.p; P.gorder = E->gorder.p; P.cdf = E->cdf; P.skin = E->skin;
     P.nbr = Lnew.nbr.p; P.numneigh = Lnew.numneigh.p; P.ptag = Lnew.ptag.p; P.hist = Lnew.hist.p;
     P.have_old = (Lold.valid && dnum && Lold.dnum == dnum) ? 1 : 0; P.cap_old = Lold.cap; P.dnum_old = Lold.dnum;
     P.perm = E->perm.p; P.nbr_old = Lold.nbr.p; P.numneigh_old = Lold.numneigh.p; P.ptag_old = Lold.ptag.p; P.hist_old = Lold.hist.p;
@@ -660,12 +925,12 @@ static void rebuild(dem_engine *E)
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
   // 6. positions at build time + primitive wall candidate bits
+  E->nwc = 0;
   if (n) {
     const int nw = (int)E->walls.size();
     E->flo.ensure(E, n + 1); E->slo.ensure(E, n + 1);
     k_hold<<<GRID(n, 256), 256, 0, st>>>(n, E->xr[c].p, E->xh.p, E->valid_tmp.p, E->dwalls.p, nw, E->skin, nw ? E->flo.p : nullptr);
     E->launches++;
-    E->nwc = 0;
     if (nw) {
       size_t tb = E->cubtmp.n;
       CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, E->flo.p, E->slo.p, n, st));
@@ -703,7 +968,7 @@ static StepP step_params(dem_engine *E, int mode)
   P.cutneighmax = E->cutneighmax;
   for (int d = 0; d < 3; d++) P.g[d] = E->g[d];
   P.have_g = E->have_g; P.have_pair = E->have_pair; P.freezebit = E->freezebit; P.integbit = E->integbit;
-  P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = E->hflag; P.ncontact = nullptr;
+  P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = E->nranks > 1 ? E->dflag.p : E->hflag; P.ncontact = nullptr;
   return P;
 }
 
@@ -739,6 +1004,21 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   E->launches++;
 }
 
+// rebuild trigger / overflow flags: single rank -> the kernels write mapped host memory directly; multi rank ->
+// they write device memory which is MAX-all-reduced (the reference: MPI_Allreduce in neighbor.cpp:1463)
+static void clear_flags(dem_engine *E)
+{
+  CK(cudaStreamSynchronize(E->stream));
+  E->hflag[0] = E->hflag[1] = 0;
+  if (E->nranks > 1) { E->dflag.ensure(E, 4); CK(cudaMemsetAsync(E->dflag.p, 0, 4 * sizeof(int), E->stream)); }
+}
+static void reduce_flags(dem_engine *E)
+{
+  if (E->nranks == 1) return;
+  NK(g_nccl.AllReduce(E->dflag.p, E->dflag.p + 2, 2, ncclInt, ncclMax, E->comm, E->stream));
+  CK(cudaMemcpyAsync(E->hflag, E->dflag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+}
+
 static void collect_timing(dem_engine *E)
 {
   for (long k = 0; k < E->ev_used; k++) {
@@ -764,6 +1044,7 @@ extern "C" int dem_setup(dem_engine *e)
       e->whist_tmp.release(); e->whist_tmp.ensure(e, (size_t)e->nwrows * e->cap);
     }
   }
+  clear_flags(e);
   rebuild(e);
   e->nbuilds = 0;  // neighbor->ncalls counts the builds of the current run only
   launch_step(e, MODE_SETUP, false);
@@ -783,14 +1064,15 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   cudaStream_t st = e->stream;
   e->step_ms = 0; e->step_calls = 0; e->ev_used = 0;
   // first half step from the stored forces (fix_nve_sphere.cpp:134-183)
-  *e->hflag = 0;
+  clear_flags(e);
   if (e->nlocal) {
     StepP P = step_params(e, MODE_STEP);
     k_initial_integrate<<<GRID(P.nlocal, 256), 256, 0, st>>>(P);
     e->launches++;
-    e->cur ^= 1;
-    ghost_update(e, 0, (int)e->nghost);
   }
+  e->cur ^= 1;
+  forward_comm(e);
+  reduce_flags(e);
   for (long s = 1; s <= nsteps; s++) {
     e->ntimestep++;
     // Neighbor::decide (neighbor.cpp:1362-1376)
@@ -798,12 +1080,13 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
     int nflag = 0;
     if (e->ago >= e->delay && e->ago % e->every == 0) {
       if (!e->check) nflag = 1;
-      else { CK(cudaStreamSynchronize(st)); nflag = *e->hflag; }
+      else { CK(cudaStreamSynchronize(st)); nflag = e->hflag[0]; }
     }
-    if (nflag) { rebuild(e); CK(cudaStreamSynchronize(st)); *e->hflag = 0; }
+    if (nflag) { rebuild(e); clear_flags(e); }
     launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
     e->cur ^= 1;
-    ghost_update(e, 0, (int)e->nghost);
+    forward_comm(e);
+    reduce_flags(e);
     if (e->ev_used >= 2048) { CK(cudaStreamSynchronize(st)); collect_timing(e); }
   }
   CK(cudaStreamSynchronize(st));

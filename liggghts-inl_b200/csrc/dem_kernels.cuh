@@ -334,28 +334,31 @@ __global__ void __launch_bounds__(256) k_initial_integrate(const StepP P)
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }
 
-// ghost refresh (== forward_comm of x,v,omega: comm_brick.cpp:563-645, atom_vec_sphere.cpp:283-293)
-struct GhostP {
-  int nghost, nlocal;
-  const int *src;      // owned source index
-  const int *shift;    // 3 small ints per ghost (periodic image offsets)
-  double prd[3];
-  double4 *xr, *vm, *wt;
-  int with_static;  // also copy radius/mass/type (at rebuild)
+// ghost refresh of one swap (== CommBrick::forward_comm of x,v,omega for one iswap, comm_brick.cpp:563-645,
+// atom_vec_sphere.cpp:283-293): gathers the swap's send list, applies the periodic shift on the sender side
+// and writes either straight into the own ghost region (periodic image on the same rank) or into the
+// NCCL send buffers.  Lists may contain ghosts received in an earlier dimension (edges/corners).
+struct SwapP {
+  int n;
+  const int *list;
+  int dim;
+  double shift;
+  const double4 *xr, *vm, *wt;
+  double4 *ox, *ov, *ow;
 };
-__global__ void __launch_bounds__(256) k_ghost_update(const GhostP G, int g0, int g1)
+__global__ void __launch_bounds__(256) k_pack_swap(const SwapP S)
 {
-  const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= g1) return;
-  const int s = G.src[g];
-  double4 x = G.xr[s];
-  const int sx = G.shift[3 * g], sy = G.shift[3 * g + 1], sz = G.shift[3 * g + 2];
-  if (sx) x.x += sx * G.prd[0];
-  if (sy) x.y += sy * G.prd[1];
-  if (sz) x.z += sz * G.prd[2];
-  G.xr[G.nlocal + g] = x;
-  G.vm[G.nlocal + g] = G.vm[s];
-  G.wt[G.nlocal + g] = G.wt[s];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= S.n) return;
+  const int s = S.list[q];
+  double4 x = S.xr[s];
+  if (S.dim == 0) x.x += S.shift; else if (S.dim == 1) x.y += S.shift; else x.z += S.shift;
+  S.ox[q] = x; S.ov[q] = S.vm[s]; S.ow[q] = S.wt[s];
+}
+__global__ void __launch_bounds__(256) k_pack_int(int n, const int *list, const int *src, int *out)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = src[list[q]];
 }
 
 // ------------------------------------------------------------------ rebuild kernels
@@ -382,10 +385,11 @@ __device__ __forceinline__ unsigned key_of(const GridP &G, int cx, int cy, int c
 
 // Domain::pbc (domain.cpp:550-640) + sort key of the owned particles
 struct BoxP { double lo[3], hi[3], prd[3]; int periodic[3]; };
-__global__ void __launch_bounds__(256) k_wrap_key(int n, double4 *xr, const GridP G, const BoxP B, unsigned *keys, int *vals)
+__global__ void __launch_bounds__(256) k_wrap_key(int n, double4 *xr, const GridP G, const BoxP B, unsigned *keys, int *vals, const int *gone)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (gone && gone[i]) { keys[i] = 0xFFFFFFFFu; vals[i] = i; return; }  // migrated away: sorts behind everybody
   double4 x = xr[i];
   {
     double c[3] = {x.x, x.y, x.z};
@@ -442,36 +446,129 @@ __global__ void __launch_bounds__(256) k_border_flag(int n, const double4 *xr, i
   flo[p] = c < lo_cut;    // image at +prd
   fhi[p] = c >= hi_cut;   // image at -prd
 }
-__global__ void __launch_bounds__(256) k_border_scatter(int n, int nlocal, int dim, const int *flo, const int *slo, const int *fhi, const int *shi,
-                                                        int nlo_total, int gbase, int *gsrc, int *gshift)
+// compact the flagged indices into a send list (deterministic order: ascending index)
+__global__ void __launch_bounds__(256) k_compact(int n, const int *flag, const int *scan, int *list)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  for (int side = 0; side < 2; side++) {
-    const int fl = side ? fhi[p] : flo[p];
-    if (!fl) continue;
-    const int g = gbase + (side ? nlo_total + shi[p] : slo[p]);
-    int s = p, sh[3] = {0, 0, 0};
-    if (p >= nlocal) { const int gp = p - nlocal; s = gsrc[gp]; sh[0] = gshift[3 * gp]; sh[1] = gshift[3 * gp + 1]; sh[2] = gshift[3 * gp + 2]; }
-    sh[dim] += side ? -1 : 1;
-    gsrc[g] = s; gshift[3 * g] = sh[0]; gshift[3 * g + 1] = sh[1]; gshift[3 * g + 2] = sh[2];
-  }
+  if (p < n && flag[p]) list[scan[p]] = p;
 }
 __global__ void __launch_bounds__(256) k_ghost_keys(int n, int nlocal, const double4 *xr, const GridP G, unsigned *keys, int *vals)
 {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   int cx, cy, cz; cell_of(G, xr[nlocal + g], cx, cy, cz);
-  keys[g] = key_of(G, cx, cy, cz); vals[g] = g;
+  keys[g] = key_of(G, cx, cy, cz); vals[g] = nlocal + g;
 }
-__global__ void __launch_bounds__(256) k_ghost_permute(int n, const int *perm, const int *src, const int *shift, int *src_o, int *shift_o,
-                                                       const int *tag, int *gtag, int nlocal)
+// cell ranges of the ghosts through their cell-sorted index list gorder[0..n)
+__global__ void __launch_bounds__(256) k_cell_ranges_idx(int n, const int *gorder, const double4 *xr, const GridP G, int *cstart, int *cend)
 {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n) return;
-  const int p = perm[g];
-  src_o[g] = src[p]; shift_o[3 * g] = shift[3 * p]; shift_o[3 * g + 1] = shift[3 * p + 1]; shift_o[3 * g + 2] = shift[3 * p + 2];
-  gtag[nlocal + g] = tag[src[p]];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int cx, cy, cz;
+  cell_of(G, xr[gorder[p]], cx, cy, cz);
+  const int c = lin_cell(G, cx, cy, cz);
+  int cp = -1, cn = -1;
+  if (p > 0) { cell_of(G, xr[gorder[p - 1]], cx, cy, cz); cp = lin_cell(G, cx, cy, cz); }
+  if (p < n - 1) { cell_of(G, xr[gorder[p + 1]], cx, cy, cz); cn = lin_cell(G, cx, cy, cz); }
+  if (c != cp) cstart[c] = p;
+  if (c != cn) cend[c] = p + 1;
+}
+
+// ---- particle migration between bricks (CommBrick::exchange, comm_brick.cpp:732-860, with the contact history
+// of fix_contact_history.cpp:508-555 travelling with the particle).  One fixed-stride record per migrant:
+// [0..11] the three 32-byte records, [12] tag, [13] density, [14] wall-history valid bits, [15] nh,
+// [16..16+nwrows) wall history, then nh x (partner tag, hrec x 4 history doubles).
+struct MigP {
+  int n, stride, nwrows, hrec, hmax, cap, lcap, dim;
+  double wrap_lo, wrap_hi, prd;  // periodic wrap applied by the sender
+  int periodic;
+  const int *list;
+  double4 *xr, *vm, *wt, *xh;
+  int *tag; double *density; double *whist;
+  unsigned *nbr; int *numneigh; int *ptag; double4 *hist; int hslots, maxk;
+  double *buf;
+};
+__global__ void __launch_bounds__(128) k_mig_pack(const MigP M)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= M.n) return;
+  const int i = M.list[q];
+  double *b = M.buf + (size_t)q * M.stride;
+  double4 x = M.xr[i];
+  if (M.periodic) {
+    double c = M.dim == 0 ? x.x : M.dim == 1 ? x.y : x.z;
+    if (c < M.wrap_lo) c += M.prd;
+    if (c >= M.wrap_hi) { c -= M.prd; c = fmax(c, M.wrap_lo); }
+    if (M.dim == 0) x.x = c; else if (M.dim == 1) x.y = c; else x.z = c;
+  }
+  const double4 v = M.vm[i], w = M.wt[i];
+  b[0] = x.x; b[1] = x.y; b[2] = x.z; b[3] = x.w; b[4] = v.x; b[5] = v.y; b[6] = v.z; b[7] = v.w;
+  b[8] = w.x; b[9] = w.y; b[10] = w.z; b[11] = w.w;
+  b[12] = (double)M.tag[i]; b[13] = M.density[i];
+  b[14] = (double)(((unsigned)(__double_as_longlong(M.xh[i].w) & 0xffffffffLL)) >> 16);
+  for (int r = 0; r < M.nwrows; r++) b[16 + r] = M.whist[(size_t)r * M.cap + i];
+  int nh = 0;
+  if (M.nbr) {
+    const int nn = M.numneigh[i] & 0xffff;
+    double *hb = b + 16 + M.nwrows;
+    for (int k = 0; k < nn; k++) {
+      const unsigned wd = M.nbr[(size_t)k * M.lcap + i];
+      if (!(wd & NBR_HIST) || nh >= M.hmax) continue;
+      const int slot = (int)((wd & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+      double *e = hb + (size_t)nh * (1 + 4 * M.hrec);
+      e[0] = (double)M.ptag[(size_t)k * M.lcap + i];
+      for (int r = 0; r < M.hrec; r++) {
+        const double4 h = M.hist[(size_t)(slot * M.hrec + r) * M.lcap + i];
+        e[1 + 4 * r] = h.x; e[2 + 4 * r] = h.y; e[3 + 4 * r] = h.z; e[4 + 4 * r] = h.w;
+      }
+      nh++;
+    }
+  }
+  b[15] = (double)nh;
+}
+// arrivals are appended behind the current particles at index base+q; their history goes into row base+q of
+// the OLD list so that the remap of k_build_list finds it through the sort permutation like any other row
+__global__ void __launch_bounds__(128) k_mig_unpack(const MigP M, int base)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= M.n) return;
+  const int i = base + q;
+  const double *b = M.buf + (size_t)q * M.stride;
+  M.xr[i] = make_double4(b[0], b[1], b[2], b[3]);
+  M.vm[i] = make_double4(b[4], b[5], b[6], b[7]);
+  M.wt[i] = make_double4(b[8], b[9], b[10], b[11]);
+  M.tag[i] = (int)b[12]; M.density[i] = b[13];
+  M.xh[i] = make_double4(0., 0., 0., __longlong_as_double((long long)(((unsigned)b[14]) << 16)));
+  for (int r = 0; r < M.nwrows; r++) M.whist[(size_t)r * M.cap + i] = b[16 + r];
+  if (M.nbr) {
+    const int nh = (int)b[15];
+    const double *hb = b + 16 + M.nwrows;
+    for (int k = 0; k < nh; k++) {
+      const double *e = hb + (size_t)k * (1 + 4 * M.hrec);
+      M.ptag[(size_t)k * M.lcap + i] = (int)e[0];
+      M.nbr[(size_t)k * M.lcap + i] = (unsigned)(k + 1) << NBR_SLOT_SHIFT;
+      for (int r = 0; r < M.hrec; r++)
+        M.hist[(size_t)(k * M.hrec + r) * M.lcap + i] = make_double4(e[1 + 4 * r], e[2 + 4 * r], e[3 + 4 * r], e[4 + 4 * r]);
+    }
+    M.numneigh[i] = nh | (nh << 16);
+  }
+}
+__global__ void __launch_bounds__(256) k_mig_flag(int n, const double4 *xr, int dim, double sublo, double subhi, int has_lo, int has_hi,
+                                                  int *flo, int *fhi, int *gone)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (gone[p]) { flo[p] = fhi[p] = 0; return; }
+  const double4 x = xr[p];
+  const double c = dim == 0 ? x.x : dim == 1 ? x.y : x.z;
+  const int l = has_lo && c < sublo, h = has_hi && c >= subhi;
+  flo[p] = l; fhi[p] = h;
+  if (l || h) gone[p] = 1;
+}
+__global__ void __launch_bounds__(256) k_max_nh(int n, const int *list, const int *numneigh, int *out)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) atomicMax(out, (numneigh[list[q]] >> 16) & 0xffff);
 }
 
 // Verlet-skin FULL list + history remap: neigh_gran.cpp:560-625 (predicates), fix_contact_history.cpp:351
@@ -481,6 +578,7 @@ struct BuildP {
   const int *tag;
   GridP G;
   const int *ocs, *oce, *gcs, *gce;  // owned / ghost cell ranges
+  const int *gorder;                 // cell-sorted ghost indices (ghost storage keeps its swap order)
   double cdf, skin;
   unsigned *nbr; int *numneigh; int *ptag; double4 *hist;
   // previous list (rows addressed through perm: new i <- old perm[i])
@@ -507,7 +605,8 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
         const int c = lin_cell(B.G, x, y, z);
         for (int pass = 0; pass < 2; pass++) {
           const int s = pass ? B.gcs[c] : B.ocs[c], e = pass ? B.gce[c] : B.oce[c];
-          for (int j = s; j < e; j++) {
+          for (int q = s; q < e; q++) {
+            const int j = pass ? B.gorder[q] : q;
             if (j == i) continue;
             const double4 xj = B.xr[j];
             const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);

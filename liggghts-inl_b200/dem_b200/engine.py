@@ -7,7 +7,7 @@ _ROOT = os.path.dirname(_HERE)
 
 # every symbol declared in include/dem_b200.h
 ABI_SYMBOLS = [
-    "dem_create", "dem_destroy", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
+    "dem_create", "dem_destroy", "dem_nccl_unique_id", "dem_decomposition", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
     "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_property",
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
@@ -57,6 +57,21 @@ class Engine:
         if rc != 0 or not self._h:
             msg = self._err() if self._h else "engine creation failed (no usable sm_100 GPU?)"
             raise DemError(msg)
+
+    @staticmethod
+    def nccl_unique_id(lib=None):
+        """128-byte ncclUniqueId (call on rank 0, then broadcast to all ranks)"""
+        lib = lib if lib is not None else load_library()
+        buf = C.create_string_buffer(128)
+        lib.dem_nccl_unique_id.argtypes = [C.c_void_p]
+        if lib.dem_nccl_unique_id(buf) != 0:
+            raise DemError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+        return bytes(buf.raw)
+
+    def decomposition(self):
+        pg = (C.c_int * 3)(); ml = (C.c_int * 3)(); lo = (C.c_double * 3)(); hi = (C.c_double * 3)()
+        self._call("decomposition", [C.c_void_p] * 4, pg, ml, lo, hi)
+        return list(pg), list(ml), list(lo), list(hi)
 
     # -- plumbing -----------------------------------------------------------------------
     def _fn(self, name):

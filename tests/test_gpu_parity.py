@@ -77,3 +77,14 @@ def test_error_paths():
     with pytest.raises(dem_b200.DemError):
         e.property_global("youngsModulus", "peratomtype", [1.0, 2.0, 3.0])  # wrong count
     e.close()
+
+
+def test_multi_gpu_bricks_match_oracle():
+    """2 GPUs: brick decomposition + NCCL halo + migration against the single-process oracle"""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(here, "run_multi.py")], capture_output=True, text=True, timeout=600)
+    assert "MULTI-GPU PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
