@@ -134,34 +134,79 @@ def run_reference_procs(nproc, tiles, steps):
     return total / max(r["seconds"] for r in res), len(res), res[0]["n"]
 
 
+def ref_server(tiles):
+    """persistent reference worker: loads the tile bed once, then serves `run S` requests on stdin"""
+    import cases
+    import ref_driver
+    c = bed_case(tiles, tiles, name="cpu")
+    tmp = tempfile.mkdtemp()
+    deck, data = cases.to_deck(c, os.path.join(tmp, "bed.data"))
+    open(os.path.join(tmp, "bed.data"), "w").write(data)
+    r = ref_driver.Ref()
+    r.cmd(deck)
+    r.cmd("run 0")
+    sys.stdout.write("ready %d\n" % len(c["tag"])); sys.stdout.flush()
+    for line in sys.stdin:
+        line = line.strip()
+        if not line or line == "quit":
+            break
+        t0 = time.perf_counter()
+        r.cmd("run %d pre no post no" % int(line))  # steady-state stepping: no Verlet::setup per request
+        sys.stdout.write("done %.6f\n" % (time.perf_counter() - t0)); sys.stdout.flush()
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import ref_driver
     cfg = {"workload": "4,194,304-sphere settled polydisperse bed (16x16 replicas of bench_data/tile16k), hertz/history/cdt, floor + periodic xy",
-           "inputs": "reference arm runs one 16,384-sphere tile of the same bed per host core"}
+           "inputs": "reference arm: every host core steps one 16,384-sphere tile of the same bed (serial reference build; the image has no MPI)"}
     if not ref_driver.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libliggghts_ref.so missing (build: make -C oracle ref)"}))
         return
-    cores = os.cpu_count() or 1
-    # bounded sample: each step of this arm = `sample_steps` reference steps of one tile per core
-    sample_steps = 150
-    vals = []
-    for it in range(args.warmup + args.steps):
-        v = run_reference_procs(cores, 1, sample_steps)
-        if v is None:
-            print(json.dumps({"impl": "reference", "unavailable": "reference worker failed"})); return
-        if it >= args.warmup:
-            vals.append(v[0])
-    value = float(np.mean(vals))
-    n_tile = 16384
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    sample_steps = 5  # reference timesteps per bench step and per core
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-server", "1"], stdin=subprocess.PIPE,
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1) for _ in range(cores)]
+    n_tile = 0
+    for p in procs:
+        line = p.stdout.readline()
+        while line and not line.startswith("ready"):
+            line = p.stdout.readline()
+        if not line:
+            print(json.dumps({"impl": "reference", "unavailable": "reference worker failed to start"})); return
+        n_tile = int(line.split()[1])
+
+    def step():
+        for p in procs:
+            p.stdin.write("%d\n" % sample_steps); p.stdin.flush()
+        for p in procs:
+            line = p.stdout.readline()
+            while line and not line.startswith("done"):
+                line = p.stdout.readline()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    for p in procs:
+        try:
+            p.stdin.write("quit\n"); p.stdin.flush()
+        except Exception:
+            pass
+    for p in procs:
+        p.wait()
+    value = cores * n_tile * sample_steps * args.steps / dt
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores * n_tile * sample_steps / value,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": cfg,
                       "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "reference",
-                                       "sample": "%d independent serial reference processes (no MPI in the image), each one 16,384-sphere tile x %d steps" % (cores, sample_steps)},
+                                       "sample": "%d concurrent serial reference processes, each one %d-sphere tile x %d timesteps per bench step"
+                                                 % (cores, n_tile, sample_steps)},
                       "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -172,35 +217,61 @@ def own_arm(args):
     import cases
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("multi-GPU brick decomposition is not enabled in this build yet")
     torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+
+    def new_engine():
+        if world == 1:
+            return dem_b200.Engine(device=local)
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(dem_b200.Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        return dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=buf.cpu().numpy().tobytes())
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+
     tiles = args.tiles
     c = bed_case(tiles, tiles)
     n = len(c["tag"])
-    eng = cases.apply(c, dem_b200.Engine(device=local))
+    eng = cases.apply(c, new_engine())
     eng.option("time_kernels", 1)
     eng.setup()
     eng.run(max(args.warmup, 3))
     st0 = eng.stats()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     eng.run(args.steps)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    if dist: dist.barrier()
+    ms = allmax(e0.elapsed_time(e1))
     clocks = sampler.stop()
     st = eng.stats()
     value = n * args.steps / (ms * 1e-3)
     # roofline of the dominant (fused step) kernel
-    K_half = st.npairs_full / 2.0 / n
-    C_half = st.ncontacts_full / 2.0 / n
+    nloc = max(int(st.nlocal), 1)
+    K_half = st.npairs_full / 2.0 / nloc
+    C_half = st.ncontacts_full / 2.0 / nloc
     dnum = st.dnum
     bytes_per_ps = 192.0 + 4.0 * K_half + (16.0 * dnum + 8.0) * C_half
     kms = st.step_kernel_ms / max(st.step_kernel_calls, 1)
     peak, peak_src = peaks()
-    achieved = bytes_per_ps * n / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    achieved = bytes_per_ps * nloc / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(tpath):
@@ -215,15 +286,16 @@ def own_arm(args):
     # end-to-end through the public API with host buffers: upload -> setup -> run(K) -> download
     ke = max(args.steps // 4, 10)
     eng.close()
+    if dist: dist.barrier()
     t0 = time.perf_counter()
-    eng2 = cases.apply(c, dem_b200.Engine(device=local))
+    eng2 = cases.apply(c, new_engine())
     eng2.setup()
     eng2.run(ke)
     xo = eng2.download("x"); vo = eng2.download("v")
     torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    h2d = n * (3 * 32 + 4 + 8)
-    d2h = xo.nbytes + vo.nbytes + 2 * n * 4
+    t_e2e = allmax(time.perf_counter() - t0)
+    h2d = allsum(int(eng2.nlocal) * (3 * 32 + 4 + 8))
+    d2h = allsum(xo.nbytes + vo.nbytes + 2 * len(xo) * 4)
     e2e = {"value": n * ke / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / ke, "d2h_bytes_per_step": d2h / ke,
            "job": "create + upload(host arrays) + setup + run(%d) + download x,v; %.3f s" % (ke, t_e2e)}
     eng2.close()
@@ -239,20 +311,25 @@ def own_arm(args):
                 cpu = {"value": r[0], "unit": "particle-steps/s", "cores": 1, "kind": "reference",
                        "sample": "one 16,384-sphere tile of the bed x %d steps, serial reference build (oracle/_ref)" % steps_cpu}
     out = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": "%d-sphere settled polydisperse bed (%dx%d replicas of bench_data/tile16k, radii U[1.5,3] mm), "
                                   "hertz/history/cdt, floor + periodic xy, dt 1e-5, skin 1 mm" % (n, tiles, tiles),
                       "particles": n, "l2_policy": "inputs (%.1f GB of state + lists) exceed the 126 MB L2" % (n * 600 / 1e9),
-                      "rebuilds_in_timed_region": int(nbuilds), "parallelism": "1 GPU"},
+                      "rebuilds_in_timed_region": int(nbuilds),
+                      "parallelism": "1 GPU" if world == 1 else "%d GPUs: x-slab bricks, NCCL halo per step (roofline fields are rank 0's)" % world},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     if rank == 0:
         print(json.dumps(out))
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
 
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--ref-worker":
         ref_worker(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]); return
+    if len(sys.argv) > 1 and sys.argv[1] == "--ref-server":
+        ref_server(int(sys.argv[2])); return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -57,18 +57,27 @@ def main():
         # give the particles a drift along x so that they migrate between the bricks
         c["v"][:, 0] += 2.5
         rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
-        eng = cases.apply(c, make_engine(rank, world, local))
+        eng = make_engine(rank, world, local)
+        eng.box(c["lo"], c["hi"], c["periodic"])
+        eng.processors(world, 1, 1)  # slabs along x, the drift direction
+        eng = cases.apply(c, eng)
+        nl0 = None
         ref = cases.apply(c, parity.oracle_engine()) if rank == 0 else None
         done = 0
         for cp in steps:
             eng.setup(); eng.run(cp - done)
             snap = gather_snapshot(eng, c, rank, world)
+            nls = [None] * world
+            dist.all_gather_object(nls, int(eng.nlocal))
+            nl0 = nl0 or nls
             if rank == 0:
                 ref.setup(); ref.run(cp - done)
                 tol = 1e-10 if cp <= 10 else (1e-6 if cp <= 400 else 1e-4)
                 errs = parity.compare_snapshot(snap, cases.snapshot(ref, c), rmass, tol=tol, label="multi@%d" % cp)
-                print("world %d step %4d ok: nlocal(rank0)=%d f err %.2e" % (world, cp, eng.nlocal, errs["f"]), flush=True)
+                print("world %d step %4d ok: nlocal per rank %s f err %.2e" % (world, cp, nls, errs["f"]), flush=True)
             done = cp
+        if not kw.get("periodic") and rank == 0:
+            assert nls != nl0, "no particle migrated between the bricks in the drift case"
         eng.close()
     dist.barrier()
     if rank == 0:
