@@ -284,7 +284,7 @@ def own_arm(args):
     nbuilds = st.nbuilds
 
     # end-to-end through the public API with host buffers: upload -> setup -> run(K) -> download
-    ke = max(args.steps // 4, 10)
+    ke = args.steps
     eng.close()
     if dist: dist.barrier()
     t0 = time.perf_counter()

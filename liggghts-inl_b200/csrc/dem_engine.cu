@@ -121,6 +121,8 @@ struct dem_engine {
   DevBuf<int> sbuf_i, gorder, gone, cnt_dev;
   DevBuf<double> migs, migr;
   int *hcnt = nullptr;  // pinned host scratch for counts
+  DevBuf<int> order, order_keys; int order_valid = 0;  // ascending-tag permutation for read-back
+  DevBuf<char> stage;  // device staging for upload / read-back
   DevBuf<int> dflag;    // device-side rebuild trigger (multi-rank: all-reduced)
   DevBuf<int> flo, fhi, slo, shi;
   // cells / sort
@@ -226,7 +228,7 @@ extern "C" void dem_destroy(dem_engine *e)
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
   e->xh.release(); e->tag.release(); e->tag_tmp.release(); e->density.release(); e->density_tmp.release();
   e->f.release(); e->tq.release(); e->whist.release(); e->whist_tmp.release(); e->tab.release(); e->dwalls.release();
-  e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
+  e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
   e->cubtmp.release(); e->overflow.release(); e->counters.release();
@@ -513,6 +515,47 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
   e->xh.release(); e->tag.release(); e->density.release(); e->f.release(); e->tq.release(); e->whist.release();
   setup_decomposition(e);
+  if (e->nranks == 1 && n > 0) {
+    // single brick: ship the caller's arrays as they are and build the records on the device
+    const double cf = e->opt.count("cap_factor") ? e->opt["cap_factor"] : 1.25;
+    ensure_particle_cap(e, std::max<long>((long)(n * cf) + 1024, 1024), 0);
+    cudaStream_t st = e->stream;
+    const size_t nd = (size_t)n;
+    const size_t bytes = nd * (3 + 3 + 3 + 1 + 1) * sizeof(double) + nd * 3 * sizeof(int) + 64;
+    e->stage.ensure(e, bytes);
+    double *dx = (double *)e->stage.p, *dv = dx + 3 * nd, *dw = dv + 3 * nd, *dr = dw + 3 * nd, *dd = dr + nd;
+    int *dt = (int *)(dd + nd), *dm = dt + nd, *dg = dm + nd;
+    CK(cudaMemcpyAsync(dx, x, 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (v) CK(cudaMemcpyAsync(dv, v, 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (omega) CK(cudaMemcpyAsync(dw, omega, 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dr, radius, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dd, density, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dt, type, nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (mask) CK(cudaMemcpyAsync(dm, mask, nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg, tag, nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    e->counters.ensure(e, 2);
+    CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    e->cur = 0;
+    k_pack_upload<<<GRID(n, 256), 256, 0, st>>>((int)n, dx, v ? dv : nullptr, omega ? dw : nullptr, dr, dd, dt, mask ? dm : nullptr, dg, e->ntypes,
+                                                 e->xr[0].p, e->vm[0].p, e->wt[0].p, (int *)(e->counters.p + 1), e->counters.p);
+    e->launches++;
+    CK(cudaMemcpyAsync(e->tag.p, dg, nd * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(e->density.p, dd, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), st));
+    unsigned long long hc[2];
+    CK(cudaMemcpyAsync(hc, e->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int errbits = (int)(hc[1] & 0xffffffffu);
+    if (errbits & 1) dem_fail(e, DEM_ERR_ARG, "Invalid atom type in particle data");
+    if (errbits & 2) dem_fail(e, DEM_ERR_ARG, "Invalid radius or density in particle data");
+    if (errbits & 4) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
+    double rmaxd; memcpy(&rmaxd, &hc[0], 8);
+    e->nlocal = n; e->nghost = 0; e->rmax = rmaxd;
+    e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0;
+    e->ls[0].valid = e->ls[1].valid = 0;
+    e->ntimestep = 0;
+    return DEM_OK;
+  }
   std::vector<double4> hx, hv, hw; std::vector<int> htag; std::vector<double> hden;
   hx.reserve(n / e->nranks + 16); hv.reserve(n / e->nranks + 16); hw.reserve(n / e->nranks + 16);
   double rmax = 0.0;
@@ -558,7 +601,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
   CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->nlocal = n; e->nghost = 0; e->rmax = rmax;
-  e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0;
+  e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0;
   e->ls[0].valid = e->ls[1].valid = 0;
   e->ntimestep = 0;
   API_END
@@ -946,6 +989,7 @@ static void rebuild(dem_engine *E)
   }
   CK(cudaGetLastError());
   E->ago = 0;
+  E->order_valid = 0;
   E->nbuilds++;
 }
 
@@ -1111,34 +1155,54 @@ static std::vector<int> tag_order(dem_engine *E, std::vector<int> &tags)
   return o;
 }
 
+// ascending-tag permutation on the device (radix sort of the tags), cached until the next rebuild
+static void ensure_order(dem_engine *E)
+{
+  if (E->order_valid) return;
+  const int n = (int)E->nlocal;
+  cudaStream_t st = E->stream;
+  if (n) {
+    E->order.ensure(E, E->cap); E->order_keys.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->keys.ensure(E, E->cap);
+    ensure_cub(E, (size_t)E->cap);
+    k_iota<<<GRID(n, 256), 256, 0, st>>>(n, E->vals.p);
+    size_t tb = E->cubtmp.n;
+    CK(cub::DeviceRadixSort::SortPairs(E->cubtmp.p, tb, (const unsigned *)E->tag.p, (unsigned *)E->order_keys.p, E->vals.p, E->order.p, n, 0, 32, st));
+    E->launches += 2;
+  }
+  E->order_valid = 1;
+}
+
 extern "C" int dem_download(dem_engine *e, const char *field, void *out, long count)
 {
   API_BEGIN
   if (!e->uploaded) dem_fail(e, DEM_ERR_STATE, "no particles");
   if (count != e->nlocal) dem_fail(e, DEM_ERR_ARG, "count %ld != nlocal %ld", count, e->nlocal);
   CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
-  const long n = e->nlocal;
-  std::vector<int> tags; std::vector<int> o = tag_order(e, tags);
+  const int n = (int)e->nlocal;
+  if (!n) return DEM_OK;
+  cudaStream_t st = e->stream;
+  ensure_order(e);
   std::string f(field);
   const int c = e->cur;
-  auto rec = [&](DevBuf<double4> &b) { std::vector<double4> h(n); if (n) CK(cudaMemcpy(h.data(), b.p, n * sizeof(double4), cudaMemcpyDeviceToHost)); return h; };
-  if (f == "tag") { for (long k = 0; k < n; k++) ((int *)out)[k] = tags[o[k]]; }
-  else if (f == "type" || f == "mask") {
-    auto h = rec(e->wt[c]);
-    for (long k = 0; k < n; k++) { long long b; memcpy(&b, &h[o[k]].w, 8); ((int *)out)[k] = f == "type" ? (int)(b & 0xff) : (int)((b >> 8) & 0xffffffffLL); }
-  } else if (f == "radius") { auto h = rec(e->xr[c]); for (long k = 0; k < n; k++) ((double *)out)[k] = h[o[k]].w; }
-  else if (f == "rmass") { auto h = rec(e->vm[c]); for (long k = 0; k < n; k++) ((double *)out)[k] = h[o[k]].w; }
-  else if (f == "density") { std::vector<double> h(n); if (n) CK(cudaMemcpy(h.data(), e->density.p, n * sizeof(double), cudaMemcpyDeviceToHost)); for (long k = 0; k < n; k++) ((double *)out)[k] = h[o[k]]; }
+  e->stage.ensure(e, (size_t)n * 3 * sizeof(double) + 64);
+  double *od = (double *)e->stage.p; int *oi = (int *)e->stage.p;
+  size_t bytes = 0;
+  if (f == "tag") { CK(cudaMemcpyAsync(out, e->order_keys.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); return DEM_OK; }
+  else if (f == "type" || f == "mask") { k_gather_out<<<GRID(n, 256), 256, 0, st>>>(n, e->order.p, e->wt[c].p, f == "type" ? 4 : 5, od, oi); bytes = (size_t)n * sizeof(int); }
+  else if (f == "radius") { k_gather_out<<<GRID(n, 256), 256, 0, st>>>(n, e->order.p, e->xr[c].p, 3, od, oi); bytes = (size_t)n * sizeof(double); }
+  else if (f == "rmass") { k_gather_out<<<GRID(n, 256), 256, 0, st>>>(n, e->order.p, e->vm[c].p, 3, od, oi); bytes = (size_t)n * sizeof(double); }
+  else if (f == "density") { k_gather_rows_out<<<GRID(n, 256), 256, 0, st>>>(n, e->order.p, e->density.p, 0, 1, od); bytes = (size_t)n * sizeof(double); }
   else if (f == "x" || f == "v" || f == "omega") {
-    auto h = rec(f == "x" ? e->xr[c] : f == "v" ? e->vm[c] : e->wt[c]);
-    for (long k = 0; k < n; k++) { ((double *)out)[3 * k] = h[o[k]].x; ((double *)out)[3 * k + 1] = h[o[k]].y; ((double *)out)[3 * k + 2] = h[o[k]].z; }
+    k_gather_out<<<GRID(n, 256), 256, 0, st>>>(n, e->order.p, f == "x" ? e->xr[c].p : f == "v" ? e->vm[c].p : e->wt[c].p, 0, od, oi);
+    bytes = (size_t)n * 3 * sizeof(double);
   } else if (f == "f" || f == "torque") {
     if (!e->forces_valid) dem_fail(e, DEM_ERR_STATE, "forces are only available after setup or run");
-    std::vector<double> h(3 * (size_t)e->cap);
-    CK(cudaMemcpy(h.data(), f == "f" ? e->f.p : e->tq.p, 3 * (size_t)e->cap * sizeof(double), cudaMemcpyDeviceToHost));
-    for (long k = 0; k < n; k++) for (int d = 0; d < 3; d++) ((double *)out)[3 * k + d] = h[(size_t)d * e->cap + o[k]];
+    k_gather_rows_out<<<GRID(n, 256), 256, 0, st>>>(n, e->order.p, f == "f" ? e->f.p : e->tq.p, (size_t)e->cap, 3, od);
+    bytes = (size_t)n * 3 * sizeof(double);
   } else dem_fail(e, DEM_ERR_ARG, "unknown field %s", field);
+  e->launches++;
+  CK(cudaMemcpyAsync(out, e->stage.p, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   API_END
 }
 

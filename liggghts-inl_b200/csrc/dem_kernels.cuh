@@ -690,6 +690,47 @@ __global__ void __launch_bounds__(256) k_extract_valid(int n, const int *perm, c
   valid[i] = ((unsigned)(__double_as_longlong(xh[perm ? perm[i] : i].w) & 0xffffffffLL)) >> 16;
 }
 
+// host-array upload: builds the three 32-byte records on the device from the caller's plain arrays
+// (atom_vec_sphere.cpp:1055-1083: radius = diameter/2 is done by the caller, rmass = 4/3 pi r^3 rho here)
+__global__ void __launch_bounds__(256) k_pack_upload(int n, const double *x, const double *v, const double *omega, const double *radius,
+                                                     const double *density, const int *type, const int *mask, const int *tag, int ntypes,
+                                                     double4 *xr, double4 *vm, double4 *wt, int *err, unsigned long long *rmax_bits)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = radius[i], rho = density[i];
+  const int t = type[i];
+  if (t < 1 || t > ntypes) atomicOr(err, 1);
+  if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
+  if (tag[i] <= 0) atomicOr(err, 4);
+  const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;
+  xr[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
+  vm[i] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
+  wt[i] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0.,
+                       __longlong_as_double(pack_bits(t, mask ? mask[i] : 1)));
+  unsigned long long b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0);
+  for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b; }
+  if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, b);  // positive doubles order like their bit patterns
+}
+// read-back in ascending tag order: field 0..2 = xyz of a record array, 3 = .w, 4 = type, 5 = mask
+__global__ void __launch_bounds__(256) k_gather_out(int n, const int *order, const double4 *rec, int what, double *outd, int *outi)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double4 r = rec[order[k]];
+  if (what == 0) { outd[3 * k] = r.x; outd[3 * k + 1] = r.y; outd[3 * k + 2] = r.z; }
+  else if (what == 3) outd[k] = r.w;
+  else if (what == 4) outi[k] = rec_type(r.w);
+  else outi[k] = rec_mask(r.w);
+}
+__global__ void __launch_bounds__(256) k_gather_rows_out(int n, const int *order, const double *src, size_t stride, int rows, double *out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  for (int r = 0; r < rows; r++) out[(size_t)rows * k + r] = src[r * stride + order[k]];
+}
+__global__ void __launch_bounds__(256) k_iota(int n, int *v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
+
 __global__ void __launch_bounds__(256) k_count_pairs(int n, const int *numneigh, const unsigned *nbr, int cap, unsigned long long *out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
