@@ -10,7 +10,7 @@ DEPS = [os.path.join(HERE, "csrc", f) for f in ("dem_engine.cu", "dem_kernels.cu
 OUT = os.path.join(HERE, "libdem_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static", "-diag-suppress", "550"]
 
 
 def build(force=False, verbose=False):

@@ -153,10 +153,11 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 
 // one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see
 // pair_chain); history records are stored in the canonical orientation "lower tag first" (sign
-// flipped on load/store when the partner is the first body)
+// flipped on load/store when the partner is the first body).  nh = the particle's count of history
+// slots in use (a shared-memory counter: in the cooperative phase several lanes may serve one particle).
 template <int NORMAL, int ROLLING, bool ONE>
-__device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, int nn, const double4 &xi, const double4 &vi,
-                                             const double4 &wi, int itype, int imask, bool su, int &nh, double *F, double *T)
+__device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
+                                             const double4 &wi, bool su, int *nh, double *F, double *T)
 {
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int j = (int)(w & NBR_IDX);
@@ -173,13 +174,15 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
-  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, itype, rec_type(wj.w), imask, rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
+  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
   if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
-    if (nh < P.hslots) {
-      slot = nh++;
+    const int s = atomicAdd(nh, 1);
+    if (s < P.hslots) {
+      slot = s;
+      const int nn = P.numneigh[i] & 0xffff;
       for (int k = 0; k < nn; k++)  // rare path: find the row entry of this partner and tag it with its slot
         if ((P.nbr[(size_t)k * P.lcap + i] & NBR_IDX) == (unsigned)j) { P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); break; }
-    } else ((volatile int *)P.flag)[1] = 1;
+    } else { atomicSub(nh, 1); ((volatile int *)P.flag)[1] = 1; }
   }
   if (P.pm.hrec && slot >= 0 && (su || !had)) {
     double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
@@ -188,15 +191,15 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   }
 }
 
-// start the memory accesses a contact will need one iteration ahead, without holding registers
+// start the memory accesses a staged contact will need, without holding registers
 __device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w)
 {
   const int j = (int)(w & NBR_IDX);
-  prefetch_l1(P.xr + j); prefetch_l1(P.vm + j); prefetch_l1(P.wt + j);
+  prefetch_l2(P.vm + j); prefetch_l2(P.wt + j);
   const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   if (slot >= 0) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-    for (int r = 0; r < P.pm.hrec; r++) prefetch_l1(hp + (size_t)r * P.lcap);
+    for (int r = 0; r < P.pm.hrec; r++) prefetch_l2(hp + (size_t)r * P.lcap);
   }
 }
 
@@ -205,75 +208,130 @@ __device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned
 //   verlet.cpp:264-391 (order of operations), pair_gran_base.h:257-496 (pair loop),
 //   fix_gravity.cpp:331-339, fix_freeze.cpp:132-144, fix_nve_sphere.cpp:134-244,
 //   neighbor.cpp:1425-1466 (rebuild trigger)
-// Two phases per particle: (1) stream the row with 8 independent position gathers in flight and
-// stage the neighbour words of the TOUCHING entries in shared memory; (2) walk the staged
-// contacts, so the lanes of a warp evaluate their c-th CONTACT together instead of idling
-// through the non-touching slots of their neighbours, prefetching contact c+1 while c computes.
+// Phases per warp (32 consecutive particles):
+//  (1) every lane streams its own row with 8 independent position gathers in flight and stages the
+//      neighbour words of its TOUCHING entries in shared memory;
+//  (2) the warp evaluates the staged contacts COOPERATIVELY: the (particle, contact) items of the
+//      32 particles are dealt out round-robin to the 32 lanes, so that a particle with 9 contacts
+//      does not keep 31 lanes with 4 contacts waiting; each item's force/torque goes through a
+//      shared-memory slot back to the owning lane, which adds its items in list order (the sum a
+//      particle receives does not depend on which lane evaluated what: runs stay bit reproducible);
+//  (3) the owner adds gravity / wall force, integrates, writes its records and votes on the rebuild.
 #ifndef DEM_STEP_MINBLOCKS
-#define DEM_STEP_MINBLOCKS 4
+#define DEM_STEP_MINBLOCKS 5
+#endif
+#ifndef DEM_STEP_WAVE_PREFETCH
+#define DEM_STEP_WAVE_PREFETCH 200  // blocks ahead whose streaming inputs are pulled towards L2 (0 = off); measured r01c
 #endif
 template <int NORMAL, int ROLLING, bool ONE>
 __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
   __shared__ unsigned s_w[DEM_CMAX][128];
+  __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
+  __shared__ double s_res[6][128];    // per-lane result slot of the current round
+  __shared__ int s_off[128], s_nh[128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
+  const bool active = i < P.nlocal;
+  const bool su = (P.mode != MODE_SETUP);
   bool trig = false;
-  if (i < P.nlocal) {
-    const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
-    const int itype = rec_type(wi.w), imask = rec_mask(wi.w);
-    const bool su = (P.mode != MODE_SETUP);
-    double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
-    if (P.have_pair) {
-      const int nnw = P.numneigh[i];
-      const int nn = nnw & 0xffff;
-      int nh = (nnw >> 16) & 0xffff;
-      const int nh0 = nh;
-      int nc = 0;
-      for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += 64) {
-        const int kn = min(64, nn - k0);
-        unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
-        // (1a) branch-free sweep: 8 neighbour words, then 8 position gathers in flight per thread
-#pragma unroll 8
-        for (int kk = 0; kk < kn; kk++) {
-          const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
-          const double4 xj = ldg4(P.xr + (w & NBR_IDX));
-          const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
-          const double radsum = xi.w + xj.w;
-          const bool t = rsq < __dmul_rn(radsum, radsum);
-          touch |= (unsigned long long)t << kk;
-          if (P.cdf > 1.0) close |= (unsigned long long)(!t && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << kk;
-        }
-        // (1b) stage the touching entries; start the partner v|m, omega|type fetches towards L2
-        while (touch) {
-          const int kk = __ffsll((long long)touch) - 1;
-          touch &= touch - 1;
-          const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
-          if (nc < DEM_CMAX) s_w[nc++][tid] = w; else extra |= 1ull << kk;
-          prefetch_l2(P.vm + (w & NBR_IDX)); prefetch_l2(P.wt + (w & NBR_IDX));
-        }
-        while (extra) {  // more than DEM_CMAX contacts (rare)
-          const int kk = __ffsll((long long)extra) - 1;
-          extra &= extra - 1;
-          pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + kk) * P.lcap + i], nn, xi, vi, wi, itype, imask, su, nh, F, T);
-        }
-        while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
-          const int kk = __ffsll((long long)close) - 1;
-          close &= close - 1;
-          const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
-          const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-          for (int r = 0; r < P.pm.hrec; r++) st4(P.hist + (size_t)(slot * P.pm.hrec + r) * P.lcap + i, make_double4(0., 0., 0., 0.));
-        }
-      }
-      if (P.debug & 1) nc = 0;
-      if (nc) prefetch_contact(P, i, s_w[0][tid]);
-      for (int c = 0; c < nc; c++) {
-        const unsigned w = s_w[c][tid];
-        if (c + 1 < nc) prefetch_contact(P, i, s_w[c + 1][tid]);
-        pair_contact<NORMAL, ROLLING, ONE>(P, i, w, nn, xi, vi, wi, itype, imask, su, nh, F, T);
-      }
-      if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
+  double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
+  int nc = 0, nh0 = 0, nn = 0;
+#if DEM_STEP_WAVE_PREFETCH > 0
+  {  // pull the streaming inputs of the block that will run one wave later towards L2
+    const int ip = i + DEM_STEP_WAVE_PREFETCH * 128;
+    if (ip < P.nlocal) {
+      prefetch_l2(P.xr + ip); prefetch_l2(P.vm + ip); prefetch_l2(P.wt + ip);
+      if (lane < 12) prefetch_l2(P.nbr + (size_t)lane * P.lcap + (ip - lane));
+      else if (lane == 12) prefetch_l2(P.numneigh + (ip - lane));
+      else if (lane == 13) prefetch_l2(P.xh + ip);
     }
+  }
+#endif
+  {
+    double4 xi = make_double4(0., 0., 0., 0.), vi = xi, wi = xi;
+    if (active) { xi = ldg4(P.xr + i); vi = ldg4(P.vm + i); wi = ldg4(P.wt + i); }
+    s_rec[0][tid] = xi; s_rec[1][tid] = vi; s_rec[2][tid] = wi;
+    if (active && P.have_pair) {
+      const int nnw = P.numneigh[i];
+      nn = nnw & 0xffff;
+      nh0 = (nnw >> 16) & 0xffff;
+    }
+    s_nh[tid] = nh0;
+    for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += 64) {
+      const int kn = min(64, nn - k0);
+      unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
+      // (1a) branch-free sweep: 8 neighbour words, then 8 position gathers in flight per thread
+#pragma unroll 8
+      for (int kk = 0; kk < kn; kk++) {
+        const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+        const double4 xj = ldg4(P.xr + (w & NBR_IDX));
+        const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+        const double radsum = xi.w + xj.w;
+        const bool t = rsq < __dmul_rn(radsum, radsum);
+        touch |= (unsigned long long)t << kk;
+        if (P.cdf > 1.0) close |= (unsigned long long)(!t && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << kk;
+      }
+      // (1b) stage the touching entries; start the partner v|m, omega|type and history fetches towards L2
+      while (touch) {
+        const int kk = __ffsll((long long)touch) - 1;
+        touch &= touch - 1;
+        const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+        if (nc < DEM_CMAX) s_w[nc++][tid] = w; else extra |= 1ull << kk;
+        prefetch_contact(P, i, w);
+      }
+      while (extra) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
+        const int kk = __ffsll((long long)extra) - 1;
+        extra &= extra - 1;
+        pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + kk) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
+      }
+      while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
+        const int kk = __ffsll((long long)close) - 1;
+        close &= close - 1;
+        const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+        const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+        for (int r = 0; r < P.pm.hrec; r++) st4(P.hist + (size_t)(slot * P.pm.hrec + r) * P.lcap + i, make_double4(0., 0., 0., 0.));
+      }
+    }
+    if (P.debug & 1) nc = 0;
+  }
+  // (2) cooperative contact phase
+  {
+    int incl = nc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int excl = incl - nc;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    s_off[tid] = excl;
+    __syncwarp();
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
+      if (t < total) {
+        int p = 0;  // owner of item t: the last lane whose first item is <= t
+#pragma unroll
+        for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
+        const int q = wb + p;
+        const unsigned w = s_w[t - s_off[q]][q];
+        pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++) { s_res[d][tid] = rF[d]; s_res[3 + d][tid] = rT[d]; }
+      __syncwarp();
+      const int qe = min(incl, t0 + 32);
+      for (int k = max(excl, t0); k < qe; k++) {
+        const int sl = wb + k - t0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { F[d] += s_res[d][sl]; T[d] += s_res[3 + d][sl]; }
+      }
+      __syncwarp();
+    }
+  }
+  // (3) owner epilogue
+  if (active) {
+    const double4 xi = s_rec[0][tid], vi = s_rec[1][tid], wi = s_rec[2][tid];
+    const int imask = rec_mask(wi.w);
+    if (P.have_pair) { const int nh = s_nh[tid]; if (nh != nh0) P.numneigh[i] = nn | (nh << 16); }
     if (P.have_g && (imask & 1)) { F[0] += vi.w * P.g[0]; F[1] += vi.w * P.g[1]; F[2] += vi.w * P.g[2]; }
     if (P.nwc) {  // primitive-wall contacts were evaluated by the k_walls pre-pass
       const unsigned widx = (unsigned)(__double_as_longlong(P.xh[i].w) >> 32);
