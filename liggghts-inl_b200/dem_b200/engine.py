@@ -12,6 +12,7 @@ ABI_SYMBOLS = [
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
+    "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_contact_count", "dem_download_mesh_contacts",
 ]
 
 
@@ -35,6 +36,30 @@ def load_library(path=None):
     if not os.path.exists(path):
         raise DemError("libdem_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
     return C.CDLL(path)
+
+
+def read_stl(path):
+    """ASCII or binary STL -> (ntri, 3, 3) float64 (the reference: input_mesh_tri.cpp:308-591)"""
+    raw = open(path, "rb").read()
+    head = raw[:512].lstrip().lower()
+    if head.startswith(b"solid") and b"facet" in raw[:4096].lower():
+        v = [[float(t) for t in line.split()[1:4]] for line in raw.decode("ascii", "replace").splitlines() if line.strip().startswith("vertex")]
+        return np.asarray(v, np.float64).reshape(-1, 3, 3)
+    n = int(np.frombuffer(raw[80:84], "<u4")[0])
+    rec = np.frombuffer(raw[84:84 + 50 * n], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    return rec["v"].astype(np.float64)
+
+
+def write_stl(path, nodes, name="mesh"):
+    """ASCII STL with round-trip (%.17g) vertices"""
+    with open(path, "w") as f:
+        f.write("solid %s\n" % name)
+        for t in np.asarray(nodes, np.float64).reshape(-1, 3, 3):
+            f.write(" facet normal 0 0 0\n  outer loop\n")
+            for v in t:
+                f.write("   vertex %.17g %.17g %.17g\n" % tuple(v))
+            f.write("  endloop\n endfacet\n")
+        f.write("endsolid %s\n" % name)
 
 
 def _strv(args):
@@ -137,6 +162,26 @@ class Engine:
         n, a = _strv(text.split())
         self._call("add_wall_primitive", [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)], wall_id.encode(), n, a)
 
+    def mesh(self, mesh_id, atom_type, nodes, options=""):
+        """`fix ID all mesh/surface file F type T [options]`; nodes = the file's triangles, shape (ntri, 3, 3)"""
+        nd = np.ascontiguousarray(nodes, np.float64).reshape(-1, 9)
+        n, a = _strv(options.split())
+        self._call("add_mesh", [C.c_char_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.POINTER(C.c_char_p)],
+                   mesh_id.encode(), int(atom_type), nd.ctypes.data, len(nd), n, a)
+
+    def mesh_stl(self, mesh_id, atom_type, path, options=""):
+        self.mesh(mesh_id, atom_type, read_stl(path), options)
+
+    def move_mesh(self, mesh_id, text):
+        """`fix ID all move/mesh mesh MESH linear vx vy vz`"""
+        n, a = _strv(text.split())
+        self._call("move_mesh", [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)], mesh_id.encode(), n, a)
+
+    def wall_mesh(self, wall_id, text):
+        """text as in the deck after `fix ID all wall/gran`: 'model ... mesh n_meshes N meshes id...'"""
+        n, a = _strv(text.split())
+        self._call("add_wall_mesh", [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)], wall_id.encode(), n, a)
+
     def gravity(self, magnitude, direction):
         self._call("set_gravity", [C.c_double, C.POINTER(C.c_double)], magnitude, (C.c_double * 3)(*direction))
 
@@ -197,6 +242,25 @@ class Engine:
         out = np.zeros((n, max(dnum, 1)), np.float64)
         self._call("download_wall_history", [C.c_char_p, C.c_void_p, C.c_long], wall_id.encode(), out.ctypes.data, n)
         return out[:, :dnum]
+
+    def mesh_field(self, mesh_id, field, ntri):
+        """topology / geometry of a mesh: nodes (ntri,3,3) f64; edge_active, corner_active (ntri,3) i32; obtuse, nneighs (ntri,) i32"""
+        if field == "nodes":
+            out = np.zeros((ntri, 3, 3), np.float64)
+        elif field in ("edge_active", "corner_active"):
+            out = np.zeros((ntri, 3), np.int32)
+        else:
+            out = np.zeros(ntri, np.int32)
+        self._call("download_mesh", [C.c_char_p, C.c_char_p, C.c_void_p, C.c_long], mesh_id.encode(), field.encode(), out.ctypes.data, out.size)
+        return out
+
+    def mesh_contacts(self, mesh_id):
+        """per-particle mesh contact rows (fix_contact_history_mesh): sorted by (tag, triangle id)"""
+        n = C.c_long(0); dnum = C.c_int(0)
+        self._call("mesh_contact_count", [C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_int)], mesh_id.encode(), C.byref(n), C.byref(dnum))
+        tag = np.zeros(n.value, np.int32); tri = np.zeros(n.value, np.int32); hist = np.zeros((n.value, max(dnum.value, 1)), np.float64)
+        self._call("download_mesh_contacts", [C.c_char_p] + [C.c_void_p] * 3, mesh_id.encode(), tag.ctypes.data, tri.ctypes.data, hist.ctypes.data)
+        return {"tag": tag, "tri": tri, "hist": hist[:, :dnum.value]}
 
     def stats(self):
         s = Stats()

@@ -50,6 +50,27 @@ typedef struct {
   double *hist;              /* n x dnum, fix property/atom "history_<id>" */
 } wall_t;
 
+#define MAXMESH 8
+#define NUM_NEIGH_MAX 5      /* tri_mesh.h:67 SurfaceMesh<3,5> */
+#define EPSILON_PRECISION 1e-8   /* multi_node_mesh.h:59 */
+#define EPSILON_CURVATURE 0.00001 /* surface_mesh.h:61 */
+#define SMALL_TRIMESH (1.e-10)   /* tri_mesh_I.h:47-50 */
+#define LARGE_TRIMESH 1000000
+#define SMALL_DELTA_MESH 1e-6
+
+typedef struct {  /* TriMesh + FixNeighlistMesh + FixContactHistoryMesh of one `fix mesh/surface` */
+  char id[64]; int atom_type; int ntri; int wall; /* wall: index of the mesh wall fix using it (-1 none) */
+  double (*node)[3][3], (*center)[3], *rbound, (*edgeVec)[3][3], (*edgeLen)[3], (*surfNorm)[3], (*edgeNorm)[3][3];
+  int *obtuse, *nNeighs, (*neighFaces)[NUM_NEIGH_MAX]; unsigned char (*edgeActive)[3], (*cornerActive)[3];
+  double curvature, precision;
+  int moving; double vel[3]; double (*vnode)[3][3]; double (*nodesLastRe)[3][3]; int next_reneighbor;
+  /* FixNeighlistMesh: per-triangle particle lists */
+  int **contacts; int *ncontacts, *capcontacts;
+  /* FixContactHistoryMesh: per-particle rows sized by the particle's candidate count */
+  int *nneighs, *npartner; int **partner; double **chist; unsigned char **keep;
+} mesh_t;
+typedef struct { char id[64]; model_t m; int nmesh; int mesh[MAXMESH]; } meshwall_t;
+
 typedef struct orc_engine {
   char err[256];
   double lo[3], hi[3], prd[3]; int periodic[3];
@@ -62,6 +83,7 @@ typedef struct orc_engine {
   double Yeff[MAXT + 1][MAXT + 1], Geff[MAXT + 1][MAXT + 1], betaeff[MAXT + 1][MAXT + 1], corLog[MAXT + 1][MAXT + 1];
   model_t pm; int have_pair;
   wall_t walls[MAXW]; int nwalls;
+  mesh_t meshes[MAXMESH]; int nmeshes; meshwall_t mwalls[MAXMESH]; int nmwalls;
   double g[3]; int have_gravity;
   int freezebit, integbit;
   double cdf; /* neighbor->contactDistanceFactor (1.0 without bond models) */
@@ -471,6 +493,436 @@ static void chain_close(const model_t *m, double *hist, int *flag)
   if (m->off_roll >= 0) { if (flag) *flag &= ~CONTACT_ROLLING; for (int d = 0; d < 3; d++) hist[m->off_roll + d] = 0.0; }
 }
 
+
+/* ================================================================ triangle mesh walls
+ * fix mesh/surface + fix wall/gran ... mesh: geometry, topology, candidate lists, contact history. */
+static void v3sub(const double *a, const double *b, double *r) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+static double v3dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static double v3mag(const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+static void v3cross(const double *a, const double *b, double *r) { r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0]; }
+static void v3sdiv(double *v, double s) { const double sinv = 1. / s; v[0] = sinv * v[0]; v[1] = sinv * v[1]; v[2] = sinv * v[2]; } /* vector_liggghts.h:288-294 */
+static int comp_double(double a, double b, double prec)
+{ /* math_extra_liggghts.h:560-571 */
+  if (a == b) return 1;
+  if (b == 0) return a < prec && a > -prec;
+  const double x = (a - b);
+  return x < prec && x > -prec;
+}
+static int nodes_equal(const mesh_t *M, const double *a, const double *b)
+{ for (int d = 0; d < 3; d++) if (!comp_double(a[d], b[d], M->precision)) return 0; return 1; } /* multi_node_mesh_I.h:246-261 */
+
+static void tri_properties(mesh_t *M, int n)
+{ /* multi_node_mesh_I.h:153-172 (center, rBound) ; surface_mesh_I.h:302-470 */
+  double avg[3] = {0., 0., 0.};
+  for (int i = 0; i < 3; i++) for (int d = 0; d < 3; d++) avg[d] = M->node[n][i][d] + avg[d];
+  v3sdiv(avg, 3.0);
+  for (int d = 0; d < 3; d++) M->center[n][d] = avg[d];
+  double rb = 0.;
+  for (int i = 0; i < 3; i++) { double vec[3]; v3sub(M->center[n], M->node[n][i], vec); const double m = v3mag(vec); if (m > rb) rb = m; }
+  M->rbound[n] = rb;
+  for (int i = 0; i < 3; i++) { /* calcEdgeVecLen */
+    v3sub(M->node[n][(i + 1) % 3], M->node[n][i], M->edgeVec[n][i]);
+    M->edgeLen[n][i] = v3mag(M->edgeVec[n][i]);
+    v3sdiv(M->edgeVec[n][i], M->edgeLen[n][i]);
+  }
+  double *sn = M->surfNorm[n]; /* calcSurfaceNorm (non-degenerate branch) */
+  v3cross(M->edgeVec[n][0], M->edgeVec[n][1], sn);
+  v3sdiv(sn, v3mag(sn));
+  for (int i = 0; i < 3; i++) { /* calcEdgeNormals */
+    v3cross(M->edgeVec[n][i], sn, M->edgeNorm[n][i]);
+    v3sdiv(M->edgeNorm[n][i], v3mag(M->edgeNorm[n][i]));
+  }
+  /* calcObtuseAngleIndex is called for iNode = 0,1,2 and each call overwrites the value (surface_mesh_I.h:331-339,
+   * 455-467): what survives is the verdict of node 2 */
+  M->obtuse[n] = -1;
+  for (int i = 0; i < 3; i++) { const double dot = v3dot(M->edgeVec[n][i], M->edgeVec[n][(i - 1 + 3) % 3]); M->obtuse[n] = dot > 0. ? i : -1; }
+}
+
+static int share_edge(const mesh_t *M, int i, int j, int *iEdge, int *jEdge)
+{ /* multi_node_mesh_I.h:281-321 share2Nodes + surface_mesh_I.h:1040-1066 shareEdge */
+  double dist[3]; v3sub(M->center[i], M->center[j], dist);
+  const double radsum = M->rbound[i] + M->rbound[j];
+  if (v3dot(dist, dist) > radsum * radsum) return 0;
+  int nShared = 0, i1 = -1, j1 = -1, i2 = -1, j2 = -1;
+  for (int a = 0; a < 3 && i2 < 0; a++) for (int b = 0; b < 3; b++) if (nodes_equal(M, M->node[i][a], M->node[j][b])) {
+    if (nShared == 0) { i1 = a; j1 = b; } else { i2 = a; j2 = b; break; }
+    nShared++;
+  }
+  if (i2 < 0) return 0;
+  *iEdge = (2 == i1 + i2) ? 2 : (i1 < i2 ? i1 : i2);
+  *jEdge = (2 == j1 + j2) ? 2 : (j1 < j2 ? j1 : j2);
+  return 1;
+}
+static int n_shared_nodes(const mesh_t *M, int i, int j)
+{ int n = 0; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) if (nodes_equal(M, M->node[i][a], M->node[j][b])) n++; return n; }
+
+static int coplanar_neighs_overlap(const mesh_t *M, int i, int iEdge, int j, int jEdge)
+{ /* surface_mesh_I.h:965-1003 */
+  double vecI[3], vecJ[3];
+  const double *pRef = M->node[i][iEdge], *edgeN = M->edgeNorm[i][iEdge];
+  v3sub(M->node[i][(iEdge + 2) % 3], pRef, vecI); v3sub(M->node[j][(jEdge + 2) % 3], pRef, vecJ);
+  return v3dot(vecI, edgeN) * v3dot(vecJ, edgeN) > 0.;
+}
+static void handle_shared_edge(mesh_t *M, int i, int iEdge, int j, int jEdge, int coplanar)
+{ /* surface_mesh_I.h:1071-1144 (ids == indices; the *Active_ override flags are all false) */
+  if (M->nNeighs[i] < NUM_NEIGH_MAX) M->neighFaces[i][M->nNeighs[i]] = j;
+  if (M->nNeighs[j] < NUM_NEIGH_MAX) M->neighFaces[j][M->nNeighs[j]] = i;
+  M->nNeighs[i]++; M->nNeighs[j]++;
+  if (!coplanar || coplanar_neighs_overlap(M, i, iEdge, j, jEdge)) {
+    if (i < j) { M->edgeActive[i][iEdge] = 0; M->edgeActive[j][jEdge] = 1; }
+    else { M->edgeActive[i][iEdge] = 1; M->edgeActive[j][jEdge] = 0; }
+  } else { M->edgeActive[i][iEdge] = 0; M->edgeActive[j][jEdge] = 0; }
+}
+typedef struct { int nVisited, nHasNode, anyActive; int *visited, *hasNode; double (*edgeList)[3], (*endPoint)[3]; } corner_t;
+static void check_node_recursive(const mesh_t *M, int iSrf, const double *node, corner_t *C)
+{ /* surface_mesh_I.h:1192-1236 */
+  for (int k = 0; k < C->nVisited; k++) if (C->visited[k] == iSrf) return;
+  C->visited[C->nVisited++] = iSrf;
+  int iNode = -1;
+  for (int a = 0; a < 3 && iNode < 0; a++) if (nodes_equal(M, M->node[iSrf][a], node)) iNode = a; /* containsNode */
+  if (iNode < 0) return;
+  int ne = 2 * C->nHasNode;
+  C->hasNode[C->nHasNode++] = iSrf;
+  const int im = (iNode - 1 + 3) % 3;
+  memcpy(C->edgeList[ne], M->edgeVec[iSrf][iNode], 24); memcpy(C->endPoint[ne++], M->node[iSrf][(iNode + 1) % 3], 24);
+  memcpy(C->edgeList[ne], M->edgeVec[iSrf][im], 24); memcpy(C->endPoint[ne++], M->node[iSrf][im], 24);
+  if (M->edgeActive[iSrf][iNode]) C->anyActive = 1; else if (M->edgeActive[iSrf][im]) C->anyActive = 1;
+  const int nn = M->nNeighs[iSrf] < NUM_NEIGH_MAX ? M->nNeighs[iSrf] : NUM_NEIGH_MAX;
+  for (int k = 0; k < nn; k++) { const int idN = M->neighFaces[iSrf][k]; if (idN < 0) return; check_node_recursive(M, idN, node, C); }
+}
+static int in_subdomain(const orc_engine *e, const double *pos)
+{ /* domain_I.h:65-87, one rank: sub-box == box, padded by SMALL_DMBRDR = 1e-8 */
+  for (int d = 0; d < 3; d++) if (!(pos[d] >= e->lo[d] - 1.0e-8 && pos[d] < e->hi[d] + 1.0e-8)) return 0;
+  return 1;
+}
+static void mesh_topology(const orc_engine *e, mesh_t *M)
+{ /* SurfaceMesh::buildNeighbours surface_mesh_I.h:474-582 */
+  const int n = M->ntri;
+  for (int i = 0; i < n; i++) {
+    M->nNeighs[i] = 0;
+    for (int k = 0; k < NUM_NEIGH_MAX; k++) M->neighFaces[i][k] = -1;
+    for (int k = 0; k < 3; k++) { M->edgeActive[i][k] = 1; M->cornerActive[i][k] = 1; }
+  }
+  for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) { /* elements inserted before i (:519-545) */
+    int iEdge = 0, jEdge = 0;
+    if (share_edge(M, i, j, &iEdge, &jEdge)) {
+      const double dot = v3dot(M->surfNorm[i], M->surfNorm[j]);
+      handle_shared_edge(M, i, iEdge, j, jEdge, fabs(dot) >= M->curvature); /* areCoplanar :874-890 */
+    }
+  }
+  corner_t C; C.visited = (int *)malloc(sizeof(int) * (n + 1)); C.hasNode = (int *)malloc(sizeof(int) * (n + 1));
+  C.edgeList = (double (*)[3])malloc(sizeof(double) * 3 * 2 * (n + 1)); C.endPoint = (double (*)[3])malloc(sizeof(double) * 3 * 2 * (n + 1));
+  for (int i = 0; i < n; i++) for (int iNode = 0; iNode < 3; iNode++) { /* handleCorner :1148-1188 */
+    C.nVisited = C.nHasNode = C.anyActive = 0;
+    check_node_recursive(M, i, M->node[i][iNode], &C);
+    if (!in_subdomain(e, M->node[i][iNode])) continue;
+    int maxId = -1; for (int k = 0; k < C.nHasNode; k++) if (C.hasNode[k] > maxId) maxId = C.hasNode[k];
+    int colinear = 0; const int nE = 2 * C.nHasNode;
+    for (int a = 0; a < nE; a++) for (int b = a + 1; b < nE; b++)
+      if (fabs(v3dot(C.edgeList[a], C.edgeList[b])) > M->curvature && !nodes_equal(M, C.endPoint[a], C.endPoint[b])) colinear = 1; /* edgeVecsColinear :1007-1014 */
+    if (colinear || !C.anyActive) M->cornerActive[i][iNode] = 0;
+    else if (i == maxId) M->cornerActive[i][iNode] = 1;
+    else M->cornerActive[i][iNode] = 0;
+  }
+  free(C.visited); free(C.hasNode); free(C.edgeList); free(C.endPoint);
+}
+static int coplanar_node_neighs(const mesh_t *M, int a, int b)
+{ /* surface_mesh_I.h:921-958 areCoplanarNodeNeighs */
+  int areNeighs = 0;
+  const int nn = M->nNeighs[a] < NUM_NEIGH_MAX ? M->nNeighs[a] : NUM_NEIGH_MAX;
+  for (int k = 0; k < nn; k++) if (M->neighFaces[a][k] == b) areNeighs = 1;
+  if (!areNeighs && n_shared_nodes(M, a, b) == 0) return 0;
+  return fabs(v3dot(M->surfNorm[a], M->surfNorm[b])) > M->curvature;
+}
+
+int orc_add_mesh(orc_engine *e, const char *id, int atom_type, const double *nodes, long ntri, int argc, const char *const *argv)
+{ /* fix mesh/surface file F type T : fix_mesh.cpp:90-260, fix_mesh_surface.cpp:90-330 (nodes are the file's vertices) */
+  if (e->nmeshes == MAXMESH) return fail(e, "too many meshes");
+  mesh_t *M = &e->meshes[e->nmeshes]; memset(M, 0, sizeof *M);
+  snprintf(M->id, sizeof M->id, "%s", id); M->atom_type = atom_type; M->ntri = (int)ntri; M->wall = -1;
+  M->curvature = 1. - EPSILON_CURVATURE; M->precision = EPSILON_PRECISION;
+  for (int k = 0; k + 1 < argc; k += 2) {
+    if (!strcmp(argv[k], "curvature")) M->curvature = cos(atof(argv[k + 1]) * M_PI / 180.); /* fix_mesh.cpp: curvature given in degrees */
+    else if (!strcmp(argv[k], "precision")) M->precision = atof(argv[k + 1]);
+    else return fail(e, "mesh option not supported by the oracle");
+  }
+  const size_t T = (size_t)(ntri ? ntri : 1);
+  M->node = calloc(T, sizeof *M->node); M->center = calloc(T, sizeof *M->center); M->rbound = calloc(T, sizeof(double));
+  M->edgeVec = calloc(T, sizeof *M->edgeVec); M->edgeLen = calloc(T, sizeof *M->edgeLen); M->surfNorm = calloc(T, sizeof *M->surfNorm);
+  M->edgeNorm = calloc(T, sizeof *M->edgeNorm); M->obtuse = calloc(T, sizeof(int)); M->nNeighs = calloc(T, sizeof(int));
+  M->neighFaces = calloc(T, sizeof *M->neighFaces); M->edgeActive = calloc(T, sizeof *M->edgeActive); M->cornerActive = calloc(T, sizeof *M->cornerActive);
+  M->vnode = calloc(T, sizeof *M->vnode); M->nodesLastRe = calloc(T, sizeof *M->nodesLastRe);
+  M->contacts = calloc(T, sizeof(int *)); M->ncontacts = calloc(T, sizeof(int)); M->capcontacts = calloc(T, sizeof(int));
+  memcpy(M->node, nodes, sizeof(double) * 9 * ntri);
+  for (int n = 0; n < ntri; n++) tri_properties(M, n);
+  mesh_topology(e, M);
+  e->nmeshes++; return 0;
+}
+int orc_move_mesh(orc_engine *e, const char *mesh_id, int argc, const char *const *argv)
+{ /* fix move/mesh mesh ID linear vx vy vz : fix_move_mesh.cpp, mesh_mover_linear.cpp:94-112 */
+  for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) {
+    if (argc != 4 || strcmp(argv[0], "linear")) return fail(e, "only 'linear vx vy vz' is supported");
+    for (int d = 0; d < 3; d++) e->meshes[m].vel[d] = atof(argv[1 + d]);
+    e->meshes[m].moving = 1; e->meshes[m].next_reneighbor = -1; return 0; }
+  return fail(e, "no such mesh");
+}
+int orc_add_wall_mesh(orc_engine *e, const char *id, int argc, const char *const *argv)
+{ /* fix wall/gran model ... mesh n_meshes N meshes id... : fix_wall_gran.cpp:171-330 */
+  if (e->nmwalls == MAXMESH) return fail(e, "too many mesh walls");
+  meshwall_t *W = &e->mwalls[e->nmwalls]; memset(W, 0, sizeof *W); snprintf(W->id, sizeof W->id, "%s", id);
+  if (parse_model(e, &argc, &argv, &W->m)) return -1;
+  if (argc < 4 || strcmp(argv[0], "mesh") || strcmp(argv[1], "n_meshes")) return fail(e, "expected 'mesh n_meshes N meshes ...'");
+  W->nmesh = atoi(argv[2]);
+  if (W->nmesh < 1 || W->nmesh > MAXMESH || argc < 4 + W->nmesh || strcmp(argv[3], "meshes")) return fail(e, "bad mesh list");
+  for (int k = 0; k < W->nmesh; k++) {
+    int found = -1; for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, argv[4 + k])) found = m;
+    if (found < 0) return fail(e, "unknown mesh id");
+    W->mesh[k] = found; e->meshes[found].wall = e->nmwalls;
+  }
+  argv += 4 + W->nmesh; argc -= 4 + W->nmesh;
+  if (parse_settings(e, argc, argv, &W->m)) return -1;
+  e->nmwalls++; return 0;
+}
+
+/* TriMesh::resolveTriSphereNeighbuild tri_mesh_I.h:275-305 */
+static int tri_sphere_neighbuild(const mesh_t *M, int t, double rSphere, const double *c, double treshold)
+{
+  const double maxDist = rSphere + treshold;
+  double v[3]; v3sub(c, M->center[t], v);
+  if (fabs(v3dot(M->surfNorm[t], v)) > maxDist) return 0;
+  const double dParaMax = maxDist * maxDist;
+  for (int i = 0; i < 3; i++) { v3sub(c, M->node[t][i], v); const double d = v3dot(M->edgeNorm[t][i], v); if (d > 0 && d * d > dParaMax) return 0; }
+  return 1;
+}
+static double calc_dist(const double *cs, const double *cp, double *delta)
+{ v3sub(cp, cs, delta); return sqrt((cs[0] - cp[0]) * (cs[0] - cp[0]) + (cs[1] - cp[1]) * (cs[1] - cp[1]) + (cs[2] - cp[2]) * (cs[2] - cp[2])); } /* tri_mesh_I.h:309-313 */
+static double resolve_edge(const mesh_t *M, int t, int iEdge, const double *p, double *delta, double *bary)
+{ /* tri_mesh_I.h:129-170, skip_inactive = true */
+  const int ip = (iEdge + 1) % 3, ipp = (iEdge + 2) % 3; double nodeToP[3];
+  v3sub(p, M->node[t][iEdge], nodeToP);
+  const double distFromNode = v3dot(nodeToP, M->edgeVec[t][iEdge]);
+  if (distFromNode < -SMALL_TRIMESH) {
+    if (!M->cornerActive[t][iEdge]) return LARGE_TRIMESH;
+    bary[iEdge] = 1.; bary[ip] = 0.; bary[ipp] = 0.;
+    return calc_dist(p, M->node[t][iEdge], delta);
+  } else if (distFromNode > M->edgeLen[t][iEdge] + SMALL_TRIMESH) {
+    if (!M->cornerActive[t][ip]) return LARGE_TRIMESH;
+    bary[iEdge] = 0.; bary[ip] = 1.; bary[ipp] = 0.;
+    return calc_dist(p, M->node[t][ip], delta);
+  }
+  if (!M->edgeActive[t][iEdge]) return LARGE_TRIMESH;
+  double cp[3]; for (int d = 0; d < 3; d++) cp[d] = M->node[t][iEdge][d] + distFromNode * M->edgeVec[t][iEdge][d];
+  const double dd = calc_dist(p, cp, delta);
+  bary[ipp] = 0.; bary[iEdge] = 1. - distFromNode / M->edgeLen[t][iEdge]; bary[ip] = 1. - bary[iEdge];
+  return dd;
+}
+static double resolve_corner(const mesh_t *M, int t, int iNode, int obtuse, const double *p, double *delta, double *bary)
+{ /* tri_mesh_I.h:174-255 */
+  const int ip = (iNode + 1) % 3, ipp = (iNode + 2) % 3; const double *n = M->node[t][iNode];
+  if (obtuse) {
+    double nodeToP[3], cp[3]; v3sub(p, n, nodeToP);
+    double distFromNode = v3dot(nodeToP, M->edgeVec[t][ipp]);
+    if (distFromNode < SMALL_TRIMESH) {
+      if (distFromNode > -M->edgeLen[t][ipp]) {
+        if (!M->edgeActive[t][ipp]) return LARGE_TRIMESH;
+        for (int d = 0; d < 3; d++) cp[d] = n[d] + distFromNode * M->edgeVec[t][ipp][d];
+        bary[ip] = 0.; bary[iNode] = 1. + distFromNode / M->edgeLen[t][ipp]; bary[ipp] = 1. - bary[iNode];
+        return calc_dist(p, cp, delta);
+      } else {
+        if (!M->cornerActive[t][ipp]) return LARGE_TRIMESH;
+        bary[ipp] = 1.; bary[iNode] = bary[ip] = 0.;
+        return calc_dist(p, M->node[t][ipp], delta);
+      }
+    }
+    distFromNode = v3dot(nodeToP, M->edgeVec[t][iNode]);
+    if (distFromNode > -SMALL_TRIMESH) {
+      if (distFromNode < M->edgeLen[t][iNode]) {
+        if (!M->edgeActive[t][iNode]) return LARGE_TRIMESH;
+        for (int d = 0; d < 3; d++) cp[d] = n[d] + distFromNode * M->edgeVec[t][iNode][d];
+        bary[ipp] = 0.; bary[iNode] = 1. - distFromNode / M->edgeLen[t][iNode]; bary[ip] = 1. - bary[iNode];
+        return calc_dist(p, cp, delta);
+      } else {
+        if (!M->cornerActive[t][ip]) return LARGE_TRIMESH;
+        bary[ip] = 1.; bary[iNode] = bary[ipp] = 0.;
+        return calc_dist(p, M->node[t][ip], delta);
+      }
+    }
+  }
+  if (!M->cornerActive[t][iNode]) return LARGE_TRIMESH;
+  bary[iNode] = 1.; bary[ip] = bary[ipp] = 0.;
+  return calc_dist(p, n, delta);
+}
+/* TriMesh::resolveTriSphereContactBary tri_mesh_I.h:65-127 ; returns distance - radius */
+static double tri_sphere_contact(const mesh_t *M, int t, double rSphere, const double *c, double *delta, double *bary, int *barySign)
+{
+  double n0c[3]; v3sub(c, M->node[t][0], n0c);
+  bary[0] = bary[1] = bary[2] = 0.;
+  { /* MathExtraLiggghts::calcBaryTriCoords math_extra_liggghts.h:583-594 */
+    const double a = v3dot(n0c, M->edgeVec[t][0]), b = v3dot(n0c, M->edgeVec[t][2]), cc = v3dot(M->edgeVec[t][0], M->edgeVec[t][2]);
+    const double oneMinCSqr = 1 - cc * cc;
+    bary[1] = (a - b * cc) / (M->edgeLen[t][0] * oneMinCSqr);
+    bary[2] = (a * cc - b) / (M->edgeLen[t][2] * oneMinCSqr);
+    bary[0] = 1. - bary[1] - bary[2];
+  }
+  const double invlen = 1. / (2. * M->rbound[t]);
+  const int bs = (bary[0] > -M->precision * invlen) + 2 * (bary[1] > -M->precision * invlen) + 4 * (bary[2] > -M->precision * invlen);
+  *barySign = bs;
+  const int ob = M->obtuse[t];
+  double d = 1.;
+  switch (bs) {
+    case 1: d = resolve_corner(M, t, 0, ob == 0, c, delta, bary); break;
+    case 2: d = resolve_corner(M, t, 1, ob == 1, c, delta, bary); break;
+    case 3: d = resolve_edge(M, t, 0, c, delta, bary); break;
+    case 4: d = resolve_corner(M, t, 2, ob == 2, c, delta, bary); break;
+    case 5: d = resolve_edge(M, t, 2, c, delta, bary); break;
+    case 6: d = resolve_edge(M, t, 1, c, delta, bary); break;
+    case 7: { /* resolveFaceContactBary :259-271 */
+      const double dNorm = v3dot(M->surfNorm[t], n0c); double cs[3];
+      for (int k = 0; k < 3; k++) cs[k] = c[k] - M->surfNorm[t][k] * dNorm;
+      d = calc_dist(c, cs, delta); break; }
+    default: d = 1.; break;
+  }
+  return d - rSphere;
+}
+
+static double cutneighmax_of(const orc_engine *e)
+{ double rmax = 0.0; for (long i = 0; i < e->n; i++) if (e->radius[i] > rmax) rmax = e->radius[i]; return 2.0 * rmax * e->cdf + e->skin; }
+
+static void mesh_sort_contacts(orc_engine *e, mesh_t *M)
+{ /* FixContactHistoryMesh::sort_contacts fix_contact_history_mesh.cpp:375-403 (pre_exchange) */
+  const int dnum = e->mwalls[M->wall].m.dnum;
+  if (!M->nneighs) return;
+  for (long i = 0; i < e->n; i++) {
+    const int nn = M->nneighs[i]; if (!nn) continue;
+    int fe, lf;
+    do {
+      fe = lf = -1;
+      for (int j = 0; j < nn; j++) { if (fe == -1 && M->partner[i][j] == -1) fe = j; if (M->partner[i][j] >= 0) lf = j; }
+      if (fe > -1 && lf > -1 && fe < lf) { /* swap(i, fe, lf, true) */
+        int t = M->partner[i][fe]; M->partner[i][fe] = M->partner[i][lf]; M->partner[i][lf] = t;
+        for (int d = 0; d < dnum; d++) { double h = M->chist[i][fe * dnum + d]; M->chist[i][fe * dnum + d] = M->chist[i][lf * dnum + d]; M->chist[i][lf * dnum + d] = h; }
+      }
+    } while (fe > -1 && lf > -1 && fe < lf);
+  }
+}
+static int contact_in_list(const mesh_t *M, int t, int i) { for (int k = 0; k < M->ncontacts[t]; k++) if (M->contacts[t][k] == i) return 1; return 0; }
+
+static void mesh_build(orc_engine *e, mesh_t *M)
+{ /* FixNeighlistMesh::pre_force fix_neighlist_mesh.cpp:230-307 + FixContactHistoryMesh::pre_force fix_contact_history_mesh.cpp:315-371 */
+  const long n = e->n; const int dnum = e->mwalls[M->wall].m.dnum;
+  const double skin = M->moving ? e->skin : 0.5 * e->skin;
+  int *nn_new = (int *)calloc(n ? n : 1, sizeof(int));
+  for (int t = 0; t < M->ntri; t++) {
+    M->ncontacts[t] = 0;
+    for (long i = 0; i < n; i++)
+      if (tri_sphere_neighbuild(M, t, e->radius[i] * e->cdf, &e->x[3 * i], skin)) {
+        if (M->ncontacts[t] == M->capcontacts[t]) { M->capcontacts[t] = M->capcontacts[t] ? 2 * M->capcontacts[t] : 8; M->contacts[t] = realloc(M->contacts[t], sizeof(int) * M->capcontacts[t]); }
+        M->contacts[t][M->ncontacts[t]++] = (int)i; nn_new[i]++;
+      }
+  }
+  if (!M->nneighs) { /* first build */
+    M->nneighs = (int *)calloc(n ? n : 1, sizeof(int)); M->npartner = (int *)calloc(n ? n : 1, sizeof(int));
+    M->partner = (int **)calloc(n ? n : 1, sizeof(int *)); M->chist = (double **)calloc(n ? n : 1, sizeof(double *)); M->keep = (unsigned char **)calloc(n ? n : 1, sizeof(unsigned char *));
+  }
+  for (long i = 0; i < n; i++) {
+    /* cleanUpContactJumps :467-504 */
+    int ip = 0;
+    while (ip < M->npartner[i]) {
+      if (!contact_in_list(M, M->partner[i][ip], (int)i)) {
+        const int last = M->npartner[i] - 1;
+        M->partner[i][ip] = -1; for (int d = 0; d < dnum; d++) M->chist[i][ip * dnum + d] = 0.0;
+        int t = M->partner[i][ip]; M->partner[i][ip] = M->partner[i][last]; M->partner[i][last] = t;
+        for (int d = 0; d < dnum; d++) { double h = M->chist[i][ip * dnum + d]; M->chist[i][ip * dnum + d] = M->chist[i][last * dnum + d]; M->chist[i][last * dnum + d] = h; }
+        M->npartner[i]--;
+      } else ip++;
+    }
+    const int nn = nn_new[i];
+    int *pn = (int *)malloc(sizeof(int) * (nn ? nn : 1)); double *hn = (double *)calloc((size_t)(nn ? nn : 1) * (dnum ? dnum : 1), sizeof(double));
+    for (int k = 0; k < nn; k++) pn[k] = -1;
+    for (int k = 0; k < M->npartner[i] && k < nn; k++) { pn[k] = M->partner[i][k]; for (int d = 0; d < dnum; d++) hn[k * dnum + d] = M->chist[i][k * dnum + d]; }
+    free(M->partner[i]); free(M->chist[i]); free(M->keep[i]);
+    M->partner[i] = pn; M->chist[i] = hn; M->keep[i] = (unsigned char *)calloc(nn ? nn : 1, 1); M->nneighs[i] = nn;
+  }
+  free(nn_new);
+  memcpy(M->nodesLastRe, M->node, sizeof(double) * 9 * M->ntri); /* storeNodePosRebuild */
+}
+
+static void mesh_wall_compute(orc_engine *e, meshwall_t *W, int shearupdate)
+{ /* FixWallGran::post_force_mesh fix_wall_gran.cpp:803-982 + fix_contact_history_mesh_I.h:51-215 */
+  const int dnum = W->m.dnum; const double cdmul = e->cdf - 1.0; const double cutneighmax = cutneighmax_of(e);
+  for (int im = 0; im < W->nmesh; im++) {
+    mesh_t *M = &e->meshes[W->mesh[im]];
+    for (long i = 0; i < e->n; i++) for (int k = 0; k < M->nneighs[i]; k++) M->keep[i][k] = 0; /* markAllContacts */
+    for (int t = 0; t < M->ntri; t++) for (int c = 0; c < M->ncontacts[t]; c++) {
+      const int ip = M->contacts[t][c];
+      double delta[3], bary[3]; int barysign = -1;
+      const double radi = e->radius[ip];
+      const double deltan = tri_sphere_contact(M, t, radi, &e->x[3 * ip], delta, bary, &barysign);
+      if (deltan > cutneighmax) continue;
+      const int intersect = (deltan <= 0);
+      if (!(deltan <= 0 || deltan < cdmul * radi)) continue;
+      /* handleContact */
+      const int nn = M->nneighs[ip]; int *tri = M->partner[ip]; double *hist = NULL; int have = 0;
+      for (int k = 0; k < nn; k++) if (tri[k] == t) { hist = &M->chist[ip][k * dnum]; M->keep[ip][k] = 1; have = 1; break; }
+      if (!have) {
+        const int faceflag = (7 == barysign);
+        if (faceflag) { /* coplanarContactAlready */
+          int already = 0;
+          for (int k = 0; k < nn; k++) { const int q = tri[k]; if (q >= 0 && q != t && coplanar_node_neighs(M, q, t) && M->keep[ip][k]) { already = 1; break; } }
+          if (already) continue;
+        }
+        int ic = -1; for (int k = 0; k < nn; k++) if (tri[k] == -1) { ic = k; break; } /* addNewTriContactToExistingParticle */
+        if (ic < 0) { snprintf(e->err, sizeof e->err, "mesh contact rows full"); continue; }
+        tri[ic] = t; M->keep[ip][ic] = 1; hist = &M->chist[ip][ic * dnum];
+        for (int d = 0; d < dnum; d++) hist[d] = 0.0;
+        M->npartner[ip]++;
+        if (faceflag) for (int k = 0; k < nn; k++) if (tri[k] >= 0 && tri[k] != t && coplanar_node_neighs(M, tri[k], t)) for (int d = 0; d < dnum; d++) hist[d] = M->chist[ip][k * dnum + d]; /* checkCoplanarContactHistory */
+      }
+      double v_wall[3] = {0., 0., 0.};
+      if (M->moving) for (int d = 0; d < 3; d++) v_wall[d] = (bary[0] * M->vnode[t][0][d] + bary[1] * M->vnode[t][1][d] + bary[2] * M->vnode[t][2][d]);
+      if (intersect) { /* Walls::Granular::compute_force fix_wall_gran_base.h:159-367 */
+        sid_t s_; sid_t *sd = &s_; memset(sd, 0, sizeof *sd);
+        sd->is_wall = 1; sd->radi = radi; sd->deltan = -deltan;
+        sd->delta[0] = -delta[0]; sd->delta[1] = -delta[1]; sd->delta[2] = -delta[2];
+        sd->vi = &e->v[3 * ip]; sd->vj = v_wall; sd->wi = &e->omega[3 * ip]; sd->wj = NULL;
+        sd->r = sd->radi - sd->deltan; sd->rinv = 1.0 / sd->r;
+        sd->itype = e->type[ip]; sd->jtype = M->atom_type; sd->meff = e->rmass[ip]; sd->mi = e->rmass[ip];
+        sd->shearupdate = shearupdate; sd->radsum = sd->radi;
+        for (int d = 0; d < 3; d++) sd->en[d] = sd->delta[d] * sd->rinv;
+        sd->hist = hist; sd->flag = NULL;
+        chain_intersect(e, &W->m, sd);
+        for (int d = 0; d < 3; d++) { e->f[3 * ip + d] += sd->Fi[d]; e->torque[3 * ip + d] += sd->Ti[d]; }
+      } else chain_close(&W->m, hist, NULL);
+    }
+    /* cleanUpContacts :437-463 */
+    for (long i = 0; i < e->n; i++) for (int k = 0; k < M->nneighs[i]; k++) if (!M->keep[i][k]) {
+      if (M->partner[i][k] > -1) M->npartner[i]--;
+      M->partner[i][k] = -1; for (int d = 0; d < dnum; d++) M->chist[i][k * dnum + d] = 0.0;
+    }
+  }
+}
+
+static void mesh_move_step(orc_engine *e)
+{ /* FixMoveMesh::initial_integrate fix_move_mesh.cpp:221-238 + MeshMoverLinear::initial_integrate mesh_mover_linear.cpp:94-112
+   * + MultiNodeMesh::move(vecIncremental) multi_node_mesh_I.h:502-526 */
+  for (int m = 0; m < e->nmeshes; m++) { mesh_t *M = &e->meshes[m]; if (!M->moving) continue;
+    double dx[3]; for (int d = 0; d < 3; d++) dx[d] = M->vel[d] * e->dt;
+    for (int t = 0; t < M->ntri; t++) {
+      for (int j = 0; j < 3; j++) for (int d = 0; d < 3; d++) { M->node[t][j][d] = M->node[t][j][d] + dx[d]; M->vnode[t][j][d] = 0. + M->vel[d]; }
+      for (int d = 0; d < 3; d++) M->center[t][d] = M->center[t][d] + dx[d];
+    } }
+}
+static int mesh_decide_rebuild(orc_engine *e)
+{ /* FixMesh::pre_force fix_mesh.cpp:553-576 + MultiNodeMesh::decideRebuild multi_node_mesh_I.h:792-826: a node moved more than
+   * skin/2 since the last build -> next_reneighbor = ntimestep + 1 */
+  int any = 0;
+  for (int m = 0; m < e->nmeshes; m++) { mesh_t *M = &e->meshes[m]; if (!M->moving) continue;
+    const double trig = 0.25 * e->skin * e->skin; int flag = 0;
+    for (int t = 0; t < M->ntri && !flag; t++) for (int j = 0; j < 3; j++) { double dd[3]; v3sub(M->node[t][j], M->nodesLastRe[t][j], dd); if (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2] > trig) flag = 1; }
+    if (flag) { M->next_reneighbor = (int)e->ntimestep + 1; any = 1; } }
+  return any;
+}
+
 /* ---------------------------------------------------------------- neighbour build */
 static void pbc_wrap(orc_engine *e)
 { /* domain.cpp Domain::pbc(): owned particles re-enter a periodic box */
@@ -484,6 +936,7 @@ static void pbc_wrap(orc_engine *e)
 static void build(orc_engine *e)
 { /* neigh_gran.cpp:485-644 (granular_bin_no_newton) incl. history remap :590-625 */
   const long n = e->n; const int dnum = e->pm.dnum;
+  for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].wall >= 0) mesh_sort_contacts(e, &e->meshes[m]); /* pre_exchange */
   pbc_wrap(e);
   double rmax = 0.0; for (long i = 0; i < n; i++) if (e->radius[i] > rmax) rmax = e->radius[i];
   const double cutmax = 2.0 * rmax * e->cdf + e->skin; /* pair_gran.cpp:591-603 + skin */
@@ -569,6 +1022,7 @@ static void build(orc_engine *e)
       if (in) W->cand[W->ncand++] = (int)i;
     }
   }
+  for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].wall >= 0) mesh_build(e, &e->meshes[m]);
   e->nbuilds++; e->ago = 0;
 }
 
@@ -666,6 +1120,7 @@ static void compute_forces(orc_engine *e, int shearupdate)
   if (e->have_gravity) for (long i = 0; i < e->n; i++) if (e->mask[i] & 1) { /* fix_gravity.cpp:331-339, group all */
     const double m = e->rmass[i]; e->f[3 * i] += m * e->g[0]; e->f[3 * i + 1] += m * e->g[1]; e->f[3 * i + 2] += m * e->g[2]; }
   for (int w = 0; w < e->nwalls; w++) wall_compute(e, &e->walls[w], shearupdate);
+  for (int w = 0; w < e->nmwalls; w++) mesh_wall_compute(e, &e->mwalls[w], shearupdate);
   if (e->freezebit) for (long i = 0; i < e->n; i++) if (e->mask[i] & e->freezebit) for (int d = 0; d < 3; d++) { e->f[3 * i + d] = 0.0; e->torque[3 * i + d] = 0.0; } /* fix_freeze.cpp:132-144 */
 }
 
@@ -674,6 +1129,7 @@ int orc_setup(orc_engine *e)
   if (!e->n && !e->tag) return fail(e, "no particles uploaded");
   derive_tables(e);
   for (int w = 0; w < e->nwalls; w++) if (!e->walls[w].hist) { e->walls[w].hist = (double *)calloc((size_t)(e->n ? e->n : 1) * (e->walls[w].m.dnum ? e->walls[w].m.dnum : 1), sizeof(double)); }
+  for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].moving) memset(e->meshes[m].vnode, 0, sizeof(double) * 9 * e->meshes[m].ntri); /* FixMoveMesh::setup fix_move_mesh.cpp:194-217: v = 0 */
   build(e);
   e->nbuilds = 0; /* neighbor->ncalls counts builds of the current run only (neighbor.cpp init: ncalls = 0) */
   compute_forces(e, 0);
@@ -692,15 +1148,18 @@ int orc_run(orc_engine *e, long nsteps)
       const double dtirotate = dtfrotate / (e->radius[i] * e->radius[i] * e->rmass[i]);
       for (int d = 0; d < 3; d++) e->omega[3 * i + d] += dtirotate * e->torque[3 * i + d];
     }
+    mesh_move_step(e);
     /* Neighbor::decide neighbor.cpp:1362-1376 + check_distance :1425-1466 */
-    int nflag = 0; e->ago++;
-    if (e->ago >= e->delay && e->ago % e->every == 0) {
+    int nflag = 0, forced = 0;
+    for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].moving && e->meshes[m].next_reneighbor == (int)e->ntimestep) forced = 1; /* fix->next_reneighbor, neighbor.cpp:1364-1369 */
+    if (forced) nflag = 1; else e->ago++;
+    if (!forced && e->ago >= e->delay && e->ago % e->every == 0) {
       if (!e->check) nflag = 1;
       else { const double deltasq = 0.25 * e->skin * e->skin;
         for (long i = 0; i < e->n; i++) { const double dx = e->x[3 * i] - e->xhold[3 * i], dy = e->x[3 * i + 1] - e->xhold[3 * i + 1], dz = e->x[3 * i + 2] - e->xhold[3 * i + 2];
           if (dx * dx + dy * dy + dz * dz > deltasq) nflag = 1; } }
     }
-    if (nflag) build(e);
+    if (nflag) build(e); else mesh_decide_rebuild(e);
     compute_forces(e, 1);
     for (long i = 0; i < e->n; i++) if (e->mask[i] & e->integbit) { /* fix_nve_sphere.cpp:205-244 */
       const double dtfm = dtf / (e->rmass[i] * (1. + 0.0 / e->density[i]));
@@ -752,6 +1211,38 @@ int orc_download_wall_history(orc_engine *e, const char *id, double *out, long c
     for (long k = 0; k < e->n; k++) for (int d = 0; d < dnum; d++) out[k * dnum + d] = e->walls[w].hist[o[2 * k + 1] * dnum + d];
     free(o); return 0; }
   return fail(e, "no such wall");
+}
+/* mesh read-back: topology (for pinning) and per-particle contact rows sorted by (tag, triangle) */
+int orc_download_mesh(orc_engine *e, const char *mesh_id, const char *field, void *out, long count)
+{
+  for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) { mesh_t *M = &e->meshes[m]; const int T = M->ntri;
+    if (!strcmp(field, "nodes") && count == 9L * T) { memcpy(out, M->node, sizeof(double) * 9 * T); return 0; }
+    if (!strcmp(field, "edge_active") && count == 3L * T) { for (int k = 0; k < 3 * T; k++) ((int *)out)[k] = M->edgeActive[k / 3][k % 3]; return 0; }
+    if (!strcmp(field, "corner_active") && count == 3L * T) { for (int k = 0; k < 3 * T; k++) ((int *)out)[k] = M->cornerActive[k / 3][k % 3]; return 0; }
+    if (!strcmp(field, "obtuse") && count == T) { for (int k = 0; k < T; k++) ((int *)out)[k] = M->obtuse[k]; return 0; }
+    if (!strcmp(field, "nneighs") && count == T) { for (int k = 0; k < T; k++) ((int *)out)[k] = M->nNeighs[k]; return 0; }
+    return fail(e, "unknown mesh field or wrong count"); }
+  return fail(e, "no such mesh");
+}
+int orc_mesh_contact_count(orc_engine *e, const char *mesh_id, long *n, int *dnum)
+{
+  for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) { mesh_t *M = &e->meshes[m]; long c = 0;
+    if (M->nneighs) for (long i = 0; i < e->n; i++) for (int k = 0; k < M->nneighs[i]; k++) c += M->partner[i][k] >= 0;
+    *n = c; *dnum = M->wall >= 0 ? e->mwalls[M->wall].m.dnum : 0; return 0; }
+  return fail(e, "no such mesh");
+}
+typedef struct { int tag, tri; const double *h; } mrow_t;
+static int cmp_mrow(const void *a, const void *b) { const mrow_t *x = a, *y = b; if (x->tag != y->tag) return (x->tag > y->tag) - (x->tag < y->tag); return (x->tri > y->tri) - (x->tri < y->tri); }
+int orc_download_mesh_contacts(orc_engine *e, const char *mesh_id, int *tag, int *tri, double *hist)
+{
+  for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) { mesh_t *M = &e->meshes[m]; long c = 0; int dn = 0;
+    orc_mesh_contact_count(e, mesh_id, &c, &dn);
+    mrow_t *rows = (mrow_t *)malloc(sizeof(mrow_t) * (c ? c : 1)); long k2 = 0;
+    if (M->nneighs) for (long i = 0; i < e->n; i++) for (int k = 0; k < M->nneighs[i]; k++) if (M->partner[i][k] >= 0) { rows[k2].tag = e->tag[i]; rows[k2].tri = M->partner[i][k]; rows[k2].h = &M->chist[i][k * dn]; k2++; }
+    qsort(rows, k2, sizeof(mrow_t), cmp_mrow);
+    for (long r = 0; r < k2; r++) { tag[r] = rows[r].tag; tri[r] = rows[r].tri; if (hist) for (int d = 0; d < dn; d++) hist[r * dn + d] = rows[r].h[d]; }
+    free(rows); return 0; }
+  return fail(e, "no such mesh");
 }
 typedef struct { long ntimestep, nbuilds, nlocal, nghost, npairs_full, ncontacts_full, kernel_launches; int maxneigh, dnum; double step_kernel_ms; long step_kernel_calls; } orc_stats;
 int orc_get_stats(orc_engine *e, orc_stats *s)

@@ -38,7 +38,7 @@ class Ref:
         L.ref_ntimestep.restype = C.c_long
         L.ref_pairlist_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ref_pairlist_dump.argtypes = [C.c_void_p] + [C.c_void_p] * 6
-        args = [b"liggghts", b"-screen", b"none", b"-log", (log or "none").encode(), b"-echo", b"none"]
+        args = [b"liggghts", b"-screen", b"/dev/null", b"-log", (log or "none").encode(), b"-echo", b"none"]
         argv = (C.c_char_p * len(args))(*args)
         self.h = C.c_void_p()
         L.lammps_open_no_mpi(len(args), argv, C.byref(self.h))
@@ -92,6 +92,28 @@ class Ref:
         rows = C.cast(p, C.POINTER(C.POINTER(C.c_double)))
         a = np.array([[rows[i][c] for c in range(ncols)] for i in range(n)], dtype=np.float64).reshape(n, ncols)
         return a[np.argsort(tag, kind="stable")]
+
+    def mesh_topology(self, mesh_id):
+        L = self.lib
+        L.ref_mesh_ntri.argtypes = [C.c_void_p, C.c_char_p]
+        n = L.ref_mesh_ntri(self.h, mesh_id.encode())
+        nodes = np.zeros((n, 3, 3)); ea = np.zeros((n, 3), np.int32); ca = np.zeros((n, 3), np.int32); nn = np.zeros(n, np.int32)
+        L.ref_mesh_topology.argtypes = [C.c_void_p, C.c_char_p] + [C.c_void_p] * 4
+        L.ref_mesh_topology(self.h, mesh_id.encode(), nodes.ctypes.data, ea.ctypes.data, ca.ctypes.data, nn.ctypes.data)
+        return {"nodes": nodes, "edge_active": ea, "corner_active": ca, "nneighs": nn}
+
+    def mesh_contacts(self, mesh_id):
+        """mesh contact rows of fix_contact_history_mesh sorted by (tag, triangle id)"""
+        L = self.lib
+        L.ref_mesh_contacts.argtypes = [C.c_void_p, C.c_char_p, C.c_int] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+        dn = C.c_int(0)
+        n = L.ref_mesh_contacts(self.h, mesh_id.encode(), 0, None, None, None, C.byref(dn))
+        tag = np.zeros(max(n, 1), np.int32); tri = np.zeros(max(n, 1), np.int32); hist = np.zeros((max(n, 1), max(dn.value, 1)))
+        if n > 0:
+            L.ref_mesh_contacts(self.h, mesh_id.encode(), n, tag.ctypes.data, tri.ctypes.data, hist.ctypes.data, C.byref(dn))
+        tag, tri, hist = tag[:max(n, 0)], tri[:max(n, 0)], hist[:max(n, 0), :dn.value]
+        o = np.lexsort((tri, tag))
+        return {"tag": tag[o], "tri": tri[o], "hist": hist[o]}
 
     def pairs(self):
         """granular half list: canonical (tag_lo, tag_hi) sorted, flag, history rows with the

@@ -13,6 +13,12 @@
 #include "neigh_list.h"
 #include "update.h"
 #include "lmptype.h"
+#include "modify.h"
+#include "fix.h"
+#include "fix_mesh_surface.h"
+#include "fix_contact_history_mesh.h"
+#include "tri_mesh.h"
+#include <string.h>
 
 using namespace LAMMPS_NS;
 
@@ -61,5 +67,60 @@ int ref_nlocal(void *ptr) { return ((LAMMPS *) ptr)->atom->nlocal; }
 int ref_nghost(void *ptr) { return ((LAMMPS *) ptr)->atom->nghost; }
 int ref_neigh_ncalls(void *ptr) { return ((LAMMPS *) ptr)->neighbor->ncalls; }
 long ref_ntimestep(void *ptr) { return (long) ((LAMMPS *) ptr)->update->ntimestep; }
+
+
+// ---- triangle meshes (fix mesh/surface): topology flags and per-particle mesh contact rows
+//   SurfaceMesh::edgeActive/cornerActive/nNeighs (surface_mesh.h:152-162), MultiNodeMesh::node (multi_node_mesh.h:151),
+//   FixContactHistory::n_partner/partner/contacthistory (fix_contact_history.h:96-110), FixContactHistoryMesh::nneighs
+static FixMeshSurface *ref_find_mesh(void *ptr, const char *id)
+{
+  LAMMPS *lmp = (LAMMPS *) ptr;
+  Fix *f = lmp->modify->find_fix_id(id);
+  return f ? dynamic_cast<FixMeshSurface *>(f) : NULL;
+}
+int ref_mesh_ntri(void *ptr, const char *id)
+{
+  FixMeshSurface *fm = ref_find_mesh(ptr, id);
+  return fm ? fm->triMesh()->sizeLocal() : -1;
+}
+int ref_mesh_topology(void *ptr, const char *id, double *nodes, int *edgeActive, int *cornerActive, int *nneighs)
+{
+  FixMeshSurface *fm = ref_find_mesh(ptr, id);
+  if (!fm) return -1;
+  TriMesh *m = fm->triMesh();
+  const int n = m->sizeLocal();
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < 3; j++) {
+      m->node(i, j, nodes + 9 * (size_t)i + 3 * j);
+      edgeActive[3 * i + j] = m->edgeActive(i, j) ? 1 : 0;
+      cornerActive[3 * i + j] = m->cornerActive(i, j) ? 1 : 0;
+    }
+    nneighs[i] = m->nNeighs(i);
+  }
+  return n;
+}
+int ref_mesh_contacts(void *ptr, const char *id, int maxrows, int *tag, int *tri, double *hist, int *dnum)
+{
+  LAMMPS *lmp = (LAMMPS *) ptr;
+  FixMeshSurface *fm = ref_find_mesh(ptr, id);
+  if (!fm || !fm->contactHistory()) return -1;
+  FixContactHistoryMesh *ch = fm->contactHistory();
+  const int dn = ch->get_dnum();
+  if (dnum) *dnum = dn;
+  int n = 0;
+  for (int i = 0; i < lmp->atom->nlocal; i++) {
+    const int nn = ch->nneighs(i);
+    for (int j = 0; j < nn; j++) {
+      const int t = ch->partner(i, j);
+      if (t < 0) continue;
+      if (n < maxrows) {
+        tag[n] = lmp->atom->tag[i]; tri[n] = t;
+        for (int d = 0; d < dn; d++) hist[(size_t)n * dn + d] = ch->contacthistory(i, j)[d];
+      }
+      n++;
+    }
+  }
+  return n;
+}
 
 }

@@ -2,6 +2,7 @@
 engine.  A case is a plain dict; `to_deck` renders it as a LIGGGHTS input script + data
 file for the unmodified reference, `apply` replays it on an Engine-like object (the CUDA
 engine or, in tests only, the CPU oracle) through the C ABI."""
+import os
 import numpy as np
 
 SEED = 20261017
@@ -61,6 +62,68 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
                 omega=rng.uniform(-5, 5, (n, 3)) * (0 if frozen else 1) + 0.0, radius=radius, density=np.full(n, 2500.0))
 
 
+def _quad(p0, p1, p2, p3):
+    """two triangles of the quad p0-p1-p2-p3 (shared diagonal p0-p2)"""
+    return [[p0, p1, p2], [p0, p2, p3]]
+
+
+def mesh_box(L, H, nf=3, z0=0.0):
+    """open box: floor of nf x nf quads (coplanar neighbours), four side walls of one quad each"""
+    t = []
+    xs = np.linspace(0.0, L, nf + 1)
+    for a in range(nf):
+        for b in range(nf):
+            t += _quad([xs[a], xs[b], z0], [xs[a + 1], xs[b], z0], [xs[a + 1], xs[b + 1], z0], [xs[a], xs[b + 1], z0])
+    t += _quad([0, 0, z0], [L, 0, z0], [L, 0, H], [0, 0, H]) + _quad([0, L, z0], [0, L, H], [L, L, H], [L, L, z0])
+    t += _quad([0, 0, z0], [0, 0, H], [0, L, H], [0, L, z0]) + _quad([L, 0, z0], [L, L, z0], [L, L, H], [L, 0, H])
+    return np.asarray(t, np.float64)
+
+
+def mesh_roof(L, zr, h):
+    """ridge obstacle (two inclined quads meeting at a convex edge) + its two gable triangles: edge and corner contacts"""
+    a, b, m = 0.2 * L, 0.8 * L, 0.5 * L
+    t = _quad([a, a, zr], [a, b, zr], [m, b, zr + h], [m, a, zr + h]) + _quad([b, a, zr], [m, a, zr + h], [m, b, zr + h], [b, b, zr])
+    t += [[[a, a, zr], [m, a, zr + h], [b, a, zr]], [[a, b, zr], [b, b, zr], [m, b, zr + h]]]
+    return np.asarray(t, np.float64)
+
+
+def mesh_funnel(L, z_top, z_bot, r_top, r_bot, nseg=12):
+    """conical funnel (non-coplanar neighbours all round)"""
+    c = 0.5 * L; t = []
+    for k in range(nseg):
+        a0, a1 = 2 * np.pi * k / nseg, 2 * np.pi * (k + 1) / nseg
+        p = lambda r, a, z: [c + r * np.cos(a), c + r * np.sin(a), z]
+        t += _quad(p(r_top, a0, z_top), p(r_top, a1, z_top), p(r_bot, a1, z_bot), p(r_bot, a0, z_bot))
+    return np.asarray(t, np.float64)
+
+
+def case_mesh(kind="box", n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdt", seed=SEED, poly=True,
+              name="mesh", move=None, settings=""):
+    """particles falling into triangle-mesh geometry (fix mesh/surface + fix wall/gran ... mesh)"""
+    c = case_box(n3=n3, model=model, seed=seed, poly=poly, name=name, settings=settings)
+    L = c["hi"][0]; H = c["hi"][2]
+    st = (" " + settings) if settings else ""
+    c["lo"] = [-0.25 * L, -0.25 * L, -0.01]; c["hi"] = [1.25 * L, 1.25 * L, H]
+    c["walls"] = []
+    if kind == "box":
+        c["meshes"] = [("cad", 1, mesh_box(L, 0.9 * H))]
+    elif kind == "roof":
+        c["meshes"] = [("cad", 1, mesh_box(L, 0.9 * H, nf=2)), ("roof", 1, mesh_roof(L, 0.002, 0.4 * L))]
+        c["x"][:, 2] += 0.45 * L
+    elif kind == "funnel":
+        c["meshes"] = [("cad", 1, mesh_box(L, 0.9 * H, nf=2)), ("fun", 1, mesh_funnel(L, 0.55 * L, 0.2 * L, 0.62 * L, 0.12 * L))]
+        c["x"][:, 2] += 0.6 * L
+        c["lo"][2] = -0.01
+    elif kind == "plate":   # floor mesh + a plate moving down onto the particles (fix move/mesh linear)
+        top = c["x"][:, 2].max() + 0.004
+        plate = np.asarray(_quad([0.02 * L, 0.02 * L, top], [0.98 * L, 0.02 * L, top], [0.98 * L, 0.98 * L, top], [0.02 * L, 0.98 * L, top]))
+        c["meshes"] = [("cad", 1, mesh_box(L, 0.9 * H, nf=2)), ("plate", 1, plate)]
+        c["mesh_moves"] = [("plate", "linear 0. 0. %s" % (move if move is not None else -0.4))]
+    c["mesh_walls"] = [("mw", model + " mesh n_meshes %d meshes %s" % (len(c["meshes"]), " ".join(m[0] for m in c["meshes"])) + st)]
+    c["hi"][2] = max(c["hi"][2], float(max(m[2][..., 2].max() for m in c["meshes"])) + 0.01, float(c["x"][:, 2].max()) + 0.01)
+    return c
+
+
 def to_deck(c, datafile):
     """LIGGGHTS deck + data file text for the reference (grammar: SURVEY.md 8b)"""
     n = len(c["tag"])
@@ -85,6 +148,15 @@ def to_deck(c, datafile):
         deck.append("fix grav all gravity %.17g vector %g %g %g" % (c["gravity"][0], *c["gravity"][1]))
     for wid, text in c["walls"]:
         deck.append("fix %s all wall/gran %s" % (wid, text))
+    for mid, mtype, nodes in c.get("meshes", []):
+        import dem_b200
+        stl = os.path.join(os.path.dirname(datafile), mid + ".stl")
+        dem_b200.write_stl(stl, nodes, mid)
+        deck.append("fix %s all mesh/surface file %s type %d" % (mid, stl, mtype))
+    for mid, text in c.get("mesh_moves", []):
+        deck.append("fix mv_%s all move/mesh mesh %s %s" % (mid, mid, text))
+    for wid, text in c.get("mesh_walls", []):
+        deck.append("fix %s all wall/gran %s" % (wid, text))
     if c["freeze"]:
         ids = " ".join(str(t) for t in c["tag"][(c["mask"] & c["freeze"]) != 0])
         deck += ["group frozen id " + ids, "fix frz frozen freeze"]
@@ -105,6 +177,12 @@ def apply(c, eng):
         eng.gravity(*c["gravity"])
     for wid, text in c["walls"]:
         eng.wall_primitive(wid, text)
+    for mid, mtype, nodes in c.get("meshes", []):
+        eng.mesh(mid, mtype, nodes)
+    for mid, text in c.get("mesh_moves", []):
+        eng.move_mesh(mid, text)
+    for wid, text in c.get("mesh_walls", []):
+        eng.wall_mesh(wid, text)
     if c["freeze"]:
         eng.freeze(c["freeze"])
     eng.integrate(1)
@@ -138,4 +216,7 @@ def snapshot(eng, c):
     for wid, text in c["walls"]:
         dn = 3 + (3 if ("epsd" in text) else 0)
         out["wall_" + wid] = eng.wall_history(wid, dn)
+    for mid, mtype, nodes in c.get("meshes", []):
+        m = eng.mesh_contacts(mid)
+        out["mesh_%s_tag" % mid] = m["tag"]; out["mesh_%s_tri" % mid] = m["tri"]; out["mesh_%s_hist" % mid] = m["hist"]
     return out
