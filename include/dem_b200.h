@@ -75,6 +75,17 @@ int dem_set_pair_style(dem_engine *e, int argc, const char *const *argv);
  *  xcylinder|ycylinder|zcylinder R c1 c2 [shear x|y|z v]` (argv starts at "model")
  *                                                        src/fix_wall_gran.cpp:171-330  */
 int dem_add_wall_primitive(dem_engine *e, const char *id, int argc, const char *const *argv);
+/* `fix ID all mesh/surface file F type T [curvature deg] [precision p]` : the triangles of the file as
+ * nodes9[ntri][3][3] (the host layer reads ASCII/binary STL, src/input_mesh_tri.cpp:308-591); load-time
+ * scale/move/rotate are applied by the caller.  Geometry, topology and active edge/corner flags follow
+ *                          src/surface_mesh_I.h:302-582,1040-1236, src/multi_node_mesh_I.h:153-321  */
+int dem_add_mesh(dem_engine *e, const char *id, int atom_type, const double *nodes9, long ntri, int argc, const char *const *argv);
+/* `fix ID all move/mesh mesh MESH linear vx vy vz`   src/fix_move_mesh.cpp:221-238, src/mesh_mover_linear.cpp:94-112 */
+int dem_move_mesh(dem_engine *e, const char *mesh_id, int argc, const char *const *argv);
+/* `fix ID all wall/gran model ... mesh n_meshes N meshes id1 ... [key on|off ...]` (argv starts at "model")
+ *      src/fix_wall_gran.cpp:171-330,803-982 ; src/fix_neighlist_mesh.cpp:230-501 ; src/tri_mesh_I.h:65-305 ;
+ *      src/fix_contact_history_mesh_I.h:51-215                                                          */
+int dem_add_wall_mesh(dem_engine *e, const char *id, int argc, const char *const *argv);
 /* `fix ID all gravity g vector x y z`                    src/fix_gravity.cpp:301-383    */
 int dem_set_gravity(dem_engine *e, double magnitude, const double dir[3]);
 /* `fix ID <group> freeze` : particles whose mask has any bit of groupbit
@@ -115,6 +126,14 @@ int dem_download_pairs(dem_engine *e, int *tag_lo, int *tag_hi, int *flag, doubl
 /* per-particle history of one primitive wall (reference: fix property/atom
  * "history_<wallid>", src/fix_wall_gran.cpp:479-503); rows by ascending tag.            */
 int dem_download_wall_history(dem_engine *e, const char *wall_id, double *out, long count);
+
+/* mesh read-back.  field: "nodes" double x 9*ntri (current positions) ; "edge_active","corner_active" int x 3*ntri ;
+ * "obtuse","nneighs" int x ntri  (reference: SurfaceMesh::edgeActive/cornerActive/nNeighs, src/surface_mesh.h:152-162) */
+int dem_download_mesh(dem_engine *e, const char *mesh_id, const char *field, void *out, long count);
+/* per-particle mesh contact rows (reference: FixContactHistoryMesh partner_/contacthistory_,
+ * src/fix_contact_history_mesh.h): one row per (particle, triangle) holding history, sorted by (tag, triangle id) */
+int dem_mesh_contact_count(dem_engine *e, const char *mesh_id, long *nrows, int *dnum);
+int dem_download_mesh_contacts(dem_engine *e, const char *mesh_id, int *tag, int *tri, double *hist);
 
 typedef struct dem_stats {
   long ntimestep;      /* steps taken since setup                                  */

@@ -1,29 +1,50 @@
-"""Builds libdem_b200.so (hand-written CUDA for sm_100a + C ABI) in-tree with nvcc."""
+"""Builds libdem_b200.so (hand-written CUDA for sm_100a + C ABI) in-tree with nvcc.
+Two translation units: dem_engine.cu (host orchestration + particle kernels) and dem_mesh.cu (triangle-mesh
+kernels, --fmad=false so that its geometric predicates round like the reference's C++)."""
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "dem_engine.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("dem_engine.cu", "dem_kernels.cuh", "dem_contact.cuh", "dem_types.h")] + \
-       [os.path.join(os.path.dirname(HERE), "include", "dem_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+UNITS = [("dem_engine.cu", []), ("dem_mesh.cu", ["--fmad=false"])]
+DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "dem_b200.h")]
 OUT = os.path.join(HERE, "libdem_b200.so")
+OBJDIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static", "-diag-suppress", "550"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-diag-suppress", "550"]
+EXTRA = os.environ.get("DEM_NVCC_EXTRA", "").split()
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+def _run(cmd, verbose):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libdem_b200.so")
     if verbose:
         print(r.stderr)
-    return OUT
+
+
+def build(force=False, verbose=False, out=OUT):
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
+        return out
+    os.makedirs(OBJDIR, exist_ok=True)
+    procs, objs = [], []
+    for src, extra in UNITS:
+        obj = os.path.join(OBJDIR, os.path.basename(out) + "." + src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [NVCC] + FLAGS + EXTRA + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for cmd, p in procs:
+        so, se = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(so + se)
+            raise RuntimeError("nvcc failed building libdem_b200.so")
+        if verbose:
+            print(se)
+    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", out] + objs, verbose)
+    return out
 
 
 if __name__ == "__main__":

@@ -18,6 +18,7 @@
 
 #include "../../include/dem_b200.h"
 #include "dem_kernels.cuh"
+#include "dem_mesh_host.h"
 
 using namespace dem;
 
@@ -135,7 +136,16 @@ struct dem_engine {
   int lcur = 0;
   DevBuf<int> overflow;
   DevBuf<unsigned long long> counters;
-  int *hflag = nullptr;  // mapped pinned rebuild flag
+  int *hflag = nullptr;  // mapped pinned flags: [0] rebuild trigger, [1] history overflow, [2] moving-mesh trigger
+  // triangle-mesh walls (dem_mesh.h)
+  std::vector<MeshHost> meshes;
+  struct MeshWall { std::string id; ModelP m; std::vector<int> mesh; };
+  std::vector<MeshWall> mwalls;
+  std::vector<TriRec> htri; std::vector<int> hcn;
+  DevBuf<TriRec> dtri; DevBuf<int> dcn, dcell_start, dcell_tri, mint[2]; DevBuf<double> dnodes_last; DevBuf<double4> mhist[2];
+  int mcur = 0, mslots = 8, mcand = 16, mhrec = 0, mesh_ready = 0, grid_ready = 0, any_moving = 0;
+  double mgorg[3] = {0, 0, 0}, mginv[3] = {1, 1, 1}; int mgnc[3] = {1, 1, 1};
+  long next_reneighbor = -1;
   // state
   int uploaded = 0, setup_done = 0, forces_valid = 0;
   long ntimestep = 0, nbuilds = 0, launches = 0;
@@ -232,6 +242,8 @@ extern "C" void dem_destroy(dem_engine *e)
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
   e->cubtmp.release(); e->overflow.release(); e->counters.release();
+  e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
+  for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   if (e->hflag) cudaFreeHost(e->hflag);
@@ -426,6 +438,178 @@ extern "C" int dem_add_wall_primitive(dem_engine *e, const char *id, int argc, c
   API_END
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// triangle-mesh walls
+extern "C" int dem_add_mesh(dem_engine *e, const char *id, int atom_type, const double *nodes9, long ntri, int argc, const char *const *argv)
+{
+  API_BEGIN
+  if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "meshes cannot be added after setup");
+  if ((int)e->meshes.size() == DEM_MAXMESH) dem_fail(e, DEM_ERR_OVERFLOW, "at most %d meshes", DEM_MAXMESH);
+  if (!id || !nodes9 || ntri < 1) dem_fail(e, DEM_ERR_ARG, "mesh needs an id and at least one triangle");
+  if (atom_type < 1 || atom_type > e->ntypes) dem_fail(e, DEM_ERR_ARG, "1 <= type <= max type as defined in create_box");
+  for (auto &m : e->meshes) if (m.id == id) dem_fail(e, DEM_ERR_ARG, "fix id %s already in use", id);
+  MeshHost M;
+  M.id = id; M.atom_type = atom_type; M.ntri = (int)ntri;
+  M.nodes.assign(nodes9, nodes9 + 9 * ntri);
+  for (int k = 0; k < argc; k += 2) {
+    if (k + 1 >= argc) dem_fail(e, DEM_ERR_ARG, "mesh keyword '%s' needs a value", argv[k]);
+    if (!strcmp(argv[k], "curvature")) M.curvature = cos(atof(argv[k + 1]) * 3.14159265358979323846 / 180.);
+    else if (!strcmp(argv[k], "precision")) M.precision = atof(argv[k + 1]);
+    else dem_fail(e, DEM_ERR_UNSUPPORTED, "fix mesh/surface keyword '%s' is outside the hot-path scope (apply scale/move/rotate to the nodes before the call)", argv[k]);
+  }
+  e->meshes.push_back(M);
+  API_END
+}
+extern "C" int dem_move_mesh(dem_engine *e, const char *mesh_id, int argc, const char *const *argv)
+{
+  API_BEGIN
+  if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "fix move/mesh cannot be added after setup");
+  for (auto &m : e->meshes) if (m.id == mesh_id) {
+    if (argc < 1 || strcmp(argv[0], "linear")) dem_fail(e, DEM_ERR_UNSUPPORTED, "fix move/mesh style '%s' not built yet (linear)", argc ? argv[0] : "");
+    if (argc != 4) dem_fail(e, DEM_ERR_ARG, "Not enough arguments for movement type linear");
+    for (int d = 0; d < 3; d++) m.vel[d] = atof(argv[1 + d]);
+    m.moving = 1;
+    return DEM_OK;
+  }
+  dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);
+  API_END
+}
+extern "C" int dem_add_wall_mesh(dem_engine *e, const char *id, int argc, const char *const *argv)
+{
+  API_BEGIN
+  if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "walls cannot be added after setup");
+  if (e->nranks > 1) dem_fail(e, DEM_ERR_UNSUPPORTED, "mesh walls on more than one GPU are not built yet");
+  dem_engine::MeshWall W; W.id = id;
+  parse_model_select(e, argc, argv, W.m);
+  if (argc < 4 || strcmp(argv[0], "mesh")) dem_fail(e, DEM_ERR_ARG, "Need to use define style 'mesh' or 'primitive'");
+  if (strcmp(argv[1], "n_meshes")) dem_fail(e, DEM_ERR_ARG, "have to define 'n_meshes' before 'meshes'");
+  const int nm = atoi(argv[2]);
+  if (nm < 1) dem_fail(e, DEM_ERR_ARG, "'n_meshes' > 0 required");
+  if (argc < 4 + nm || strcmp(argv[3], "meshes")) dem_fail(e, DEM_ERR_ARG, "Need to provide the number and a list of meshes by using 'n_meshes' and 'meshes'");
+  for (int k = 0; k < nm; k++) {
+    int found = -1;
+    for (size_t m = 0; m < e->meshes.size(); m++) if (e->meshes[m].id == argv[4 + k]) found = (int)m;
+    if (found < 0) dem_fail(e, DEM_ERR_ARG, "could not find fix mesh id %s", argv[4 + k]);
+    if (e->meshes[found].wall >= 0) dem_fail(e, DEM_ERR_ARG, "mesh %s is already used by another wall", argv[4 + k]);
+    e->meshes[found].wall = (int)e->mwalls.size();
+    W.mesh.push_back(found);
+  }
+  argv += 4 + nm; argc -= 4 + nm;
+  parse_model_settings(e, argc, argv, W.m);
+  e->mwalls.push_back(W);
+  API_END
+}
+
+static bool have_mesh_walls(const dem_engine *E) { return !E->mwalls.empty(); }
+
+static MeshP mesh_params(dem_engine *E)
+{
+  MeshP M;
+  memset(&M, 0, sizeof M);
+  M.ntri = (int)E->htri.size(); M.nmesh = (int)E->meshes.size(); M.mslots = E->mslots; M.mcand = E->mcand; M.cap = E->cap; M.hrec = E->mhrec;
+  M.tri = E->dtri.p; M.nodes_last = E->dnodes_last.p; M.cn = E->dcn.p; M.cell_start = E->dcell_start.p; M.cell_tri = E->dcell_tri.p;
+  for (int d = 0; d < 3; d++) { M.gorg[d] = E->mgorg[d]; M.ginv[d] = E->mginv[d]; M.gnc[d] = E->mgnc[d]; }
+  M.mint = E->mint[E->mcur].p; M.mhist = E->mhist[E->mcur].p;
+  for (size_t m = 0; m < E->meshes.size(); m++) {
+    const MeshHost &H = E->meshes[m];
+    MeshMeta &mm = M.meta[m];
+    mm.atom_type = H.atom_type; mm.wall = H.wall; mm.moving = H.moving; mm.first = H.first; mm.ntri = H.ntri; mm.precision = H.precision;
+    for (int d = 0; d < 3; d++) mm.vel[d] = H.vel[d];
+    if (H.wall >= 0) M.wm[m] = E->mwalls[H.wall].m;
+  }
+  M.overflow = E->overflow.p;
+  return M;
+}
+
+// setup-time: geometry + topology on the host, triangle records to the device, per-particle rows
+static void mesh_prepare(dem_engine *E)
+{
+  if (E->mesh_ready || !have_mesh_walls(E)) return;
+  E->htri.clear(); E->hcn.clear(); E->mhrec = 0; E->any_moving = 0;
+  for (size_t m = 0; m < E->meshes.size(); m++) {
+    MeshHost &H = E->meshes[m];
+    H.first = (int)E->htri.size();
+    const std::string err = meshhost::derive(E->lo, E->hi, H, (int)m, E->htri, E->hcn);
+    if (!err.empty()) dem_fail(E, DEM_ERR_ARG, "%s", err.c_str());
+    if (H.wall >= 0) E->mhrec = std::max(E->mhrec, E->mwalls[H.wall].m.hrec);
+    if (H.moving) E->any_moving = 1;
+  }
+  if (E->opt.count("meshslots")) E->mslots = std::min(30, std::max(2, (int)E->opt["meshslots"]));
+  if (E->opt.count("meshcand")) E->mcand = std::max(4, (int)E->opt["meshcand"]);
+  cudaStream_t st = E->stream;
+  E->dtri.ensure(E, E->htri.size()); E->dcn.ensure(E, E->hcn.size()); E->dnodes_last.ensure(E, 9 * E->htri.size());
+  CK(cudaMemcpyAsync(E->dtri.p, E->htri.data(), E->htri.size() * sizeof(TriRec), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(E->dcn.p, E->hcn.data(), E->hcn.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const size_t rows = 1 + E->mslots + E->mcand;
+  for (int b = 0; b < 2; b++) {
+    E->mint[b].release(); E->mint[b].ensure(E, rows * E->cap);
+    CK(cudaMemsetAsync(E->mint[b].p, 0xFF, rows * E->cap * sizeof(int), st));   // partner rows: -1 = free
+    CK(cudaMemsetAsync(E->mint[b].p, 0, (size_t)E->cap * sizeof(int), st));     // row 0: candidate count
+    E->mhist[b].release();
+    if (E->mhrec) { E->mhist[b].ensure(E, (size_t)E->mslots * E->mhrec * E->cap); CK(cudaMemsetAsync(E->mhist[b].p, 0, (size_t)E->mslots * E->mhrec * E->cap * sizeof(double4), st)); }
+  }
+  CK(cudaStreamSynchronize(st));
+  E->mcur = 0; E->mesh_ready = 1; E->grid_ready = 0; E->next_reneighbor = -1;
+}
+
+// coarse triangle grid (moving meshes: from the current device nodes at every rebuild)
+static void mesh_grid(dem_engine *E)
+{
+  if (E->grid_ready && !E->any_moving) return;
+  cudaStream_t st = E->stream;
+  if (E->grid_ready && E->any_moving) {
+    CK(cudaMemcpyAsync(E->htri.data(), E->dtri.p, E->htri.size() * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  std::vector<int> cs, ct;
+  meshhost::build_grid(E->lo, E->hi, 4.0 * E->cutneighmax, E->cutneighmax + E->skin, E->htri, E->mgorg, E->mginv, E->mgnc, cs, ct);
+  E->dcell_start.ensure(E, cs.size()); E->dcell_tri.ensure(E, std::max<size_t>(ct.size(), 1));
+  CK(cudaMemcpyAsync(E->dcell_start.p, cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!ct.empty()) CK(cudaMemcpyAsync(E->dcell_tri.p, ct.data(), ct.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  E->grid_ready = 1;
+}
+
+// rebuild: carry the per-particle rows through the sort permutation, then candidates + contact-row maintenance
+static void mesh_rebuild(dem_engine *E, int n, bool permuted)
+{
+  cudaStream_t st = E->stream;
+  mesh_grid(E);
+  const int src = E->mcur, dst = E->mcur ^ 1;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    const size_t rows = 1 + E->mslots + E->mcand;
+    E->mint[dst].ensure(E, rows * E->cap);
+    if (n) {
+      if (permuted) {
+        k_gather_rows<int><<<GRID(n, 256), 256, 0, st>>>(n, 1 + E->mslots, (size_t)E->cap, (size_t)E->cap, E->perm.p, E->mint[src].p, E->mint[dst].p);
+        if (E->mhrec) k_gather_rows<double4><<<GRID(n, 256), 256, 0, st>>>(n, E->mslots * E->mhrec, (size_t)E->cap, (size_t)E->cap, E->perm.p, E->mhist[src].p, E->mhist[dst].p);
+      } else {
+        CK(cudaMemcpyAsync(E->mint[dst].p, E->mint[src].p, (size_t)(1 + E->mslots) * E->cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        if (E->mhrec) CK(cudaMemcpyAsync(E->mhist[dst].p, E->mhist[src].p, (size_t)E->mslots * E->mhrec * E->cap * sizeof(double4), cudaMemcpyDeviceToDevice, st));
+      }
+      E->launches += 2;
+    }
+    E->mcur = dst;
+    CK(cudaMemsetAsync(E->overflow.p, 0, 2 * sizeof(int), st));
+    MeshP M = mesh_params(E);
+    mesh_launch_candidates(M, n, E->xr[E->cur].p, E->skin, E->cdf, st);
+    E->launches++;
+    int ov[2] = {0, 0};
+    CK(cudaMemcpyAsync(ov, E->overflow.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ov[0] <= E->mcand) break;
+    if (attempt == 5) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d candidate triangles", ov[0]);
+    E->mcand = ov[0] + 4; E->mcur = src;
+  }
+  // the other buffer must be able to take the rows at the next rebuild
+  E->mint[src].ensure(E, (size_t)(1 + E->mslots + E->mcand) * E->cap);
+  MeshP M = mesh_params(E);
+  mesh_launch_hold(M, st);
+  E->launches++;
+  E->hflag[2] = 0;
+}
+
 extern "C" int dem_set_gravity(dem_engine *e, double mag, const double dir[3])
 {
   API_BEGIN
@@ -462,6 +646,22 @@ static void ensure_particle_cap(dem_engine *E, long need, long keep)
     b.release(); b = nb;
   };
   restride(E->f, 3); restride(E->tq, 3); restride(E->whist, E->nwrows);
+  if (E->mesh_ready && oldcap) {  // mesh rows: [rows][cap] int / double4
+    for (int b = 0; b < 2; b++) {
+      const int rows = 1 + E->mslots + E->mcand;
+      DevBuf<int> ni; ni.ensure(E, (size_t)rows * ncap, 0, st);
+      CK(cudaMemsetAsync(ni.p, 0xFF, (size_t)rows * ncap * sizeof(int), st)); CK(cudaMemsetAsync(ni.p, 0, (size_t)ncap * sizeof(int), st));
+      if (E->mint[b].p && keep) CK(cudaMemcpy2DAsync(ni.p, ncap * sizeof(int), E->mint[b].p, (size_t)oldcap * sizeof(int), std::min<long>(keep, oldcap) * sizeof(int), std::min<size_t>(rows, E->mint[b].n / oldcap), cudaMemcpyDeviceToDevice, st));
+      CK(cudaStreamSynchronize(st)); E->mint[b].release(); E->mint[b] = ni;
+      if (E->mhrec) {
+        const int hr = E->mslots * E->mhrec;
+        DevBuf<double4> nh; nh.ensure(E, (size_t)hr * ncap, 0, st);
+        CK(cudaMemsetAsync(nh.p, 0, (size_t)hr * ncap * sizeof(double4), st));
+        if (E->mhist[b].p && keep) CK(cudaMemcpy2DAsync(nh.p, ncap * sizeof(double4), E->mhist[b].p, (size_t)oldcap * sizeof(double4), std::min<long>(keep, oldcap) * sizeof(double4), hr, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st)); E->mhist[b].release(); E->mhist[b] = nh;
+      }
+    }
+  }
   if (E->nwrows) { E->whist_tmp.release(); E->whist_tmp.ensure(E, (size_t)E->nwrows * ncap, 0, st); }
   E->cap = (int)ncap;
 }
@@ -551,7 +751,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     if (errbits & 4) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
     double rmaxd; memcpy(&rmaxd, &hc[0], 8);
     e->nlocal = n; e->nghost = 0; e->rmax = rmaxd;
-    e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0;
+    e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0; e->mesh_ready = 0;
     e->ls[0].valid = e->ls[1].valid = 0;
     e->ntimestep = 0;
     return DEM_OK;
@@ -601,7 +801,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
   CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->nlocal = n; e->nghost = 0; e->rmax = rmax;
-  e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0;
+  e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0; e->mesh_ready = 0;
   e->ls[0].valid = e->ls[1].valid = 0;
   e->ntimestep = 0;
   API_END
@@ -617,6 +817,7 @@ static void derive_tables(dem_engine *E)
   auto scan = [&](const ModelP &m) { hertz |= m.normal == N_HERTZ; hooke |= m.normal == N_HOOKE; tang |= m.tangential != 0; roll |= m.rolling != R_OFF; epsd |= m.rolling == R_EPSD; };
   if (E->have_pair) scan(E->pm);
   for (auto &w : E->walls) scan(w.p.m);
+  for (auto &w : E->mwalls) scan(w.m);
   if (hertz || hooke) { need("youngsModulus"); need("poissonsRatio"); need("coefficientRestitution"); }
   if (hooke) need("characteristicVelocity");
   if (tang) need("coefficientFriction");
@@ -857,6 +1058,7 @@ static void rebuild(dem_engine *E)
   ensure_cub(E, (size_t)E->cap);
   E->keys.ensure(E, E->cap); E->keys2.ensure(E, E->cap); E->vals.ensure(E, E->cap); E->perm.ensure(E, E->cap);
   int c = E->cur;
+  bool did_permute = false;
   if (ncur) {
     // 1. pbc wrap, cell keys, radix sort, gather the particle records into cell (Morton) order
     k_wrap_key<<<GRID(ncur, 256), 256, 0, st>>>(ncur, E->xr[c].p, E->grid, B, E->keys.p, E->vals.p, E->nranks > 1 ? E->gone.p : nullptr);
@@ -878,6 +1080,7 @@ static void rebuild(dem_engine *E)
     k_extract_valid<<<GRID(n, 256), 256, 0, st>>>(n, E->perm.p, E->xh.p, E->valid_tmp.p);
     E->launches += 4;
     E->cur = c ^ 1; c = E->cur;
+    did_permute = true;
   }
   E->nlocal = n;
   // 2. owned cell ranges
@@ -967,14 +1170,18 @@ static void rebuild(dem_engine *E)
   }
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
+  // 5b. triangle-mesh candidate rows + carry-over of the mesh contact rows
+  const bool meshw = have_mesh_walls(E) && E->mesh_ready;
+  if (meshw) mesh_rebuild(E, n, did_permute);
   // 6. positions at build time + primitive wall candidate bits
   E->nwc = 0;
   if (n) {
     const int nw = (int)E->walls.size();
     E->flo.ensure(E, n + 1); E->slo.ensure(E, n + 1);
-    k_hold<<<GRID(n, 256), 256, 0, st>>>(n, E->xr[c].p, E->xh.p, E->valid_tmp.p, E->dwalls.p, nw, E->skin, nw ? E->flo.p : nullptr);
+    k_hold<<<GRID(n, 256), 256, 0, st>>>(n, E->xr[c].p, E->xh.p, E->valid_tmp.p, E->dwalls.p, nw, E->skin, (nw || meshw) ? E->flo.p : nullptr,
+                                       meshw ? E->mint[E->mcur].p : nullptr);
     E->launches++;
-    if (nw) {
+    if (nw || meshw) {
       size_t tb = E->cubtmp.n;
       CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, E->flo.p, E->slo.p, n, st));
       int last[2];
@@ -1032,6 +1239,7 @@ static void launch_step(dem_engine *E, int mode, bool timed)
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
   }
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
+  if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
   switch (key) {
     case N_HERTZ * 4 + R_OFF: launch_step_t<N_HERTZ, R_OFF>(E, P); break;
@@ -1077,11 +1285,12 @@ extern "C" int dem_setup(dem_engine *e)
   API_BEGIN
   if (!e->uploaded) dem_fail(e, DEM_ERR_STATE, "setup before dem_upload_particles");
   if (!(e->dt > 0)) dem_fail(e, DEM_ERR_STATE, "timestep not set");
-  if (!e->have_pair && e->walls.empty()) dem_fail(e, DEM_ERR_STATE, "no pair_style and no wall defined");
+  if (!e->have_pair && e->walls.empty() && e->mwalls.empty()) dem_fail(e, DEM_ERR_STATE, "no pair_style and no wall defined");
   CK(cudaSetDevice(e->device));
   if (!e->setup_done) {
     derive_tables(e);
     setup_grid(e);
+    mesh_prepare(e);
     if (e->nwrows) {
       e->whist.release(); e->whist.ensure(e, (size_t)e->nwrows * e->cap);
       CK(cudaMemsetAsync(e->whist.p, 0, (size_t)e->nwrows * e->cap * sizeof(double), e->stream));
@@ -1119,14 +1328,28 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   reduce_flags(e);
   for (long s = 1; s <= nsteps; s++) {
     e->ntimestep++;
-    // Neighbor::decide (neighbor.cpp:1362-1376)
-    e->ago++;
+    // fix move/mesh: initial_integrate of this step moves the mesh (fix_move_mesh.cpp:221-238)
+    const bool moving = e->any_moving && e->mesh_ready;
+    if (moving) {
+      MeshP M = mesh_params(e);
+      for (size_t m = 0; m < e->meshes.size(); m++) if (e->meshes[m].moving) { mesh_launch_move(M, (int)m, e->dt, 0.25 * e->skin * e->skin, e->hflag + 2, st); e->launches++; }
+    }
+    // Neighbor::decide (neighbor.cpp:1362-1376): a fix may force the rebuild (fix->next_reneighbor), else distance check
     int nflag = 0;
-    if (e->ago >= e->delay && e->ago % e->every == 0) {
-      if (!e->check) nflag = 1;
-      else { CK(cudaStreamSynchronize(st)); nflag = e->hflag[0]; }
+    bool synced = false;
+    if (moving && e->next_reneighbor == e->ntimestep) nflag = 1;
+    else {
+      e->ago++;
+      if (e->ago >= e->delay && e->ago % e->every == 0) {
+        if (!e->check) nflag = 1;
+        else { CK(cudaStreamSynchronize(st)); synced = true; nflag = e->hflag[0]; }
+      }
     }
     if (nflag) { rebuild(e); clear_flags(e); }
+    else if (moving) {  // FixMesh::pre_force on a regular step: MultiNodeMesh::decideRebuild (fix_mesh.cpp:553-576)
+      if (!synced) CK(cudaStreamSynchronize(st));
+      if (e->hflag[2]) e->next_reneighbor = e->ntimestep + 1;
+    }
     launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
     e->cur ^= 1;
     forward_comm(e);
@@ -1292,6 +1515,92 @@ extern "C" int dem_download_wall_history(dem_engine *e, const char *wall_id, dou
     const bool valid = ((unsigned)(b & 0xffffffffLL) >> (16 + wi)) & 1u;
     for (int d = 0; d < W.m.dnum; d++) out[k * W.m.dnum + d] = valid ? h[(size_t)d * e->cap + o[k]] : 0.0;
   }
+  API_END
+}
+
+// ---- mesh read-back --------------------------------------------------------------------------
+extern "C" int dem_download_mesh(dem_engine *e, const char *mesh_id, const char *field, void *out, long count)
+{
+  API_BEGIN
+  CK(cudaSetDevice(e->device));
+  for (auto &m : e->meshes) if (m.id == mesh_id) {
+    const long T = m.ntri;
+    std::string f(field);
+    if (f == "nodes") {
+      if (count != 9 * T) dem_fail(e, DEM_ERR_ARG, "nodes: count must be 9*ntri");
+      if (e->mesh_ready) {
+        std::vector<TriRec> h(T);
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMemcpy(h.data(), e->dtri.p + m.first, T * sizeof(TriRec), cudaMemcpyDeviceToHost));
+        for (long t = 0; t < T; t++) memcpy((double *)out + 9 * t, h[t].node, 9 * sizeof(double));
+      } else memcpy(out, m.nodes.data(), 9 * T * sizeof(double));
+      return DEM_OK;
+    }
+    if (!e->mesh_ready) dem_fail(e, DEM_ERR_STATE, "mesh topology is available after setup");
+    const std::vector<int> *src = f == "edge_active" ? &m.edge_active : f == "corner_active" ? &m.corner_active : f == "obtuse" ? &m.obtuse : f == "nneighs" ? &m.nneighs : nullptr;
+    if (!src) dem_fail(e, DEM_ERR_ARG, "unknown mesh field %s", field);
+    if (count != (long)src->size()) dem_fail(e, DEM_ERR_ARG, "%s: count %ld != %ld", field, count, (long)src->size());
+    memcpy(out, src->data(), src->size() * sizeof(int));
+    return DEM_OK;
+  }
+  dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);
+  API_END
+}
+
+struct MeshRow { int tag, tri; long src; };
+static void collect_mesh_rows(dem_engine *E, const MeshHost &m, std::vector<MeshRow> &rows, std::vector<double4> &hist)
+{
+  rows.clear();
+  if (!E->mesh_ready || !E->nlocal) return;
+  CK(cudaStreamSynchronize(E->stream));
+  const long n = E->nlocal;
+  std::vector<int> tags(n), mi((size_t)(1 + E->mslots) * E->cap);
+  CK(cudaMemcpy(tags.data(), E->tag.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(mi.data(), E->mint[E->mcur].p, mi.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  hist.assign((size_t)E->mslots * E->mhrec * E->cap, make_double4(0., 0., 0., 0.));
+  if (E->mhrec) CK(cudaMemcpy(hist.data(), E->mhist[E->mcur].p, hist.size() * sizeof(double4), cudaMemcpyDeviceToHost));
+  for (long i = 0; i < n; i++) for (int s = 0; s < E->mslots; s++) {
+    const int t = mi[(size_t)(1 + s) * E->cap + i];
+    if (t >= m.first && t < m.first + m.ntri) rows.push_back(MeshRow{tags[i], t - m.first, (long)s * E->cap + i});
+  }
+  std::sort(rows.begin(), rows.end(), [](const MeshRow &a, const MeshRow &b) { return a.tag != b.tag ? a.tag < b.tag : a.tri < b.tri; });
+}
+extern "C" int dem_mesh_contact_count(dem_engine *e, const char *mesh_id, long *n, int *dnum)
+{
+  API_BEGIN
+  CK(cudaSetDevice(e->device));
+  for (auto &m : e->meshes) if (m.id == mesh_id) {
+    std::vector<MeshRow> rows; std::vector<double4> h;
+    collect_mesh_rows(e, m, rows, h);
+    if (n) *n = (long)rows.size();
+    if (dnum) *dnum = m.wall >= 0 ? e->mwalls[m.wall].m.dnum : 0;
+    return DEM_OK;
+  }
+  dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);
+  API_END
+}
+extern "C" int dem_download_mesh_contacts(dem_engine *e, const char *mesh_id, int *tag, int *tri, double *hist)
+{
+  API_BEGIN
+  CK(cudaSetDevice(e->device));
+  for (auto &m : e->meshes) if (m.id == mesh_id) {
+    std::vector<MeshRow> rows; std::vector<double4> h;
+    collect_mesh_rows(e, m, rows, h);
+    const ModelP *W = m.wall >= 0 ? &e->mwalls[m.wall].m : nullptr;
+    const int dn = W ? W->dnum : 0;
+    for (size_t r = 0; r < rows.size(); r++) {
+      if (tag) tag[r] = rows[r].tag;
+      if (tri) tri[r] = rows[r].tri;
+      if (hist && W) {
+        const long s = rows[r].src / e->cap, i = rows[r].src % e->cap;
+        for (int d = 0; d < dn; d++) hist[r * dn + d] = 0.0;
+        if (W->rec_shear >= 0) { const double4 v = h[(size_t)(s * e->mhrec + W->rec_shear) * e->cap + i]; hist[r * dn + W->off_shear] = v.x; hist[r * dn + W->off_shear + 1] = v.y; hist[r * dn + W->off_shear + 2] = v.z; }
+        if (W->rec_roll >= 0) { const double4 v = h[(size_t)(s * e->mhrec + W->rec_roll) * e->cap + i]; hist[r * dn + W->off_roll] = v.x; hist[r * dn + W->off_roll + 1] = v.y; hist[r * dn + W->off_roll + 2] = v.z; }
+      }
+    }
+    return DEM_OK;
+  }
+  dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);
   API_END
 }
 

@@ -714,7 +714,8 @@ __global__ void __launch_bounds__(256) k_wall_index(int n, const int *flag, cons
   const long long b = (__double_as_longlong(xh[i].w) & 0xffffffffLL) | ((long long)(c + 1) << 32);
   xh[i].w = __longlong_as_double(b);
 }
-__global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 *xh, const unsigned *valid_in, const WallP *walls, int nwalls, double skin, int *cflag)
+__global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 *xh, const unsigned *valid_in, const WallP *walls, int nwalls, double skin, int *cflag,
+                                              const int *mesh_ncand)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(256) k_hold(int n, const double4 *xr, double4 
   const unsigned valid = valid_in ? valid_in[i] : 0u;
   double4 o; o.x = x.x; o.y = x.y; o.z = x.z; o.w = __longlong_as_double((long long)(cand | (valid << 16)));
   xh[i] = o;
-  if (cflag) cflag[i] = cand != 0;
+  if (cflag) cflag[i] = cand != 0 || (mesh_ncand && mesh_ncand[i] > 0);  // compact wall list: primitive or mesh candidates
 }
 __global__ void __launch_bounds__(256) k_extract_valid(int n, const int *perm, const double4 *xh, unsigned *valid)
 {

@@ -1,0 +1,343 @@
+// dem_mesh.cu -- triangle-mesh wall kernels (sm_100a).  Compiled with --fmad=false: see dem_mesh.h.
+//
+// B200-first layout: the reference walks triangle-major (each triangle owns a std::vector of
+// particles, fix_wall_gran.cpp:851-856) and keeps per-particle partner pages; here everything is
+// particle-major so that one thread owns one particle's candidate row, contact rows and force sum:
+//   rebuild : k_mesh_cand   particle -> coarse grid cell -> ascending triangle ids -> ELLPACK candidate row,
+//                           plus the carry-over of the contact rows (sort_contacts, cleanUpContactJumps)
+//   step    : k_mesh_step   over the compact list of wall-candidate particles (a thin layer of the bed);
+//                           triangles are visited in ascending id, which is the order the reference's
+//                           triangle-major loop presents them to any one particle, so the order-dependent
+//                           coplanar de-duplication (fix_contact_history_mesh_I.h:61-87) is reproduced
+//   motion  : k_mesh_move   nodes += v*dt, rebuild trigger on node displacement
+#include "dem_mesh.h"
+#include "dem_contact.cuh"
+
+namespace dem {
+
+#define SMALL_TRIMESH (1.e-10)
+#define LARGE_TRIMESH 1000000
+
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void sub3(const double *a, const double *b, double *r) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+
+// TriMesh::resolveTriSphereNeighbuild  tri_mesh_I.h:275-305
+__device__ __forceinline__ bool tri_neighbuild(const TriRec &T, double rSphere, const double *c, double treshold)
+{
+  const double maxDist = rSphere + treshold;
+  double v[3];
+  sub3(c, T.center, v);
+  if (fabs(dot3(T.surfNorm, v)) > maxDist) return false;
+  const double dParaMax = maxDist * maxDist;
+  for (int i = 0; i < 3; i++) {
+    sub3(c, T.node + 3 * i, v);
+    const double d = dot3(T.edgeNorm + 3 * i, v);
+    if (d > 0 && d * d > dParaMax) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ double calc_dist(const double *cs, const double *cp, double *delta)
+{  // tri_mesh_I.h:309-313
+  sub3(cp, cs, delta);
+  return sqrt((cs[0] - cp[0]) * (cs[0] - cp[0]) + (cs[1] - cp[1]) * (cs[1] - cp[1]) + (cs[2] - cp[2]) * (cs[2] - cp[2]));
+}
+__device__ __forceinline__ bool edge_active(const TriRec &T, int k) { return (T.flags >> (2 + k)) & 1; }
+__device__ __forceinline__ bool corner_active(const TriRec &T, int k) { return (T.flags >> (5 + k)) & 1; }
+
+// tri_mesh_I.h:129-170 (skip_inactive = true)
+__device__ double resolve_edge(const TriRec &T, int iEdge, const double *p, double *delta, double *bary)
+{
+  const int ip = (iEdge + 1) % 3, ipp = (iEdge + 2) % 3;
+  double nodeToP[3];
+  sub3(p, T.node + 3 * iEdge, nodeToP);
+  const double distFromNode = dot3(nodeToP, T.edgeVec + 3 * iEdge);
+  if (distFromNode < -SMALL_TRIMESH) {
+    if (!corner_active(T, iEdge)) return LARGE_TRIMESH;
+    bary[iEdge] = 1.; bary[ip] = 0.; bary[ipp] = 0.;
+    return calc_dist(p, T.node + 3 * iEdge, delta);
+  } else if (distFromNode > T.edgeLen[iEdge] + SMALL_TRIMESH) {
+    if (!corner_active(T, ip)) return LARGE_TRIMESH;
+    bary[iEdge] = 0.; bary[ip] = 1.; bary[ipp] = 0.;
+    return calc_dist(p, T.node + 3 * ip, delta);
+  }
+  if (!edge_active(T, iEdge)) return LARGE_TRIMESH;
+  double cp[3];
+  for (int d = 0; d < 3; d++) cp[d] = T.node[3 * iEdge + d] + distFromNode * T.edgeVec[3 * iEdge + d];
+  const double dd = calc_dist(p, cp, delta);
+  bary[ipp] = 0.; bary[iEdge] = 1. - distFromNode / T.edgeLen[iEdge]; bary[ip] = 1. - bary[iEdge];
+  return dd;
+}
+// tri_mesh_I.h:174-255
+__device__ double resolve_corner(const TriRec &T, int iNode, bool obtuse, const double *p, double *delta, double *bary)
+{
+  const int ip = (iNode + 1) % 3, ipp = (iNode + 2) % 3;
+  const double *n = T.node + 3 * iNode;
+  if (obtuse) {
+    double nodeToP[3], cp[3];
+    sub3(p, n, nodeToP);
+    double distFromNode = dot3(nodeToP, T.edgeVec + 3 * ipp);
+    if (distFromNode < SMALL_TRIMESH) {
+      if (distFromNode > -T.edgeLen[ipp]) {
+        if (!edge_active(T, ipp)) return LARGE_TRIMESH;
+        for (int d = 0; d < 3; d++) cp[d] = n[d] + distFromNode * T.edgeVec[3 * ipp + d];
+        bary[ip] = 0.; bary[iNode] = 1. + distFromNode / T.edgeLen[ipp]; bary[ipp] = 1. - bary[iNode];
+        return calc_dist(p, cp, delta);
+      } else {
+        if (!corner_active(T, ipp)) return LARGE_TRIMESH;
+        bary[ipp] = 1.; bary[iNode] = bary[ip] = 0.;
+        return calc_dist(p, T.node + 3 * ipp, delta);
+      }
+    }
+    distFromNode = dot3(nodeToP, T.edgeVec + 3 * iNode);
+    if (distFromNode > -SMALL_TRIMESH) {
+      if (distFromNode < T.edgeLen[iNode]) {
+        if (!edge_active(T, iNode)) return LARGE_TRIMESH;
+        for (int d = 0; d < 3; d++) cp[d] = n[d] + distFromNode * T.edgeVec[3 * iNode + d];
+        bary[ipp] = 0.; bary[iNode] = 1. - distFromNode / T.edgeLen[iNode]; bary[ip] = 1. - bary[iNode];
+        return calc_dist(p, cp, delta);
+      } else {
+        if (!corner_active(T, ip)) return LARGE_TRIMESH;
+        bary[ip] = 1.; bary[iNode] = bary[ipp] = 0.;
+        return calc_dist(p, T.node + 3 * ip, delta);
+      }
+    }
+  }
+  if (!corner_active(T, iNode)) return LARGE_TRIMESH;
+  bary[iNode] = 1.; bary[ip] = bary[ipp] = 0.;
+  return calc_dist(p, n, delta);
+}
+// TriMesh::resolveTriSphereContactBary  tri_mesh_I.h:65-127 ; returns distance - radius
+__device__ double tri_contact(const TriRec &T, double precision, double rSphere, const double *c, double *delta, double *bary, int &barySign)
+{
+  double n0c[3];
+  sub3(c, T.node, n0c);
+  {  // MathExtraLiggghts::calcBaryTriCoords  math_extra_liggghts.h:583-594
+    const double a = dot3(n0c, T.edgeVec), b = dot3(n0c, T.edgeVec + 6), cc = dot3(T.edgeVec, T.edgeVec + 6);
+    const double oneMinCSqr = 1 - cc * cc;
+    bary[1] = (a - b * cc) / (T.edgeLen[0] * oneMinCSqr);
+    bary[2] = (a * cc - b) / (T.edgeLen[2] * oneMinCSqr);
+    bary[0] = 1. - bary[1] - bary[2];
+  }
+  const double invlen = 1. / (2. * T.rbound);
+  const int bs = (bary[0] > -precision * invlen) + 2 * (bary[1] > -precision * invlen) + 4 * (bary[2] > -precision * invlen);
+  barySign = bs;
+  const int ob = (T.flags & 3) - 1;
+  double d = 1.;
+  switch (bs) {
+    case 1: d = resolve_corner(T, 0, ob == 0, c, delta, bary); break;
+    case 2: d = resolve_corner(T, 1, ob == 1, c, delta, bary); break;
+    case 3: d = resolve_edge(T, 0, c, delta, bary); break;
+    case 4: d = resolve_corner(T, 2, ob == 2, c, delta, bary); break;
+    case 5: d = resolve_edge(T, 2, c, delta, bary); break;
+    case 6: d = resolve_edge(T, 1, c, delta, bary); break;
+    case 7: {  // resolveFaceContactBary :259-271
+      const double dNorm = dot3(T.surfNorm, n0c);
+      double cs[3];
+      for (int k = 0; k < 3; k++) cs[k] = c[k] - T.surfNorm[k] * dNorm;
+      d = calc_dist(c, cs, delta);
+      break;
+    }
+    default: d = 1.; break;
+  }
+  return d - rSphere;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int *part_row(const MeshP &M, int s, int i) { return M.mint + (size_t)(1 + s) * M.cap + i; }
+__device__ __forceinline__ int *cand_row(const MeshP &M, int k, int i) { return M.mint + (size_t)(1 + M.mslots + k) * M.cap + i; }
+__device__ __forceinline__ double4 *hist_rec(const MeshP &M, int s, int r, int i) { return M.mhist + (size_t)(s * M.hrec + r) * M.cap + i; }
+__device__ __forceinline__ void zero_hist(const MeshP &M, int s, int i)
+{
+  for (int r = 0; r < M.hrec; r++) *hist_rec(M, s, r, i) = make_double4(0., 0., 0., 0.);
+}
+__device__ __forceinline__ void swap_rows(const MeshP &M, int a, int b, int i)
+{
+  int *pa = part_row(M, a, i), *pb = part_row(M, b, i);
+  const int t = *pa; *pa = *pb; *pb = t;
+  for (int r = 0; r < M.hrec; r++) { double4 *ha = hist_rec(M, a, r, i), *hb = hist_rec(M, b, r, i); const double4 h = *ha; *ha = *hb; *hb = h; }
+}
+
+__global__ void __launch_bounds__(128) k_mesh_cand(const MeshP M, int nlocal, const double4 *xr, double skin, double cdf)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  const double4 x4 = xr[i];
+  const double x[3] = {x4.x, x4.y, x4.z};
+  int c[3];
+  for (int d = 0; d < 3; d++) { c[d] = (int)floor((x[d] - M.gorg[d]) * M.ginv[d]); c[d] = min(max(c[d], 0), M.gnc[d] - 1); }
+  const int cell = (c[2] * M.gnc[1] + c[1]) * M.gnc[0] + c[0];
+  const int s = M.cell_start[cell], e = M.cell_start[cell + 1];
+  int n = 0;
+  for (int q = s; q < e; q++) {  // FixNeighlistMesh::checkBin fix_neighlist_mesh.cpp:313-363
+    const int t = M.cell_tri[q];
+    const TriRec &T = M.tri[t];
+    const double thr = M.meta[T.mesh].moving ? skin : 0.5 * skin;  // :254-268
+    if (tri_neighbuild(T, x4.w * cdf, x, thr)) { if (n < M.mcand) *cand_row(M, n, i) = t; n++; }
+  }
+  if (n > M.mcand) atomicMax(M.overflow, n);
+  const int nnew = min(n, M.mcand);
+  // carry the contact rows over the rebuild
+  const int nold = min(M.mint[i], M.mslots);
+  for (;;) {  // FixContactHistoryMesh::sort_contacts fix_contact_history_mesh.cpp:375-403
+    int fe = -1, lf = -1;
+    for (int j = 0; j < nold; j++) { const int p = *part_row(M, j, i); if (fe == -1 && p == -1) fe = j; if (p >= 0) lf = j; }
+    if (fe > -1 && lf > -1 && fe < lf) swap_rows(M, fe, lf, i); else break;
+  }
+  int np = 0;
+  for (int j = 0; j < nold; j++) np += *part_row(M, j, i) >= 0;
+  int ip = 0;
+  while (ip < np) {  // cleanUpContactJumps :467-504
+    const int p = *part_row(M, ip, i);
+    bool in = false;
+    for (int k = 0; k < nnew; k++) in |= (*cand_row(M, k, i) == p);
+    if (!in) { *part_row(M, ip, i) = -1; zero_hist(M, ip, i); swap_rows(M, ip, np - 1, i); np--; }
+    else ip++;
+  }
+  M.mint[i] = nnew;
+}
+
+__device__ __noinline__ void mesh_chain(const StepP &P, const ModelP &m, const Contact &c, double (&h)[3], double (&g)[3], bool su, ContactOut &o)
+{
+  switch (m.normal * 4 + m.rolling) {
+    case N_HERTZ * 4 + R_OFF: contact_chain<N_HERTZ, R_OFF, true>(P, m, c, h, g, su, o); break;
+    case N_HERTZ * 4 + R_CDT: contact_chain<N_HERTZ, R_CDT, true>(P, m, c, h, g, su, o); break;
+    case N_HERTZ * 4 + R_EPSD: contact_chain<N_HERTZ, R_EPSD, true>(P, m, c, h, g, su, o); break;
+    case N_HERTZ * 4 + R_EPSD2: contact_chain<N_HERTZ, R_EPSD2, true>(P, m, c, h, g, su, o); break;
+    case N_HOOKE * 4 + R_OFF: contact_chain<N_HOOKE, R_OFF, true>(P, m, c, h, g, su, o); break;
+    case N_HOOKE * 4 + R_CDT: contact_chain<N_HOOKE, R_CDT, true>(P, m, c, h, g, su, o); break;
+    case N_HOOKE * 4 + R_EPSD: contact_chain<N_HOOKE, R_EPSD, true>(P, m, c, h, g, su, o); break;
+    default: contact_chain<N_HOOKE, R_EPSD2, true>(P, m, c, h, g, su, o); break;
+  }
+}
+
+__device__ __forceinline__ bool coplanar_nn(const MeshP &M, int a, int b)
+{  // SurfaceMesh::areCoplanarNodeNeighs surface_mesh_I.h:921-958, precomputed per triangle on the host
+  const int *l = M.cn + (size_t)a * DEM_MAXCN;
+  for (int k = 0; k < DEM_MAXCN; k++) { const int q = l[k]; if (q < 0) return false; if (q == b) return true; }
+  return false;
+}
+
+// FixWallGran::post_force_mesh fix_wall_gran.cpp:803-982 for the particles of the compact wall list
+__global__ void __launch_bounds__(128) k_mesh_step(const StepP P, const MeshP M)
+{
+  const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cidx >= P.nwc) return;
+  const int i = P.wlist[cidx];
+  const int nct = M.mint[i];
+  if (!nct) return;
+  const double4 xi = P.xr[i], vi = P.vm[i], wi = P.wt[i];
+  const double pos[3] = {xi.x, xi.y, xi.z};
+  const double radi = xi.w;
+  const int itype = (int)(__double_as_longlong(wi.w) & 0xff);
+  const bool su = (P.mode != MODE_SETUP);
+  const int nrows = min(nct, M.mslots);  // the reference sizes the rows by the candidate count
+  unsigned keep = 0;                     // markAllContacts: nothing kept yet
+  double F[3] = {0., 0., 0.}, Tq[3] = {0., 0., 0.};
+  for (int k = 0; k < nct; k++) {
+    const int t = *cand_row(M, k, i);
+    const TriRec &T = M.tri[t];
+    const MeshMeta &mm = M.meta[T.mesh];
+    double delta[3], bary[3];
+    int barysign = -1;
+    const double deltan = tri_contact(T, mm.precision, radi, pos, delta, bary, barysign);
+    if (deltan > P.cutneighmax) continue;
+    const bool intersect = (deltan <= 0);
+    if (!(deltan <= 0 || deltan < (P.cdf - 1.0) * radi)) continue;
+    // FixContactHistoryMesh::handleContact fix_contact_history_mesh_I.h:51-87
+    int slot = -1;
+    for (int s = 0; s < nrows; s++) if (*part_row(M, s, i) == t) { slot = s; break; }
+    if (slot < 0) {
+      const bool faceflag = (7 == barysign);
+      if (faceflag) {  // coplanarContactAlready :118-137
+        bool already = false;
+        for (int s = 0; s < nrows; s++) { const int q = *part_row(M, s, i); if (q >= 0 && q != t && ((keep >> s) & 1u) && coplanar_nn(M, q, t)) { already = true; break; } }
+        if (already) continue;
+      }
+      for (int s = 0; s < nrows; s++) if (*part_row(M, s, i) == -1) { slot = s; break; }  // addNewTriContactToExistingParticle :166-208
+      if (slot < 0) { atomicMax(M.overflow + 1, nct + 1); continue; }
+      *part_row(M, slot, i) = t;
+      zero_hist(M, slot, i);
+      if (faceflag)  // checkCoplanarContactHistory :141-160 (the last coplanar partner wins)
+        for (int s = 0; s < nrows; s++) { const int q = *part_row(M, s, i); if (q >= 0 && q != t && coplanar_nn(M, q, t)) for (int r = 0; r < M.hrec; r++) *hist_rec(M, slot, r, i) = *hist_rec(M, s, r, i); }
+    }
+    keep |= 1u << slot;
+    const ModelP &wm = M.wm[T.mesh];
+    if (intersect) {  // Walls::Granular::compute_force fix_wall_gran_base.h:159-367
+      Contact c;
+      c.dx = -delta[0]; c.dy = -delta[1]; c.dz = -delta[2];
+      c.radi = radi; c.radj = 0.0; c.radsum = radi; c.deltan_in = -deltan;
+      c.r = c.radi - c.deltan_in; c.rinv = 1.0 / c.r;
+      c.meff = vi.w; c.mi = vi.w; c.mj = 0.0;
+      c.vi[0] = vi.x; c.vi[1] = vi.y; c.vi[2] = vi.z;
+      c.wi[0] = wi.x; c.wi[1] = wi.y; c.wi[2] = wi.z;
+      c.wj[0] = c.wj[1] = c.wj[2] = 0.0;
+      for (int d = 0; d < 3; d++) c.vj[d] = 0.0;
+      if (mm.moving && su)  // per-node mesh velocity is zero during setup (fix_move_mesh.cpp:194-217), v_node = 0 + vel afterwards
+        for (int d = 0; d < 3; d++) { const double vn = 0. + mm.vel[d]; c.vj[d] = (bary[0] * vn + bary[1] * vn + bary[2] * vn); }
+      c.itype = itype; c.jtype = mm.atom_type;
+      double h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
+      if (wm.rec_shear >= 0) { const double4 v = *hist_rec(M, slot, wm.rec_shear, i); h[0] = v.x; h[1] = v.y; h[2] = v.z; }
+      if (wm.rec_roll >= 0) { const double4 v = *hist_rec(M, slot, wm.rec_roll, i); g[0] = v.x; g[1] = v.y; g[2] = v.z; }
+      ContactOut o;
+      mesh_chain(P, wm, c, h, g, su, o);
+      F[0] += o.F[0]; F[1] += o.F[1]; F[2] += o.F[2];
+      Tq[0] += o.Ti[0]; Tq[1] += o.Ti[1]; Tq[2] += o.Ti[2];
+      if (su) {
+        if (wm.rec_shear >= 0) *hist_rec(M, slot, wm.rec_shear, i) = make_double4(h[0], h[1], h[2], 0.);
+        if (wm.rec_roll >= 0) *hist_rec(M, slot, wm.rec_roll, i) = make_double4(g[0], g[1], g[2], 0.);
+      }
+    } else zero_hist(M, slot, i);  // surfacesClose: tangential / rolling history zeroed
+  }
+  for (int s = 0; s < nrows; s++)  // cleanUpContacts fix_contact_history_mesh.cpp:437-463
+    if (!((keep >> s) & 1u) && *part_row(M, s, i) != -1) { *part_row(M, s, i) = -1; zero_hist(M, s, i); }
+#pragma unroll
+  for (int d = 0; d < 3; d++) { P.fw[(size_t)d * P.nwcap + cidx] += F[d]; P.fw[(size_t)(3 + d) * P.nwcap + cidx] += Tq[d]; }
+}
+
+// fix move/mesh linear: node += vel*dt, center += vel*dt ; a node that moved more than skin/2 since the last
+// rebuild raises the flag (MultiNodeMesh::decideRebuild)
+__global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, double dt, double trigsq, int *flag)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const MeshMeta &mm = M.meta[mesh];
+  if (q >= mm.ntri) return;
+  const int t = mm.first + q;
+  TriRec &T = M.tri[t];
+  double dx[3];
+  for (int d = 0; d < 3; d++) dx[d] = mm.vel[d] * dt;
+  bool trig = false;
+  for (int j = 0; j < 3; j++) {
+    double dd[3];
+    for (int d = 0; d < 3; d++) { T.node[3 * j + d] = T.node[3 * j + d] + dx[d]; dd[d] = T.node[3 * j + d] - M.nodes_last[(size_t)t * 9 + 3 * j + d]; }
+    if (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2] > trigsq) trig = true;
+  }
+  for (int d = 0; d < 3; d++) T.center[d] = T.center[d] + dx[d];
+  if (trig) *((volatile int *)flag) = 1;
+}
+__global__ void __launch_bounds__(128) k_mesh_hold(const MeshP M)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.ntri) return;
+  for (int k = 0; k < 9; k++) M.nodes_last[(size_t)t * 9 + k] = M.tri[t].node[k];
+}
+
+void mesh_launch_candidates(const MeshP &M, int nlocal, const double4 *xr, double skin, double cdf, cudaStream_t st)
+{
+  if (nlocal > 0) k_mesh_cand<<<(nlocal + 127) / 128, 128, 0, st>>>(M, nlocal, xr, skin, cdf);
+}
+void mesh_launch_step(const StepP &P, const MeshP &M, cudaStream_t st)
+{
+  if (P.nwc > 0) k_mesh_step<<<(P.nwc + 127) / 128, 128, 0, st>>>(P, M);
+}
+void mesh_launch_move(const MeshP &M, int mesh, double dt, double trigsq, int *flag, cudaStream_t st)
+{
+  const int n = M.meta[mesh].ntri;
+  if (n > 0) k_mesh_move<<<(n + 127) / 128, 128, 0, st>>>(M, mesh, dt, trigsq, flag);
+}
+void mesh_launch_hold(const MeshP &M, cudaStream_t st)
+{
+  if (M.ntri > 0) k_mesh_hold<<<(M.ntri + 127) / 128, 128, 0, st>>>(M);
+}
+
+}  // namespace dem

@@ -44,6 +44,8 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
         props.append(("coefficientRollingViscousDamping", "peratomtypepair", np.full(T * T, 0.3)))
     if "hooke" in model:
         props.append(("characteristicVelocity", "scalar", [2.0]))
+    if "epsd2" in model:  # registered by the reference's epsd2 model although unused
+        pass
     # wall/gran keyword order: model selection, wall keywords, then on/off settings (fix_wall_gran.cpp:150-342)
     st = (" " + settings) if settings else ""
     walls = [("zw", model + " primitive type %d zplane 0.0" % T + (" shear x 0.2" if shear else "") + st)]
@@ -124,6 +126,18 @@ def case_mesh(kind="box", n3=(4, 4, 4), model="model hertz tangential history ro
     return c
 
 
+def write_stl(path, nodes, name="mesh"):
+    """ASCII STL with round-trip (%.17g) vertices: the reference parses them with atof (input_mesh_tri.cpp:509-511)"""
+    with open(path, "w") as f:
+        f.write("solid %s\n" % name)
+        for t in np.asarray(nodes, np.float64).reshape(-1, 3, 3):
+            f.write(" facet normal 0 0 0\n  outer loop\n")
+            for v in t:
+                f.write("   vertex %.17g %.17g %.17g\n" % tuple(v))
+            f.write("  endloop\n endfacet\n")
+        f.write("endsolid %s\n" % name)
+
+
 def to_deck(c, datafile):
     """LIGGGHTS deck + data file text for the reference (grammar: SURVEY.md 8b)"""
     n = len(c["tag"])
@@ -149,9 +163,8 @@ def to_deck(c, datafile):
     for wid, text in c["walls"]:
         deck.append("fix %s all wall/gran %s" % (wid, text))
     for mid, mtype, nodes in c.get("meshes", []):
-        import dem_b200
         stl = os.path.join(os.path.dirname(datafile), mid + ".stl")
-        dem_b200.write_stl(stl, nodes, mid)
+        write_stl(stl, nodes, mid)
         deck.append("fix %s all mesh/surface file %s type %d" % (mid, stl, mtype))
     for mid, text in c.get("mesh_moves", []):
         deck.append("fix mv_%s all move/mesh mesh %s %s" % (mid, mid, text))
@@ -200,11 +213,20 @@ GOLDEN_CASES = {
                                    poly=True, periodic=(1, 1, 0), ntypes=2, shear=True), checkpoints=[0, 1, 2, 10, 400, 2500]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
+    # triangle-mesh walls (fix mesh/surface + fix wall/gran mesh): coplanar floor grid, convex ridge, cone, moving plate
+    "mesh_box": dict(mesh="box", kw=dict(n3=(4, 4, 4)), checkpoints=[0, 1, 10, 400, 2500]),
+    "mesh_roof_epsd2": dict(mesh="roof", kw=dict(n3=(4, 4, 4), model="model hertz tangential history rolling_friction epsd2"),
+                            checkpoints=[0, 1, 10, 1500, 3000]),
+    "mesh_funnel_hooke": dict(mesh="funnel", kw=dict(n3=(4, 4, 3), model="model hooke tangential history rolling_friction cdt"),
+                              checkpoints=[0, 1, 10, 1500, 3000]),
+    "mesh_plate_moving": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
 }
 
 
 def make_case(name):
     g = GOLDEN_CASES[name]
+    if "mesh" in g:
+        return case_mesh(kind=g["mesh"], name=name, **g["kw"])
     return case_box(name=name, **g["kw"])
 
 

@@ -39,7 +39,15 @@ def run_case(name):
         for wid, text in c["walls"]:
             dn = 3 + (3 if "epsd" in text else 0)
             out["s%d_wall_%s" % (cp, wid)] = r.fix_peratom_array("history_" + wid, dn)
+        for mid, mtype, nodes in c.get("meshes", []):
+            m = r.mesh_contacts(mid)
+            out["s%d_mesh_%s_tag" % (cp, mid)] = m["tag"]; out["s%d_mesh_%s_tri" % (cp, mid)] = m["tri"]; out["s%d_mesh_%s_hist" % (cp, mid)] = m["hist"]
         out["s%d_nbuilds" % cp] = np.array(r.neigh_builds)
+    for mid, mtype, nodes in c.get("meshes", []):
+        t = r.mesh_topology(mid)
+        assert len(t["nodes"]) == len(nodes), "the reference dropped triangles of mesh " + mid
+        for k in ("edge_active", "corner_active", "nneighs"):
+            out["topo_%s_%s" % (mid, k)] = t[k]
     out["rmass"] = r.atoms()["rmass"]
     r.close()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

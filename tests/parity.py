@@ -66,7 +66,25 @@ def compare_snapshot(got, ref, rmass, tol=FTOL, tol_state=None, hist_tol=None, l
             tiny = 1e-12 * scale  # projections leave 1e-40-size residues: "zeroed" means far below scale
             assert np.array_equal(np.abs(got[k]) > tiny, np.abs(ref[k]) > tiny), "%s: %s bookkeeping differs" % (label, k)
             assert errs[k] <= hist_tol, "%s: %s rel err %.3e" % (label, k, errs[k])
+    for k in ref:  # triangle-mesh contact rows: (tag, triangle) sets bit-exact, history to tolerance
+        if k.startswith("mesh_") and k.endswith("_tag"):
+            mid = k[5:-4]
+            gt, gi = got["mesh_%s_tag" % mid], got["mesh_%s_tri" % mid]
+            assert len(gt) == len(ref[k]) and np.array_equal(gt, ref[k]) and np.array_equal(gi, ref["mesh_%s_tri" % mid]), \
+                "%s: mesh %s contact rows differ" % (label, mid)
+            rh, gh = ref["mesh_%s_hist" % mid], got["mesh_%s_hist" % mid]
+            if rh.size:
+                errs["mesh_" + mid] = float(np.abs(gh - rh).max() / max(np.abs(rh).max(), 1e-300))
+                assert errs["mesh_" + mid] <= hist_tol, "%s: mesh %s history rel err %.3e" % (label, mid, errs["mesh_" + mid])
     return errs
+
+
+def compare_topology(eng, c, g):
+    """active edge / corner flags and neighbour counts of every mesh against the reference's (golden `topo_*`)"""
+    for mid, mtype, nodes in c.get("meshes", []):
+        for k in ("edge_active", "corner_active", "nneighs"):
+            got = eng.mesh_field(mid, k, len(nodes))
+            assert np.array_equal(got, g["topo_%s_%s" % (mid, k)]), "mesh %s: %s differs from the reference" % (mid, k)
 
 
 def golden(name):

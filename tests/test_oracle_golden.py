@@ -14,6 +14,8 @@ def test_oracle_matches_reference_golden(name):
     done = 0
     for cp in cases.GOLDEN_CASES[name]["checkpoints"]:
         e.setup()  # every `run` command of the deck starts with Verlet::setup (verlet.cpp:134)
+        if done == 0:
+            parity.compare_topology(e, c, g)  # mesh cases: active edges / corners as the reference derived them
         e.run(cp - done); done = cp
         snap = cases.snapshot(e, c)
         ref = parity.golden_at(g, cp)
