@@ -31,12 +31,17 @@
 
 enum { N_HERTZ = 1, N_HOOKE = 2 };
 enum { R_OFF = 0, R_CDT = 1, R_EPSD = 2, R_EPSD2 = 3 };
-enum { CONTACT_NORMAL = 2, CONTACT_TANGENTIAL = 4, CONTACT_ROLLING = 16 }; /* contact_model_constants.h:64-69 (values irrelevant: only != 0 is tested) */
+enum { CONTACT_NORMAL = 1, CONTACT_COHESION = 2, CONTACT_TANGENTIAL = 4, CONTACT_ROLLING = 8 }; /* contact_model_constants.h:64-69 (values irrelevant: only != 0 is tested) */
 
+enum { C_OFF = 0, C_BOND = 1, C_BONDNL = 2 };
 typedef struct {
   int normal, tangential, rolling;
   int tangential_damping, limitForce, torsionTorque, ktToKn;
   int dnum, off_shear, off_roll;
+  /* cohesion bond / bond/nonlinear: cohesion_model_bond.h:254-276, cohesion_model_bond_nonlinear.h:233-246 */
+  int cohesion, off_bond;
+  int stressBreak, tension, compression, shear, ntorque, ttorque, createAlways, damping, dampingSmooth, ratioTC;
+  signed char nflag[40]; /* newtonflag of every history value (1: flips sign with the pair orientation) */
 } model_t;
 
 typedef struct {
@@ -81,6 +86,8 @@ typedef struct orc_engine {
       rmu[MAXT + 1][MAXT + 1], rvisc[MAXT + 1][MAXT + 1], charVel;
   /* derived (global_properties.cpp:428-560) */
   double Yeff[MAXT + 1][MAXT + 1], Geff[MAXT + 1][MAXT + 1], betaeff[MAXT + 1][MAXT + 1], corLog[MAXT + 1][MAXT + 1];
+  /* bond properties (peratomtypepair unless noted), index = enum BP_* */
+  double bp[32][MAXT + 1][MAXT + 1]; double tsCreateBond; double rmin;
   model_t pm; int have_pair;
   wall_t walls[MAXW]; int nwalls;
   mesh_t meshes[MAXMESH]; int nmeshes; meshwall_t mwalls[MAXMESH]; int nmwalls;
@@ -128,11 +135,29 @@ int orc_set_neighbor(orc_engine *e, double skin, int every, int delay, int check
 { e->skin = skin; e->every = every; e->delay = delay; e->check = check; return 0; }
 int orc_set_timestep(orc_engine *e, double dt) { e->dt = dt; return 0; }
 
+/* peratomtypepair properties of the two bond models (cohesion_model_bond.h:76-178, cohesion_model_bond_nonlinear.h:77-147) */
+enum { BP_LAMBDA = 0, BP_KN, BP_KT, BP_DFN, BP_DFT, BP_DTN, BP_DTT, BP_MAXDIST, BP_MAXSIGMA, BP_MAXTAU, BP_CREATEDIST, BP_RATIOTC,
+       BP_K_FN1, BP_KU_FN1, BP_KC_FN1, BP_K_FN2, BP_KU_FN2, BP_KC_FN2, BP_K_FT, BP_K_TN, BP_KU_TN, BP_KC_TN, BP_K_TT, BP_KU_TT, BP_KC_TT, BP_COUNT };
+static int bond_prop_index(const char *name)
+{
+  static const char *lin[] = {"radiusMultiplierBond", "normalBondStiffnessPerUnitArea", "tangentialBondStiffnessPerUnitArea", "dampingNormalForceBond",
+    "dampingTangentialForceBond", "dampingNormalTorqueBond", "dampingTangentialTorqueBond", "maxDistanceBond", "maxSigmaBond", "maxTauBond", "createDistanceBond", "ratioTensionCompression"};
+  static const char *nl[] = {"radiusMultiplierBondnonlinear", "", "", "dampingNormalForceBondnonlinear", "dampingTangentialForceBondnonlinear",
+    "dampingNormalTorqueBondnonlinear", "dampingTangentialTorqueBondnonlinear", "maxDistanceBondnonlinear", "maxSigmaBondnonlinear", "maxTauBondnonlinear",
+    "createDistanceBondnonlinear", "ratioTensionCompressionBondnonlinear", "stiffnessPerUnitAreaK_fn1", "stiffnessPerUnitAreaKu_fn1", "stiffnessPerUnitAreaKc_fn1",
+    "stiffnessPerUnitAreaK_fn2", "stiffnessPerUnitAreaKu_fn2", "stiffnessPerUnitAreaKc_fn2", "stiffnessPerUnitAreaK_ft", "stiffnessPerUnitAreaK_tn",
+    "stiffnessPerUnitAreaKu_tn", "stiffnessPerUnitAreaKc_tn", "stiffnessPerUnitAreaK_tt", "stiffnessPerUnitAreaKu_tt", "stiffnessPerUnitAreaKc_tt"};
+  for (int k = 0; k < 12; k++) if (!strcmp(name, lin[k])) return k;
+  for (int k = 0; k < BP_COUNT; k++) if (nl[k][0] && !strcmp(name, nl[k])) return k;
+  return -1;
+}
+
 int orc_set_property(orc_engine *e, const char *name, const char *kind, const double *v, int n)
 {
   const int T = e->ntypes;
   if (!strcmp(kind, "scalar")) {
     if (!strcmp(name, "characteristicVelocity")) { e->charVel = v[0]; return 0; }
+    if (!strcmp(name, "tsCreateBond") || !strcmp(name, "tsCreateBondnonlinear")) { e->tsCreateBond = v[0]; return 0; }
     return fail(e, "unknown scalar property");
   }
   if (!strcmp(kind, "peratomtype")) {
@@ -148,6 +173,7 @@ int orc_set_property(orc_engine *e, const char *name, const char *kind, const do
                             : !strcmp(name, "coefficientFriction") ? e->mu
                             : !strcmp(name, "coefficientRollingFriction") ? e->rmu
                             : !strcmp(name, "coefficientRollingViscousDamping") ? e->rvisc : NULL;
+    if (!dst) { const int b = bond_prop_index(name); if (b >= 0) dst = e->bp[b]; }
     if (!dst) return fail(e, "unknown peratomtypepair property");
     for (int i = 0; i < T; i++) for (int j = 0; j < T; j++) dst[i + 1][j + 1] = v[i * T + j];
     return 0;
@@ -169,7 +195,12 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
     if (!strcmp(a[1], "history")) m->tangential = 1; else return fail(e, "tangential model not supported");
     a += 2; argc -= 2;
   }
-  if (argc > 1 && !strcmp(a[0], "cohesion")) return fail(e, "cohesion model not supported by the oracle yet");
+  m->tension = m->compression = m->shear = m->ntorque = m->ttorque = m->damping = 1;
+  if (argc > 1 && !strcmp(a[0], "cohesion")) {
+    if (!strcmp(a[1], "bond")) m->cohesion = C_BOND; else if (!strcmp(a[1], "bond/nonlinear")) m->cohesion = C_BONDNL;
+    else if (!strcmp(a[1], "off")) m->cohesion = C_OFF; else return fail(e, "cohesion model not supported");
+    a += 2; argc -= 2;
+  }
   if (argc > 1 && !strcmp(a[0], "rolling_friction")) {
     if (!strcmp(a[1], "cdt")) m->rolling = R_CDT; else if (!strcmp(a[1], "epsd")) m->rolling = R_EPSD;
     else if (!strcmp(a[1], "epsd2")) m->rolling = R_EPSD2; else if (!strcmp(a[1], "off")) m->rolling = R_OFF;
@@ -177,9 +208,14 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
     a += 2; argc -= 2;
   }
   /* history slot order = model construction order: cohesion, tangential, rolling (contact_models.h:141-145) */
-  m->dnum = 0; m->off_shear = m->off_roll = -1;
-  if (m->tangential) { m->off_shear = m->dnum; m->dnum += 3; }
-  if (m->rolling == R_EPSD || m->rolling == R_EPSD2) { m->off_roll = m->dnum; m->dnum += 3; }
+  m->dnum = 0; m->off_shear = m->off_roll = m->off_bond = -1;
+  memset(m->nflag, 0, sizeof m->nflag);
+  if (m->cohesion) { /* bondFlag, initial_dist, contactPos[3] (newtonflag 0) ; ft, torque/theta n, t (1) ; nonlinear: 14 more trackers (0) */
+    m->off_bond = m->dnum; for (int k = 5; k < 14; k++) m->nflag[m->dnum + k] = 1;
+    m->dnum += (m->cohesion == C_BOND) ? 14 : 28;
+  }
+  if (m->tangential) { m->off_shear = m->dnum; for (int k = 0; k < 3; k++) m->nflag[m->dnum + k] = 1; m->dnum += 3; }
+  if (m->rolling == R_EPSD || m->rolling == R_EPSD2) { m->off_roll = m->dnum; for (int k = 0; k < 3; k++) m->nflag[m->dnum + k] = 1; m->dnum += 3; }
   *pargc = argc; *pargv = a; return 0;
 }
 /* Settings::parseArguments: trailing `key on|off` pairs registered by the selected models */
@@ -193,6 +229,17 @@ static int parse_settings(orc_engine *e, int argc, const char *const *a, model_t
     else if (!strcmp(a[0], "limitForce")) m->limitForce = on;
     else if (!strcmp(a[0], "torsionTorque") && m->rolling != R_OFF) m->torsionTorque = on;
     else if (!strcmp(a[0], "ktToKnUser") && m->normal == N_HOOKE) m->ktToKn = on;
+    else if (m->cohesion && !strcmp(a[0], "stressBreak")) m->stressBreak = on;
+    else if (m->cohesion && !strcmp(a[0], "tensionStress")) m->tension = on;
+    else if (m->cohesion && !strcmp(a[0], "compressionStress")) m->compression = on;
+    else if (m->cohesion && !strcmp(a[0], "shearStress")) m->shear = on;
+    else if (m->cohesion && !strcmp(a[0], "normalTorqueStress")) m->ntorque = on;
+    else if (m->cohesion && !strcmp(a[0], "shearTorqueStress")) m->ttorque = on;
+    else if (m->cohesion && !strcmp(a[0], "createBondAlways")) m->createAlways = on;
+    else if (m->cohesion && !strcmp(a[0], "dampingBond")) m->damping = on;
+    else if (m->cohesion && !strcmp(a[0], "dampingBondSmooth")) m->dampingSmooth = on;
+    else if (m->cohesion == C_BOND && !strcmp(a[0], "ratioTensionCompression")) m->ratioTC = on;
+    else if (m->cohesion == C_BONDNL && !strcmp(a[0], "ratioTensionCompressionBond")) m->ratioTC = on;
     else return fail(e, "unknown or unsupported setting");
     a += 2; argc -= 2;
   }
@@ -212,6 +259,7 @@ int orc_add_wall_primitive(orc_engine *e, const char *id, int argc, const char *
   wall_t *w = &e->walls[e->nwalls]; memset(w, 0, sizeof *w);
   snprintf(w->id, sizeof w->id, "%s", id);
   if (parse_model(e, &argc, &argv, &w->m)) return -1;
+  if (w->m.cohesion) return fail(e, "bond models on walls are not supported");
   if (argc < 4 || strcmp(argv[0], "primitive") || strcmp(argv[1], "type")) return fail(e, "expected 'primitive type T <style> ...'");
   w->atom_type = atoi(argv[2]);
   static const char *names[6] = {"xplane", "yplane", "zplane", "xcylinder", "ycylinder", "zcylinder"};
@@ -281,6 +329,7 @@ typedef struct {
   double kn, kt, gamman, gammat, Fn, vn, cri, crj, wr1, wr2, wr3, vtr1, vtr2, vtr3;
   double *hist; int *flag;
   double Fi[3], Ti[3], Fj[3], Tj[3];
+  double rsq; int has_force_update; long ntimestep; const double *xi;
 } sid_t;
 
 static void surface_default(sid_t *s)
@@ -477,11 +526,185 @@ static void rolling_epsd(const orc_engine *e, const model_t *m, sid_t *s)
   for (int d = 0; d < 3; d++) { s->Ti[d] -= rt[d]; s->Tj[d] += rt[d]; }
 }
 
+
+/* ---------------------------------------------------------------- cohesion models bond and bond/nonlinear (sphere-sphere) */
+static void vproject(const double *v, const double *on, double *res)
+{ /* vector_liggghts.h:437-442 vectorProject3D: normalises `on` first (zero vector -> zero) */
+  double n[3] = {on[0], on[1], on[2]};
+  const double norm = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]); const double inv = (norm == 0.) ? 0. : 1. / norm;
+  n[0] *= inv; n[1] *= inv; n[2] *= inv;
+  const double d = v[0] * n[0] + v[1] * n[1] + v[2] * n[2];
+  res[0] = n[0] * d; res[1] = n[1] * d; res[2] = n[2] * d;
+}
+static int isgn(double v) { return (0. < v) - (v < 0.); } /* math_extra_liggghts.h:120-123 */
+static double damp_mult(const model_t *m, double vel, double minvel, double dv) { return m->dampingSmooth ? fmin(1.0, fmax(-1.0, vel / fmax(minvel, dv))) : (double)isgn(vel); }
+
+/* hysteretic torque law of one component, cohesion_model_bond_nonlinear.h:669-872; tmax/tmin = the running extreme angles */
+static double nl_torque_comp(double theta, double *tmax, double *tmin, double k, double ku, double kc, double JI)
+{
+  if (theta > 0.0) *tmin = 0.0; else if (theta < 0.0) *tmax = 0.0;
+  const double c1 = (ku - k) / (ku + kc) * *tmax, c2 = (ku - k) / (ku + kc) * *tmin;
+  double tq;
+  if ((theta >= *tmax) || (theta <= *tmin)) tq = -k * JI * theta;
+  else if (theta > c1) tq = -ku * JI * theta + (ku - k) * JI * *tmax;
+  else if (theta >= c2) tq = kc * JI * theta;
+  else tq = -ku * JI * theta + (ku - k) * JI * *tmin;
+  if (theta > *tmax) *tmax = theta;
+  if (theta < *tmin) *tmin = theta;
+  return tq;
+}
+
+/* CohesionModel<COHESION_BOND>::surfacesClose cohesion_model_bond.h:491-950 and
+ * CohesionModel<COHESION_BOND_NONLINEAR>::surfacesClose cohesion_model_bond_nonlinear.h:394-940, sphere-sphere branch.
+ * Called for touching pairs (via surfacesIntersect) and for pairs inside the contact-distance band. */
+static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
+{
+  const int it = s->itype, jt = s->jtype, NL = (m->cohesion == C_BONDNL);
+  const int update_history = s->shearupdate; /* computeflag is 1 on this path */
+  const double lambda = e->bp[BP_LAMBDA][it][jt];
+  if (lambda < 1.e-15) return;
+  double *H = &s->hist[m->off_bond];
+  const double r_create = sqrt(s->rsq);
+  double r = r_create;
+  if (update_history) {
+    if (H[0] < 1.e-15) {
+      const int create = (m->createAlways || (s->ntimestep == (int)e->tsCreateBond)) && (r_create < e->bp[BP_CREATEDIST][it][jt]);
+      if (!create) return;
+      /* createBond :1015-1034 / createBondnonlinear :958-975 */
+      if (s->flag) *s->flag |= CONTACT_COHESION;
+      H[0] = 1.0; H[1] = r;
+      for (int d = 0; d < 3; d++) H[2 + d] = s->xi[d] - s->delta[d];
+      for (int d = 5; d < 14; d++) H[d] = 0.0;
+    }
+  } else if (H[0] < 1.e-15) return;
+  double force_tang[3] = {H[5], H[6], H[7]}, tn[3] = {H[8], H[9], H[10]}, tt[3] = {H[11], H[12], H[13]}; /* linear: torques ; nonlinear: angles */
+  const double radi = s->radi, radj = s->radj;
+  const double *delta = s->delta;
+  if (!m->stressBreak && r > e->bp[BP_MAXDIST][it][jt] && update_history) { /* breakBond :1036-1070 */
+    if (s->flag) *s->flag &= ~CONTACT_COHESION;
+    H[0] = 0.; H[1] = 0.; return;
+  }
+  if (s->flag) *s->flag |= CONTACT_COHESION;
+  const double rinv = 1. / r;
+  const double en[3] = {delta[0] * rinv, delta[1] * rinv, delta[2] * rinv};
+  const double *vi = s->vi, *vj = s->vj, *omegai = s->wi, *omegaj = s->wj;
+  const double rb = lambda * (radi < radj ? radi : radj);
+  const double A = M_PI * rb * rb, J = 0.5 * A * rb * rb, I = 0.5 * J, dt = e->dt;
+  const double radsuminv = 1. / (radi + radj);
+  const double cri = r * radi * radsuminv, crj = r * radj * radsuminv;
+  double vr[3], vn[3], vt[3], wr[3], tmp1[3], tmp2[3], vtr[3], wn[3], wt[3];
+  for (int d = 0; d < 3; d++) vr[d] = vi[d] - vj[d];
+  vproject(vr, en, vn);
+  for (int d = 0; d < 3; d++) vt[d] = vr[d] - vn[d];
+  for (int d = 0; d < 3; d++) { tmp1[d] = omegai[d] * (radi * radsuminv); tmp2[d] = omegaj[d] * (radj * radsuminv); wr[d] = tmp1[d] + tmp2[d]; }
+  tmp1[0] = delta[1] * wr[2] - delta[2] * wr[1]; tmp1[1] = delta[2] * wr[0] - delta[0] * wr[2]; tmp1[2] = delta[0] * wr[1] - delta[1] * wr[0];
+  for (int d = 0; d < 3; d++) vtr[d] = vt[d] + tmp1[d];
+  for (int d = 0; d < 3; d++) wr[d] = omegai[d] - omegaj[d];
+  vproject(wr, en, wn);
+  for (int d = 0; d < 3; d++) wt[d] = wr[d] - wn[d];
+  double nforce[3] = {0., 0., 0.}, nforce_d[3] = {0., 0., 0.}, tforce_d[3] = {0., 0., 0.}, ntorque_d[3] = {0., 0., 0.}, ttorque_d[3] = {0., 0., 0.};
+  double torque_normal[3] = {0., 0., 0.}, torque_tang[3] = {0., 0., 0.};
+  const double displacement = H[1] - r;
+  const double minvel = 1e-5 * fmin(radi, radj) / dt;
+  const double dfn = e->bp[BP_DFN][it][jt], dft = e->bp[BP_DFT][it][jt], dtn = e->bp[BP_DTN][it][jt], dtt = e->bp[BP_DTT][it][jt];
+  double dmax = 0., dmin = 0.;
+  if (NL) { /* running extreme displacements :566-580 (updated even when shearupdate == 0) */
+    if (displacement > H[14]) { H[14] = displacement; dmax = displacement; } else dmax = H[14];
+    if (displacement < H[27]) { H[27] = displacement; dmin = displacement; } else dmin = H[27];
+    if (displacement < 0.0) H[14] = 0.0;
+    if (displacement > 0.0) H[27] = 0.0;
+  }
+  if (m->tension || m->compression) {
+    if ((m->tension && displacement < -1.e-15) || (m->compression && displacement > 1.e-15)) {
+      double frcmag;
+      if (!NL) frcmag = e->bp[BP_KN][it][jt] * A * displacement;
+      else {
+        const double k1 = e->bp[BP_K_FN1][it][jt], ku1 = e->bp[BP_KU_FN1][it][jt], kc1 = e->bp[BP_KC_FN1][it][jt];
+        const double k2 = e->bp[BP_K_FN2][it][jt], ku2 = e->bp[BP_KU_FN2][it][jt], kc2 = e->bp[BP_KC_FN2][it][jt];
+        const double c1 = pow((ku1 - k1) / (ku1 + kc1), 2.0) * dmax, c2 = pow((ku2 - k2) / (ku2 + kc2), 1.0) * dmin;
+        if (displacement < dmin) frcmag = k2 * A * displacement;
+        else if (displacement < c2) frcmag = ku2 * A * displacement + (k2 - ku2) * A * dmin;
+        else if (displacement < 0.0) frcmag = -kc2 * A * displacement;
+        else if (displacement < c1) frcmag = -kc1 * pow(fabs(displacement), 0.5);
+        else if (displacement < dmax) frcmag = ku1 * pow(fabs(displacement), 0.5) + (k1 - ku1) * pow(fabs(dmax), 0.5);
+        else frcmag = k1 * pow(fabs(displacement), 0.5);
+      }
+      for (int d = 0; d < 3; d++) nforce[d] = en[d] * frcmag;
+      if (m->damping) for (int d = 0; d < 3; d++) nforce_d[d] = nforce[d] - dfn * fabs(nforce[d]) * damp_mult(m, vn[d], minvel, 0.01 * nforce[d] * dt);
+      else for (int d = 0; d < 3; d++) nforce_d[d] = nforce[d];
+    }
+  }
+  if (m->shear) {
+    const double ktA = (NL ? e->bp[BP_K_FT][it][jt] : e->bp[BP_KT][it][jt]);
+    double dtforce[3]; for (int d = 0; d < 3; d++) dtforce[d] = vtr[d] * (-ktA * A * dt);
+    vproject(force_tang, en, tmp1);
+    for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] - tmp1[d];
+    for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] + dtforce[d];
+    if (m->damping) for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d] - dft * fabs(force_tang[d]) * damp_mult(m, vtr[d], minvel, 0.01 * force_tang[d] * dt);
+    else for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d];
+  }
+  if (!NL) {
+    const double kn_pb = e->bp[BP_KN][it][jt], kt_pb = e->bp[BP_KT][it][jt];
+    for (int d = 0; d < 3; d++) { torque_normal[d] = tn[d]; torque_tang[d] = tt[d]; }
+    if (m->ntorque) {
+      double dnt[3]; for (int d = 0; d < 3; d++) dnt[d] = wn[d] * (-kt_pb * J * dt);
+      vproject(torque_normal, en, torque_normal);
+      for (int d = 0; d < 3; d++) torque_normal[d] = torque_normal[d] + dnt[d];
+      if (m->damping) for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d] - dtn * fabs(torque_normal[d]) * isgn(wn[d]);
+      else for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d];
+    }
+    if (m->ttorque) {
+      const double wtsq = wt[0] * wt[0] + wt[1] * wt[1] + wt[2] * wt[2];
+      if (wtsq > 0) {
+        double dtt3[3]; for (int d = 0; d < 3; d++) dtt3[d] = wt[d] * (-kn_pb * I * dt);
+        vproject(torque_tang, wt, torque_tang);
+        for (int d = 0; d < 3; d++) torque_tang[d] = torque_tang[d] + dtt3[d];
+        if (m->damping) for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d] - dtt * fabs(torque_tang[d]) * isgn(wt[d]);
+        else for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d];
+      }
+    }
+  } else {
+    if (m->ntorque) { /* :658-757 */
+      const double k = e->bp[BP_K_TN][it][jt], ku = e->bp[BP_KU_TN][it][jt], kc = e->bp[BP_KC_TN][it][jt];
+      for (int d = 0; d < 3; d++) tn[d] = tn[d] + wn[d] * dt;
+      for (int d = 0; d < 3; d++) torque_normal[d] = tn[d] * (-k * J);
+      vproject(torque_normal, wn, torque_normal);
+      for (int d = 0; d < 3; d++) torque_normal[d] = nl_torque_comp(tn[d], &H[15 + d], &H[21 + d], k, ku, kc, J);
+      if (m->damping) for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d] - dtn * fabs(torque_normal[d]) * isgn(wn[d]);
+      else for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d];
+    }
+    if (m->ttorque) { /* :760-872 */
+      const double k = e->bp[BP_K_TT][it][jt], ku = e->bp[BP_KU_TT][it][jt], kc = e->bp[BP_KC_TT][it][jt];
+      for (int d = 0; d < 3; d++) tt[d] = tt[d] + wt[d] * dt;
+      for (int d = 0; d < 3; d++) torque_tang[d] = nl_torque_comp(tt[d], &H[18 + d], &H[24 + d], k, ku, kc, I);
+      if (m->damping) for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d] - dtt * fabs(torque_tang[d]) * isgn(wt[d]);
+      else for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d];
+    }
+  }
+  if (m->stressBreak) { /* :816-848 / :875-890 (un-damped forces and torques) */
+    const double nfm = sqrt(nforce[0] * nforce[0] + nforce[1] * nforce[1] + nforce[2] * nforce[2]), tfm = sqrt(force_tang[0] * force_tang[0] + force_tang[1] * force_tang[1] + force_tang[2] * force_tang[2]),
+      ntm = sqrt(torque_normal[0] * torque_normal[0] + torque_normal[1] * torque_normal[1] + torque_normal[2] * torque_normal[2]), ttm = sqrt(torque_tang[0] * torque_tang[0] + torque_tang[1] * torque_tang[1] + torque_tang[2] * torque_tang[2]);
+    double maxSigma = e->bp[BP_MAXSIGMA][it][jt];
+    if (m->ratioTC && (NL ? displacement < -1.e-15 : displacement < 1e-16)) maxSigma *= e->bp[BP_RATIOTC][it][jt];
+    const int nstress = maxSigma < (nfm / A + ttm * rb / I);
+    const int tstress = e->bp[BP_MAXTAU][it][jt] < (tfm / A + ntm * rb / J);
+    if ((nstress || tstress) && update_history) { if (s->flag) *s->flag &= ~CONTACT_COHESION; H[0] = 0.; H[1] = 0.; return; }
+  }
+  double tor[3]; tor[0] = tforce_d[1] * en[2] - tforce_d[2] * en[1]; tor[1] = tforce_d[2] * en[0] - tforce_d[0] * en[2]; tor[2] = tforce_d[0] * en[1] - tforce_d[1] * en[0];
+  s->has_force_update = 1;
+  double F[3], Ti[3], Tj[3];
+  for (int d = 0; d < 3; d++) { F[d] = nforce_d[d] + tforce_d[d]; Ti[d] = cri * tor[d] + ntorque_d[d] + ttorque_d[d]; Tj[d] = crj * tor[d] - ntorque_d[d] - ttorque_d[d]; }
+  if (update_history) for (int d = 0; d < 3; d++) { H[5 + d] = force_tang[d]; H[8 + d] = NL ? tn[d] : torque_normal[d]; H[11 + d] = NL ? tt[d] : torque_tang[d]; }
+  if (!NL) for (int d = 0; d < 3; d++) { s->Fi[d] += F[d]; s->Ti[d] += Ti[d]; s->Fj[d] -= F[d]; s->Tj[d] += Tj[d]; }
+  else for (int d = 0; d < 3; d++) { s->Fi[d] = F[d]; s->Ti[d] = Ti[d]; s->Fj[d] = -F[d]; s->Tj[d] = Tj[d]; } /* the nonlinear bond OVERWRITES :917-937 */
+}
+
 /* ContactModel::surfacesIntersect, contact_models.h:228-238 */
 static void chain_intersect(const orc_engine *e, const model_t *m, sid_t *s)
 {
   surface_default(s);
   if (m->normal == N_HERTZ) normal_hertz(e, m, s); else normal_hooke(e, m, s);
+  if (m->cohesion) cohesion_bond(e, m, s);
   if (m->tangential) tangential_history(e, m, s);
   if (m->rolling == R_CDT) rolling_cdt(e, m, s);
   else if (m->rolling == R_EPSD || m->rolling == R_EPSD2) rolling_epsd(e, m, s);
@@ -1056,9 +1279,19 @@ static void pair_compute(orc_engine *e, int shearupdate)
         sd->meff = meff; sd->mi = mi; sd->mj = mj;
         sd->vi = &e->v[3 * i]; sd->vj = &e->v[3 * j]; sd->wi = &e->omega[3 * i]; sd->wj = &e->omega[3 * j];
         sd->hist = dnum ? &e->hist[m * dnum] : NULL; sd->flag = &e->flag[m];
+        sd->rsq = rsq; sd->ntimestep = e->ntimestep; sd->xi = &e->x[3 * i];
         chain_intersect(e, &e->pm, sd);
         for (int d = 0; d < 3; d++) { e->f[3 * i + d] += sd->Fi[d]; e->torque[3 * i + d] += sd->Ti[d]; e->f[3 * j + d] += sd->Fj[d]; e->torque[3 * j + d] += sd->Tj[d]; }
       } else if (rsq < cdm * radsum * radsum) { /* :420 ; unreachable when cdf == 1 */
+        if (e->pm.cohesion) { /* ContactModel::surfacesClose contact_models.h:246-253: the bond may act across the gap */
+          sid_t s_; sid_t *sd = &s_; memset(sd, 0, sizeof *sd);
+          sd->itype = e->type[i]; sd->jtype = e->type[j]; sd->shearupdate = shearupdate; sd->radi = radi; sd->radj = radj; sd->radsum = radsum;
+          sd->delta[0] = delx; sd->delta[1] = dely; sd->delta[2] = delz; sd->rsq = rsq; sd->ntimestep = e->ntimestep; sd->xi = &e->x[3 * i];
+          sd->vi = &e->v[3 * i]; sd->vj = &e->v[3 * j]; sd->wi = &e->omega[3 * i]; sd->wj = &e->omega[3 * j];
+          sd->hist = &e->hist[m * dnum]; sd->flag = &e->flag[m];
+          cohesion_bond(e, &e->pm, sd);
+          if (sd->has_force_update) for (int d = 0; d < 3; d++) { e->f[3 * i + d] += sd->Fi[d]; e->torque[3 * i + d] += sd->Ti[d]; e->f[3 * j + d] += sd->Fj[d]; e->torque[3 * j + d] += sd->Tj[d]; }
+        }
         chain_close(&e->pm, dnum ? &e->hist[m * dnum] : NULL, &e->flag[m]);
       }
     }
@@ -1128,6 +1361,24 @@ int orc_setup(orc_engine *e)
 { /* Verlet::setup verlet.cpp:134-199 */
   if (!e->n && !e->tag) return fail(e, "no particles uploaded");
   derive_tables(e);
+  e->cdf = 1.0;
+  if (e->have_pair && e->pm.cohesion) { /* cohesion_model_bond.h:391-475 / cohesion_model_bond_nonlinear.h:336-382: neighbor->register_contact_dist_factor */
+    double minrad = 1e99; for (long i = 0; i < e->n; i++) if (e->radius[i] < minrad) minrad = e->radius[i];
+    double cdf_all = 1.;
+    for (int i = 1; i <= e->ntypes; i++) for (int j = 1; j <= e->ntypes; j++) {
+      double one;
+      if (!e->pm.stressBreak) one = 1.1 * 0.5 * e->bp[BP_MAXDIST][i][j] / minrad;
+      else {
+        double stress = e->bp[BP_MAXSIGMA][i][j];
+        if (e->pm.ratioTC) stress = fmax(stress, stress * e->bp[BP_RATIOTC][i][j]);
+        if (e->pm.cohesion == C_BOND) one = 0.5 * (1.1 * e->bp[BP_CREATEDIST][i][j] / minrad + 1.1 * stress / (e->bp[BP_KN][i][j] * minrad));
+        else one = 0.5 * 1.1 * e->bp[BP_CREATEDIST][i][j] / minrad + 0.5 * 1.1 * stress / (e->bp[BP_K_FN2][i][j] * minrad);
+      }
+      cdf_all = one > cdf_all ? one : cdf_all;
+    }
+    if (cdf_all > 10.) return fail(e, "Maximum bond distance exceeding 10 x particle diameter");
+    e->cdf = cdf_all;
+  }
   for (int w = 0; w < e->nwalls; w++) if (!e->walls[w].hist) { e->walls[w].hist = (double *)calloc((size_t)(e->n ? e->n : 1) * (e->walls[w].m.dnum ? e->walls[w].m.dnum : 1), sizeof(double)); }
   for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].moving) memset(e->meshes[m].vnode, 0, sizeof(double) * 9 * e->meshes[m].ntri); /* FixMoveMesh::setup fix_move_mesh.cpp:194-217: v = 0 */
   build(e);
@@ -1200,7 +1451,7 @@ int orc_download_pairs(orc_engine *e, int *lo, int *hi, int *flag, double *hist)
     const int ti = e->tag[i], tj = e->tag[e->jlist[m]]; rows[k].swap = ti > tj; rows[k].lo = ti < tj ? ti : tj; rows[k].hi = ti < tj ? tj : ti; rows[k].flag = e->flag[m]; rows[k].m = m; k++; }
   qsort(rows, k, sizeof(prow_t), cmp_prow);
   for (long r = 0; r < k; r++) { lo[r] = rows[r].lo; hi[r] = rows[r].hi; if (flag) flag[r] = rows[r].flag;
-    if (hist) for (int d = 0; d < dnum; d++) hist[r * dnum + d] = rows[r].swap ? -e->hist[rows[r].m * dnum + d] : e->hist[rows[r].m * dnum + d]; }
+    if (hist) for (int d = 0; d < dnum; d++) hist[r * dnum + d] = (rows[r].swap && e->pm.nflag[d]) ? -e->hist[rows[r].m * dnum + d] : e->hist[rows[r].m * dnum + d]; }
   free(rows); return 0;
 }
 int orc_download_wall_history(orc_engine *e, const char *id, double *out, long count)

@@ -16,7 +16,7 @@ def lattice(n3, pitch, origin, jitter, rng):
 
 def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdt", seed=SEED,
              poly=False, periodic=(0, 0, 0), ntypes=1, hooke=False, frozen=0, cyl=False, shear=False, name="box",
-             settings=""):
+             settings="", bond=None):
     """particles on a jittered lattice falling under gravity onto a floor inside side walls"""
     rng = np.random.default_rng(seed)
     rad = 0.0025
@@ -46,8 +46,43 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
         props.append(("characteristicVelocity", "scalar", [2.0]))
     if "epsd2" in model:  # registered by the reference's epsd2 model although unused
         pass
+    wmodel = model
+    if bond:  # bonded-sphere decks: `cohesion bond|bond/nonlinear` on the pair style, plain contact model on the walls
+        kind = bond.get("kind", "bond")
+        wmodel = model
+        model = model.replace("tangential history", "tangential history cohesion " + kind)
+        sfx = "" if kind == "bond" else "nonlinear"
+        TT = T * T
+        full = lambda v: np.full(TT, float(v))
+        props += [("radiusMultiplierBond" + sfx, "peratomtypepair", full(bond.get("lam", 0.8))),
+                  ("dampingNormalForceBond" + sfx, "peratomtypepair", full(bond.get("damp", 0.1))),
+                  ("dampingTangentialForceBond" + sfx, "peratomtypepair", full(bond.get("damp", 0.1))),
+                  ("dampingNormalTorqueBond" + sfx, "peratomtypepair", full(bond.get("damp", 0.1))),
+                  ("dampingTangentialTorqueBond" + sfx, "peratomtypepair", full(bond.get("damp", 0.1))),
+                  ("tsCreateBond" + sfx, "scalar", [bond.get("ts", 2)]),
+                  ("createDistanceBond" + sfx, "peratomtypepair", full(bond.get("create", 2.2 * 0.003 if poly else 2.2 * rad)))]
+        if "stressBreak on" in settings:
+            props += [("maxSigmaBond" + sfx, "peratomtypepair", full(bond.get("sigma", 2e5))), ("maxTauBond" + sfx, "peratomtypepair", full(bond.get("tau", 1e5)))]
+        else:
+            props += [("maxDistanceBond" + sfx, "peratomtypepair", full(bond.get("maxdist", 2.5 * 0.003 if poly else 2.5 * rad)))]
+        if kind == "bond":
+            props += [("normalBondStiffnessPerUnitArea", "peratomtypepair", full(bond.get("kn", 2e9))),
+                      ("tangentialBondStiffnessPerUnitArea", "peratomtypepair", full(bond.get("kt", 1e9)))]
+        else:
+            k = bond.get("k", 1e9)
+            # the compression branch is k*sqrt(displacement) without the area factor (cohesion_model_bond_nonlinear.h:603-612)
+            for nm, val in (("K_fn1", 20.0), ("Ku_fn1", 80.0), ("Kc_fn1", 10.0)):
+                props.append(("stiffnessPerUnitArea" + nm, "peratomtypepair", full(val)))
+            for nm, f in (("K_fn2", 1.0), ("Ku_fn2", 4.0), ("Kc_fn2", 0.5), ("K_ft", 0.5),
+                          ("K_tn", 0.4), ("Ku_tn", 1.6), ("Kc_tn", 0.2), ("K_tt", 0.6), ("Ku_tt", 2.4), ("Kc_tt", 0.3)):
+                props.append(("stiffnessPerUnitArea" + nm, "peratomtypepair", full(k * f)))
     # wall/gran keyword order: model selection, wall keywords, then on/off settings (fix_wall_gran.cpp:150-342)
     st = (" " + settings) if settings else ""
+    wst = (" " + " ".join(w for w in [settings] if bond is None)) if (settings and bond is None) else ""
+    pair_model = model
+    model = wmodel
+    st_pair = st
+    st = wst if bond else st
     walls = [("zw", model + " primitive type %d zplane 0.0" % T + (" shear x 0.2" if shear else "") + st)]
     if cyl:
         walls.append(("cw", model + " primitive type 1 zcylinder %.17g %.17g %.17g" % (0.64 * L, 0.5 * L, 0.5 * L)
@@ -59,7 +94,7 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
         if not periodic[1]:
             walls += [("y0", model + " primitive type 1 yplane 0.0" + st), ("y1", model + " primitive type 1 yplane %.17g" % L + st)]
     return dict(name=name, lo=lo, hi=hi, periodic=list(periodic), ntypes=T, skin=0.001, dt=1e-5, props=props,
-                pair=model + st, walls=walls, gravity=(9.81, [0.0, 0.0, -1.0]), freeze=2 if frozen else 0,
+                pair=pair_model + st_pair, walls=walls, gravity=(9.81, [0.0, 0.0, -1.0]), freeze=2 if frozen else 0,
                 tag=np.arange(1, n + 1, dtype=np.int32), type=typ, mask=mask, x=x, v=v,
                 omega=rng.uniform(-5, 5, (n, 3)) * (0 if frozen else 1) + 0.0, radius=radius, density=np.full(n, 2500.0))
 
@@ -220,6 +255,14 @@ GOLDEN_CASES = {
     "mesh_funnel_hooke": dict(mesh="funnel", kw=dict(n3=(4, 4, 3), model="model hooke tangential history rolling_friction cdt"),
                               checkpoints=[0, 1, 10, 1500, 3000]),
     "mesh_plate_moving": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
+    # bonded spheres (INL bond models): bonds form at step 2, stretch, some break
+    # (sgn()-type bond damping makes these trajectories diverge from rounding noise within a few hundred steps: short horizons)
+    "bond_linear": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history", poly=True, bond=dict(kind="bond", maxdist=2.1 * 0.003)),
+                        checkpoints=[0, 1, 2, 3, 10, 100, 200]),
+    "bond_linear_stress": dict(kw=dict(n3=(4, 4, 3), model="model hertz tangential history rolling_friction cdt", settings="stressBreak on",
+                                       bond=dict(kind="bond", sigma=4e4, tau=2e4)), checkpoints=[0, 1, 2, 3, 10, 100]),
+    "bond_nonlinear": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history", poly=True, bond=dict(kind="bond/nonlinear")),
+                           checkpoints=[0, 1, 2, 3, 10, 100, 400]),
 }
 
 
@@ -235,6 +278,8 @@ def snapshot(eng, c):
     out = dict(eng.atoms(("x", "v", "f", "omega", "torque")))
     p = eng.pairs()
     out.update(pair_lo=p["lo"], pair_hi=p["hi"], pair_flag=(p["flag"] != 0).astype(np.int32), pair_hist=p["hist"])
+    if "cohesion" in c["pair"]:  # contactPos (history 2..4) is written at bond creation and read for wall bonds only: not compared
+        out["pair_hist"] = out["pair_hist"].copy(); out["pair_hist"][:, 2:5] = 0.0
     for wid, text in c["walls"]:
         dn = 3 + (3 if ("epsd" in text) else 0)
         out["wall_" + wid] = eng.wall_history(wid, dn)

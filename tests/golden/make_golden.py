@@ -35,6 +35,8 @@ def run_case(name):
             out["s%d_%s" % (cp, k)] = a[k]
         p = r.pairs()
         out["s%d_pair_lo" % cp] = p["lo"]; out["s%d_pair_hi" % cp] = p["hi"]
+        if "cohesion" in c["pair"]:
+            p["hist"][:, 2:5] = 0.0  # contactPos: written at bond creation, read for wall bonds only -> not part of the parity contract
         out["s%d_pair_flag" % cp] = (p["flag"] != 0).astype(np.int32); out["s%d_pair_hist" % cp] = p["hist"]
         for wid, text in c["walls"]:
             dn = 3 + (3 if "epsd" in text else 0)

@@ -87,6 +87,20 @@ def compare_topology(eng, c, g):
             assert np.array_equal(got, g["topo_%s_%s" % (mid, k)]), "mesh %s: %s differs from the reference" % (mid, k)
 
 
+def tol_for(c, cp, gpu=False):
+    """force/state tolerance at checkpoint `cp`.  The first steps carry the 1e-10 bar of BASELINE.json; DEM trajectories are
+    chaotic, so rounding-level differences (summation order, FMA contraction on the GPU) grow with the step count.  The bond
+    models damp with sgn(v)*|F| (cohesion_model_bond.h:700-712): a sign flip of a ~1e-16 velocity component changes a force by
+    2*damping*|F|, so bonded decks lose digits much faster and are only compared over short horizons."""
+    if cp <= 10:
+        return 1e-10
+    if "cohesion" in c["pair"]:
+        return 1e-5 if cp <= 100 else 1e-3
+    if gpu:
+        return 1e-6 if cp <= 400 else 1e-4
+    return 1e-7 if cp <= 400 else 1e-5
+
+
 def golden(name):
     return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
 

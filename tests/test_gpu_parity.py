@@ -31,7 +31,7 @@ def test_engine_matches_reference_golden(name):
             parity.compare_topology(e, c, g)
         e.run(cp - done); done = cp
         ref = parity.golden_at(g, cp)
-        parity.compare_snapshot(cases.snapshot(e, c), ref, g["rmass"], tol=tol_at(cp), label="%s@%d" % (name, cp))
+        parity.compare_snapshot(cases.snapshot(e, c), ref, g["rmass"], tol=parity.tol_for(c, cp, gpu=True), label="%s@%d" % (name, cp))
         assert e.stats().nbuilds == int(ref["nbuilds"]), "rebuild cadence differs at %d" % cp
     assert e.stats().kernel_launches > 0
     e.close()

@@ -20,7 +20,7 @@ def test_oracle_matches_reference_golden(name):
         snap = cases.snapshot(e, c)
         ref = parity.golden_at(g, cp)
         # trajectories are chaotic: rounding-level differences grow with step count
-        tol = 1e-10 if cp <= 10 else (1e-7 if cp <= 400 else 1e-5)
+        tol = parity.tol_for(c, cp)
         errs = parity.compare_snapshot(snap, ref, g["rmass"], tol=tol, label="%s@%d" % (name, cp))
         assert e.stats().nbuilds == int(ref["nbuilds"]) , "rebuild cadence differs at %d" % cp
     e.close()

@@ -34,6 +34,11 @@ for cp in cps:
     a = r.atoms(); p = r.pairs()
     ref = dict(x=a["x"], v=a["v"], f=a["f"], omega=a["omega"], torque=a["torque"], pair_lo=p["lo"], pair_hi=p["hi"],
                pair_flag=(p["flag"] != 0).astype(np.int32), pair_hist=p["hist"])
+    if "cohesion" in c["pair"]:
+        ref["pair_hist"][:, 2:5] = 0.0
+        msg_b = "bonds ref %d orc %d" % (int((ref["pair_hist"][:, 0] > 0).sum()), int((cases.snapshot(o, c)["pair_hist"][:, 0] > 0).sum()))
+    else:
+        msg_b = ""
     got = cases.snapshot(o, c)
     msg = []
     try:
@@ -47,5 +52,5 @@ for cp in cps:
         same = len(gt) == len(m["tag"]) and np.array_equal(gt, m["tag"]) and np.array_equal(gi, m["tri"])
         herr = float(np.abs(gh - m["hist"]).max() / max(np.abs(m["hist"]).max(), 1e-300)) if same and gh.size else 0.0
         msg.append("mesh %s rows %d/%d %s hist %.1e" % (mid, len(gt), len(m["tag"]), "OK" if same else "ROWS DIFFER", herr))
-    print("step %5d builds ref %d orc %d | %s" % (cp, r.neigh_builds, o.stats().nbuilds, " | ".join(msg)))
+    print("step %5d builds ref %d orc %d | %s %s" % (cp, r.neigh_builds, o.stats().nbuilds, " | ".join(msg), msg_b))
 print("log:", os.path.join(tmp, "log.liggghts"))
