@@ -44,7 +44,7 @@ __device__ __forceinline__ double tabp(const StepP &P, int which, int tij)
 // (fixed-size so that they live in registers; the caller maps them to rows off_shear.. / off_roll..)
 template <int NORMAL, int ROLLING, bool WALL>
 __device__ __forceinline__ void contact_chain(const StepP &P, const ModelP &M, const Contact &c,
-                                              double (&shear)[3], double (&ch)[3], bool shearupdate, ContactOut &o)
+                                              double (&shear)[3], double (&ch)[3], bool shearupdate, ContactOut &o, bool drop_normal = false)
 {
   const double enx = c.dx * c.rinv, eny = c.dy * c.rinv, enz = c.dz * c.rinv;
   // ---- surface model: relative kinematics at the contact point
@@ -94,6 +94,7 @@ __device__ __forceinline__ void contact_chain(const StepP &P, const ModelP &M, c
   double Fn = -gamman * vn + kn * deltan;
   if (M.limitForce && Fn < 0.0) Fn = 0.0;
   o.F[0] = Fn * enx; o.F[1] = Fn * eny; o.F[2] = Fn * enz;
+  if (drop_normal) o.F[0] = o.F[1] = o.F[2] = 0.0;  // cohesion bond/nonlinear assigns the pair force after the normal model
   o.Ti[0] = o.Ti[1] = o.Ti[2] = 0.0; o.Tj[0] = o.Tj[1] = o.Tj[2] = 0.0;
 
   // ---- tangential model: history
@@ -341,6 +342,177 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
   }
   F[0] += F1; F[1] += F2; F[2] += F3;
   T[0] += T1; T[1] += T2; T[2] += T3;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Bonded-sphere models, sphere-sphere branch:
+//   cohesion bond            cohesion_model_bond.h:491-950 (createBond :1015-1034, breakBond :1036-1070)
+//   cohesion bond/nonlinear  cohesion_model_bond_nonlinear.h:394-940 (:958-995)
+// Evaluated in the canonical orientation "first body = lower tag" by both owners of a pair, with identical operands in
+// identical order, so that the two copies of the history stay bit-identical (the running max/min trackers of the nonlinear
+// model are orientation dependent and carry no newtonflag in the reference: a canonical orientation is the only consistent
+// choice).  H = the nbond history doubles of the pair (bondFlag, initial_dist, contactPos[3], ft[3], tn[3], tt[3], trackers).
+// Returns true when the bond acts (the reference's has_force_update); F/Ti/Tj = force on the first body, torques on both.
+__device__ __forceinline__ void vproject(const double *v, const double *on, double *res)
+{  // vector_liggghts.h:437-442: `on` is normalised first (zero vector -> zero)
+  const double norm = sqrt(on[0] * on[0] + on[1] * on[1] + on[2] * on[2]);
+  const double inv = (norm == 0.) ? 0. : 1. / norm;
+  const double n0 = on[0] * inv, n1 = on[1] * inv, n2 = on[2] * inv;
+  const double d = v[0] * n0 + v[1] * n1 + v[2] * n2;
+  res[0] = n0 * d; res[1] = n1 * d; res[2] = n2 * d;
+}
+__device__ __forceinline__ double dsgn(double v) { return (double)((0. < v) - (v < 0.)); }
+__device__ __forceinline__ double damp_mult(const ModelP &M, double vel, double minvel, double dv)
+{
+  return M.dampingSmooth ? fmin(1.0, fmax(-1.0, vel / fmax(minvel, dv))) : dsgn(vel);
+}
+__device__ __forceinline__ double nl_torque_comp(double theta, double &tmax, double &tmin, double k, double ku, double kc, double JI)
+{  // one component of the hysteretic twist / bend law, cohesion_model_bond_nonlinear.h:669-872
+  if (theta > 0.0) tmin = 0.0; else if (theta < 0.0) tmax = 0.0;
+  const double c1 = (ku - k) / (ku + kc) * tmax, c2 = (ku - k) / (ku + kc) * tmin;
+  double tq;
+  if ((theta >= tmax) || (theta <= tmin)) tq = -k * JI * theta;
+  else if (theta > c1) tq = -ku * JI * theta + (ku - k) * JI * tmax;
+  else if (theta >= c2) tq = kc * JI * theta;
+  else tq = -ku * JI * theta + (ku - k) * JI * tmin;
+  if (theta > tmax) tmax = theta;
+  if (theta < tmin) tmin = theta;
+  return tq;
+}
+
+template <int COH>
+__device__ __noinline__ bool bond_eval(const StepP &P, const ModelP &M, const double *delta, double rsq, double radi, double radj,
+                                       const double *xi, const double *vi, const double *vj, const double *omegai, const double *omegaj,
+                                       int it, int jt, bool update_history, double *H, double *F, double *Ti, double *Tj)
+{
+  constexpr bool NL = (COH == C_BONDNL);
+  const double lambda = tabv(P, T_B_LAMBDA, it, jt);
+  if (lambda < 1.e-15) return false;
+  const double r = sqrt(rsq);
+  if (update_history) {
+    if (H[0] < 1.e-15) {
+      const bool create = (M.createAlways || (P.ntimestep == P.tsCreateBond)) && (r < tabv(P, T_B_CREATEDIST, it, jt));
+      if (!create) return false;
+      H[0] = 1.0; H[1] = r;
+      for (int d = 0; d < 3; d++) H[2 + d] = xi[d] - delta[d];
+      for (int d = 5; d < 14; d++) H[d] = 0.0;
+    }
+  } else if (H[0] < 1.e-15) return false;
+  double force_tang[3] = {H[5], H[6], H[7]}, tn[3] = {H[8], H[9], H[10]}, tt[3] = {H[11], H[12], H[13]};
+  if (!M.stressBreak && r > tabv(P, T_B_MAXDIST, it, jt) && update_history) { H[0] = 0.; H[1] = 0.; return false; }
+  const double rinv = 1. / r;
+  const double en[3] = {delta[0] * rinv, delta[1] * rinv, delta[2] * rinv};
+  const double rb = lambda * (radi < radj ? radi : radj);
+  const double A = 3.14159265358979323846 * rb * rb, J = 0.5 * A * rb * rb, I = 0.5 * J, dt = P.dt;
+  const double radsuminv = 1. / (radi + radj);
+  const double cri = r * radi * radsuminv, crj = r * radj * radsuminv;
+  double vr[3], vn[3], vt[3], wr[3], tmp1[3], vtr[3], wn[3], wt[3];
+  for (int d = 0; d < 3; d++) vr[d] = vi[d] - vj[d];
+  vproject(vr, en, vn);
+  for (int d = 0; d < 3; d++) vt[d] = vr[d] - vn[d];
+  for (int d = 0; d < 3; d++) wr[d] = omegai[d] * (radi * radsuminv) + omegaj[d] * (radj * radsuminv);
+  tmp1[0] = delta[1] * wr[2] - delta[2] * wr[1]; tmp1[1] = delta[2] * wr[0] - delta[0] * wr[2]; tmp1[2] = delta[0] * wr[1] - delta[1] * wr[0];
+  for (int d = 0; d < 3; d++) vtr[d] = vt[d] + tmp1[d];
+  for (int d = 0; d < 3; d++) wr[d] = omegai[d] - omegaj[d];
+  vproject(wr, en, wn);
+  for (int d = 0; d < 3; d++) wt[d] = wr[d] - wn[d];
+  double nforce[3] = {0., 0., 0.}, nforce_d[3] = {0., 0., 0.}, tforce_d[3] = {0., 0., 0.}, ntorque_d[3] = {0., 0., 0.}, ttorque_d[3] = {0., 0., 0.};
+  double torque_normal[3] = {0., 0., 0.}, torque_tang[3] = {0., 0., 0.};
+  const double displacement = H[1] - r;
+  const double minvel = 1e-5 * fmin(radi, radj) / dt;
+  const double dfn = tabv(P, T_B_DFN, it, jt), dft = tabv(P, T_B_DFT, it, jt), dtn = tabv(P, T_B_DTN, it, jt), dtt = tabv(P, T_B_DTT, it, jt);
+  double dmax = 0., dmin = 0.;
+  if (NL) {  // running extreme displacements, updated even when shearupdate == 0 (:566-580)
+    if (displacement > H[14]) { H[14] = displacement; dmax = displacement; } else dmax = H[14];
+    if (displacement < H[27]) { H[27] = displacement; dmin = displacement; } else dmin = H[27];
+    if (displacement < 0.0) H[14] = 0.0;
+    if (displacement > 0.0) H[27] = 0.0;
+  }
+  if (M.tension || M.compression) {
+    if ((M.tension && displacement < -1.e-15) || (M.compression && displacement > 1.e-15)) {
+      double frcmag;
+      if (!NL) frcmag = tabv(P, T_B_KN, it, jt) * A * displacement;
+      else {
+        const double k1 = tabv(P, T_B_K_FN1, it, jt), ku1 = tabv(P, T_B_KU_FN1, it, jt), kc1 = tabv(P, T_B_KC_FN1, it, jt);
+        const double k2 = tabv(P, T_B_K_FN2, it, jt), ku2 = tabv(P, T_B_KU_FN2, it, jt), kc2 = tabv(P, T_B_KC_FN2, it, jt);
+        const double q1 = (ku1 - k1) / (ku1 + kc1);
+        const double c1 = (q1 * q1) * dmax, c2 = ((ku2 - k2) / (ku2 + kc2)) * dmin;  // pow(x,2.0) and pow(x,1.0) are exact products in libm
+        if (displacement < dmin) frcmag = k2 * A * displacement;
+        else if (displacement < c2) frcmag = ku2 * A * displacement + (k2 - ku2) * A * dmin;
+        else if (displacement < 0.0) frcmag = -kc2 * A * displacement;
+        else if (displacement < c1) frcmag = -kc1 * sqrt(fabs(displacement));
+        else if (displacement < dmax) frcmag = ku1 * sqrt(fabs(displacement)) + (k1 - ku1) * sqrt(fabs(dmax));
+        else frcmag = k1 * sqrt(fabs(displacement));
+      }
+      for (int d = 0; d < 3; d++) nforce[d] = en[d] * frcmag;
+      if (M.damping) for (int d = 0; d < 3; d++) nforce_d[d] = nforce[d] - dfn * fabs(nforce[d]) * damp_mult(M, vn[d], minvel, 0.01 * nforce[d] * dt);
+      else for (int d = 0; d < 3; d++) nforce_d[d] = nforce[d];
+    }
+  }
+  if (M.shearf) {
+    const double ktA = NL ? tabv(P, T_B_K_FT, it, jt) : tabv(P, T_B_KT, it, jt);
+    double dtforce[3];
+    for (int d = 0; d < 3; d++) dtforce[d] = vtr[d] * (-ktA * A * dt);
+    vproject(force_tang, en, tmp1);
+    for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] - tmp1[d];
+    for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] + dtforce[d];
+    if (M.damping) for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d] - dft * fabs(force_tang[d]) * damp_mult(M, vtr[d], minvel, 0.01 * force_tang[d] * dt);
+    else for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d];
+  }
+  if (!NL) {
+    const double kn_pb = tabv(P, T_B_KN, it, jt), kt_pb = tabv(P, T_B_KT, it, jt);
+    for (int d = 0; d < 3; d++) { torque_normal[d] = tn[d]; torque_tang[d] = tt[d]; }
+    if (M.ntorque) {
+      double dnt[3];
+      for (int d = 0; d < 3; d++) dnt[d] = wn[d] * (-kt_pb * J * dt);
+      vproject(torque_normal, en, torque_normal);
+      for (int d = 0; d < 3; d++) torque_normal[d] = torque_normal[d] + dnt[d];
+      if (M.damping) for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d] - dtn * fabs(torque_normal[d]) * dsgn(wn[d]);
+      else for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d];
+    }
+    if (M.ttorque) {
+      const double wtsq = wt[0] * wt[0] + wt[1] * wt[1] + wt[2] * wt[2];
+      if (wtsq > 0) {
+        double dtt3[3];
+        for (int d = 0; d < 3; d++) dtt3[d] = wt[d] * (-kn_pb * I * dt);
+        vproject(torque_tang, wt, torque_tang);
+        for (int d = 0; d < 3; d++) torque_tang[d] = torque_tang[d] + dtt3[d];
+        if (M.damping) for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d] - dtt * fabs(torque_tang[d]) * dsgn(wt[d]);
+        else for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d];
+      }
+    }
+  } else {
+    if (M.ntorque) {
+      const double k = tabv(P, T_B_K_TN, it, jt), ku = tabv(P, T_B_KU_TN, it, jt), kc = tabv(P, T_B_KC_TN, it, jt);
+      for (int d = 0; d < 3; d++) tn[d] = tn[d] + wn[d] * dt;
+      for (int d = 0; d < 3; d++) torque_normal[d] = nl_torque_comp(tn[d], H[15 + d], H[21 + d], k, ku, kc, J);
+      if (M.damping) for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d] - dtn * fabs(torque_normal[d]) * dsgn(wn[d]);
+      else for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d];
+    }
+    if (M.ttorque) {
+      const double k = tabv(P, T_B_K_TT, it, jt), ku = tabv(P, T_B_KU_TT, it, jt), kc = tabv(P, T_B_KC_TT, it, jt);
+      for (int d = 0; d < 3; d++) tt[d] = tt[d] + wt[d] * dt;
+      for (int d = 0; d < 3; d++) torque_tang[d] = nl_torque_comp(tt[d], H[18 + d], H[24 + d], k, ku, kc, I);
+      if (M.damping) for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d] - dtt * fabs(torque_tang[d]) * dsgn(wt[d]);
+      else for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d];
+    }
+  }
+  if (M.stressBreak) {  // un-damped forces / torques (:816-848, :875-890)
+    const double nfm = sqrt(nforce[0] * nforce[0] + nforce[1] * nforce[1] + nforce[2] * nforce[2]);
+    const double tfm = sqrt(force_tang[0] * force_tang[0] + force_tang[1] * force_tang[1] + force_tang[2] * force_tang[2]);
+    const double ntm = sqrt(torque_normal[0] * torque_normal[0] + torque_normal[1] * torque_normal[1] + torque_normal[2] * torque_normal[2]);
+    const double ttm = sqrt(torque_tang[0] * torque_tang[0] + torque_tang[1] * torque_tang[1] + torque_tang[2] * torque_tang[2]);
+    double maxSigma = tabv(P, T_B_MAXSIGMA, it, jt);
+    if (M.ratioTC && (NL ? displacement < -1.e-15 : displacement < 1e-16)) maxSigma *= tabv(P, T_B_RATIOTC, it, jt);
+    const bool nstress = maxSigma < (nfm / A + ttm * rb / I);
+    const bool tstress = tabv(P, T_B_MAXTAU, it, jt) < (tfm / A + ntm * rb / J);
+    if ((nstress || tstress) && update_history) { H[0] = 0.; H[1] = 0.; return false; }
+  }
+  const double tor[3] = {tforce_d[1] * en[2] - tforce_d[2] * en[1], tforce_d[2] * en[0] - tforce_d[0] * en[2], tforce_d[0] * en[1] - tforce_d[1] * en[0]};
+  for (int d = 0; d < 3; d++) { F[d] = nforce_d[d] + tforce_d[d]; Ti[d] = cri * tor[d] + ntorque_d[d] + ttorque_d[d]; Tj[d] = crj * tor[d] - ntorque_d[d] - ttorque_d[d]; }
+  if (update_history) for (int d = 0; d < 3; d++) { H[5 + d] = force_tang[d]; H[8 + d] = NL ? tn[d] : torque_normal[d]; H[11 + d] = NL ? tt[d] : torque_tang[d]; }
+  return true;
 }
 
 }  // namespace dem

@@ -91,6 +91,8 @@ struct dem_engine {
   int every = 1, delay = 0, check = 1;
   double Y[MAXT + 1] = {0}, nu[MAXT + 1] = {0}, cor[MAXT + 1][MAXT + 1] = {{0}}, mu[MAXT + 1][MAXT + 1] = {{0}},
          rmu[MAXT + 1][MAXT + 1] = {{0}}, rvisc[MAXT + 1][MAXT + 1] = {{0}}, charVel = 0.0;
+  double bp[T_COUNT][MAXT + 1][MAXT + 1] = {{{0}}};  // bond tables, indexed by the T_B_* table id
+  double tsCreateBond = 0.0, rmin = 0.0;
   std::map<std::string, int> have_prop;
   ModelP pm = {};
   int have_pair = 0;
@@ -304,6 +306,24 @@ extern "C" int dem_set_timestep(dem_engine *e, double dt)
   API_END
 }
 
+// property/global names of the two bond models -> table id
+static int bond_table_of(const std::string &nm)
+{
+  static const std::map<std::string, int> m = {
+    {"radiusMultiplierBond", T_B_LAMBDA}, {"normalBondStiffnessPerUnitArea", T_B_KN}, {"tangentialBondStiffnessPerUnitArea", T_B_KT},
+    {"dampingNormalForceBond", T_B_DFN}, {"dampingTangentialForceBond", T_B_DFT}, {"dampingNormalTorqueBond", T_B_DTN}, {"dampingTangentialTorqueBond", T_B_DTT},
+    {"maxDistanceBond", T_B_MAXDIST}, {"maxSigmaBond", T_B_MAXSIGMA}, {"maxTauBond", T_B_MAXTAU}, {"createDistanceBond", T_B_CREATEDIST}, {"ratioTensionCompression", T_B_RATIOTC},
+    {"radiusMultiplierBondnonlinear", T_B_LAMBDA}, {"dampingNormalForceBondnonlinear", T_B_DFN}, {"dampingTangentialForceBondnonlinear", T_B_DFT},
+    {"dampingNormalTorqueBondnonlinear", T_B_DTN}, {"dampingTangentialTorqueBondnonlinear", T_B_DTT}, {"maxDistanceBondnonlinear", T_B_MAXDIST},
+    {"maxSigmaBondnonlinear", T_B_MAXSIGMA}, {"maxTauBondnonlinear", T_B_MAXTAU}, {"createDistanceBondnonlinear", T_B_CREATEDIST},
+    {"ratioTensionCompressionBondnonlinear", T_B_RATIOTC}, {"stiffnessPerUnitAreaK_fn1", T_B_K_FN1}, {"stiffnessPerUnitAreaKu_fn1", T_B_KU_FN1},
+    {"stiffnessPerUnitAreaKc_fn1", T_B_KC_FN1}, {"stiffnessPerUnitAreaK_fn2", T_B_K_FN2}, {"stiffnessPerUnitAreaKu_fn2", T_B_KU_FN2}, {"stiffnessPerUnitAreaKc_fn2", T_B_KC_FN2},
+    {"stiffnessPerUnitAreaK_ft", T_B_K_FT}, {"stiffnessPerUnitAreaK_tn", T_B_K_TN}, {"stiffnessPerUnitAreaKu_tn", T_B_KU_TN}, {"stiffnessPerUnitAreaKc_tn", T_B_KC_TN},
+    {"stiffnessPerUnitAreaK_tt", T_B_K_TT}, {"stiffnessPerUnitAreaKu_tt", T_B_KU_TT}, {"stiffnessPerUnitAreaKc_tt", T_B_KC_TT}};
+  auto it = m.find(nm);
+  return it == m.end() ? -1 : it->second;
+}
+
 extern "C" int dem_set_property(dem_engine *e, const char *name, const char *kind, const double *v, int n)
 {
   API_BEGIN
@@ -311,6 +331,7 @@ extern "C" int dem_set_property(dem_engine *e, const char *name, const char *kin
   std::string nm(name), kd(kind);
   if (kd == "scalar") {
     if (nm == "characteristicVelocity" && n == 1) e->charVel = v[0];
+    else if ((nm == "tsCreateBond" || nm == "tsCreateBondnonlinear") && n == 1) e->tsCreateBond = v[0];
     else dem_fail(e, DEM_ERR_UNSUPPORTED, "scalar property %s not on the hot path", name);
   } else if (kd == "peratomtype") {
     if (n != T) dem_fail(e, DEM_ERR_ARG, "%s: peratomtype needs %d values", name, T);
@@ -321,6 +342,7 @@ extern "C" int dem_set_property(dem_engine *e, const char *name, const char *kin
     if (n != T * T) dem_fail(e, DEM_ERR_ARG, "%s: peratomtypepair needs %d values", name, T * T);
     double(*dst)[MAXT + 1] = nm == "coefficientRestitution" ? e->cor : nm == "coefficientFriction" ? e->mu
                             : nm == "coefficientRollingFriction" ? e->rmu : nm == "coefficientRollingViscousDamping" ? e->rvisc : nullptr;
+    if (!dst) { const int b = bond_table_of(nm); if (b >= 0) dst = e->bp[b]; }
     if (!dst) dem_fail(e, DEM_ERR_UNSUPPORTED, "peratomtypepair property %s not on the hot path", name);
     for (int i = 0; i < T; i++) for (int j = 0; j < T; j++) {
       if (v[i * T + j] != v[j * T + i]) dem_fail(e, DEM_ERR_ARG, "%s: per-atomtype property matrix must be symmetric", name);
@@ -347,8 +369,11 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
     else dem_fail(e, DEM_ERR_UNSUPPORTED, "tangential model '%s' is outside the hot-path scope (history)", a[1]);
     a += 2; argc -= 2;
   }
+  m.tension = m.compression = m.shearf = m.ntorque = m.ttorque = m.damping = 1;
   if (argc > 1 && !strcmp(a[0], "cohesion")) {
-    if (strcmp(a[1], "off")) dem_fail(e, DEM_ERR_UNSUPPORTED, "cohesion model '%s' not built yet", a[1]);
+    if (!strcmp(a[1], "bond")) m.cohesion = C_BOND; else if (!strcmp(a[1], "bond/nonlinear")) m.cohesion = C_BONDNL;
+    else if (!strcmp(a[1], "off")) m.cohesion = C_OFF;
+    else dem_fail(e, DEM_ERR_UNSUPPORTED, "cohesion model '%s' is outside the hot-path scope (bond, bond/nonlinear)", a[1]);
     a += 2; argc -= 2;
   }
   if (argc > 1 && !strcmp(a[0], "rolling_friction")) {
@@ -363,7 +388,11 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
   }
   if ((m.rolling == R_EPSD || m.rolling == R_EPSD2) && !m.tangential)
     dem_fail(e, DEM_ERR_ARG, "rolling_friction epsd/epsd2 requires tangential history");
-  m.dnum = 0; m.hrec = 0; m.rec_shear = m.rec_roll = -1;
+  m.dnum = 0; m.hrec = 0; m.rec_shear = m.rec_roll = m.rec_bond = -1; m.off_bond = -1;
+  if (m.cohesion) {  // history slot order = model construction order: cohesion, tangential, rolling (contact_models.h:141-145)
+    m.nbond = m.cohesion == C_BOND ? 14 : 28; m.off_bond = 0; m.dnum += m.nbond;
+    m.rec_bond = 0; m.nbrec = (m.nbond + 1 + 3) / 4; m.hrec += m.nbrec;
+  }
   if (m.tangential) { m.off_shear = m.dnum; m.dnum += 3; m.rec_shear = m.hrec++; }
   if (m.rolling == R_EPSD || m.rolling == R_EPSD2) { m.off_roll = m.dnum; m.dnum += 3; m.rec_roll = m.hrec++; }
 }
@@ -379,6 +408,17 @@ static void parse_model_settings(dem_engine *e, int argc, const char *const *a, 
     else if (!strcmp(a[0], "limitForce")) m.limitForce = on;
     else if (!strcmp(a[0], "torsionTorque") && m.rolling != R_OFF) m.torsion = on;
     else if (!strcmp(a[0], "ktToKnUser") && m.normal == N_HOOKE) m.ktToKn = on;
+    else if (m.cohesion && !strcmp(a[0], "stressBreak")) m.stressBreak = on;
+    else if (m.cohesion && !strcmp(a[0], "tensionStress")) m.tension = on;
+    else if (m.cohesion && !strcmp(a[0], "compressionStress")) m.compression = on;
+    else if (m.cohesion && !strcmp(a[0], "shearStress")) m.shearf = on;
+    else if (m.cohesion && !strcmp(a[0], "normalTorqueStress")) m.ntorque = on;
+    else if (m.cohesion && !strcmp(a[0], "shearTorqueStress")) m.ttorque = on;
+    else if (m.cohesion && !strcmp(a[0], "createBondAlways")) m.createAlways = on;
+    else if (m.cohesion && !strcmp(a[0], "dampingBond")) m.damping = on;
+    else if (m.cohesion && !strcmp(a[0], "dampingBondSmooth")) { m.dampingSmooth = on; if (on) m.damping = 1; }
+    else if (m.cohesion == C_BOND && !strcmp(a[0], "ratioTensionCompression")) m.ratioTC = on;
+    else if (m.cohesion == C_BONDNL && !strcmp(a[0], "ratioTensionCompressionBond")) m.ratioTC = on;
     else dem_fail(e, DEM_ERR_UNSUPPORTED, "setting '%s' is unknown or outside the hot-path scope", a[0]);
     a += 2; argc -= 2;
   }
@@ -403,6 +443,7 @@ extern "C" int dem_add_wall_primitive(dem_engine *e, const char *id, int argc, c
   for (auto &w : e->walls) if (w.id == id) dem_fail(e, DEM_ERR_ARG, "fix id %s already in use", id);
   WallHost W; W.id = id; memset(&W.p, 0, sizeof W.p);
   parse_model_select(e, argc, argv, W.p.m);
+  if (W.p.m.cohesion) dem_fail(e, DEM_ERR_UNSUPPORTED, "bond models on walls are outside the hot-path scope");
   if (argc < 4 || strcmp(argv[0], "primitive")) {
     if (argc > 0 && !strcmp(argv[0], "mesh")) dem_fail(e, DEM_ERR_UNSUPPORTED, "mesh walls go through dem_add_wall_mesh");
     dem_fail(e, DEM_ERR_ARG, "Need to use define style 'mesh' or 'primitive'");
@@ -482,6 +523,7 @@ extern "C" int dem_add_wall_mesh(dem_engine *e, const char *id, int argc, const 
   if (e->nranks > 1) dem_fail(e, DEM_ERR_UNSUPPORTED, "mesh walls on more than one GPU are not built yet");
   dem_engine::MeshWall W; W.id = id;
   parse_model_select(e, argc, argv, W.m);
+  if (W.m.cohesion) dem_fail(e, DEM_ERR_UNSUPPORTED, "bond models on walls are outside the hot-path scope");
   if (argc < 4 || strcmp(argv[0], "mesh")) dem_fail(e, DEM_ERR_ARG, "Need to use define style 'mesh' or 'primitive'");
   if (strcmp(argv[1], "n_meshes")) dem_fail(e, DEM_ERR_ARG, "have to define 'n_meshes' before 'meshes'");
   const int nm = atoi(argv[2]);
@@ -750,6 +792,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     if (errbits & 2) dem_fail(e, DEM_ERR_ARG, "Invalid radius or density in particle data");
     if (errbits & 4) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
     double rmaxd; memcpy(&rmaxd, &hc[0], 8);
+    { double rm = 1e300; for (long i = 0; i < n; i++) rm = std::min(rm, radius[i]); e->rmin = rm; }
     e->nlocal = n; e->nghost = 0; e->rmax = rmaxd;
     e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0; e->mesh_ready = 0;
     e->ls[0].valid = e->ls[1].valid = 0;
@@ -766,6 +809,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     const double r = radius[i];
     const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * density[i];  // atom_vec_sphere.cpp:1078
     rmax = std::max(rmax, r);  // global maximum: every rank sees the full set
+    e->rmin = (i == 0) ? r : std::min(e->rmin, r);
     if (e->nranks > 1) {  // ownership test on the wrapped position (Domain::pbc + sub-box, like read_data)
       bool mine = true;
       for (int d = 0; d < 3 && mine; d++) {
@@ -837,7 +881,39 @@ static void derive_tables(dem_engine *E)
     at(T_MU) = E->mu[i][j]; at(T_RMU) = E->rmu[i][j]; at(T_RVISC) = E->rvisc[i][j];
     if (hertz || hooke) { at(T_SQ2Y) = sqrt(2. * at(T_YEFF)); at(T_SQ8G) = sqrt(8. * at(T_GEFF)); at(T_INV8G) = 1. / (8. * at(T_GEFF)); }
   }
-  for (int w = 0; w < T_COUNT; w++) E->t1[w] = t[((size_t)w * n1 + 1) * n1 + 1];
+  E->cdf = 1.0;
+  if (E->have_pair && E->pm.cohesion) {
+    const ModelP &m = E->pm;
+    const bool nl = m.cohesion == C_BONDNL;
+    const char *sfx = nl ? "nonlinear" : "";
+    auto needb = [&](const std::string &base) { const std::string nm = base + sfx; need(nm.c_str()); };
+    needb("radiusMultiplierBond"); needb("createDistanceBond");
+    if (!m.createAlways) needb("tsCreateBond");
+    if (m.damping) { needb("dampingNormalForceBond"); needb("dampingTangentialForceBond"); needb("dampingNormalTorqueBond"); needb("dampingTangentialTorqueBond"); }
+    if (!m.stressBreak) needb("maxDistanceBond"); else { needb("maxSigmaBond"); needb("maxTauBond"); }
+    if (!nl) { need("normalBondStiffnessPerUnitArea"); need("tangentialBondStiffnessPerUnitArea"); }
+    else for (const char *k : {"K_fn1", "Ku_fn1", "Kc_fn1", "K_fn2", "Ku_fn2", "Kc_fn2", "K_ft", "K_tn", "Ku_tn", "Kc_tn", "K_tt", "Ku_tt", "Kc_tt"}) need((std::string("stiffnessPerUnitArea") + k).c_str());
+    for (int w = T_B_LAMBDA; w < T_COUNT; w++) for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) t[((size_t)w * n1 + i) * n1 + j] = E->bp[w][i][j];
+    // neighbor->register_contact_dist_factor: cohesion_model_bond.h:391-475, cohesion_model_bond_nonlinear.h:336-382
+    if (!(E->rmin > 0.)) dem_fail(E, DEM_ERR_STATE, "Bond settings: The minimum radius can't be <= 0!");
+    double cdf_all = 1.;
+    for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) {
+      double one;
+      if (!m.stressBreak) one = 1.1 * 0.5 * E->bp[T_B_MAXDIST][i][j] / E->rmin;
+      else {
+        double stress = E->bp[T_B_MAXSIGMA][i][j];
+        if (m.ratioTC) stress = fmax(stress, stress * E->bp[T_B_RATIOTC][i][j]);
+        const double kk = nl ? E->bp[T_B_K_FN2][i][j] : E->bp[T_B_KN][i][j];
+        if (kk <= 1e-15) dem_fail(E, DEM_ERR_ARG, "Bond settings: In case of stress breakage, the normal bond stiffness can't be <= 0!");
+        one = nl ? 0.5 * 1.1 * E->bp[T_B_CREATEDIST][i][j] / E->rmin + 0.5 * 1.1 * stress / (kk * E->rmin)
+                 : 0.5 * (1.1 * E->bp[T_B_CREATEDIST][i][j] / E->rmin + 1.1 * stress / (kk * E->rmin));
+      }
+      cdf_all = one > cdf_all ? one : cdf_all;
+    }
+    if (cdf_all > 10.) dem_fail(E, DEM_ERR_ARG, "Maximum bond distance exceeding 10 x particle diameter, please reduce maxDistanceBond or maxSigmaBond/maxTauBond");
+    E->cdf = cdf_all;
+  }
+  for (int w = 0; w < T_B_LAMBDA; w++) E->t1[w] = t[((size_t)w * n1 + 1) * n1 + 1];
   E->tab.ensure(E, t.size());
   CK(cudaMemcpyAsync(E->tab.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
   if (!E->walls.empty()) {
@@ -1157,6 +1233,7 @@ static void rebuild(dem_engine *E)
     P.have_old = (Lold.valid && dnum && Lold.dnum == dnum) ? 1 : 0; P.cap_old = Lold.cap; P.dnum_old = Lold.dnum;
     P.perm = E->perm.p; P.nbr_old = Lold.nbr.p; P.numneigh_old = Lold.numneigh.p; P.ptag_old = Lold.ptag.p; P.hist_old = Lold.hist.p;
     P.overflow = E->overflow.p;
+    P.coh_nbond = (E->have_pair && E->pm.cohesion) ? E->pm.nbond : 0; P.coh_rec = E->pm.rec_bond;
     k_build_list<<<GRID(n, 128), 128, 0, st>>>(P);
     E->launches++;
     int ov[2] = {0, 0};
@@ -1212,7 +1289,8 @@ static StepP step_params(dem_engine *E, int mode)
   P.xh = E->xh.p; P.nbr = L.nbr.p; P.numneigh = L.numneigh.p; P.hist = L.hist.p; P.hslots = L.hslots;
   P.whist = E->whist.p; P.f = E->f.p; P.tq = E->tq.p; P.walls = E->dwalls.p; P.nwalls = (int)E->walls.size(); P.nwc = E->nwc; P.nwcap = E->nwcap; P.wlist = E->wlist.p; P.fw = E->fw.p;
   P.pm = E->pm; P.tab = E->tab.p; P.nt1 = E->ntypes + 1;
-  for (int w = 0; w < T_COUNT; w++) P.t1[w] = E->t1[w];
+  for (int w = 0; w < T_B_LAMBDA; w++) P.t1[w] = E->t1[w];
+  P.ntimestep = E->ntimestep; P.tsCreateBond = (long)(int)E->tsCreateBond;
   P.dt = E->dt; P.dtv = E->dt; P.dtf = 0.5 * E->dt * E->ftm2v; P.dtfrot = P.dtf / 0.4;  // fix_nve.cpp:86, fix_nve_sphere.cpp:69,150
   P.nktv2p = E->nktv2p; P.charVel = E->charVel; P.cdf = E->cdf; P.cdfsq = E->cdf * E->cdf;
   P.trigsq = 0.25 * E->skin * E->skin;  // neighbor.cpp:298
@@ -1241,6 +1319,21 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
   if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
+  if (E->have_pair && E->pm.cohesion) {
+    const unsigned g = GRID(P.nlocal, 128);
+#define BONDK(N, R) { if (E->pm.cohesion == C_BOND) k_step_bond<N, R, C_BOND><<<g, 128, 0, E->stream>>>(P); else k_step_bond<N, R, C_BONDNL><<<g, 128, 0, E->stream>>>(P); }
+    switch (key) {
+      case N_HERTZ * 4 + R_OFF: BONDK(N_HERTZ, R_OFF) break;
+      case N_HERTZ * 4 + R_CDT: BONDK(N_HERTZ, R_CDT) break;
+      case N_HERTZ * 4 + R_EPSD: BONDK(N_HERTZ, R_EPSD) break;
+      case N_HERTZ * 4 + R_EPSD2: BONDK(N_HERTZ, R_EPSD2) break;
+      case N_HOOKE * 4 + R_OFF: BONDK(N_HOOKE, R_OFF) break;
+      case N_HOOKE * 4 + R_CDT: BONDK(N_HOOKE, R_CDT) break;
+      case N_HOOKE * 4 + R_EPSD: BONDK(N_HOOKE, R_EPSD) break;
+      default: BONDK(N_HOOKE, R_EPSD2) break;
+    }
+#undef BONDK
+  } else
   switch (key) {
     case N_HERTZ * 4 + R_OFF: launch_step_t<N_HERTZ, R_OFF>(E, P); break;
     case N_HERTZ * 4 + R_CDT: launch_step_t<N_HERTZ, R_CDT>(E, P); break;
@@ -1429,7 +1522,7 @@ extern "C" int dem_download(dem_engine *e, const char *field, void *out, long co
   API_END
 }
 
-struct PairRow { int lo, hi, flag; long src; };
+struct PairRow { int lo, hi, flag; long src; int has; };
 static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector<double4> &hist, int &dnum)
 {
   ListSet &L = E->ls[E->lcur];
@@ -1450,11 +1543,19 @@ static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector
   }
   hist.assign((size_t)L.hslots * dnum * L.cap, make_double4(0., 0., 0., 0.));
   if (kmax && dnum) CK(cudaMemcpy(hist.data(), L.hist.p, hist.size() * sizeof(double4), cudaMemcpyDeviceToHost));
+  const ModelP &M = E->pm;
+  auto comp = [](const double4 &v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; };
   for (long i = 0; i < n; i++) for (int k = 0; k < nn[i]; k++) {
     const unsigned w = nbr[(size_t)k * L.cap + i];
     const int tj = ptag[(size_t)k * L.cap + i];
     const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-    if (tags[i] < tj) rows.push_back(PairRow{tags[i], tj, slot >= 0 ? 1 : 0, (long)std::max(slot, 0) * L.cap + i});
+    int flag = slot >= 0 ? 1 : 0;
+    if (flag && E->have_pair && M.cohesion) {  // reference contact_flags != 0 <=> bonded or sticky (see k_step_bond)
+      const double b0 = hist[(size_t)(slot * dnum + M.rec_bond) * L.cap + i].x;
+      const double S = comp(hist[(size_t)(slot * dnum + M.rec_bond + M.nbond / 4) * L.cap + i], M.nbond % 4);
+      flag = (b0 != 0.0 || S != 0.0) ? 1 : 0;
+    }
+    if (tags[i] < tj) rows.push_back(PairRow{tags[i], tj, flag, (long)std::max(slot, 0) * L.cap + i, slot >= 0 ? 1 : 0});
   }
   std::sort(rows.begin(), rows.end(), [](const PairRow &a, const PairRow &b) { return a.lo != b.lo ? a.lo < b.lo : a.hi < b.hi; });
 }
@@ -1485,7 +1586,11 @@ extern "C" int dem_download_pairs(dem_engine *e, int *lo, int *hi, int *flag, do
     if (hist) {
       const long k = rows[r].src / L.cap, i = rows[r].src % L.cap;  // k = history slot
       for (int d = 0; d < dn; d++) hist[r * dn + d] = 0.0;
-      if (rows[r].flag) {
+      if (rows[r].has) {
+        if (M.cohesion) for (int d = 0; d < M.nbond; d++) {
+          const double4 v = h[(size_t)(k * nrec + M.rec_bond + d / 4) * L.cap + i];
+          hist[r * dn + M.off_bond + d] = (d % 4 == 0) ? v.x : (d % 4 == 1) ? v.y : (d % 4 == 2) ? v.z : v.w;
+        }
         if (M.rec_shear >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_shear) * L.cap + i]; hist[r * dn + M.off_shear] = v.x; hist[r * dn + M.off_shear + 1] = v.y; hist[r * dn + M.off_shear + 2] = v.z; }
         if (M.rec_roll >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_roll) * L.cap + i]; hist[r * dn + M.off_roll] = v.x; hist[r * dn + M.off_roll + 1] = v.y; hist[r * dn + M.off_roll + 2] = v.z; }
       }

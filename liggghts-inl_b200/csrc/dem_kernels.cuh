@@ -203,6 +203,49 @@ __device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned
   }
 }
 
+// owner epilogue of a step: gravity, primitive/mesh wall force of the pre-pass, freeze, (optional) force output,
+// final_integrate(n) + initial_integrate(n+1), rebuild trigger.  fix_gravity.cpp:331-339, fix_freeze.cpp:132-144,
+// fix_nve_sphere.cpp:134-244, neighbor.cpp:1425-1466
+__device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const double4 &xi, const double4 &vi, const double4 &wi, double *F, double *T)
+{
+  bool trig = false;
+  const int imask = rec_mask(wi.w);
+  if (P.have_g && (imask & 1)) { F[0] += vi.w * P.g[0]; F[1] += vi.w * P.g[1]; F[2] += vi.w * P.g[2]; }
+  if (P.nwc) {  // wall contacts were evaluated by the k_walls / k_mesh_step pre-passes
+    const unsigned widx = (unsigned)(__double_as_longlong(P.xh[i].w) >> 32);
+    if (widx) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) { F[d] += P.fw[(size_t)d * P.nwcap + widx - 1]; T[d] += P.fw[(size_t)(3 + d) * P.nwcap + widx - 1]; }
+    }
+  }
+  if (imask & P.freezebit) { F[0] = F[1] = F[2] = 0.0; T[0] = T[1] = T[2] = 0.0; }
+  if (P.mode != MODE_STEP) {  // forces are only materialised when somebody will read them
+    P.f[i] = F[0]; P.f[P.cap + i] = F[1]; P.f[2 * (size_t)P.cap + i] = F[2];
+    P.tq[i] = T[0]; P.tq[P.cap + i] = T[1]; P.tq[2 * (size_t)P.cap + i] = T[2];
+  }
+  if (P.mode != MODE_SETUP) {
+    double4 xo = xi, vo = vi, wo = wi;
+    if (imask & P.integbit) {
+      const double dtfm = P.dtf / vi.w;
+      const double dtir = P.dtfrot / (xi.w * xi.w * vi.w);
+      // final_integrate of this step
+      vo.x += dtfm * F[0]; vo.y += dtfm * F[1]; vo.z += dtfm * F[2];
+      wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
+      if (P.mode == MODE_STEP) {  // initial_integrate of the next step
+        vo.x += dtfm * F[0]; vo.y += dtfm * F[1]; vo.z += dtfm * F[2];
+        xo.x += P.dtv * vo.x; xo.y += P.dtv * vo.y; xo.z += P.dtv * vo.z;
+        wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
+      }
+    }
+    st4(P.xr_o + i, xo); st4(P.vm_o + i, vo); st4(P.wt_o + i, wo);
+    if (P.mode == MODE_STEP) {
+      const double4 xh = P.xh[i];
+      trig = sq3_rn(xo.x - xh.x, xo.y - xh.y, xo.z - xh.z) > P.trigsq;
+    }
+  }
+  return trig;
+}
+
 // ----------------------------------------------------------------------------------------
 // THE hot kernel: one launch == one timestep of the owned particles of this GPU.
 //   verlet.cpp:264-391 (order of operations), pair_gran_base.h:257-496 (pair loop),
@@ -329,43 +372,127 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   }
   // (3) owner epilogue
   if (active) {
-    const double4 xi = s_rec[0][tid], vi = s_rec[1][tid], wi = s_rec[2][tid];
-    const int imask = rec_mask(wi.w);
     if (P.have_pair) { const int nh = s_nh[tid]; if (nh != nh0) P.numneigh[i] = nn | (nh << 16); }
-    if (P.have_g && (imask & 1)) { F[0] += vi.w * P.g[0]; F[1] += vi.w * P.g[1]; F[2] += vi.w * P.g[2]; }
-    if (P.nwc) {  // primitive-wall contacts were evaluated by the k_walls pre-pass
-      const unsigned widx = (unsigned)(__double_as_longlong(P.xh[i].w) >> 32);
-      if (widx) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) { F[d] += P.fw[(size_t)d * P.nwcap + widx - 1]; T[d] += P.fw[(size_t)(3 + d) * P.nwcap + widx - 1]; }
-      }
-    }
-    if (imask & P.freezebit) { F[0] = F[1] = F[2] = 0.0; T[0] = T[1] = T[2] = 0.0; }
+    trig = step_epilogue(P, i, s_rec[0][tid], s_rec[1][tid], s_rec[2][tid], F, T);
+  }
+  if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
+}
 
-    if (P.mode != MODE_STEP) {  // forces are only materialised when somebody will read them
-      P.f[i] = F[0]; P.f[P.cap + i] = F[1]; P.f[2 * (size_t)P.cap + i] = F[2];
-      P.tq[i] = T[0]; P.tq[P.cap + i] = T[1]; P.tq[2 * (size_t)P.cap + i] = T[2];
-    }
-    if (P.mode != MODE_SETUP) {
-      double4 xo = xi, vo = vi, wo = wi;
-      if (imask & P.integbit) {
-        const double dtfm = P.dtf / vi.w;
-        const double dtir = P.dtfrot / (xi.w * xi.w * vi.w);
-        // final_integrate of this step
-        vo.x += dtfm * F[0]; vo.y += dtfm * F[1]; vo.z += dtfm * F[2];
-        wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
-        if (P.mode == MODE_STEP) {  // initial_integrate of the next step
-          vo.x += dtfm * F[0]; vo.y += dtfm * F[1]; vo.z += dtfm * F[2];
-          xo.x += P.dtv * vo.x; xo.y += P.dtv * vo.y; xo.z += P.dtv * vo.z;
-          wo.x += dtir * T[0]; wo.y += dtir * T[1]; wo.z += dtir * T[2];
+
+// ----------------------------------------------------------------------------------------
+// Step kernel of the bonded-sphere decks (pair_style gran ... cohesion bond | bond/nonlinear).  Same contract as k_step;
+// differences: (a) the contact-distance factor is > 1, so entries inside the band (radsum*cdf) are evaluated although the
+// spheres do not touch: bonded pairs pull across the gap, un-bonded ones are bond candidates on the creation step;
+// (b) every pair is evaluated in the canonical orientation (lower tag = first body) by both owners -- see bond_eval;
+// (c) a history row is nbrec + 1 (+1) records; the double after the bond values is the row's sticky flag S: the reference's
+// contact_flags stay != 0 after the first touch (CONTACT_NORMAL_MODEL is never cleared) and are reset to 1 for rows kept by
+// a rebuild (neigh_gran.cpp:596-612), while CONTACT_COHESION_MODEL follows the bond; "flag != 0" == (S != 0 || bondFlag != 0).
+// Chain order per contact_models.h:228-253: surface, normal, cohesion, tangential, rolling.
+template <int NORMAL, int ROLLING, int COH>
+__global__ void __launch_bounds__(128) k_step_bond(const StepP P)
+{
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool trig = false;
+  if (i < P.nlocal) {
+    const ModelP &M = P.pm;
+    const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
+    const int itype = rec_type(wi.w), imask = rec_mask(wi.w);
+    const bool su = (P.mode != MODE_SETUP);
+    const bool create_step = su && (M.createAlways || P.ntimestep == P.tsCreateBond);
+    double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
+    const int nnw = P.numneigh[i];
+    const int nn = nnw & 0xffff;
+    int nh = (nnw >> 16) & 0xffff;
+    const int nh0 = nh;
+    for (int k = 0; k < nn; k++) {
+      unsigned w = P.nbr[(size_t)k * P.lcap + i];
+      const int j = (int)(w & NBR_IDX);
+      const double4 xj = ldg4(P.xr + j);
+      const double dxm = xi.x - xj.x, dym = xi.y - xj.y, dzm = xi.z - xj.z;  // me - partner
+      const double rsq = sq3_rn(dxm, dym, dzm);
+      const double radsum = xi.w + xj.w;
+      const bool touch = rsq < __dmul_rn(radsum, radsum);
+      const bool inband = touch || rsq < P.cdfsq * radsum * radsum;
+      int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+      if (!inband || (!touch && slot < 0 && !create_step)) continue;
+      const double4 vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
+      const bool jfirst = (w & NBR_JFIRST) != 0;
+      // canonical operands: a = first body (lower tag), b = second
+      const double4 &xa = jfirst ? xj : xi, &xb = jfirst ? xi : xj, &va = jfirst ? vj : vi, &vb = jfirst ? vi : vj, &wa = jfirst ? wj : wi, &wb = jfirst ? wi : wj;
+      const double delta[3] = {xa.x - xb.x, xa.y - xb.y, xa.z - xb.z};
+      const int ta = rec_type(wa.w), tb = rec_type(wb.w);
+      // history row -> registers
+      double H[28], S = 0.0, h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
+#pragma unroll
+      for (int d = 0; d < 28; d++) H[d] = 0.0;
+      const bool had = slot >= 0;
+      if (had) {
+        const double4 *hp = P.hist + (size_t)(slot * M.hrec) * P.lcap + i;
+#pragma unroll
+        for (int r = 0; r < (COH == C_BOND ? 4 : 8); r++) {
+          const double4 v = hp[(size_t)(M.rec_bond + r) * P.lcap];
+          if (4 * r < M.nbond) H[4 * r] = v.x; else if (4 * r == M.nbond) S = v.x;
+          if (4 * r + 1 < M.nbond) H[4 * r + 1] = v.y; else if (4 * r + 1 == M.nbond) S = v.y;
+          if (4 * r + 2 < M.nbond) H[4 * r + 2] = v.z; else if (4 * r + 2 == M.nbond) S = v.z;
+          if (4 * r + 3 < M.nbond) H[4 * r + 3] = v.w; else if (4 * r + 3 == M.nbond) S = v.w;
         }
+        if (M.tangential) { const double4 v = hp[(size_t)M.rec_shear * P.lcap]; h[0] = v.x; h[1] = v.y; h[2] = v.z; }
+        if (HAS_ROLL_HIST) { const double4 v = hp[(size_t)M.rec_roll * P.lcap]; g[0] = v.x; g[1] = v.y; g[2] = v.z; }
       }
-      st4(P.xr_o + i, xo); st4(P.vm_o + i, vo); st4(P.wt_o + i, wo);
-      if (P.mode == MODE_STEP) {
-        const double4 xh = P.xh[i];
-        trig = sq3_rn(xo.x - xh.x, xo.y - xh.y, xo.z - xh.z) > P.trigsq;
+      const double S0 = S;
+      // cohesion model first (it only needs kinematics + its own history); force on the first body
+      double Fb[3] = {0., 0., 0.}, Tbi[3] = {0., 0., 0.}, Tbj[3] = {0., 0., 0.};
+      const double xav[3] = {xa.x, xa.y, xa.z}, vav[3] = {va.x, va.y, va.z}, vbv[3] = {vb.x, vb.y, vb.z}, wav[3] = {wa.x, wa.y, wa.z}, wbv[3] = {wb.x, wb.y, wb.z};
+      const bool bonded = bond_eval<COH>(P, M, delta, rsq, xa.w, xb.w, xav, vav, vbv, wav, wbv, ta, tb, su, H, Fb, Tbi, Tbj);
+      double Fa[3] = {0., 0., 0.}, Ta[3] = {0., 0., 0.}, Tb[3] = {0., 0., 0.};
+      if (touch) {
+        Contact c;
+        c.dx = delta[0]; c.dy = delta[1]; c.dz = delta[2];
+        c.r = sqrt(rsq); c.rinv = 1.0 / c.r;
+        c.radi = xa.w; c.radj = xb.w; c.radsum = xa.w + xb.w; c.deltan_in = 0.0;
+        c.mi = va.w; c.mj = vb.w;
+        double meff = va.w * vb.w / (va.w + vb.w);
+        if (rec_mask(wa.w) & P.freezebit) meff = vb.w;
+        if (rec_mask(wb.w) & P.freezebit) meff = va.w;
+        c.meff = meff;
+        for (int d = 0; d < 3; d++) { c.vi[d] = vav[d]; c.vj[d] = vbv[d]; c.wi[d] = wav[d]; c.wj[d] = wbv[d]; }
+        c.itype = ta; c.jtype = tb;
+        ContactOut o;
+        contact_chain<NORMAL, ROLLING, false>(P, M, c, h, g, su, o, COH == C_BONDNL && bonded);
+        for (int d = 0; d < 3; d++) { Fa[d] = o.F[d] + Fb[d]; Ta[d] = o.Ti[d] + Tbi[d]; Tb[d] = o.Tj[d] + Tbj[d]; }
+        S = 1.0;
+      } else {  // surfacesClose: tangential / rolling history zeroed (tangential_model_history.h:428-440, rolling_model_epsd.h:225-235)
+        for (int d = 0; d < 3; d++) { Fa[d] = Fb[d]; Ta[d] = Tbi[d]; Tb[d] = Tbj[d]; h[d] = 0.0; g[d] = 0.0; }
+      }
+      if (jfirst) { for (int d = 0; d < 3; d++) { F[d] -= Fa[d]; T[d] += Tb[d]; } }
+      else { for (int d = 0; d < 3; d++) { F[d] += Fa[d]; T[d] += Ta[d]; } }
+      // write the row back: a row is created by the first touch or by a bond creation
+      const bool want = had || touch || H[0] != 0.0;
+      if (!want) continue;
+      if (!had) {
+        if (nh < P.hslots) { slot = nh++; P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); }
+        else { ((volatile int *)P.flag)[1] = 1; continue; }
+      }
+      (void)S0;
+      {  // rows are always written back: surfacesClose zeroes and the nonlinear trackers move even in the setup step
+        double4 *hp = P.hist + (size_t)(slot * M.hrec) * P.lcap + i;
+#pragma unroll
+        for (int r = 0; r < (COH == C_BOND ? 4 : 8); r++) {
+          double4 v;
+          v.x = 4 * r < M.nbond ? H[4 * r] : (4 * r == M.nbond ? S : 0.0);
+          v.y = 4 * r + 1 < M.nbond ? H[4 * r + 1] : (4 * r + 1 == M.nbond ? S : 0.0);
+          v.z = 4 * r + 2 < M.nbond ? H[4 * r + 2] : (4 * r + 2 == M.nbond ? S : 0.0);
+          v.w = 4 * r + 3 < M.nbond ? H[4 * r + 3] : (4 * r + 3 == M.nbond ? S : 0.0);
+          st4(hp + (size_t)(M.rec_bond + r) * P.lcap, v);
+        }
+        if (M.tangential) st4(hp + (size_t)M.rec_shear * P.lcap, make_double4(h[0], h[1], h[2], 0.));
+        if (HAS_ROLL_HIST) st4(hp + (size_t)M.rec_roll * P.lcap, make_double4(g[0], g[1], g[2], 0.));
       }
     }
+    if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
+    (void)itype; (void)imask;
+    trig = step_epilogue(P, i, xi, vi, wi, F, T);
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }
@@ -641,6 +768,7 @@ struct BuildP {
   unsigned *nbr; int *numneigh; int *ptag; double4 *hist;
   // previous list (rows addressed through perm: new i <- old perm[i])
   int have_old, cap_old, dnum_old;
+  int coh_nbond, coh_rec;  // bond models: a row is kept iff its bondFlag or its sticky flag is set (see k_step_bond)
   const int *perm; const unsigned *nbr_old; const int *numneigh_old; const int *ptag_old; const double4 *hist_old;
   int *overflow;
 };
@@ -679,10 +807,19 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
                     const unsigned wo = B.nbr_old[(size_t)m * B.cap_old + oi];
                     if ((wo & NBR_HIST) && B.ptag_old[(size_t)m * B.cap_old + oi] == tagj) {
                       const int so = (int)((wo & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+                      const int srec = B.coh_rec + B.coh_nbond / 4, scomp = B.coh_nbond % 4;
+                      if (B.coh_nbond) {  // reference: contact_flags == 0 rows are not partners (fix_contact_history.cpp:351)
+                        const double4 b0 = B.hist_old[(size_t)(so * B.dnum + B.coh_rec) * B.cap_old + oi], sr = B.hist_old[(size_t)(so * B.dnum + srec) * B.cap_old + oi];
+                        const double S = scomp == 0 ? sr.x : scomp == 1 ? sr.y : scomp == 2 ? sr.z : sr.w;
+                        if (b0.x == 0.0 && S == 0.0) break;
+                      }
                       if (nh < B.hslots) {
                         w |= (unsigned)(nh + 1) << NBR_SLOT_SHIFT;
-                        for (int d = 0; d < B.dnum; d++)  // dnum = 32-byte records per contact here
-                          B.hist[(size_t)(nh * B.dnum + d) * B.cap + i] = B.hist_old[(size_t)(so * B.dnum + d) * B.cap_old + oi];
+                        for (int d = 0; d < B.dnum; d++) {  // dnum = 32-byte records per contact here
+                          double4 v = B.hist_old[(size_t)(so * B.dnum + d) * B.cap_old + oi];
+                          if (B.coh_nbond && d == srec) { if (scomp == 0) v.x = 1.0; else if (scomp == 1) v.y = 1.0; else if (scomp == 2) v.z = 1.0; else v.w = 1.0; }  // kept rows restart with flag 1
+                          B.hist[(size_t)(nh * B.dnum + d) * B.cap + i] = v;
+                        }
                       }
                       nh++;
                       break;

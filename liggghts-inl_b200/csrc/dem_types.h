@@ -7,7 +7,12 @@ namespace dem {
 enum { N_OFF = 0, N_HERTZ = 1, N_HOOKE = 2 };
 enum { R_OFF = 0, R_CDT = 1, R_EPSD = 2, R_EPSD2 = 3 };
 // per-type-pair tables, each (ntypes+1)^2 doubles, concatenated in this order
-enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_SQ2Y, T_SQ8G, T_INV8G, T_COUNT };
+enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_SQ2Y, T_SQ8G, T_INV8G,
+       // bond models (cohesion_model_bond.h:76-178, cohesion_model_bond_nonlinear.h:77-147)
+       T_B_LAMBDA, T_B_KN, T_B_KT, T_B_DFN, T_B_DFT, T_B_DTN, T_B_DTT, T_B_MAXDIST, T_B_MAXSIGMA, T_B_MAXTAU, T_B_CREATEDIST, T_B_RATIOTC,
+       T_B_K_FN1, T_B_KU_FN1, T_B_KC_FN1, T_B_K_FN2, T_B_KU_FN2, T_B_KC_FN2, T_B_K_FT, T_B_K_TN, T_B_KU_TN, T_B_KC_TN, T_B_K_TT, T_B_KU_TT, T_B_KC_TT,
+       T_COUNT };
+enum { C_OFF = 0, C_BOND = 1, C_BONDNL = 2 };
 
 #define DEM_MAXW 16  // primitive walls per engine (candidate + valid bits share one 32-bit word)
 
@@ -27,6 +32,10 @@ struct ModelP {
   int tdamp, limitForce, torsion, ktToKn;
   int dnum, off_shear, off_roll;  // reference layout of a history row (fix_contact_history)
   int hrec, rec_shear, rec_roll;   // device layout: hrec 32-byte records per contact, one per sub-model
+  // cohesion bond | bond/nonlinear: nbond history doubles (14 | 28) in records rec_bond.. , followed by one "sticky flag"
+  // double (the reference's contact_flags != 0 after a touch or a kept rebuild, see dem_kernels.cuh k_step_bond)
+  int cohesion, off_bond, nbond, rec_bond, nbrec;
+  int stressBreak, tension, compression, shearf, ntorque, ttorque, createAlways, damping, dampingSmooth, ratioTC;
 };
 
 struct WallP {
@@ -62,7 +71,8 @@ struct StepP {
   ModelP pm;
   const double *tab;
   int nt1;  // ntypes+1
-  double t1[T_COUNT];  // the tables' single entry when ntypes == 1
+  double t1[T_B_LAMBDA];  // the contact tables' single entry when ntypes == 1
+  long ntimestep, tsCreateBond;  // bond creation step (update->ntimestep == tsCreateBond)
   double dt, dtv, dtf, dtfrot, nktv2p, charVel, cdf, cdfsq, trigsq, cutneighmax;
   double g[3];
   int have_g, have_pair, freezebit, integbit;

@@ -87,6 +87,31 @@ def test_mesh_walls_match_oracle(kind, kw):
     got.close(); ref.close()
 
 
+@pytest.mark.parametrize("kw", [
+    dict(n3=(9, 9, 8), poly=True, model="model hertz tangential history", bond=dict(kind="bond", maxdist=2.1 * 0.003)),
+    dict(n3=(8, 8, 8), model="model hertz tangential history rolling_friction epsd2", settings="stressBreak on", periodic=(1, 1, 0),
+         bond=dict(kind="bond", sigma=4e4, tau=2e4)),
+    dict(n3=(8, 8, 7), poly=True, model="model hooke tangential history rolling_friction cdt", bond=dict(kind="bond/nonlinear")),
+])
+def test_bonded_spheres_match_oracle(kw):
+    """~600 bonded spheres: bonds form at step 2, some break; pair set, flags, bond bookkeeping bit-exact, forces to tolerance"""
+    c = cases.case_box(name="bonded", seed=5, **kw)
+    rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
+    got = cases.apply(c, gpu_engine())
+    ref = cases.apply(c, parity.oracle_engine())
+    done = 0
+    for cp in (0, 1, 2, 3, 10, 30, 60):
+        for eng in (got, ref):
+            eng.setup(); eng.run(cp - done)
+        done = cp
+        sg, sr = cases.snapshot(got, c), cases.snapshot(ref, c)
+        parity.compare_snapshot(sg, sr, rmass, tol=parity.tol_for(c, cp, gpu=True), label="bonded@%d" % cp)
+        assert np.array_equal(sg["pair_hist"][:, 0] > 0, sr["pair_hist"][:, 0] > 0), "bond flags differ at %d" % cp
+        assert got.stats().nbuilds == ref.stats().nbuilds
+    assert (sg["pair_hist"][:, 0] > 0).sum() > 50, "no bonds were exercised"
+    got.close(); ref.close()
+
+
 def test_engine_is_deterministic():
     c = cases.case_box(n3=(8, 8, 8), poly=True, name="det", seed=3)
     snaps = []
