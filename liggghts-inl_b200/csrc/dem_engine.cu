@@ -148,6 +148,9 @@ struct dem_engine {
   int mcur = 0, mslots = 8, mcand = 16, mhrec = 0, mesh_ready = 0, grid_ready = 0, any_moving = 0;
   double mgorg[3] = {0, 0, 0}, mginv[3] = {1, 1, 1}; int mgnc[3] = {1, 1, 1};
   long next_reneighbor = -1;
+  cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
+  int fslot = 0;                            // slot the next step writes
+  const int *gate = nullptr; int gate_mask = 0;  // gate of the step being launched (nullptr: not speculative)
   // state
   int uploaded = 0, setup_done = 0, forces_valid = 0;
   long ntimestep = 0, nbuilds = 0, launches = 0;
@@ -216,8 +219,8 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
       NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
     }
     CK(cudaHostAlloc((void **)&e->hcnt, 64 * sizeof(int), cudaHostAllocDefault));
-    CK(cudaHostAlloc((void **)&e->hflag, 4 * sizeof(int), cudaHostAllocMapped));
-    e->hflag[0] = e->hflag[1] = 0;
+    CK(cudaHostAlloc((void **)&e->hflag, 8 * sizeof(int), cudaHostAllocDefault));
+    for (int k = 0; k < 8; k++) e->hflag[k] = 0;
     e->pm.tdamp = 1;
   } catch (const DemFail &f) { return f.code; }
   return DEM_OK;
@@ -249,6 +252,7 @@ extern "C" void dem_destroy(dem_engine *e)
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   if (e->hflag) cudaFreeHost(e->hflag);
+  for (int k = 0; k < 2; k++) if (e->fev[k]) cudaEventDestroy(e->fev[k]);
   if (e->hcnt) cudaFreeHost(e->hcnt);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   delete e;
@@ -649,7 +653,6 @@ static void mesh_rebuild(dem_engine *E, int n, bool permuted)
   MeshP M = mesh_params(E);
   mesh_launch_hold(M, st);
   E->launches++;
-  E->hflag[2] = 0;
 }
 
 extern "C" int dem_set_gravity(dem_engine *e, double mag, const double dir[3])
@@ -999,39 +1002,47 @@ static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &s
 // per-step ghost refresh == CommBrick::forward_comm (comm_brick.cpp:563-645): one pack kernel per swap; periodic
 // images on the same rank are written in place, remote ghosts travel as three NCCL send/recv pairs that land
 // directly in the ghost region of the record arrays.  Swaps run in order so that edge/corner ghosts propagate.
-static void do_swap(dem_engine *E, dem_engine::Swap &W)
-{
+static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw)
+{  // nsw = 1, or the two (independent) swaps of one decomposed dimension exchanged in ONE NCCL group
   cudaStream_t st = E->stream;
   const int c = E->cur;
-  SwapP S;
-  S.n = W.nsend; S.list = W.list.p; S.dim = W.dim; S.shift = W.shift; S.xr = E->xr[c].p; S.vm = E->vm[c].p; S.wt = E->wt[c].p;
-  if (W.self) {
-    if (!W.nsend) return;
-    S.ox = E->xr[c].p + W.gfirst; S.ov = E->vm[c].p + W.gfirst; S.ow = E->wt[c].p + W.gfirst;
-    k_pack_swap<<<GRID(W.nsend, 256), 256, 0, st>>>(S);
-    E->launches++;
-    return;
+  size_t off[2] = {0, 0}, tot = 0;
+  for (int q = 0; q < nsw; q++) { off[q] = tot; if (!Ws[q].self) tot += 3 * (size_t)Ws[q].nsend; }
+  if (tot) E->sbuf.ensure(E, tot, 0, st);
+  bool any_remote = false;
+  for (int q = 0; q < nsw; q++) {
+    dem_engine::Swap &W = Ws[q];
+    SwapP S;
+    S.n = W.nsend; S.list = W.list.p; S.dim = W.dim; S.shift = W.shift; S.xr = E->xr[c].p; S.vm = E->vm[c].p; S.wt = E->wt[c].p;
+    if (W.self) { S.ox = E->xr[c].p + W.gfirst; S.ov = E->vm[c].p + W.gfirst; S.ow = E->wt[c].p + W.gfirst; }
+    else { any_remote = true; S.ox = E->sbuf.p + off[q]; S.ov = S.ox + W.nsend; S.ow = S.ox + 2 * (size_t)W.nsend; }
+    if (W.nsend) { k_pack_swap<<<GRID(W.nsend, 256), 256, 0, st>>>(S); E->launches++; }
   }
-  if (W.nsend) {
-    E->sbuf.ensure(E, 3 * (size_t)W.nsend, 0, st);
-    S.ox = E->sbuf.p; S.ov = E->sbuf.p + W.nsend; S.ow = E->sbuf.p + 2 * (size_t)W.nsend;
-    k_pack_swap<<<GRID(W.nsend, 256), 256, 0, st>>>(S);
-    E->launches++;
-  }
-  const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+  if (!any_remote) return;
   NK(g_nccl.GroupStart());
-  if (peer_send >= 0 && W.nsend)
-    for (int a = 0; a < 3; a++) NK(g_nccl.Send(E->sbuf.p + (size_t)a * W.nsend, 4 * (size_t)W.nsend, ncclDouble, peer_send, E->comm, st));
-  if (peer_recv >= 0 && W.nrecv) {
-    NK(g_nccl.Recv(E->xr[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
-    NK(g_nccl.Recv(E->vm[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
-    NK(g_nccl.Recv(E->wt[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+  for (int q = 0; q < nsw; q++) {
+    dem_engine::Swap &W = Ws[q];
+    if (W.self) continue;
+    const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+    if (peer_send >= 0 && W.nsend)
+      for (int a = 0; a < 3; a++) NK(g_nccl.Send(E->sbuf.p + off[q] + (size_t)a * W.nsend, 4 * (size_t)W.nsend, ncclDouble, peer_send, E->comm, st));
+    if (peer_recv >= 0 && W.nrecv) {
+      NK(g_nccl.Recv(E->xr[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+      NK(g_nccl.Recv(E->vm[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+      NK(g_nccl.Recv(E->wt[c].p + W.gfirst, 4 * (size_t)W.nrecv, ncclDouble, peer_recv, E->comm, st));
+    }
   }
   NK(g_nccl.GroupEnd());
 }
 static void forward_comm(dem_engine *E)
 {
-  for (int q = 0; q < E->nswap; q++) do_swap(E, E->swaps[q]);
+  // the two swaps of a dimension never feed each other (comm_brick.cpp:899-905: the candidates of both are the atoms
+  // present before the dimension starts), so they travel together; dimensions stay ordered (edge / corner ghosts)
+  for (int q = 0; q < E->nswap;) {
+    const int n = (q + 1 < E->nswap && E->swaps[q + 1].dim == E->swaps[q].dim) ? 2 : 1;
+    do_swap(E, &E->swaps[q], n);
+    q += n;
+  }
 }
 
 static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum, int hslots)
@@ -1204,8 +1215,7 @@ static void rebuild(dem_engine *E)
       E->nswap++;
     }
     // records of this dimension's new ghosts (the next dimension's flags look at them)
-    do_swap(E, E->swaps[E->nswap - 2]);
-    do_swap(E, E->swaps[E->nswap - 1]);
+    do_swap(E, &E->swaps[E->nswap - 2], 2);
   }
   // 4. cell order of the ghosts (storage keeps the swap order so that NCCL can receive in place)
   if (E->nghost) {
@@ -1277,6 +1287,7 @@ static void rebuild(dem_engine *E)
   E->nbuilds++;
 }
 
+static int *flag_slot(dem_engine *E, int slot);
 static StepP step_params(dem_engine *E, int mode)
 {
   StepP P;
@@ -1297,7 +1308,7 @@ static StepP step_params(dem_engine *E, int mode)
   P.cutneighmax = E->cutneighmax;
   for (int d = 0; d < 3; d++) P.g[d] = E->g[d];
   P.have_g = E->have_g; P.have_pair = E->have_pair; P.freezebit = E->freezebit; P.integbit = E->integbit;
-  P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = E->nranks > 1 ? E->dflag.p : E->hflag; P.ncontact = nullptr;
+  P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = flag_slot(E, E->fslot); P.gate = E->gate; P.gate_mask = E->gate_mask; P.ncontact = nullptr;
   return P;
 }
 
@@ -1349,19 +1360,27 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   E->launches++;
 }
 
-// rebuild trigger / overflow flags: single rank -> the kernels write mapped host memory directly; multi rank ->
-// they write device memory which is MAX-all-reduced (the reference: MPI_Allreduce in neighbor.cpp:1463)
+// Step flags ([0] rebuild trigger, [1] history overflow, [2] moving-mesh trigger) live in two device slots that alternate
+// between steps: step n writes slot n&1 and is GATED by the slot step n-1 wrote (all-reduced over the ranks; the reference
+// does MPI_Allreduce in neighbor.cpp:1463).  The host copy of a slot arrives one step late through an event, so the host
+// queues step n before it knows whether step n must be preceded by a rebuild; if it must, the gated kernels of step n have
+// returned without touching anything and the host redoes the step after the rebuild (see dem_run).
+static int *flag_slot(dem_engine *E, int slot) { return E->dflag.p + 8 * slot; }
+static const int *gate_slot(dem_engine *E, int slot) { return E->nranks > 1 ? E->dflag.p + 8 * slot + 4 : E->dflag.p + 8 * slot; }
 static void clear_flags(dem_engine *E)
 {
+  E->dflag.ensure(E, 16);
   CK(cudaStreamSynchronize(E->stream));
-  E->hflag[0] = E->hflag[1] = 0;
-  if (E->nranks > 1) { E->dflag.ensure(E, 4); CK(cudaMemsetAsync(E->dflag.p, 0, 4 * sizeof(int), E->stream)); }
+  for (int k = 0; k < 8; k++) E->hflag[k] = 0;
+  CK(cudaMemsetAsync(E->dflag.p, 0, 16 * sizeof(int), E->stream));
 }
-static void reduce_flags(dem_engine *E)
+// after a step: reduce its flags over the ranks, start the copy to the host, mark the point with an event
+static void post_flags(dem_engine *E, int slot)
 {
-  if (E->nranks == 1) return;
-  NK(g_nccl.AllReduce(E->dflag.p, E->dflag.p + 2, 2, ncclInt, ncclMax, E->comm, E->stream));
-  CK(cudaMemcpyAsync(E->hflag, E->dflag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  if (E->nranks > 1) NK(g_nccl.AllReduce(flag_slot(E, slot), flag_slot(E, slot) + 4, 4, ncclInt, ncclMax, E->comm, E->stream));
+  CK(cudaMemcpyAsync(E->hflag + 4 * slot, gate_slot(E, slot), 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  if (!E->fev[slot]) CK(cudaEventCreateWithFlags(&E->fev[slot], cudaEventDisableTiming));
+  CK(cudaEventRecord(E->fev[slot], E->stream));
 }
 
 static void collect_timing(dem_engine *E)
@@ -1411,6 +1430,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   e->step_ms = 0; e->step_calls = 0; e->ev_used = 0;
   // first half step from the stored forces (fix_nve_sphere.cpp:134-183)
   clear_flags(e);
+  e->fslot = 0; e->gate = nullptr; e->gate_mask = 0;
   if (e->nlocal) {
     StepP P = step_params(e, MODE_STEP);
     k_initial_integrate<<<GRID(P.nlocal, 256), 256, 0, st>>>(P);
@@ -1418,41 +1438,71 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   }
   e->cur ^= 1;
   forward_comm(e);
-  reduce_flags(e);
-  for (long s = 1; s <= nsteps; s++) {
-    e->ntimestep++;
-    // fix move/mesh: initial_integrate of this step moves the mesh (fix_move_mesh.cpp:221-238)
-    const bool moving = e->any_moving && e->mesh_ready;
+  post_flags(e, 0);
+  const bool moving = e->any_moving && e->mesh_ready;
+  int overflow_seen = 0;
+  // one step on the device: mesh motion (fix move/mesh initial_integrate, fix_move_mesh.cpp:221-238), the fused step
+  // kernel(s), the ghost refresh and the flag hand-over
+  auto issue_step = [&](long s, int slot) {
+    e->fslot = slot;
+    CK(cudaMemsetAsync(flag_slot(e, slot), 0, 8 * sizeof(int), st));
     if (moving) {
       MeshP M = mesh_params(e);
-      for (size_t m = 0; m < e->meshes.size(); m++) if (e->meshes[m].moving) { mesh_launch_move(M, (int)m, e->dt, 0.25 * e->skin * e->skin, e->hflag + 2, st); e->launches++; }
-    }
-    // Neighbor::decide (neighbor.cpp:1362-1376): a fix may force the rebuild (fix->next_reneighbor), else distance check
-    int nflag = 0;
-    bool synced = false;
-    if (moving && e->next_reneighbor == e->ntimestep) nflag = 1;
-    else {
-      e->ago++;
-      if (e->ago >= e->delay && e->ago % e->every == 0) {
-        if (!e->check) nflag = 1;
-        else { CK(cudaStreamSynchronize(st)); synced = true; nflag = e->hflag[0]; }
-      }
-    }
-    if (nflag) { rebuild(e); clear_flags(e); }
-    else if (moving) {  // FixMesh::pre_force on a regular step: MultiNodeMesh::decideRebuild (fix_mesh.cpp:553-576)
-      if (!synced) CK(cudaStreamSynchronize(st));
-      if (e->hflag[2]) e->next_reneighbor = e->ntimestep + 1;
+      for (size_t m = 0; m < e->meshes.size(); m++)
+        if (e->meshes[m].moving) { mesh_launch_move(M, (int)m, e->dt, 0.25 * e->skin * e->skin, flag_slot(e, slot), e->gate, e->gate_mask, st); e->launches++; }
     }
     launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
     e->cur ^= 1;
     forward_comm(e);
-    reduce_flags(e);
+    post_flags(e, slot);
+  };
+  for (long s = 1; s <= nsteps; s++) {
+    e->ntimestep++;
+    const int prev = (int)((s - 1) & 1), slot = (int)(s & 1);
+    // Neighbor::decide (neighbor.cpp:1362-1376): a fix may force the rebuild (fix->next_reneighbor = the mesh trigger of
+    // the previous step), else the distance check when it is due
+    const int ago1 = e->ago + 1;
+    const bool due = ago1 >= e->delay && ago1 % e->every == 0;
+    const int mask = ((due && e->check) ? 1 : 0) | (moving ? 4 : 0);
+    bool rebuild_now = due && !e->check;
+    if (!rebuild_now) {
+      // speculative: queue the step gated on the previous step's flags, then look at those flags
+      e->gate = mask ? gate_slot(e, prev) : nullptr; e->gate_mask = mask;
+      const long ev0 = e->ev_used, l0 = e->launches;
+      issue_step(s, slot);
+      CK(cudaEventSynchronize(e->fev[prev]));
+      const int *hf = e->hflag + 4 * prev;
+      overflow_seen |= hf[1];
+      if (((mask & 1) && hf[0]) || ((mask & 4) && hf[2])) {  // the queued step returned at its gate: undo the host side
+        rebuild_now = true;
+        e->cur ^= 1; e->ev_used = ev0; e->launches = l0;
+      } else e->ago = ago1;
+    }
+    if (rebuild_now) {
+      e->gate = nullptr; e->gate_mask = 0;
+      if (moving) {  // the mesh moves before the lists are rebuilt
+        MeshP M = mesh_params(e);
+        for (size_t m = 0; m < e->meshes.size(); m++)
+          if (e->meshes[m].moving) { mesh_launch_move(M, (int)m, e->dt, 0.25 * e->skin * e->skin, flag_slot(e, slot), nullptr, 0, st); e->launches++; }
+      }
+      rebuild(e);
+      clear_flags(e);
+      const bool was_moving = false;
+      (void)was_moving;
+      // the step itself, not gated; its mesh motion has been done above
+      e->fslot = slot;
+      launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
+      e->cur ^= 1;
+      forward_comm(e);
+      post_flags(e, slot);
+    }
     if (e->ev_used >= 2048) { CK(cudaStreamSynchronize(st)); collect_timing(e); }
   }
+  e->gate = nullptr; e->gate_mask = 0;
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   collect_timing(e);
-  if (e->hflag[1]) { e->hflag[1] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
+  if (overflow_seen || e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;
   API_END
 }

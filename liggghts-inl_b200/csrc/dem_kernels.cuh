@@ -35,6 +35,10 @@ __device__ __forceinline__ void st4(double4 *p, const double4 &v)
 }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ bool step_gated(const StepP &P)
+{  // see StepP::gate
+  return P.gate && (((P.gate_mask & 1) && P.gate[0]) || ((P.gate_mask & 4) && P.gate[2]));
+}
 __device__ __forceinline__ int rec_type(double w) { return (int)(__double_as_longlong(w) & 0xff); }
 __device__ __forceinline__ int rec_mask(double w) { return (int)((__double_as_longlong(w) >> 8) & 0xffffffffLL); }
 __host__ __device__ __forceinline__ long long pack_bits(int type, int mask) { return ((long long)(unsigned)mask << 8) | (long long)(type & 0xff); }
@@ -63,7 +67,7 @@ __device__ __noinline__ void wall_chain(const StepP &P, const ModelP &M, const C
 __global__ void __launch_bounds__(128) k_walls(const StepP P)
 {
   const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cidx >= P.nwc) return;
+  if (cidx >= P.nwc || step_gated(P)) return;
   const int i = P.wlist[cidx];
   const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
   const int itype = rec_type(wi.w);
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   __shared__ int s_off[128], s_nh[128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
+  if (step_gated(P)) return;
   const bool active = i < P.nlocal;
   const bool su = (P.mode != MODE_SETUP);
   bool trig = false;
@@ -394,6 +399,7 @@ __global__ void __launch_bounds__(128) k_step_bond(const StepP P)
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool trig = false;
+  if (step_gated(P)) return;
   if (i < P.nlocal) {
     const ModelP &M = P.pm;
     const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);

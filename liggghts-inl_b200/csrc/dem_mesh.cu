@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(128) k_mesh_step(const StepP P, const MeshP M)
 {
   const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (cidx >= P.nwc) return;
+  if (P.gate && (((P.gate_mask & 1) && P.gate[0]) || ((P.gate_mask & 4) && P.gate[2]))) return;  // speculative launch, see StepP::gate
   const int i = P.wlist[cidx];
   const int nct = M.mint[i];
   if (!nct) return;
@@ -297,11 +298,12 @@ __global__ void __launch_bounds__(128) k_mesh_step(const StepP P, const MeshP M)
 
 // fix move/mesh linear: node += vel*dt, center += vel*dt ; a node that moved more than skin/2 since the last
 // rebuild raises the flag (MultiNodeMesh::decideRebuild)
-__global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, double dt, double trigsq, int *flag)
+__global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, double dt, double trigsq, int *flag, const int *gate, int gate_mask)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const MeshMeta &mm = M.meta[mesh];
   if (q >= mm.ntri) return;
+  if (gate && (((gate_mask & 1) && gate[0]) || ((gate_mask & 4) && gate[2]))) return;
   const int t = mm.first + q;
   TriRec &T = M.tri[t];
   double dx[3];
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, doub
     if (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2] > trigsq) trig = true;
   }
   for (int d = 0; d < 3; d++) T.center[d] = T.center[d] + dx[d];
-  if (trig) *((volatile int *)flag) = 1;
+  if (trig) ((volatile int *)flag)[2] = 1;
 }
 __global__ void __launch_bounds__(128) k_mesh_hold(const MeshP M)
 {
@@ -330,10 +332,10 @@ void mesh_launch_step(const StepP &P, const MeshP &M, cudaStream_t st)
 {
   if (P.nwc > 0) k_mesh_step<<<(P.nwc + 127) / 128, 128, 0, st>>>(P, M);
 }
-void mesh_launch_move(const MeshP &M, int mesh, double dt, double trigsq, int *flag, cudaStream_t st)
+void mesh_launch_move(const MeshP &M, int mesh, double dt, double trigsq, int *flag, const int *gate, int gate_mask, cudaStream_t st)
 {
   const int n = M.meta[mesh].ntri;
-  if (n > 0) k_mesh_move<<<(n + 127) / 128, 128, 0, st>>>(M, mesh, dt, trigsq, flag);
+  if (n > 0) k_mesh_move<<<(n + 127) / 128, 128, 0, st>>>(M, mesh, dt, trigsq, flag, gate, gate_mask);
 }
 void mesh_launch_hold(const MeshP &M, cudaStream_t st)
 {

@@ -51,7 +51,7 @@ struct MeshP {
 // launchers implemented in dem_mesh.cu
 void mesh_launch_candidates(const MeshP &M, int nlocal, const double4 *xr, double skin, double cdf, cudaStream_t st);
 void mesh_launch_step(const StepP &P, const MeshP &M, cudaStream_t st);
-void mesh_launch_move(const MeshP &M, int mesh, double dt, double trigsq, int *flag, cudaStream_t st);
+void mesh_launch_move(const MeshP &M, int mesh, double dt, double trigsq, int *flag, const int *gate, int gate_mask, cudaStream_t st);
 void mesh_launch_hold(const MeshP &M, cudaStream_t st);
 
 }  // namespace dem

@@ -78,7 +78,12 @@ struct StepP {
   int have_g, have_pair, freezebit, integbit;
   int mode;
   int debug;  // profiling aid (option "debug"): bit0 skip contact evaluation, bit1 skip list walk
-  int *flag;  // [0] rebuild trigger, [1] history-slot overflow (mapped host memory)
+  int *flag;  // device flags written by this step: [0] rebuild trigger, [1] history-slot overflow, [2] moving-mesh trigger
+  // speculative launch: the flags the PREVIOUS step produced (all-reduced over the ranks).  If a masked entry is set the
+  // neighbour list must be rebuilt before this step, so every kernel of the step returns at once and the host relaunches it
+  // after the rebuild; the host therefore never has to wait for a step before queueing the next one.
+  const int *gate;
+  int gate_mask;  // bit0: gate[0] (distance check due this step), bit2: gate[2] (a moving mesh forces the rebuild)
   unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
 };
 
