@@ -247,6 +247,8 @@ def own_arm(args):
     n = len(c["tag"])
     eng = cases.apply(c, new_engine())
     eng.option("time_kernels", 1)
+    if os.environ.get("DEM_DEBUG"):
+        eng.option("debug", int(os.environ["DEM_DEBUG"]))  # profiling aid only (the numbers are not bench values)
     eng.setup()
     eng.run(max(args.warmup, 3))
     st0 = eng.stats()

@@ -118,7 +118,11 @@ struct dem_engine {
   double sublo[3] = {0, 0, 0}, subhi[3] = {1, 1, 1};
   ncclComm_t comm = nullptr;
   // ghost swaps, LAMMPS order: for dim 0..2: (send to lo neighbour, send to hi neighbour)
-  struct Swap { int dim = 0, side = 0, peer = -1, self = 0, nsend = 0, nrecv = 0, gfirst = 0; double shift = 0.0; DevBuf<int> list; };
+  struct Swap {
+    int dim = 0, side = 0, peer = -1, self = 0, nsend = 0, nrecv = 0, gfirst = 0; double shift = 0.0; DevBuf<int> list;
+    // peer-memory path (valid between rebuilds): the receiver's record arrays, ghost offset and buffer parity
+    double4 *pbase[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; int *psig = nullptr; int pgfirst = 0, pcur0 = 0, p2p = 0, serial = 0;
+  };
   Swap swaps[6]; int nswap = 0;
   DevBuf<double4> sbuf, rbuf_unused;
   DevBuf<int> sbuf_i, gorder, gone, cnt_dev;
@@ -148,6 +152,12 @@ struct dem_engine {
   int mcur = 0, mslots = 8, mcand = 16, mhrec = 0, mesh_ready = 0, grid_ready = 0, any_moving = 0;
   double mgorg[3] = {0, 0, 0}, mginv[3] = {1, 1, 1}; int mgnc[3] = {1, 1, 1};
   long next_reneighbor = -1;
+  // CUDA IPC mappings of neighbour ranks' buffers (key = the 64 handle bytes)
+  struct IpcMap { unsigned char key[64]; void *ptr; int rank, gen; };
+  int alloc_gen = 0;  // bumped whenever the record arrays are reallocated (their IPC handles change meaning)
+  std::vector<IpcMap> ipc;
+  DevBuf<int> hsig;       // [0..5] incoming halo serials per swap, [8..13] block counters of my pack kernels
+  int cur0 = 0, p2p_ok = 0;
   cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
   int fslot = 0;                            // slot the next step writes
   const int *gate = nullptr; int gate_mask = 0;  // gate of the step being launched (nullptr: not speculative)
@@ -253,6 +263,8 @@ extern "C" void dem_destroy(dem_engine *e)
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   if (e->hflag) cudaFreeHost(e->hflag);
   for (int k = 0; k < 2; k++) if (e->fev[k]) cudaEventDestroy(e->fev[k]);
+  for (auto &m : e->ipc) cudaIpcCloseMemHandle(m.ptr);
+  e->hsig.release();
   if (e->hcnt) cudaFreeHost(e->hcnt);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   delete e;
@@ -672,6 +684,7 @@ static void ensure_particle_cap(dem_engine *E, long need, long keep)
 {
   if (need <= E->cap) return;
   const int oldcap = E->cap;
+  E->alloc_gen++;
   long ncap = std::max(need + need / 8 + 256, (long)oldcap * 3 / 2);
   ncap = (ncap + 127) / 128 * 128;
   cudaStream_t st = E->stream;
@@ -983,6 +996,86 @@ static void xchg_ints(dem_engine *E, int peer_send, const int *sendv, int peer_r
   for (int k = 0; k < n; k++) recvv[k] = E->hcnt[32 + k];
 }
 
+// blocking exchange of a small byte block with the two peers of a swap (either may be -1)
+static void xchg_bytes(dem_engine *E, int peer_send, const void *sendv, int peer_recv, void *recvv, size_t nbytes)
+{
+  cudaStream_t st = E->stream;
+  E->stage.ensure(E, 2 * nbytes + 64);
+  char *d = E->stage.p;
+  CK(cudaMemcpyAsync(d, sendv, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d + nbytes, 0, nbytes, st));
+  NK(g_nccl.GroupStart());
+  if (peer_send >= 0) NK(g_nccl.Send(d, nbytes, ncclChar, peer_send, E->comm, st));
+  if (peer_recv >= 0) NK(g_nccl.Recv(d + nbytes, nbytes, ncclChar, peer_recv, E->comm, st));
+  NK(g_nccl.GroupEnd());
+  CK(cudaMemcpyAsync(recvv, d + nbytes, nbytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+}
+
+// End of a rebuild: every rank tells the rank that will push ghosts to it where they go (CUDA IPC handles of its six
+// record arrays and of its signal words, the first ghost index of the swap, its buffer parity).  From here until the
+// next rebuild the per-step ghost refresh is plain NVLink stores issued by the sender's pack kernel -- no NCCL call.
+struct HaloInfo { cudaIpcMemHandle_t h[7]; int gfirst, cur, ok, gen; };
+static void *ipc_open(dem_engine *E, const cudaIpcMemHandle_t &h, int rank, int gen)
+{
+  // mappings of an older allocation generation of that rank are dead: close them
+  for (size_t k = 0; k < E->ipc.size();) {
+    if (E->ipc[k].rank == rank && E->ipc[k].gen != gen) { cudaIpcCloseMemHandle(E->ipc[k].ptr); E->ipc.erase(E->ipc.begin() + k); }
+    else k++;
+  }
+  for (auto &m : E->ipc) if (m.rank == rank && !memcmp(m.key, &h, 64)) return m.ptr;
+  void *p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  dem_engine::IpcMap m; memcpy(m.key, &h, 64); m.ptr = p; m.rank = rank; m.gen = gen;
+  E->ipc.push_back(m);
+  return p;
+}
+static void halo_p2p_setup(dem_engine *E)
+{
+  if (E->nranks == 1) return;
+  const bool want = !(E->opt.count("p2p") && E->opt["p2p"] == 0);
+  cudaStream_t st = E->stream;
+  E->hsig.ensure(E, 16);
+  CK(cudaMemsetAsync(E->hsig.p, 0, 16 * sizeof(int), st));
+  CK(cudaStreamSynchronize(st));
+  E->cur0 = E->cur;
+  int all_ok = 1;
+  for (int q = 0; q < E->nswap; q++) {
+    dem_engine::Swap &W = E->swaps[q];
+    W.p2p = 0; W.serial = 0;
+    if (W.self) continue;
+    const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+    HaloInfo mine, theirs;
+    memset(&mine, 0, sizeof mine); memset(&theirs, 0, sizeof theirs);
+    mine.ok = want ? 1 : 0;
+    if (want) {
+      void *bufs[7] = {E->xr[0].p, E->xr[1].p, E->vm[0].p, E->vm[1].p, E->wt[0].p, E->wt[1].p, E->hsig.p};
+      for (int k = 0; k < 7; k++) if (cudaIpcGetMemHandle(&mine.h[k], bufs[k]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    }
+    mine.gfirst = W.gfirst; mine.cur = E->cur; mine.gen = E->alloc_gen;
+    // my info goes to the rank that sends to me in this swap; I receive the info of the rank I send to
+    xchg_bytes(E, peer_recv, &mine, peer_send, &theirs, sizeof(HaloInfo));
+    if (peer_send < 0) continue;
+    int ok = theirs.ok && want;
+    if (ok) {
+      for (int k = 0; k < 6 && ok; k++) { W.pbase[k] = (double4 *)ipc_open(E, theirs.h[k], peer_send, theirs.gen); if (!W.pbase[k]) ok = 0; }
+      W.psig = ok ? (int *)ipc_open(E, theirs.h[6], peer_send, theirs.gen) : nullptr;
+      if (!W.psig) ok = 0;
+    }
+    W.pgfirst = theirs.gfirst; W.pcur0 = theirs.cur; W.p2p = ok;
+    if (!ok) all_ok = 0;
+  }
+  // every rank must take the same path for a given swap pair: agree globally
+  E->cnt_dev.ensure(E, 64);
+  E->hcnt[0] = all_ok;
+  CK(cudaMemcpyAsync(E->cnt_dev.p, E->hcnt, sizeof(int), cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllReduce(E->cnt_dev.p, E->cnt_dev.p + 1, 1, ncclInt, ncclMin, E->comm, st));
+  CK(cudaMemcpyAsync(E->hcnt + 1, E->cnt_dev.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  E->p2p_ok = E->hcnt[1];
+  if (!E->p2p_ok) for (int q = 0; q < E->nswap; q++) E->swaps[q].p2p = 0;
+}
+
 // flags -> deterministic compact list; returns the number of set flags
 static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &scan, DevBuf<int> &list)
 {
@@ -1002,10 +1095,32 @@ static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &s
 // per-step ghost refresh == CommBrick::forward_comm (comm_brick.cpp:563-645): one pack kernel per swap; periodic
 // images on the same rank are written in place, remote ghosts travel as three NCCL send/recv pairs that land
 // directly in the ghost region of the record arrays.  Swaps run in order so that edge/corner ghosts propagate.
-static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw)
+static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw, bool allow_p2p = false)
 {  // nsw = 1, or the two (independent) swaps of one decomposed dimension exchanged in ONE NCCL group
   cudaStream_t st = E->stream;
   const int c = E->cur;
+  if (allow_p2p && E->p2p_ok && !Ws[0].self) {  // peer-memory path (between rebuilds)
+    const bool skip = E->opt.count("debug") && ((int)E->opt["debug"] & 8);
+    const volatile int *wsig[2] = {nullptr, nullptr}; int wser[2] = {0, 0};
+    for (int q = 0; q < nsw; q++) {
+      dem_engine::Swap &W = Ws[q];
+      const int qi = (int)(&W - E->swaps);
+      W.serial++;
+      const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+      if (peer_send >= 0 && !skip) {
+        const int pc = W.pcur0 ^ (c ^ E->cur0);  // the receiver's buffer parity moves in lock step with mine
+        SwapP S;
+        S.n = W.nsend; S.list = W.list.p; S.dim = W.dim; S.shift = W.shift; S.xr = E->xr[c].p; S.vm = E->vm[c].p; S.wt = E->wt[c].p;
+        S.ox = W.pbase[0 + pc] + W.pgfirst; S.ov = W.pbase[2 + pc] + W.pgfirst; S.ow = W.pbase[4 + pc] + W.pgfirst;
+        if (W.nsend) k_pack_push<<<GRID(W.nsend, 256), 256, 0, st>>>(S, (unsigned *)E->hsig.p + 8 + qi, W.psig + qi, W.serial);
+        else k_halo_signal<<<1, 1, 0, st>>>(W.psig + qi, W.serial);
+        E->launches++;
+      }
+      if (peer_recv >= 0 && !skip) { wsig[q] = E->hsig.p + qi; wser[q] = W.serial; }
+    }
+    if (wsig[0] || wsig[1]) { k_halo_wait<<<1, 1, 0, st>>>(wsig[0], wser[0], wsig[1], wser[1], E->hsig.p + 15); E->launches++; }
+    return;
+  }
   size_t off[2] = {0, 0}, tot = 0;
   for (int q = 0; q < nsw; q++) { off[q] = tot; if (!Ws[q].self) tot += 3 * (size_t)Ws[q].nsend; }
   if (tot) E->sbuf.ensure(E, tot, 0, st);
@@ -1019,6 +1134,7 @@ static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw)
     if (W.nsend) { k_pack_swap<<<GRID(W.nsend, 256), 256, 0, st>>>(S); E->launches++; }
   }
   if (!any_remote) return;
+  if (E->opt.count("debug") && ((int)E->opt["debug"] & 8) && E->setup_done) return;  // profiling aid: no halo traffic between rebuilds
   NK(g_nccl.GroupStart());
   for (int q = 0; q < nsw; q++) {
     dem_engine::Swap &W = Ws[q];
@@ -1040,7 +1156,7 @@ static void forward_comm(dem_engine *E)
   // present before the dimension starts), so they travel together; dimensions stay ordered (edge / corner ghosts)
   for (int q = 0; q < E->nswap;) {
     const int n = (q + 1 < E->nswap && E->swaps[q + 1].dim == E->swaps[q].dim) ? 2 : 1;
-    do_swap(E, &E->swaps[q], n);
+    do_swap(E, &E->swaps[q], n, true);
     q += n;
   }
 }
@@ -1282,6 +1398,7 @@ static void rebuild(dem_engine *E)
     }
   }
   CK(cudaGetLastError());
+  halo_p2p_setup(E);
   E->ago = 0;
   E->order_valid = 0;
   E->nbuilds++;
@@ -1377,7 +1494,11 @@ static void clear_flags(dem_engine *E)
 // after a step: reduce its flags over the ranks, start the copy to the host, mark the point with an event
 static void post_flags(dem_engine *E, int slot)
 {
-  if (E->nranks > 1) NK(g_nccl.AllReduce(flag_slot(E, slot), flag_slot(E, slot) + 4, 4, ncclInt, ncclMax, E->comm, E->stream));
+  const int dbg = E->opt.count("debug") ? (int)E->opt["debug"] : 0;
+  if (E->nranks > 1) {
+    if (dbg & 4) CK(cudaMemcpyAsync(flag_slot(E, slot) + 4, flag_slot(E, slot), 4 * sizeof(int), cudaMemcpyDeviceToDevice, E->stream));  // profiling aid: no all-reduce
+    else NK(g_nccl.AllReduce(flag_slot(E, slot), flag_slot(E, slot) + 4, 4, ncclInt, ncclMax, E->comm, E->stream));
+  }
   CK(cudaMemcpyAsync(E->hflag + 4 * slot, gate_slot(E, slot), 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   if (!E->fev[slot]) CK(cudaEventCreateWithFlags(&E->fev[slot], cudaEventDisableTiming));
   CK(cudaEventRecord(E->fev[slot], E->stream));
@@ -1502,6 +1623,11 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   collect_timing(e);
+  if (e->nranks > 1 && e->p2p_ok) {
+    int to = 0;
+    CK(cudaMemcpy(&to, e->hsig.p + 15, sizeof(int), cudaMemcpyDeviceToHost));
+    if (to) dem_fail(e, DEM_ERR_CUDA, "halo exchange timed out waiting for a neighbour rank");
+  }
   if (overflow_seen || e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;
   API_END

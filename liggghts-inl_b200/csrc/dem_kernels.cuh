@@ -546,6 +546,35 @@ __global__ void __launch_bounds__(256) k_pack_swap(const SwapP S)
   if (S.dim == 0) x.x += S.shift; else if (S.dim == 1) x.y += S.shift; else x.z += S.shift;
   S.ox[q] = x; S.ov[q] = S.vm[s]; S.ow[q] = S.wt[s];
 }
+// Per-step ghost refresh over NVLink peer memory: the sender's pack kernel stores the three records of every send-list
+// entry straight into the RECEIVER's ghost region (pointers obtained through CUDA IPC at the last rebuild, see
+// halo_p2p_setup) and the last block to finish publishes the exchange's serial number in the receiver's signal word.
+// The receiver's stream waits on that word (k_halo_wait) before anything that reads those ghosts.
+__global__ void __launch_bounds__(256) k_pack_push(const SwapP S, unsigned *done_counter, volatile int *peer_signal, int serial)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < S.n) {
+    const int s = S.list[q];
+    double4 x = S.xr[s];
+    if (S.dim == 0) x.x += S.shift; else if (S.dim == 1) x.y += S.shift; else x.z += S.shift;
+    st4(S.ox + q, x); st4(S.ov + q, S.vm[s]); st4(S.ow + q, S.wt[s]);
+  }
+  __threadfence_system();  // my peer stores are performed before my block is counted
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) { *done_counter = 0; __threadfence_system(); *peer_signal = serial; }
+}
+__global__ void k_halo_signal(volatile int *peer_signal, int serial) { *peer_signal = serial; }  // empty send list
+__global__ void k_halo_wait(const volatile int *sig_a, int serial_a, const volatile int *sig_b, int serial_b, int *timeout_flag)
+{  // bounded (~4 s): a lost peer must not hang the device
+  const long long t0 = clock64();
+  const long long limit = 8000000000LL;
+  if (sig_a) while (*sig_a < serial_a) { __nanosleep(64); if (clock64() - t0 > limit) { *timeout_flag = 1; return; } }
+  if (sig_b) while (*sig_b < serial_b) { __nanosleep(64); if (clock64() - t0 > limit) { *timeout_flag = 1; return; } }
+  __threadfence_system();
+}
 __global__ void __launch_bounds__(256) k_pack_int(int n, const int *list, const int *src, int *out)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
