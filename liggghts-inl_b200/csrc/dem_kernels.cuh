@@ -153,7 +153,12 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
   for (int d = 0; d < 3; d++) { P.fw[(size_t)d * P.nwcap + cidx] = F[d]; P.fw[(size_t)(3 + d) * P.nwcap + cidx] = T[d]; }
 }
 
-#define DEM_CMAX 16  // contacts per particle staged in shared memory (more go through the bit-mask path)
+#ifndef DEM_CMAX
+#define DEM_CMAX 12  // contacts per particle staged in shared memory (more go through the bit-mask path)
+#endif
+#ifndef DEM_RWIN
+#define DEM_RWIN 2   // rounds of 32 contact items whose results are parked in shared memory before the owners add them
+#endif
 
 // one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see
 // pair_chain); history records are stored in the canonical orientation "lower tag first" (sign
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
   __shared__ unsigned s_w[DEM_CMAX][128];
   __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
-  __shared__ double s_res[6][128];    // per-lane result slot of the current round
+  __shared__ double s_res[6][4 * 32 * DEM_RWIN];  // per warp: force / torque of the items of the current window
   __shared__ int s_off[128], s_nh[128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
@@ -352,23 +357,29 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     s_off[tid] = excl;
     __syncwarp();
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
-      if (t < total) {
-        int p = 0;  // owner of item t: the last lane whose first item is <= t
+    // rounds of 32 items; results are parked in shared memory and each owner adds its items (in list order) once per
+    // window of DEM_RWIN rounds -- one short loop per window instead of one per round
+    for (int b0 = 0; b0 < total; b0 += 32 * DEM_RWIN) {
+      const int bend = min(total, b0 + 32 * DEM_RWIN);
+      for (int t0 = b0; t0 < bend; t0 += 32) {
+        const int t = t0 + lane;
+        double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
+        if (t < total) {
+          int p = 0;  // owner of item t: the last lane whose first item is <= t
 #pragma unroll
-        for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
-        const int q = wb + p;
-        const unsigned w = s_w[t - s_off[q]][q];
-        pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
+          for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
+          const int q = wb + p;
+          const unsigned w = s_w[t - s_off[q]][q];
+          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
+          const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
+#pragma unroll
+          for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
+        }
       }
-#pragma unroll
-      for (int d = 0; d < 3; d++) { s_res[d][tid] = rF[d]; s_res[3 + d][tid] = rT[d]; }
       __syncwarp();
-      const int qe = min(incl, t0 + 32);
-      for (int k = max(excl, t0); k < qe; k++) {
-        const int sl = wb + k - t0;
+      const int qe = min(incl, bend);
+      for (int k = max(excl, b0); k < qe; k++) {
+        const int sl = (wb >> 5) * (32 * DEM_RWIN) + (k - b0);
 #pragma unroll
         for (int d = 0; d < 3; d++) { F[d] += s_res[d][sl]; T[d] += s_res[3 + d][sl]; }
       }

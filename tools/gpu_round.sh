@@ -5,7 +5,7 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
-tail -5 gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
 timeout 900 python bench.py --gpus 1 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${TAG}_bench.json
 timeout 600 python bench.py --impl reference --gpus 1 --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"
@@ -14,4 +14,4 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 30 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_step -s 12 -c 2 -f -o gpurun_out/${TAG}_k_step \
     python bench.py --steps 30 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out
+ls -la gpurun_out | tail -12

@@ -16,8 +16,10 @@ b = blocks[which]
 h = b["hdr"]; iS = h.index("# Samples"); iI = h.index("Instructions Executed"); iT = h.index("Thread Instructions Executed")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cub = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for f in sorted(os.listdir(tmp)):
+    if f.endswith(".cubin"):
+        dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout.splitlines()
 lines, insec, curline = [], False, None
 for l in dis:
     if l.startswith("\t.section"):
