@@ -153,6 +153,12 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
   for (int d = 0; d < 3; d++) { P.fw[(size_t)d * P.nwcap + cidx] = F[d]; P.fw[(size_t)(3 + d) * P.nwcap + cidx] = T[d]; }
 }
 
+#ifndef DEM_INBLOCK
+#define DEM_INBLOCK 0  // 1: records of partners inside the own block come from shared memory (measured r01d: 1.36 vs 1.25 ms, off)
+#endif
+#ifndef DEM_CPREFETCH
+#define DEM_CPREFETCH 2  // L2 prefetch of a staged contact's operands: 0 none, 1 history rows, 2 history + partner v|m, omega|bits
+#endif
 #ifndef DEM_CMAX
 #define DEM_CMAX 12  // contacts per particle staged in shared memory (more go through the bit-mask path)
 #endif
@@ -166,13 +172,19 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 // slots in use (a shared-memory counter: in the cooperative phase several lanes may serve one particle).
 template <int NORMAL, int ROLLING, bool ONE>
 __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
-                                             const double4 &wi, bool su, int *nh, double *F, double *T)
+                                             const double4 &wi, bool su, int *nh, double *F, double *T,
+                                             const double4 (*srec)[128], unsigned bbase, unsigned blim)
 {
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int j = (int)(w & NBR_IDX);
   int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   const bool had = slot >= 0;
-  const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
+  // partners that live in the same block are read from the block's shared-memory copy of its records (after a
+  // Morton sort about half of all partners): a scattered 32-byte global gather costs one L1 wavefront per lane
+  const unsigned jl = (unsigned)j - bbase;
+  double4 xj, vj, wj;
+  if (DEM_INBLOCK && jl < blim) { xj = srec[0][jl]; vj = srec[1][jl]; wj = srec[2][jl]; }
+  else { xj = ldg4(P.xr + j); vj = ldg4(P.vm + j); wj = ldg4(P.wt + j); }
   double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
   if (had) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
@@ -201,12 +213,12 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
 }
 
 // start the memory accesses a staged contact will need, without holding registers
-__device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w)
+__device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w, unsigned bbase, unsigned blim)
 {
   const int j = (int)(w & NBR_IDX);
-  prefetch_l2(P.vm + j); prefetch_l2(P.wt + j);
+  if (DEM_CPREFETCH >= 2 && !(DEM_INBLOCK && (unsigned)j - bbase < blim)) { prefetch_l2(P.vm + j); prefetch_l2(P.wt + j); }
   const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-  if (slot >= 0) {
+  if (DEM_CPREFETCH >= 1 && slot >= 0) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
     for (int r = 0; r < P.pm.hrec; r++) prefetch_l2(hp + (size_t)r * P.lcap);
   }
@@ -287,6 +299,8 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   if (step_gated(P)) return;
   const bool active = i < P.nlocal;
   const bool su = (P.mode != MODE_SETUP);
+  const unsigned bbase = blockIdx.x * blockDim.x;                                  // first particle of this block
+  const unsigned blim = (unsigned)min(128, P.nlocal - (int)bbase);                 // ... and how many of them are owned
   bool trig = false;
   double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
   int nc = 0, nh0 = 0, nn = 0;
@@ -311,6 +325,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       nh0 = (nnw >> 16) & 0xffff;
     }
     s_nh[tid] = nh0;
+    if (DEM_INBLOCK) __syncthreads();  // s_rec of the whole block is complete
     for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += 64) {
       const int kn = min(64, nn - k0);
       unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
@@ -318,7 +333,8 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 #pragma unroll 8
       for (int kk = 0; kk < kn; kk++) {
         const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
-        const double4 xj = ldg4(P.xr + (w & NBR_IDX));
+        const unsigned jl = (w & NBR_IDX) - bbase;
+        const double4 xj = (DEM_INBLOCK && jl < blim) ? s_rec[0][jl] : ldg4(P.xr + (w & NBR_IDX));
         const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
         const double radsum = xi.w + xj.w;
         const bool t = rsq < __dmul_rn(radsum, radsum);
@@ -331,12 +347,12 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         touch &= touch - 1;
         const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
         if (nc < DEM_CMAX) s_w[nc++][tid] = w; else extra |= 1ull << kk;
-        prefetch_contact(P, i, w);
+        prefetch_contact(P, i, w, bbase, blim);
       }
       while (extra) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
         const int kk = __ffsll((long long)extra) - 1;
         extra &= extra - 1;
-        pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + kk) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
+        pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + kk) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T, s_rec, bbase, blim);
       }
       while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
         const int kk = __ffsll((long long)close) - 1;
@@ -370,7 +386,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
           for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
           const int q = wb + p;
           const unsigned w = s_w[t - s_off[q]][q];
-          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
+          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT, s_rec, bbase, blim);
           const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }

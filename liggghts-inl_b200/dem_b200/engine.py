@@ -214,14 +214,20 @@ class Engine:
         f = self._fn("nlocal"); f.argtypes = [C.c_void_p]; f.restype = C.c_long
         return f(self._h)
 
-    def download(self, field):
+    def download(self, field, out=None):
+        """per-particle field ordered by tag.  `out`: optional caller-owned C-contiguous array of the right dtype/shape
+        (e.g. a view of page-locked memory: the engine copies straight into the caller's buffer)"""
         n = self.nlocal
         if field in ("tag", "type", "mask"):
-            out = np.zeros(n, np.int32)
+            shape, dt = (n,), np.int32
         elif field in ("radius", "rmass", "density"):
-            out = np.zeros(n, np.float64)
+            shape, dt = (n,), np.float64
         else:
-            out = np.zeros((n, 3), np.float64)
+            shape, dt = (n, 3), np.float64
+        if out is None:
+            out = np.zeros(shape, dt)
+        elif out.dtype != dt or out.shape != shape or not out.flags.c_contiguous:
+            raise ValueError("download(%s): out must be a C-contiguous %s array of shape %s" % (field, np.dtype(dt).name, shape))
         self._call("download", [C.c_char_p, C.c_void_p, C.c_long], field.encode(), out.ctypes.data, n)
         return out
 
@@ -244,9 +250,11 @@ class Engine:
         return out[:, :dnum]
 
     def mesh_field(self, mesh_id, field, ntri):
-        """topology / geometry of a mesh: nodes (ntri,3,3) f64; edge_active, corner_active (ntri,3) i32; obtuse, nneighs (ntri,) i32"""
-        if field == "nodes":
+        """topology / geometry of a mesh: nodes, edge_vec, edge_norm (ntri,3,3) f64; surf_norm, center (ntri,3) f64; edge_active, corner_active (ntri,3) i32; obtuse, nneighs (ntri,) i32"""
+        if field in ("nodes", "edge_vec", "edge_norm"):
             out = np.zeros((ntri, 3, 3), np.float64)
+        elif field in ("surf_norm", "center"):
+            out = np.zeros((ntri, 3), np.float64)
         elif field in ("edge_active", "corner_active"):
             out = np.zeros((ntri, 3), np.int32)
         else:

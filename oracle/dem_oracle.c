@@ -68,7 +68,7 @@ typedef struct {  /* TriMesh + FixNeighlistMesh + FixContactHistoryMesh of one `
   double (*node)[3][3], (*center)[3], *rbound, (*edgeVec)[3][3], (*edgeLen)[3], (*surfNorm)[3], (*edgeNorm)[3][3];
   int *obtuse, *nNeighs, (*neighFaces)[NUM_NEIGH_MAX]; unsigned char (*edgeActive)[3], (*cornerActive)[3];
   double curvature, precision;
-  int moving; double vel[3]; double (*vnode)[3][3]; double (*nodesLastRe)[3][3]; int next_reneighbor;
+  int moving; /* 0 static, 1 `linear`, 2 `rotate` */ double vel[3]; double rot_origin[3], rot_axis[3], rot_omega; double (*vnode)[3][3]; double (*nodesLastRe)[3][3]; int next_reneighbor;
   /* FixNeighlistMesh: per-triangle particle lists */
   int **contacts; int *ncontacts, *capcontacts;
   /* FixContactHistoryMesh: per-particle rows sized by the particle's candidate count */
@@ -734,6 +734,7 @@ static int comp_double(double a, double b, double prec)
 static int nodes_equal(const mesh_t *M, const double *a, const double *b)
 { for (int d = 0; d < 3; d++) if (!comp_double(a[d], b[d], M->precision)) return 0; return 1; } /* multi_node_mesh_I.h:246-261 */
 
+static void tri_surf_properties(mesh_t *M, int n);
 static void tri_properties(mesh_t *M, int n)
 { /* multi_node_mesh_I.h:153-172 (center, rBound) ; surface_mesh_I.h:302-470 */
   double avg[3] = {0., 0., 0.};
@@ -743,6 +744,12 @@ static void tri_properties(mesh_t *M, int n)
   double rb = 0.;
   for (int i = 0; i < 3; i++) { double vec[3]; v3sub(M->center[n], M->node[n][i], vec); const double m = v3mag(vec); if (m > rb) rb = m; }
   M->rbound[n] = rb;
+  tri_surf_properties(M, n);
+}
+static void tri_surf_properties(mesh_t *M, int n)
+{ /* SurfaceMesh::recalcLocalSurfProperties surface_mesh_I.h:187-222: edge vectors/lengths, surface and edge normals, obtuse
+   * index recomputed from the nodes -- at first setup, at every later setup and, for moving meshes, at every neighbour
+   * rebuild (FixMesh::setup_pre_force / pre_force fix_mesh.cpp:491-575 -> pbcExchangeBorders -> refreshOwned) */
   for (int i = 0; i < 3; i++) { /* calcEdgeVecLen */
     v3sub(M->node[n][(i + 1) % 3], M->node[n][i], M->edgeVec[n][i]);
     M->edgeLen[n][i] = v3mag(M->edgeVec[n][i]);
@@ -882,11 +889,26 @@ int orc_add_mesh(orc_engine *e, const char *id, int atom_type, const double *nod
   e->nmeshes++; return 0;
 }
 int orc_move_mesh(orc_engine *e, const char *mesh_id, int argc, const char *const *argv)
-{ /* fix move/mesh mesh ID linear vx vy vz : fix_move_mesh.cpp, mesh_mover_linear.cpp:94-112 */
+{ /* fix move/mesh mesh ID linear vx vy vz : fix_move_mesh.cpp, mesh_mover_linear.cpp:94-112
+   * fix move/mesh mesh ID rotate origin x y z axis x y z period T : mesh_mover_rotation.cpp:58-82 */
   for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) {
-    if (argc != 4 || strcmp(argv[0], "linear")) return fail(e, "only 'linear vx vy vz' is supported");
-    for (int d = 0; d < 3; d++) e->meshes[m].vel[d] = atof(argv[1 + d]);
-    e->meshes[m].moving = 1; e->meshes[m].next_reneighbor = -1; return 0; }
+    mesh_t *M = &e->meshes[m];
+    if (M->moving) return fail(e, "one fix move/mesh per mesh is supported");
+    if (argc == 4 && !strcmp(argv[0], "linear")) {
+      for (int d = 0; d < 3; d++) M->vel[d] = atof(argv[1 + d]);
+      M->moving = 1;
+    } else if (argc >= 11 && !strcmp(argv[0], "rotate")) {
+      if (strcmp(argv[1], "origin")) return fail(e, "Expected keyword 'origin'");
+      if (strcmp(argv[5], "axis")) return fail(e, "Expected keyword 'axis'");
+      if (strcmp(argv[9], "period")) return fail(e, "Expected keyword 'period'");
+      for (int d = 0; d < 3; d++) { M->rot_origin[d] = atof(argv[2 + d]); M->rot_axis[d] = atof(argv[6 + d]); }
+      { /* vectorNormalize3D vector_liggghts.h:63-70 */
+        double *v = M->rot_axis; const double norm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const double invnorm = (norm == 0.) ? 0. : 1. / norm; v[0] *= invnorm; v[1] *= invnorm; v[2] *= invnorm; }
+      M->rot_omega = 2. * M_PI / atof(argv[10]);
+      M->moving = 2;
+    } else return fail(e, "supported: 'linear vx vy vz' | 'rotate origin x y z axis x y z period T'");
+    M->next_reneighbor = -1; return 0; }
   return fail(e, "no such mesh");
 }
 int orc_add_wall_mesh(orc_engine *e, const char *id, int argc, const char *const *argv)
@@ -1125,10 +1147,53 @@ static void mesh_wall_compute(orc_engine *e, meshwall_t *W, int shearupdate)
   }
 }
 
+/* MathExtra::quatquat math_extra.h:596-602 ; MathExtraLiggghts::vec_quat_rotate math_extra_liggghts.h:435-474 */
+static void quatquat(const double *a, const double *b, double *c)
+{
+  c[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  c[1] = a[0] * b[1] + b[0] * a[1] + a[2] * b[3] - a[3] * b[2];
+  c[2] = a[0] * b[2] + b[0] * a[2] + a[3] * b[1] - a[1] * b[3];
+  c[3] = a[0] * b[3] + b[0] * a[3] + a[1] * b[2] - a[2] * b[1];
+}
+static void vec_quat_rotate(double *vec, const double *quat)
+{
+  double vecQ[4] = {0., vec[0], vec[1], vec[2]}, quatC[4] = {quat[0], -quat[1], -quat[2], -quat[3]}, temp[4], resultQ[4];
+  quatquat(quat, vecQ, temp); quatquat(temp, quatC, resultQ);
+  vec[0] = resultQ[1]; vec[1] = resultQ[2]; vec[2] = resultQ[3];
+}
+static void mesh_rotate_step(orc_engine *e, mesh_t *M)
+{ /* MeshMoverRotate::initial_integrate mesh_mover_rotation.cpp:98-125 -> FixMesh::rotate fix_mesh.cpp:747-759 ->
+   * MultiNodeMesh::rotate(dAngle,axis,p) multi_node_mesh_I.h:620-672 + TrackingMesh::rotate tracking_mesh_I.h:400-411
+   * (edgeVec, edgeNorm, surfaceNorm are the rotating element properties, surface_mesh_I.h:78-80; GeneralContainer::rotate
+   * general_container_I.h:642-651); then v_node = 0 + omegaVec x (node - reference point) */
+  const double dphi = M->rot_omega * e->dt;
+  double axisNorm[3] = {M->rot_axis[0], M->rot_axis[1], M->rot_axis[2]};
+  { const double sinv = 1. / sqrt(axisNorm[0] * axisNorm[0] + axisNorm[1] * axisNorm[1] + axisNorm[2] * axisNorm[2]);
+    axisNorm[0] = sinv * axisNorm[0]; axisNorm[1] = sinv * axisNorm[1]; axisNorm[2] = sinv * axisNorm[2]; }
+  double dQ[4]; dQ[0] = cos(dphi * 0.5); for (int i = 0; i < 3; i++) dQ[i + 1] = axisNorm[i] * sin(dphi * 0.5);
+  const double *origin = M->rot_origin;
+  const int trans = (origin[0] * origin[0] + origin[1] * origin[1] + origin[2] * origin[2]) > 0.;
+  double omegaVec[3]; for (int d = 0; d < 3; d++) omegaVec[d] = M->rot_axis[d] * M->rot_omega;
+  for (int t = 0; t < M->ntri; t++) {
+    double *c = M->center[t]; c[0] = c[1] = c[2] = 0.;
+    for (int j = 0; j < 3; j++) { double *nd = M->node[t][j];
+      if (trans) for (int d = 0; d < 3; d++) nd[d] = nd[d] - origin[d];
+      vec_quat_rotate(nd, dQ);
+      if (trans) for (int d = 0; d < 3; d++) nd[d] = nd[d] + origin[d];
+      for (int d = 0; d < 3; d++) c[d] = nd[d] + c[d]; }
+    { const double sinv = 1. / 3.; c[0] = sinv * c[0]; c[1] = sinv * c[1]; c[2] = sinv * c[2]; }
+    for (int j = 0; j < 3; j++) { vec_quat_rotate(M->edgeVec[t][j], dQ); vec_quat_rotate(M->edgeNorm[t][j], dQ); }
+    vec_quat_rotate(M->surfNorm[t], dQ);
+    for (int j = 0; j < 3; j++) { double rPA[3], vRot[3]; v3sub(M->node[t][j], origin, rPA);
+      vRot[0] = omegaVec[1] * rPA[2] - omegaVec[2] * rPA[1]; vRot[1] = omegaVec[2] * rPA[0] - omegaVec[0] * rPA[2]; vRot[2] = omegaVec[0] * rPA[1] - omegaVec[1] * rPA[0];
+      for (int d = 0; d < 3; d++) M->vnode[t][j][d] = 0. + vRot[d]; }
+  }
+}
 static void mesh_move_step(orc_engine *e)
 { /* FixMoveMesh::initial_integrate fix_move_mesh.cpp:221-238 + MeshMoverLinear::initial_integrate mesh_mover_linear.cpp:94-112
    * + MultiNodeMesh::move(vecIncremental) multi_node_mesh_I.h:502-526 */
   for (int m = 0; m < e->nmeshes; m++) { mesh_t *M = &e->meshes[m]; if (!M->moving) continue;
+    if (M->moving == 2) { mesh_rotate_step(e, M); continue; }
     double dx[3]; for (int d = 0; d < 3; d++) dx[d] = M->vel[d] * e->dt;
     for (int t = 0; t < M->ntri; t++) {
       for (int j = 0; j < 3; j++) for (int d = 0; d < 3; d++) { M->node[t][j][d] = M->node[t][j][d] + dx[d]; M->vnode[t][j][d] = 0. + M->vel[d]; }
@@ -1245,6 +1310,7 @@ static void build(orc_engine *e)
       if (in) W->cand[W->ncand++] = (int)i;
     }
   }
+  for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].moving) for (int t = 0; t < e->meshes[m].ntri; t++) tri_surf_properties(&e->meshes[m], t); /* refreshOwned */
   for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].wall >= 0) mesh_build(e, &e->meshes[m]);
   e->nbuilds++; e->ago = 0;
 }
@@ -1468,6 +1534,11 @@ int orc_download_mesh(orc_engine *e, const char *mesh_id, const char *field, voi
 {
   for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) { mesh_t *M = &e->meshes[m]; const int T = M->ntri;
     if (!strcmp(field, "nodes") && count == 9L * T) { memcpy(out, M->node, sizeof(double) * 9 * T); return 0; }
+    if (!strcmp(field, "edge_vec") && count == 9L * T) { memcpy(out, M->edgeVec, sizeof(double) * 9 * T); return 0; }
+    if (!strcmp(field, "edge_norm") && count == 9L * T) { memcpy(out, M->edgeNorm, sizeof(double) * 9 * T); return 0; }
+    if (!strcmp(field, "surf_norm") && count == 3L * T) { memcpy(out, M->surfNorm, sizeof(double) * 3 * T); return 0; }
+    if (!strcmp(field, "center") && count == 3L * T) { memcpy(out, M->center, sizeof(double) * 3 * T); return 0; }
+    if (!strcmp(field, "v_node") && count == 9L * T) { memcpy(out, M->vnode, sizeof(double) * 9 * T); return 0; }
     if (!strcmp(field, "edge_active") && count == 3L * T) { for (int k = 0; k < 3 * T; k++) ((int *)out)[k] = M->edgeActive[k / 3][k % 3]; return 0; }
     if (!strcmp(field, "corner_active") && count == 3L * T) { for (int k = 0; k < 3 * T; k++) ((int *)out)[k] = M->cornerActive[k / 3][k % 3]; return 0; }
     if (!strcmp(field, "obtuse") && count == T) { for (int k = 0; k < T; k++) ((int *)out)[k] = M->obtuse[k]; return 0; }

@@ -102,6 +102,15 @@ class Ref:
         L.ref_mesh_topology(self.h, mesh_id.encode(), nodes.ctypes.data, ea.ctypes.data, ca.ctypes.data, nn.ctypes.data)
         return {"nodes": nodes, "edge_active": ea, "corner_active": ca, "nneighs": nn}
 
+    def mesh_geometry(self, mesh_id):
+        L = self.lib
+        L.ref_mesh_ntri.argtypes = [C.c_void_p, C.c_char_p]
+        n = L.ref_mesh_ntri(self.h, mesh_id.encode())
+        ev = np.zeros((n, 3, 3)); en = np.zeros((n, 3, 3)); sn = np.zeros((n, 3)); ce = np.zeros((n, 3)); vn = np.zeros((n, 3, 3))
+        L.ref_mesh_geometry.argtypes = [C.c_void_p, C.c_char_p] + [C.c_void_p] * 5
+        L.ref_mesh_geometry(self.h, mesh_id.encode(), ev.ctypes.data, en.ctypes.data, sn.ctypes.data, ce.ctypes.data, vn.ctypes.data)
+        return {"edge_vec": ev, "edge_norm": en, "surf_norm": sn, "center": ce, "v_node": vn}
+
     def mesh_contacts(self, mesh_id):
         """mesh contact rows of fix_contact_history_mesh sorted by (tag, triangle id)"""
         L = self.lib

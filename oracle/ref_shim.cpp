@@ -83,6 +83,28 @@ int ref_mesh_ntri(void *ptr, const char *id)
   FixMeshSurface *fm = ref_find_mesh(ptr, id);
   return fm ? fm->triMesh()->sizeLocal() : -1;
 }
+// derived per-triangle geometry (surface_mesh.h:143-147,259-262) and the per-node mesh velocity "v" of fix move/mesh
+int ref_mesh_geometry(void *ptr, const char *id, double *edgeVec, double *edgeNorm, double *surfNorm, double *center, double *vnode)
+{
+  FixMeshSurface *fm = ref_find_mesh(ptr, id);
+  if (!fm) return -1;
+  TriMesh *m = fm->triMesh();
+  const int n = m->sizeLocal();
+  MultiVectorContainer<double,3,3> *en = m->prop().getElementProperty<MultiVectorContainer<double,3,3> >("edgeNorm");
+  MultiVectorContainer<double,3,3> *v = m->prop().getElementProperty<MultiVectorContainer<double,3,3> >("v");
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < 3; j++) {
+      m->edgeVec(i, j, edgeVec + 9 * (size_t)i + 3 * j);
+      for (int d = 0; d < 3; d++) {
+        edgeNorm[9 * (size_t)i + 3 * j + d] = en ? (*en)(i)[j][d] : 0.0;
+        vnode[9 * (size_t)i + 3 * j + d] = v ? (*v)(i)[j][d] : 0.0;
+      }
+    }
+    m->surfaceNorm(i, surfNorm + 3 * (size_t)i);
+    m->center(i, center + 3 * (size_t)i);
+  }
+  return n;
+}
 int ref_mesh_topology(void *ptr, const char *id, double *nodes, int *edgeActive, int *cornerActive, int *nneighs)
 {
   FixMeshSurface *fm = ref_find_mesh(ptr, id);

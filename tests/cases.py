@@ -134,6 +134,17 @@ def mesh_funnel(L, z_top, z_bot, r_top, r_bot, nseg=12):
     return np.asarray(t, np.float64)
 
 
+def mesh_drum(cx, cz, R, y0, y1, nseg=12):
+    """closed polygonal drum about the y axis through (cx, *, cz): mantle quads + two end-cap fans"""
+    t = []
+    p = lambda a, y: [cx + R * np.cos(a), y, cz + R * np.sin(a)]
+    for k in range(nseg):
+        a0, a1 = 2 * np.pi * k / nseg, 2 * np.pi * (k + 1) / nseg
+        t += _quad(p(a0, y0), p(a1, y0), p(a1, y1), p(a0, y1))
+        t += [[[cx, y0, cz], p(a0, y0), p(a1, y0)], [[cx, y1, cz], p(a1, y1), p(a0, y1)]]
+    return np.asarray(t, np.float64)
+
+
 def case_mesh(kind="box", n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdt", seed=SEED, poly=True,
               name="mesh", move=None, settings=""):
     """particles falling into triangle-mesh geometry (fix mesh/surface + fix wall/gran ... mesh)"""
@@ -156,6 +167,12 @@ def case_mesh(kind="box", n3=(4, 4, 4), model="model hertz tangential history ro
         plate = np.asarray(_quad([0.02 * L, 0.02 * L, top], [0.98 * L, 0.02 * L, top], [0.98 * L, 0.98 * L, top], [0.02 * L, 0.98 * L, top]))
         c["meshes"] = [("cad", 1, mesh_box(L, 0.9 * H, nf=2)), ("plate", 1, plate)]
         c["mesh_moves"] = [("plate", "linear 0. 0. %s" % (move if move is not None else -0.4))]
+    elif kind == "drum":    # particles inside a closed drum rotating about its (y) axis (fix move/mesh rotate)
+        cx, cz, R = 0.5 * L, 0.62 * L, 0.62 * L
+        c["x"][:, 2] += 0.22 * L
+        c["meshes"] = [("drum", 1, mesh_drum(cx, cz, R, -0.12 * L, 1.12 * L))]
+        c["mesh_moves"] = [("drum", "rotate origin %.17g 0. %.17g axis 0. 1. 0. period %s" % (cx, cz, move if move is not None else 0.25))]
+        c["lo"] = [cx - 1.1 * R, -0.2 * L, cz - 1.1 * R]; c["hi"] = [cx + 1.1 * R, 1.2 * L, cz + 1.1 * R]
     c["mesh_walls"] = [("mw", model + " mesh n_meshes %d meshes %s" % (len(c["meshes"]), " ".join(m[0] for m in c["meshes"])) + st)]
     c["hi"][2] = max(c["hi"][2], float(max(m[2][..., 2].max() for m in c["meshes"])) + 0.01, float(c["x"][:, 2].max()) + 0.01)
     return c
@@ -255,6 +272,7 @@ GOLDEN_CASES = {
     "mesh_funnel_hooke": dict(mesh="funnel", kw=dict(n3=(4, 4, 3), model="model hooke tangential history rolling_friction cdt"),
                               checkpoints=[0, 1, 10, 1500, 3000]),
     "mesh_plate_moving": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
+    "mesh_drum_rotating": dict(mesh="drum", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
     # bonded spheres (INL bond models): bonds form at step 2, stretch, some break
     # (sgn()-type bond damping makes these trajectories diverge from rounding noise within a few hundred steps: short horizons)
     "bond_linear": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history", poly=True, bond=dict(kind="bond", maxdist=2.1 * 0.003)),
