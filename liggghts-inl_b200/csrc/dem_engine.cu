@@ -523,10 +523,24 @@ extern "C" int dem_move_mesh(dem_engine *e, const char *mesh_id, int argc, const
   API_BEGIN
   if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "fix move/mesh cannot be added after setup");
   for (auto &m : e->meshes) if (m.id == mesh_id) {
-    if (argc < 1 || strcmp(argv[0], "linear")) dem_fail(e, DEM_ERR_UNSUPPORTED, "fix move/mesh style '%s' not built yet (linear)", argc ? argv[0] : "");
-    if (argc != 4) dem_fail(e, DEM_ERR_ARG, "Not enough arguments for movement type linear");
-    for (int d = 0; d < 3; d++) m.vel[d] = atof(argv[1 + d]);
-    m.moving = 1;
+    if (m.moving) dem_fail(e, DEM_ERR_UNSUPPORTED, "one fix move/mesh per mesh (superposed movers are outside the hot-path scope)");
+    if (argc >= 1 && !strcmp(argv[0], "linear")) {
+      if (argc != 4) dem_fail(e, DEM_ERR_ARG, "Not enough arguments for movement type linear");
+      for (int d = 0; d < 3; d++) m.vel[d] = atof(argv[1 + d]);
+      m.moving = 1;
+    } else if (argc >= 1 && !strcmp(argv[0], "rotate")) {  // mesh_mover_rotation.cpp:58-82
+      if (argc < 11) dem_fail(e, DEM_ERR_ARG, "Not enough arguments for movement type rotate");
+      if (strcmp(argv[1], "origin")) dem_fail(e, DEM_ERR_ARG, "Expected keyword 'origin'");
+      if (strcmp(argv[5], "axis")) dem_fail(e, DEM_ERR_ARG, "Expected keyword 'axis'");
+      if (strcmp(argv[9], "period")) dem_fail(e, DEM_ERR_ARG, "Expected keyword 'period'");
+      for (int d = 0; d < 3; d++) { m.rot_origin[d] = atof(argv[2 + d]); m.rot_axis[d] = atof(argv[6 + d]); }
+      const double norm = sqrt(m.rot_axis[0] * m.rot_axis[0] + m.rot_axis[1] * m.rot_axis[1] + m.rot_axis[2] * m.rot_axis[2]);
+      const double invnorm = (norm == 0.) ? 0. : 1. / norm;  // vectorNormalize3D, vector_liggghts.h:63-70
+      if (norm == 0.) dem_fail(e, DEM_ERR_ARG, "fix move/mesh rotate: axis = 0");
+      for (int d = 0; d < 3; d++) m.rot_axis[d] *= invnorm;
+      m.rot_omega = 2. * 3.14159265358979323846 / atof(argv[10]);
+      m.moving = 2;
+    } else dem_fail(e, DEM_ERR_UNSUPPORTED, "fix move/mesh style '%s' is outside the hot-path scope (linear, rotate)", argc ? argv[0] : "");
     return DEM_OK;
   }
   dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);
@@ -574,6 +588,15 @@ static MeshP mesh_params(dem_engine *E)
     MeshMeta &mm = M.meta[m];
     mm.atom_type = H.atom_type; mm.wall = H.wall; mm.moving = H.moving; mm.first = H.first; mm.ntri = H.ntri; mm.precision = H.precision;
     for (int d = 0; d < 3; d++) mm.vel[d] = H.vel[d];
+    if (H.moving == 2) {  // MultiNodeMesh::rotate(dAngle, axis, p), multi_node_mesh_I.h:620-640
+      const double dphi = H.rot_omega * E->dt;
+      double ax[3] = {H.rot_axis[0], H.rot_axis[1], H.rot_axis[2]};
+      const double sinv = 1. / sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+      for (int d = 0; d < 3; d++) ax[d] = sinv * ax[d];
+      mm.rot_dq[0] = cos(dphi * 0.5);
+      for (int d = 0; d < 3; d++) { mm.rot_dq[d + 1] = ax[d] * sin(dphi * 0.5); mm.rot_origin[d] = H.rot_origin[d]; mm.rot_omegavec[d] = H.rot_axis[d] * H.rot_omega; }
+      mm.rot_trans = (H.rot_origin[0] * H.rot_origin[0] + H.rot_origin[1] * H.rot_origin[1] + H.rot_origin[2] * H.rot_origin[2]) > 0.;
+    }
     if (H.wall >= 0) M.wm[m] = E->mwalls[H.wall].m;
   }
   M.overflow = E->overflow.p;
@@ -619,6 +642,13 @@ static void mesh_grid(dem_engine *E)
   if (E->grid_ready && E->any_moving) {
     CK(cudaMemcpyAsync(E->htri.data(), E->dtri.p, E->htri.size() * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    // moving meshes: edge vectors / normals / obtuse index are recomputed from the nodes at every rebuild, as the
+    // reference does (SurfaceMesh::refreshOwned); the records travel to the host for the grid anyway
+    for (size_t m = 0; m < E->meshes.size(); m++) if (E->meshes[m].moving) {
+      const MeshHost &H = E->meshes[m];
+      for (int t = 0; t < H.ntri; t++) meshhost::surf_refresh(E->htri[H.first + t]);
+      CK(cudaMemcpyAsync(E->dtri.p + H.first, E->htri.data() + H.first, (size_t)H.ntri * sizeof(TriRec), cudaMemcpyHostToDevice, st));
+    }
   }
   std::vector<int> cs, ct;
   meshhost::build_grid(E->lo, E->hi, 4.0 * E->cutneighmax, E->cutneighmax + E->skin, E->htri, E->mgorg, E->mginv, E->mgnc, cs, ct);
@@ -1818,6 +1848,16 @@ extern "C" int dem_download_mesh(dem_engine *e, const char *mesh_id, const char 
       return DEM_OK;
     }
     if (!e->mesh_ready) dem_fail(e, DEM_ERR_STATE, "mesh topology is available after setup");
+    if (f == "edge_vec" || f == "edge_norm" || f == "surf_norm" || f == "center") {
+      const int w = (f == "edge_vec" || f == "edge_norm") ? 9 : 3;
+      if (count != w * T) dem_fail(e, DEM_ERR_ARG, "%s: count must be %d*ntri", field, w);
+      std::vector<TriRec> h(T);
+      CK(cudaStreamSynchronize(e->stream));
+      CK(cudaMemcpy(h.data(), e->dtri.p + m.first, T * sizeof(TriRec), cudaMemcpyDeviceToHost));
+      for (long t = 0; t < T; t++)
+        memcpy((double *)out + w * t, f == "edge_vec" ? h[t].edgeVec : f == "edge_norm" ? h[t].edgeNorm : f == "surf_norm" ? h[t].surfNorm : h[t].center, w * sizeof(double));
+      return DEM_OK;
+    }
     const std::vector<int> *src = f == "edge_active" ? &m.edge_active : f == "corner_active" ? &m.corner_active : f == "obtuse" ? &m.obtuse : f == "nneighs" ? &m.nneighs : nullptr;
     if (!src) dem_fail(e, DEM_ERR_ARG, "unknown mesh field %s", field);
     if (count != (long)src->size()) dem_fail(e, DEM_ERR_ARG, "%s: count %ld != %ld", field, count, (long)src->size());

@@ -274,8 +274,18 @@ __global__ void __launch_bounds__(128) k_mesh_step(const StepP P, const MeshP M)
       c.wi[0] = wi.x; c.wi[1] = wi.y; c.wi[2] = wi.z;
       c.wj[0] = c.wj[1] = c.wj[2] = 0.0;
       for (int d = 0; d < 3; d++) c.vj[d] = 0.0;
-      if (mm.moving && su)  // per-node mesh velocity is zero during setup (fix_move_mesh.cpp:194-217), v_node = 0 + vel afterwards
+      if (mm.moving == 1 && su)  // per-node mesh velocity is zero during setup (fix_move_mesh.cpp:194-217), v_node = 0 + vel afterwards
         for (int d = 0; d < 3; d++) { const double vn = 0. + mm.vel[d]; c.vj[d] = (bary[0] * vn + bary[1] * vn + bary[2] * vn); }
+      else if (mm.moving == 2 && su) {  // v_node = 0 + omegaVec x (node - reference point), mesh_mover_rotation.cpp:113-124
+        double vn[3][3];
+        for (int j = 0; j < 3; j++) {
+          const double rx = T.node[3 * j] - mm.rot_origin[0], ry = T.node[3 * j + 1] - mm.rot_origin[1], rz = T.node[3 * j + 2] - mm.rot_origin[2];
+          vn[j][0] = 0. + (mm.rot_omegavec[1] * rz - mm.rot_omegavec[2] * ry);
+          vn[j][1] = 0. + (mm.rot_omegavec[2] * rx - mm.rot_omegavec[0] * rz);
+          vn[j][2] = 0. + (mm.rot_omegavec[0] * ry - mm.rot_omegavec[1] * rx);
+        }
+        for (int d = 0; d < 3; d++) c.vj[d] = (bary[0] * vn[0][d] + bary[1] * vn[1][d] + bary[2] * vn[2][d]);
+      }
       c.itype = itype; c.jtype = mm.atom_type;
       double h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
       if (wm.rec_shear >= 0) { const double4 v = *hist_rec(M, slot, wm.rec_shear, i); h[0] = v.x; h[1] = v.y; h[2] = v.z; }
@@ -296,8 +306,25 @@ __global__ void __launch_bounds__(128) k_mesh_step(const StepP P, const MeshP M)
   for (int d = 0; d < 3; d++) { P.fw[(size_t)d * P.nwcap + cidx] += F[d]; P.fw[(size_t)(3 + d) * P.nwcap + cidx] += Tq[d]; }
 }
 
-// fix move/mesh linear: node += vel*dt, center += vel*dt ; a node that moved more than skin/2 since the last
-// rebuild raises the flag (MultiNodeMesh::decideRebuild)
+// MathExtra::quatquat (math_extra.h:596-602) and MathExtraLiggghts::vec_quat_rotate (math_extra_liggghts.h:457-474),
+// same expression order (this translation unit is compiled without FMA contraction)
+__device__ __forceinline__ void quatquat(const double *a, const double *b, double *c)
+{
+  c[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  c[1] = a[0] * b[1] + b[0] * a[1] + a[2] * b[3] - a[3] * b[2];
+  c[2] = a[0] * b[2] + b[0] * a[2] + a[3] * b[1] - a[1] * b[3];
+  c[3] = a[0] * b[3] + b[0] * a[3] + a[1] * b[2] - a[2] * b[1];
+}
+__device__ __forceinline__ void vec_quat_rotate(double *vec, const double *quat)
+{
+  const double vecQ[4] = {0., vec[0], vec[1], vec[2]}, quatC[4] = {quat[0], -quat[1], -quat[2], -quat[3]};
+  double temp[4], resultQ[4];
+  quatquat(quat, vecQ, temp); quatquat(temp, quatC, resultQ);
+  vec[0] = resultQ[1]; vec[1] = resultQ[2]; vec[2] = resultQ[3];
+}
+// fix move/mesh linear: node += vel*dt, center += vel*dt ; rotate: nodes turned about the axis through the origin by the
+// per-step quaternion, center re-averaged, edge vectors / edge normals / surface normal turned by the same quaternion ;
+// a node that moved more than skin/2 since the last rebuild raises the flag (MultiNodeMesh::decideRebuild)
 __global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, double dt, double trigsq, int *flag, const int *gate, int gate_mask)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,9 +333,27 @@ __global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, doub
   if (gate && (((gate_mask & 1) && gate[0]) || ((gate_mask & 4) && gate[2]))) return;
   const int t = mm.first + q;
   TriRec &T = M.tri[t];
+  bool trig = false;
+  if (mm.moving == 2) {
+    double c[3] = {0., 0., 0.};
+    for (int j = 0; j < 3; j++) {
+      double nd[3] = {T.node[3 * j], T.node[3 * j + 1], T.node[3 * j + 2]};
+      if (mm.rot_trans) for (int d = 0; d < 3; d++) nd[d] = nd[d] - mm.rot_origin[d];
+      vec_quat_rotate(nd, mm.rot_dq);
+      if (mm.rot_trans) for (int d = 0; d < 3; d++) nd[d] = nd[d] + mm.rot_origin[d];
+      double dd[3];
+      for (int d = 0; d < 3; d++) { T.node[3 * j + d] = nd[d]; c[d] = nd[d] + c[d]; dd[d] = nd[d] - M.nodes_last[(size_t)t * 9 + 3 * j + d]; }
+      if (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2] > trigsq) trig = true;
+    }
+    const double sinv = 1. / 3.;
+    for (int d = 0; d < 3; d++) T.center[d] = sinv * c[d];
+    for (int j = 0; j < 3; j++) { vec_quat_rotate(T.edgeVec + 3 * j, mm.rot_dq); vec_quat_rotate(T.edgeNorm + 3 * j, mm.rot_dq); }
+    vec_quat_rotate(T.surfNorm, mm.rot_dq);
+    if (trig) ((volatile int *)flag)[2] = 1;
+    return;
+  }
   double dx[3];
   for (int d = 0; d < 3; d++) dx[d] = mm.vel[d] * dt;
-  bool trig = false;
   for (int j = 0; j < 3; j++) {
     double dd[3];
     for (int d = 0; d < 3; d++) { T.node[3 * j + d] = T.node[3 * j + d] + dx[d]; dd[d] = T.node[3 * j + d] - M.nodes_last[(size_t)t * 9 + 3 * j + d]; }

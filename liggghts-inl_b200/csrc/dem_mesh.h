@@ -11,6 +11,7 @@
 //   contact rows + coplanar    fix_contact_history_mesh_I.h:51-215, fix_contact_history_mesh.cpp:315-505
 //   wall force driver          fix_wall_gran.cpp:803-982, fix_wall_gran_base.h:159-367
 //   mesh motion                fix_move_mesh.cpp:221-238, mesh_mover_linear.cpp:94-112, multi_node_mesh_I.h:502-526,792-826
+//                              rotate: mesh_mover_rotation.cpp:58-125, multi_node_mesh_I.h:620-672, tracking_mesh_I.h:400-411
 #pragma once
 #include "dem_types.h"
 
@@ -25,7 +26,13 @@ struct TriRec {  // one triangle, 320 bytes: everything the contact and candidat
   int mesh;   // which `fix mesh/surface` it belongs to
 };
 
-struct MeshMeta { int atom_type, wall, moving, first, ntri; double vel[3], precision; };
+struct MeshMeta {
+  int atom_type, wall, moving, first, ntri;  // moving: 0 static, 1 `linear`, 2 `rotate`
+  double vel[3], precision;
+  // rotate: origin, omega*axis, and the per-step quaternion (cos(dphi/2), axis*sin(dphi/2)) evaluated on the host with libm
+  double rot_origin[3], rot_omegavec[3], rot_dq[4];
+  int rot_trans;  // |origin|^2 > 0 (multi_node_mesh_I.h:648)
+};
 
 struct MeshP {
   int ntri, nmesh;

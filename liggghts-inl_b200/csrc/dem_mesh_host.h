@@ -23,8 +23,9 @@ namespace dem {
 
 struct MeshHost {
   std::string id;
-  int atom_type = 1, ntri = 0, first = 0, wall = -1, moving = 0;
+  int atom_type = 1, ntri = 0, first = 0, wall = -1, moving = 0;  // moving: 0 static, 1 linear, 2 rotate
   double vel[3] = {0, 0, 0};
+  double rot_origin[3] = {0, 0, 0}, rot_axis[3] = {0, 0, 1}, rot_omega = 0.;  // fix move/mesh rotate (axis normalised)
   double curvature = 1. - 0.00001, precision = 1e-8;  // surface_mesh.h:61, multi_node_mesh.h:59
   std::vector<double> nodes;                          // [ntri][3][3] as given by the caller
   std::vector<int> edge_active, corner_active, obtuse, nneighs;  // read-back for tests (dem_download_mesh)
@@ -58,6 +59,25 @@ inline void geometry(const double *nd, TriRec &T)
   cross(T.edgeVec, T.edgeVec + 3, T.surfNorm);
   sdiv(T.surfNorm, mag(T.surfNorm));
   for (int i = 0; i < 3; i++) { double *en = T.edgeNorm + 3 * i; cross(T.edgeVec + 3 * i, T.surfNorm, en); sdiv(en, mag(en)); }
+}
+
+// SurfaceMesh::recalcLocalSurfProperties (surface_mesh_I.h:187-222): what the reference recomputes from the nodes at every
+// setup and, for moving meshes, at every neighbour rebuild (fix_mesh.cpp:491-575 -> pbcExchangeBorders -> refreshOwned)
+inline void surf_refresh(TriRec &T)
+{
+  const double *nd = T.node;
+  for (int i = 0; i < 3; i++) {
+    double *e = T.edgeVec + 3 * i;
+    sub(nd + 3 * ((i + 1) % 3), nd + 3 * i, e);
+    T.edgeLen[i] = mag(e);
+    sdiv(e, T.edgeLen[i]);
+  }
+  cross(T.edgeVec, T.edgeVec + 3, T.surfNorm);
+  sdiv(T.surfNorm, mag(T.surfNorm));
+  for (int i = 0; i < 3; i++) { double *en = T.edgeNorm + 3 * i; cross(T.edgeVec + 3 * i, T.surfNorm, en); sdiv(en, mag(en)); }
+  int ob = -1;
+  for (int i = 0; i < 3; i++) ob = dot(T.edgeVec + 3 * i, T.edgeVec + 3 * ((i + 2) % 3)) > 0. ? i : -1;
+  T.flags = (T.flags & ~3) | ((ob + 1) & 3);
 }
 
 struct UF {

@@ -63,10 +63,11 @@ def test_engine_matches_oracle_bed(kw):
     ("roof", dict(n3=(9, 9, 8), model="model hertz tangential history rolling_friction epsd")),
     ("funnel", dict(n3=(9, 9, 7))),
     ("plate", dict(n3=(8, 8, 6), model="model hooke tangential history rolling_friction epsd2")),
+    ("drum", dict(n3=(8, 8, 6), model="model hertz tangential history rolling_friction epsd", move=0.2)),
 ])
 def test_mesh_walls_match_oracle(kind, kw):
-    """~700 particles in triangle-mesh geometry, 3000 steps incl. rebuilds (and a moving plate): mesh contact rows
-    (particle, triangle) bit-exact, topology flags identical, forces to tolerance"""
+    """~700 particles in triangle-mesh geometry, 3000 steps incl. rebuilds (a moving plate, a rotating drum): mesh contact
+    rows (particle, triangle) bit-exact, topology flags identical, moved mesh geometry bit-exact, forces to tolerance"""
     c = cases.case_mesh(kind=kind, name="mesh_" + kind, seed=11, **kw)
     rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
     got = cases.apply(c, gpu_engine())
@@ -80,10 +81,15 @@ def test_mesh_walls_match_oracle(kind, kw):
                 for f in ("edge_active", "corner_active", "obtuse", "nneighs"):
                     assert np.array_equal(got.mesh_field(mid, f, len(nodes)), ref.mesh_field(mid, f, len(nodes))), (mid, f)
         done = cp
+        for mid, text in c.get("mesh_moves", []):  # moved / rotated geometry: same arithmetic as the reference -> bit-exact
+            nt = len([m for m in c["meshes"] if m[0] == mid][0][2])
+            for f in ("nodes", "center", "edge_vec", "edge_norm", "surf_norm"):
+                assert np.array_equal(got.mesh_field(mid, f, nt), ref.mesh_field(mid, f, nt)), (mid, f, cp)
         parity.compare_snapshot(cases.snapshot(got, c), cases.snapshot(ref, c), rmass, tol=tol_at(cp) if cp <= 500 else 1e-3, label="%s@%d" % (kind, cp))
         assert got.stats().nbuilds == ref.stats().nbuilds
         if cp == 3000:
-            assert len(cases.snapshot(got, c)["mesh_%s_tag" % c["meshes"][-1][0]]) + len(cases.snapshot(got, c)["mesh_cad_tag"]) > 0, "no mesh contact was exercised"
+            sg = cases.snapshot(got, c)
+            assert sum(len(sg["mesh_%s_tag" % m[0]]) for m in c["meshes"]) > 0, "no mesh contact was exercised"
     got.close(); ref.close()
 
 
