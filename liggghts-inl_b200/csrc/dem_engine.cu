@@ -550,7 +550,6 @@ extern "C" int dem_add_wall_mesh(dem_engine *e, const char *id, int argc, const 
 {
   API_BEGIN
   if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "walls cannot be added after setup");
-  if (e->nranks > 1) dem_fail(e, DEM_ERR_UNSUPPORTED, "mesh walls on more than one GPU are not built yet");
   dem_engine::MeshWall W; W.id = id;
   parse_model_select(e, argc, argv, W.m);
   if (W.m.cohesion) dem_fail(e, DEM_ERR_UNSUPPORTED, "bond models on walls are outside the hot-path scope");
@@ -1240,11 +1239,15 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
       M.periodic = E->periodic[d]; M.wrap_lo = E->lo[d]; M.wrap_hi = E->hi[d]; M.prd = E->prd[d];
       M.density = E->density.p; M.whist = E->whist.p;
       if (hist) { M.nbr = Lold.nbr.p; M.numneigh = Lold.numneigh.p; M.ptag = Lold.ptag.p; M.hist = Lold.hist.p; M.hslots = Lold.hslots; M.maxk = Lold.maxk; }
-      const int ss = 16 + E->nwrows + H * (1 + 4 * hrec), sr = 16 + E->nwrows + Hr * (1 + 4 * hrec);
+      const bool meshrows = E->mesh_ready && have_mesh_walls(E);
+      const int mblock = meshrows ? E->mslots * (1 + 4 * E->mhrec) : 0;
+      if (meshrows) { M.mslots = E->mslots; M.mhrec = E->mhrec; }
+      const int ss = 16 + E->nwrows + mblock + H * (1 + 4 * hrec), sr = 16 + E->nwrows + mblock + Hr * (1 + 4 * hrec);
       if (nsend[side]) {
         E->migs.ensure(E, (size_t)nsend[side] * ss);
         M.n = nsend[side]; M.stride = ss; M.hmax = H; M.list = lists[side].p; M.buf = E->migs.p;
         M.xr = E->xr[c].p; M.vm = E->vm[c].p; M.wt = E->wt[c].p; M.xh = E->xh.p; M.tag = E->tag.p;
+        if (meshrows) { M.mint = E->mint[E->mcur].p; M.mhist = E->mhist[E->mcur].p; }
         k_mig_pack<<<GRID(M.n, 128), 128, 0, st>>>(M);
         E->launches++;
       }
@@ -1264,6 +1267,7 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
         M.n = nrecv; M.stride = sr; M.hmax = Hr; M.buf = E->migr.p; M.cap = E->cap;
         M.xr = E->xr[E->cur].p; M.vm = E->vm[E->cur].p; M.wt = E->wt[E->cur].p; M.xh = E->xh.p; M.tag = E->tag.p;
         M.density = E->density.p; M.whist = E->whist.p;
+        if (meshrows) { M.mint = E->mint[E->mcur].p; M.mhist = E->mhist[E->mcur].p; }  // (re-strided if the capacity grew)
         k_mig_unpack<<<GRID(nrecv, 128), 128, 0, st>>>(M, ncur);
         E->launches++;
         ncur += nrecv;

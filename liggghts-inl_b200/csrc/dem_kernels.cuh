@@ -724,7 +724,8 @@ __global__ void __launch_bounds__(256) k_cell_ranges_idx(int n, const int *gorde
 // ---- particle migration between bricks (CommBrick::exchange, comm_brick.cpp:732-860, with the contact history
 // of fix_contact_history.cpp:508-555 travelling with the particle).  One fixed-stride record per migrant:
 // [0..11] the three 32-byte records, [12] tag, [13] density, [14] wall-history valid bits, [15] nh,
-// [16..16+nwrows) wall history, then nh x (partner tag, hrec x 4 history doubles).
+// [16..16+nwrows) wall history, then the mesh contact rows (mslots x (partner triangle, mhrec x 4 history doubles),
+// fix_contact_history_mesh.cpp pack_exchange), then nh x (partner tag, hrec x 4 history doubles).
 struct MigP {
   int n, stride, nwrows, hrec, hmax, cap, lcap, dim;
   double wrap_lo, wrap_hi, prd;  // periodic wrap applied by the sender
@@ -733,6 +734,7 @@ struct MigP {
   double4 *xr, *vm, *wt, *xh;
   int *tag; double *density; double *whist;
   unsigned *nbr; int *numneigh; int *ptag; double4 *hist; int hslots, maxk;
+  int mslots, mhrec; int *mint; double4 *mhist;  // mesh contact rows (row stride = cap)
   double *buf;
 };
 __global__ void __launch_bounds__(128) k_mig_pack(const MigP M)
@@ -754,10 +756,19 @@ __global__ void __launch_bounds__(128) k_mig_pack(const MigP M)
   b[12] = (double)M.tag[i]; b[13] = M.density[i];
   b[14] = (double)(((unsigned)(__double_as_longlong(M.xh[i].w) & 0xffffffffLL)) >> 16);
   for (int r = 0; r < M.nwrows; r++) b[16 + r] = M.whist[(size_t)r * M.cap + i];
+  const int mblock = M.mslots * (1 + 4 * M.mhrec);
+  for (int s = 0; s < M.mslots; s++) {
+    double *e = b + 16 + M.nwrows + (size_t)s * (1 + 4 * M.mhrec);
+    e[0] = (double)M.mint[(size_t)(1 + s) * M.cap + i];
+    for (int r = 0; r < M.mhrec; r++) {
+      const double4 h = M.mhist[(size_t)(s * M.mhrec + r) * M.cap + i];
+      e[1 + 4 * r] = h.x; e[2 + 4 * r] = h.y; e[3 + 4 * r] = h.z; e[4 + 4 * r] = h.w;
+    }
+  }
   int nh = 0;
   if (M.nbr) {
     const int nn = M.numneigh[i] & 0xffff;
-    double *hb = b + 16 + M.nwrows;
+    double *hb = b + 16 + M.nwrows + mblock;
     for (int k = 0; k < nn; k++) {
       const unsigned wd = M.nbr[(size_t)k * M.lcap + i];
       if (!(wd & NBR_HIST) || nh >= M.hmax) continue;
@@ -787,9 +798,16 @@ __global__ void __launch_bounds__(128) k_mig_unpack(const MigP M, int base)
   M.tag[i] = (int)b[12]; M.density[i] = b[13];
   M.xh[i] = make_double4(0., 0., 0., __longlong_as_double((long long)(((unsigned)b[14]) << 16)));
   for (int r = 0; r < M.nwrows; r++) M.whist[(size_t)r * M.cap + i] = b[16 + r];
+  const int mblock = M.mslots * (1 + 4 * M.mhrec);
+  if (M.mslots) M.mint[i] = 0;  // candidate count: rebuilt by k_mesh_cand
+  for (int s = 0; s < M.mslots; s++) {
+    const double *e = b + 16 + M.nwrows + (size_t)s * (1 + 4 * M.mhrec);
+    M.mint[(size_t)(1 + s) * M.cap + i] = (int)e[0];
+    for (int r = 0; r < M.mhrec; r++) M.mhist[(size_t)(s * M.mhrec + r) * M.cap + i] = make_double4(e[1 + 4 * r], e[2 + 4 * r], e[3 + 4 * r], e[4 + 4 * r]);
+  }
   if (M.nbr) {
     const int nh = (int)b[15];
-    const double *hb = b + 16 + M.nwrows;
+    const double *hb = b + 16 + M.nwrows + mblock;
     for (int k = 0; k < nh; k++) {
       const double *e = hb + (size_t)k * (1 + 4 * M.hrec);
       M.ptag[(size_t)k * M.lcap + i] = (int)e[0];

@@ -42,6 +42,11 @@ def gather_snapshot(eng, c, rank, world):
     fl = np.concatenate([o["pair_flag"] for o in out]); hs = np.concatenate([o["pair_hist"] for o in out])
     o2 = np.lexsort((hi, lo))
     merged.update(pair_lo=lo[o2], pair_hi=hi[o2], pair_flag=fl[o2], pair_hist=hs[o2])
+    for mid, mtype, nodes in c.get("meshes", []):  # mesh contact rows live with the owning rank: merge, order by (tag, triangle)
+        mt = np.concatenate([o["mesh_%s_tag" % mid] for o in out]); mi = np.concatenate([o["mesh_%s_tri" % mid] for o in out])
+        mh = np.concatenate([o["mesh_%s_hist" % mid] for o in out])
+        o3 = np.lexsort((mi, mt))
+        merged["mesh_%s_tag" % mid] = mt[o3]; merged["mesh_%s_tri" % mid] = mi[o3]; merged["mesh_%s_hist" % mid] = mh[o3]
     return merged
 
 
@@ -52,10 +57,16 @@ def main():
     torch.cuda.set_device(local)
     ok = True
     for kw, steps in ((dict(n3=(16, 8, 8), poly=True, periodic=(1, 1, 0), model="model hertz tangential history rolling_friction epsd2", ntypes=2), (0, 1, 10, 300, 900)),
-                      (dict(n3=(14, 6, 6), model="model hertz tangential history rolling_friction cdt"), (0, 1, 10, 400))):
-        c = cases.case_box(name="multi", seed=11, **kw)
+                      (dict(n3=(14, 6, 6), model="model hertz tangential history rolling_friction cdt"), (0, 1, 10, 400)),
+                      # triangle-mesh walls on several GPUs: triangles replicated, mesh contact rows migrate with their particle
+                      (dict(mesh="box", n3=(14, 6, 4)), (0, 1, 10, 400, 1200)),
+                      (dict(mesh="plate", n3=(12, 6, 4), model="model hertz tangential history rolling_friction epsd"), (0, 1, 10, 400, 1500)),
+                      (dict(mesh="drum", n3=(10, 10, 5), move=0.2), (0, 1, 10, 600, 1800))):
+        kw = dict(kw)
+        mesh = kw.pop("mesh", None)
+        c = cases.case_mesh(kind=mesh, name="multi_" + mesh, seed=11, **kw) if mesh else cases.case_box(name="multi", seed=11, **kw)
         # give the particles a drift along x so that they migrate between the bricks
-        c["v"][:, 0] += 2.5
+        c["v"][:, 0] += 2.5 if not mesh else 0.8
         rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
         eng = make_engine(rank, world, local)
         eng.box(c["lo"], c["hi"], c["periodic"])
@@ -72,12 +83,14 @@ def main():
             nl0 = nl0 or nls
             if rank == 0:
                 ref.setup(); ref.run(cp - done)
-                tol = 1e-10 if cp <= 10 else (1e-6 if cp <= 400 else 1e-4)
+                tol = 1e-10 if cp <= 10 else (1e-6 if cp <= 400 else (1e-4 if not mesh else 1e-3))
                 errs = parity.compare_snapshot(snap, cases.snapshot(ref, c), rmass, tol=tol, label="multi@%d" % cp)
                 print("world %d step %4d ok: nlocal per rank %s f err %.2e" % (world, cp, nls, errs["f"]), flush=True)
             done = cp
         if not kw.get("periodic") and rank == 0:
             assert nls != nl0, "no particle migrated between the bricks in the drift case"
+        if mesh and rank == 0:
+            assert sum(len(snap["mesh_%s_tag" % m[0]]) for m in c["meshes"]) > 0, "no mesh contact was exercised"
         eng.close()
     dist.barrier()
     if rank == 0:
