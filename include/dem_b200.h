@@ -149,6 +149,27 @@ typedef struct dem_stats {
 } dem_stats;
 int dem_get_stats(dem_engine *e, dem_stats *out);
 
+/* ---- input-script front end (csrc/dem_deck.cpp): the reference's embedding API
+ *   void lammps_open_no_mpi(int, char **, void **)   src/library.cpp:85-100   -> dem_create + dem_deck_open
+ *   void lammps_file(void *, char *)                 src/library.cpp:130-140  -> dem_deck_file
+ *   char *lammps_command(void *, char *)             src/library.cpp:142-160  -> dem_deck_command
+ *   void lammps_close(void *)                        src/library.cpp:118-128  -> dem_deck_close + dem_destroy
+ * A deck wraps an engine the caller created and still owns.  Commands on the particle hot path (units, atom_style,
+ * boundary, newton, communicate, processors, region block, create_box, read_data, neighbor, neigh_modify, group id|type,
+ * fix property/global | gravity | wall/gran primitive|mesh | mesh/surface* file [type|scale|move|rotate|curvature|
+ * precision] | move/mesh linear|rotate | freeze | nve/sphere, pair_style gran, pair_coeff, timestep, variable NAME
+ * equal|string|index VALUE, run N [upto]) become the ABI calls above in deck order; output-only commands (thermo*,
+ * compute, dump*, ...) are accepted and reported by dem_deck_warnings; everything else returns DEM_ERR_UNSUPPORTED.
+ * Errors carry the reference's message texts where one exists (src/input.cpp, src/read_data.cpp). */
+typedef struct dem_deck_handle dem_deck;
+int dem_deck_open(dem_deck **out, dem_engine *e);
+void dem_deck_close(dem_deck *d);
+int dem_deck_command(dem_deck *d, const char *line);
+int dem_deck_file(dem_deck *d, const char *path);
+const char *dem_deck_last_error(const dem_deck *d);
+const char *dem_deck_warnings(const dem_deck *d);
+long dem_deck_ntimestep(const dem_deck *d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,580 @@
+// dem_deck.cpp -- input-script front end of the B200 DEM engine: the reference's `lammps_open / lammps_command /
+// lammps_file / lammps_close` (src/library.cpp:70-180) and the command grammar of src/input.cpp for the commands that
+// configure the particle hot path.  Pure host C++ on top of the PUBLIC C ABI only (include/dem_b200.h):
+// every deck command becomes the ABI call that replaces the reference object it would have created.
+//
+//   Input::file / Input::one / Input::parse / Input::substitute     src/input.cpp:160-560
+//   read_data (header, Atoms, Velocities of atom_style sphere)        src/read_data.cpp:120-560, atom_vec_sphere.cpp:980-1060
+//   region block, create_box                                           src/region_block.cpp:40-110, create_box.cpp:40-130
+//   group id|type                                                      src/group.cpp:90-260
+//   fix mesh/surface file ... [move|rotate|scale]                      src/fix_mesh.cpp:95-240,600-690, input_mesh_tri.cpp:308-591
+//   run N [upto]                                                       src/run.cpp:40-130
+// Commands that only produce output (thermo, dump, compute, ...) are accepted and listed by dem_deck_warnings();
+// anything else that is valid reference syntax but outside the hot path returns DEM_ERR_UNSUPPORTED.
+//
+// The same source builds the test-only oracle binding when DEM_DECK_ORACLE is defined (tests/: the entry points are then
+// named orc_deck_* and drive the CPU oracle's orc_* functions) so that the parser is covered without a GPU.
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#ifdef DEM_DECK_ORACLE
+extern "C" {
+typedef struct orc_engine dem_engine;
+#define API(n) orc_##n
+#define DECK(n) orc_deck_##n
+#else
+#include "../../include/dem_b200.h"
+#define API(n) dem_##n
+#define DECK(n) dem_deck_##n
+extern "C" {
+#endif
+#ifdef DEM_DECK_ORACLE
+const char *API(last_error)(const dem_engine *e);
+int API(set_units)(dem_engine *e, const char *style);
+int API(set_box)(dem_engine *e, const double lo[3], const double hi[3], const int periodic[3]);
+int API(set_ntypes)(dem_engine *e, int ntypes);
+int API(set_processors)(dem_engine *e, int px, int py, int pz);
+int API(set_neighbor)(dem_engine *e, double skin, int every, int delay, int check);
+int API(set_timestep)(dem_engine *e, double dt);
+int API(set_property)(dem_engine *e, const char *name, const char *kind, const double *values, int n);
+int API(set_pair_style)(dem_engine *e, int argc, const char *const *argv);
+int API(add_wall_primitive)(dem_engine *e, const char *id, int argc, const char *const *argv);
+int API(add_mesh)(dem_engine *e, const char *id, int atom_type, const double *nodes9, long ntri, int argc, const char *const *argv);
+int API(move_mesh)(dem_engine *e, const char *mesh_id, int argc, const char *const *argv);
+int API(add_wall_mesh)(dem_engine *e, const char *id, int argc, const char *const *argv);
+int API(set_gravity)(dem_engine *e, double magnitude, const double dir[3]);
+int API(set_freeze)(dem_engine *e, int groupbit);
+int API(set_integrate)(dem_engine *e, int groupbit);
+int API(upload_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
+                          const double *omega, const double *radius, const double *density);
+int API(setup)(dem_engine *e);
+int API(run)(dem_engine *e, long nsteps);
+#endif
+}
+
+namespace {
+
+enum { OK = 0, ERR_ARG = -1, ERR_UNSUPPORTED = -2, ERR_STATE = -3 };
+
+struct Deck {
+  dem_engine *e = nullptr;
+  std::string err, warnings, dir;  // dir: directory of the deck file (relative paths in read_data / mesh files)
+  std::map<std::string, std::string> vars;
+  struct Region { double lo[3], hi[3]; };
+  std::map<std::string, Region> regions;
+  std::map<std::string, int> groups;  // name -> mask bit
+  std::map<std::string, std::string> ignored_fixes;
+  // box / particles held until the first `run`
+  bool have_box = false, box_sent = false, uploaded = false, newton_off = false, have_pair = false;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  int periodic[3] = {0, 0, 0}, ntypes = 0;
+  double skin = 0.0; int every = 1, delay = 10, check = 1;  // neighbor.cpp:100-130 defaults (delay 10, every 1, check yes)
+  std::vector<int> tag, type, mask;
+  std::vector<double> x, v, omega, radius, density;
+  long ntimestep = 0;
+};
+
+int fail(Deck *d, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  d->err = buf;
+  return code;
+}
+// an ABI call failed: keep its status, take the engine's message
+int engine_failed(Deck *d, int rc) { d->err = API(last_error)(d->e); return rc; }
+#define TRY(call) do { const int rc_ = (call); if (rc_ != 0) return engine_failed(d, rc_); } while (0)
+
+bool is_number(const std::string &s) { if (s.empty()) return false; char *end = nullptr; strtod(s.c_str(), &end); return end && *end == 0; }
+// Force::numeric / inumeric (force.cpp:740-800): the whole token must be a number
+int numeric(Deck *d, const std::string &s, double &out)
+{
+  if (!is_number(s)) return fail(d, ERR_ARG, "Expected floating point parameter in input script or data file: '%s'", s.c_str());
+  out = atof(s.c_str()); return OK;
+}
+int inumeric(Deck *d, const std::string &s, int &out)
+{
+  if (s.empty()) return fail(d, ERR_ARG, "Expected integer parameter in input script or data file");
+  for (size_t k = 0; k < s.size(); k++) if (!(isdigit((unsigned char)s[k]) || (k == 0 && (s[k] == '-' || s[k] == '+')))) return fail(d, ERR_ARG, "Expected integer parameter in input script or data file: '%s'", s.c_str());
+  out = atoi(s.c_str()); return OK;
+}
+
+// Input::substitute (input.cpp:430-520): ${name} and $x
+int substitute(Deck *d, std::string &line)
+{
+  std::string out; bool quote = false;
+  for (size_t k = 0; k < line.size(); k++) {
+    const char c = line[k];
+    if (c == '"') quote = !quote;
+    if (c == '$' && !quote && k + 1 < line.size()) {
+      std::string name; size_t end;
+      if (line[k + 1] == '{') { end = line.find('}', k + 2); if (end == std::string::npos) return fail(d, ERR_ARG, "Invalid variable name"); name = line.substr(k + 2, end - k - 2); }
+      else { name = line.substr(k + 1, 1); end = k + 1; }
+      auto it = d->vars.find(name);
+      if (it == d->vars.end()) return fail(d, ERR_ARG, "Substitution for illegal variable '%s'", name.c_str());
+      out += it->second; k = end; continue;
+    }
+    out += c;
+  }
+  line = out; return OK;
+}
+// Input::parse (input.cpp:330-420): '#' starts a comment outside quotes; words split on whitespace, "..." kept as one word
+std::vector<std::string> split(std::string line)
+{
+  bool quote = false;
+  for (size_t k = 0; k < line.size(); k++) { if (line[k] == '"') quote = !quote; if (line[k] == '#' && !quote) { line.resize(k); break; } }
+  std::vector<std::string> w; std::string cur; quote = false; bool have = false;
+  for (char c : line) {
+    if (c == '"') { quote = !quote; have = true; continue; }
+    if (!quote && isspace((unsigned char)c)) { if (have) { w.push_back(cur); cur.clear(); have = false; } continue; }
+    cur += c; have = true;
+  }
+  if (have) w.push_back(cur);
+  return w;
+}
+std::string resolve(const Deck *d, const std::string &path)
+{
+  if (path.empty() || path[0] == '/' || d->dir.empty()) return path;
+  std::ifstream probe(path.c_str());
+  return probe.good() ? path : d->dir + "/" + path;
+}
+std::vector<const char *> cptrs(const std::vector<std::string> &w, size_t from)
+{
+  std::vector<const char *> a;
+  for (size_t k = from; k < w.size(); k++) a.push_back(w[k].c_str());
+  return a;
+}
+
+// ---- read_data: header + Atoms + Velocities of atom_style sphere (id type diameter density x y z [ix iy iz]; id vx vy vz wx wy wz)
+int read_data(Deck *d, const std::string &path)
+{
+  std::ifstream f(resolve(d, path).c_str());
+  if (!f.good()) return fail(d, ERR_ARG, "Cannot open file %s", path.c_str());
+  std::string line;
+  std::getline(f, line);  // title
+  long natoms = -1; int ntypes = -1; double lo[3], hi[3]; bool hb[3] = {false, false, false};
+  std::string section;
+  auto strip = [](std::string s) { const size_t h = s.find('#'); if (h != std::string::npos) s.resize(h); return s; };
+  while (std::getline(f, line)) {
+    const std::vector<std::string> w = split(strip(line));
+    if (w.empty()) continue;
+    if (w.size() == 2 && w[1] == "atoms") natoms = atol(w[0].c_str());
+    else if (w.size() == 3 && w[1] == "atom" && w[2] == "types") ntypes = atoi(w[0].c_str());
+    else if (w.size() == 4 && w[2] == "xlo" && w[3] == "xhi") { lo[0] = atof(w[0].c_str()); hi[0] = atof(w[1].c_str()); hb[0] = true; }
+    else if (w.size() == 4 && w[2] == "ylo" && w[3] == "yhi") { lo[1] = atof(w[0].c_str()); hi[1] = atof(w[1].c_str()); hb[1] = true; }
+    else if (w.size() == 4 && w[2] == "zlo" && w[3] == "zhi") { lo[2] = atof(w[0].c_str()); hi[2] = atof(w[1].c_str()); hb[2] = true; }
+    else if (w.size() >= 2 && (w[1] == "bonds" || w[1] == "angles" || w[1] == "dihedrals" || w[1] == "impropers" || w[1] == "bond" || w[1] == "angle" || w[1] == "extra")) continue;
+    else if (isalpha((unsigned char)w[0][0])) { section = w[0]; break; }
+    else return fail(d, ERR_ARG, "Unknown identifier in data file: %s", line.c_str());
+  }
+  if (natoms < 0) return fail(d, ERR_ARG, "No atoms in data file");
+  if (!d->have_box) {
+    if (!(hb[0] && hb[1] && hb[2]) || ntypes < 1) return fail(d, ERR_ARG, "data file header needs 'atom types' and the box bounds");
+    for (int k = 0; k < 3; k++) { d->lo[k] = lo[k]; d->hi[k] = hi[k]; }
+    d->ntypes = ntypes; d->have_box = true;
+  }
+  const size_t base = d->tag.size();
+  std::map<int, size_t> index;
+  bool got_atoms = false;
+  while (!section.empty()) {
+    const std::string sec = section; section.clear();
+    long nread = 0;
+    if (sec == "Atoms") {
+      d->tag.resize(base + natoms); d->type.resize(base + natoms); d->mask.resize(base + natoms, 1);
+      d->x.resize(3 * (base + natoms)); d->v.resize(3 * (base + natoms), 0.0); d->omega.resize(3 * (base + natoms), 0.0);
+      d->radius.resize(base + natoms); d->density.resize(base + natoms);
+    } else if (sec != "Velocities") return fail(d, ERR_UNSUPPORTED, "data file section '%s' is outside the hot-path scope", sec.c_str());
+    while (nread < natoms && std::getline(f, line)) {
+      const std::vector<std::string> w = split(strip(line));
+      if (w.empty()) continue;
+      if (sec == "Atoms") {
+        if (w.size() != 7 && w.size() != 10) return fail(d, ERR_ARG, "Incorrect atom format in data file");
+        const size_t i = base + nread;
+        d->tag[i] = atoi(w[0].c_str()); d->type[i] = atoi(w[1].c_str()); d->mask[i] = 1;
+        d->radius[i] = 0.5 * atof(w[2].c_str());  // atom_vec_sphere.cpp data_atom: radius = 0.5 * diameter
+        d->density[i] = atof(w[3].c_str());
+        for (int k = 0; k < 3; k++) d->x[3 * i + k] = atof(w[4 + k].c_str());
+        if (d->tag[i] <= 0) return fail(d, ERR_ARG, "Invalid atom ID in Atoms section of data file");
+        if (d->type[i] <= 0 || d->type[i] > d->ntypes) return fail(d, ERR_ARG, "Invalid atom type in Atoms section of data file");
+        if (!(d->radius[i] >= 0.0) || !(d->density[i] > 0.0)) return fail(d, ERR_ARG, "Invalid radius or density in Atoms section of data file");
+        index[d->tag[i]] = i;
+      } else {
+        if (!got_atoms) return fail(d, ERR_ARG, "Must read Atoms before Velocities");
+        if (w.size() != 7) return fail(d, ERR_ARG, "Incorrect velocity format in data file");
+        auto it = index.find(atoi(w[0].c_str()));
+        if (it == index.end()) return fail(d, ERR_ARG, "Invalid atom ID in Velocities section of data file");
+        for (int k = 0; k < 3; k++) { d->v[3 * it->second + k] = atof(w[1 + k].c_str()); d->omega[3 * it->second + k] = atof(w[4 + k].c_str()); }
+      }
+      nread++;
+    }
+    if (nread != natoms) return fail(d, ERR_ARG, "Unexpected end of data file");
+    if (sec == "Atoms") got_atoms = true;
+    while (std::getline(f, line)) { const std::vector<std::string> w = split(strip(line)); if (!w.empty()) { section = w[0]; break; } }
+  }
+  if (!got_atoms) return fail(d, ERR_ARG, "No Atoms section in data file");
+  return OK;
+}
+
+// ---- STL reader: InputMeshTri::meshtrifile_stl (ASCII, vertices by atof) and meshtrifile_stl_binary, input_mesh_tri.cpp:308-591
+int read_stl(Deck *d, const std::string &path, std::vector<double> &nodes)
+{
+  const std::string p = resolve(d, path);
+  std::ifstream f(p.c_str(), std::ios::binary);
+  if (!f.good()) return fail(d, ERR_ARG, "Cannot open mesh file %s", path.c_str());
+  std::string first;
+  std::getline(f, first);
+  const std::vector<std::string> fw = split(first);
+  const bool ascii = !fw.empty() && fw[0].compare(0, 5, "solid") == 0;
+  nodes.clear();
+  if (ascii) {
+    std::string line; int nv = 0; bool infacet = false;
+    while (std::getline(f, line)) {
+      const std::vector<std::string> w = split(line);
+      if (w.empty()) continue;
+      if (w[0] == "facet") { if (infacet) return fail(d, ERR_ARG, "Corrupt or unknown STL file: New facet begins without closing prior facet."); infacet = true; nv = 0; }
+      else if (w[0] == "vertex") {
+        if (!infacet || w.size() < 4) return fail(d, ERR_ARG, "Corrupt or unknown STL file: Vertex found outside a loop.");
+        if (nv == 3) return fail(d, ERR_ARG, "Corrupt or unknown STL file: Found more than 3 vertices in a facet (only triangular meshes supported).");
+        for (int k = 0; k < 3; k++) nodes.push_back(atof(w[1 + k].c_str()));
+        nv++;
+      } else if (w[0] == "endfacet") { if (!infacet || nv != 3) return fail(d, ERR_ARG, "Corrupt or unknown STL file: End of facet found, but no begin."); infacet = false; }
+    }
+  } else {
+    f.clear(); f.seekg(80, std::ios::beg);
+    unsigned int nf = 0;
+    f.read((char *)&nf, 4);
+    for (unsigned int t = 0; t < nf; t++) {
+      float rec[12]; unsigned short attr;
+      f.read((char *)rec, 48); f.read((char *)&attr, 2);
+      if (!f.good()) return fail(d, ERR_ARG, "Corrupt STL file: Error in reading binary STL file.");
+      for (int k = 3; k < 12; k++) nodes.push_back((double)rec[k]);
+    }
+  }
+  if (nodes.empty()) return fail(d, ERR_ARG, "mesh file %s holds no triangles", path.c_str());
+  return OK;
+}
+// load-time transforms of `fix mesh/surface` in keyword order: FixMesh::moveMesh / rotateMesh / scaleMesh (fix_mesh.cpp:600-690)
+// -> MultiNodeMesh::move / rotate(dAngle, axis, p = 0) / scale (multi_node_mesh_I.h:470-700), same floating-point expressions
+void quatquat(const double *a, const double *b, double *c)
+{
+  c[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  c[1] = a[0] * b[1] + b[0] * a[1] + a[2] * b[3] - a[3] * b[2];
+  c[2] = a[0] * b[2] + b[0] * a[2] + a[3] * b[1] - a[1] * b[3];
+  c[3] = a[0] * b[3] + b[0] * a[3] + a[1] * b[2] - a[2] * b[1];
+}
+void mesh_rotate(std::vector<double> &nodes, const double axis[3], double phi_deg)
+{
+  const double dAngle = phi_deg * 3.14159265 / 180.0;  // FixMesh::rotateMesh uses this literal (fix_mesh.cpp:656)
+  double ax[3] = {axis[0], axis[1], axis[2]};
+  const double sinv = 1. / std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  for (int k = 0; k < 3; k++) ax[k] = sinv * ax[k];
+  double q[4] = {std::cos(dAngle * 0.5), ax[0] * std::sin(dAngle * 0.5), ax[1] * std::sin(dAngle * 0.5), ax[2] * std::sin(dAngle * 0.5)};
+  const double qc[4] = {q[0], -q[1], -q[2], -q[3]};
+  for (size_t n = 0; n + 2 < nodes.size(); n += 3) {
+    const double vq[4] = {0., nodes[n], nodes[n + 1], nodes[n + 2]};
+    double t[4], r[4];
+    quatquat(q, vq, t); quatquat(t, qc, r);
+    nodes[n] = r[1]; nodes[n + 1] = r[2]; nodes[n + 2] = r[3];
+  }
+}
+
+int first_run_prepare(Deck *d)
+{
+  if (d->uploaded) return OK;
+  if (!d->have_box) return fail(d, ERR_STATE, "Run command before simulation box is defined");
+  if (d->tag.empty()) return fail(d, ERR_UNSUPPORTED, "no particles: initial states come from read_data (particle insertion is outside the hot-path scope)");
+  if (!d->newton_off && d->have_pair) return fail(d, ERR_ARG, "Pair granular with shear history requires newton pair off");
+  TRY(API(upload_particles)(d->e, (long)d->tag.size(), d->tag.data(), d->type.data(), d->mask.data(), d->x.data(), d->v.data(), d->omega.data(),
+                            d->radius.data(), d->density.data()));
+  d->uploaded = true;
+  return OK;
+}
+int send_box(Deck *d)
+{
+  if (d->box_sent || !d->have_box) return OK;
+  TRY(API(set_box)(d->e, d->lo, d->hi, d->periodic));
+  TRY(API(set_ntypes)(d->e, d->ntypes));
+  d->box_sent = true;
+  return OK;
+}
+
+int cmd_fix(Deck *d, const std::vector<std::string> &w)
+{
+  if (w.size() < 4) return fail(d, ERR_ARG, "Illegal fix command");
+  const std::string &id = w[1], &group = w[2], &style = w[3];
+  if (!d->groups.count(group)) return fail(d, ERR_ARG, "Could not find fix group ID %s", group.c_str());
+  const int bit = d->groups[group];
+  int rc = send_box(d); if (rc) return rc;
+  if (style == "property/global") {  // fix_property_global.cpp:60-200
+    if (w.size() < 7) return fail(d, ERR_ARG, "Illegal fix property/global command, not enough arguments");
+    const std::string &name = w[4], &kind = w[5];
+    size_t from = 6;
+    if (kind == "peratomtypepair" || kind == "atomtypepair") {
+      int nt; rc = inumeric(d, w[6], nt); if (rc) return rc;
+      if (nt != d->ntypes) return fail(d, ERR_ARG, "Fix property/global %s: the number of atom types (%d) must match create_box / the data file (%d)", name.c_str(), nt, d->ntypes);
+      from = 7;
+    }
+    std::vector<double> vals;
+    for (size_t k = from; k < w.size(); k++) { double v; rc = numeric(d, w[k], v); if (rc) return rc; vals.push_back(v); }
+    const char *kk = (kind == "atomtypepair") ? "peratomtypepair" : (kind == "atomtype") ? "peratomtype" : kind.c_str();
+    TRY(API(set_property)(d->e, name.c_str(), kk, vals.data(), (int)vals.size()));
+    return OK;
+  }
+  if (style == "gravity") {  // fix_gravity.cpp:60-140
+    if (w.size() != 9 || w[5] != "vector") return fail(d, w.size() >= 6 && w[5] != "vector" ? ERR_UNSUPPORTED : ERR_ARG, "Illegal fix gravity command (supported: MAG vector x y z)");
+    if (bit != 1) return fail(d, ERR_UNSUPPORTED, "fix gravity on a group other than 'all' is outside the hot-path scope");
+    double mag, dir[3];
+    rc = numeric(d, w[4], mag); if (rc) return rc;
+    for (int k = 0; k < 3; k++) { rc = numeric(d, w[6 + k], dir[k]); if (rc) return rc; }
+    TRY(API(set_gravity)(d->e, mag, dir));
+    return OK;
+  }
+  if (style == "wall/gran") {  // fix_wall_gran.cpp:120-342
+    if (bit != 1) return fail(d, ERR_UNSUPPORTED, "fix wall/gran on a group other than 'all' is outside the hot-path scope");
+    bool mesh = false;
+    for (size_t k = 4; k < w.size(); k++) if (w[k] == "mesh") mesh = true; else if (w[k] == "primitive") break;
+    std::vector<const char *> a = cptrs(w, 4);
+    if (mesh) TRY(API(add_wall_mesh)(d->e, id.c_str(), (int)a.size(), a.data()));
+    else TRY(API(add_wall_primitive)(d->e, id.c_str(), (int)a.size(), a.data()));
+    return OK;
+  }
+  if (style.compare(0, 12, "mesh/surface") == 0) {  // any mesh/surface* style falls back to the base creator (modify.cpp:852-856)
+    if (w.size() < 6 || w[4] != "file") return fail(d, w.size() >= 5 && w[4] == "fix" ? ERR_UNSUPPORTED : ERR_ARG, "expecting keyword 'file' or 'fix'");
+    std::vector<double> nodes;
+    rc = read_stl(d, w[5], nodes); if (rc) return rc;
+    int atom_type = 1;
+    std::vector<std::string> pass;
+    for (size_t k = 6; k < w.size();) {
+      const std::string &key = w[k];
+      auto need = [&](size_t n) { return k + n < w.size() + 0 ? OK : fail(d, ERR_ARG, "not enough arguments for '%s'", key.c_str()); };
+      if (key == "type") { rc = need(1); if (rc) return rc; rc = inumeric(d, w[k + 1], atom_type); if (rc) return rc; if (atom_type < 1) return fail(d, ERR_ARG, "'type' > 0 required"); k += 2; }
+      else if (key == "move") {
+        rc = need(3); if (rc) return rc;
+        double dx[3]; for (int c = 0; c < 3; c++) { rc = numeric(d, w[k + 1 + c], dx[c]); if (rc) return rc; }
+        for (size_t n = 0; n < nodes.size(); n++) nodes[n] = nodes[n] + dx[n % 3];
+        k += 4;
+      } else if (key == "scale") {
+        rc = need(1); if (rc) return rc;
+        double s; rc = numeric(d, w[k + 1], s); if (rc) return rc;
+        for (size_t n = 0; n < nodes.size(); n++) nodes[n] *= s;
+        k += 2;
+      } else if (key == "rotate") {
+        rc = need(6); if (rc) return rc;
+        if (w[k + 1] != "axis") return fail(d, ERR_ARG, "expecting keyword 'axis' after keyword 'rotate'");
+        if (w[k + 5] != "angle") return fail(d, ERR_ARG, "expecting keyword 'angle' after axis definition");
+        double ax[3], ang; for (int c = 0; c < 3; c++) { rc = numeric(d, w[k + 2 + c], ax[c]); if (rc) return rc; }
+        rc = numeric(d, w[k + 6], ang); if (rc) return rc;
+        if (std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]) < 1e-5) return fail(d, ERR_ARG, "illegal magnitude of rotation axis");
+        mesh_rotate(nodes, ax, ang);
+        k += 7;
+      } else if (key == "curvature" || key == "precision") { rc = need(1); if (rc) return rc; pass.push_back(key); pass.push_back(w[k + 1]); k += 2; }
+      else if (key == "verbose" || key == "heal") { rc = need(1); if (rc) return rc; k += 2; }
+      else return fail(d, ERR_UNSUPPORTED, "fix mesh/surface keyword '%s' is outside the hot-path scope", key.c_str());
+    }
+    std::vector<const char *> a = cptrs(pass, 0);
+    TRY(API(add_mesh)(d->e, id.c_str(), atom_type, nodes.data(), (long)(nodes.size() / 9), (int)a.size(), a.data()));
+    return OK;
+  }
+  if (style == "move/mesh") {  // fix_move_mesh.cpp:60-110
+    if (w.size() < 7 || w[4] != "mesh") return fail(d, ERR_ARG, "Illegal fix move/mesh command, expecting keyword 'mesh'");
+    std::vector<const char *> a = cptrs(w, 6);
+    TRY(API(move_mesh)(d->e, w[5].c_str(), (int)a.size(), a.data()));
+    return OK;
+  }
+  if (style == "freeze") { TRY(API(set_freeze)(d->e, bit)); return OK; }
+  if (style == "nve/sphere") { TRY(API(set_integrate)(d->e, bit)); return OK; }
+  if (style == "check/timestep/gran") { d->ignored_fixes[id] = style; d->warnings += "fix " + style + " ignored (diagnostic only)\n"; return OK; }
+  return fail(d, ERR_UNSUPPORTED, "fix style '%s' is outside the hot-path scope", style.c_str());
+}
+
+int cmd_group(Deck *d, const std::vector<std::string> &w)
+{  // group.cpp:90-260 (styles id and type; a group keeps its bit, members are OR-ed in)
+  if (w.size() < 4) return fail(d, ERR_ARG, "Illegal group command");
+  if (d->uploaded) return fail(d, ERR_UNSUPPORTED, "group changes after the first run are outside the hot-path scope");
+  int bit;
+  if (d->groups.count(w[1])) bit = d->groups[w[1]];
+  else { if (d->groups.size() >= 31) return fail(d, ERR_ARG, "Too many groups"); bit = 1 << (int)d->groups.size(); d->groups[w[1]] = bit; }
+  if (w[2] != "id" && w[2] != "type") return fail(d, ERR_UNSUPPORTED, "group style '%s' is outside the hot-path scope", w[2].c_str());
+  std::vector<std::pair<int, int>> ranges;
+  for (size_t k = 3; k < w.size(); k++) {
+    const size_t c = w[k].find(':');
+    int a, b;
+    int rc = inumeric(d, w[k].substr(0, c), a); if (rc) return rc;
+    b = a;
+    if (c != std::string::npos) { rc = inumeric(d, w[k].substr(c + 1), b); if (rc) return rc; }
+    ranges.push_back({a, b});
+  }
+  const std::vector<int> &key = (w[2] == "id") ? d->tag : d->type;
+  for (size_t i = 0; i < key.size(); i++) for (auto &r : ranges) if (key[i] >= r.first && key[i] <= r.second) { d->mask[i] |= bit; break; }
+  return OK;
+}
+
+int one(Deck *d, const std::string &raw)
+{
+  std::string line = raw;
+  int rc = substitute(d, line); if (rc) return rc;
+  const std::vector<std::string> w = split(line);
+  if (w.empty()) return OK;
+  const std::string &c = w[0];
+  static const char *output_only[] = {"thermo", "thermo_style", "thermo_modify", "compute", "uncompute", "dump", "dump_modify", "undump", "echo", "log",
+                                     "print", "restart", "write_restart", "write_data", "info", "reset_timestep_info", nullptr};
+  for (int k = 0; output_only[k]; k++) if (c == output_only[k]) { d->warnings += c + " ignored (output only)\n"; return OK; }
+  if (c == "variable") {  // styles equal / string / index with a literal value (variable.cpp:90-330); formulas are not evaluated
+    if (w.size() < 4) return fail(d, ERR_ARG, "Illegal variable command");
+    if (w[2] != "equal" && w[2] != "string" && w[2] != "index") return fail(d, ERR_UNSUPPORTED, "variable style '%s' is outside the hot-path scope", w[2].c_str());
+    if (w[2] == "equal" && !is_number(w[3])) return fail(d, ERR_UNSUPPORTED, "variable formulas are outside the hot-path scope: '%s'", w[3].c_str());
+    if (w[2] == "index" && d->vars.count(w[1])) return OK;  // an index variable keeps its first value
+    d->vars[w[1]] = w[3]; return OK;
+  }
+  if (c == "units") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal units command"); TRY(API(set_units)(d->e, w[1].c_str())); return OK; }
+  if (c == "atom_style") {
+    if (w.size() < 2) return fail(d, ERR_ARG, "Illegal atom_style command");
+    if (w[1] != "sphere" && w[1] != "granular") return fail(d, ERR_UNSUPPORTED, "atom_style %s is outside the hot-path scope (sphere | granular)", w[1].c_str());
+    return OK;
+  }
+  if (c == "atom_modify" || c == "pair_coeff" || c == "hard_particles" || c == "soft_particles" || c == "modify_timing") return OK;
+  if (c == "dimension") { if (w.size() != 2 || w[1] != "3") return fail(d, ERR_UNSUPPORTED, "only dimension 3"); return OK; }
+  if (c == "boundary") {
+    if (w.size() != 4) return fail(d, ERR_ARG, "Illegal boundary command");
+    for (int k = 0; k < 3; k++) {
+      const std::string &b = w[1 + k];
+      if (b == "p") d->periodic[k] = 1;
+      else if (b == "f" || b == "m" || b == "s" || b == "ff" || b == "mm" || b == "fm" || b == "mf" || b == "ss") d->periodic[k] = 0;
+      else return fail(d, ERR_ARG, "Illegal boundary command");
+    }
+    return OK;
+  }
+  if (c == "newton") { if (w.size() < 2) return fail(d, ERR_ARG, "Illegal newton command"); d->newton_off = (w[1] == "off"); return OK; }
+  if (c == "communicate" || c == "comm_modify") {
+    for (size_t k = 1; k + 1 < w.size(); k++) if (w[k] == "vel" && w[k + 1] != "yes") return fail(d, ERR_ARG, "Pair granular requires ghost atoms store velocity");
+    return OK;
+  }
+  if (c == "processors") {
+    if (w.size() < 4) return fail(d, ERR_ARG, "Illegal processors command");
+    if (w[1] == "*" || w[2] == "*" || w[3] == "*") return OK;  // left to the engine's own choice
+    int p[3]; for (int k = 0; k < 3; k++) { rc = inumeric(d, w[1 + k], p[k]); if (rc) return rc; }
+    TRY(API(set_processors)(d->e, p[0], p[1], p[2])); return OK;
+  }
+  if (c == "region") {
+    if (w.size() < 9 || w[2] != "block") return fail(d, w.size() >= 3 && w[2] != "block" ? ERR_UNSUPPORTED : ERR_ARG, "region: only 'ID block xlo xhi ylo yhi zlo zhi [units box]' is on the hot path");
+    Deck::Region R;
+    for (int k = 0; k < 3; k++) { rc = numeric(d, w[3 + 2 * k], R.lo[k]); if (rc) return rc; rc = numeric(d, w[4 + 2 * k], R.hi[k]); if (rc) return rc; }
+    for (size_t k = 9; k + 1 < w.size(); k++) if (w[k] == "units" && w[k + 1] != "box") return fail(d, ERR_UNSUPPORTED, "region units lattice is outside the hot-path scope");
+    d->regions[w[1]] = R; return OK;
+  }
+  if (c == "create_box") {
+    if (w.size() != 3) return fail(d, ERR_ARG, "Illegal create_box command");
+    if (d->have_box) return fail(d, ERR_ARG, "Cannot create_box after simulation box is defined");
+    if (!d->regions.count(w[2])) return fail(d, ERR_ARG, "Create_box region ID does not exist");
+    rc = inumeric(d, w[1], d->ntypes); if (rc) return rc;
+    for (int k = 0; k < 3; k++) { d->lo[k] = d->regions[w[2]].lo[k]; d->hi[k] = d->regions[w[2]].hi[k]; }
+    d->have_box = true; return send_box(d);
+  }
+  if (c == "read_data") { if (w.size() < 2) return fail(d, ERR_ARG, "Illegal read_data command"); rc = read_data(d, w[1]); if (rc) return rc; return send_box(d); }
+  if (c == "neighbor") {
+    if (w.size() != 3) return fail(d, ERR_ARG, "Illegal neighbor command");
+    if (w[2] != "bin") return fail(d, ERR_UNSUPPORTED, "neighbor style %s is outside the hot-path scope (bin)", w[2].c_str());
+    rc = numeric(d, w[1], d->skin); if (rc) return rc;
+    TRY(API(set_neighbor)(d->e, d->skin, d->every, d->delay, d->check)); return OK;
+  }
+  if (c == "neigh_modify") {  // neighbor.cpp:2180-2290
+    for (size_t k = 1; k < w.size(); k += 2) {
+      if (k + 1 >= w.size()) return fail(d, ERR_ARG, "Illegal neigh_modify command");
+      if (w[k] == "every") { rc = inumeric(d, w[k + 1], d->every); if (rc) return rc; }
+      else if (w[k] == "delay") { rc = inumeric(d, w[k + 1], d->delay); if (rc) return rc; }
+      else if (w[k] == "check") { if (w[k + 1] != "yes" && w[k + 1] != "no") return fail(d, ERR_ARG, "Illegal neigh_modify command"); d->check = w[k + 1] == "yes"; }
+      else if (w[k] == "contact_distance_factor") { double f; rc = numeric(d, w[k + 1], f); if (rc) return rc; if (f != 1.0) return fail(d, ERR_UNSUPPORTED, "neigh_modify contact_distance_factor != 1 is set by the bond models only"); }
+      else if (w[k] == "page" || w[k] == "one" || w[k] == "binsize") continue;
+      else return fail(d, ERR_UNSUPPORTED, "neigh_modify keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    TRY(API(set_neighbor)(d->e, d->skin, d->every, d->delay, d->check)); return OK;
+  }
+  if (c == "pair_style") {
+    if (w.size() < 2 || w[1] != "gran") return fail(d, ERR_UNSUPPORTED, "pair_style %s is outside the hot-path scope (gran)", w.size() > 1 ? w[1].c_str() : "");
+    rc = send_box(d); if (rc) return rc;
+    std::vector<const char *> a = cptrs(w, 2);
+    TRY(API(set_pair_style)(d->e, (int)a.size(), a.data()));
+    d->have_pair = true; return OK;
+  }
+  if (c == "fix") return cmd_fix(d, w);
+  if (c == "unfix") {
+    if (w.size() != 2) return fail(d, ERR_ARG, "Illegal unfix command");
+    if (d->ignored_fixes.erase(w[1])) return OK;
+    return fail(d, ERR_UNSUPPORTED, "unfix of a hot-path fix is outside the hot-path scope");
+  }
+  if (c == "group") return cmd_group(d, w);
+  if (c == "timestep") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal timestep command"); double dt; rc = numeric(d, w[1], dt); if (rc) return rc; TRY(API(set_timestep)(d->e, dt)); return OK; }
+  if (c == "run") {  // run.cpp:40-130: every run starts with Verlet::setup
+    if (w.size() < 2) return fail(d, ERR_ARG, "Illegal run command");
+    double nd; rc = numeric(d, w[1], nd); if (rc) return rc;
+    long n = (long)nd;
+    for (size_t k = 2; k < w.size(); k++) {
+      if (w[k] == "upto") { n -= d->ntimestep; if (n < 0) return fail(d, ERR_ARG, "Run command upto value is before current timestep"); }
+      else return fail(d, ERR_UNSUPPORTED, "run keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    if (n < 0) return fail(d, ERR_ARG, "Invalid run command N value");
+    rc = first_run_prepare(d); if (rc) return rc;
+    TRY(API(setup)(d->e));
+    TRY(API(run)(d->e, n));
+    d->ntimestep += n; return OK;
+  }
+  return fail(d, ERR_UNSUPPORTED, "command '%s' is outside the hot-path scope", c.c_str());
+}
+
+}  // namespace
+
+extern "C" {
+
+typedef struct DECK(handle) { Deck d; } DECK(handle);
+
+// `lammps_open_no_mpi` analogue: the deck state wraps an engine the caller created (and still owns)
+int DECK(open)(DECK(handle) **out, dem_engine *e)
+{
+  if (!out || !e) return ERR_ARG;
+  DECK(handle) *h = new DECK(handle)();
+  h->d.e = e; h->d.groups["all"] = 1;
+  *out = h; return OK;
+}
+void DECK(close)(DECK(handle) *h) { delete h; }
+const char *DECK(last_error)(const DECK(handle) *h) { return h ? h->d.err.c_str() : "null deck"; }
+const char *DECK(warnings)(const DECK(handle) *h) { return h ? h->d.warnings.c_str() : ""; }
+long DECK(ntimestep)(const DECK(handle) *h) { return h ? h->d.ntimestep : -1; }
+// `lammps_command`: one input-script line (no continuation handling, as Input::one)
+int DECK(command)(DECK(handle) *h, const char *line)
+{
+  if (!h || !line) return ERR_ARG;
+  try { return one(&h->d, line); } catch (const std::exception &ex) { h->d.err = ex.what(); return ERR_ARG; }
+}
+// `lammps_file`: a whole input script, '&' continuation lines joined (Input::file input.cpp:160-250); stops at the first error
+int DECK(file)(DECK(handle) *h, const char *path)
+{
+  if (!h || !path) return ERR_ARG;
+  std::ifstream f(path);
+  if (!f.good()) { h->d.err = std::string("Cannot open input script ") + path; return ERR_ARG; }
+  const std::string p(path); const size_t sl = p.rfind('/');
+  const std::string olddir = h->d.dir;
+  h->d.dir = sl == std::string::npos ? "" : p.substr(0, sl);
+  std::string line, acc; int lineno = 0, rc = OK;
+  while (std::getline(f, line)) {
+    lineno++;
+    size_t end = line.find_last_not_of(" \t\r\n");
+    if (end != std::string::npos && line[end] == '&') { acc += line.substr(0, end) + " "; continue; }
+    acc += line;
+    rc = DECK(command)(h, acc.c_str());
+    if (rc != OK) { char where[64]; snprintf(where, sizeof where, " (line %d)", lineno); h->d.err += where; break; }
+    acc.clear();
+  }
+  h->d.dir = olddir;
+  return rc;
+}
+
+}  // extern "C"

@@ -346,6 +346,9 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         const int kk = __ffsll((long long)touch) - 1;
         touch &= touch - 1;
         const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+#ifdef DEM_EXP_SKIP_INWARP  // timing experiment only (wrong physics): upper bound of what in-warp pair sharing can save
+        if (((w & NBR_IDX) - (unsigned)(i - lane)) < (unsigned)lane) continue;
+#endif
         if (nc < DEM_CMAX) s_w[nc++][tid] = w; else extra |= 1ull << kk;
         prefetch_contact(P, i, w, bbase, blim);
       }

@@ -13,6 +13,7 @@ ABI_SYMBOLS = [
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_contact_count", "dem_download_mesh_contacts",
+    "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
 ]
 
 
@@ -274,3 +275,49 @@ class Engine:
         s = Stats()
         self._call("get_stats", [C.POINTER(Stats)], C.byref(s))
         return s
+
+
+class Deck:
+    """Input-script front end over an Engine: the reference's `lammps.command()` / `lammps.file()` (python/liggghts.py)
+    for the hot-path commands.  `lib`/`prefix` let the test-suite bind the same parser to the CPU oracle (tests only)."""
+
+    def __init__(self, engine, lib=None, prefix=None):
+        self.engine = engine
+        self._lib = lib if lib is not None else engine._lib
+        self._p = prefix if prefix is not None else engine._p + "deck_"
+        self._h = C.c_void_p()
+        f = getattr(self._lib, self._p + "open"); f.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]; f.restype = C.c_int
+        if f(C.byref(self._h), engine._h) != 0:
+            raise DemError("deck_open failed")
+
+    def _err(self):
+        f = getattr(self._lib, self._p + "last_error"); f.restype = C.c_char_p; f.argtypes = [C.c_void_p]
+        return (f(self._h) or b"").decode()
+
+    def command(self, line):
+        f = getattr(self._lib, self._p + "command"); f.argtypes = [C.c_void_p, C.c_char_p]; f.restype = C.c_int
+        for one in line.splitlines():
+            rc = f(self._h, one.encode())
+            if rc != 0:
+                raise DemError("%s (%d): %s" % (one.strip(), rc, self._err()))
+
+    def file(self, path):
+        f = getattr(self._lib, self._p + "file"); f.argtypes = [C.c_void_p, C.c_char_p]; f.restype = C.c_int
+        rc = f(self._h, path.encode())
+        if rc != 0:
+            raise DemError("%s (%d): %s" % (path, rc, self._err()))
+
+    @property
+    def warnings(self):
+        f = getattr(self._lib, self._p + "warnings"); f.restype = C.c_char_p; f.argtypes = [C.c_void_p]
+        return (f(self._h) or b"").decode()
+
+    @property
+    def ntimestep(self):
+        f = getattr(self._lib, self._p + "ntimestep"); f.restype = C.c_long; f.argtypes = [C.c_void_p]
+        return f(self._h)
+
+    def close(self):
+        if self._h:
+            f = getattr(self._lib, self._p + "close"); f.argtypes = [C.c_void_p]; f.restype = None
+            f(self._h); self._h = C.c_void_p()

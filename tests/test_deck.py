@@ -1,0 +1,108 @@
+"""The input-script front end (csrc/dem_deck.cpp): the SAME deck text that tests/golden/make_golden.py feeds to the
+unmodified reference is parsed by the product's front end.  CPU: the parser source re-targeted at the oracle
+(oracle/libdeck_oracle.so, tests only) against the reference's golden vectors; GPU: the shipped library."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+import pytest
+import cases
+import parity
+
+
+def oracle_deck():
+    import dem_b200
+    so = os.path.join(parity.ROOT, "oracle", "libdeck_oracle.so")
+    subprocess.run(["make", "-C", os.path.join(parity.ROOT, "oracle"), "libdeck_oracle.so"], check=True, capture_output=True)
+    eng = parity.oracle_engine()
+    return eng, dem_b200.Deck(eng, lib=ctypes.CDLL(so), prefix="orc_deck_")
+
+
+def write_deck(c, tmp_path, lines_extra=()):
+    deck, data = cases.to_deck(c, str(tmp_path / "case.data"))
+    (tmp_path / "case.data").write_text(data)
+    # exercise the file reader: a comment, a continuation line and a variable
+    deck = deck.replace("timestep ", "variable dt equal ").replace("fix integr all nve/sphere", "fix integr all &\n   nve/sphere   # integrator")
+    deck += "\ntimestep ${dt}\nthermo 1000\ncompute 1 all erotate\n" + "\n".join(lines_extra) + "\n"
+    (tmp_path / "in.case").write_text(deck)
+    return str(tmp_path / "in.case")
+
+
+def follow_golden(name, eng, deck, path, gpu):
+    c = cases.make_case(name)
+    g = parity.golden(name)
+    deck.file(path)
+    done = 0
+    for cp in cases.GOLDEN_CASES[name]["checkpoints"]:
+        deck.command("run %d upto" % cp if cp else "run 0")
+        if done == 0:
+            parity.compare_topology(eng, c, g)
+        done = cp
+        parity.compare_snapshot(cases.snapshot(eng, c), parity.golden_at(g, cp), g["rmass"], tol=parity.tol_for(c, cp, gpu=gpu), label="deck %s@%d" % (name, cp))
+        assert eng.stats().nbuilds == int(parity.golden_at(g, cp)["nbuilds"])
+    assert deck.ntimestep == done
+    assert "thermo ignored" in deck.warnings
+    deck.close(); eng.close()
+
+
+DECK_CASES = ["box_hertz_cdt", "poly_hooke_epsd_cyl", "periodic_epsd2", "mesh_funnel_hooke", "mesh_plate_moving", "mesh_drum_rotating", "bond_nonlinear"]
+
+
+@pytest.mark.parametrize("name", DECK_CASES)
+def test_deck_on_oracle_matches_reference_golden(name, tmp_path):
+    path = write_deck(cases.make_case(name), tmp_path)
+    eng, deck = oracle_deck()
+    follow_golden(name, eng, deck, path, gpu=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DECK_CASES)
+def test_deck_on_engine_matches_reference_golden(name, tmp_path):
+    import dem_b200
+    path = write_deck(cases.make_case(name), tmp_path)
+    eng = dem_b200.Engine(device=0)
+    follow_golden(name, eng, dem_b200.Deck(eng), path, gpu=True)
+
+
+def test_deck_mesh_load_transforms_and_errors(tmp_path):
+    """`fix mesh/surface ... move/rotate/scale` act on the nodes like FixMesh::moveMesh/rotateMesh/scaleMesh; error classes"""
+    import dem_b200
+    c = cases.make_case("mesh_funnel_hooke")
+    path = write_deck(c, tmp_path)
+    text = open(path).read()
+    stl = str(tmp_path / "fun.stl")
+    text = text.replace("file %s type 1" % stl, "file %s type 1 move 0.001 0. 0. rotate axis 0. 0. 1. angle 90. scale 0.5" % stl)
+    open(path, "w").write(text)
+    eng, deck = oracle_deck()
+    deck.file(path)
+    nodes = np.asarray([m for m in c["meshes"] if m[0] == "fun"][0][2]).reshape(-1, 3)
+    moved = nodes + [0.001, 0., 0.]
+    a = 90. * 3.14159265 / 180.
+    want = 0.5 * np.stack([np.cos(a) * moved[:, 0] - np.sin(a) * moved[:, 1], np.sin(a) * moved[:, 0] + np.cos(a) * moved[:, 1], moved[:, 2]], 1)
+    got = eng.mesh_field("fun", "nodes", len(nodes) // 3).reshape(-1, 3)
+    assert np.abs(got - want).max() < 1e-15
+    # error classes: unsupported (-2) vs bad argument (-1), with the reference's message text where one exists
+    with pytest.raises(dem_b200.DemError, match=r"\(-2\).*outside the hot-path scope"):
+        deck.command("fix ins all insert/pack seed 1")
+    with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Expected floating point parameter"):
+        deck.command("timestep abc")
+    with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Substitution for illegal variable"):
+        deck.command("timestep ${nope}")
+    with pytest.raises(dem_b200.DemError, match=r"\(-2\)"):
+        deck.command("pair_style lj/cut 2.5")
+    with pytest.raises(dem_b200.DemError, match=r"Could not find fix group ID"):
+        deck.command("fix g nobody gravity 9.81 vector 0 0 -1")
+    deck.close(); eng.close()
+
+
+@pytest.mark.gpu
+def test_lmp_b200_cli_runs_a_deck(tmp_path):
+    """`lmp_b200 -in deck`: the reference's `lmp_<machine> -in deck` for the hot-path commands"""
+    path = write_deck(cases.make_case("box_hertz_cdt"), tmp_path, lines_extra=["run 300"])
+    exe = os.path.join(parity.ROOT, "liggghts-inl_b200", "lmp_b200")
+    r = subprocess.run([exe, "-in", path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "for 300 steps with 64 atoms" in r.stdout, r.stdout
+    bad = tmp_path / "in.bad"; bad.write_text("units si\nfix ins all insert/pack seed 1\n")
+    r = subprocess.run([exe, "-in", str(bad)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "outside the hot-path scope" in r.stderr and "line 2" in r.stderr
