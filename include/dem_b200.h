@@ -44,6 +44,9 @@ int dem_nccl_unique_id(void *out128);
  * Domain::set_local_box  src/domain.cpp.  Pure host logic, valid after dem_set_box / dem_set_processors.  */
 int dem_decomposition(dem_engine *e, int pgrid[3], int myloc[3], double sublo[3], double subhi[3]);
 const char *dem_last_error(const dem_engine *e);
+/* Device blocks released by engines are kept in a process-wide cache for the next engine (set DEM_B200_NO_CACHE=1 to
+ * switch it off); this returns them to the driver and reports the bytes freed.                                        */
+long dem_trim_memory(void);
 const char *dem_version(void);
 
 /* engine tuning knobs that have no deck equivalent: "time_kernels" (0/1: CUDA-event timing of the

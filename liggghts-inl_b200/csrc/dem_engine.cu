@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,11 +62,70 @@ static void dem_fail(dem_engine *e, int code, const char *fmt, ...);
     if (err__ != cudaSuccess) dem_fail(E, DEM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
   } while (0)
 
+// Device memory comes from a process-wide cache of whole cudaMalloc blocks (per device, best fit within 25 %): engines
+// that follow one another in a process (a parameter sweep, bench.py's two passes) reuse the blocks instead of paying the
+// driver's map/unmap cost again -- cudaMalloc/cudaFree of the ~8 GB a 4M-sphere bed needs was measured at 0.2-0.6 s.
+// Blocks are never sub-divided, so CUDA-IPC handles (peer-memory halo) stay valid.  dem_trim_memory() empties the cache.
+static std::mutex g_mem_mu;
+static std::multimap<size_t, void *> g_mem_free[32];
+static std::map<void *, std::pair<int, size_t>> g_mem_size;
+static bool mem_cache_on() { static const bool on = !getenv("DEM_B200_NO_CACHE"); return on; }
+static size_t mem_trim(int dev)
+{
+  size_t bytes = 0;
+  std::lock_guard<std::mutex> lk(g_mem_mu);
+  for (int d = 0; d < 32; d++) if (dev < 0 || d == dev) {
+    int cur = 0; cudaGetDevice(&cur);
+    if (!g_mem_free[d].empty()) cudaSetDevice(d);
+    for (auto &kv : g_mem_free[d]) { bytes += kv.first; g_mem_size.erase(kv.second); cudaFree(kv.second); }
+    if (!g_mem_free[d].empty()) cudaSetDevice(cur);
+    g_mem_free[d].clear();
+  }
+  return bytes;
+}
+static cudaError_t dev_alloc(void **out, size_t bytes)
+{
+  int dev = 0; cudaGetDevice(&dev); dev &= 31;
+  const size_t gran = bytes >= (1u << 20) ? (2u << 20) : 512;
+  const size_t sz = (bytes + gran - 1) / gran * gran;
+  if (mem_cache_on()) {
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    auto it = g_mem_free[dev].lower_bound(sz);
+    if (it != g_mem_free[dev].end() && it->first <= sz + sz / 4 + (2u << 20)) { *out = it->second; g_mem_free[dev].erase(it); return cudaSuccess; }
+  }
+  cudaError_t rc = cudaMalloc(out, sz);
+  if (rc != cudaSuccess) { cudaGetLastError(); mem_trim(dev); rc = cudaMalloc(out, sz); }
+  if (rc == cudaSuccess) { std::lock_guard<std::mutex> lk(g_mem_mu); g_mem_size[*out] = {dev, sz}; }
+  return rc;
+}
+static void dev_free(void *p)
+{
+  if (!p) return;
+  cudaDeviceSynchronize();  // like cudaFree: nothing in flight may still touch the block when its next owner gets it
+  std::lock_guard<std::mutex> lk(g_mem_mu);
+  auto it = g_mem_size.find(p);
+  if (!mem_cache_on() || it == g_mem_size.end()) { if (it != g_mem_size.end()) g_mem_size.erase(it); cudaFree(p); return; }
+  g_mem_free[it->second.first].insert({it->second.second, p});
+}
+
+// the engines' small page-locked blocks (flag words, counters; 512 bytes each) are recycled too: cudaHostAlloc was seen to
+// take up to 0.15 s right after a large page-locked region had been released
+static std::vector<void *> g_host_small;
+static void *host_small_alloc()
+{
+  { std::lock_guard<std::mutex> lk(g_mem_mu); if (!g_host_small.empty()) { void *p = g_host_small.back(); g_host_small.pop_back(); memset(p, 0, 512); return p; } }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, 512, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  memset(p, 0, 512);
+  return p;
+}
+static void host_small_free(void *p) { std::lock_guard<std::mutex> lk(g_mem_mu); g_host_small.push_back(p); }
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) dev_free(p); p = nullptr; n = 0; }
   // grow to at least m elements; keep = number of leading elements to preserve
   void ensure(dem_engine *E, size_t m, size_t keep = 0, cudaStream_t st = 0);
 };
@@ -185,9 +245,9 @@ void DevBuf<T>::ensure(dem_engine *E, size_t m, size_t keep, cudaStream_t st)
 {
   if (m <= n) return;
   T *q = nullptr;
-  CK(cudaMalloc(&q, m * sizeof(T)));
+  CK(dev_alloc((void **)&q, m * sizeof(T)));
   if (keep && p) CK(cudaMemcpyAsync(q, p, std::min(keep, n) * sizeof(T), cudaMemcpyDeviceToDevice, st));
-  if (p) { CK(cudaStreamSynchronize(st)); cudaFree(p); }
+  if (p) { CK(cudaStreamSynchronize(st)); dev_free(p); }
   p = q; n = m;
 }
 
@@ -216,9 +276,10 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
     cudaError_t rc = cudaGetDeviceCount(&ndev);
     if (rc != cudaSuccess || ndev == 0) dem_fail(e, DEM_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU path", cudaGetErrorString(rc));
     if (device < 0 || device >= ndev) dem_fail(e, DEM_ERR_ARG, "device ordinal %d out of range (%d devices)", device, ndev);
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) dem_fail(e, DEM_ERR_CUDA, "device %d is sm_%d%d; this library only contains sm_100a code", device, prop.major, prop.minor);
+    int cc_major = 0, cc_minor = 0;  // (cudaGetDeviceProperties takes tens of milliseconds; two attributes do not)
+    CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CK(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (cc_major < 10) dem_fail(e, DEM_ERR_CUDA, "device %d is sm_%d%d; this library only contains sm_100a code", device, cc_major, cc_minor);
     CK(cudaSetDevice(device));
     e->device = device; e->rank = rank; e->nranks = nranks; e->stream = (cudaStream_t)stream;
     if (nranks < 1 || rank < 0 || rank >= nranks) dem_fail(e, DEM_ERR_ARG, "bad rank/nranks %d/%d", rank, nranks);
@@ -228,8 +289,8 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
       ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
       NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
     }
-    CK(cudaHostAlloc((void **)&e->hcnt, 64 * sizeof(int), cudaHostAllocDefault));
-    CK(cudaHostAlloc((void **)&e->hflag, 8 * sizeof(int), cudaHostAllocDefault));
+    e->hcnt = (int *)host_small_alloc(); e->hflag = (int *)host_small_alloc();
+    if (!e->hcnt || !e->hflag) dem_fail(e, DEM_ERR_CUDA, "cudaHostAlloc failed");
     for (int k = 0; k < 8; k++) e->hflag[k] = 0;
     e->pm.tdamp = 1;
   } catch (const DemFail &f) { return f.code; }
@@ -261,14 +322,16 @@ extern "C" void dem_destroy(dem_engine *e)
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
   for (auto &ev : e->ev) cudaEventDestroy(ev);
-  if (e->hflag) cudaFreeHost(e->hflag);
+  if (e->hflag) host_small_free(e->hflag);
   for (int k = 0; k < 2; k++) if (e->fev[k]) cudaEventDestroy(e->fev[k]);
   for (auto &m : e->ipc) cudaIpcCloseMemHandle(m.ptr);
   e->hsig.release();
-  if (e->hcnt) cudaFreeHost(e->hcnt);
+  if (e->hcnt) host_small_free(e->hcnt);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   delete e;
 }
+
+extern "C" long dem_trim_memory(void) { return (long)mem_trim(-1); }
 
 extern "C" int dem_set_option(dem_engine *e, const char *name, double value)
 {

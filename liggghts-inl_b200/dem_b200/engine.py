@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_contact_count", "dem_download_mesh_contacts",
-    "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
+    "dem_trim_memory", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
 ]
 
 
