@@ -110,6 +110,8 @@ static void dev_free(void *p)
 
 // the engines' small page-locked blocks (flag words, counters; 512 bytes each) are recycled too: cudaHostAlloc was seen to
 // take up to 0.15 s right after a large page-locked region had been released
+struct CachedComm { int device, rank, nranks; ncclComm_t comm; };
+static std::vector<CachedComm> g_comm_cache;
 static std::vector<void *> g_host_small;
 static void *host_small_alloc()
 {
@@ -287,7 +289,14 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
       if (!nccl_id) dem_fail(e, DEM_ERR_ARG, "nranks > 1 needs the shared 128-byte ncclUniqueId (dem_nccl_unique_id on rank 0)");
       if (!g_nccl.load()) dem_fail(e, DEM_ERR_CUDA, "could not load libnccl.so.2");
       ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
-      NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+      // a communicator released by an earlier engine of this process with the same (device, rank, nranks) is taken over:
+      // ncclCommInitRank over 8 GPUs costs seconds, and every rank of an SPMD job creates its engines in the same order
+      {
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        for (auto it = g_comm_cache.begin(); it != g_comm_cache.end(); ++it)
+          if (it->device == device && it->rank == rank && it->nranks == nranks) { e->comm = it->comm; g_comm_cache.erase(it); break; }
+      }
+      if (!e->comm) NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
     }
     e->hcnt = (int *)host_small_alloc(); e->hflag = (int *)host_small_alloc();
     if (!e->hcnt || !e->hflag) dem_fail(e, DEM_ERR_CUDA, "cudaHostAlloc failed");
@@ -327,7 +336,10 @@ extern "C" void dem_destroy(dem_engine *e)
   for (auto &m : e->ipc) cudaIpcCloseMemHandle(m.ptr);
   e->hsig.release();
   if (e->hcnt) host_small_free(e->hcnt);
-  if (e->comm) g_nccl.CommDestroy(e->comm);
+  if (e->comm) {
+    if (getenv("DEM_B200_NO_COMM_CACHE")) g_nccl.CommDestroy(e->comm);
+    else { std::lock_guard<std::mutex> lk(g_mem_mu); g_comm_cache.push_back({e->device, e->rank, e->nranks, e->comm}); }
+  }
   delete e;
 }
 

@@ -156,6 +156,14 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #ifndef DEM_INBLOCK
 #define DEM_INBLOCK 0  // 1: records of partners inside the own block come from shared memory (measured r01d: 1.36 vs 1.25 ms, off)
 #endif
+#ifndef DEM_PAIRSHARE
+#define DEM_PAIRSHARE 0  // 1: a touching pair whose two particles sit in the same warp (49 % of all contacts after the Morton sort) is
+#endif                   //    evaluated once, by the lower lane's item; the higher lane takes -F and its torque from shared memory.
+                         //    Measured r01h (4.19M bed): parity green, but 1.43-1.61 ms against 1.25 ms -- registration, the second
+                         //    history store and 48 KB of shared memory cost more than the 24 % fewer evaluations save (bound 1.07 ms). Off.
+#ifndef DEM_MMAX
+#define DEM_MMAX 8       // such "mirror" entries per particle (more: evaluated by both sides as before)
+#endif
 #ifndef DEM_CPREFETCH
 #define DEM_CPREFETCH 2  // L2 prefetch of a staged contact's operands: 0 none, 1 history rows, 2 history + partner v|m, omega|bits
 #endif
@@ -173,8 +181,10 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 template <int NORMAL, int ROLLING, bool ONE>
 __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
                                              const double4 &wi, bool su, int *nh, double *F, double *T,
-                                             const double4 (*srec)[128], unsigned bbase, unsigned blim)
-{
+                                             const double4 (*srec)[128], unsigned bbase, unsigned blim,
+                                             unsigned reg = 0u, int iwarp = 0, double *Tm = nullptr)
+{  // reg != 0: the pair is evaluated ONCE for both bodies (the partner sits in the same warp, lane reg & 31, and keeps its
+   // copy of the history in its slot ((reg >> 5) & 63) - 1): Tm receives the partner's torque, the partner's force is -F
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int j = (int)(w & NBR_IDX);
   int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
@@ -195,7 +205,7 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
-  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
+  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T, Tm);
   if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
     const int s = atomicAdd(nh, 1);
     if (s < P.hslots) {
@@ -207,6 +217,11 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   }
   if (P.pm.hrec && slot >= 0 && (su || !had)) {
     double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
+    if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
+    if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
+  }
+  if (DEM_PAIRSHARE && reg && P.pm.hrec && (su || !had)) {  // the partner's copy: same values (rows are stored in the canonical orientation)
+    double4 *hp = P.hist + (size_t)((int)((reg >> 5) & 63u) - 1) * P.pm.hrec * P.lcap + (iwarp + (int)(reg & 31u));
     if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
     if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
   }
@@ -292,8 +307,11 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
   __shared__ unsigned s_w[DEM_CMAX][128];
   __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
-  __shared__ double s_res[6][4 * 32 * DEM_RWIN];  // per warp: force / torque of the items of the current window
+  __shared__ double s_res[DEM_PAIRSHARE ? 9 : 6][4 * 32 * DEM_RWIN];  // per warp: force / torque (/ partner torque) of the items of the current window
   __shared__ int s_off[128], s_nh[128];
+  __shared__ unsigned short s_reg[DEM_PAIRSHARE ? DEM_CMAX : 1][128];  // item -> 0x8000 | lane of the mirror particle | (its history slot + 1) << 5
+  __shared__ unsigned s_m[DEM_PAIRSHARE ? DEM_MMAX : 1][128];          // mirror entries of a particle: slot/orientation bits of its neighbour word | partner lane | row position << 5 (staging), then the item index
+  __shared__ unsigned char s_pair[DEM_PAIRSHARE ? 4 : 1][32][32];      // [warp][evaluating lane][mirror lane] = staged position + 1 of their pair in the evaluating lane's list
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
   if (step_gated(P)) return;
@@ -303,7 +321,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   const unsigned blim = (unsigned)min(128, P.nlocal - (int)bbase);                 // ... and how many of them are owned
   bool trig = false;
   double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
-  int nc = 0, nh0 = 0, nn = 0;
+  int nc = 0, nh0 = 0, nn = 0, mc = 0;
 #if DEM_STEP_WAVE_PREFETCH > 0
   {  // pull the streaming inputs of the block that will run one wave later towards L2
     const int ip = i + DEM_STEP_WAVE_PREFETCH * 128;
@@ -315,6 +333,10 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
     }
   }
 #endif
+  if (DEM_PAIRSHARE) {
+    uint4 *z = reinterpret_cast<uint4 *>(&s_pair[tid >> 5][lane][0]);
+    z[0] = make_uint4(0u, 0u, 0u, 0u); z[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
   {
     double4 xi = make_double4(0., 0., 0., 0.), vi = xi, wi = xi;
     if (active) { xi = ldg4(P.xr + i); vi = ldg4(P.vm + i); wi = ldg4(P.wt + i); }
@@ -349,7 +371,15 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 #ifdef DEM_EXP_SKIP_INWARP  // timing experiment only (wrong physics): upper bound of what in-warp pair sharing can save
         if (((w & NBR_IDX) - (unsigned)(i - lane)) < (unsigned)lane) continue;
 #endif
-        if (nc < DEM_CMAX) s_w[nc++][tid] = w; else extra |= 1ull << kk;
+        const unsigned jl = (w & NBR_IDX) - (unsigned)(i - lane);  // partner's lane if it sits in my warp
+        if (DEM_PAIRSHARE && jl < (unsigned)lane && mc < DEM_MMAX && k0 + kk < 64) {
+          s_m[mc++][tid] = (w & (NBR_HIST | NBR_JFIRST)) | jl | ((unsigned)(k0 + kk) << 5);  // a lower lane of my warp evaluates it
+          continue;
+        }
+        if (nc < DEM_CMAX) {
+          if (DEM_PAIRSHARE) { s_reg[nc][tid] = 0; if (jl - (unsigned)lane - 1u < 31u - (unsigned)lane) s_pair[tid >> 5][lane][jl] = (unsigned char)(nc + 1); }
+          s_w[nc++][tid] = w;
+        } else extra |= 1ull << kk;
         prefetch_contact(P, i, w, bbase, blim);
       }
       while (extra) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
@@ -367,32 +397,63 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
     }
     if (P.debug & 1) nc = 0;
   }
+  // (1c) mirror entries register with the item of the lower lane that will evaluate their pair: the item learns where the
+  //      partner's copy of the history lives, the mirror entry learns which item's result it has to collect.  Items are
+  //      numbered here already (prefix sums over the staged counts).
+  int incl = nc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int excl = incl - nc;
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  s_off[tid] = excl;
+  __syncwarp();
+  int mreg = 0;
+  if (DEM_PAIRSHARE) {
+    for (int m = 0; m < mc; m++) {
+      const unsigned e = s_m[m][tid];
+      const int ql = (int)(e & 31u), kk = (int)((e >> 5) & 63u);
+      const int c = (int)s_pair[tid >> 5][ql][lane] - 1;
+      int slot = (int)((e & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+      const unsigned w = (e & (NBR_HIST | NBR_JFIRST)) | (unsigned)(i - lane + ql);
+      bool ok = c >= 0;
+      if (ok && slot < 0 && P.pm.hrec) {  // first touch since the last rebuild: my row gets its slot now, the evaluator fills it
+        const int sfree = s_nh[tid];
+        if (sfree < P.hslots) { slot = sfree; s_nh[tid] = sfree + 1; P.nbr[(size_t)kk * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); }
+        else { ((volatile int *)P.flag)[1] = 1; ok = false; }
+      }
+      if (ok) {
+        s_reg[c][wb + ql] = (unsigned short)(0x8000u | (unsigned)lane | ((unsigned)(slot + 1) << 5));
+        s_m[mreg++][tid] = (unsigned)(s_off[wb + ql] + c);
+      } else  // the partner did not stage this pair (its row overflowed the staging area): my side is evaluated here, as before
+        pair_contact<NORMAL, ROLLING, ONE>(P, i, w, s_rec[0][tid], s_rec[1][tid], s_rec[2][tid], su, &s_nh[tid], F, T, s_rec, bbase, blim);
+    }
+    __syncwarp();
+  }
   // (2) cooperative contact phase
   {
-    int incl = nc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    const int excl = incl - nc;
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    s_off[tid] = excl;
-    __syncwarp();
     // rounds of 32 items; results are parked in shared memory and each owner adds its items (in list order) once per
     // window of DEM_RWIN rounds -- one short loop per window instead of one per round
     for (int b0 = 0; b0 < total; b0 += 32 * DEM_RWIN) {
       const int bend = min(total, b0 + 32 * DEM_RWIN);
       for (int t0 = b0; t0 < bend; t0 += 32) {
         const int t = t0 + lane;
-        double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
+        double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.}, rM[3] = {0., 0., 0.};
         if (t < total) {
           int p = 0;  // owner of item t: the last lane whose first item is <= t
 #pragma unroll
           for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
           const int q = wb + p;
           const unsigned w = s_w[t - s_off[q]][q];
-          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT, s_rec, bbase, blim);
+          const unsigned reg = DEM_PAIRSHARE ? (unsigned)s_reg[t - s_off[q]][q] : 0u;
+          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT, s_rec, bbase, blim,
+                                             reg, i - lane, DEM_PAIRSHARE ? rM : nullptr);
           const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
+          if (DEM_PAIRSHARE && reg) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) s_res[6 + d][sl] = rM[d];
+          }
         }
       }
       __syncwarp();
@@ -401,6 +462,16 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         const int sl = (wb >> 5) * (32 * DEM_RWIN) + (k - b0);
 #pragma unroll
         for (int d = 0; d < 3; d++) { F[d] += s_res[d][sl]; T[d] += s_res[3 + d][sl]; }
+      }
+      if (DEM_PAIRSHARE) {
+        for (int m = 0; m < mreg; m++) {  // pairs a lower lane evaluated for me: equal and opposite force, my own torque
+          const int t = (int)s_m[m][tid];
+          if (t >= b0 && t < bend) {
+            const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
+#pragma unroll
+            for (int d = 0; d < 3; d++) { F[d] -= s_res[d][sl]; T[d] += s_res[6 + d][sl]; }
+          }
+        }
       }
       __syncwarp();
     }

@@ -64,6 +64,8 @@ def main():
                       (dict(mesh="drum", n3=(10, 10, 5), move=0.2), (0, 1, 10, 600, 1800))):
         kw = dict(kw)
         mesh = kw.pop("mesh", None)
+        if world > 2:  # keep every brick wider than two neighbour cutoffs: stretch the bed along x with the rank count
+            kw["n3"] = (kw["n3"][0] * world // 2,) + tuple(kw["n3"][1:])
         c = cases.case_mesh(kind=mesh, name="multi_" + mesh, seed=11, **kw) if mesh else cases.case_box(name="multi", seed=11, **kw)
         # give the particles a drift along x so that they migrate between the bricks
         c["v"][:, 0] += 2.5 if not mesh else 0.8
