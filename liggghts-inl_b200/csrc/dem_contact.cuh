@@ -386,7 +386,7 @@ __device__ __forceinline__ double nl_torque_comp(double theta, double &tmax, dou
 }
 
 template <int COH>
-__device__ __noinline__ bool bond_eval(const StepP &P, const ModelP &M, const double *delta, double rsq, double radi, double radj,
+__device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const double *delta, double rsq, double radi, double radj,
                                        const double *xi, const double *vi, const double *vj, const double *omegai, const double *omegaj,
                                        int it, int jt, bool update_history, double *H, double *F, double *Ti, double *Tj)
 {

@@ -512,7 +512,26 @@ __global__ void __launch_bounds__(128) k_step_bond(const StepP P)
     const int nn = nnw & 0xffff;
     int nh = (nnw >> 16) & 0xffff;
     const int nh0 = nh;
-    for (int k = 0; k < nn; k++) {
+    constexpr int NB = (COH == C_BOND ? 14 : 28);  // == M.nbond (compile-time so that the history row lives in registers)
+    for (int k0 = 0; k0 < nn; k0 += 32) {
+    // (a) branch-free sweep of up to 32 row entries, 8 position gathers in flight: which entries need the contact chain
+    //     (touching, or inside the contact-distance band and bonded / bond candidates on the creation step)
+    unsigned need = 0u;
+    const int kn = min(32, nn - k0);
+#pragma unroll 8
+    for (int kk = 0; kk < kn; kk++) {
+      const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+      const double4 xj = ldg4(P.xr + (w & NBR_IDX));
+      const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+      const double radsum = xi.w + xj.w;
+      const bool touch = rsq < __dmul_rn(radsum, radsum);
+      const bool inband = touch || rsq < P.cdfsq * radsum * radsum;
+      need |= (unsigned)(inband && (touch || (w & NBR_HIST) || create_step)) << kk;
+    }
+    // (b) the selected entries
+    while (need) {
+      const int k = k0 + __ffs((int)need) - 1;
+      need &= need - 1;
       unsigned w = P.nbr[(size_t)k * P.lcap + i];
       const int j = (int)(w & NBR_IDX);
       const double4 xj = ldg4(P.xr + j);
@@ -520,9 +539,7 @@ __global__ void __launch_bounds__(128) k_step_bond(const StepP P)
       const double rsq = sq3_rn(dxm, dym, dzm);
       const double radsum = xi.w + xj.w;
       const bool touch = rsq < __dmul_rn(radsum, radsum);
-      const bool inband = touch || rsq < P.cdfsq * radsum * radsum;
       int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-      if (!inband || (!touch && slot < 0 && !create_step)) continue;
       const double4 vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
       const bool jfirst = (w & NBR_JFIRST) != 0;
       // canonical operands: a = first body (lower tag), b = second
@@ -539,10 +556,10 @@ __global__ void __launch_bounds__(128) k_step_bond(const StepP P)
 #pragma unroll
         for (int r = 0; r < (COH == C_BOND ? 4 : 8); r++) {
           const double4 v = hp[(size_t)(M.rec_bond + r) * P.lcap];
-          if (4 * r < M.nbond) H[4 * r] = v.x; else if (4 * r == M.nbond) S = v.x;
-          if (4 * r + 1 < M.nbond) H[4 * r + 1] = v.y; else if (4 * r + 1 == M.nbond) S = v.y;
-          if (4 * r + 2 < M.nbond) H[4 * r + 2] = v.z; else if (4 * r + 2 == M.nbond) S = v.z;
-          if (4 * r + 3 < M.nbond) H[4 * r + 3] = v.w; else if (4 * r + 3 == M.nbond) S = v.w;
+          if (4 * r < NB) H[4 * r] = v.x; else if (4 * r == NB) S = v.x;
+          if (4 * r + 1 < NB) H[4 * r + 1] = v.y; else if (4 * r + 1 == NB) S = v.y;
+          if (4 * r + 2 < NB) H[4 * r + 2] = v.z; else if (4 * r + 2 == NB) S = v.z;
+          if (4 * r + 3 < NB) H[4 * r + 3] = v.w; else if (4 * r + 3 == NB) S = v.w;
         }
         if (M.tangential) { const double4 v = hp[(size_t)M.rec_shear * P.lcap]; h[0] = v.x; h[1] = v.y; h[2] = v.z; }
         if (HAS_ROLL_HIST) { const double4 v = hp[(size_t)M.rec_roll * P.lcap]; g[0] = v.x; g[1] = v.y; g[2] = v.z; }
@@ -587,15 +604,16 @@ __global__ void __launch_bounds__(128) k_step_bond(const StepP P)
 #pragma unroll
         for (int r = 0; r < (COH == C_BOND ? 4 : 8); r++) {
           double4 v;
-          v.x = 4 * r < M.nbond ? H[4 * r] : (4 * r == M.nbond ? S : 0.0);
-          v.y = 4 * r + 1 < M.nbond ? H[4 * r + 1] : (4 * r + 1 == M.nbond ? S : 0.0);
-          v.z = 4 * r + 2 < M.nbond ? H[4 * r + 2] : (4 * r + 2 == M.nbond ? S : 0.0);
-          v.w = 4 * r + 3 < M.nbond ? H[4 * r + 3] : (4 * r + 3 == M.nbond ? S : 0.0);
+          v.x = 4 * r < NB ? H[4 * r] : (4 * r == NB ? S : 0.0);
+          v.y = 4 * r + 1 < NB ? H[4 * r + 1] : (4 * r + 1 == NB ? S : 0.0);
+          v.z = 4 * r + 2 < NB ? H[4 * r + 2] : (4 * r + 2 == NB ? S : 0.0);
+          v.w = 4 * r + 3 < NB ? H[4 * r + 3] : (4 * r + 3 == NB ? S : 0.0);
           st4(hp + (size_t)(M.rec_bond + r) * P.lcap, v);
         }
         if (M.tangential) st4(hp + (size_t)M.rec_shear * P.lcap, make_double4(h[0], h[1], h[2], 0.));
         if (HAS_ROLL_HIST) st4(hp + (size_t)M.rec_roll * P.lcap, make_double4(g[0], g[1], g[2], 0.));
       }
+    }
     }
     if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
     (void)itype; (void)imask;
