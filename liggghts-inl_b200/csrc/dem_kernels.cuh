@@ -302,6 +302,28 @@ __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const doubl
 #ifndef DEM_STEP_WAVE_PREFETCH
 #define DEM_STEP_WAVE_PREFETCH 200  // blocks ahead whose streaming inputs are pulled towards L2 (0 = off); measured r01c
 #endif
+// Touch sweep as its own light kernel (40 registers, full occupancy), option "split_sweep" (measured slower than the fused
+// walk, see launch_step; kept as the measured alternative): the row walk is pure gather latency.  One thread per particle: 8 neighbour words, then 8 position gathers
+// in flight, verdicts of the first 64 row entries as one 64-bit mask (rows longer than that: k_step sweeps the rest).
+// Used when the contact-distance factor is 1 (no surfacesClose band), i.e. for every plain contact model deck.
+__global__ void __launch_bounds__(256) k_sweep(const StepP P)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nlocal || step_gated(P)) return;
+  const double4 xi = ldg4(P.xr + i);
+  const int nn = min(P.numneigh[i] & 0xffff, 64);
+  unsigned long long touch = 0ull;
+#pragma unroll 8
+  for (int kk = 0; kk < nn; kk++) {
+    const unsigned w = P.nbr[(size_t)kk * P.lcap + i];
+    const double4 xj = ldg4(P.xr + (w & NBR_IDX));
+    const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+    const double radsum = xi.w + xj.w;
+    touch |= (unsigned long long)(rsq < __dmul_rn(radsum, radsum)) << kk;
+  }
+  P.tmask[i] = touch;
+}
+
 template <int NORMAL, int ROLLING, bool ONE>
 __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
@@ -352,6 +374,9 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       const int kn = min(64, nn - k0);
       unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
       // (1a) branch-free sweep: 8 neighbour words, then 8 position gathers in flight per thread
+      // (or the verdict of the k_sweep pre-pass for the first 64 entries)
+      if (P.tmask && k0 == 0) touch = P.tmask[i];
+      else
 #pragma unroll 8
       for (int kk = 0; kk < kn; kk++) {
         const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
@@ -494,8 +519,11 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 // contact_flags stay != 0 after the first touch (CONTACT_NORMAL_MODEL is never cleared) and are reset to 1 for rows kept by
 // a rebuild (neigh_gran.cpp:596-612), while CONTACT_COHESION_MODEL follows the bond; "flag != 0" == (S != 0 || bondFlag != 0).
 // Chain order per contact_models.h:228-253: surface, normal, cohesion, tangential, rolling.
+#ifndef DEM_BOND_MINBLOCKS
+#define DEM_BOND_MINBLOCKS 2
+#endif
 template <int NORMAL, int ROLLING, int COH>
-__global__ void __launch_bounds__(128) k_step_bond(const StepP P)
+__global__ void __launch_bounds__(128, DEM_BOND_MINBLOCKS) k_step_bond(const StepP P)
 {
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
