@@ -311,7 +311,7 @@ def own_arm(args):
     torch.cuda.synchronize()
     t3 = time.perf_counter()
     t_e2e = allmax(t3 - t0)
-    h2d = allsum(int(eng2.nlocal) * (3 * 32 + 4 + 8))
+    h2d = allsum(sum(int(cp[k].nbytes) for k in ("tag", "type", "mask", "x", "v", "omega", "radius", "density")))  # every rank receives the whole set and keeps its brick
     d2h = allsum(xo.nbytes + vo.nbytes + 2 * len(xo) * 4)
     e2e = {"value": n * ke / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / ke, "d2h_bytes_per_step": d2h / ke,
            "job": "create + upload(page-locked host arrays) + setup + run(%d) + download x,v; %.3f s (create+upload %.3f, setup %.3f, run+download %.3f on rank 0)"

@@ -867,6 +867,8 @@ extern "C" int dem_decomposition(dem_engine *e, int pgrid[3], int myloc[3], doub
   API_END
 }
 
+static void ensure_cub(dem_engine *E, size_t n);
+static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &scan, DevBuf<int> &list);
 extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
                                     const double *v, const double *omega, const double *radius, const double *density)
 {
@@ -878,6 +880,61 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
   e->xh.release(); e->tag.release(); e->density.release(); e->f.release(); e->tq.release(); e->whist.release();
   setup_decomposition(e);
+  if (e->nranks > 1 && n > 0 && !getenv("DEM_B200_HOST_UPLOAD")) {
+    // several bricks: every rank ships the caller's arrays as they are; the brick's particles are selected, compacted (in
+    // input order) and packed into records on the device
+    cudaStream_t st = e->stream;
+    const size_t nd = (size_t)n;
+    const size_t bytes = nd * (3 + 3 + 3 + 1 + 1) * sizeof(double) + nd * 3 * sizeof(int) + 64;
+    e->stage.ensure(e, bytes);
+    double *dx = (double *)e->stage.p, *dv = dx + 3 * nd, *dw = dv + 3 * nd, *dr = dw + 3 * nd, *dd = dr + nd;
+    int *dt = (int *)(dd + nd), *dm = dt + nd, *dg = dm + nd;
+    CK(cudaMemcpyAsync(dx, x, 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (v) CK(cudaMemcpyAsync(dv, v, 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (omega) CK(cudaMemcpyAsync(dw, omega, 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dr, radius, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dd, density, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dt, type, nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (mask) CK(cudaMemcpyAsync(dm, mask, nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg, tag, nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    e->counters.ensure(e, 2);
+    CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    MineP B;
+    for (int d = 0; d < 3; d++) {
+      B.lo[d] = e->lo[d]; B.hi[d] = e->hi[d]; B.prd[d] = e->prd[d]; B.sublo[d] = e->sublo[d]; B.subhi[d] = e->subhi[d];
+      B.periodic[d] = e->periodic[d]; B.first[d] = e->myloc[d] == 0; B.last[d] = e->myloc[d] == e->pgrid[d] - 1;
+    }
+    e->flo.ensure(e, nd + 1); e->slo.ensure(e, nd + 1);
+    ensure_cub(e, nd);
+    k_flag_mine<<<GRID(n, 256), 256, 0, st>>>((int)n, dx, dr, dd, dt, dg, e->ntypes, B, e->flo.p, (int *)(e->counters.p + 1), e->counters.p);
+    e->launches++;
+    DevBuf<int> list;
+    const int nmine = compact_flags(e, (int)n, e->flo, e->slo, list);
+    const double cf = e->opt.count("cap_factor") ? e->opt["cap_factor"] : 1.5;
+    ensure_particle_cap(e, std::max<long>((long)(nmine * cf) + 1024, 1024), 0);
+    e->cur = 0;
+    if (nmine) {
+      k_pack_upload_sel<<<GRID(nmine, 256), 256, 0, st>>>(nmine, list.p, dx, v ? dv : nullptr, omega ? dw : nullptr, dr, dd, dt, mask ? dm : nullptr, dg,
+                                                          e->xr[0].p, e->vm[0].p, e->wt[0].p, e->tag.p, e->density.p);
+      e->launches++;
+    }
+    CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), st));
+    unsigned long long hc[2];
+    CK(cudaMemcpyAsync(hc, e->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    list.release();
+    const int errbits = (int)(hc[1] & 0xffffffffu);
+    if (errbits & 1) dem_fail(e, DEM_ERR_ARG, "Invalid atom type in particle data");
+    if (errbits & 2) dem_fail(e, DEM_ERR_ARG, "Invalid radius or density in particle data");
+    if (errbits & 4) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
+    double rmaxd; memcpy(&rmaxd, &hc[0], 8);
+    { double rm = 1e300; for (long i = 0; i < n; i++) rm = std::min(rm, radius[i]); e->rmin = rm; }
+    e->nlocal = nmine; e->nghost = 0; e->rmax = rmaxd;
+    e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0; e->mesh_ready = 0;
+    e->ls[0].valid = e->ls[1].valid = 0;
+    e->ntimestep = 0;
+    return DEM_OK;
+  }
   if (e->nranks == 1 && n > 0) {
     // single brick: ship the caller's arrays as they are and build the records on the device
     const double cf = e->opt.count("cap_factor") ? e->opt["cap_factor"] : 1.25;
@@ -1554,10 +1611,10 @@ static void launch_step(dem_engine *E, int mode, bool timed)
     if ((long)E->ev.size() < 2 * (E->ev_used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); E->ev.push_back(a); E->ev.push_back(b); }
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
   }
-  // split sweep (option "split_sweep" 1, default off): needs cdf == 1 (no surfacesClose band) and a plain contact model.
+  // split sweep (build with -DDEM_SPLIT_SWEEP=1, then option "split_sweep" 1): needs cdf == 1 (no surfacesClose band) and a plain contact model.
   // Measured r01n on the 4.19M bed: k_sweep + k_step 1.303 ms against 1.253 ms fused -- the row walk's gathers double as the
   // prefetch of the contact phase's partner positions, so splitting it off only moves the latency.
-  const bool split = E->have_pair && !E->pm.cohesion && E->cdf == 1.0 && E->opt.count("split_sweep") && E->opt["split_sweep"] != 0;
+  const bool split = DEM_SPLIT_SWEEP && E->have_pair && !E->pm.cohesion && E->cdf == 1.0 && E->opt.count("split_sweep") && E->opt["split_sweep"] != 0;
   if (split) {
     E->tmask.ensure(E, E->cap);
     P.tmask = E->tmask.p;

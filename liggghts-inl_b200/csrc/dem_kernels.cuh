@@ -164,6 +164,15 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #ifndef DEM_MMAX
 #define DEM_MMAX 8       // such "mirror" entries per particle (more: evaluated by both sides as before)
 #endif
+#ifndef DEM_SPLIT_SWEEP
+#define DEM_SPLIT_SWEEP 0  // 1: compiles the k_sweep pre-pass path in (then option "split_sweep" 1 selects it); measured slower, see launch_step
+#endif
+#ifndef DEM_PIPE
+#define DEM_PIPE 0  // 1: software-pipelined contact phase -- the operands of round r+1 are loaded while round r is evaluated.
+                    //    Measured r01o (4.19M bed), parity green: 1.53 ms at 5 blocks/SM (96 registers, spills), 1.30 ms at 4 blocks/SM
+                    //    (128 registers) against 1.25 ms un-pipelined at 5 blocks/SM: the extra 32 live registers cost more than the
+                    //    hidden gather latency returns.  Off.
+#endif
 #ifndef DEM_CPREFETCH
 #define DEM_CPREFETCH 2  // L2 prefetch of a staged contact's operands: 0 none, 1 history rows, 2 history + partner v|m, omega|bits
 #endif
@@ -178,12 +187,28 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 // pair_chain); history records are stored in the canonical orientation "lower tag first" (sign
 // flipped on load/store when the partner is the first body).  nh = the particle's count of history
 // slots in use (a shared-memory counter: in the cooperative phase several lanes may serve one particle).
+// the global operands of one staged contact: partner records and the pair's history records (as stored)
+struct PairOps { double4 xj, vj, wj, hs, hr; };
+template <int ROLLING>
+__device__ __forceinline__ void pair_fetch(const StepP &P, int i, unsigned w, PairOps &o)
+{
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  const int j = (int)(w & NBR_IDX);
+  const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+  o.xj = ldg4(P.xr + j); o.vj = ldg4(P.vm + j); o.wj = ldg4(P.wt + j);
+  o.hs = make_double4(0., 0., 0., 0.); o.hr = o.hs;
+  if (slot >= 0) {
+    const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
+    if (P.pm.tangential) o.hs = hp[(size_t)P.pm.rec_shear * P.lcap];
+    if (HAS_ROLL_HIST) o.hr = hp[(size_t)P.pm.rec_roll * P.lcap];
+  }
+}
 template <int NORMAL, int ROLLING, bool ONE>
 __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
                                              const double4 &wi, bool su, int *nh, double *F, double *T,
                                              const double4 (*srec)[128], unsigned bbase, unsigned blim,
-                                             unsigned reg = 0u, int iwarp = 0, double *Tm = nullptr)
-{  // reg != 0: the pair is evaluated ONCE for both bodies (the partner sits in the same warp, lane reg & 31, and keeps its
+                                             unsigned reg = 0u, int iwarp = 0, double *Tm = nullptr, const PairOps *pre = nullptr)
+{  // pre: operands fetched ahead of time (software-pipelined contact phase), else they are loaded here  // reg != 0: the pair is evaluated ONCE for both bodies (the partner sits in the same warp, lane reg & 31, and keeps its
    // copy of the history in its slot ((reg >> 5) & 63) - 1): Tm receives the partner's torque, the partner's force is -F
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int j = (int)(w & NBR_IDX);
@@ -193,10 +218,11 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   // Morton sort about half of all partners): a scattered 32-byte global gather costs one L1 wavefront per lane
   const unsigned jl = (unsigned)j - bbase;
   double4 xj, vj, wj;
-  if (DEM_INBLOCK && jl < blim) { xj = srec[0][jl]; vj = srec[1][jl]; wj = srec[2][jl]; }
-  else { xj = ldg4(P.xr + j); vj = ldg4(P.vm + j); wj = ldg4(P.wt + j); }
   double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
-  if (had) {
+  if (pre) { xj = pre->xj; vj = pre->vj; wj = pre->wj; hs = pre->hs; hr = pre->hr; }
+  else if (DEM_INBLOCK && jl < blim) { xj = srec[0][jl]; vj = srec[1][jl]; wj = srec[2][jl]; }
+  else { xj = ldg4(P.xr + j); vj = ldg4(P.vm + j); wj = ldg4(P.wt + j); }
+  if (had && !pre) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
     if (P.pm.tangential) hs = hp[(size_t)P.pm.rec_shear * P.lcap];
     if (HAS_ROLL_HIST) hr = hp[(size_t)P.pm.rec_roll * P.lcap];
@@ -375,8 +401,10 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
       // (1a) branch-free sweep: 8 neighbour words, then 8 position gathers in flight per thread
       // (or the verdict of the k_sweep pre-pass for the first 64 entries)
+#if DEM_SPLIT_SWEEP
       if (P.tmask && k0 == 0) touch = P.tmask[i];
       else
+#endif
 #pragma unroll 8
       for (int kk = 0; kk < kn; kk++) {
         const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
@@ -458,20 +486,39 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   {
     // rounds of 32 items; results are parked in shared memory and each owner adds its items (in list order) once per
     // window of DEM_RWIN rounds -- one short loop per window instead of one per round
+    // item t belongs to the last lane whose first item is <= t (binary search over the warp's prefix sums)
+    [[maybe_unused]] auto locate = [&](int t, int &q, unsigned &w) {
+      int p = 0;
+#pragma unroll
+      for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
+      q = wb + p;
+      w = s_w[t - s_off[q]][q];
+    };
+#if DEM_PIPE
+    int q_n = wb; unsigned w_n = 0u; PairOps o_n;
+    if (lane < total) { locate(lane, q_n, w_n); pair_fetch<ROLLING>(P, i - tid + q_n, w_n, o_n); }
+#endif
     for (int b0 = 0; b0 < total; b0 += 32 * DEM_RWIN) {
       const int bend = min(total, b0 + 32 * DEM_RWIN);
       for (int t0 = b0; t0 < bend; t0 += 32) {
         const int t = t0 + lane;
         double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.}, rM[3] = {0., 0., 0.};
+#if DEM_PIPE
+        int q = q_n; unsigned w = w_n; PairOps o = o_n;  // operands fetched during the previous round; start the next round's loads
+        if (t + 32 < total) { locate(t + 32, q_n, w_n); pair_fetch<ROLLING>(P, i - tid + q_n, w_n, o_n); }
+#endif
         if (t < total) {
+#if !DEM_PIPE
           int p = 0;  // owner of item t: the last lane whose first item is <= t
 #pragma unroll
           for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
           const int q = wb + p;
           const unsigned w = s_w[t - s_off[q]][q];
+          const PairOps o = {};
+#endif
           const unsigned reg = DEM_PAIRSHARE ? (unsigned)s_reg[t - s_off[q]][q] : 0u;
           pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT, s_rec, bbase, blim,
-                                             reg, i - lane, DEM_PAIRSHARE ? rM : nullptr);
+                                             reg, i - lane, DEM_PAIRSHARE ? rM : nullptr, DEM_PIPE ? &o : nullptr);
           const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
@@ -1107,6 +1154,51 @@ __global__ void __launch_bounds__(256) k_pack_upload(int n, const double *x, con
   unsigned long long b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0);
   for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b; }
   if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, b);  // positive doubles order like their bit patterns
+}
+// multi-rank upload: every rank receives the whole particle set and keeps its brick.  Ownership test on the wrapped
+// position (Domain::pbc + sub-box, like read_data.cpp / atom.cpp data_atoms); validity checks and the global maximum
+// radius run over ALL particles.  flag[i] = 1 when the particle is mine.
+struct MineP { double lo[3], hi[3], prd[3], sublo[3], subhi[3]; int periodic[3], first[3], last[3]; };
+__global__ void __launch_bounds__(256) k_flag_mine(int n, const double *x, const double *radius, const double *density, const int *type, const int *tag,
+                                                   int ntypes, const MineP B, int *flag, int *err, unsigned long long *rmax_bits)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long b = 0ull;
+  if (i < n) {
+    const double r = radius[i], rho = density[i];
+    const int t = type[i];
+    if (t < 1 || t > ntypes) atomicOr(err, 1);
+    if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
+    if (tag[i] <= 0) atomicOr(err, 4);
+    bool mine = true;
+    for (int d = 0; d < 3 && mine; d++) {
+      double c = x[3 * i + d];
+      if (B.periodic[d]) { if (c < B.lo[d]) c += B.prd[d]; if (c >= B.hi[d]) { c -= B.prd[d]; c = fmax(c, B.lo[d]); } }
+      const bool lo_ok = c >= B.sublo[d] || (B.first[d] && !B.periodic[d]);
+      const bool hi_ok = c < B.subhi[d] || (B.last[d] && !B.periodic[d]);
+      mine = lo_ok && hi_ok;
+    }
+    flag[i] = mine ? 1 : 0;
+    b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0);
+  }
+  for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b; }
+  if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, b);
+}
+// records of the selected particles (ascending original index, like the host loop it replaces)
+__global__ void __launch_bounds__(256) k_pack_upload_sel(int nsel, const int *list, const double *x, const double *v, const double *omega, const double *radius,
+                                                         const double *density, const int *type, const int *mask, const int *tag,
+                                                         double4 *xr, double4 *vm, double4 *wt, int *otag, double *odensity)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nsel) return;
+  const int i = list[q];
+  const double r = radius[i], rho = density[i];
+  const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;  // atom_vec_sphere.cpp:1078
+  xr[q] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
+  vm[q] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
+  wt[q] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0.,
+                       __longlong_as_double(pack_bits(type[i], mask ? mask[i] : 1)));
+  otag[q] = tag[i]; odensity[q] = rho;
 }
 // read-back in ascending tag order: field 0..2 = xyz of a record array, 3 = .w, 4 = type, 5 = mask
 __global__ void __launch_bounds__(256) k_gather_out(int n, const int *order, const double4 *rec, int what, double *outd, int *outi)
