@@ -691,6 +691,15 @@ static void mesh_prepare(dem_engine *E)
     if (H.wall >= 0) E->mhrec = std::max(E->mhrec, E->mwalls[H.wall].m.hrec);
     if (H.moving) E->any_moving = 1;
   }
+  {  // coplanar node-neighbour lists: (count, entries...) per triangle -> CSR [ntri+1 offsets into the same array][entries]
+    const size_t T = E->htri.size();
+    std::vector<int> csr(T + 1, 0), ent;
+    size_t r = 0;
+    for (size_t t = 0; t < T; t++) { const int c = E->hcn[r++]; csr[t] = (int)(T + 1 + ent.size()); ent.insert(ent.end(), E->hcn.begin() + r, E->hcn.begin() + r + c); r += c; }
+    csr[T] = (int)(T + 1 + ent.size());
+    csr.insert(csr.end(), ent.begin(), ent.end());
+    E->hcn.swap(csr);
+  }
   if (E->opt.count("meshslots")) E->mslots = std::min(30, std::max(2, (int)E->opt["meshslots"]));
   if (E->opt.count("meshcand")) E->mcand = std::max(4, (int)E->opt["meshcand"]);
   cudaStream_t st = E->stream;

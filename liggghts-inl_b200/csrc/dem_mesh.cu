@@ -213,8 +213,8 @@ __device__ __noinline__ void mesh_chain(const StepP &P, const ModelP &m, const C
 
 __device__ __forceinline__ bool coplanar_nn(const MeshP &M, int a, int b)
 {  // SurfaceMesh::areCoplanarNodeNeighs surface_mesh_I.h:921-958, precomputed per triangle on the host
-  const int *l = M.cn + (size_t)a * DEM_MAXCN;
-  for (int k = 0; k < DEM_MAXCN; k++) { const int q = l[k]; if (q < 0) return false; if (q == b) return true; }
+  int lo = M.cn[a], hi = M.cn[a + 1];  // ascending list: binary search
+  while (lo < hi) { const int mid = (lo + hi) >> 1; const int q = M.cn[mid]; if (q == b) return true; if (q < b) lo = mid + 1; else hi = mid; }
   return false;
 }
 

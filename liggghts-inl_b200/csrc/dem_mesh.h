@@ -18,7 +18,6 @@
 namespace dem {
 
 #define DEM_MAXMESH 8
-#define DEM_MAXCN 24  // coplanar node-neighbours kept per triangle
 
 struct TriRec {  // one triangle, 320 bytes: everything the contact and candidate kernels gather
   double node[9], edgeVec[9], edgeNorm[9], edgeLen[3], surfNorm[3], center[3], rbound;
@@ -42,7 +41,8 @@ struct MeshP {
   int hrec;    // 32-byte history records per contact row (max over the mesh walls)
   TriRec *tri;
   double *nodes_last;   // [9][ntri] node positions at the last rebuild (moving meshes)
-  const int *cn;        // [ntri][DEM_MAXCN] coplanar node-neighbours, -1 padded
+  const int *cn;        // coplanar node-neighbours of triangle t: cn[t] .. cn[t+1] index into this same array (CSR: ntri+1 offsets, then the
+                        // ascending lists) -- no fixed width: a flat fan of 256 triangles has 255 of them per triangle
   // coarse uniform grid over the box: cell -> ascending triangle ids (CSR)
   const int *cell_start, *cell_tri;
   double gorg[3], ginv[3];

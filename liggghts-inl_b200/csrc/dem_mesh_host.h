@@ -186,9 +186,9 @@ inline std::string derive(const double lo[3], const double hi[3], MeshHost &M, i
       }
     }
   }
-  // 4. flags, coplanar node-neighbours
+  // 4. flags, coplanar node-neighbours (variable-length lists)
   M.edge_active.assign(3 * (size_t)T, 0); M.corner_active.assign(3 * (size_t)T, 0); M.obtuse.assign(T, -1); M.nneighs = nN;
-  cn.resize((base + T) * DEM_MAXCN, -1);
+  std::vector<std::vector<int>> cnl(T);
   for (int t = 0; t < T; t++) {
     int ob = -1;  // what survives calcObtuseAngleIndex's three overwriting calls is node 2's verdict
     for (int i = 0; i < 3; i++) ob = dot(R[t].edgeVec + 3 * i, R[t].edgeVec + 3 * ((i + 2) % 3)) > 0. ? i : -1;
@@ -201,12 +201,10 @@ inline std::string derive(const double lo[3], const double hi[3], MeshHost &M, i
     for (int k = 0; k < std::min(nN[t], 5); k++) cand.push_back(nf[(size_t)t * 5 + k]);
     std::sort(cand.begin(), cand.end());
     cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-    int n = 0;
-    for (int b : cand) if (std::fabs(dot(R[t].surfNorm, R[b].surfNorm)) > M.curvature) {
-      if (n == DEM_MAXCN) return "mesh " + M.id + ": triangle " + std::to_string(t) + " has more than " + std::to_string(DEM_MAXCN) + " coplanar node-neighbours";
-      cn[(base + t) * DEM_MAXCN + n++] = (int)base + b;
-    }
+    for (int b : cand) if (std::fabs(dot(R[t].surfNorm, R[b].surfNorm)) > M.curvature) cnl[t].push_back((int)base + b);  // ascending
   }
+  // `cn` collects the lists of all meshes so far as [triangle][list]; dem_engine.cu flattens it to CSR once every mesh is derived
+  for (int t = 0; t < T; t++) { cn.push_back((int)cnl[t].size()); cn.insert(cn.end(), cnl[t].begin(), cnl[t].end()); }
   return "";
 }
 

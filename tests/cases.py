@@ -146,7 +146,7 @@ def mesh_drum(cx, cz, R, y0, y1, nseg=12):
 
 
 def case_mesh(kind="box", n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdt", seed=SEED, poly=True,
-              name="mesh", move=None, settings=""):
+              name="mesh", move=None, settings="", nseg=12):
     """particles falling into triangle-mesh geometry (fix mesh/surface + fix wall/gran ... mesh)"""
     c = case_box(n3=n3, model=model, seed=seed, poly=poly, name=name, settings=settings)
     L = c["hi"][0]; H = c["hi"][2]
@@ -170,7 +170,7 @@ def case_mesh(kind="box", n3=(4, 4, 4), model="model hertz tangential history ro
     elif kind == "drum":    # particles inside a closed drum rotating about its (y) axis (fix move/mesh rotate)
         cx, cz, R = 0.5 * L, 0.62 * L, 0.62 * L
         c["x"][:, 2] += 0.22 * L
-        c["meshes"] = [("drum", 1, mesh_drum(cx, cz, R, -0.12 * L, 1.12 * L))]
+        c["meshes"] = [("drum", 1, mesh_drum(cx, cz, R, -0.12 * L, 1.12 * L, nseg=nseg))]
         c["mesh_moves"] = [("drum", "rotate origin %.17g 0. %.17g axis 0. 1. 0. period %s" % (cx, cz, move if move is not None else 0.25))]
         c["lo"] = [cx - 1.1 * R, -0.2 * L, cz - 1.1 * R]; c["hi"] = [cx + 1.1 * R, 1.2 * L, cz + 1.1 * R]
     c["mesh_walls"] = [("mw", model + " mesh n_meshes %d meshes %s" % (len(c["meshes"]), " ".join(m[0] for m in c["meshes"])) + st)]

@@ -64,6 +64,7 @@ def test_engine_matches_oracle_bed(kw):
     ("funnel", dict(n3=(9, 9, 7))),
     ("plate", dict(n3=(8, 8, 6), model="model hooke tangential history rolling_friction epsd2")),
     ("drum", dict(n3=(8, 8, 6), model="model hertz tangential history rolling_friction epsd", move=0.2)),
+    ("drum", dict(n3=(8, 8, 6), move=0.3, nseg=40)),  # end caps = flat fans of 40 triangles: 39 coplanar node-neighbours per triangle
 ])
 def test_mesh_walls_match_oracle(kind, kw):
     """~700 particles in triangle-mesh geometry, 3000 steps incl. rebuilds (a moving plate, a rotating drum): mesh contact

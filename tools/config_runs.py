@@ -4,6 +4,7 @@
   C3  1,000,000 spheres falling into triangle-mesh geometry (box of 2 x 40 x 40 floor triangles + walls, 128-segment
       funnel = 256 triangles), hertz/history/cdt on `fix wall/gran ... mesh`
   C4  499,200 bonded spheres (INL bond/nonlinear, bonds created at step 2), hertz/history
+  C5brick  2,252,800 spheres in a rotating 256-segment drum (`fix move/mesh rotate`): one GPU's share of configs[4]
 Each prints one JSON line: particle-steps/s over the timed window, list/contact statistics, rebuilds, and sanity checks
 (no particle lost, finite state).  usage (GPU box): python tools/config_runs.py [C1 C3 C4]"""
 import json
@@ -29,6 +30,12 @@ def make(name):
         return c, 20, 300
     if name == "C4":
         return cases.case_box(n3=(80, 80, 78), model="model hertz tangential history", poly=True, name="C4", bond=dict(kind="bond/nonlinear")), 10, 200
+    if name == "C5brick":  # one GPU's share of the 16M-sphere drum of configs[4]: 2.25M spheres in a rotating 256-segment drum
+        c = cases.case_mesh(kind="drum", n3=(160, 160, 88), name="C5brick", poly=True, move=2.0)
+        L = 160 * 2.05 * 0.003
+        c["x"][:, 2] += 0.62 * L - 0.5 * (c["x"][:, 2].min() + c["x"][:, 2].max())  # bed centred on the drum axis
+        c["meshes"] = [("drum", 1, cases.mesh_drum(0.5 * L, 0.62 * L, 0.62 * L, -0.12 * L, 1.12 * L, nseg=256))]
+        return c, 20, 300
     raise SystemExit("unknown config " + name)
 
 
