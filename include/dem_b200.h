@@ -43,6 +43,13 @@ int dem_nccl_unique_id(void *out128);
 /* the brick this rank owns (processor grid, grid position, sub-box): Comm::set_proc_grid  src/comm.cpp,
  * Domain::set_local_box  src/domain.cpp.  Pure host logic, valid after dem_set_box / dem_set_processors.  */
 int dem_decomposition(dem_engine *e, int pgrid[3], int myloc[3], double sublo[3], double subhi[3]);
+/* The same decomposition without an engine or a GPU (pure host): brick of `rank`, its face neighbours
+ * (neigh[2*d], neigh[2*d+1] = lower / upper neighbour in dimension d, -1 = none) and mine[i] = 1 for the positions this
+ * rank would keep at dem_upload_particles.  procgrid: {px,py,pz} as `processors`, or NULL / zeros for the engine's choice.
+ *                                                   src/comm_brick.cpp:215-330, src/procmap.cpp                  */
+int dem_brick_layout(int nranks, int rank, const double lo[3], const double hi[3], const int periodic[3], const int *procgrid,
+                     int pgrid[3], int myloc[3], double sublo[3], double subhi[3], int neigh[6],
+                     long n, const double *x, int *mine);
 const char *dem_last_error(const dem_engine *e);
 /* Device blocks released by engines are kept in a process-wide cache for the next engine (set DEM_B200_NO_CACHE=1 to
  * switch it off); this returns them to the driver and reports the bytes freed.                                        */

@@ -876,6 +876,41 @@ extern "C" int dem_decomposition(dem_engine *e, int pgrid[3], int myloc[3], doub
   API_END
 }
 
+static MineP brick_params(const dem_engine *e)
+{
+  MineP B;
+  for (int d = 0; d < 3; d++) {
+    B.lo[d] = e->lo[d]; B.hi[d] = e->hi[d]; B.prd[d] = e->prd[d]; B.sublo[d] = e->sublo[d]; B.subhi[d] = e->subhi[d];
+    B.periodic[d] = e->periodic[d]; B.first[d] = e->myloc[d] == 0; B.last[d] = e->myloc[d] == e->pgrid[d] - 1;
+  }
+  return B;
+}
+// Decomposition without a device: the brick of `rank` among `nranks` over a box (processors grid optional: px*py*pz == nranks,
+// or null / zeros for the engine's own choice), its six face neighbours (-1 = none) and, for `n` positions, whether this rank
+// owns them -- the very functions dem_upload_particles and the halo code use (procmap.cpp / comm_brick.cpp:215-330 analogue).
+// Needs no GPU: lets multi-process host logic be tested with any torch.distributed backend.
+extern "C" int dem_brick_layout(int nranks, int rank, const double lo[3], const double hi[3], const int periodic[3], const int *procgrid,
+                                int pgrid[3], int myloc[3], double sublo[3], double subhi[3], int neigh[6],
+                                long n, const double *x, int *mine)
+{
+  if (nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi || !periodic) return DEM_ERR_ARG;
+  dem_engine E;
+  E.nranks = nranks; E.rank = rank;
+  for (int d = 0; d < 3; d++) { E.lo[d] = lo[d]; E.hi[d] = hi[d]; E.prd[d] = hi[d] - lo[d]; E.periodic[d] = periodic[d]; if (!(hi[d] > lo[d])) return DEM_ERR_ARG; }
+  if (procgrid && procgrid[0] * procgrid[1] * procgrid[2] != 0) {
+    if (procgrid[0] * procgrid[1] * procgrid[2] != nranks) return DEM_ERR_ARG;
+    for (int d = 0; d < 3; d++) E.pgrid[d] = procgrid[d];
+    E.user_grid = 1;
+  }
+  setup_decomposition(&E);
+  for (int d = 0; d < 3; d++) {
+    if (pgrid) pgrid[d] = E.pgrid[d]; if (myloc) myloc[d] = E.myloc[d]; if (sublo) sublo[d] = E.sublo[d]; if (subhi) subhi[d] = E.subhi[d];
+    if (neigh) { neigh[2 * d] = E.pgrid[d] > 1 ? neighbor_rank(&E, d, -1) : -1; neigh[2 * d + 1] = E.pgrid[d] > 1 ? neighbor_rank(&E, d, 1) : -1; }
+  }
+  if (n > 0 && x && mine) { const MineP B = brick_params(&E); for (long i = 0; i < n; i++) mine[i] = brick_owns(B, x + 3 * i) ? 1 : 0; }
+  return DEM_OK;
+}
+
 static void ensure_cub(dem_engine *E, size_t n);
 static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &scan, DevBuf<int> &list);
 extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
@@ -908,11 +943,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     CK(cudaMemcpyAsync(dg, tag, nd * sizeof(int), cudaMemcpyHostToDevice, st));
     e->counters.ensure(e, 2);
     CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), st));
-    MineP B;
-    for (int d = 0; d < 3; d++) {
-      B.lo[d] = e->lo[d]; B.hi[d] = e->hi[d]; B.prd[d] = e->prd[d]; B.sublo[d] = e->sublo[d]; B.subhi[d] = e->subhi[d];
-      B.periodic[d] = e->periodic[d]; B.first[d] = e->myloc[d] == 0; B.last[d] = e->myloc[d] == e->pgrid[d] - 1;
-    }
+    const MineP B = brick_params(e);
     e->flo.ensure(e, nd + 1); e->slo.ensure(e, nd + 1);
     ensure_cub(e, nd);
     k_flag_mine<<<GRID(n, 256), 256, 0, st>>>((int)n, dx, dr, dd, dt, dg, e->ntypes, B, e->flo.p, (int *)(e->counters.p + 1), e->counters.p);
@@ -997,17 +1028,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * density[i];  // atom_vec_sphere.cpp:1078
     rmax = std::max(rmax, r);  // global maximum: every rank sees the full set
     e->rmin = (i == 0) ? r : std::min(e->rmin, r);
-    if (e->nranks > 1) {  // ownership test on the wrapped position (Domain::pbc + sub-box, like read_data)
-      bool mine = true;
-      for (int d = 0; d < 3 && mine; d++) {
-        double c = x[3 * i + d];
-        if (e->periodic[d]) { if (c < e->lo[d]) c += e->prd[d]; if (c >= e->hi[d]) { c -= e->prd[d]; c = std::max(c, e->lo[d]); } }
-        const bool lo_ok = c >= e->sublo[d] || (e->myloc[d] == 0 && !e->periodic[d]);
-        const bool hi_ok = c < e->subhi[d] || (e->myloc[d] == e->pgrid[d] - 1 && !e->periodic[d]);
-        mine = lo_ok && hi_ok;
-      }
-      if (!mine) continue;
-    }
+    if (e->nranks > 1 && !brick_owns(brick_params(e), x + 3 * i)) continue;  // ownership on the wrapped position (Domain::pbc + sub-box, like read_data)
     hx.push_back(make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r));
     hv.push_back(make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m));
     const long long bits = pack_bits(type[i], mask ? mask[i] : 1);

@@ -1159,6 +1159,18 @@ __global__ void __launch_bounds__(256) k_pack_upload(int n, const double *x, con
 // position (Domain::pbc + sub-box, like read_data.cpp / atom.cpp data_atoms); validity checks and the global maximum
 // radius run over ALL particles.  flag[i] = 1 when the particle is mine.
 struct MineP { double lo[3], hi[3], prd[3], sublo[3], subhi[3]; int periodic[3], first[3], last[3]; };
+__host__ __device__ __forceinline__ bool brick_owns(const MineP &B, const double *x3)
+{
+  bool mine = true;
+  for (int d = 0; d < 3 && mine; d++) {
+    double c = x3[d];
+    if (B.periodic[d]) { if (c < B.lo[d]) c += B.prd[d]; if (c >= B.hi[d]) { c -= B.prd[d]; c = c > B.lo[d] ? c : B.lo[d]; } }
+    const bool lo_ok = c >= B.sublo[d] || (B.first[d] && !B.periodic[d]);
+    const bool hi_ok = c < B.subhi[d] || (B.last[d] && !B.periodic[d]);
+    mine = lo_ok && hi_ok;
+  }
+  return mine;
+}
 __global__ void __launch_bounds__(256) k_flag_mine(int n, const double *x, const double *radius, const double *density, const int *type, const int *tag,
                                                    int ntypes, const MineP B, int *flag, int *err, unsigned long long *rmax_bits)
 {
@@ -1170,15 +1182,7 @@ __global__ void __launch_bounds__(256) k_flag_mine(int n, const double *x, const
     if (t < 1 || t > ntypes) atomicOr(err, 1);
     if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
     if (tag[i] <= 0) atomicOr(err, 4);
-    bool mine = true;
-    for (int d = 0; d < 3 && mine; d++) {
-      double c = x[3 * i + d];
-      if (B.periodic[d]) { if (c < B.lo[d]) c += B.prd[d]; if (c >= B.hi[d]) { c -= B.prd[d]; c = fmax(c, B.lo[d]); } }
-      const bool lo_ok = c >= B.sublo[d] || (B.first[d] && !B.periodic[d]);
-      const bool hi_ok = c < B.subhi[d] || (B.last[d] && !B.periodic[d]);
-      mine = lo_ok && hi_ok;
-    }
-    flag[i] = mine ? 1 : 0;
+    flag[i] = brick_owns(B, x + 3 * (size_t)i) ? 1 : 0;
     b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0);
   }
   for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b; }

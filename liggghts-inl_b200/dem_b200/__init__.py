@@ -6,4 +6,4 @@ neighbor, timestep, run ...) so that a deck maps 1:1 onto calls.  The CUDA libra
 mandatory: importing works without it (so CPU-only hosts can inspect symbols), but
 creating an Engine raises if libdem_b200.so or a B200 is missing -- there is no CPU path.
 """
-from .engine import Engine, Deck, DemError, Stats, library_path, load_library, ABI_SYMBOLS, read_stl, write_stl  # noqa: F401
+from .engine import Engine, Deck, brick_layout, DemError, Stats, library_path, load_library, ABI_SYMBOLS, read_stl, write_stl  # noqa: F401

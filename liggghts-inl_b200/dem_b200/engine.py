@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_contact_count", "dem_download_mesh_contacts",
-    "dem_trim_memory", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
+    "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
 ]
 
 
@@ -275,6 +275,24 @@ class Engine:
         s = Stats()
         self._call("get_stats", [C.POINTER(Stats)], C.byref(s))
         return s
+
+
+def brick_layout(nranks, rank, lo, hi, periodic, procgrid=None, x=None, lib=None):
+    """decomposition without an engine or a GPU: dict(pgrid, myloc, sublo, subhi, neigh[6], mine[n] or None)"""
+    lib = lib if lib is not None else load_library()
+    f = lib.dem_brick_layout
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_long, C.c_void_p, C.c_void_p]
+    pg = (C.c_int * 3)(); ml = (C.c_int * 3)(); sl = (C.c_double * 3)(); sh = (C.c_double * 3)(); ng = (C.c_int * 6)()
+    n = 0 if x is None else len(x)
+    xs = None if x is None else np.ascontiguousarray(x, np.float64)
+    mine = None if x is None else np.zeros(n, np.int32)
+    rc = f(nranks, rank, (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_int * 3)(*[int(p) for p in periodic]),
+           (C.c_int * 3)(*procgrid) if procgrid else None, pg, ml, sl, sh, ng, n,
+           xs.ctypes.data if xs is not None else None, mine.ctypes.data if mine is not None else None)
+    if rc != 0:
+        raise DemError("dem_brick_layout failed (%d)" % rc)
+    return dict(pgrid=list(pg), myloc=list(ml), sublo=list(sl), subhi=list(sh), neigh=list(ng), mine=mine)
 
 
 class Deck:

@@ -30,6 +30,11 @@ def gather_snapshot(eng, c, rank, world):
     dist.all_gather_object(out, snap)
     if rank != 0:
         return None
+    return merge_snapshots(out, c)
+
+
+def merge_snapshots(out, c):
+    """per-rank snapshots (each with its owned particles' tags) -> one snapshot ordered like a single-process run"""
     tag = np.concatenate([o["tag"] for o in out]); order = np.argsort(tag, kind="stable")
     assert np.array_equal(tag[order], np.sort(c["tag"])), "particles lost or duplicated across ranks"
     merged = {}
