@@ -164,6 +164,14 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #ifndef DEM_MMAX
 #define DEM_MMAX 8       // such "mirror" entries per particle (more: evaluated by both sides as before)
 #endif
+#ifndef DEM_OWNR
+#define DEM_OWNR 12 // upper limit of contacts per particle evaluated by the particle's own lane before the cooperative deal (see k_step (1d));
+                    // 0 = cooperative deal only (1.252 ms on the 4.19M bed), 12 with the cost rule below 1.125 ms, fixed 5: 1.118 ms, all 12: 1.33 ms
+#endif
+#ifndef DEM_COST_OWN
+#define DEM_COST_OWN 3   // relative cost of an own-lane round ...
+#define DEM_COST_COOP 5  // ... and of a cooperative round (measured r01t/r01u on the 4.19M bed)
+#endif
 #ifndef DEM_SPLIT_SWEEP
 #define DEM_SPLIT_SWEEP 0  // 1: compiles the k_sweep pre-pass path in (then option "split_sweep" 1 selects it); measured slower, see launch_step
 #endif
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #define DEM_CMAX 12  // contacts per particle staged in shared memory (more go through the bit-mask path)
 #endif
 #ifndef DEM_RWIN
-#define DEM_RWIN 2   // rounds of 32 contact items whose results are parked in shared memory before the owners add them
+#define DEM_RWIN 1   // rounds of 32 contact items whose results are parked in shared memory before the owners add them
 #endif
 
 // one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see
@@ -453,10 +461,39 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   // (1c) mirror entries register with the item of the lower lane that will evaluate their pair: the item learns where the
   //      partner's copy of the history lives, the mirror entry learns which item's result it has to collect.  Items are
   //      numbered here already (prefix sums over the staged counts).
-  int incl = nc;
+#if DEM_OWNR > 0
+  // (1d) every lane evaluates the first DEM_OWNR contacts of its own particle itself: no owner search, no shared-memory
+  //      round trip of operands and results, and nearly all lanes are busy (few particles have fewer contacts); only the
+  //      contacts beyond that -- where the counts differ from lane to lane -- go through the cooperative deal below.
+  //      The sum order of a particle is unchanged (list order), so results are bit-identical to DEM_OWNR 0.
+  //      How many such rounds: the count that minimises (own rounds) x DEM_COST_OWN + (cooperative rounds of 32 items that
+  //      remain) x DEM_COST_COOP for this warp -- an own round costs the same whatever the number of busy lanes, a cooperative
+  //      round (owner search, operand and result round trip, owner accumulation) costs more but is always full.
+  static_assert(!DEM_PAIRSHARE && !DEM_PIPE, "DEM_OWNR is built for the default contact phase");
+  int ownr = 0;
+  {
+    int best = 0x7fffffff;
+#pragma unroll 1
+    for (int r = 0; r <= DEM_OWNR; r++) {
+      const int rem = __reduce_add_sync(0xffffffffu, max(nc - r, 0));
+      const int cost = r * DEM_COST_OWN + ((rem + 31) >> 5) * DEM_COST_COOP;
+      if (cost < best) { best = cost; ownr = r; }
+      if (rem == 0) break;
+    }
+    const double4 xo = s_rec[0][tid], vo = s_rec[1][tid], wo = s_rec[2][tid];
+#pragma unroll 1
+    for (int r = 0; r < ownr; r++)
+      if (r < nc) pair_contact<NORMAL, ROLLING, ONE>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T, s_rec, bbase, blim);
+  }
+  const int ncc = max(nc - ownr, 0);
+#else
+  constexpr int ownr = 0;
+  const int ncc = nc;
+#endif
+  int incl = ncc;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  const int excl = incl - nc;
+  const int excl = incl - ncc;
   const int total = __shfl_sync(0xffffffffu, incl, 31);
   s_off[tid] = excl;
   __syncwarp();
@@ -513,7 +550,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 #pragma unroll
           for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
           const int q = wb + p;
-          const unsigned w = s_w[t - s_off[q]][q];
+          const unsigned w = s_w[ownr + t - s_off[q]][q];
           const PairOps o = {};
 #endif
           const unsigned reg = DEM_PAIRSHARE ? (unsigned)s_reg[t - s_off[q]][q] : 0u;
