@@ -203,7 +203,6 @@ struct dem_engine {
   ListSet ls[2];
   int lcur = 0;
   DevBuf<int> overflow;
-  DevBuf<unsigned long long> tmask;  // touch masks of the split sweep (k_sweep -> k_step)
   DevBuf<unsigned long long> counters;
   int *hflag = nullptr;  // mapped pinned flags: [0] rebuild trigger, [1] history overflow, [2] moving-mesh trigger
   // triangle-mesh walls (dem_mesh.h)
@@ -327,7 +326,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
-  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->tmask.release();
+  e->cubtmp.release(); e->overflow.release(); e->counters.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
@@ -1640,16 +1639,6 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (tm) {
     if ((long)E->ev.size() < 2 * (E->ev_used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); E->ev.push_back(a); E->ev.push_back(b); }
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
-  }
-  // split sweep (build with -DDEM_SPLIT_SWEEP=1, then option "split_sweep" 1): needs cdf == 1 (no surfacesClose band) and a plain contact model.
-  // Measured r01n on the 4.19M bed: k_sweep + k_step 1.303 ms against 1.253 ms fused -- the row walk's gathers double as the
-  // prefetch of the contact phase's partner positions, so splitting it off only moves the latency.
-  const bool split = DEM_SPLIT_SWEEP && E->have_pair && !E->pm.cohesion && E->cdf == 1.0 && E->opt.count("split_sweep") && E->opt["split_sweep"] != 0;
-  if (split) {
-    E->tmask.ensure(E, E->cap);
-    P.tmask = E->tmask.p;
-    k_sweep<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);
-    E->launches++;
   }
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
   if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }

@@ -153,84 +153,48 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
   for (int d = 0; d < 3; d++) { P.fw[(size_t)d * P.nwcap + cidx] = F[d]; P.fw[(size_t)(3 + d) * P.nwcap + cidx] = T[d]; }
 }
 
-#ifndef DEM_INBLOCK
-#define DEM_INBLOCK 0  // 1: records of partners inside the own block come from shared memory (measured r01d: 1.36 vs 1.25 ms, off)
+// ---- tuning constants of k_step (each set by measurement on the 4,194,304-sphere bed; profiles/)
+#ifndef DEM_CMAX
+#define DEM_CMAX 12  // touching entries per particle staged in shared memory (more: evaluated by the owner on the spot)
 #endif
-#ifndef DEM_PAIRSHARE
-#define DEM_PAIRSHARE 0  // 1: a touching pair whose two particles sit in the same warp (49 % of all contacts after the Morton sort) is
-#endif                   //    evaluated once, by the lower lane's item; the higher lane takes -F and its torque from shared memory.
-                         //    Measured r01h (4.19M bed): parity green, but 1.43-1.61 ms against 1.25 ms -- registration, the second
-                         //    history store and 48 KB of shared memory cost more than the 24 % fewer evaluations save (bound 1.07 ms). Off.
-#ifndef DEM_MMAX
-#define DEM_MMAX 8       // such "mirror" entries per particle (more: evaluated by both sides as before)
+#ifndef DEM_RWIN
+#define DEM_RWIN 1   // cooperative rounds of 32 items whose results are parked in shared memory before the owners add them
 #endif
 #ifndef DEM_OWNR
-#define DEM_OWNR 12 // upper limit of contacts per particle evaluated by the particle's own lane before the cooperative deal (see k_step (1d));
-                    // 0 = cooperative deal only (1.252 ms on the 4.19M bed), 12 with the cost rule below 1.125 ms, fixed 5: 1.118 ms, all 12: 1.33 ms
-#endif
+#define DEM_OWNR 12  // upper limit of contacts per particle evaluated by the particle's own lane before the cooperative deal;
+#endif               // 0 = cooperative deal only (1.252 ms), 12 with the cost rule below 1.125 ms, fixed 5: 1.118 ms, all own: 1.33 ms
 #ifndef DEM_COST_OWN
 #define DEM_COST_OWN 3   // relative cost of an own-lane round ...
-#define DEM_COST_COOP 5  // ... and of a cooperative round (measured r01t/r01u on the 4.19M bed)
+#define DEM_COST_COOP 5  // ... and of a cooperative round (r01t / r01u)
 #endif
-#ifndef DEM_SPLIT_SWEEP
-#define DEM_SPLIT_SWEEP 0  // 1: compiles the k_sweep pre-pass path in (then option "split_sweep" 1 selects it); measured slower, see launch_step
-#endif
-#ifndef DEM_PIPE
-#define DEM_PIPE 0  // 1: software-pipelined contact phase -- the operands of round r+1 are loaded while round r is evaluated.
-                    //    Measured r01o (4.19M bed), parity green: 1.53 ms at 5 blocks/SM (96 registers, spills), 1.30 ms at 4 blocks/SM
-                    //    (128 registers) against 1.25 ms un-pipelined at 5 blocks/SM: the extra 32 live registers cost more than the
-                    //    hidden gather latency returns.  Off.
+#ifndef DEM_SWEEPW
+#define DEM_SWEEPW 5  // row entries per sweep pass = position gathers in flight per thread (4: 1.125 ms, 5: 1.082 ms, 6: 1.215 ms, 8: 1.31 ms -- spills)
 #endif
 #ifndef DEM_CPREFETCH
 #define DEM_CPREFETCH 2  // L2 prefetch of a staged contact's operands: 0 none, 1 history rows, 2 history + partner v|m, omega|bits
 #endif
-#ifndef DEM_CMAX
-#define DEM_CMAX 12  // contacts per particle staged in shared memory (more go through the bit-mask path)
+#ifndef DEM_STEP_MINBLOCKS
+#define DEM_STEP_MINBLOCKS 5    // 96 registers; 4 (128 registers) 1.45 ms, 6 (80 registers, spills) 1.42 ms
 #endif
-#ifndef DEM_RWIN
-#define DEM_RWIN 1   // rounds of 32 contact items whose results are parked in shared memory before the owners add them
+#ifndef DEM_STEP_WAVE_PREFETCH
+#define DEM_STEP_WAVE_PREFETCH 200  // blocks ahead whose streaming inputs are pulled towards L2 (0 = off: 1.31 ms)
 #endif
 
-// one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see
-// pair_chain); history records are stored in the canonical orientation "lower tag first" (sign
-// flipped on load/store when the partner is the first body).  nh = the particle's count of history
-// slots in use (a shared-memory counter: in the cooperative phase several lanes may serve one particle).
-// the global operands of one staged contact: partner records and the pair's history records (as stored)
-struct PairOps { double4 xj, vj, wj, hs, hr; };
-template <int ROLLING>
-__device__ __forceinline__ void pair_fetch(const StepP &P, int i, unsigned w, PairOps &o)
-{
-  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
-  const int j = (int)(w & NBR_IDX);
-  const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-  o.xj = ldg4(P.xr + j); o.vj = ldg4(P.vm + j); o.wj = ldg4(P.wt + j);
-  o.hs = make_double4(0., 0., 0., 0.); o.hr = o.hs;
-  if (slot >= 0) {
-    const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-    if (P.pm.tangential) o.hs = hp[(size_t)P.pm.rec_shear * P.lcap];
-    if (HAS_ROLL_HIST) o.hr = hp[(size_t)P.pm.rec_roll * P.lcap];
-  }
-}
+// one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see pair_chain); history
+// records are stored in the canonical orientation "lower tag first" (sign flipped on load/store when the partner is the
+// first body).  nh = the particle's count of history slots in use (a shared-memory counter: in the cooperative phase
+// another lane may be serving the particle).
 template <int NORMAL, int ROLLING, bool ONE>
 __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
-                                             const double4 &wi, bool su, int *nh, double *F, double *T,
-                                             const double4 (*srec)[128], unsigned bbase, unsigned blim,
-                                             unsigned reg = 0u, int iwarp = 0, double *Tm = nullptr, const PairOps *pre = nullptr)
-{  // pre: operands fetched ahead of time (software-pipelined contact phase), else they are loaded here  // reg != 0: the pair is evaluated ONCE for both bodies (the partner sits in the same warp, lane reg & 31, and keeps its
-   // copy of the history in its slot ((reg >> 5) & 63) - 1): Tm receives the partner's torque, the partner's force is -F
+                                             const double4 &wi, bool su, int *nh, double *F, double *T)
+{
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int j = (int)(w & NBR_IDX);
   int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   const bool had = slot >= 0;
-  // partners that live in the same block are read from the block's shared-memory copy of its records (after a
-  // Morton sort about half of all partners): a scattered 32-byte global gather costs one L1 wavefront per lane
-  const unsigned jl = (unsigned)j - bbase;
-  double4 xj, vj, wj;
+  const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
   double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
-  if (pre) { xj = pre->xj; vj = pre->vj; wj = pre->wj; hs = pre->hs; hr = pre->hr; }
-  else if (DEM_INBLOCK && jl < blim) { xj = srec[0][jl]; vj = srec[1][jl]; wj = srec[2][jl]; }
-  else { xj = ldg4(P.xr + j); vj = ldg4(P.vm + j); wj = ldg4(P.wt + j); }
-  if (had && !pre) {
+  if (had) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
     if (P.pm.tangential) hs = hp[(size_t)P.pm.rec_shear * P.lcap];
     if (HAS_ROLL_HIST) hr = hp[(size_t)P.pm.rec_roll * P.lcap];
@@ -239,7 +203,7 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
-  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T, Tm);
+  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
   if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
     const int s = atomicAdd(nh, 1);
     if (s < P.hslots) {
@@ -254,18 +218,13 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
     if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
     if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
   }
-  if (DEM_PAIRSHARE && reg && P.pm.hrec && (su || !had)) {  // the partner's copy: same values (rows are stored in the canonical orientation)
-    double4 *hp = P.hist + (size_t)((int)((reg >> 5) & 63u) - 1) * P.pm.hrec * P.lcap + (iwarp + (int)(reg & 31u));
-    if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
-    if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
-  }
 }
 
 // start the memory accesses a staged contact will need, without holding registers
-__device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w, unsigned bbase, unsigned blim)
+__device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w)
 {
   const int j = (int)(w & NBR_IDX);
-  if (DEM_CPREFETCH >= 2 && !(DEM_INBLOCK && (unsigned)j - bbase < blim)) { prefetch_l2(P.vm + j); prefetch_l2(P.wt + j); }
+  if (DEM_CPREFETCH >= 2) { prefetch_l2(P.vm + j); prefetch_l2(P.wt + j); }
   const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   if (DEM_CPREFETCH >= 1 && slot >= 0) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
@@ -322,62 +281,34 @@ __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const doubl
 //   fix_gravity.cpp:331-339, fix_freeze.cpp:132-144, fix_nve_sphere.cpp:134-244,
 //   neighbor.cpp:1425-1466 (rebuild trigger)
 // Phases per warp (32 consecutive particles):
-//  (1) every lane streams its own row with 8 independent position gathers in flight and stages the
-//      neighbour words of its TOUCHING entries in shared memory;
-//  (2) the warp evaluates the staged contacts COOPERATIVELY: the (particle, contact) items of the
-//      32 particles are dealt out round-robin to the 32 lanes, so that a particle with 9 contacts
-//      does not keep 31 lanes with 4 contacts waiting; each item's force/torque goes through a
-//      shared-memory slot back to the owning lane, which adds its items in list order (the sum a
-//      particle receives does not depend on which lane evaluated what: runs stay bit reproducible);
+//  (1) every lane walks its own row in passes of DEM_SWEEPW entries: the neighbour words, as many independent position gathers in flight,
+//      the touch verdicts; the words of the touching entries go (from registers) into the lane's column of a shared-memory
+//      staging area, and the fetches of what their evaluation will need are started towards L2;
+//  (2a) every lane evaluates the first contacts of its own particle itself -- no owner search, no shared-memory round
+//      trip of operands and results, nearly all lanes busy; how many such rounds is decided per warp by a cost rule;
+//  (2b) the uneven remainder is evaluated COOPERATIVELY: the (particle, contact) items of the 32 particles are dealt out
+//      round-robin to the 32 lanes, each item's force/torque goes through a shared-memory slot back to the owning lane,
+//      which adds its items in list order.  Either way a particle's sum runs in list order and does not depend on which
+//      lane evaluated what: runs are bit reproducible;
 //  (3) the owner adds gravity / wall force, integrates, writes its records and votes on the rebuild.
-#ifndef DEM_STEP_MINBLOCKS
-#define DEM_STEP_MINBLOCKS 5
-#endif
-#ifndef DEM_STEP_WAVE_PREFETCH
-#define DEM_STEP_WAVE_PREFETCH 200  // blocks ahead whose streaming inputs are pulled towards L2 (0 = off); measured r01c
-#endif
-// Touch sweep as its own light kernel (40 registers, full occupancy), option "split_sweep" (measured slower than the fused
-// walk, see launch_step; kept as the measured alternative): the row walk is pure gather latency.  One thread per particle: 8 neighbour words, then 8 position gathers
-// in flight, verdicts of the first 64 row entries as one 64-bit mask (rows longer than that: k_step sweeps the rest).
-// Used when the contact-distance factor is 1 (no surfacesClose band), i.e. for every plain contact model deck.
-__global__ void __launch_bounds__(256) k_sweep(const StepP P)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.nlocal || step_gated(P)) return;
-  const double4 xi = ldg4(P.xr + i);
-  const int nn = min(P.numneigh[i] & 0xffff, 64);
-  unsigned long long touch = 0ull;
-#pragma unroll 8
-  for (int kk = 0; kk < nn; kk++) {
-    const unsigned w = P.nbr[(size_t)kk * P.lcap + i];
-    const double4 xj = ldg4(P.xr + (w & NBR_IDX));
-    const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
-    const double radsum = xi.w + xj.w;
-    touch |= (unsigned long long)(rsq < __dmul_rn(radsum, radsum)) << kk;
-  }
-  P.tmask[i] = touch;
-}
-
+// Alternatives that were built, found parity-green and measured slower on the 4.19M bed (git history):
+// partner records from shared memory, one evaluation per in-warp pair, a separate sweep kernel, a software-pipelined
+// contact phase.
 template <int NORMAL, int ROLLING, bool ONE>
 __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {
   __shared__ unsigned s_w[DEM_CMAX][128];
   __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
-  __shared__ double s_res[DEM_PAIRSHARE ? 9 : 6][4 * 32 * DEM_RWIN];  // per warp: force / torque (/ partner torque) of the items of the current window
+  __shared__ double s_res[6][4 * 32 * DEM_RWIN];  // per warp: force / torque of the items of the current window
   __shared__ int s_off[128], s_nh[128];
-  __shared__ unsigned short s_reg[DEM_PAIRSHARE ? DEM_CMAX : 1][128];  // item -> 0x8000 | lane of the mirror particle | (its history slot + 1) << 5
-  __shared__ unsigned s_m[DEM_PAIRSHARE ? DEM_MMAX : 1][128];          // mirror entries of a particle: slot/orientation bits of its neighbour word | partner lane | row position << 5 (staging), then the item index
-  __shared__ unsigned char s_pair[DEM_PAIRSHARE ? 4 : 1][32][32];      // [warp][evaluating lane][mirror lane] = staged position + 1 of their pair in the evaluating lane's list
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
   if (step_gated(P)) return;
   const bool active = i < P.nlocal;
   const bool su = (P.mode != MODE_SETUP);
-  const unsigned bbase = blockIdx.x * blockDim.x;                                  // first particle of this block
-  const unsigned blim = (unsigned)min(128, P.nlocal - (int)bbase);                 // ... and how many of them are owned
   bool trig = false;
   double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
-  int nc = 0, nh0 = 0, nn = 0, mc = 0;
+  int nc = 0, nh0 = 0, nn = 0;
 #if DEM_STEP_WAVE_PREFETCH > 0
   {  // pull the streaming inputs of the block that will run one wave later towards L2
     const int ip = i + DEM_STEP_WAVE_PREFETCH * 128;
@@ -389,10 +320,6 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
     }
   }
 #endif
-  if (DEM_PAIRSHARE) {
-    uint4 *z = reinterpret_cast<uint4 *>(&s_pair[tid >> 5][lane][0]);
-    z[0] = make_uint4(0u, 0u, 0u, 0u); z[1] = make_uint4(0u, 0u, 0u, 0u);
-  }
   {
     double4 xi = make_double4(0., 0., 0., 0.), vi = xi, wi = xi;
     if (active) { xi = ldg4(P.xr + i); vi = ldg4(P.vm + i); wi = ldg4(P.wt + i); }
@@ -403,74 +330,48 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       nh0 = (nnw >> 16) & 0xffff;
     }
     s_nh[tid] = nh0;
-    if (DEM_INBLOCK) __syncthreads();  // s_rec of the whole block is complete
-    for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += 64) {
-      const int kn = min(64, nn - k0);
-      unsigned long long touch = 0ull, extra = 0ull, close = 0ull;
-      // (1a) branch-free sweep: 8 neighbour words, then 8 position gathers in flight per thread
-      // (or the verdict of the k_sweep pre-pass for the first 64 entries)
-#if DEM_SPLIT_SWEEP
-      if (P.tmask && k0 == 0) touch = P.tmask[i];
-      else
-#endif
-#pragma unroll 8
-      for (int kk = 0; kk < kn; kk++) {
-        const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
-        const unsigned jl = (w & NBR_IDX) - bbase;
-        const double4 xj = (DEM_INBLOCK && jl < blim) ? s_rec[0][jl] : ldg4(P.xr + (w & NBR_IDX));
-        const double rsq = sq3_rn(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
-        const double radsum = xi.w + xj.w;
-        const bool t = rsq < __dmul_rn(radsum, radsum);
-        touch |= (unsigned long long)t << kk;
-        if (P.cdf > 1.0) close |= (unsigned long long)(!t && (w & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << kk;
+    for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += DEM_SWEEPW) {
+      // (1) one pass = DEM_SWEEPW row entries: words, gathers, verdicts -- branch free, then the staging of the touching ones
+      unsigned wv[DEM_SWEEPW];
+      double4 xv[DEM_SWEEPW];
+#pragma unroll
+      for (int u = 0; u < DEM_SWEEPW; u++) wv[u] = (k0 + u < nn) ? P.nbr[(size_t)(k0 + u) * P.lcap + i] : (unsigned)i;  // past the row's end: myself (never touches)
+#pragma unroll
+      for (int u = 0; u < DEM_SWEEPW; u++) xv[u] = ldg4(P.xr + (wv[u] & NBR_IDX));
+      unsigned touch = 0u, close = 0u;
+#pragma unroll
+      for (int u = 0; u < DEM_SWEEPW; u++) {
+        const double rsq = sq3_rn(xi.x - xv[u].x, xi.y - xv[u].y, xi.z - xv[u].z);
+        const double radsum = xi.w + xv[u].w;
+        const bool t = (k0 + u < nn) && rsq < __dmul_rn(radsum, radsum);
+        touch |= (unsigned)t << u;
+        if (P.cdf > 1.0) close |= (unsigned)((k0 + u < nn) && !t && (wv[u] & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << u;
       }
-      // (1b) stage the touching entries; start the partner v|m, omega|type and history fetches towards L2
-      while (touch) {
-        const int kk = __ffsll((long long)touch) - 1;
+#pragma unroll
+      for (int u = 0; u < DEM_SWEEPW; u++) {
+        if (!((touch >> u) & 1u)) continue;
+        if (nc < DEM_CMAX) { s_w[nc++][tid] = wv[u]; prefetch_contact(P, i, wv[u]); touch &= ~(1u << u); }
+      }
+      while (touch) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
+        const int u = __ffs((int)touch) - 1;
         touch &= touch - 1;
-        const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
-#ifdef DEM_EXP_SKIP_INWARP  // timing experiment only (wrong physics): upper bound of what in-warp pair sharing can save
-        if (((w & NBR_IDX) - (unsigned)(i - lane)) < (unsigned)lane) continue;
-#endif
-        const unsigned jl = (w & NBR_IDX) - (unsigned)(i - lane);  // partner's lane if it sits in my warp
-        if (DEM_PAIRSHARE && jl < (unsigned)lane && mc < DEM_MMAX && k0 + kk < 64) {
-          s_m[mc++][tid] = (w & (NBR_HIST | NBR_JFIRST)) | jl | ((unsigned)(k0 + kk) << 5);  // a lower lane of my warp evaluates it
-          continue;
-        }
-        if (nc < DEM_CMAX) {
-          if (DEM_PAIRSHARE) { s_reg[nc][tid] = 0; if (jl - (unsigned)lane - 1u < 31u - (unsigned)lane) s_pair[tid >> 5][lane][jl] = (unsigned char)(nc + 1); }
-          s_w[nc++][tid] = w;
-        } else extra |= 1ull << kk;
-        prefetch_contact(P, i, w, bbase, blim);
-      }
-      while (extra) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
-        const int kk = __ffsll((long long)extra) - 1;
-        extra &= extra - 1;
-        pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + kk) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T, s_rec, bbase, blim);
+        pair_contact<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + u) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
       }
       while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
-        const int kk = __ffsll((long long)close) - 1;
+        const int u = __ffs((int)close) - 1;
         close &= close - 1;
-        const unsigned w = P.nbr[(size_t)(k0 + kk) * P.lcap + i];
+        const unsigned w = P.nbr[(size_t)(k0 + u) * P.lcap + i];
         const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
         for (int r = 0; r < P.pm.hrec; r++) st4(P.hist + (size_t)(slot * P.pm.hrec + r) * P.lcap + i, make_double4(0., 0., 0., 0.));
       }
     }
     if (P.debug & 1) nc = 0;
   }
-  // (1c) mirror entries register with the item of the lower lane that will evaluate their pair: the item learns where the
-  //      partner's copy of the history lives, the mirror entry learns which item's result it has to collect.  Items are
-  //      numbered here already (prefix sums over the staged counts).
-#if DEM_OWNR > 0
-  // (1d) every lane evaluates the first DEM_OWNR contacts of its own particle itself: no owner search, no shared-memory
-  //      round trip of operands and results, and nearly all lanes are busy (few particles have fewer contacts); only the
-  //      contacts beyond that -- where the counts differ from lane to lane -- go through the cooperative deal below.
-  //      The sum order of a particle is unchanged (list order), so results are bit-identical to DEM_OWNR 0.
-  //      How many such rounds: the count that minimises (own rounds) x DEM_COST_OWN + (cooperative rounds of 32 items that
-  //      remain) x DEM_COST_COOP for this warp -- an own round costs the same whatever the number of busy lanes, a cooperative
-  //      round (owner search, operand and result round trip, owner accumulation) costs more but is always full.
-  static_assert(!DEM_PAIRSHARE && !DEM_PIPE, "DEM_OWNR is built for the default contact phase");
+  // (2a) own-lane rounds.  Their number minimises (own rounds) x DEM_COST_OWN + (cooperative rounds of 32 items that remain)
+  //      x DEM_COST_COOP for this warp: an own round costs the same whatever the number of busy lanes, a cooperative round
+  //      (owner search, operand and result round trip, owner accumulation) costs more but is always full.
   int ownr = 0;
+#if DEM_OWNR > 0
   {
     int best = 0x7fffffff;
 #pragma unroll 1
@@ -483,86 +384,36 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
     const double4 xo = s_rec[0][tid], vo = s_rec[1][tid], wo = s_rec[2][tid];
 #pragma unroll 1
     for (int r = 0; r < ownr; r++)
-      if (r < nc) pair_contact<NORMAL, ROLLING, ONE>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T, s_rec, bbase, blim);
+      if (r < nc) pair_contact<NORMAL, ROLLING, ONE>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T);
   }
-  const int ncc = max(nc - ownr, 0);
-#else
-  constexpr int ownr = 0;
-  const int ncc = nc;
 #endif
-  int incl = ncc;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  const int excl = incl - ncc;
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  s_off[tid] = excl;
-  __syncwarp();
-  int mreg = 0;
-  if (DEM_PAIRSHARE) {
-    for (int m = 0; m < mc; m++) {
-      const unsigned e = s_m[m][tid];
-      const int ql = (int)(e & 31u), kk = (int)((e >> 5) & 63u);
-      const int c = (int)s_pair[tid >> 5][ql][lane] - 1;
-      int slot = (int)((e & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-      const unsigned w = (e & (NBR_HIST | NBR_JFIRST)) | (unsigned)(i - lane + ql);
-      bool ok = c >= 0;
-      if (ok && slot < 0 && P.pm.hrec) {  // first touch since the last rebuild: my row gets its slot now, the evaluator fills it
-        const int sfree = s_nh[tid];
-        if (sfree < P.hslots) { slot = sfree; s_nh[tid] = sfree + 1; P.nbr[(size_t)kk * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); }
-        else { ((volatile int *)P.flag)[1] = 1; ok = false; }
-      }
-      if (ok) {
-        s_reg[c][wb + ql] = (unsigned short)(0x8000u | (unsigned)lane | ((unsigned)(slot + 1) << 5));
-        s_m[mreg++][tid] = (unsigned)(s_off[wb + ql] + c);
-      } else  // the partner did not stage this pair (its row overflowed the staging area): my side is evaluated here, as before
-        pair_contact<NORMAL, ROLLING, ONE>(P, i, w, s_rec[0][tid], s_rec[1][tid], s_rec[2][tid], su, &s_nh[tid], F, T, s_rec, bbase, blim);
-    }
-    __syncwarp();
-  }
-  // (2) cooperative contact phase
+  // (2b) cooperative deal of the remaining items: item t belongs to the last lane whose first item is <= t
   {
-    // rounds of 32 items; results are parked in shared memory and each owner adds its items (in list order) once per
-    // window of DEM_RWIN rounds -- one short loop per window instead of one per round
-    // item t belongs to the last lane whose first item is <= t (binary search over the warp's prefix sums)
-    [[maybe_unused]] auto locate = [&](int t, int &q, unsigned &w) {
-      int p = 0;
+    const int ncc = max(nc - ownr, 0);
+    int incl = ncc;
 #pragma unroll
-      for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
-      q = wb + p;
-      w = s_w[t - s_off[q]][q];
-    };
-#if DEM_PIPE
-    int q_n = wb; unsigned w_n = 0u; PairOps o_n;
-    if (lane < total) { locate(lane, q_n, w_n); pair_fetch<ROLLING>(P, i - tid + q_n, w_n, o_n); }
-#endif
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int excl = incl - ncc;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    s_off[tid] = excl;
+    __syncwarp();
+    // rounds of 32 items; results are parked in shared memory and each owner adds its items (in list order) once per
+    // window of DEM_RWIN rounds
     for (int b0 = 0; b0 < total; b0 += 32 * DEM_RWIN) {
       const int bend = min(total, b0 + 32 * DEM_RWIN);
       for (int t0 = b0; t0 < bend; t0 += 32) {
         const int t = t0 + lane;
-        double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.}, rM[3] = {0., 0., 0.};
-#if DEM_PIPE
-        int q = q_n; unsigned w = w_n; PairOps o = o_n;  // operands fetched during the previous round; start the next round's loads
-        if (t + 32 < total) { locate(t + 32, q_n, w_n); pair_fetch<ROLLING>(P, i - tid + q_n, w_n, o_n); }
-#endif
         if (t < total) {
-#if !DEM_PIPE
-          int p = 0;  // owner of item t: the last lane whose first item is <= t
+          int p = 0;
 #pragma unroll
           for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
           const int q = wb + p;
           const unsigned w = s_w[ownr + t - s_off[q]][q];
-          const PairOps o = {};
-#endif
-          const unsigned reg = DEM_PAIRSHARE ? (unsigned)s_reg[t - s_off[q]][q] : 0u;
-          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT, s_rec, bbase, blim,
-                                             reg, i - lane, DEM_PAIRSHARE ? rM : nullptr, DEM_PIPE ? &o : nullptr);
+          double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
+          pair_contact<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
           const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
-          if (DEM_PAIRSHARE && reg) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) s_res[6 + d][sl] = rM[d];
-          }
         }
       }
       __syncwarp();
@@ -571,16 +422,6 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         const int sl = (wb >> 5) * (32 * DEM_RWIN) + (k - b0);
 #pragma unroll
         for (int d = 0; d < 3; d++) { F[d] += s_res[d][sl]; T[d] += s_res[3 + d][sl]; }
-      }
-      if (DEM_PAIRSHARE) {
-        for (int m = 0; m < mreg; m++) {  // pairs a lower lane evaluated for me: equal and opposite force, my own torque
-          const int t = (int)s_m[m][tid];
-          if (t >= b0 && t < bend) {
-            const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
-#pragma unroll
-            for (int d = 0; d < 3; d++) { F[d] -= s_res[d][sl]; T[d] += s_res[6 + d][sl]; }
-          }
-        }
       }
       __syncwarp();
     }

@@ -85,8 +85,6 @@ struct StepP {
   const int *gate;
   int gate_mask;  // bit0: gate[0] (distance check due this step), bit2: gate[2] (a moving mesh forces the rebuild)
   unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
-  // split sweep (k_sweep -> k_step): bit k of tmask[i] = entry k (< 64) of particle i's row touches; null = k_step sweeps itself
-  unsigned long long *tmask;
 };
 
 }  // namespace dem
