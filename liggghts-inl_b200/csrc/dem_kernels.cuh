@@ -313,10 +313,9 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   {  // pull the streaming inputs of the block that will run one wave later towards L2
     const int ip = i + DEM_STEP_WAVE_PREFETCH * 128;
     if (ip < P.nlocal) {
-      prefetch_l2(P.xr + ip); prefetch_l2(P.vm + ip); prefetch_l2(P.wt + ip);
+      prefetch_l2(P.xr + ip); prefetch_l2(P.vm + ip); prefetch_l2(P.wt + ip); prefetch_l2(P.xh + ip);
       if (lane < 12) prefetch_l2(P.nbr + (size_t)lane * P.lcap + (ip - lane));
       else if (lane == 12) prefetch_l2(P.numneigh + (ip - lane));
-      else if (lane == 13) prefetch_l2(P.xh + ip);
     }
   }
 #endif
