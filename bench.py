@@ -284,6 +284,12 @@ def own_arm(args):
                 "kernel_share_of_step": kms * st.step_kernel_calls / ms if ms > 0 else None}
     launches = st.kernel_launches - st0.kernel_launches
     nbuilds = st.nbuilds
+    # cost of one neighbour rebuild (sort, gather, cell ranges, halo lists, list build + history remap), reported next to the
+    # step time: setup() of a running engine is a full rebuild plus one force evaluation (Verlet::setup)
+    torch.cuda.synchronize(); tr0 = time.perf_counter()
+    eng.setup()
+    torch.cuda.synchronize()
+    rebuild_ms = allmax((time.perf_counter() - tr0) * 1e3) - (kms if kms > 0 else 0.0)
 
     # end-to-end through the public API with host buffers: upload -> setup -> run(K) -> download
     ke = args.steps
@@ -334,7 +340,7 @@ def own_arm(args):
            "config": {"workload": "%d-sphere settled polydisperse bed (%dx%d replicas of bench_data/tile16k, radii U[1.5,3] mm), "
                                   "hertz/history/cdt, floor + periodic xy, dt 1e-5, skin 1 mm" % (n, tiles, tiles),
                       "particles": n, "l2_policy": "inputs (%.1f GB of state + lists) exceed the 126 MB L2" % (n * 600 / 1e9),
-                      "rebuilds_in_timed_region": int(nbuilds),
+                      "rebuilds_in_timed_region": int(nbuilds), "rebuild_ms": round(rebuild_ms, 3),
                       "parallelism": "1 GPU" if world == 1 else "%d GPUs: x-slab bricks, NCCL halo per step (roofline fields are rank 0's)" % world},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     if rank == 0:
