@@ -286,6 +286,7 @@ def own_arm(args):
     nbuilds = st.nbuilds
     # cost of one neighbour rebuild (sort, gather, cell ranges, halo lists, list build + history remap), reported next to the
     # step time: setup() of a running engine is a full rebuild plus one force evaluation (Verlet::setup)
+    eng.setup()  # (the first rebuild after the initial one allocates the second list set: not steady state)
     torch.cuda.synchronize(); tr0 = time.perf_counter()
     eng.setup()
     torch.cuda.synchronize()

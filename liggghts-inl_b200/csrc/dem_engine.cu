@@ -4,6 +4,7 @@
 // run the sort / border / list kernels.  No CPU fallback exists anywhere in this file.
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1441,10 +1442,25 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
   return ncur;
 }
 
+// developer aid: DEM_B200_TRACE=1 prints the host+device time of each rebuild stage (synchronises at every mark)
+struct StageTrace {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+  explicit StageTrace(cudaStream_t s) : on(getenv("DEM_B200_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what)
+  {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dem trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // Neighbor rebuild: verlet.cpp:305-328 (pre_exchange .. neighbor->build) re-designed for the GPU.
 static void rebuild(dem_engine *E)
 {
   cudaStream_t st = E->stream;
+  StageTrace tr(st);
   const int dnum = E->have_pair ? E->pm.hrec : 0;  // history records per contact
   ensure_cub(E, (size_t)E->cap);
   E->overflow.ensure(E, 2);
@@ -1481,6 +1497,7 @@ static void rebuild(dem_engine *E)
     E->cur = c ^ 1; c = E->cur;
     did_permute = true;
   }
+  tr.mark("migrate+sort+gather");
   E->nlocal = n;
   // 2. owned cell ranges
   CK(cudaMemsetAsync(E->ocs.p, 0, E->ncells * sizeof(int), st)); CK(cudaMemsetAsync(E->oce.p, 0, E->ncells * sizeof(int), st));
@@ -1529,6 +1546,7 @@ static void rebuild(dem_engine *E)
     // records of this dimension's new ghosts (the next dimension's flags look at them)
     do_swap(E, &E->swaps[E->nswap - 2], 2);
   }
+  tr.mark("cell ranges + borders");
   // 4. cell order of the ghosts (storage keeps the swap order so that NCCL can receive in place)
   if (E->nghost) {
     const int ng = (int)E->nghost;
@@ -1540,6 +1558,7 @@ static void rebuild(dem_engine *E)
     k_cell_ranges_idx<<<GRID(ng, 256), 256, 0, st>>>(ng, E->gorder.p, E->xr[c].p, E->grid, E->gcs.p, E->gce.p);
     E->launches += 3;
   }
+  tr.mark("ghost order");
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
@@ -1569,6 +1588,7 @@ static void rebuild(dem_engine *E)
   }
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
+  tr.mark("list build + remap");
   // 5b. triangle-mesh candidate rows + carry-over of the mesh contact rows
   const bool meshw = have_mesh_walls(E) && E->mesh_ready;
   if (meshw) mesh_rebuild(E, n, did_permute);
@@ -1594,7 +1614,9 @@ static void rebuild(dem_engine *E)
     }
   }
   CK(cudaGetLastError());
+  tr.mark("mesh + hold + wall index");
   halo_p2p_setup(E);
+  tr.mark("halo p2p setup");
   E->ago = 0;
   E->order_valid = 0;
   E->nbuilds++;
