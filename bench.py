@@ -284,8 +284,9 @@ def own_arm(args):
                 "kernel_share_of_step": kms * st.step_kernel_calls / ms if ms > 0 else None}
     launches = st.kernel_launches - st0.kernel_launches
     nbuilds = st.nbuilds
-    # cost of one neighbour rebuild (sort, gather, cell ranges, halo lists, list build + history remap), reported next to the
-    # step time: setup() of a running engine is a full rebuild plus one force evaluation (Verlet::setup)
+    # upper bound of the cost of one neighbour rebuild, reported next to the step time: wall time of setup() on a running engine
+    # (a full rebuild -- sort, gather, cell ranges, halo lists, list build + history remap; its stages sum to 3.2 ms for 4.19M
+    # spheres under DEM_B200_TRACE -- plus Verlet::setup's force evaluation with force read-out and the host synchronisation)
     eng.setup()  # (the first rebuild after the initial one allocates the second list set: not steady state)
     torch.cuda.synchronize(); tr0 = time.perf_counter()
     eng.setup()
@@ -341,7 +342,7 @@ def own_arm(args):
            "config": {"workload": "%d-sphere settled polydisperse bed (%dx%d replicas of bench_data/tile16k, radii U[1.5,3] mm), "
                                   "hertz/history/cdt, floor + periodic xy, dt 1e-5, skin 1 mm" % (n, tiles, tiles),
                       "particles": n, "l2_policy": "inputs (%.1f GB of state + lists) exceed the 126 MB L2" % (n * 600 / 1e9),
-                      "rebuilds_in_timed_region": int(nbuilds), "rebuild_ms": round(rebuild_ms, 3),
+                      "rebuilds_in_timed_region": int(nbuilds), "resetup_ms": round(rebuild_ms, 3),
                       "parallelism": "1 GPU" if world == 1 else "%d GPUs: x-slab bricks, NCCL halo per step (roofline fields are rank 0's)" % world},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     if rank == 0:
