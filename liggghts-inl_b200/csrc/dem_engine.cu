@@ -597,7 +597,8 @@ extern "C" int dem_add_mesh(dem_engine *e, const char *id, int atom_type, const 
 extern "C" int dem_move_mesh(dem_engine *e, const char *mesh_id, int argc, const char *const *argv)
 {
   API_BEGIN
-  if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "fix move/mesh cannot be added after setup");
+  // may also arrive between two runs (the t01a tutorial deck starts its mesh after the settling run): the next dem_setup
+  // rebuilds the lists with the moving-mesh candidate skin and the mesh starts to move with the first step
   for (auto &m : e->meshes) if (m.id == mesh_id) {
     if (m.moving) dem_fail(e, DEM_ERR_UNSUPPORTED, "one fix move/mesh per mesh (superposed movers are outside the hot-path scope)");
     if (argc >= 1 && !strcmp(argv[0], "linear")) {
@@ -617,6 +618,7 @@ extern "C" int dem_move_mesh(dem_engine *e, const char *mesh_id, int argc, const
       m.rot_omega = 2. * 3.14159265358979323846 / atof(argv[10]);
       m.moving = 2;
     } else dem_fail(e, DEM_ERR_UNSUPPORTED, "fix move/mesh style '%s' is outside the hot-path scope (linear, rotate)", argc ? argv[0] : "");
+    e->any_moving = 1;
     return DEM_OK;
   }
   dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);

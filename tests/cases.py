@@ -273,6 +273,8 @@ GOLDEN_CASES = {
                               checkpoints=[0, 1, 10, 1500, 3000]),
     "mesh_plate_moving": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
     "mesh_drum_rotating": dict(mesh="drum", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
+    # `fix move/mesh` issued between two runs (the t01a tutorial deck starts its mesh after the settling run)
+    "mesh_plate_late_move": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 200, 201, 210, 800, 2000], late_move_at=201),
     # bonded spheres (INL bond models): bonds form at step 2, stretch, some break
     # (sgn()-type bond damping makes these trajectories diverge from rounding noise within a few hundred steps: short horizons)
     "bond_linear": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history", poly=True, bond=dict(kind="bond", maxdist=2.1 * 0.003)),
@@ -287,8 +289,25 @@ GOLDEN_CASES = {
 def make_case(name):
     g = GOLDEN_CASES[name]
     if "mesh" in g:
-        return case_mesh(kind=g["mesh"], name=name, **g["kw"])
+        c = case_mesh(kind=g["mesh"], name=name, **g["kw"])
+        if "late_move_at" in g:  # the movers are not part of the initial deck: late_commands() issues them before that checkpoint
+            c["late_moves"] = (g["late_move_at"], c.pop("mesh_moves"))
+        return c
     return case_box(name=name, **g["kw"])
+
+
+def late_commands(c, cp):
+    """deck lines to issue before running on to checkpoint cp (empty for most cases)"""
+    at, moves = c.get("late_moves", (None, []))
+    return ["fix mv_%s all move/mesh mesh %s %s" % (mid, mid, text) for mid, text in moves] if cp == at else []
+
+
+def apply_late(c, eng, cp):
+    """the same through the Engine API"""
+    at, moves = c.get("late_moves", (None, []))
+    if cp == at:
+        for mid, text in moves:
+            eng.move_mesh(mid, text)
 
 
 def snapshot(eng, c):

@@ -26,6 +26,8 @@ def run_case(name):
     out = {}
     done = 0
     for cp in cps:
+        for line in cases.late_commands(c, cp):
+            r.cmd(line)
         r.cmd("run %d" % (cp - done) if cp else "run 0")
         if cp and done == 0 and cps[0] != 0:
             pass

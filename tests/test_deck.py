@@ -34,6 +34,8 @@ def follow_golden(name, eng, deck, path, gpu):
     deck.file(path)
     done = 0
     for cp in cases.GOLDEN_CASES[name]["checkpoints"]:
+        for line in cases.late_commands(c, cp):
+            deck.command(line)
         deck.command("run %d upto" % cp if cp else "run 0")
         if done == 0:
             parity.compare_topology(eng, c, g)
@@ -45,7 +47,8 @@ def follow_golden(name, eng, deck, path, gpu):
     deck.close(); eng.close()
 
 
-DECK_CASES = ["box_hertz_cdt", "poly_hooke_epsd_cyl", "periodic_epsd2", "mesh_funnel_hooke", "mesh_plate_moving", "mesh_drum_rotating", "bond_nonlinear"]
+DECK_CASES = ["box_hertz_cdt", "poly_hooke_epsd_cyl", "periodic_epsd2", "mesh_funnel_hooke", "mesh_plate_moving", "mesh_drum_rotating",
+              "mesh_plate_late_move", "bond_nonlinear"]
 
 
 @pytest.mark.parametrize("name", DECK_CASES)

@@ -26,6 +26,7 @@ def test_engine_matches_reference_golden(name):
     e = cases.apply(c, gpu_engine())
     done = 0
     for cp in cases.GOLDEN_CASES[name]["checkpoints"]:
+        cases.apply_late(c, e, cp)
         e.setup()
         if done == 0:
             parity.compare_topology(e, c, g)

@@ -13,6 +13,7 @@ def test_oracle_matches_reference_golden(name):
     e = cases.apply(c, parity.oracle_engine())
     done = 0
     for cp in cases.GOLDEN_CASES[name]["checkpoints"]:
+        cases.apply_late(c, e, cp)
         e.setup()  # every `run` command of the deck starts with Verlet::setup (verlet.cpp:134)
         if done == 0:
             parity.compare_topology(e, c, g)  # mesh cases: active edges / corners as the reference derived them
