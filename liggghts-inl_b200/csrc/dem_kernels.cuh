@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
   int cx, cy, cz; cell_of(B.G, xi, cx, cy, cz);
   const int oi = B.have_old ? B.perm[i] : 0;
   const int nold = B.have_old ? (B.numneigh_old[oi] & 0xffff) : 0;
-  int n = 0, nh = 0;
+  int n = 0, nh = 0, nband = 0;  // list entries, kept history rows, entries inside the contact band right now
   for (int dz = -1; dz <= 1; dz++) {
     const int z = cz + dz; if (z < 0 || z >= B.G.nc[2]) continue;
     for (int dy = -1; dy <= 1; dy++) {
@@ -923,6 +923,7 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
             const double radsum = __dmul_rn(xi.w + xj.w, B.cdf);
             const double rc = radsum + B.skin;
             if (rsq <= __dmul_rn(rc, rc)) {
+              if (!B.coh_nbond && rsq < __dmul_rn(radsum, radsum)) nband++;  // (bond decks: the band is wide, rows follow the bonds)
               if (n < B.maxk) {
                 const int tagj = B.tag[j];
                 unsigned w = (unsigned)j | (tagj < tagi ? NBR_JFIRST : 0u);
@@ -962,7 +963,9 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
   }
   B.numneigh[i] = min(n, B.maxk) | (min(nh, B.hslots) << 16);
   if (n > B.maxk) atomicMax(B.overflow, n);
-  if (nh + 8 > B.hslots) atomicMax(B.overflow + 1, nh);
+  // history slots: the rows kept from the old list, or -- a bed uploaded in a packed state, an overlapping initial
+  // condition -- every entry that is inside the contact band now and will ask for a row in the first step, plus 8 spare
+  if (max(nh, nband) + 8 > B.hslots) atomicMax(B.overflow + 1, max(nh, nband));
 }
 
 // positions at build time (neighbor.cpp:1486-1510) + primitive-wall candidate bits (primitive_wall.h:129-138)

@@ -120,6 +120,39 @@ def test_bonded_spheres_match_oracle(kw):
     got.close(); ref.close()
 
 
+def test_many_contacts_on_one_particle_match_oracle():
+    """a sphere three times larger than the 40 small ones sitting on its surface: all 40 contacts form in the first step -- far
+    more than the 12 contacts the step kernel stages in shared memory and than the default 16 history slots.  Exercises the
+    on-the-spot evaluation of surplus contacts and the sizing of the history rows from the entries inside the contact band."""
+    c = cases.case_box(n3=(4, 4, 3), name="shell", seed=13)
+    rs, R, nshell = 0.0025, 0.0075, 40
+    L = c["hi"][0]
+    ctr = np.array([0.5 * L, 0.5 * L, 0.03])
+    k = np.arange(nshell) + 0.5
+    phi = np.arccos(1.0 - 2.0 * k / nshell); th = np.pi * (1.0 + 5.0 ** 0.5) * k   # Fibonacci sphere
+    shell = ctr + (R + rs) * 0.999 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
+    n = nshell + 1
+    c.update(tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32), mask=np.ones(n, np.int32),
+             x=np.vstack([ctr, shell]), v=np.zeros((n, 3)), omega=np.zeros((n, 3)),
+             radius=np.concatenate([[R], np.full(nshell, rs)]), density=np.full(n, c["density"][0]))
+    c["hi"][2] = max(c["hi"][2], 0.06)
+    rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
+    got = cases.apply(c, gpu_engine())
+    ref = cases.apply(c, parity.oracle_engine())
+    done = 0
+    for cp in (0, 1, 2, 10, 300, 1500):
+        for eng in (got, ref):
+            eng.setup(); eng.run(cp - done)
+        done = cp
+        sg = cases.snapshot(got, c)
+        parity.compare_snapshot(sg, cases.snapshot(ref, c), rmass, tol=tol_at(cp), label="shell@%d" % cp)
+        assert got.stats().nbuilds == ref.stats().nbuilds
+        if cp == 1:
+            on_big = int(((sg["pair_lo"] == 1) & (sg["pair_flag"] != 0)).sum())
+            assert on_big == nshell, "the big sphere holds %d contacts" % on_big
+    got.close(); ref.close()
+
+
 def test_engine_is_deterministic():
     c = cases.case_box(n3=(8, 8, 8), poly=True, name="det", seed=3)
     snaps = []
