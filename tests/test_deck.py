@@ -109,3 +109,80 @@ def test_lmp_b200_cli_runs_a_deck(tmp_path):
     bad = tmp_path / "in.bad"; bad.write_text("units si\nfix ins all insert/pack seed 1\n")
     r = subprocess.run([exe, "-in", str(bad)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 1 and "outside the hot-path scope" in r.stderr and "line 2" in r.stderr
+
+
+def test_tutorial_style_deck_on_oracle(tmp_path):
+    """a deck written the way the INL tutorial decks are (tabs, trailing comments, continuation lines, create_box from a region,
+    two atom types with the wall as the last one, a diagnostic fix that is later unfixed, `run N upto`, a mesh that starts to
+    move between two runs) -- particles come from read_data, because insertion is outside the hot path"""
+    import dem_b200
+    c = cases.case_mesh(kind="plate", n3=(4, 4, 3), name="tut")
+    _, data = cases.to_deck(c, str(tmp_path / "case.data"))
+    (tmp_path / "case.data").write_text(data)
+    for mid, mtype, nodes in c["meshes"]:
+        cases.write_stl(str(tmp_path / (mid + ".stl")), nodes, mid)
+    lo, hi = c["lo"], c["hi"]
+    deck = """
+units\t\tsi
+atom_style\tsphere
+atom_modify\tmap array
+boundary\tm m m # f f f
+newton\t\toff
+communicate\tsingle vel yes
+region\t\tdomain block %.17g %.17g %.17g %.17g %.17g %.17g units box # the simulation box
+create_box\t2 domain # the last type is the wall
+read_data\tcase.data
+neighbor\t0.001 bin
+neigh_modify\tdelay 0
+variable\tyoung equal 5e6
+fix\t\tm1 all property/global youngsModulus peratomtype ${young}  1e9
+fix\t\tm2 all property/global poissonsRatio peratomtype 0.45 0.3
+fix\t\tm3 all property/global coefficientRestitution peratomtypepair 2 &
+\t\t0.3 0.3 &
+\t\t0.3 0.3
+fix\t\tm4 all property/global coefficientFriction peratomtypepair 2 &
+\t\t0.5 0.3 &
+\t\t0.3 0.3
+fix\t\tm11 all property/global coefficientRollingFriction peratomtypepair 2 0.1 0.1 0.1 0.1
+fix\t\tcad all mesh/surface file cad.stl    type 2
+fix\t\tplate all mesh/surface file plate.stl type 2
+fix\t\tgeo all wall/gran model hertz tangential history rolling_friction cdt mesh n_meshes 2 meshes cad plate
+pair_style\tgran model hertz tangential history rolling_friction cdt
+pair_coeff\t* *
+fix\t\tintegr1 all nve/sphere
+fix\t\tgrav all gravity 9.81 vector 0.0 0.0 -1.0
+timestep\t0.00001
+compute\t\t1 all erotate
+thermo_style\tcustom step atoms c_1 cpu
+thermo\t\t50000
+fix\t\tctg all check/timestep/gran 1 0.01 0.01
+run\t\t1
+unfix\t\tctg
+dump\t\tdmp all custom 50000 out.*.dump id type x y z radius
+run\t\t300 upto
+fix\t\tmove all move/mesh mesh plate linear 0. 0. -0.4
+run\t\t200
+""" % (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
+    (tmp_path / "in.tut").write_text(deck)
+    eng, dk = oracle_deck()
+    dk.file(str(tmp_path / "in.tut"))
+    assert dk.ntimestep == 500
+    assert "dump ignored" in dk.warnings and "check/timestep/gran ignored" in dk.warnings
+    # the same through the API calls, step for step
+    ref = parity.oracle_engine()
+    ref.units("si"); ref.box(lo, hi, [0, 0, 0]); ref.ntypes(2); ref.neighbor(0.001, every=1, delay=0, check=True)
+    ref.property_global("youngsModulus", "peratomtype", [5e6, 1e9]); ref.property_global("poissonsRatio", "peratomtype", [0.45, 0.3])
+    ref.property_global("coefficientRestitution", "peratomtypepair", [0.3] * 4); ref.property_global("coefficientFriction", "peratomtypepair", [0.5, 0.3, 0.3, 0.3])
+    ref.property_global("coefficientRollingFriction", "peratomtypepair", [0.1] * 4)
+    for mid, mtype, nodes in c["meshes"]:
+        ref.mesh(mid, 2, nodes)
+    ref.wall_mesh("geo", "model hertz tangential history rolling_friction cdt mesh n_meshes 2 meshes cad plate")
+    ref.pair_style("model hertz tangential history rolling_friction cdt")
+    ref.integrate(1); ref.gravity(9.81, [0.0, 0.0, -1.0]); ref.timestep(0.00001)
+    ref.upload(c["tag"], c["type"], c["x"], c["radius"], c["density"], v=c["v"], omega=c["omega"], mask=c["mask"])
+    ref.setup(); ref.run(1); ref.setup(); ref.run(299)
+    ref.move_mesh("plate", "linear 0. 0. -0.4")
+    ref.setup(); ref.run(200)
+    for k in ("x", "v", "f", "omega", "torque"):
+        assert np.array_equal(eng.download(k), ref.download(k)), k
+    dk.close(); eng.close(); ref.close()
