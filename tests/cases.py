@@ -205,7 +205,8 @@ def to_deck(c, datafile):
     b = " ".join("p" if p else "f" for p in c["periodic"])
     deck = ["units si", "atom_style sphere", "atom_modify map array sort 0 0", "boundary " + b, "newton off",
             "communicate single vel yes", "read_data " + datafile, "neighbor %.17g bin" % c["skin"],
-            "neigh_modify delay 0"]
+            "neigh_modify delay %d every %d check %s" % (c.get("neigh", (1, 0, True))[1], c.get("neigh", (1, 0, True))[0],
+                                                         "yes" if c.get("neigh", (1, 0, True))[2] else "no")]
     for k, (name, kind, vals) in enumerate(c["props"]):
         extra = " %d" % c["ntypes"] if kind == "peratomtypepair" else ""
         deck.append("fix m%d all property/global %s %s%s %s" % (k, name, kind, extra, " ".join("%.17g" % v for v in vals)))
@@ -234,7 +235,8 @@ def apply(c, eng):
     eng.units("si")
     eng.box(c["lo"], c["hi"], c["periodic"])
     eng.ntypes(c["ntypes"])
-    eng.neighbor(c["skin"], every=1, delay=0, check=True)
+    every, delay, check = c.get("neigh", (1, 0, True))  # neigh_modify every / delay / check
+    eng.neighbor(c["skin"], every=every, delay=delay, check=check)
     for name, kind, vals in c["props"]:
         eng.property_global(name, kind, vals)
     eng.pair_style(c["pair"])
@@ -265,6 +267,9 @@ GOLDEN_CASES = {
                                    poly=True, periodic=(1, 1, 0), ntypes=2, shear=True), checkpoints=[0, 1, 2, 10, 400, 2500]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
+    # rebuild cadence other than `delay 0 every 1 check yes` (Neighbor::decide, neighbor.cpp:1362-1376)
+    "box_neigh_every2_delay4": dict(kw=dict(n3=(4, 4, 4), poly=True), neigh=(2, 4, True), checkpoints=[0, 1, 10, 400, 1500]),
+    "box_neigh_nocheck": dict(kw=dict(n3=(4, 4, 4)), neigh=(25, 0, False), checkpoints=[0, 1, 10, 400, 1500]),
     # triangle-mesh walls (fix mesh/surface + fix wall/gran mesh): coplanar floor grid, convex ridge, cone, moving plate
     "mesh_box": dict(mesh="box", kw=dict(n3=(4, 4, 4)), checkpoints=[0, 1, 10, 400, 2500]),
     "mesh_roof_epsd2": dict(mesh="roof", kw=dict(n3=(4, 4, 4), model="model hertz tangential history rolling_friction epsd2"),
@@ -293,7 +298,10 @@ def make_case(name):
         if "late_move_at" in g:  # the movers are not part of the initial deck: late_commands() issues them before that checkpoint
             c["late_moves"] = (g["late_move_at"], c.pop("mesh_moves"))
         return c
-    return case_box(name=name, **g["kw"])
+    c = case_box(name=name, **g["kw"])
+    if "neigh" in g:
+        c["neigh"] = g["neigh"]
+    return c
 
 
 def late_commands(c, cp):
