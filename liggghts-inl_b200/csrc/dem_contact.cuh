@@ -221,8 +221,8 @@ template <int NORMAL, int ROLLING, bool ONE>
 __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, const double4 &xi, const double4 &vi, const double4 &wi,
                                            const double4 &xj, const double4 &vj, const double4 &wj, int itype, int jtype,
                                            int imask, int jmask, double dx, double dy, double dz, double rsq,
-                                           double (&shear)[3], double (&ch)[3], bool shearupdate, double *F, double *T)
-{
+                                           double (&shear)[3], double (&ch)[3], bool shearupdate, double *F, double *T, double *Tp = nullptr)
+{  // Tp (optional, half-list variant): receives the torque on the PARTNER, -crj (en x Ft) + rolling torque
   const int tij = itype * P.nt1 + jtype;
   double r, rinv;
   sqrt_rsqrt_fast(rsq, r, rinv);
@@ -274,7 +274,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
   double Fn = -gamman * vn + kn * deltan;
   if (M.limitForce && Fn < 0.0) Fn = 0.0;
   double F1 = Fn * enx, F2 = Fn * eny, F3 = Fn * enz;
-  double T1 = 0.0, T2 = 0.0, T3 = 0.0;
+  double T1 = 0.0, T2 = 0.0, T3 = 0.0, P1 = 0.0, P2 = 0.0, P3 = 0.0;
   if (M.tangential) {  // tangential_model_history.h:136-240,288-334
     if (shearupdate) {
       shear[0] += vtr1 * P.dt; shear[1] += vtr2 * P.dt; shear[2] += vtr3 * P.dt;
@@ -297,6 +297,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
     }
     F1 += Ft1; F2 += Ft2; F3 += Ft3;
     T1 = -cri * (eny * Ft3 - enz * Ft2); T2 = -cri * (enz * Ft1 - enx * Ft3); T3 = -cri * (enx * Ft2 - eny * Ft1);
+    if (Tp) { P1 = -crj * (eny * Ft3 - enz * Ft2); P2 = -crj * (enz * Ft1 - enx * Ft3); P3 = -crj * (enx * Ft2 - eny * Ft1); }
   }
   if (ROLLING != R_OFF) {
     const double a1 = wi.x - wj.x, a2 = wi.y - wj.y, a3 = wi.z - wj.z;
@@ -312,6 +313,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
           r1 -= enx * dot; r2 -= eny * dot; r3 -= enz * dot;
         }
         T1 -= r1; T2 -= r2; T3 -= r3;
+        P1 += r1; P2 += r2; P3 += r3;
       }
     } else {  // rolling_model_epsd.h:97-340, rolling_model_epsd2.h:152-205
       double w1 = a1, w2 = a2, w3 = a3;
@@ -338,10 +340,12 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
         }
       }
       T1 -= r1; T2 -= r2; T3 -= r3;
+      P1 += r1; P2 += r2; P3 += r3;
     }
   }
   F[0] += F1; F[1] += F2; F[2] += F3;
   T[0] += T1; T[1] += T2; T[2] += T3;
+  if (Tp) { Tp[0] += P1; Tp[1] += P2; Tp[2] += P3; }
 }
 
 

@@ -204,6 +204,7 @@ struct dem_engine {
   ListSet ls[2];
   int lcur = 0;
   DevBuf<int> overflow;
+  DevBuf<double> fa, ta;  // accumulation arrays of the half-list alternative (option "half_list")
   DevBuf<unsigned long long> counters;
   int *hflag = nullptr;  // mapped pinned flags: [0] rebuild trigger, [1] history overflow, [2] moving-mesh trigger
   // triangle-mesh walls (dem_mesh.h)
@@ -327,7 +328,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
-  e->cubtmp.release(); e->overflow.release(); e->counters.release();
+  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
@@ -1652,6 +1653,13 @@ static StepP step_params(dem_engine *E, int mode)
 template <int N, int R>
 static void launch_step_t(dem_engine *E, const StepP &P)
 {
+  if (P.fa) {  // measured half-list alternative (option "half_list"): pair kernel with fp64 reductions + integration kernel
+    if (E->ntypes == 1) k_step<N, R, true, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+    else k_step<N, R, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+    k_integrate_half<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);
+    E->launches++;
+    return;
+  }
   if (E->ntypes == 1) k_step<N, R, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
   else k_step<N, R, false><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
 }
@@ -1663,6 +1671,14 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (tm) {
     if ((long)E->ev.size() < 2 * (E->ev_used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); E->ev.push_back(a); E->ev.push_back(b); }
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
+  }
+  if (E->have_pair && !E->pm.cohesion && E->nranks == 1 && E->opt.count("half_list") && E->opt["half_list"] != 0) {
+    if (E->fa.n < 3 * (size_t)E->cap) {
+      E->fa.release(); E->ta.release(); E->fa.ensure(E, 3 * (size_t)E->cap); E->ta.ensure(E, 3 * (size_t)E->cap);
+      CK(cudaMemsetAsync(E->fa.p, 0, 3 * (size_t)E->cap * sizeof(double), E->stream));
+      CK(cudaMemsetAsync(E->ta.p, 0, 3 * (size_t)E->cap * sizeof(double), E->stream));
+    }
+    P.fa = E->fa.p; P.ta = E->ta.p;
   }
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
   if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }

@@ -63,6 +63,7 @@ struct StepP {
   int hslots;
   double *whist;  // [sum wall dnum][cap]
   double *f, *tq; // [3][cap]
+  double *fa, *ta; // [3][cap] accumulation arrays of the half-list alternative (option "half_list"), else null
   const WallP *walls;
   int nwalls;
   int nwc, nwcap;     // primitive-wall candidates (compact list) and row stride of fw
