@@ -155,20 +155,22 @@ def test_many_contacts_on_one_particle_match_oracle():
 
 def test_half_list_alternative_agrees_with_the_default():
     """option half_list (every pair once, fp64 reductions) is a measurement variant -- its numbers only
-    mean something if it computes the same step as the default full-list kernel"""
-    c = cases.case_box(n3=(12, 12, 10), poly=True, periodic=(1, 1, 0), name="half", seed=21)
+    mean something if it computes the same step as the default full-list kernel.  Compared on one settled tile of the bench
+    bed over a window without a rebuild (the variant does not maintain the mirror copy of a pair's history)."""
+    import bench
+    c = bench.bed_case(1, 1)
     rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
     out = []
     for half in (0, 1):
         e = cases.apply(c, gpu_engine())
         e.option("half_list", half)
-        e.setup(); e.run(300)   # no rebuild-spanning history is needed within the first contacts of a falling bed
-        out.append({k: e.download(k) for k in ("x", "v", "omega", "f", "torque")}); nb = e.stats().nbuilds
+        e.setup(); e.run(50)
+        assert e.stats().nbuilds == 0
+        out.append({k: e.download(k) for k in ("x", "v", "omega", "f", "torque")})
         e.close()
     w = (rmass * 9.81)[:, None]
-    assert nb >= 0
-    assert np.abs(out[0]["x"] - out[1]["x"]).max() < 1e-9
-    assert (np.abs(out[0]["f"] - out[1]["f"]) / np.maximum(np.abs(out[0]["f"]), w)).max() < 1e-6
+    assert np.abs(out[0]["x"] - out[1]["x"]).max() < 1e-12
+    assert (np.abs(out[0]["f"] - out[1]["f"]) / w).max() < 1e-8
 
 
 def test_engine_is_deterministic():
