@@ -56,8 +56,16 @@ const char *dem_last_error(const dem_engine *e);
 long dem_trim_memory(void);
 const char *dem_version(void);
 
-/* engine tuning knobs that have no deck equivalent: "time_kernels" (0/1: CUDA-event timing of the
- * step kernel, reported by dem_get_stats), "maxneigh" (initial ELLPACK width), "morton" (0/1).  */
+/* engine knobs that have no deck equivalent (set before dem_setup):
+ *   "time_kernels" 0|1   CUDA-event timing of the step kernels, reported by dem_get_stats
+ *   "maxneigh" N         initial ELLPACK width of the neighbour rows (default 24; grows on overflow at a rebuild)
+ *   "histslots" N        initial history rows per particle (default 16; sized from the contact band at every rebuild)
+ *   "cap_factor" x       head room of the per-particle arrays over the uploaded count (1.25; 1.5 with several ranks)
+ *   "meshslots" N, "meshcand" N   contact rows / candidate triangles per particle for mesh walls (8 / 16)
+ *   "morton" 0|1         Morton (default) or linear cell order of the particle storage
+ *   "half_list" 0|1      MEASUREMENT ONLY: half list with fp64 reductions instead of the full list
+ *                        without atomics; valid between two rebuilds only, single rank, plain contact models
+ *   "debug" bits         profiling aids (skip contact evaluation / list walk / flag all-reduce / halo traffic): timings only */
 int dem_set_option(dem_engine *e, const char *name, double value);
 
 /* ---- deck-level settings (same vocabulary as the input script) --------------------- */
