@@ -176,7 +176,8 @@ int dem_get_stats(dem_engine *e, dem_stats *out);
  * boundary, newton, communicate, processors, region block, create_box, read_data, neighbor, neigh_modify, group id|type,
  * fix property/global | gravity | wall/gran primitive|mesh | mesh/surface* file [type|scale|move|rotate|curvature|
  * precision] | move/mesh linear|rotate | freeze | nve/sphere, pair_style gran, pair_coeff, timestep, variable NAME
- * equal|string|index VALUE, run N [upto]) become the ABI calls above in deck order; output-only commands (thermo*,
+ * equal FORMULA | string|index VALUE (formulas: numbers, + - * / ^, parentheses, v_name, PI, sqrt exp ln log abs sin cos ...),
+ * run N [upto]) become the ABI calls above in deck order; output-only commands (thermo*,
  * compute, dump*, ...) are accepted and reported by dem_deck_warnings; everything else returns DEM_ERR_UNSUPPORTED.
  * Errors carry the reference's message texts where one exists (src/input.cpp, src/read_data.cpp). */
 typedef struct dem_deck_handle dem_deck;

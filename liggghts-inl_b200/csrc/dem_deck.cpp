@@ -22,6 +22,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <set>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -69,6 +70,7 @@ struct Deck {
   dem_engine *e = nullptr;
   std::string err, warnings, dir;  // dir: directory of the deck file (relative paths in read_data / mesh files)
   std::map<std::string, std::string> vars;
+  std::set<std::string> var_is_equal;  // equal-style: the stored text is a formula
   struct Region { double lo[3], hi[3]; };
   std::map<std::string, Region> regions;
   std::map<std::string, int> groups;  // name -> mask bit
@@ -108,6 +110,77 @@ int inumeric(Deck *d, const std::string &s, int &out)
   out = atoi(s.c_str()); return OK;
 }
 
+// equal-style variable formulas (variable.cpp:700-1500): numbers, + - * / ^, unary minus, parentheses, v_name references to
+// other variables, PI, and the math functions sqrt exp ln log abs sin cos tan asin acos atan floor ceil round.  Anything else
+// (thermo keywords, atom values vx[1], compute / fix references ...) only feeds output commands and is reported as
+// unsupported when -- and only when -- a hot-path command asks for the value.
+struct Formula {
+  Deck *d; const char *p; std::string err; int depth;
+  void ws() { while (*p == ' ' || *p == '\t') p++; }
+  double fail(const std::string &m) { if (err.empty()) err = m; return 0.0; }
+  double atom()
+  {
+    ws();
+    if (*p == '(') { p++; const double v = expr(); ws(); if (*p != ')') return fail("Invalid syntax in variable formula"); p++; return v; }
+    if (*p == '-') { p++; return -power(); }
+    if (*p == '+') { p++; return power(); }
+    if (isdigit((unsigned char)*p) || *p == '.') { char *e; const double v = strtod(p, &e); p = e; return v; }
+    if (isalpha((unsigned char)*p) || *p == '_') {
+      std::string id; while (isalnum((unsigned char)*p) || *p == '_') id += *p++;
+      ws();
+      if (id == "PI") return 3.14159265358979323846;
+      if (id.compare(0, 2, "v_") == 0) return value_of(id.substr(2));
+      if (*p == '(') {
+        p++; const double a = expr(); ws(); if (*p != ')') return fail("Invalid syntax in variable formula"); p++;
+        if (id == "sqrt") return a < 0 ? fail("Sqrt of negative value in variable formula") : std::sqrt(a);
+        if (id == "exp") return std::exp(a);
+        if (id == "ln") return a <= 0 ? fail("Log of zero/negative value in variable formula") : std::log(a);
+        if (id == "log") return a <= 0 ? fail("Log of zero/negative value in variable formula") : std::log10(a);
+        if (id == "abs") return std::fabs(a);
+        if (id == "sin") return std::sin(a);
+        if (id == "cos") return std::cos(a);
+        if (id == "tan") return std::tan(a);
+        if (id == "asin") return std::asin(a);
+        if (id == "acos") return std::acos(a);
+        if (id == "atan") return std::atan(a);
+        if (id == "floor") return std::floor(a);
+        if (id == "ceil") return std::ceil(a);
+        if (id == "round") return std::floor(a + 0.5);
+      }
+      return fail("variable formula term '" + id + "' is outside the hot-path scope");
+    }
+    return fail("Invalid syntax in variable formula");
+  }
+  double power() { const double b = atom(); ws(); if (*p == '^') { p++; const double e = power(); return std::pow(b, e); } return b; }
+  double term()
+  {
+    double v = power();
+    for (;;) { ws(); if (*p == '*') { p++; v *= power(); } else if (*p == '/') { p++; const double q = power(); if (q == 0.0) return fail("Divide by 0 in variable formula"); v /= q; } else return v; }
+  }
+  double expr() { double v = term(); for (;;) { ws(); if (*p == '+') { p++; v += term(); } else if (*p == '-') { p++; v -= term(); } else return v; } }
+  double value_of(const std::string &name);
+};
+int evaluate(Deck *d, const std::string &text, double &out, int depth);
+double Formula::value_of(const std::string &name)
+{
+  auto it = d->vars.find(name);
+  if (it == d->vars.end()) return fail("Invalid variable name '" + name + "' in variable formula");
+  if (depth > 32) return fail("variable formulas reference each other in a loop");
+  double v = 0.0;
+  const bool formula = d->var_is_equal.count(name) != 0;
+  if (formula) { if (evaluate(d, it->second, v, depth + 1) != OK) return fail(d->err); return v; }
+  if (!is_number(it->second)) return fail("Variable '" + name + "' does not hold a number");
+  return atof(it->second.c_str());
+}
+int evaluate(Deck *d, const std::string &text, double &out, int depth = 0)
+{
+  Formula f{d, text.c_str(), "", depth};
+  out = f.expr(); f.ws();
+  if (f.err.empty() && *f.p) f.err = "Invalid syntax in variable formula";
+  if (!f.err.empty()) return fail(d, f.err.find("outside the hot-path scope") != std::string::npos ? ERR_UNSUPPORTED : ERR_ARG, "%s: '%s'", f.err.c_str(), text.c_str());
+  return OK;
+}
+
 // Input::substitute (input.cpp:430-520): ${name} and $x
 int substitute(Deck *d, std::string &line)
 {
@@ -121,7 +194,12 @@ int substitute(Deck *d, std::string &line)
       else { name = line.substr(k + 1, 1); end = k + 1; }
       auto it = d->vars.find(name);
       if (it == d->vars.end()) return fail(d, ERR_ARG, "Substitution for illegal variable '%s'", name.c_str());
-      out += it->second; k = end; continue;
+      if (d->var_is_equal.count(name)) {  // Variable::retrieve, variable.cpp:595-606: the formula is evaluated now, printed %.15g
+        double v; const int rc = evaluate(d, it->second, v); if (rc) return rc;
+        char buf[64]; snprintf(buf, sizeof buf, "%.15g", v);
+        out += buf;
+      } else out += it->second;
+      k = end; continue;
     }
     out += c;
   }
@@ -428,12 +506,16 @@ int one(Deck *d, const std::string &raw)
   static const char *output_only[] = {"thermo", "thermo_style", "thermo_modify", "compute", "uncompute", "dump", "dump_modify", "undump", "echo", "log",
                                      "print", "restart", "write_restart", "write_data", "info", "reset_timestep_info", nullptr};
   for (int k = 0; output_only[k]; k++) if (c == output_only[k]) { d->warnings += c + " ignored (output only)\n"; return OK; }
-  if (c == "variable") {  // styles equal / string / index with a literal value (variable.cpp:90-330); formulas are not evaluated
+  if (c == "variable") {  // styles equal (formula, see Formula) / string / index (variable.cpp:90-330)
     if (w.size() < 4) return fail(d, ERR_ARG, "Illegal variable command");
     if (w[2] != "equal" && w[2] != "string" && w[2] != "index") return fail(d, ERR_UNSUPPORTED, "variable style '%s' is outside the hot-path scope", w[2].c_str());
-    if (w[2] == "equal" && !is_number(w[3])) return fail(d, ERR_UNSUPPORTED, "variable formulas are outside the hot-path scope: '%s'", w[3].c_str());
     if (w[2] == "index" && d->vars.count(w[1])) return OK;  // an index variable keeps its first value
-    d->vars[w[1]] = w[3]; return OK;
+    if (w[2] == "equal") {  // the formula is everything after the style (it may contain blanks); evaluated when substituted
+      std::string f = w[3];
+      for (size_t k = 4; k < w.size(); k++) f += w[k];
+      d->vars[w[1]] = f; d->var_is_equal.insert(w[1]);
+    } else { d->vars[w[1]] = w[3]; d->var_is_equal.erase(w[1]); }
+    return OK;
   }
   if (c == "units") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal units command"); TRY(API(set_units)(d->e, w[1].c_str())); return OK; }
   if (c == "atom_style") {

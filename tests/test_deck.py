@@ -186,3 +186,31 @@ run\t\t200
     for k in ("x", "v", "f", "omega", "torque"):
         assert np.array_equal(eng.download(k), ref.download(k)), k
     dk.close(); eng.close(); ref.close()
+
+
+def test_deck_variable_formulas(tmp_path):
+    """equal-style formulas as the INL example decks use them (`variable max_dist equal 1.5*${d}`), evaluated at substitution
+    and printed %.15g like Variable::retrieve; output-only variables (vx[1], time, f_mesh[3]) are accepted and only fail when a
+    hot-path command asks for their value"""
+    import dem_b200
+    c = cases.make_case("box_hertz_cdt")
+    path = write_deck(c, tmp_path)
+    text = open(path).read()
+    text = text.replace("variable dt equal", "variable dt_unused equal").replace("timestep ${dt}", "")
+    text += "\n".join(["variable d equal 2", "variable half equal 0.5*${d}", "variable vz1 equal vz[1]", "variable top_Fz equal f_mesh_top[3]",
+                       "variable tc equal time", "variable dt equal ${half}*1e-5*(v_d^2-3)+sqrt(16)*0-abs(-0)",
+                       "timestep ${dt}", "run 10"]) + "\n"
+    open(path, "w").write(text)
+    eng, deck = oracle_deck()
+    deck.file(path)
+    ref = cases.apply(c, parity.oracle_engine())   # 0.5*2 * 1e-5 * (4-3) == the case's 1e-5
+    ref.setup(); ref.run(10)
+    for k in ("x", "v", "f"):
+        assert np.array_equal(eng.download(k), ref.download(k)), k
+    with pytest.raises(dem_b200.DemError, match=r"\(-2\).*vz.*outside the hot-path scope"):
+        deck.command("timestep ${vz1}")
+    with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Divide by 0"):
+        deck.command("variable z equal 1/0"); deck.command("timestep ${z}")
+    with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Invalid syntax"):
+        deck.command("variable y equal 2*(3"); deck.command("timestep ${y}")
+    deck.close(); eng.close(); ref.close()
