@@ -73,6 +73,7 @@ struct Deck {
   std::set<std::string> var_is_equal;  // equal-style: the stored text is a formula
   struct Region { double lo[3], hi[3]; };
   std::map<std::string, Region> regions;
+  std::set<std::string> opaque_regions;  // regions of other shapes: known by name only
   std::map<std::string, int> groups;  // name -> mask bit
   std::map<std::string, std::string> ignored_fixes;
   // box / particles held until the first `run`
@@ -470,7 +471,12 @@ int cmd_fix(Deck *d, const std::vector<std::string> &w)
   }
   if (style == "freeze") { TRY(API(set_freeze)(d->e, bit)); return OK; }
   if (style == "nve/sphere") { TRY(API(set_integrate)(d->e, bit)); return OK; }
-  if (style == "check/timestep/gran") { d->ignored_fixes[id] = style; d->warnings += "fix " + style + " ignored (diagnostic only)\n"; return OK; }
+  if (style == "check/timestep/gran" || style == "print" || style.compare(0, 4, "ave/") == 0) {
+    d->ignored_fixes[id] = style; d->warnings += "fix " + style + " ignored (diagnostic / output only)\n"; return OK;
+  }
+  if (style == "balance") {  // dynamic load balancing (fix_balance.cpp) moves brick boundaries, never the physics: bricks stay static here
+    d->ignored_fixes[id] = style; d->warnings += "fix balance ignored (bricks are static)\n"; return OK;
+  }
   return fail(d, ERR_UNSUPPORTED, "fix style '%s' is outside the hot-path scope", style.c_str());
 }
 
@@ -547,7 +553,10 @@ int one(Deck *d, const std::string &raw)
     TRY(API(set_processors)(d->e, p[0], p[1], p[2])); return OK;
   }
   if (c == "region") {
-    if (w.size() < 9 || w[2] != "block") return fail(d, w.size() >= 3 && w[2] != "block" ? ERR_UNSUPPORTED : ERR_ARG, "region: only 'ID block xlo xhi ylo yhi zlo zhi [units box]' is on the hot path");
+    if (w.size() >= 3 && w[2] != "block") {  // other shapes only feed insertion / groups, which are rejected where they are used
+      d->opaque_regions.insert(w[1]); d->warnings += "region " + w[1] + " (" + w[2] + ") kept as a name only\n"; return OK;
+    }
+    if (w.size() < 9) return fail(d, ERR_ARG, "Illegal region command");
     Deck::Region R;
     for (int k = 0; k < 3; k++) { rc = numeric(d, w[3 + 2 * k], R.lo[k]); if (rc) return rc; rc = numeric(d, w[4 + 2 * k], R.hi[k]); if (rc) return rc; }
     for (size_t k = 9; k + 1 < w.size(); k++) if (w[k] == "units" && w[k + 1] != "box") return fail(d, ERR_UNSUPPORTED, "region units lattice is outside the hot-path scope");
@@ -556,6 +565,7 @@ int one(Deck *d, const std::string &raw)
   if (c == "create_box") {
     if (w.size() != 3) return fail(d, ERR_ARG, "Illegal create_box command");
     if (d->have_box) return fail(d, ERR_ARG, "Cannot create_box after simulation box is defined");
+    if (d->opaque_regions.count(w[2])) return fail(d, ERR_UNSUPPORTED, "create_box from a region that is not a block is outside the hot-path scope");
     if (!d->regions.count(w[2])) return fail(d, ERR_ARG, "Create_box region ID does not exist");
     rc = inumeric(d, w[1], d->ntypes); if (rc) return rc;
     for (int k = 0; k < 3; k++) { d->lo[k] = d->regions[w[2]].lo[k]; d->hi[k] = d->regions[w[2]].hi[k]; }

@@ -156,6 +156,8 @@ compute\t\t1 all erotate
 thermo_style\tcustom step atoms c_1 cpu
 thermo\t\t50000
 fix\t\tctg all check/timestep/gran 1 0.01 0.01
+region\t\tfactory cylinder z 0 0 0.033 0.002 1.0 units box
+fix\t\tbal all balance 100 xyz 20 1.2
 run\t\t1
 unfix\t\tctg
 dump\t\tdmp all custom 50000 out.*.dump id type x y z radius
@@ -167,7 +169,8 @@ run\t\t200
     eng, dk = oracle_deck()
     dk.file(str(tmp_path / "in.tut"))
     assert dk.ntimestep == 500
-    assert "dump ignored" in dk.warnings and "check/timestep/gran ignored" in dk.warnings
+    assert "dump ignored" in dk.warnings and "check/timestep/gran ignored" in dk.warnings and "fix balance ignored" in dk.warnings
+    assert "region factory (cylinder) kept as a name only" in dk.warnings
     # the same through the API calls, step for step
     ref = parity.oracle_engine()
     ref.units("si"); ref.box(lo, hi, [0, 0, 0]); ref.ntypes(2); ref.neighbor(0.001, every=1, delay=0, check=True)
