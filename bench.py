@@ -23,7 +23,10 @@ sys.path.insert(0, os.path.join(ROOT, "liggghts-inl_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
-METRIC = "particle-steps/s (Hertz/history, 4M spheres)"
+try:  # the metric name is BASELINE.json's, verbatim
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+except Exception:
+    METRIC = "particle-steps/s (Hertz/history, 4M spheres) at 1/2/4/8 B200; % HBM roofline"
 MODEL = "model hertz tangential history rolling_friction cdt"
 PROPS = [("youngsModulus", "peratomtype", [5e6]), ("poissonsRatio", "peratomtype", [0.45]),
          ("coefficientRestitution", "peratomtypepair", [0.3]), ("coefficientFriction", "peratomtypepair", [0.5]),
