@@ -93,7 +93,7 @@ int dem_set_pair_style(dem_engine *e, int argc, const char *const *argv);
  *  xcylinder|ycylinder|zcylinder R c1 c2 [shear x|y|z v]` (argv starts at "model")
  *                                                        src/fix_wall_gran.cpp:171-330  */
 int dem_add_wall_primitive(dem_engine *e, const char *id, int argc, const char *const *argv);
-/* `fix ID all mesh/surface file F type T [curvature deg] [precision p]` : the triangles of the file as
+/* `fix ID all mesh/surface[/stress] file F type T [curvature deg] [precision p] [stress on|off] [reference_point x y z]` : the triangles of the file as
  * nodes9[ntri][3][3] (the host layer reads ASCII/binary STL, src/input_mesh_tri.cpp:308-591); load-time
  * scale/move/rotate are applied by the caller.  Geometry, topology and active edge/corner flags follow
  *                          src/surface_mesh_I.h:302-582,1040-1236, src/multi_node_mesh_I.h:153-321  */
@@ -150,6 +150,10 @@ int dem_download_wall_history(dem_engine *e, const char *wall_id, double *out, l
 int dem_download_mesh(dem_engine *e, const char *mesh_id, const char *field, void *out, long count);
 /* per-particle mesh contact rows (reference: FixContactHistoryMesh partner_/contacthistory_,
  * src/fix_contact_history_mesh.h): one row per (particle, triangle) holding history, sorted by (tag, triangle id) */
+/* `f_<mesh>[1..9]` of a `fix ID all mesh/surface/stress ...` (dem_add_mesh with "stress on" [, "reference_point x y z"]): total
+ * force on the mesh in the last step, total torque about the reference point, the reference point (it travels with a moving
+ * mesh).  Rank-local sum with several ranks.   src/mesh_module_stress.cpp:286-345,479-488, src/fix_wall_gran_base.h:350-362 */
+int dem_mesh_force(dem_engine *e, const char *mesh_id, double *out9);
 int dem_mesh_contact_count(dem_engine *e, const char *mesh_id, long *nrows, int *dnum);
 int dem_download_mesh_contacts(dem_engine *e, const char *mesh_id, int *tag, int *tri, double *hist);
 

@@ -455,9 +455,15 @@ int cmd_fix(Deck *d, const std::vector<std::string> &w)
         if (std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]) < 1e-5) return fail(d, ERR_ARG, "illegal magnitude of rotation axis");
         mesh_rotate(nodes, ax, ang);
         k += 7;
-      } else if (key == "curvature" || key == "precision") { rc = need(1); if (rc) return rc; pass.push_back(key); pass.push_back(w[k + 1]); k += 2; }
+      } else if (key == "curvature" || key == "precision" || key == "stress") { rc = need(1); if (rc) return rc; pass.push_back(key); pass.push_back(w[k + 1]); k += 2; }
+      else if (key == "reference_point") { rc = need(3); if (rc) return rc; pass.push_back(key); for (int c = 1; c <= 3; c++) pass.push_back(w[k + c]); k += 4; }
       else if (key == "verbose" || key == "heal") { rc = need(1); if (rc) return rc; k += 2; }
       else return fail(d, ERR_UNSUPPORTED, "fix mesh/surface keyword '%s' is outside the hot-path scope", key.c_str());
+    }
+    if (style == "mesh/surface/stress") {  // the stress module tracks the total force unless the deck says `stress off`
+      bool given = false;
+      for (size_t k = 0; k + 1 < pass.size(); k++) if (pass[k] == "stress") given = true;
+      if (!given) { pass.push_back("stress"); pass.push_back("on"); }
     }
     std::vector<const char *> a = cptrs(pass, 0);
     TRY(API(add_mesh)(d->e, id.c_str(), atom_type, nodes.data(), (long)(nodes.size() / 9), (int)a.size(), a.data()));

@@ -212,6 +212,7 @@ struct dem_engine {
   struct MeshWall { std::string id; ModelP m; std::vector<int> mesh; };
   std::vector<MeshWall> mwalls;
   std::vector<TriRec> htri; std::vector<int> hcn;
+  DevBuf<double> dmforce, dmpref; int any_stress = 0;  // fix mesh/surface/stress accumulators / reference points
   DevBuf<TriRec> dtri; DevBuf<int> dcn, dcell_start, dcell_tri, mint[2]; DevBuf<double> dnodes_last; DevBuf<double4> mhist[2];
   int mcur = 0, mslots = 8, mcand = 16, mhrec = 0, mesh_ready = 0, grid_ready = 0, any_moving = 0;
   double mgorg[3] = {0, 0, 0}, mginv[3] = {1, 1, 1}; int mgnc[3] = {1, 1, 1};
@@ -329,6 +330,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
   e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release();
+  e->dmforce.release(); e->dmpref.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
   for (int s = 0; s < 2; s++) { e->ls[s].nbr.release(); e->ls[s].ptag.release(); e->ls[s].numneigh.release(); e->ls[s].hist.release(); }
@@ -590,6 +592,12 @@ extern "C" int dem_add_mesh(dem_engine *e, const char *id, int atom_type, const 
     if (k + 1 >= argc) dem_fail(e, DEM_ERR_ARG, "mesh keyword '%s' needs a value", argv[k]);
     if (!strcmp(argv[k], "curvature")) M.curvature = cos(atof(argv[k + 1]) * 3.14159265358979323846 / 180.);
     else if (!strcmp(argv[k], "precision")) M.precision = atof(argv[k + 1]);
+    else if (!strcmp(argv[k], "stress")) M.stress = !strcmp(argv[k + 1], "on");  // fix mesh/surface/stress (mesh_module_stress.cpp:120-140)
+    else if (!strcmp(argv[k], "reference_point")) {
+      if (k + 3 >= argc) dem_fail(e, DEM_ERR_ARG, "mesh keyword 'reference_point' needs three values");
+      for (int d = 0; d < 3; d++) M.p_ref[d] = atof(argv[k + 1 + d]);
+      k += 2;
+    }
     else dem_fail(e, DEM_ERR_UNSUPPORTED, "fix mesh/surface keyword '%s' is outside the hot-path scope (apply scale/move/rotate to the nodes before the call)", argv[k]);
   }
   e->meshes.push_back(M);
@@ -658,12 +666,14 @@ static MeshP mesh_params(dem_engine *E)
   MeshP M;
   memset(&M, 0, sizeof M);
   M.ntri = (int)E->htri.size(); M.nmesh = (int)E->meshes.size(); M.mslots = E->mslots; M.mcand = E->mcand; M.cap = E->cap; M.hrec = E->mhrec;
+  M.mforce = E->any_stress ? E->dmforce.p : nullptr; M.mpref = E->any_stress ? E->dmpref.p : nullptr;
   M.tri = E->dtri.p; M.nodes_last = E->dnodes_last.p; M.cn = E->dcn.p; M.cell_start = E->dcell_start.p; M.cell_tri = E->dcell_tri.p;
   for (int d = 0; d < 3; d++) { M.gorg[d] = E->mgorg[d]; M.ginv[d] = E->mginv[d]; M.gnc[d] = E->mgnc[d]; }
   M.mint = E->mint[E->mcur].p; M.mhist = E->mhist[E->mcur].p;
   for (size_t m = 0; m < E->meshes.size(); m++) {
     const MeshHost &H = E->meshes[m];
     MeshMeta &mm = M.meta[m];
+    mm.stress = H.stress;
     mm.atom_type = H.atom_type; mm.wall = H.wall; mm.moving = H.moving; mm.first = H.first; mm.ntri = H.ntri; mm.precision = H.precision;
     for (int d = 0; d < 3; d++) mm.vel[d] = H.vel[d];
     if (H.moving == 2) {  // MultiNodeMesh::rotate(dAngle, axis, p), multi_node_mesh_I.h:620-640
@@ -706,6 +716,16 @@ static void mesh_prepare(dem_engine *E)
   if (E->opt.count("meshslots")) E->mslots = std::min(30, std::max(2, (int)E->opt["meshslots"]));
   if (E->opt.count("meshcand")) E->mcand = std::max(4, (int)E->opt["meshcand"]);
   cudaStream_t st = E->stream;
+  E->any_stress = 0;
+  for (auto &H : E->meshes) if (H.stress) E->any_stress = 1;
+  if (E->any_stress) {
+    E->dmforce.ensure(E, 6 * DEM_MAXMESH); E->dmpref.ensure(E, 3 * DEM_MAXMESH);
+    double hp[3 * DEM_MAXMESH] = {0};
+    for (size_t m = 0; m < E->meshes.size(); m++) for (int d = 0; d < 3; d++) hp[3 * m + d] = E->meshes[m].p_ref[d];
+    CK(cudaMemcpyAsync(E->dmpref.p, hp, sizeof hp, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(E->dmforce.p, 0, 6 * DEM_MAXMESH * sizeof(double), st));
+    CK(cudaStreamSynchronize(st));
+  }
   E->dtri.ensure(E, E->htri.size()); E->dcn.ensure(E, E->hcn.size()); E->dnodes_last.ensure(E, 9 * E->htri.size());
   CK(cudaMemcpyAsync(E->dtri.p, E->htri.data(), E->htri.size() * sizeof(TriRec), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(E->dcn.p, E->hcn.data(), E->hcn.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1681,6 +1701,7 @@ static void launch_step(dem_engine *E, int mode, bool timed)
     P.fa = E->fa.p; P.ta = E->ta.p;
   }
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
+  if (have_mesh_walls(E) && E->mesh_ready && E->any_stress) CK(cudaMemsetAsync(E->dmforce.p, 0, 6 * DEM_MAXMESH * sizeof(double), E->stream));  // MeshModuleStress::pre_force
   if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
   if (E->have_pair && E->pm.cohesion) {
@@ -2091,6 +2112,22 @@ static void collect_mesh_rows(dem_engine *E, const MeshHost &m, std::vector<Mesh
     if (t >= m.first && t < m.first + m.ntri) rows.push_back(MeshRow{tags[i], t - m.first, (long)s * E->cap + i});
   }
   std::sort(rows.begin(), rows.end(), [](const MeshRow &a, const MeshRow &b) { return a.tag != b.tag ? a.tag < b.tag : a.tri < b.tri; });
+}
+extern "C" int dem_mesh_force(dem_engine *e, const char *mesh_id, double *out9)
+{
+  API_BEGIN
+  if (!out9) dem_fail(e, DEM_ERR_ARG, "null output");
+  CK(cudaSetDevice(e->device));
+  for (size_t m = 0; m < e->meshes.size(); m++) if (e->meshes[m].id == mesh_id) {
+    if (!e->meshes[m].stress) dem_fail(e, DEM_ERR_STATE, "mesh %s does not track stress (fix mesh/surface/stress)", mesh_id);
+    if (!e->mesh_ready) { for (int d = 0; d < 6; d++) out9[d] = 0.0; for (int d = 0; d < 3; d++) out9[6 + d] = e->meshes[m].p_ref[d]; return DEM_OK; }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out9, e->dmforce.p + 6 * m, 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out9 + 6, e->dmpref.p + 3 * m, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return DEM_OK;
+  }
+  dem_fail(e, DEM_ERR_ARG, "no mesh with id %s", mesh_id);
+  API_END
 }
 extern "C" int dem_mesh_contact_count(dem_engine *e, const char *mesh_id, long *n, int *dnum)
 {

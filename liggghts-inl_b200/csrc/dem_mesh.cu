@@ -293,6 +293,14 @@ __global__ void __launch_bounds__(128) k_mesh_step(const StepP P, const MeshP M)
       ContactOut o;
       mesh_chain(P, wm, c, h, g, su, o);
       F[0] += o.F[0]; F[1] += o.F[1]; F[2] += o.F[2];
+      if (mm.stress && M.mforce) {  // MeshModuleStress::add_particle_contribution mesh_module_stress.cpp:316-345 (an output: summation order is free)
+        const double frc[3] = {-o.F[0], -o.F[1], -o.F[2]};
+        const double *pr = M.mpref + 3 * T.mesh;
+        const double a0 = (pos[0] + delta[0]) - pr[0], a1 = (pos[1] + delta[1]) - pr[1], a2 = (pos[2] + delta[2]) - pr[2];  // contact point - p_ref
+        double *acc = M.mforce + 6 * T.mesh;
+        atomicAdd(acc + 0, frc[0]); atomicAdd(acc + 1, frc[1]); atomicAdd(acc + 2, frc[2]);
+        atomicAdd(acc + 3, a1 * frc[2] - a2 * frc[1]); atomicAdd(acc + 4, a2 * frc[0] - a0 * frc[2]); atomicAdd(acc + 5, a0 * frc[1] - a1 * frc[0]);
+      }
       Tq[0] += o.Ti[0]; Tq[1] += o.Ti[1]; Tq[2] += o.Ti[2];
       if (su) {
         if (wm.rec_shear >= 0) *hist_rec(M, slot, wm.rec_shear, i) = make_double4(h[0], h[1], h[2], 0.);
@@ -334,6 +342,16 @@ __global__ void __launch_bounds__(128) k_mesh_move(const MeshP M, int mesh, doub
   const int t = mm.first + q;
   TriRec &T = M.tri[t];
   bool trig = false;
+  if (q == 0 && mm.stress && M.mpref) {  // the reference point is a mesh property: it travels with the mesh
+    double *pr = M.mpref + 3 * mesh;
+    if (mm.moving == 2) {
+      double v[3] = {pr[0], pr[1], pr[2]};
+      if (mm.rot_trans) for (int d = 0; d < 3; d++) v[d] = v[d] + (-mm.rot_origin[d]);
+      vec_quat_rotate(v, mm.rot_dq);
+      if (mm.rot_trans) for (int d = 0; d < 3; d++) v[d] = v[d] + mm.rot_origin[d];
+      pr[0] = v[0]; pr[1] = v[1]; pr[2] = v[2];
+    } else for (int d = 0; d < 3; d++) pr[d] = pr[d] + mm.vel[d] * dt;
+  }
   if (mm.moving == 2) {
     double c[3] = {0., 0., 0.};
     for (int j = 0; j < 3; j++) {

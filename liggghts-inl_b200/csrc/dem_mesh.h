@@ -10,6 +10,7 @@
 //   sphere/triangle contact    tri_mesh_I.h:65-271, math_extra_liggghts.h:583-594
 //   contact rows + coplanar    fix_contact_history_mesh_I.h:51-215, fix_contact_history_mesh.cpp:315-505
 //   wall force driver          fix_wall_gran.cpp:803-982, fix_wall_gran_base.h:159-367
+//   total force on a mesh      mesh_module_stress.cpp:286-345,479-488 (fix mesh/surface/stress)
 //   mesh motion                fix_move_mesh.cpp:221-238, mesh_mover_linear.cpp:94-112, multi_node_mesh_I.h:502-526,792-826
 //                              rotate: mesh_mover_rotation.cpp:58-125, multi_node_mesh_I.h:620-672, tracking_mesh_I.h:400-411
 #pragma once
@@ -31,6 +32,7 @@ struct MeshMeta {
   // rotate: origin, omega*axis, and the per-step quaternion (cos(dphi/2), axis*sin(dphi/2)) evaluated on the host with libm
   double rot_origin[3], rot_omegavec[3], rot_dq[4];
   int rot_trans;  // |origin|^2 > 0 (multi_node_mesh_I.h:648)
+  int stress;     // fix mesh/surface/stress: accumulate the total force / torque on this mesh
 };
 
 struct MeshP {
@@ -41,6 +43,8 @@ struct MeshP {
   int hrec;    // 32-byte history records per contact row (max over the mesh walls)
   TriRec *tri;
   double *nodes_last;   // [9][ntri] node positions at the last rebuild (moving meshes)
+  double *mforce;       // [nmesh][6] total force and torque of the current step on the stress-tracking meshes (or null)
+  double *mpref;        // [nmesh][3] their reference points (travel with a moving mesh)
   const int *cn;        // coplanar node-neighbours of triangle t: cn[t] .. cn[t+1] index into this same array (CSR: ntri+1 offsets, then the
                         // ascending lists) -- no fixed width: a flat fan of 256 triangles has 255 of them per triangle
   // coarse uniform grid over the box: cell -> ascending triangle ids (CSR)

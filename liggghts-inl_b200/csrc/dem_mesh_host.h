@@ -26,6 +26,7 @@ struct MeshHost {
   int atom_type = 1, ntri = 0, first = 0, wall = -1, moving = 0;  // moving: 0 static, 1 linear, 2 rotate
   double vel[3] = {0, 0, 0};
   double rot_origin[3] = {0, 0, 0}, rot_axis[3] = {0, 0, 1}, rot_omega = 0.;  // fix move/mesh rotate (axis normalised)
+  int stress = 0; double p_ref[3] = {0, 0, 0};  // fix mesh/surface/stress: total force / torque about p_ref (mesh_module_stress.cpp)
   double curvature = 1. - 0.00001, precision = 1e-8;  // surface_mesh.h:61, multi_node_mesh.h:59
   std::vector<double> nodes;                          // [ntri][3][3] as given by the caller
   std::vector<int> edge_active, corner_active, obtuse, nneighs;  // read-back for tests (dem_download_mesh)

@@ -12,7 +12,7 @@ ABI_SYMBOLS = [
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
-    "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_contact_count", "dem_download_mesh_contacts",
+    "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
     "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
 ]
 
@@ -261,6 +261,12 @@ class Engine:
         else:
             out = np.zeros(ntri, np.int32)
         self._call("download_mesh", [C.c_char_p, C.c_char_p, C.c_void_p, C.c_long], mesh_id.encode(), field.encode(), out.ctypes.data, out.size)
+        return out
+
+    def mesh_force(self, mesh_id):
+        """`f_<mesh>[1..9]` of a `fix mesh/surface/stress`: total force, total torque about the reference point, reference point"""
+        out = np.zeros(9, np.float64)
+        self._call("mesh_force", [C.c_char_p, C.c_void_p], mesh_id.encode(), out.ctypes.data)
         return out
 
     def mesh_contacts(self, mesh_id):

@@ -68,6 +68,7 @@ typedef struct {  /* TriMesh + FixNeighlistMesh + FixContactHistoryMesh of one `
   double (*node)[3][3], (*center)[3], *rbound, (*edgeVec)[3][3], (*edgeLen)[3], (*surfNorm)[3], (*edgeNorm)[3][3];
   int *obtuse, *nNeighs, (*neighFaces)[NUM_NEIGH_MAX]; unsigned char (*edgeActive)[3], (*cornerActive)[3];
   double curvature, precision;
+  int stress; double f_total[3], torque_total[3], p_ref[3]; /* fix mesh/surface/stress: mesh_module_stress.cpp:286-345,479-488 */
   int moving; /* 0 static, 1 `linear`, 2 `rotate` */ double vel[3]; double rot_origin[3], rot_axis[3], rot_omega; double (*vnode)[3][3]; double (*nodesLastRe)[3][3]; int next_reneighbor;
   /* FixNeighlistMesh: per-triangle particle lists */
   int **contacts; int *ncontacts, *capcontacts;
@@ -874,6 +875,8 @@ int orc_add_mesh(orc_engine *e, const char *id, int atom_type, const double *nod
   for (int k = 0; k + 1 < argc; k += 2) {
     if (!strcmp(argv[k], "curvature")) M->curvature = cos(atof(argv[k + 1]) * M_PI / 180.); /* fix_mesh.cpp: curvature given in degrees */
     else if (!strcmp(argv[k], "precision")) M->precision = atof(argv[k + 1]);
+    else if (!strcmp(argv[k], "stress")) M->stress = !strcmp(argv[k + 1], "on"); /* mesh_module_stress.cpp:120-140 */
+    else if (!strcmp(argv[k], "reference_point") && k + 3 < argc) { for (int d = 0; d < 3; d++) M->p_ref[d] = atof(argv[k + 1 + d]); k += 2; }
     else return fail(e, "mesh option not supported by the oracle");
   }
   const size_t T = (size_t)(ntri ? ntri : 1);
@@ -1097,6 +1100,7 @@ static void mesh_wall_compute(orc_engine *e, meshwall_t *W, int shearupdate)
   const int dnum = W->m.dnum; const double cdmul = e->cdf - 1.0; const double cutneighmax = cutneighmax_of(e);
   for (int im = 0; im < W->nmesh; im++) {
     mesh_t *M = &e->meshes[W->mesh[im]];
+    for (int d = 0; d < 3; d++) M->f_total[d] = M->torque_total[d] = 0.; /* MeshModuleStress::pre_force :286-297 */
     for (long i = 0; i < e->n; i++) for (int k = 0; k < M->nneighs[i]; k++) M->keep[i][k] = 0; /* markAllContacts */
     for (int t = 0; t < M->ntri; t++) for (int c = 0; c < M->ncontacts[t]; c++) {
       const int ip = M->contacts[t][c];
@@ -1136,7 +1140,16 @@ static void mesh_wall_compute(orc_engine *e, meshwall_t *W, int shearupdate)
         for (int d = 0; d < 3; d++) sd->en[d] = sd->delta[d] * sd->rinv;
         sd->hist = hist; sd->flag = NULL;
         chain_intersect(e, &W->m, sd);
+        double force_old[3] = {e->f[3 * ip], e->f[3 * ip + 1], e->f[3 * ip + 2]};
         for (int d = 0; d < 3; d++) { e->f[3 * ip + d] += sd->Fi[d]; e->torque[3 * ip + d] += sd->Ti[d]; }
+        if (M->stress) { /* fix_wall_gran_base.h:350-362 (f_pw = f - force_old) + MeshModuleStress::add_particle_contribution :316-345 */
+          double frc[3], cp[3], tmp[3];
+          for (int d = 0; d < 3; d++) { frc[d] = -(e->f[3 * ip + d] - force_old[d]); cp[d] = e->x[3 * ip + d] + delta[d]; }
+          for (int d = 0; d < 3; d++) { M->f_total[d] = M->f_total[d] + frc[d]; tmp[d] = cp[d] - M->p_ref[d]; }
+          M->torque_total[0] = M->torque_total[0] + (tmp[1] * frc[2] - tmp[2] * frc[1]);
+          M->torque_total[1] = M->torque_total[1] + (tmp[2] * frc[0] - tmp[0] * frc[2]);
+          M->torque_total[2] = M->torque_total[2] + (tmp[0] * frc[1] - tmp[1] * frc[0]);
+        }
       } else chain_close(&W->m, hist, NULL);
     }
     /* cleanUpContacts :437-463 */
@@ -1188,6 +1201,10 @@ static void mesh_rotate_step(orc_engine *e, mesh_t *M)
       vRot[0] = omegaVec[1] * rPA[2] - omegaVec[2] * rPA[1]; vRot[1] = omegaVec[2] * rPA[0] - omegaVec[0] * rPA[2]; vRot[2] = omegaVec[0] * rPA[1] - omegaVec[1] * rPA[0];
       for (int d = 0; d < 3; d++) M->vnode[t][j][d] = 0. + vRot[d]; }
   }
+  { double *q = M->p_ref; /* TrackingMesh::rotate: customValues_.move(-origin), rotate(dQ), move(origin) on the global properties too */
+    if (trans) for (int d = 0; d < 3; d++) q[d] = q[d] + (-origin[d]);
+    vec_quat_rotate(q, dQ);
+    if (trans) for (int d = 0; d < 3; d++) q[d] = q[d] + origin[d]; }
 }
 static void mesh_move_step(orc_engine *e)
 { /* FixMoveMesh::initial_integrate fix_move_mesh.cpp:221-238 + MeshMoverLinear::initial_integrate mesh_mover_linear.cpp:94-112
@@ -1198,7 +1215,9 @@ static void mesh_move_step(orc_engine *e)
     for (int t = 0; t < M->ntri; t++) {
       for (int j = 0; j < 3; j++) for (int d = 0; d < 3; d++) { M->node[t][j][d] = M->node[t][j][d] + dx[d]; M->vnode[t][j][d] = 0. + M->vel[d]; }
       for (int d = 0; d < 3; d++) M->center[t][d] = M->center[t][d] + dx[d];
-    } }
+    }
+    for (int d = 0; d < 3; d++) M->p_ref[d] = M->p_ref[d] + dx[d]; /* p_ref is a frame_general mesh property: it travels with the mesh (mesh_module_stress.cpp:75-80) */
+  }
 }
 static int mesh_decide_rebuild(orc_engine *e)
 { /* FixMesh::pre_force fix_mesh.cpp:553-576 + MultiNodeMesh::decideRebuild multi_node_mesh_I.h:792-826: a node moved more than
@@ -1544,6 +1563,14 @@ int orc_download_mesh(orc_engine *e, const char *mesh_id, const char *field, voi
     if (!strcmp(field, "obtuse") && count == T) { for (int k = 0; k < T; k++) ((int *)out)[k] = M->obtuse[k]; return 0; }
     if (!strcmp(field, "nneighs") && count == T) { for (int k = 0; k < T; k++) ((int *)out)[k] = M->nNeighs[k]; return 0; }
     return fail(e, "unknown mesh field or wrong count"); }
+  return fail(e, "no such mesh");
+}
+int orc_mesh_force(orc_engine *e, const char *mesh_id, double *out9)
+{ /* FixMeshSurface::compute_vector(0..8) of the stress module: total force, total torque about p_ref, p_ref */
+  for (int m = 0; m < e->nmeshes; m++) if (!strcmp(e->meshes[m].id, mesh_id)) { mesh_t *M = &e->meshes[m];
+    if (!M->stress) return fail(e, "mesh does not track stress (fix mesh/surface/stress)");
+    for (int d = 0; d < 3; d++) { out9[d] = M->f_total[d]; out9[3 + d] = M->torque_total[d]; out9[6 + d] = M->p_ref[d]; }
+    return 0; }
   return fail(e, "no such mesh");
 }
 int orc_mesh_contact_count(orc_engine *e, const char *mesh_id, long *n, int *dnum)

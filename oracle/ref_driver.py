@@ -102,6 +102,16 @@ class Ref:
         L.ref_mesh_topology(self.h, mesh_id.encode(), nodes.ctypes.data, ea.ctypes.data, ca.ctypes.data, nn.ctypes.data)
         return {"nodes": nodes, "edge_active": ea, "corner_active": ca, "nneighs": nn}
 
+    def fix_vector(self, fix_id, n):
+        """global vector of a fix (Fix::compute_vector(0..n-1)) through lammps_extract_fix(style 0, type 1)"""
+        out = np.zeros(n)
+        for i in range(n):
+            p = self.lib.lammps_extract_fix(self.h, fix_id.encode(), 0, 1, i, 0)
+            out[i] = C.cast(p, C.POINTER(C.c_double))[0]
+            self.lib.lammps_free.argtypes = [C.c_void_p]
+            self.lib.lammps_free(p)
+        return out
+
     def mesh_geometry(self, mesh_id):
         L = self.lib
         L.ref_mesh_ntri.argtypes = [C.c_void_p, C.c_char_p]

@@ -218,7 +218,8 @@ def to_deck(c, datafile):
     for mid, mtype, nodes in c.get("meshes", []):
         stl = os.path.join(os.path.dirname(datafile), mid + ".stl")
         write_stl(stl, nodes, mid)
-        deck.append("fix %s all mesh/surface file %s type %d" % (mid, stl, mtype))
+        style = "mesh/surface/stress" if mid in c.get("mesh_stress", []) else "mesh/surface"
+        deck.append("fix %s all %s file %s type %d" % (mid, style, stl, mtype))
     for mid, text in c.get("mesh_moves", []):
         deck.append("fix mv_%s all move/mesh mesh %s %s" % (mid, mid, text))
     for wid, text in c.get("mesh_walls", []):
@@ -245,7 +246,7 @@ def apply(c, eng):
     for wid, text in c["walls"]:
         eng.wall_primitive(wid, text)
     for mid, mtype, nodes in c.get("meshes", []):
-        eng.mesh(mid, mtype, nodes)
+        eng.mesh(mid, mtype, nodes, options="stress on" if mid in c.get("mesh_stress", []) else "")
     for mid, text in c.get("mesh_moves", []):
         eng.move_mesh(mid, text)
     for wid, text in c.get("mesh_walls", []):
@@ -278,6 +279,9 @@ GOLDEN_CASES = {
                               checkpoints=[0, 1, 10, 1500, 3000]),
     "mesh_plate_moving": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
     "mesh_drum_rotating": dict(mesh="drum", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 10, 1500, 3000]),
+    # fix mesh/surface/stress: total force / torque on a static floor, a moving plate and a rotating drum (reference point travels)
+    "mesh_plate_stress": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), stress=["cad", "plate"], checkpoints=[0, 1, 10, 1500, 3000]),
+    "mesh_drum_stress": dict(mesh="drum", kw=dict(n3=(4, 4, 3)), stress=["drum"], checkpoints=[0, 1, 600, 1500, 3000]),
     # `fix move/mesh` issued between two runs (the t01a tutorial deck starts its mesh after the settling run)
     "mesh_plate_late_move": dict(mesh="plate", kw=dict(n3=(4, 4, 3)), checkpoints=[0, 1, 200, 201, 210, 800, 2000], late_move_at=201),
     # bonded spheres (INL bond models): bonds form at step 2, stretch, some break
@@ -295,6 +299,8 @@ def make_case(name):
     g = GOLDEN_CASES[name]
     if "mesh" in g:
         c = case_mesh(kind=g["mesh"], name=name, **g["kw"])
+        if "stress" in g:
+            c["mesh_stress"] = list(g["stress"])
         if "late_move_at" in g:  # the movers are not part of the initial deck: late_commands() issues them before that checkpoint
             c["late_moves"] = (g["late_move_at"], c.pop("mesh_moves"))
         return c
@@ -331,4 +337,6 @@ def snapshot(eng, c):
     for mid, mtype, nodes in c.get("meshes", []):
         m = eng.mesh_contacts(mid)
         out["mesh_%s_tag" % mid] = m["tag"]; out["mesh_%s_tri" % mid] = m["tri"]; out["mesh_%s_hist" % mid] = m["hist"]
+        if mid in c.get("mesh_stress", []):
+            out["meshforce_%s" % mid] = eng.mesh_force(mid)
     return out

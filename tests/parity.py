@@ -76,6 +76,16 @@ def compare_snapshot(got, ref, rmass, tol=FTOL, tol_state=None, hist_tol=None, l
             if rh.size:
                 errs["mesh_" + mid] = float(np.abs(gh - rh).max() / max(np.abs(rh).max(), 1e-300))
                 assert errs["mesh_" + mid] <= hist_tol, "%s: mesh %s history rel err %.3e" % (label, mid, errs["mesh_" + mid])
+    for k in ref:  # fix mesh/surface/stress: total force, total torque, reference point of a mesh (f_<id>[1..9])
+        if k.startswith("meshforce_"):
+            assert k in got, label + ": " + k + " missing"
+            gv, rv = np.asarray(got[k]), np.asarray(ref[k])
+            fs = max(np.abs(rv[:3]).max(), 1e-12 * float(mg.max()))
+            errs[k] = float(np.abs(gv[:3] - rv[:3]).max() / fs)
+            assert errs[k] <= max(tol, 1e-12), "%s: %s force rel err %.3e" % (label, k, errs[k])
+            ts = max(np.abs(rv[3:6]).max(), fs * 1e-3)
+            assert np.abs(gv[3:6] - rv[3:6]).max() / ts <= max(tol, 1e-12), "%s: %s torque differs" % (label, k)
+            assert np.abs(gv[6:9] - rv[6:9]).max() <= 1e-14 * max(1.0, np.abs(rv[6:9]).max()), "%s: %s reference point differs" % (label, k)
     return errs
 
 
