@@ -70,6 +70,20 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_first(self, timeout=5.0):
+        """block until nvidia-smi has printed its first sample: its start-up (NVML initialisation over all GPUs of the box,
+        tens to hundreds of milliseconds during which CUDA calls of running processes stall) must not fall into a timed region"""
+        if not self.p:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -116,6 +130,22 @@ def ref_worker(tiles, steps, out):
     r.cmd("run %d" % steps)
     dt = time.perf_counter() - t0
     json.dump({"seconds": dt, "n": len(c["tag"]), "steps": steps}, open(out, "w"))
+
+
+def ref_state_worker(steps, out):
+    """parity leg: the unmodified reference steps ONE periodic tile of the bed `steps` timesteps from the bench's initial state
+    and writes x, v by tag -- the checker of the `parity` field, never timed"""
+    import cases
+    import ref_driver
+    c = bed_case(1, 1, name="cpu")
+    tmp = tempfile.mkdtemp()
+    deck, data = cases.to_deck(c, os.path.join(tmp, "bed.data"))
+    open(os.path.join(tmp, "bed.data"), "w").write(data)
+    r = ref_driver.Ref()
+    r.cmd(deck)
+    r.cmd("run %d" % steps)
+    a = r.atoms()
+    np.savez(out, x=a["x"], v=a["v"], omega=a["omega"])
 
 
 def run_reference_procs(nproc, tiles, steps):
@@ -225,14 +255,21 @@ def own_arm(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl")
+    # clocks / throttle reasons are sampled over the whole run of rank 0's GPU; nvidia-smi is started FIRST and its first
+    # sample awaited, so that its start-up (which stalls CUDA calls of running processes) cannot fall into a timed region
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("DEM_BENCH_NO_SAMPLER")) else None
+    have_comm = [False]
 
     def new_engine():
         if world == 1:
             return dem_b200.Engine(device=local)
+        if have_comm[0]:  # explicit reuse of the communicator the previous engine of this process released (dem_b200.h: dem_create)
+            return dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=None)
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(dem_b200.Engine.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
+        have_comm[0] = True
         return dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=buf.cpu().numpy().tobytes())
 
     def allmax(v):
@@ -248,24 +285,32 @@ def own_arm(args):
     tiles = args.tiles
     c = bed_case(tiles, tiles)
     n = len(c["tag"])
+    if world > 1:
+        # every rank holds (and uploads) its own brick of the bed, like a rank of the reference after read_data: the
+        # engine's own decomposition code decides the ownership (dem_brick_layout == dem_upload_particles' test)
+        lay = dem_b200.brick_layout(world, rank, c["lo"], c["hi"], c["periodic"], x=c["x"])
+        mine = lay["mine"] != 0
+        for k in ("tag", "type", "mask", "x", "v", "omega", "radius", "density"):
+            c[k] = np.ascontiguousarray(c[k][mine])
+    n_mine = len(c["tag"])
     eng = cases.apply(c, new_engine())
     eng.option("time_kernels", 1)
     if os.environ.get("DEM_DEBUG"):
         eng.option("debug", int(os.environ["DEM_DEBUG"]))  # profiling aid only (the numbers are not bench values)
     eng.setup()
+    if sampler:
+        sampler.wait_first()
     eng.run(max(args.warmup, 3))
     st0 = eng.stats()
     torch.cuda.synchronize()
     if dist: dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     eng.run(args.steps)
     e1.record(); torch.cuda.synchronize()
     if dist: dist.barrier()
     ms = allmax(e0.elapsed_time(e1))
-    clocks = sampler.stop()
     st = eng.stats()
     value = n * args.steps / (ms * 1e-3)
     # roofline of the dominant (fused step) kernel
@@ -287,28 +332,60 @@ def own_arm(args):
                 "kernel_share_of_step": kms * st.step_kernel_calls / ms if ms > 0 else None}
     launches = st.kernel_launches - st0.kernel_launches
     nbuilds = st.nbuilds
-    # upper bound of the cost of one neighbour rebuild, reported next to the step time: wall time of setup() on a running engine
-    # (a full rebuild -- sort, gather, cell ranges, halo lists, list build + history remap; its stages sum to 3.2 ms for 4.19M
-    # spheres under DEM_B200_TRACE -- plus Verlet::setup's force evaluation with force read-out and the host synchronisation)
-    eng.setup()  # (the first rebuild after the initial one allocates the second list set: not steady state)
-    torch.cuda.synchronize(); tr0 = time.perf_counter()
-    eng.setup()
-    torch.cuda.synchronize()
-    rebuild_ms = allmax((time.perf_counter() - tr0) * 1e3) - (kms if kms > 0 else 0.0)
 
-    # end-to-end through the public API with host buffers: upload -> setup -> run(K) -> download
-    ke = args.steps
+    # ---- neighbour rebuilds ("with and without amortised rebuilds" + a falling window) ------------------
+    # (a) cost of ONE rebuild in the steady state of this bed: the same window again with forced rebuilds (`neigh_modify
+    #     every R check no`); the difference to the rebuild-free window divided by the number of rebuilds
+    R = max(2, min(10, args.steps // 2))
+    nsteps_r = (args.steps // R) * R
+    eng.neighbor(c["skin"], every=R, delay=0, check=False)
+    eng.run(R)  # (the first rebuild after the initial one allocates the second list set: not steady state)
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    b0 = eng.stats().nbuilds
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(); eng.run(nsteps_r); r1.record(); torch.cuda.synchronize()
+    ms_forced = allmax(r0.elapsed_time(r1))
+    nb_forced = nsteps_r // R
+    rebuild_ms = max(ms_forced - nsteps_r * ms / args.steps, 0.0) / max(nb_forced, 1)
+    eng.neighbor(c["skin"], every=1, delay=0, check=True)
     eng.close()
+    # (b) a FALLING window: the same bed stretched by 15 % in z (no new overlaps: distances only grow) and dropped; the bed
+    #     collapses back onto itself, contacts re-form and the distance check trips rebuilds at its own pace.  Its
+    #     particle-steps/s includes every rebuild -- the honest throughput of an unsettled bed.
+    falling = None
+    if not args.no_falling:
+        cf = dict(c); cf["x"] = c["x"] * np.array([1.0, 1.0, 1.15]); cf["hi"] = [c["hi"][0], c["hi"][1], c["hi"][2] * 1.15 + 0.01]
+        engf = cases.apply(cf, new_engine())
+        engf.setup(); engf.run(20)
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fsteps = max(args.falling_steps, 1)
+        f0.record(); engf.run(fsteps); f1.record(); torch.cuda.synchronize()
+        ms_f = allmax(f0.elapsed_time(f1))
+        sf = engf.stats()
+        falling = {"value": n * fsteps / (ms_f * 1e-3), "unit": "particle-steps/s", "steps": fsteps, "rebuilds": int(sf.nbuilds),
+                   "ms_per_step": ms_f / fsteps, "workload": "the same bed stretched 1.15x in z and dropped (contacts re-form; rebuilds included)"}
+        engf.close()
+    amortised = None
+    if falling and falling["rebuilds"] > 0:
+        interval = falling["steps"] / falling["rebuilds"]
+        amortised = {"value": n / ((ms / args.steps + rebuild_ms / interval) * 1e-3), "unit": "particle-steps/s",
+                     "rebuild_interval_steps": interval, "note": "settled-bed step time + rebuild_ms spread over the falling window's measured rebuild interval"}
+
+    # ---- end to end through the public API with host buffers: create -> upload -> setup -> run(K) -> download -----------
+    ke = args.steps
     # the job's host buffers are page-locked (inputs and results), as a production caller's would be
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True); v = t.numpy(); v[...] = a; return v
-    import numpy as np
     cp = dict(c)
     for k in ("tag", "type", "mask", "x", "v", "omega", "radius", "density"):
         cp[k] = pinned(np.ascontiguousarray(c[k], np.int32 if k in ("tag", "type", "mask") else np.float64))
-    xo = pinned(np.zeros((n, 3))) if world == 1 else None
-    vo = pinned(np.zeros((n, 3))) if world == 1 else None
-    # one short untimed pass of the same job first (warm-up, like the W steps of the kernel-level number)
+    xo = pinned(np.zeros((n_mine, 3))); vo = pinned(np.zeros((n_mine, 3)))
+    # one short untimed pass of the same job first (warm-up, like the W steps of the kernel-level number): the timed job
+    # therefore runs in a WARM process -- device blocks, page-locked flag words and (multi-GPU) the NCCL communicator are
+    # recycled from the engine before it, as in a service that runs job after job
     engw = cases.apply(cp, new_engine()); engw.setup(); engw.run(3); engw.download("x", out=xo); engw.close()
     torch.cuda.synchronize()
     if dist: dist.barrier()
@@ -322,16 +399,65 @@ def own_arm(args):
     torch.cuda.synchronize()
     t3 = time.perf_counter()
     t_e2e = allmax(t3 - t0)
-    h2d = allsum(sum(int(cp[k].nbytes) for k in ("tag", "type", "mask", "x", "v", "omega", "radius", "density")))  # every rank receives the whole set and keeps its brick
-    d2h = allsum(xo.nbytes + vo.nbytes + 2 * len(xo) * 4)
+    h2d = allsum(sum(int(cp[k].nbytes) for k in ("tag", "type", "mask", "x", "v", "omega", "radius", "density")))
+    d2h = allsum(xo.nbytes + vo.nbytes)
     e2e = {"value": n * ke / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / ke, "d2h_bytes_per_step": d2h / ke,
-           "job": "create + upload(page-locked host arrays) + setup + run(%d) + download x,v; %.3f s (create+upload %.3f, setup %.3f, run+download %.3f on rank 0)"
-                  % (ke, t_e2e, t1 - t0, t2 - t1, t3 - t2)}
+           "job": "create + upload(page-locked host arrays%s) + setup + run(%d) + download x,v; %.3f s (create+upload %.3f, setup %.3f, run+download %.3f on rank 0); warm process (see bench.py)"
+                  % ("" if world == 1 else ", every rank its own brick", ke, t_e2e, t1 - t0, t2 - t1, t3 - t2)}
+    tags_mine = eng2.download("tag")
     eng2.close()
+
+    # ---- parity inside the bench (all N): the e2e job's result against the UNMODIFIED reference stepping ONE periodic
+    # tile of the bed for the same K steps from the same initial state (the bed is tiles x tiles replicas of that tile, so
+    # every replica on every rank must reproduce it), plus the conservation of the particle set across ranks.  The
+    # reference here is the checker, not the thing measured.
+    parity = {"checked": False}
+    try:
+        ref = None
+        if rank == 0 and ke <= 5000:
+            import ref_driver
+            if ref_driver.available():
+                out = tempfile.mktemp(suffix=".npz")
+                subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-state", str(ke), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+                if os.path.exists(out):
+                    z = np.load(out); ref = np.concatenate([z["x"], z["v"]], axis=1); os.unlink(out)
+        n0 = n // (tiles * tiles)
+        if world > 1:
+            flag = torch.tensor([1 if ref is not None else 0], device="cuda"); dist.broadcast(flag, 0)
+            have_ref = bool(flag.item())
+            rt = torch.zeros((n0, 6), dtype=torch.float64, device="cuda")
+            if have_ref:
+                if rank == 0: rt.copy_(torch.from_numpy(ref))
+                dist.broadcast(rt, 0); ref = rt.cpu().numpy()
+        else:
+            have_ref = ref is not None
+        tile0 = load_tile()
+        Lx, Ly = tile0["hi"][0] - tile0["lo"][0], tile0["hi"][1] - tile0["lo"][1]
+        t_idx = (tags_mine.astype(np.int64) - 1) // n0; k_idx = (tags_mine.astype(np.int64) - 1) % n0
+        ntot = allsum(float(len(tags_mine))); tagsum = allsum(float(tags_mine.astype(np.float64).sum()))
+        conserved = (int(ntot) == n) and (tagsum == n * (n + 1) / 2.0)
+        if have_ref:
+            off = np.stack([(t_idx // tiles) * Lx, (t_idx % tiles) * Ly, np.zeros(len(t_idx))], axis=1)
+            dx = xo - off - ref[k_idx, 0:3]
+            dx[:, 0] -= Lx * np.round(dx[:, 0] / Lx); dx[:, 1] -= Ly * np.round(dx[:, 1] / Ly)
+            rmin = float(tile0["radius"].min())
+            ex = allmax(float(np.abs(dx).max()) / rmin if len(dx) else 0.0)
+            vscale = float(np.sqrt(9.81 * tile0["radius"].mean()))
+            ev = allmax(float(np.abs(vo - ref[k_idx, 3:6]).max()) / vscale if len(dx) else 0.0)
+            # rounding-level differences (summation order, FMA contraction, the replica offsets' own rounding) grow with the
+            # step count -- DEM trajectories are chaotic: 1e-9 of a radius / of sqrt(g r) for the first steps, looser later
+            tol = 1e-9 if ke <= 50 else (1e-6 if ke <= 400 else 1e-4)
+            parity = {"checked": True, "ok": bool(conserved and ex <= tol and ev <= tol), "particles_conserved": bool(conserved),
+                      "max_dx_over_rmin": ex, "max_dv_over_sqrt_g_r": ev, "tol": tol, "steps": ke, "replicas_checked": tiles * tiles,
+                      "against": "unmodified reference (oracle/_ref) stepping one periodic tile of the bed"}
+        else:
+            parity = {"checked": False, "particles_conserved": bool(conserved), "why": "oracle/_ref not available on this box or steps > 5000"}
+    except Exception as ex_:  # the bench line must survive a failing checker
+        parity = {"checked": False, "error": repr(ex_)[:200]}
 
     # CPU baseline: the unmodified reference, 1 core, one tile of the same bed
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu and world == 1:
         import ref_driver
         if ref_driver.available():
             steps_cpu = 1500
@@ -339,15 +465,18 @@ def own_arm(args):
             if r:
                 cpu = {"value": r[0], "unit": "particle-steps/s", "cores": 1, "kind": "reference",
                        "sample": "one 16,384-sphere tile of the bed x %d steps, serial reference build (oracle/_ref)" % steps_cpu}
+    clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler disabled"]}
     out = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": "%d-sphere settled polydisperse bed (%dx%d replicas of bench_data/tile16k, radii U[1.5,3] mm), "
                                   "hertz/history/cdt, floor + periodic xy, dt 1e-5, skin 1 mm" % (n, tiles, tiles),
                       "particles": n, "l2_policy": "inputs (%.1f GB of state + lists) exceed the 126 MB L2" % (n * 600 / 1e9),
-                      "rebuilds_in_timed_region": int(nbuilds), "resetup_ms": round(rebuild_ms, 3),
-                      "parallelism": "1 GPU" if world == 1 else "%d GPUs: x-slab bricks, NCCL halo per step (roofline fields are rank 0's)" % world},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                      "rebuilds_in_timed_region": int(nbuilds), "rebuild_ms": round(rebuild_ms, 3),
+                      "rebuild_ms_how": "same window with %d forced rebuilds (neigh_modify every %d check no) minus the rebuild-free window" % (nb_forced, R),
+                      "parallelism": "1 GPU" if world == 1 else "%d GPUs: x-slab bricks, peer-memory halo per step (roofline fields are rank 0's)" % world},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "parity": parity, "falling": falling, "amortised": amortised}
     if rank == 0:
         print(json.dumps(out))
     if dist:
@@ -357,6 +486,8 @@ def own_arm(args):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--ref-worker":
         ref_worker(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]); return
+    if len(sys.argv) > 1 and sys.argv[1] == "--ref-state":
+        ref_state_worker(int(sys.argv[2]), sys.argv[3]); return
     if len(sys.argv) > 1 and sys.argv[1] == "--ref-server":
         ref_server(int(sys.argv[2])); return
     ap = argparse.ArgumentParser()
@@ -366,6 +497,8 @@ def main():
     ap.add_argument("--impl", default="own")
     ap.add_argument("--tiles", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-falling", action="store_true")
+    ap.add_argument("--falling-steps", type=int, default=2000)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

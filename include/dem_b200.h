@@ -33,7 +33,10 @@ enum dem_status {
 /* ---- life cycle ---------------------------------------------------------------------
  * replaces: lammps_open_no_mpi / lammps_close           src/library.h:60-61
  * device   CUDA ordinal; rank/nranks = position in the spatial brick of GPUs;
- * nccl_id  128-byte ncclUniqueId shared by all ranks (NULL when nranks == 1);
+ * nccl_id  128-byte ncclUniqueId shared by all ranks (NULL when nranks == 1).  With nranks > 1 a NULL id asks,
+ *          explicitly, for the communicator that an earlier engine of this process with the same (device, rank,
+ *          nranks) released in good standing -- every rank of the job must make the same choice; a non-NULL id
+ *          always builds a fresh communicator for exactly the ranks that share the id;
  * stream   cudaStream_t to launch on (NULL = legacy default stream).                  */
 int dem_create(dem_engine **out, int device, int rank, int nranks, const void *nccl_id, void *stream);
 void dem_destroy(dem_engine *e);

@@ -123,8 +123,9 @@ struct Formula {
   {
     ws();
     if (*p == '(') { p++; const double v = expr(); ws(); if (*p != ')') return fail("Invalid syntax in variable formula"); p++; return v; }
-    if (*p == '-') { p++; return -power(); }
-    if (*p == '+') { p++; return power(); }
+    // Variable::evaluate precedence (variable.cpp:133-141): UNARY (8) binds tighter than CARAT (7), so -2^2 == 4
+    if (*p == '-') { p++; return -atom(); }
+    if (*p == '+') { p++; return atom(); }
     if (isdigit((unsigned char)*p) || *p == '.') { char *e; const double v = strtod(p, &e); p = e; return v; }
     if (isalpha((unsigned char)*p) || *p == '_') {
       std::string id; while (isalnum((unsigned char)*p) || *p == '_') id += *p++;
@@ -152,7 +153,8 @@ struct Formula {
     }
     return fail("Invalid syntax in variable formula");
   }
-  double power() { const double b = atom(); ws(); if (*p == '^') { p++; const double e = power(); return std::pow(b, e); } return b; }
+  // '^' pops on >= precedence in the reference, i.e. it is LEFT-associative: 2^3^2 == 64
+  double power() { double b = atom(); for (;;) { ws(); if (*p == '^') { p++; const double e = atom(); b = std::pow(b, e); } else return b; } }
   double term()
   {
     double v = power();

@@ -60,7 +60,7 @@ static void dem_fail(dem_engine *e, int code, const char *fmt, ...);
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t err__ = (call);                                                                    \
-    if (err__ != cudaSuccess) dem_fail(E, DEM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    if (err__ != cudaSuccess) { if (E) E->comm_bad = 1; dem_fail(E, DEM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); } \
   } while (0)
 
 // Device memory comes from a process-wide cache of whole cudaMalloc blocks (per device, best fit within 25 %): engines
@@ -180,6 +180,7 @@ struct dem_engine {
   int pgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0}, user_grid = 0;
   double sublo[3] = {0, 0, 0}, subhi[3] = {1, 1, 1};
   ncclComm_t comm = nullptr;
+  int comm_bad = 0;  // an NCCL call failed or a halo wait timed out: the communicator is not handed to a later engine
   // ghost swaps, LAMMPS order: for dim 0..2: (send to lo neighbour, send to hi neighbour)
   struct Swap {
     int dim = 0, side = 0, peer = -1, self = 0, nsend = 0, nrecv = 0, gfirst = 0; double shift = 0.0; DevBuf<int> list;
@@ -228,6 +229,7 @@ struct dem_engine {
   const int *gate = nullptr; int gate_mask = 0;  // gate of the step being launched (nullptr: not speculative)
   // state
   int uploaded = 0, setup_done = 0, forces_valid = 0;
+  int dirty = 0;  // a deck setting (box, neighbor, property, timestep-independent tables) changed after the first setup: re-derive
   long ntimestep = 0, nbuilds = 0, launches = 0;
   int ago = 0;
   // timing of the step kernel
@@ -259,7 +261,7 @@ void DevBuf<T>::ensure(dem_engine *E, size_t m, size_t keep, cudaStream_t st)
 #define NK(call)                                                                                   \
   do {                                                                                             \
     ncclResult_t r__ = (call);                                                                     \
-    if (r__ != ncclSuccess) dem_fail(E, DEM_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+    if (r__ != ncclSuccess) { E->comm_bad = 1; dem_fail(E, DEM_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); } \
   } while (0)
 #define GRID(n, b) (unsigned)(((n) + (b)-1) / (b))
 #define API_BEGIN  if (!e) return DEM_ERR_ARG; dem_engine *E = e; (void)E; try {
@@ -289,17 +291,23 @@ extern "C" int dem_create(dem_engine **out, int device, int rank, int nranks, co
     e->device = device; e->rank = rank; e->nranks = nranks; e->stream = (cudaStream_t)stream;
     if (nranks < 1 || rank < 0 || rank >= nranks) dem_fail(e, DEM_ERR_ARG, "bad rank/nranks %d/%d", rank, nranks);
     if (nranks > 1) {
-      if (!nccl_id) dem_fail(e, DEM_ERR_ARG, "nranks > 1 needs the shared 128-byte ncclUniqueId (dem_nccl_unique_id on rank 0)");
       if (!g_nccl.load()) dem_fail(e, DEM_ERR_CUDA, "could not load libnccl.so.2");
-      ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
-      // a communicator released by an earlier engine of this process with the same (device, rank, nranks) is taken over:
-      // ncclCommInitRank over 8 GPUs costs seconds, and every rank of an SPMD job creates its engines in the same order
+      // Communicator reuse is explicit: nccl_id == NULL asks for the communicator an earlier engine of this process with the
+      // same (device, rank, nranks) released in good standing (ncclCommInitRank over 8 GPUs costs seconds; an SPMD job that
+      // creates its engines in the same order on every rank may reuse it).  A non-NULL id always builds a fresh communicator
+      // for exactly the peer group that shares the id, and retires a cached one.
       {
         std::lock_guard<std::mutex> lk(g_mem_mu);
         for (auto it = g_comm_cache.begin(); it != g_comm_cache.end(); ++it)
           if (it->device == device && it->rank == rank && it->nranks == nranks) { e->comm = it->comm; g_comm_cache.erase(it); break; }
       }
-      if (!e->comm) NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+      if (!nccl_id) {
+        if (!e->comm) dem_fail(e, DEM_ERR_ARG, "nranks > 1 needs the shared 128-byte ncclUniqueId (dem_nccl_unique_id on rank 0); NULL only reuses a communicator released by an earlier engine of this process");
+      } else {
+        if (e->comm) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
+        ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
+        NK(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+      }
     }
     e->hcnt = (int *)host_small_alloc(); e->hflag = (int *)host_small_alloc();
     if (!e->hcnt || !e->hflag) dem_fail(e, DEM_ERR_CUDA, "cudaHostAlloc failed");
@@ -341,7 +349,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->hsig.release();
   if (e->hcnt) host_small_free(e->hcnt);
   if (e->comm) {
-    if (getenv("DEM_B200_NO_COMM_CACHE")) g_nccl.CommDestroy(e->comm);
+    if (e->comm_bad || getenv("DEM_B200_NO_COMM_CACHE")) g_nccl.CommDestroy(e->comm);
     else { std::lock_guard<std::mutex> lk(g_mem_mu); g_comm_cache.push_back({e->device, e->rank, e->nranks, e->comm}); }
   }
   delete e;
@@ -370,6 +378,7 @@ extern "C" int dem_set_box(dem_engine *e, const double lo[3], const double hi[3]
     if (!(hi[d] > lo[d])) dem_fail(e, DEM_ERR_ARG, "box hi <= lo in dim %d", d);
     e->lo[d] = lo[d]; e->hi[d] = hi[d]; e->prd[d] = hi[d] - lo[d]; e->periodic[d] = periodic[d] ? 1 : 0;
   }
+  e->dirty = 1;
   API_END
 }
 extern "C" int dem_set_ntypes(dem_engine *e, int n)
@@ -390,6 +399,7 @@ extern "C" int dem_set_neighbor(dem_engine *e, double skin, int every, int delay
 {
   API_BEGIN
   if (skin < 0 || every < 1 || delay < 0) dem_fail(e, DEM_ERR_ARG, "bad neighbor settings");
+  if (skin != e->skin) e->dirty = 1;  // cell grid, cutneighmax, border slabs and the mesh grid depend on the skin
   e->skin = skin; e->every = every; e->delay = delay; e->check = check;
   API_END
 }
@@ -445,6 +455,7 @@ extern "C" int dem_set_property(dem_engine *e, const char *name, const char *kin
     }
   } else dem_fail(e, DEM_ERR_ARG, "unknown property kind %s", kind);
   e->have_prop[nm] = 1;
+  e->dirty = 1;  // the material tables are re-derived by the next dem_setup
   API_END
 }
 
@@ -746,7 +757,7 @@ static void mesh_grid(dem_engine *E)
 {
   if (E->grid_ready && !E->any_moving) return;
   cudaStream_t st = E->stream;
-  if (E->grid_ready && E->any_moving) {
+  if ((E->grid_ready || E->setup_done) && E->any_moving) {  // (setup_done: the grid was invalidated by a changed skin)
     CK(cudaMemcpyAsync(E->htri.data(), E->dtri.p, E->htri.size() * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     // moving meshes: edge vectors / normals / obtuse index are recomputed from the nodes at every rebuild, as the
@@ -941,7 +952,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
 {
   API_BEGIN
   if (n < 0 || (n > 0 && (!tag || !type || !x || !radius || !density))) dem_fail(e, DEM_ERR_ARG, "missing particle arrays");
-  if (n >= (long)NBR_IDX) dem_fail(e, DEM_ERR_OVERFLOW, "more than 2^30 particles on one GPU");
+  if (n >= (long)NBR_IDX) dem_fail(e, DEM_ERR_OVERFLOW, "more than 2^25 particles on one GPU (neighbour words index owned + ghost particles in 25 bits)");
   CK(cudaSetDevice(e->device));
   e->cap = 0;  // force fresh allocation
   for (int b = 0; b < 2; b++) { e->xr[b].release(); e->vm[b].release(); e->wt[b].release(); }
@@ -964,8 +975,9 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     CK(cudaMemcpyAsync(dt, type, nd * sizeof(int), cudaMemcpyHostToDevice, st));
     if (mask) CK(cudaMemcpyAsync(dm, mask, nd * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dg, tag, nd * sizeof(int), cudaMemcpyHostToDevice, st));
-    e->counters.ensure(e, 2);
+    e->counters.ensure(e, 4);
     CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(e->counters.p + 2, 0xFF, sizeof(unsigned long long), st));  // running minimum of the radius bits
     const MineP B = brick_params(e);
     e->flo.ensure(e, nd + 1); e->slo.ensure(e, nd + 1);
     ensure_cub(e, nd);
@@ -982,7 +994,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
       e->launches++;
     }
     CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), st));
-    unsigned long long hc[2];
+    unsigned long long hc[3];
     CK(cudaMemcpyAsync(hc, e->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     list.release();
@@ -991,7 +1003,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     if (errbits & 2) dem_fail(e, DEM_ERR_ARG, "Invalid radius or density in particle data");
     if (errbits & 4) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
     double rmaxd; memcpy(&rmaxd, &hc[0], 8);
-    { double rm = 1e300; for (long i = 0; i < n; i++) rm = std::min(rm, radius[i]); e->rmin = rm; }
+    { double rm; memcpy(&rm, &hc[2], 8); e->rmin = rm; }  // (minimum over the uploaded set, found on the device)
     e->nlocal = nmine; e->nghost = 0; e->rmax = rmaxd;
     e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0; e->mesh_ready = 0;
     e->ls[0].valid = e->ls[1].valid = 0;
@@ -1016,8 +1028,9 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     CK(cudaMemcpyAsync(dt, type, nd * sizeof(int), cudaMemcpyHostToDevice, st));
     if (mask) CK(cudaMemcpyAsync(dm, mask, nd * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dg, tag, nd * sizeof(int), cudaMemcpyHostToDevice, st));
-    e->counters.ensure(e, 2);
+    e->counters.ensure(e, 4);
     CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(e->counters.p + 2, 0xFF, sizeof(unsigned long long), st));  // running minimum of the radius bits
     e->cur = 0;
     k_pack_upload<<<GRID(n, 256), 256, 0, st>>>((int)n, dx, v ? dv : nullptr, omega ? dw : nullptr, dr, dd, dt, mask ? dm : nullptr, dg, e->ntypes,
                                                  e->xr[0].p, e->vm[0].p, e->wt[0].p, (int *)(e->counters.p + 1), e->counters.p);
@@ -1025,7 +1038,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     CK(cudaMemcpyAsync(e->tag.p, dg, nd * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(e->density.p, dd, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), st));
-    unsigned long long hc[2];
+    unsigned long long hc[3];
     CK(cudaMemcpyAsync(hc, e->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int errbits = (int)(hc[1] & 0xffffffffu);
@@ -1033,7 +1046,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     if (errbits & 2) dem_fail(e, DEM_ERR_ARG, "Invalid radius or density in particle data");
     if (errbits & 4) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
     double rmaxd; memcpy(&rmaxd, &hc[0], 8);
-    { double rm = 1e300; for (long i = 0; i < n; i++) rm = std::min(rm, radius[i]); e->rmin = rm; }
+    { double rm; memcpy(&rm, &hc[2], 8); e->rmin = rm; }  // (minimum over the uploaded set, found on the device)
     e->nlocal = n; e->nghost = 0; e->rmax = rmaxd;
     e->uploaded = 1; e->setup_done = 0; e->forces_valid = 0; e->order_valid = 0; e->mesh_ready = 0;
     e->ls[0].valid = e->ls[1].valid = 0;
@@ -1569,6 +1582,8 @@ static void rebuild(dem_engine *E)
     // records of this dimension's new ghosts (the next dimension's flags look at them)
     do_swap(E, &E->swaps[E->nswap - 2], 2);
   }
+  if (E->nlocal + E->nghost >= (long)NBR_IDX)
+    dem_fail(E, DEM_ERR_OVERFLOW, "%ld owned + %ld ghost particles exceed the 2^25 indices of a neighbour word", E->nlocal, E->nghost);
   tr.mark("cell ranges + borders");
   // 4. cell order of the ghosts (storage keeps the swap order so that NCCL can receive in place)
   if (E->nghost) {
@@ -1777,11 +1792,29 @@ extern "C" int dem_setup(dem_engine *e)
   if (!(e->dt > 0)) dem_fail(e, DEM_ERR_STATE, "timestep not set");
   if (!e->have_pair && e->walls.empty() && e->mwalls.empty()) dem_fail(e, DEM_ERR_STATE, "no pair_style and no wall defined");
   CK(cudaSetDevice(e->device));
-  if (!e->setup_done) {
+  if (!e->setup_done || e->dirty) {
+    // (also after the first run: `neighbor`, `fix property/global` or the box changed between two runs -- tables, cutoff, cell
+    // grid and the triangle grid are derived again; lists are rebuilt below anyway)
+    const bool first = !e->setup_done;
+    if (e->nranks > 1) {
+      // every rank may have been handed only its own share of the particles (or none at all): the neighbour cutoff and the
+      // bond models' contact-distance factor need the GLOBAL extreme radii (the reference: MPI_Allreduce in
+      // pair_gran.cpp:591-603 / neighbor.cpp)
+      e->cnt_dev.ensure(e, 64);
+      double h[2] = {e->rmax, e->rmin > 0.0 ? -e->rmin : -1e300};
+      double *d = (double *)(e->cnt_dev.p + 16);
+      CK(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
+      NK(g_nccl.AllReduce(d, d + 2, 2, ncclDouble, ncclMax, e->comm, e->stream));
+      CK(cudaMemcpyAsync(h, d + 2, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      e->rmax = h[0]; e->rmin = -h[1];
+    }
     derive_tables(e);
     setup_grid(e);
+    if (!first) e->grid_ready = 0;
     mesh_prepare(e);
-    if (e->nwrows) {
+    e->dirty = 0;
+    if (first && e->nwrows) {
       e->whist.release(); e->whist.ensure(e, (size_t)e->nwrows * e->cap);
       CK(cudaMemsetAsync(e->whist.p, 0, (size_t)e->nwrows * e->cap * sizeof(double), e->stream));
       e->whist_tmp.release(); e->whist_tmp.ensure(e, (size_t)e->nwrows * e->cap);
@@ -1857,6 +1890,9 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
       } else e->ago = ago1;
     }
     if (rebuild_now) {
+      // (forced rebuild, `check no`: the previous step's flags were not looked at above -- its history-slot overflow must
+      // not be wiped by clear_flags)
+      if (e->fev[prev]) { CK(cudaEventSynchronize(e->fev[prev])); overflow_seen |= e->hflag[4 * prev + 1]; }
       e->gate = nullptr; e->gate_mask = 0;
       if (moving) {  // the mesh moves before the lists are rebuilt
         MeshP M = mesh_params(e);
@@ -1883,7 +1919,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   if (e->nranks > 1 && e->p2p_ok) {
     int to = 0;
     CK(cudaMemcpy(&to, e->hsig.p + 15, sizeof(int), cudaMemcpyDeviceToHost));
-    if (to) dem_fail(e, DEM_ERR_CUDA, "halo exchange timed out waiting for a neighbour rank");
+    if (to) { e->comm_bad = 1; dem_fail(e, DEM_ERR_CUDA, "halo exchange timed out waiting for a neighbour rank"); }
   }
   if (overflow_seen || e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;

@@ -1058,20 +1058,25 @@ __global__ void __launch_bounds__(256) k_pack_upload(int n, const double *x, con
                                                      double4 *xr, double4 *vm, double4 *wt, int *err, unsigned long long *rmax_bits)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double r = radius[i], rho = density[i];
-  const int t = type[i];
-  if (t < 1 || t > ntypes) atomicOr(err, 1);
-  if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
-  if (tag[i] <= 0) atomicOr(err, 4);
-  const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;
-  xr[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
-  vm[i] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
-  wt[i] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0.,
-                       __longlong_as_double(pack_bits(t, mask ? mask[i] : 1)));
-  unsigned long long b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0);
-  for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b; }
-  if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, b);  // positive doubles order like their bit patterns
+  unsigned long long b = 0ull, bm = ~0ull;  // running maximum / minimum of the radius bit patterns (rmax_bits[0] / rmax_bits[2])
+  if (i < n) {
+    const double r = radius[i], rho = density[i];
+    const int t = type[i];
+    if (t < 1 || t > ntypes) atomicOr(err, 1);
+    if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
+    if (tag[i] <= 0) atomicOr(err, 4);
+    const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;
+    xr[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
+    vm[i] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
+    wt[i] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0.,
+                         __longlong_as_double(pack_bits(t, mask ? mask[i] : 1)));
+    b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0); bm = b;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b;
+    const unsigned long long om = __shfl_down_sync(0xffffffffu, bm, o); bm = om < bm ? om : bm;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(rmax_bits, b); atomicMin(rmax_bits + 2, bm); }  // positive doubles order like their bit patterns
 }
 // multi-rank upload: every rank receives the whole particle set and keeps its brick.  Ownership test on the wrapped
 // position (Domain::pbc + sub-box, like read_data.cpp / atom.cpp data_atoms); validity checks and the global maximum
@@ -1093,7 +1098,7 @@ __global__ void __launch_bounds__(256) k_flag_mine(int n, const double *x, const
                                                    int ntypes, const MineP B, int *flag, int *err, unsigned long long *rmax_bits)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long b = 0ull;
+  unsigned long long b = 0ull, bm = ~0ull;
   if (i < n) {
     const double r = radius[i], rho = density[i];
     const int t = type[i];
@@ -1101,10 +1106,13 @@ __global__ void __launch_bounds__(256) k_flag_mine(int n, const double *x, const
     if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
     if (tag[i] <= 0) atomicOr(err, 4);
     flag[i] = brick_owns(B, x + 3 * (size_t)i) ? 1 : 0;
-    b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0);
+    b = (unsigned long long)__double_as_longlong(r > 0.0 ? r : 0.0); bm = b;
   }
-  for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b; }
-  if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, b);
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long ob = __shfl_down_sync(0xffffffffu, b, o); b = ob > b ? ob : b;
+    const unsigned long long om = __shfl_down_sync(0xffffffffu, bm, o); bm = om < bm ? om : bm;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(rmax_bits, b); atomicMin(rmax_bits + 2, bm); }
 }
 // records of the selected particles (ascending original index, like the host loop it replaces)
 __global__ void __launch_bounds__(256) k_pack_upload_sel(int nsel, const int *list, const double *x, const double *v, const double *omega, const double *radius,

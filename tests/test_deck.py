@@ -201,7 +201,7 @@ def test_deck_variable_formulas(tmp_path):
     text = open(path).read()
     text = text.replace("variable dt equal", "variable dt_unused equal").replace("timestep ${dt}", "")
     text += "\n".join(["variable d equal 2", "variable half equal 0.5*${d}", "variable vz1 equal vz[1]", "variable top_Fz equal f_mesh_top[3]",
-                       "variable tc equal time", "variable dt equal ${half}*1e-5*(v_d^2-3)+sqrt(16)*0-abs(-0)",
+                       "variable tc equal time", "variable dt equal ${half}*1e-5*(v_d^2-3)+sqrt(16)*0-abs(-0)+(2^3^2-64)+(-2^2-4)",  # ^ is left-associative and binds less than unary minus (variable.cpp:133-141)
                        "timestep ${dt}", "run 10"]) + "\n"
     open(path, "w").write(text)
     eng, deck = oracle_deck()

@@ -173,6 +173,56 @@ def test_half_list_alternative_agrees_with_the_default():
     assert (np.abs(out[0]["f"] - out[1]["f"]) / w).max() < 1e-8
 
 
+def test_settings_changed_between_runs_match_oracle():
+    """`neighbor` and `fix property/global` between two runs (the deck front end forwards them and calls setup again): the
+    material tables, the neighbour cutoff and the cell grid are derived again -- a doubled skin must not lose pairs beyond
+    the old cells, a changed friction coefficient must reach the contact law"""
+    c = cases.case_box(n3=(9, 9, 9), poly=True, name="resetup", seed=21)
+    rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
+    got = cases.apply(c, gpu_engine())
+    ref = cases.apply(c, parity.oracle_engine())
+    for eng in (got, ref):
+        eng.setup(); eng.run(100)
+    parity.compare_snapshot(cases.snapshot(got, c), cases.snapshot(ref, c), rmass, tol=1e-6, label="resetup@100")
+    for eng in (got, ref):
+        eng.neighbor(3.0 * c["skin"], every=1, delay=0, check=True)
+        eng.property_global("coefficientFriction", "peratomtypepair", [0.15])
+        eng.setup()
+    s0g, s0r = cases.snapshot(got, c), cases.snapshot(ref, c)
+    assert len(s0g["pair_lo"]) == len(s0r["pair_lo"]) and np.array_equal(s0g["pair_lo"], s0r["pair_lo"]) and np.array_equal(s0g["pair_hi"], s0r["pair_hi"])
+    for eng in (got, ref):
+        eng.run(300)
+    parity.compare_snapshot(cases.snapshot(got, c), cases.snapshot(ref, c), rmass, tol=1e-6, label="resetup@400")
+    assert got.stats().nbuilds == ref.stats().nbuilds
+    got.close(); ref.close()
+
+
+def test_history_overflow_is_reported_under_check_no():
+    """forced rebuilds (`neigh_modify every 1 check no`) must not swallow the history-slot overflow of the step before the
+    rebuild: 40 small spheres just off the surface of a big one fly inwards, all 40 contacts form within a step or two --
+    more than the 16 history rows sized at the (contact-free) build -- and dem_run has to say so although every following
+    step starts with a rebuild that clears the step flags"""
+    import dem_b200
+    c = cases.case_box(n3=(4, 4, 3), name="ovf", seed=13)
+    rs, R, nshell = 0.0025, 0.0075, 40
+    L = c["hi"][0]
+    ctr = np.array([0.5 * L, 0.5 * L, 0.03])
+    k = np.arange(nshell) + 0.5
+    phi = np.arccos(1.0 - 2.0 * k / nshell); th = np.pi * (1.0 + 5.0 ** 0.5) * k
+    u = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
+    n = nshell + 1
+    c.update(tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32), mask=np.ones(n, np.int32),
+             x=np.vstack([ctr, ctr + (R + rs) * 1.002 * u]), v=np.vstack([np.zeros(3), -0.5 * u]), omega=np.zeros((n, 3)),
+             radius=np.concatenate([[R], np.full(nshell, rs)]), density=np.full(n, c["density"][0]))
+    c["hi"][2] = max(c["hi"][2], 0.06)
+    c["neigh"] = (1, 0, False)
+    e = cases.apply(c, gpu_engine())
+    e.setup()
+    with pytest.raises(dem_b200.DemError, match="history"):
+        e.run(20)
+    e.close()
+
+
 def test_engine_is_deterministic():
     c = cases.case_box(n3=(8, 8, 8), poly=True, name="det", seed=3)
     snaps = []
