@@ -260,7 +260,16 @@ def own_arm(args):
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("DEM_BENCH_NO_SAMPLER")) else None
     have_comm = [False]
 
+    def with_opts(e):  # developer aid: DEM_OPTS="chunk=65536,wave_skew=8" sets engine options on every engine of the run
+        for kv in os.environ.get("DEM_OPTS", "").split(","):
+            if "=" in kv:
+                e.option(kv.split("=")[0].strip(), float(kv.split("=")[1]))
+        return e
+
     def new_engine():
+        return with_opts(new_engine_())
+
+    def new_engine_():
         if world == 1:
             return dem_b200.Engine(device=local)
         if have_comm[0]:  # explicit reuse of the communicator the previous engine of this process released (dem_b200.h: dem_create)

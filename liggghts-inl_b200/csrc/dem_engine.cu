@@ -19,7 +19,7 @@
 #include <nccl.h>
 
 #include "../../include/dem_b200.h"
-#include "dem_kernels.cuh"
+#include "dem_pairs.cuh"
 #include "dem_mesh_host.h"
 
 using namespace dem;
@@ -138,6 +138,8 @@ struct ListSet {  // one ELLPACK neighbour list + history (two sets ping-pong ac
   DevBuf<int> ptag, numneigh;
   DevBuf<double4> hist;
   int cap = 0, maxk = 0, dnum = 0, hslots = 0, valid = 0;  // dnum = 32-byte history records per contact
+  int fmt = 0;        // 0: full list, both owners hold the history (bond decks, k_step_bond); 1: owner list (dem_pairs.cuh)
+  int nlocal = 0;     // owned particles when the list was built (decides who owned a pair of the OLD list)
 };
 
 struct WallHost { std::string id; WallP p; };
@@ -204,6 +206,11 @@ struct dem_engine {
   DevBuf<char> cubtmp;
   ListSet ls[2];
   int lcur = 0;
+  DevBuf<double4> res;  // owner list: ring of per-contact result records
+  DevBuf<double> part;  // owner list: ring of per-particle partial sums
+  DevBuf<int> wtab;     // wavefront: chunk_start[260] | grp[520] | grp_start[524] | meta[8] | counters[8 + 512]
+  int wave_skew = 1, wave_ring = 1, wave_ccap = 0, wave_nitems = 0, wave_ngrp = 0, num_sms = 0;
+  long serial = 0;      // step launches so far (stamps the result records)
   DevBuf<int> overflow;
   DevBuf<double> fa, ta;  // accumulation arrays of the half-list alternative (option "half_list")
   DevBuf<unsigned long long> counters;
@@ -337,7 +344,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
-  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release();
+  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release(); e->res.release(); e->part.release(); e->wtab.release();
   e->dmforce.release(); e->dmpref.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
@@ -1193,8 +1200,25 @@ static void setup_grid(dem_engine *E)
     if (E->pgrid[d] > 1 && E->subhi[d] - E->sublo[d] < 2.0 * E->cutneighmax)
       dem_fail(E, DEM_ERR_UNSUPPORTED, "sub-box of a rank in dim %d is thinner than two neighbour cutoffs", d);
   }
-  E->grid.morton = (E->grid.nc[0] <= 1024 && E->grid.nc[1] <= 1024 && E->grid.nc[2] <= 1024) ? 1 : 0;
-  if (E->opt.count("morton") && E->opt["morton"] == 0) E->grid.morton = 0;
+  {  // storage order: slabs along the longest dimension of the sub-box (the chunks of the step wavefront, dem_pairs.cuh),
+     // Morton inside a slab.  A slab is a whole number of cell layers, i.e. at least one neighbour cutoff thick.
+    GridP &G = E->grid;
+    G.sdim = 0;
+    for (int d = 1; d < 3; d++) if (G.nc[d] > G.nc[G.sdim]) G.sdim = d;
+    const bool wave = !(E->opt.count("wave") && E->opt["wave"] == 0);
+    const long per_chunk = E->opt.count("chunk") ? (long)E->opt["chunk"] : 32768;
+    long want = wave ? std::max<long>(1, std::min<long>(250, E->nlocal / std::max<long>(per_chunk, 128))) : 1;
+    G.cps = std::max(1, (int)((G.nc[G.sdim] + want - 1) / want));
+    G.nslab = (G.nc[G.sdim] + G.cps - 1) / G.cps;
+    while (G.nslab > 250) { G.cps++; G.nslab = (G.nc[G.sdim] + G.cps - 1) / G.cps; }
+    const int d1 = (G.sdim + 1) % 3, d2 = (G.sdim + 2) % 3;
+    const int mx = std::max(G.cps, std::max(G.nc[d1], G.nc[d2]));
+    int b = 1; while ((1 << b) < mx) b++;
+    int sb = 0; while ((1 << sb) < G.nslab) sb++;
+    G.mbits = b;
+    G.morton = (b <= 10 && sb + 3 * b <= 32) ? 1 : 0;
+    if (E->opt.count("morton") && E->opt["morton"] == 0) G.morton = 0;
+  }
   E->ncells = total;
   E->ocs.ensure(E, total); E->oce.ensure(E, total); E->gcs.ensure(E, total); E->gce.ensure(E, total);
 }
@@ -1424,7 +1448,8 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
       int H = 0;
       if (hist && nsend[side]) {
         CK(cudaMemsetAsync(E->overflow.p, 0, sizeof(int), st));
-        k_max_nh<<<GRID(nsend[side], 256), 256, 0, st>>>(nsend[side], lists[side].p, Lold.numneigh.p, E->overflow.p);
+        if (Lold.fmt) k_max_nh2<<<GRID(nsend[side], 256), 256, 0, st>>>(nsend[side], lists[side].p, Lold.numneigh.p, Lold.nbr.p, Lold.cap, Lold.maxk, E->overflow.p);
+        else k_max_nh<<<GRID(nsend[side], 256), 256, 0, st>>>(nsend[side], lists[side].p, Lold.numneigh.p, E->overflow.p);
         CK(cudaMemcpyAsync(&E->hcnt[62], E->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         H = E->hcnt[62];
@@ -1447,7 +1472,8 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
         M.n = nsend[side]; M.stride = ss; M.hmax = H; M.list = lists[side].p; M.buf = E->migs.p;
         M.xr = E->xr[c].p; M.vm = E->vm[c].p; M.wt = E->wt[c].p; M.xh = E->xh.p; M.tag = E->tag.p;
         if (meshrows) { M.mint = E->mint[E->mcur].p; M.mhist = E->mhist[E->mcur].p; }
-        k_mig_pack<<<GRID(M.n, 128), 128, 0, st>>>(M);
+        if (hist && Lold.fmt) k_mig_pack2<<<GRID(M.n, 128), 128, 0, st>>>(M, Lold.nlocal);
+        else k_mig_pack<<<GRID(M.n, 128), 128, 0, st>>>(M);
         E->launches++;
       }
       if (nrecv) {
@@ -1467,7 +1493,8 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
         M.xr = E->xr[E->cur].p; M.vm = E->vm[E->cur].p; M.wt = E->wt[E->cur].p; M.xh = E->xh.p; M.tag = E->tag.p;
         M.density = E->density.p; M.whist = E->whist.p;
         if (meshrows) { M.mint = E->mint[E->mcur].p; M.mhist = E->mhist[E->mcur].p; }  // (re-strided if the capacity grew)
-        k_mig_unpack<<<GRID(nrecv, 128), 128, 0, st>>>(M, ncur);
+        if (hist && Lold.fmt) k_mig_unpack2<<<GRID(nrecv, 128), 128, 0, st>>>(M, ncur);
+        else k_mig_unpack<<<GRID(nrecv, 128), 128, 0, st>>>(M, ncur);
         E->launches++;
         ncur += nrecv;
       }
@@ -1532,6 +1559,23 @@ static void rebuild(dem_engine *E)
     E->launches += 4;
     E->cur = c ^ 1; c = E->cur;
     did_permute = true;
+  }
+  // chunk table + work queue of the step wavefront (owner list): from the sorted keys
+  E->wtab.ensure(E, 260 + 520 + 524 + 8 + 8 + 512);
+  {
+    int *chunk_start = E->wtab.p, *grp = E->wtab.p + 260, *grp_start = grp + 520, *meta = grp_start + 524, *wctr = meta + 8;
+    CK(cudaMemsetAsync(wctr, 0, (8 + 512) * sizeof(int), st));
+    CK(cudaMemsetAsync(meta, 0, 8 * sizeof(int), st));
+    const GridP &G = E->grid;
+    if (E->num_sms == 0) CK(cudaDeviceGetAttribute(&E->num_sms, cudaDevAttrMultiProcessorCount, E->device));
+    // phase B of a chunk is queued `skew` chunks behind its phase A: far enough for the A blocks to have left the device
+    const double avg_blocks = std::max(1.0, (double)n / 128.0 / G.nslab);
+    int skew = (int)ceil(1.5 * E->num_sms * DEM_P_MINBLOCKS / avg_blocks);
+    skew = std::max(1, std::min(skew, 24));
+    if (E->opt.count("wave_skew")) skew = std::max(1, (int)E->opt["wave_skew"]);
+    E->wave_skew = skew; E->wave_ring = G.nslab == 1 ? 1 : skew + 3;
+    if (n) { k_wave_table<<<1, 256, 0, st>>>(G.nslab, n, E->keys2.p, G, skew, chunk_start, grp, grp_start, meta); E->launches++; }
+    CK(cudaMemcpyAsync(E->hcnt + 48, meta, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   tr.mark("migrate+sort+gather");
   E->nlocal = n;
@@ -1599,21 +1643,28 @@ static void rebuild(dem_engine *E)
   tr.mark("ghost order");
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
+  // plain contact models: owner list (every pair evaluated once, dem_pairs.cuh); bond decks: full list (k_step_bond)
+  const int fmt = ((E->have_pair && E->pm.cohesion) || (E->opt.count("full_list") && E->opt["full_list"] != 0)) ? 0 : 1;  // (full_list: first-generation k_step, kept for A/B measurements)
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
-  int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : 16));
+  int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : (fmt ? 12 : 16)));
   for (int attempt = 0; attempt < 6; attempt++) {
     ensure_list(E, Lnew, E->cap, maxk, dnum, hslots);
+    Lnew.fmt = fmt; Lnew.nlocal = n;
     if (!n) break;
     CK(cudaMemsetAsync(E->overflow.p, 0, 2 * sizeof(int), st));
     BuildP P;
     P.nlocal = n; P.cap = Lnew.cap; P.maxk = Lnew.maxk; P.dnum = dnum; P.hslots = Lnew.hslots; P.xr = E->xr[c].p; P.tag = E->tag.p; P.G = E->grid;
     P.ocs = E->ocs.p; P.oce = E->oce.p; P.gcs = E->gcs.p; P.gce = E->gce.p; P.gorder = E->gorder.p; P.cdf = E->cdf; P.skin = E->skin;
     P.nbr = Lnew.nbr.p; P.numneigh = Lnew.numneigh.p; P.ptag = Lnew.ptag.p; P.hist = Lnew.hist.p;
-    P.have_old = (Lold.valid && dnum && Lold.dnum == dnum) ? 1 : 0; P.cap_old = Lold.cap; P.dnum_old = Lold.dnum;
+    P.have_old = (Lold.valid && dnum && Lold.dnum == dnum && Lold.fmt == fmt) ? 1 : 0; P.cap_old = Lold.cap; P.dnum_old = Lold.dnum;
     P.perm = E->perm.p; P.nbr_old = Lold.nbr.p; P.numneigh_old = Lold.numneigh.p; P.ptag_old = Lold.ptag.p; P.hist_old = Lold.hist.p;
     P.overflow = E->overflow.p;
     P.coh_nbond = (E->have_pair && E->pm.cohesion) ? E->pm.nbond : 0; P.coh_rec = E->pm.rec_bond;
-    k_build_list<<<GRID(n, 128), 128, 0, st>>>(P);
+    if (fmt) {
+      k_build_list2<<<GRID(n, 128), 128, 0, st>>>(P, Lold.nlocal, Lold.maxk);
+      k_link_slots<<<GRID(n, 128), 128, 0, st>>>(n, Lnew.cap, Lnew.maxk, Lnew.nbr.p, Lnew.numneigh.p);
+      E->launches++;
+    } else k_build_list<<<GRID(n, 128), 128, 0, st>>>(P);
     E->launches++;
     int ov[2] = {0, 0};
     CK(cudaMemcpyAsync(ov, E->overflow.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1622,7 +1673,16 @@ static void rebuild(dem_engine *E)
     if (attempt == 5) dem_fail(E, DEM_ERR_OVERFLOW, "neighbour list overflow (%d neighbours, %d history partners)", ov[0], ov[1]);
     if (ov[0]) maxk = ov[0] + 4;
     if (ov[1]) hslots = ov[1] + 12;
-    if (maxk > 0xffff || hslots > NBR_MAXSLOTS) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d neighbours / %d history partners", ov[0], ov[1]);
+    if (maxk > (fmt ? NN2_MAXK : 0xffff) || hslots > NBR_MAXSLOTS) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d neighbours / %d history partners", ov[0], ov[1]);
+  }
+  if (fmt) {  // rings of the wavefront: `ring` chunk-sized buffers of result records and partial sums
+    // (hcnt[48..50] = work items, largest chunk, work groups: copied above, the stream has been synchronised since)
+    E->wave_nitems = n ? E->hcnt[48] : 0; E->wave_ngrp = n ? E->hcnt[50] : 0;
+    const int mxc = n ? E->hcnt[49] : 0;
+    if (mxc > E->wave_ccap || !E->wave_ccap) E->wave_ccap = ((mxc + mxc / 8 + 127) / 128) * 128 + 128;
+    const size_t need_res = (size_t)E->wave_ring * Lnew.hslots * E->wave_ccap * 2, need_part = (size_t)E->wave_ring * 6 * E->wave_ccap;
+    if (E->res.n < need_res) { E->res.release(); E->res.ensure(E, need_res); }
+    if (E->part.n < need_part) { E->part.release(); E->part.ensure(E, need_part); }
   }
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
@@ -1671,6 +1731,9 @@ static StepP step_params(dem_engine *E, int mode)
   P.xr = E->xr[c].p; P.vm = E->vm[c].p; P.wt = E->wt[c].p;
   P.xr_o = E->xr[c ^ 1].p; P.vm_o = E->vm[c ^ 1].p; P.wt_o = E->wt[c ^ 1].p;
   P.xh = E->xh.p; P.nbr = L.nbr.p; P.numneigh = L.numneigh.p; P.hist = L.hist.p; P.hslots = L.hslots;
+  P.res = E->res.p; P.part = E->part.p; P.serial = (double)E->serial;
+  P.chunk_start = E->wtab.p; P.grp = E->wtab.p + 260; P.grp_start = E->wtab.p + 260 + 520; P.wctr = E->wtab.p + 260 + 520 + 524 + 8;
+  P.nslab = E->grid.nslab; P.ring = E->wave_ring; P.ccap = E->wave_ccap; P.ngrp = E->wave_ngrp; P.nitems = E->wave_nitems;
   P.whist = E->whist.p; P.f = E->f.p; P.tq = E->tq.p; P.walls = E->dwalls.p; P.nwalls = (int)E->walls.size(); P.nwc = E->nwc; P.nwcap = E->nwcap; P.wlist = E->wlist.p; P.fw = E->fw.p;
   P.pm = E->pm; P.tab = E->tab.p; P.nt1 = E->ntypes + 1;
   for (int w = 0; w < T_B_LAMBDA; w++) P.t1[w] = E->t1[w];
@@ -1685,6 +1748,29 @@ static StepP step_params(dem_engine *E, int mode)
   return P;
 }
 
+// result records are stamped with a serial number that is unique in the process (and starts at the wall clock in
+// microseconds): device blocks are recycled between engines, so a stale record must never carry the current stamp
+static long next_serial()
+{
+  static std::mutex mu; static long cur = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!cur) cur = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count() & ((1L << 52) - 1);
+  return ++cur;
+}
+template <int N, int R>
+static void launch_pairs_t(dem_engine *E, const StepP &P)
+{  // owner list: the whole step as one persistent wavefront kernel; a single chunk (option wave 0) runs as two plain launches
+  if (P.nslab > 1) {
+    const unsigned grid = (unsigned)std::min<long>((long)E->num_sms * DEM_P_MINBLOCKS, std::max(1, P.nitems));
+    if (E->ntypes == 1) k_wave<N, R, true><<<grid, 128, 0, E->stream>>>(P);
+    else k_wave<N, R, false><<<grid, 128, 0, E->stream>>>(P);
+    return;
+  }
+  if (E->ntypes == 1) k_pairs<N, R, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+  else k_pairs<N, R, false><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+  k_finish<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);
+  E->launches++;
+}
 template <int N, int R>
 static void launch_step_t(dem_engine *E, const StepP &P)
 {
@@ -1719,6 +1805,22 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (have_mesh_walls(E) && E->mesh_ready && E->any_stress) CK(cudaMemsetAsync(E->dmforce.p, 0, 6 * DEM_MAXMESH * sizeof(double), E->stream));  // MeshModuleStress::pre_force
   if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
+  if (E->ls[E->lcur].fmt == 1) {
+    E->serial = next_serial(); P.serial = (double)E->serial;
+    if (E->have_pair) {
+      switch (key) {
+        case N_HERTZ * 4 + R_OFF: launch_pairs_t<N_HERTZ, R_OFF>(E, P); break;
+        case N_HERTZ * 4 + R_CDT: launch_pairs_t<N_HERTZ, R_CDT>(E, P); break;
+        case N_HERTZ * 4 + R_EPSD: launch_pairs_t<N_HERTZ, R_EPSD>(E, P); break;
+        case N_HERTZ * 4 + R_EPSD2: launch_pairs_t<N_HERTZ, R_EPSD2>(E, P); break;
+        case N_HOOKE * 4 + R_OFF: launch_pairs_t<N_HOOKE, R_OFF>(E, P); break;
+        case N_HOOKE * 4 + R_CDT: launch_pairs_t<N_HOOKE, R_CDT>(E, P); break;
+        case N_HOOKE * 4 + R_EPSD: launch_pairs_t<N_HOOKE, R_EPSD>(E, P); break;
+        case N_HOOKE * 4 + R_EPSD2: launch_pairs_t<N_HOOKE, R_EPSD2>(E, P); break;
+        default: dem_fail(E, DEM_ERR_STATE, "no kernel for this model combination");
+      }
+    } else k_finish<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);  // walls only
+  } else
   if (E->have_pair && E->pm.cohesion) {
     const unsigned g = GRID(P.nlocal, 128);
 #define BONDK(N, R) { if (E->pm.cohesion == C_BOND) k_step_bond<N, R, C_BOND><<<g, 128, 0, E->stream>>>(P); else k_step_bond<N, R, C_BONDNL><<<g, 128, 0, E->stream>>>(P); }
@@ -1921,6 +2023,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
     CK(cudaMemcpy(&to, e->hsig.p + 15, sizeof(int), cudaMemcpyDeviceToHost));
     if (to) { e->comm_bad = 1; dem_fail(e, DEM_ERR_CUDA, "halo exchange timed out waiting for a neighbour rank"); }
   }
+  if (e->hflag[3] || e->hflag[7]) { e->hflag[3] = e->hflag[7] = 0; dem_fail(e, DEM_ERR_CUDA, "the step wavefront timed out on a chunk dependency (internal error)"); }
   if (overflow_seen || e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;
   API_END
@@ -2003,8 +2106,11 @@ static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector
   std::vector<int> tags(n), nn(n);
   CK(cudaMemcpy(tags.data(), E->tag.p, n * sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(nn.data(), L.numneigh.p, n * sizeof(int), cudaMemcpyDeviceToHost));
-  for (long i = 0; i < n; i++) nn[i] &= 0xffff;
+  std::vector<int> nown(n, 0);
+  if (L.fmt) for (long i = 0; i < n; i++) { nown[i] = NN2_OWN(nn[i]); nn[i] = NN2_TOT(nn[i]); }
+  else for (long i = 0; i < n; i++) nn[i] &= 0xffff;
   int kmax = 0; for (long i = 0; i < n; i++) kmax = std::max(kmax, nn[i]);
+  if (L.fmt) kmax = L.maxk;  // (owner list: partner-owned entries sit at the back of the row)
   std::vector<unsigned> nbr((size_t)kmax * L.cap); std::vector<int> ptag((size_t)kmax * L.cap);
   if (kmax) {
     CK(cudaMemcpy(nbr.data(), L.nbr.p, nbr.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
@@ -2014,6 +2120,16 @@ static void collect_pairs(dem_engine *E, std::vector<PairRow> &rows, std::vector
   if (kmax && dnum) CK(cudaMemcpy(hist.data(), L.hist.p, hist.size() * sizeof(double4), cudaMemcpyDeviceToHost));
   const ModelP &M = E->pm;
   auto comp = [](const double4 &v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; };
+  if (L.fmt) {
+    // owner list: one row per OWNED entry (a pair across a periodic face or a brick boundary is owned on both sides: the
+    // reference lists such a pair on both sides, too); history is stored "lower tag first" whoever owns the pair
+    for (long i = 0; i < n; i++) for (int k = 0; k < nown[i]; k++) {
+      const unsigned w = nbr[(size_t)k * L.cap + i];
+      const int tj = ptag[(size_t)k * L.cap + i];
+      const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+      rows.push_back(PairRow{std::min(tags[i], tj), std::max(tags[i], tj), slot >= 0 ? 1 : 0, (long)std::max(slot, 0) * L.cap + i, slot >= 0 ? 1 : 0});
+    }
+  } else
   for (long i = 0; i < n; i++) for (int k = 0; k < nn[i]; k++) {
     const unsigned w = nbr[(size_t)k * L.cap + i];
     const int tj = ptag[(size_t)k * L.cap + i];
@@ -2217,7 +2333,8 @@ extern "C" int dem_get_stats(dem_engine *e, dem_stats *s)
   if (L.valid && e->nlocal) {
     e->counters.ensure(e, 2);
     CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), e->stream));
-    k_count_pairs<<<GRID(e->nlocal, 256), 256, 0, e->stream>>>((int)e->nlocal, L.numneigh.p, L.nbr.p, L.cap, e->counters.p);
+    if (L.fmt) k_count_pairs2<<<GRID(e->nlocal, 256), 256, 0, e->stream>>>((int)e->nlocal, L.numneigh.p, L.nbr.p, L.cap, L.maxk, e->counters.p);
+    else k_count_pairs<<<GRID(e->nlocal, 256), 256, 0, e->stream>>>((int)e->nlocal, L.numneigh.p, L.nbr.p, L.cap, e->counters.p);
     unsigned long long h[2];
     CK(cudaMemcpyAsync(h, e->counters.p, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

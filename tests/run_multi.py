@@ -20,7 +20,9 @@ def make_engine(rank, world, local):
     if rank == 0:
         buf.copy_(torch.frombuffer(bytearray(dem_b200.Engine.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(buf, 0)
-    return dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=bytes(buf.cpu().numpy().tobytes()))
+    e = dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=bytes(buf.cpu().numpy().tobytes()))
+    e.option("chunk", 128)  # small beds: several chunks per brick, so that the step runs as the wavefront kernel
+    return e
 
 
 def gather_snapshot(eng, c, rank, world):
