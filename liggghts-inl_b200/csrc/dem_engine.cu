@@ -206,10 +206,7 @@ struct dem_engine {
   DevBuf<char> cubtmp;
   ListSet ls[2];
   int lcur = 0;
-  DevBuf<double4> res;  // owner list: ring of per-contact result records
-  DevBuf<double> part;  // owner list: ring of per-particle partial sums
-  DevBuf<int> wtab;     // wavefront: chunk_start[260] | grp[520] | grp_start[524] | meta[8] | counters[8 + 512]
-  int wave_skew = 1, wave_ring = 1, wave_ccap = 0, wave_nitems = 0, wave_ngrp = 0, num_sms = 0;
+  DevBuf<double4> res;  // owner list: per-contact result records
   long serial = 0;      // step launches so far (stamps the result records)
   DevBuf<int> overflow;
   DevBuf<double> fa, ta;  // accumulation arrays of the half-list alternative (option "half_list")
@@ -344,7 +341,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
-  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release(); e->res.release(); e->part.release(); e->wtab.release();
+  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release(); e->res.release();
   e->dmforce.release(); e->dmpref.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
@@ -1200,25 +1197,8 @@ static void setup_grid(dem_engine *E)
     if (E->pgrid[d] > 1 && E->subhi[d] - E->sublo[d] < 2.0 * E->cutneighmax)
       dem_fail(E, DEM_ERR_UNSUPPORTED, "sub-box of a rank in dim %d is thinner than two neighbour cutoffs", d);
   }
-  {  // storage order: slabs along the longest dimension of the sub-box (the chunks of the step wavefront, dem_pairs.cuh),
-     // Morton inside a slab.  A slab is a whole number of cell layers, i.e. at least one neighbour cutoff thick.
-    GridP &G = E->grid;
-    G.sdim = 0;
-    for (int d = 1; d < 3; d++) if (G.nc[d] > G.nc[G.sdim]) G.sdim = d;
-    const bool wave = !(E->opt.count("wave") && E->opt["wave"] == 0);
-    const long per_chunk = E->opt.count("chunk") ? (long)E->opt["chunk"] : 32768;
-    long want = wave ? std::max<long>(1, std::min<long>(250, E->nlocal / std::max<long>(per_chunk, 128))) : 1;
-    G.cps = std::max(1, (int)((G.nc[G.sdim] + want - 1) / want));
-    G.nslab = (G.nc[G.sdim] + G.cps - 1) / G.cps;
-    while (G.nslab > 250) { G.cps++; G.nslab = (G.nc[G.sdim] + G.cps - 1) / G.cps; }
-    const int d1 = (G.sdim + 1) % 3, d2 = (G.sdim + 2) % 3;
-    const int mx = std::max(G.cps, std::max(G.nc[d1], G.nc[d2]));
-    int b = 1; while ((1 << b) < mx) b++;
-    int sb = 0; while ((1 << sb) < G.nslab) sb++;
-    G.mbits = b;
-    G.morton = (b <= 10 && sb + 3 * b <= 32) ? 1 : 0;
-    if (E->opt.count("morton") && E->opt["morton"] == 0) G.morton = 0;
-  }
+  E->grid.morton = (E->grid.nc[0] <= 1024 && E->grid.nc[1] <= 1024 && E->grid.nc[2] <= 1024) ? 1 : 0;
+  if (E->opt.count("morton") && E->opt["morton"] == 0) E->grid.morton = 0;
   E->ncells = total;
   E->ocs.ensure(E, total); E->oce.ensure(E, total); E->gcs.ensure(E, total); E->gce.ensure(E, total);
 }
@@ -1560,23 +1540,6 @@ static void rebuild(dem_engine *E)
     E->cur = c ^ 1; c = E->cur;
     did_permute = true;
   }
-  // chunk table + work queue of the step wavefront (owner list): from the sorted keys
-  E->wtab.ensure(E, 260 + 520 + 524 + 8 + 8 + 512);
-  {
-    int *chunk_start = E->wtab.p, *grp = E->wtab.p + 260, *grp_start = grp + 520, *meta = grp_start + 524, *wctr = meta + 8;
-    CK(cudaMemsetAsync(wctr, 0, (8 + 512) * sizeof(int), st));
-    CK(cudaMemsetAsync(meta, 0, 8 * sizeof(int), st));
-    const GridP &G = E->grid;
-    if (E->num_sms == 0) CK(cudaDeviceGetAttribute(&E->num_sms, cudaDevAttrMultiProcessorCount, E->device));
-    // phase B of a chunk is queued `skew` chunks behind its phase A: far enough for the A blocks to have left the device
-    const double avg_blocks = std::max(1.0, (double)n / 128.0 / G.nslab);
-    int skew = (int)ceil(1.5 * E->num_sms * DEM_P_MINBLOCKS / avg_blocks);
-    skew = std::max(1, std::min(skew, 24));
-    if (E->opt.count("wave_skew")) skew = std::max(1, (int)E->opt["wave_skew"]);
-    E->wave_skew = skew; E->wave_ring = G.nslab == 1 ? 1 : skew + 3;
-    if (n) { k_wave_table<<<1, 256, 0, st>>>(G.nslab, n, E->keys2.p, G, skew, chunk_start, grp, grp_start, meta); E->launches++; }
-    CK(cudaMemcpyAsync(E->hcnt + 48, meta, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  }
   tr.mark("migrate+sort+gather");
   E->nlocal = n;
   // 2. owned cell ranges
@@ -1643,8 +1606,8 @@ static void rebuild(dem_engine *E)
   tr.mark("ghost order");
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
-  // plain contact models: owner list (every pair evaluated once, dem_pairs.cuh); bond decks: full list (k_step_bond)
-  const int fmt = ((E->have_pair && E->pm.cohesion) || (E->opt.count("full_list") && E->opt["full_list"] != 0)) ? 0 : 1;  // (full_list: first-generation k_step, kept for A/B measurements)
+  // full list (k_step, k_step_bond) unless option owner_list asks for the measured alternative of dem_pairs.cuh
+  const int fmt = (E->have_pair && !E->pm.cohesion && E->opt.count("owner_list") && E->opt["owner_list"] != 0) ? 1 : 0;
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
   int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : (fmt ? 12 : 16)));
   for (int attempt = 0; attempt < 6; attempt++) {
@@ -1675,15 +1638,7 @@ static void rebuild(dem_engine *E)
     if (ov[1]) hslots = ov[1] + 12;
     if (maxk > (fmt ? NN2_MAXK : 0xffff) || hslots > NBR_MAXSLOTS) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d neighbours / %d history partners", ov[0], ov[1]);
   }
-  if (fmt) {  // rings of the wavefront: `ring` chunk-sized buffers of result records and partial sums
-    // (hcnt[48..50] = work items, largest chunk, work groups: copied above, the stream has been synchronised since)
-    E->wave_nitems = n ? E->hcnt[48] : 0; E->wave_ngrp = n ? E->hcnt[50] : 0;
-    const int mxc = n ? E->hcnt[49] : 0;
-    if (mxc > E->wave_ccap || !E->wave_ccap) E->wave_ccap = ((mxc + mxc / 8 + 127) / 128) * 128 + 128;
-    const size_t need_res = (size_t)E->wave_ring * Lnew.hslots * E->wave_ccap * 2, need_part = (size_t)E->wave_ring * 6 * E->wave_ccap;
-    if (E->res.n < need_res) { E->res.release(); E->res.ensure(E, need_res); }
-    if (E->part.n < need_part) { E->part.release(); E->part.ensure(E, need_part); }
-  }
+  if (fmt && E->res.n < (size_t)Lnew.hslots * 2 * Lnew.cap) { E->res.release(); E->res.ensure(E, (size_t)Lnew.hslots * 2 * Lnew.cap); }
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
   tr.mark("list build + remap");
@@ -1731,9 +1686,7 @@ static StepP step_params(dem_engine *E, int mode)
   P.xr = E->xr[c].p; P.vm = E->vm[c].p; P.wt = E->wt[c].p;
   P.xr_o = E->xr[c ^ 1].p; P.vm_o = E->vm[c ^ 1].p; P.wt_o = E->wt[c ^ 1].p;
   P.xh = E->xh.p; P.nbr = L.nbr.p; P.numneigh = L.numneigh.p; P.hist = L.hist.p; P.hslots = L.hslots;
-  P.res = E->res.p; P.part = E->part.p; P.serial = (double)E->serial;
-  P.chunk_start = E->wtab.p; P.grp = E->wtab.p + 260; P.grp_start = E->wtab.p + 260 + 520; P.wctr = E->wtab.p + 260 + 520 + 524 + 8;
-  P.nslab = E->grid.nslab; P.ring = E->wave_ring; P.ccap = E->wave_ccap; P.ngrp = E->wave_ngrp; P.nitems = E->wave_nitems;
+  P.res = E->res.p; P.serial = (double)E->serial;
   P.whist = E->whist.p; P.f = E->f.p; P.tq = E->tq.p; P.walls = E->dwalls.p; P.nwalls = (int)E->walls.size(); P.nwc = E->nwc; P.nwcap = E->nwcap; P.wlist = E->wlist.p; P.fw = E->fw.p;
   P.pm = E->pm; P.tab = E->tab.p; P.nt1 = E->ntypes + 1;
   for (int w = 0; w < T_B_LAMBDA; w++) P.t1[w] = E->t1[w];
@@ -1759,13 +1712,7 @@ static long next_serial()
 }
 template <int N, int R>
 static void launch_pairs_t(dem_engine *E, const StepP &P)
-{  // owner list: the whole step as one persistent wavefront kernel; a single chunk (option wave 0) runs as two plain launches
-  if (P.nslab > 1) {
-    const unsigned grid = (unsigned)std::min<long>((long)E->num_sms * DEM_P_MINBLOCKS, std::max(1, P.nitems));
-    if (E->ntypes == 1) k_wave<N, R, true><<<grid, 128, 0, E->stream>>>(P);
-    else k_wave<N, R, false><<<grid, 128, 0, E->stream>>>(P);
-    return;
-  }
+{  // owner list: phase A (owned pairs, once each), then phase B (partner shares + integration)
   if (E->ntypes == 1) k_pairs<N, R, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
   else k_pairs<N, R, false><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
   k_finish<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);
@@ -1807,7 +1754,7 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
   if (E->ls[E->lcur].fmt == 1) {
     E->serial = next_serial(); P.serial = (double)E->serial;
-    if (E->have_pair) {
+    {
       switch (key) {
         case N_HERTZ * 4 + R_OFF: launch_pairs_t<N_HERTZ, R_OFF>(E, P); break;
         case N_HERTZ * 4 + R_CDT: launch_pairs_t<N_HERTZ, R_CDT>(E, P); break;
@@ -1819,7 +1766,7 @@ static void launch_step(dem_engine *E, int mode, bool timed)
         case N_HOOKE * 4 + R_EPSD2: launch_pairs_t<N_HOOKE, R_EPSD2>(E, P); break;
         default: dem_fail(E, DEM_ERR_STATE, "no kernel for this model combination");
       }
-    } else k_finish<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);  // walls only
+    }
   } else
   if (E->have_pair && E->pm.cohesion) {
     const unsigned g = GRID(P.nlocal, 128);
@@ -2023,7 +1970,6 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
     CK(cudaMemcpy(&to, e->hsig.p + 15, sizeof(int), cudaMemcpyDeviceToHost));
     if (to) { e->comm_bad = 1; dem_fail(e, DEM_ERR_CUDA, "halo exchange timed out waiting for a neighbour rank"); }
   }
-  if (e->hflag[3] || e->hflag[7]) { e->hflag[3] = e->hflag[7] = 0; dem_fail(e, DEM_ERR_CUDA, "the step wavefront timed out on a chunk dependency (internal error)"); }
   if (overflow_seen || e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;
   API_END

@@ -695,11 +695,6 @@ struct GridP {
   double org[3], inv[3];
   int nc[3];
   int morton;
-  // storage order = slab-major: the cells are grouped into slabs of `cps` cell layers along dimension `sdim`; inside a slab
-  // they follow a Morton curve (morton = 1: `mbits` bits per dimension, slab index above bit 3*mbits) or a plain linear
-  // order.  A slab is at least one neighbour cutoff thick, so every neighbour of a particle lives in its own or an adjacent
-  // slab: the chunks of the step kernel's wavefront (dem_pairs.cuh).
-  int sdim, cps, mbits, nslab;
 };
 __device__ __forceinline__ unsigned spread10(unsigned v)
 {
@@ -712,20 +707,9 @@ __device__ __forceinline__ void cell_of(const GridP &G, const double4 &x, int &c
   cx = min(max(cx, 0), G.nc[0] - 1); cy = min(max(cy, 0), G.nc[1] - 1); cz = min(max(cz, 0), G.nc[2] - 1);
 }
 __device__ __forceinline__ int lin_cell(const GridP &G, int cx, int cy, int cz) { return (cz * G.nc[1] + cy) * G.nc[0] + cx; }
-__host__ __device__ __forceinline__ unsigned slab_key_lo(const GridP &G, int slab)
-{  // smallest key of a slab
-  if (G.morton) return (unsigned)slab << (3 * G.mbits);
-  const int d1 = (G.sdim + 1) % 3, d2 = (G.sdim + 2) % 3;
-  return (unsigned)slab * (unsigned)(G.nc[d1] * G.nc[d2] * G.cps);
-}
 __device__ __forceinline__ unsigned key_of(const GridP &G, int cx, int cy, int cz)
 {
-  int c[3] = {cx, cy, cz};
-  const int slab = c[G.sdim] / G.cps;
-  c[G.sdim] -= slab * G.cps;
-  if (G.morton) return ((unsigned)slab << (3 * G.mbits)) | spread10(c[0]) | (spread10(c[1]) << 1) | (spread10(c[2]) << 2);
-  const int d1 = (G.sdim + 1) % 3, d2 = (G.sdim + 2) % 3;
-  return slab_key_lo(G, slab) + (unsigned)((c[d2] * G.nc[d1] + c[d1]) * G.cps + c[G.sdim]);
+  return G.morton ? (spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2)) : (unsigned)lin_cell(G, cx, cy, cz);
 }
 
 // Domain::pbc (domain.cpp:550-640) + sort key of the owned particles

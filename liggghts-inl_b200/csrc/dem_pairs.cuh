@@ -1,22 +1,29 @@
-// dem_pairs.cuh -- the pair step of the plain contact models (no cohesion), second generation ("owner list").
+// dem_pairs.cuh -- the pair step of the plain contact models as an OWNER LIST (option owner_list): a measured alternative
+// to the full list of k_step, kept because it is what the reference's half list maps to and because its rebuild is cheaper.
 //
-// Why: the first-generation k_step evaluated every contact twice (once per owner of a FULL list) and kept two copies of
-// its history; ncu showed the kernel issue/latency bound with a third of its 561 M warp instructions in fp64 and 1.9x the
-// algorithmic DRAM traffic (profiles/r02_*).  Here every pair has ONE owner -- the particle with the lower storage index,
-// or the local particle when the partner is a ghost -- which evaluates the contact once, keeps the single copy of its
-// history and leaves the partner's share (-F, torque on the partner) in a per-contact result record.  The partner picks
-// the record up through its own row.  Nothing is accumulated with atomics: a particle's sum always runs over its row in
-// row order (own contacts first, then the received shares), so runs stay bit reproducible -- what the reference gets from
-// its half list with `newton off` (pair_gran_base.h:257-496, f[j] updated by the owner of the pair) without the races.
+// Every pair has ONE owner -- the particle with the lower storage index, or the local particle when the partner is a ghost
+// -- which evaluates the contact once (k_pairs), keeps the single copy of its history and leaves the partner's share (the
+// force on the owner, the torque on the partner) in a per-contact result record; the partner picks the record up through
+// its own row in k_finish, which also integrates.  Nothing is accumulated with atomics: a particle's sum always runs over
+// its row in row order (own contacts first, then the received shares), so runs stay bit reproducible -- what the reference
+// gets from its half list with `newton off` (pair_gran_base.h:257-496, f[j] updated by the owner of the pair) without races.
+//
+// Measured on the 4,194,304-sphere bed (profiles/r2*_owner_list*): k_pairs 0.78 ms + k_finish 0.43 ms = 1.22-1.24 ms per step
+// against 1.07 ms for the full list.  Half the contact math (364 M instead of 561 M warp instructions) does not pay for the
+// result records: 64 B written and read per contact is the traffic the second history copy of the full list cost, plus the
+// partial sums' round trip -- 4.2 GB per step against 2.8 GB.  A persistent wavefront form (phase B of a slab of the bed
+// following its phase A through a queue, result rings meant to stay in L2, eviction hints) was built and measured at
+// 1.7-2.2 ms with unchanged DRAM traffic: the ~95 k particles in flight move ~100 MB between a record's write and its read,
+// the size of the L2 (commit e91a57a has that kernel).  The full list remains the default.
 //
 // Row layout (ELLPACK, transposed, stride lcap; numneigh word = NN2_PACK(total, owned, history slots in use)):
 //   entries [0, owned)              pairs this particle owns: partner index > own index, or partner is a ghost
 //   entries [maxk - (total-owned), maxk)  pairs the partner owns, filled from the back of the row
 // A neighbour word is [31] partner tag < own tag, [30:25] history slot + 1 of the pair IN THE OWNER'S ROW (0: the pair has
 // no history == reference contact_flag 0), [24:0] partner index.  History records live at hist[(slot*hrec + r)*lcap + owner],
-// result records in a ring of chunk-sized buffers (res_at below; one aligned 64-byte block per pair): h=0 (Fx, Fy, Fz, Tpx), h=1 (Tpy, Tpz, serial, owner index) with F the force
-// on the owner and Tp the torque on the partner; `serial` = the launch that wrote it (a partner ignores stale records and
-// records of another chunk that shares the ring slot).
+// result records at res[(slot*lcap + owner)*2 + h] (one aligned 64-byte block per pair): h=0 (Fx, Fy, Fz, Tpx), h=1 (Tpy,
+// Tpz, serial, 0) with F the force on the owner and Tp the torque on the partner; `serial` = the launch that wrote the record
+// (a partner ignores stale records).
 #pragma once
 #include "dem_kernels.cuh"
 
@@ -41,104 +48,7 @@ __device__ __forceinline__ double4 ldcg4(const double4 *p)
   return v;
 }
 
-// L2 eviction hints (createpolicy + .L2::cache_hint): the rings must stay in L2 from the moment a record is written until
-// the slot is overwritten a few chunks later, while ~1 KB per particle of use-once data (rows, history, fresh records)
-// streams through the same cache.  Ring traffic is marked evict_last, the use-once streams evict_first.
-#ifndef DEM_L2HINTS
-#define DEM_L2HINTS 1
-#endif
-struct L2Pol { unsigned long long first, last; };
-__device__ __forceinline__ L2Pol l2_policies()
-{
-  L2Pol p;
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.first));
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.last));
-  return p;
-}
-__device__ __forceinline__ double4 ld4_pol(const double4 *p, unsigned long long pol)
-{
-  double4 v;
-#if DEM_L2HINTS
-  asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
-#else
-  v = *p;
-#endif
-  return v;
-}
-__device__ __forceinline__ double4 ldcg4_pol(const double4 *p, unsigned long long pol)
-{
-  double4 v;
-#if DEM_L2HINTS
-  asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
-#else
-  v = ldcg4(p);
-#endif
-  return v;
-}
-__device__ __forceinline__ void st4_pol(double4 *p, const double4 &v, unsigned long long pol)
-{
-#if DEM_L2HINTS
-  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w), "l"(pol));
-#else
-  st4(p, v);
-#endif
-}
-__device__ __forceinline__ double ldcg_pol(const double *p, unsigned long long pol)
-{
-#if DEM_L2HINTS
-  double v; asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
-#else
-  return __ldcg(p);
-#endif
-}
-__device__ __forceinline__ void st_pol(double *p, double v, unsigned long long pol)
-{
-#if DEM_L2HINTS
-  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol));
-#else
-  *p = v;
-#endif
-}
-__device__ __forceinline__ unsigned ldu32_pol(const unsigned *p, unsigned long long pol)
-{
-#if DEM_L2HINTS
-  unsigned v; asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
-#else
-  return *p;
-#endif
-}
-__device__ __forceinline__ unsigned ldcgu32_pol(const unsigned *p, unsigned long long pol)
-{
-#if DEM_L2HINTS
-  unsigned v; asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
-#else
-  return ldcg_u32(p);
-#endif
-}
-
-// A step runs as a wavefront over chunks (= slabs of the storage order, dem_kernels.cuh GridP): phase A of chunk c (owned
-// pairs) must be complete before phase B (shares of the partner-owned pairs + integration) of chunks c and c+1 runs --
-// the owner of a pair has the lower index, so it sits in the same or the previous chunk.  Results and partial sums of a
-// chunk live in slot (c % ring) of a ring: the addresses are re-used a few chunks later, while the lines are still in
-// L2, so this traffic never reaches DRAM.
-struct Chunk {
-  int c, cs, ce;             // chunk index, first particle, one past the last
-  int cs_prev;               // first particle of the previous chunk
-  double4 *res, *res_prev;   // ring buffers of result records of this / the previous chunk
-  double *part;              // ring buffer of partial sums of this chunk
-  L2Pol pol;
-};
-__device__ __forceinline__ Chunk chunk_of(const StepP &P, int c, int cs, int ce, int cs_prev)
-{
-  Chunk K;
-  K.c = c; K.cs = cs; K.ce = ce; K.cs_prev = cs_prev;
-  const int r = c % P.ring, rp = (c + P.ring - 1) % P.ring;
-  K.res = P.res + (size_t)r * P.hslots * P.ccap * 2; K.res_prev = P.res + (size_t)rp * P.hslots * P.ccap * 2;
-  K.part = P.part + (size_t)r * 6 * P.ccap;
-  K.pol = l2_policies();
-  return K;
-}
-__device__ __forceinline__ double4 *res_rec(const StepP &P, double4 *base, int slot, int off) { return base + ((size_t)slot * P.ccap + off) * 2; }
+__device__ __forceinline__ double4 *res_rec(const StepP &P, int slot, int owner) { return P.res + ((size_t)slot * P.lcap + owner) * 2; }
 
 // one owned, touching pair of particle i: evaluated once, in the owner's orientation (pair_chain); history in the canonical
 // orientation "lower tag first"; the partner's share goes to the pair's result record
@@ -146,7 +56,7 @@ __device__ __forceinline__ double4 *res_rec(const StepP &P, double4 *base, int s
 #define DEM_P_INLINE __forceinline__
 #endif
 template <int NORMAL, int ROLLING, bool ONE>
-__device__ DEM_P_INLINE void pair_contact2(const StepP &P, const Chunk &K, int i, unsigned w, const double4 &xi, const double4 &vi, const double4 &wi,
+__device__ DEM_P_INLINE void pair_contact2(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi, const double4 &wi,
                                               bool su, int *nh, double *F, double *T)
 {
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
@@ -157,8 +67,8 @@ __device__ DEM_P_INLINE void pair_contact2(const StepP &P, const Chunk &K, int i
   double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
   if (had) {
     const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-    if (P.pm.tangential) hs = ld4_pol(hp + (size_t)P.pm.rec_shear * P.lcap, K.pol.first);
-    if (HAS_ROLL_HIST) hr = ld4_pol(hp + (size_t)P.pm.rec_roll * P.lcap, K.pol.first);
+    if (P.pm.tangential) hs = hp[(size_t)P.pm.rec_shear * P.lcap];
+    if (HAS_ROLL_HIST) hr = hp[(size_t)P.pm.rec_roll * P.lcap];
   }
   const double sgn = (w & NBR_JFIRST) ? -1.0 : 1.0;
   double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
@@ -190,13 +100,13 @@ __device__ DEM_P_INLINE void pair_contact2(const StepP &P, const Chunk &K, int i
   if (slot >= 0) {
     if (P.pm.hrec && (su || !had)) {
       double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-      if (P.pm.tangential) st4_pol(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.), K.pol.first);
-      if (HAS_ROLL_HIST) st4_pol(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.), K.pol.first);
+      if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
+      if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
     }
     if (j < P.nlocal) {
-      double4 *rp = res_rec(P, K.res, slot, i - K.cs);
-      st4_pol(rp, make_double4(Fc[0], Fc[1], Fc[2], Tp[0]), K.pol.last);
-      st4_pol(rp + 1, make_double4(Tp[1], Tp[2], P.serial, (double)i), K.pol.last);
+      double4 *rp = res_rec(P, slot, i);
+      st4(rp, make_double4(Fc[0], Fc[1], Fc[2], Tp[0]));
+      st4(rp + 1, make_double4(Tp[1], Tp[2], P.serial, 0.));
     }
   } else if (j < P.nlocal) ((volatile int *)P.flag)[1] = 1;  // no slot: the partner cannot be served (reported as history overflow)
 }
@@ -232,11 +142,11 @@ __device__ __forceinline__ void prefetch_contact2(const StepP &P, int i, unsigne
 // (sweep in passes with the gathers in flight, own-lane rounds, cooperative deal of the uneven remainder), half the entries.
 // Leaves the particle's partial sum (its owned contacts, row order) in P.f / P.tq.
 template <int NORMAL, int ROLLING, bool ONE>
-__device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int i0, unsigned (*s_w)[128], double4 (*s_rec)[128], double (*s_res)[4 * 32], int *s_off, int *s_nh)
+__device__ __forceinline__ void pairs_block(const StepP &P, int i0, unsigned (*s_w)[128], double4 (*s_rec)[128], double (*s_res)[4 * 32], int *s_off, int *s_nh)
 {
   const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
   const int i = i0 + tid;
-  const bool active = i < K.ce;
+  const bool active = i < P.nlocal;
   const bool su = (P.mode != MODE_SETUP);
   double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
   int nc = 0, nh0 = 0, nown = 0, nnw = 0;
@@ -260,7 +170,7 @@ __device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int 
       unsigned wv[DEM_P_SWEEPW];
       double4 xv[DEM_P_SWEEPW];
 #pragma unroll
-      for (int u = 0; u < DEM_P_SWEEPW; u++) wv[u] = (k0 + u < nown) ? ldu32_pol(P.nbr + (size_t)(k0 + u) * P.lcap + i, K.pol.first) : (unsigned)i;  // past the end: myself (never touches)
+      for (int u = 0; u < DEM_P_SWEEPW; u++) wv[u] = (k0 + u < nown) ? P.nbr[(size_t)(k0 + u) * P.lcap + i] : (unsigned)i;  // past the end: myself (never touches)
 #pragma unroll
       for (int u = 0; u < DEM_P_SWEEPW; u++) xv[u] = ldg4(P.xr + (wv[u] & NBR_IDX));
       unsigned touch = 0u;
@@ -278,7 +188,7 @@ __device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int 
       while (touch) {  // more than DEM_P_CMAX owned contacts (rare): evaluated on the spot
         const int u = __ffs((int)touch) - 1;
         touch &= touch - 1;
-        pair_contact2<NORMAL, ROLLING, ONE>(P, K, i, P.nbr[(size_t)(k0 + u) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
+        pair_contact2<NORMAL, ROLLING, ONE>(P, i, P.nbr[(size_t)(k0 + u) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
       }
     }
   }
@@ -296,7 +206,7 @@ __device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int 
     const double4 xo = s_rec[0][tid], vo = s_rec[1][tid], wo = s_rec[2][tid];
 #pragma unroll 1
     for (int r = 0; r < ownr; r++)
-      if (r < nc) pair_contact2<NORMAL, ROLLING, ONE>(P, K, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T);
+      if (r < nc) pair_contact2<NORMAL, ROLLING, ONE>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T);
   }
   {  // cooperative deal of the remaining items: item t belongs to the last lane whose first item is <= t
     const int ncc = max(nc - ownr, 0);
@@ -317,7 +227,7 @@ __device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int 
         const int q = wb + p;
         const unsigned w = s_w[ownr + t - s_off[q]][q];
         double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
-        pair_contact2<NORMAL, ROLLING, ONE>(P, K, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
+        pair_contact2<NORMAL, ROLLING, ONE>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
         const int sl = (wb >> 5) * 32 + (t - b0);
 #pragma unroll
         for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
@@ -335,9 +245,8 @@ __device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int 
   if (active) {
     const int nh = s_nh[tid];
     if (nh != nh0) P.numneigh[i] = NN2_PACK(NN2_TOT(nnw), nown, nh);
-    double *pp = K.part + (i - K.cs);
-#pragma unroll
-    for (int d = 0; d < 3; d++) { st_pol(pp + (size_t)d * P.ccap, F[d], K.pol.last); st_pol(pp + (size_t)(3 + d) * P.ccap, T[d], K.pol.last); }
+    P.f[i] = F[0]; P.f[P.cap + i] = F[1]; P.f[2 * (size_t)P.cap + i] = F[2];
+    P.tq[i] = T[0]; P.tq[P.cap + i] = T[1]; P.tq[2 * (size_t)P.cap + i] = T[2];
   }
 }
 
@@ -346,41 +255,35 @@ __device__ __forceinline__ void pairs_block(const StepP &P, const Chunk &K, int 
 #ifndef DEM_F_UNROLL
 #define DEM_F_UNROLL 4
 #endif
-template <bool CG>
-__device__ __forceinline__ bool finish_particle(const StepP &P, const Chunk &K, int i)
+__device__ __forceinline__ bool finish_particle(const StepP &P, int i)
 {
   const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
   double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
   if (P.have_pair) {
     const int nnw = P.numneigh[i];
     const int nnon = NN2_TOT(nnw) - NN2_OWN(nnw);
-    {
-      const double *pp = K.part + (i - K.cs);
-#pragma unroll
-      for (int d = 0; d < 3; d++) { F[d] = ldcg_pol(pp + (size_t)d * P.ccap, K.pol.last); T[d] = ldcg_pol(pp + (size_t)(3 + d) * P.ccap, K.pol.last); }
-    }
+    F[0] = P.f[i]; F[1] = P.f[P.cap + i]; F[2] = P.f[2 * (size_t)P.cap + i];
+    T[0] = P.tq[i]; T[1] = P.tq[P.cap + i]; T[2] = P.tq[2 * (size_t)P.cap + i];
     for (int m0 = 0; m0 < nnon; m0 += DEM_F_UNROLL) {
       unsigned wv[DEM_F_UNROLL];
       double4 r0[DEM_F_UNROLL], r1[DEM_F_UNROLL];
 #pragma unroll
       for (int u = 0; u < DEM_F_UNROLL; u++) {
         const unsigned *q = P.nbr + (size_t)(P.maxk - 1 - (m0 + u)) * P.lcap + i;
-        wv[u] = (m0 + u < nnon) ? ldcgu32_pol(q, K.pol.first) : 0u;
+        wv[u] = (m0 + u < nnon) ? *q : 0u;
       }
 #pragma unroll
       for (int u = 0; u < DEM_F_UNROLL; u++) {
         r0[u] = make_double4(0., 0., 0., 0.); r1[u] = make_double4(0., 0., -1., 0.);
         if (wv[u] & NBR_HIST) {
           const int slot = (int)((wv[u] & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
-          const int j = (int)(wv[u] & NBR_IDX);  // the owner: lower index, same or previous chunk
-          const double4 *rp = j >= K.cs ? res_rec(P, K.res, slot, j - K.cs) : res_rec(P, K.res_prev, slot, j - K.cs_prev);
-          r0[u] = ldcg4_pol(rp, K.pol.last); r1[u] = ldcg4_pol(rp + 1, K.pol.last);
+          const double4 *rp = res_rec(P, slot, (int)(wv[u] & NBR_IDX));
+          r0[u] = rp[0]; r1[u] = rp[1];
         }
       }
 #pragma unroll
       for (int u = 0; u < DEM_F_UNROLL; u++) {
-        // (a ring slot is shared by the chunks c, c + ring, ...: the record must be this launch's AND this owner's)
-        if ((wv[u] & NBR_HIST) && r1[u].z == P.serial && r1[u].w == (double)(wv[u] & NBR_IDX)) {
+        if ((wv[u] & NBR_HIST) && r1[u].z == P.serial) {
           F[0] -= r0[u].x; F[1] -= r0[u].y; F[2] -= r0[u].z;
           T[0] += r0[u].w; T[1] += r1[u].x; T[2] += r1[u].y;
         }
@@ -390,7 +293,7 @@ __device__ __forceinline__ bool finish_particle(const StepP &P, const Chunk &K, 
   return step_epilogue(P, i, xi, vi, wi, F, T);
 }
 
-// ---- plain two-launch form (option wave 0: a single chunk; kept for per-phase profiling)
+// ---- the step as two launches: phase A over all particles, then phase B
 template <int NORMAL, int ROLLING, bool ONE>
 __global__ void __launch_bounds__(128, DEM_P_MINBLOCKS) k_pairs(const StepP P)
 {
@@ -399,116 +302,15 @@ __global__ void __launch_bounds__(128, DEM_P_MINBLOCKS) k_pairs(const StepP P)
   __shared__ double s_res[6][4 * 32];
   __shared__ int s_off[128], s_nh[128];
   if (step_gated(P)) return;
-  const Chunk K = chunk_of(P, 0, 0, P.nlocal, 0);
-  pairs_block<NORMAL, ROLLING, ONE>(P, K, blockIdx.x * 128, s_w, s_rec, s_res, s_off, s_nh);
+  pairs_block<NORMAL, ROLLING, ONE>(P, blockIdx.x * 128, s_w, s_rec, s_res, s_off, s_nh);
 }
 __global__ void __launch_bounds__(256) k_finish(const StepP P)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (step_gated(P)) return;
   bool trig = false;
-  const Chunk K = chunk_of(P, 0, 0, P.nlocal, 0);
-  if (i < P.nlocal) trig = finish_particle<false>(P, K, i);
+  if (i < P.nlocal) trig = finish_particle(P, i);
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
-}
-
-// ---- the step as ONE persistent kernel: blocks draw (chunk, phase, block) items from a queue whose order interleaves
-// phase A of chunk t with phase B of chunk t - skew; counters of finished blocks per chunk and phase carry the
-// dependencies (always on items handed out earlier, so a waiting block can never starve the block it waits for)
-__device__ __forceinline__ bool wave_wait(const StepP &P, const int *ctr, int target)
-{  // bounded (~0.5 s for the first block that gives up, none for the others): a broken dependency must not hang the device
-  const long long t0 = clock64();
-  while (*((volatile const int *)ctr) < target) {
-    __nanosleep(100);
-    if (((volatile int *)P.flag)[3] || clock64() - t0 > 1000000000LL) return false;
-  }
-  return true;
-}
-__device__ __forceinline__ int chunk_blocks(const StepP &P, int c) { return (P.chunk_start[c + 1] - P.chunk_start[c] + 127) >> 7; }
-template <int NORMAL, int ROLLING, bool ONE>
-__global__ void __launch_bounds__(128, DEM_P_MINBLOCKS) k_wave(const StepP P)
-{
-  __shared__ unsigned s_w[DEM_P_CMAX][128];
-  __shared__ double4 s_rec[3][128];
-  __shared__ double s_res[6][4 * 32];
-  __shared__ int s_off[128], s_nh[128];
-  __shared__ int s_item[2], s_grp[2];
-  if (step_gated(P)) return;
-  const int tid = threadIdx.x;
-  int *ctr = P.wctr, *doneA = P.wctr + 8, *doneB = P.wctr + 8 + 256;
-  // thread 0 draws the items one ahead (the atomic's latency hides behind the current item) and tracks the work group of
-  // its item with a running pointer (a block's items ascend)
-  int gcur = 0, nxt = 0, par = 0;
-  if (tid == 0) nxt = atomicAdd(ctr, 1);
-  for (;;) {
-    if (tid == 0) {
-      const int item = nxt;
-      if (item < P.nitems) { while (P.grp_start[gcur + 1] <= item) gcur++; nxt = atomicAdd(ctr, 1); }
-      s_item[par] = item; s_grp[par] = gcur;
-    }
-    __syncthreads();
-    const int item = s_item[par], g = s_grp[par];
-    par ^= 1;
-    if (item >= P.nitems) break;
-    const int gc = P.grp[g], c = gc >> 1, b = item - P.grp_start[g];
-    const Chunk K = chunk_of(P, c, P.chunk_start[c], P.chunk_start[c + 1], c > 0 ? P.chunk_start[c - 1] : 0);
-    if ((gc & 1) == 0) {
-      if (c >= P.ring) {  // my ring slot was chunk c - ring's: its readers are phase B of chunks c - ring and c - ring + 1
-        if (tid == 0) {
-          bool ok = wave_wait(P, doneB + c - P.ring + 1, chunk_blocks(P, c - P.ring + 1));
-          ok = ok && wave_wait(P, doneB + c - P.ring, chunk_blocks(P, c - P.ring));
-          if (!ok) ((volatile int *)P.flag)[3] = 1;
-        }
-        __syncthreads();
-      }
-      pairs_block<NORMAL, ROLLING, ONE>(P, K, K.cs + b * 128, s_w, s_rec, s_res, s_off, s_nh);
-      __syncthreads();
-      if (tid == 0) { __threadfence(); atomicAdd(doneA + c, 1); }
-    } else {
-      if (tid == 0) {
-        bool ok = wave_wait(P, doneA + c, chunk_blocks(P, c));
-        if (c > 0) ok = ok && wave_wait(P, doneA + c - 1, chunk_blocks(P, c - 1));
-        if (!ok) ((volatile int *)P.flag)[3] = 1;
-        __threadfence();
-      }
-      __syncthreads();
-      const int i = K.cs + b * 128 + tid;
-      bool trig = false;
-      if (i < K.ce) trig = finish_particle<true>(P, K, i);
-      if (__any_sync(0xffffffffu, trig) && (tid & 31) == 0) *((volatile int *)P.flag) = 1;
-      __syncthreads();
-      if (tid == 0) { __threadfence(); atomicAdd(doneB + c, 1); }
-    }
-  }
-  if (tid == 0) {  // the last block to leave re-arms the queue for the next launch
-    __threadfence();
-    if (atomicAdd(ctr + 1, 1) == (int)gridDim.x - 1) {
-      for (int k = 0; k < P.nslab; k++) { doneA[k] = 0; doneB[k] = 0; }
-      ctr[1] = 0; __threadfence(); ctr[0] = 0;
-    }
-  }
-}
-// chunk table and work queue of the wavefront, from the sorted cell keys of the owned particles (rebuild time)
-__global__ void __launch_bounds__(256) k_wave_table(int nslab, int n, const unsigned *skeys, const GridP G, int skew,
-                                                    int *chunk_start, int *grp, int *grp_start, int *meta)
-{
-  __shared__ int cs[260];
-  for (int c = threadIdx.x; c <= nslab; c += blockDim.x) {
-    int lo = 0, hi = n;  // first particle whose key is >= the slab's first key
-    if (c == nslab) lo = n;
-    else { const unsigned key = slab_key_lo(G, c); while (lo < hi) { const int mid = (lo + hi) >> 1; if (skeys[mid] < key) lo = mid + 1; else hi = mid; } }
-    cs[c] = lo; chunk_start[c] = lo;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int g = 0, acc = 0, mx = 0;
-    grp_start[0] = 0;
-    for (int t = 0; t < nslab + skew; t++) {
-      if (t < nslab) { grp[g] = t * 2; acc += (cs[t + 1] - cs[t] + 127) >> 7; grp_start[++g] = acc; mx = max(mx, cs[t + 1] - cs[t]); }
-      if (t >= skew) { const int c = t - skew; grp[g] = c * 2 + 1; acc += (cs[c + 1] - cs[c] + 127) >> 7; grp_start[++g] = acc; }
-    }
-    meta[0] = acc; meta[1] = mx; meta[2] = g;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ rebuild

@@ -64,14 +64,9 @@ struct StepP {
   double *whist;  // [sum wall dnum][cap]
   double *f, *tq; // [3][cap]
   double *fa, *ta; // [3][cap] accumulation arrays of the half-list alternative (option "half_list"), else null
-  // owner list (dem_pairs.cuh): the step runs as a wavefront over `nslab` chunks (slabs of the storage order); per-contact
-  // result records and per-particle partial sums live in rings of `ring` chunk-sized buffers (capacity ccap particles)
-  double4 *res;    // [ring][hslots][ccap][2]
-  double *part;    // [ring][6][ccap]
-  double serial;   // serial number of this step launch (stamps the result records)
-  const int *chunk_start, *grp, *grp_start;  // [nslab+1] first particle of a chunk; work groups (chunk*2 + phase) and their first item
-  int *wctr;       // [0] next item, [1] blocks that left, [8..8+256) A-phase blocks done per chunk, [264..) B-phase blocks done
-  int nslab, ring, ccap, ngrp, nitems;
+  // owner list (option owner_list, dem_pairs.cuh): per-contact result records [hslots][lcap][2], stamped with the launch serial
+  double4 *res;
+  double serial;
   const WallP *walls;
   int nwalls;
   int nwc, nwcap;     // primitive-wall candidates (compact list) and row stride of fw

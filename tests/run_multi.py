@@ -21,7 +21,8 @@ def make_engine(rank, world, local):
         buf.copy_(torch.frombuffer(bytearray(dem_b200.Engine.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(buf, 0)
     e = dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=bytes(buf.cpu().numpy().tobytes()))
-    e.option("chunk", 128)  # small beds: several chunks per brick, so that the step runs as the wavefront kernel
+    if os.environ.get("DEM_TEST_OWNER_LIST"):
+        e.option("owner_list", 1)
     return e
 
 

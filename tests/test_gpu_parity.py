@@ -8,13 +8,13 @@ import parity
 pytestmark = pytest.mark.gpu
 
 
-def gpu_engine(chunk=0, **kw):
-    """chunk: particles per chunk of the step wavefront (option `chunk`; the default of 32768 would leave the small test
-    beds in a single chunk, i.e. on the two-launch form of the step)"""
+def gpu_engine(owner_list=0, **kw):
+    """owner_list: the measured alternative of dem_pairs.cuh (every pair evaluated once by its owner, k_pairs + k_finish)
+    instead of the default full list (k_step)"""
     import dem_b200
     e = dem_b200.Engine(device=0, **kw)
-    if chunk:
-        e.option("chunk", chunk)
+    if owner_list:
+        e.option("owner_list", 1)
     return e
 
 
@@ -24,12 +24,12 @@ def tol_at(cp):
     return 1e-10 if cp <= 10 else (1e-6 if cp <= 400 else 1e-4)
 
 
-@pytest.mark.parametrize("chunk", [0, 128])
+@pytest.mark.parametrize("owner_list", [0, 1])
 @pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
-def test_engine_matches_reference_golden(name, chunk):
+def test_engine_matches_reference_golden(name, owner_list):
     c = cases.make_case(name)
     g = parity.golden(name)
-    e = cases.apply(c, gpu_engine(chunk=chunk))
+    e = cases.apply(c, gpu_engine(owner_list=owner_list))
     done = 0
     for cp in cases.GOLDEN_CASES[name]["checkpoints"]:
         cases.apply_late(c, e, cp)
@@ -49,12 +49,12 @@ def test_engine_matches_reference_golden(name, chunk):
     dict(n3=(10, 10, 10), poly=True, periodic=(1, 1, 0), model="model hertz tangential history rolling_friction epsd2"),
     dict(n3=(8, 8, 8), model="model hooke tangential history rolling_friction epsd", frozen=20, cyl=True),
 ])
-def test_engine_matches_oracle_bed(kw):
-    """~2k particle beds, 600 steps incl. rebuilds: pair set / flags bit-exact, forces to tolerance (the step runs as a
-    wavefront over chunks of ~256 particles)"""
+@pytest.mark.parametrize("owner_list", [0, 1])
+def test_engine_matches_oracle_bed(kw, owner_list):
+    """~2k particle beds, 600 steps incl. rebuilds: pair set / flags bit-exact, forces to tolerance"""
     c = cases.case_box(name="bed", seed=7, **kw)
     rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
-    got = cases.apply(c, gpu_engine(chunk=256))
+    got = cases.apply(c, gpu_engine(owner_list=owner_list))
     ref = cases.apply(c, parity.oracle_engine())
     done = 0
     for cp in (0, 1, 2, 10, 200, 600):
@@ -79,7 +79,7 @@ def test_mesh_walls_match_oracle(kind, kw):
     rows (particle, triangle) bit-exact, topology flags identical, moved mesh geometry bit-exact, forces to tolerance"""
     c = cases.case_mesh(kind=kind, name="mesh_" + kind, seed=11, **kw)
     rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
-    got = cases.apply(c, gpu_engine(chunk=128))
+    got = cases.apply(c, gpu_engine())
     ref = cases.apply(c, parity.oracle_engine())
     done = 0
     for cp in (0, 1, 10, 500, 1500, 3000):
@@ -185,10 +185,10 @@ def test_settings_changed_between_runs_match_oracle():
 
 
 def test_history_overflow_is_reported_under_check_no():
-    """forced rebuilds (`neigh_modify every 1 check no`) must not swallow the history-slot overflow of the step before the
-    rebuild: 40 small spheres just off the surface of a big one fly inwards, all 40 contacts form within a step or two --
-    more than the 16 history rows sized at the (contact-free) build -- and dem_run has to say so although every following
-    step starts with a rebuild that clears the step flags"""
+    """forced rebuilds (`neigh_modify every 2 check no`) must not swallow the history-slot overflow of the step before the
+    rebuild: 40 small spheres just off the surface of a big one fly inwards and all touch it in step 3 -- more than the 16
+    history rows sized at the (contact-free) build before step 2 -- and dem_run has to say so although step 4 starts with a
+    forced rebuild that clears the step flags"""
     import dem_b200
     c = cases.case_box(n3=(4, 4, 3), name="ovf", seed=13)
     rs, R, nshell = 0.001, 0.004, 40   # (shell radius 5 mm: clear of the side walls, all 40 gaps close in the same step)
@@ -199,10 +199,10 @@ def test_history_overflow_is_reported_under_check_no():
     u = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
     n = nshell + 1
     c.update(tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32), mask=np.ones(n, np.int32),
-             x=np.vstack([ctr, ctr + (R + rs) * 1.002 * u]), v=np.vstack([np.zeros(3), -0.5 * u]), omega=np.zeros((n, 3)),
+             x=np.vstack([ctr, ctr + (R + rs) * 1.00225 * u]), v=np.vstack([np.zeros(3), -0.5 * u]), omega=np.zeros((n, 3)),
              radius=np.concatenate([[R], np.full(nshell, rs)]), density=np.full(n, c["density"][0]))
     c["hi"][2] = max(c["hi"][2], 0.06)
-    c["neigh"] = (1, 0, False)
+    c["neigh"] = (2, 0, False)
     e = cases.apply(c, gpu_engine())
     e.setup()
     with pytest.raises(dem_b200.DemError, match="history"):
@@ -214,7 +214,7 @@ def test_engine_is_deterministic():
     c = cases.case_box(n3=(8, 8, 8), poly=True, name="det", seed=3)
     snaps = []
     for rep in range(2):
-        e = cases.apply(c, gpu_engine(chunk=128))
+        e = cases.apply(c, gpu_engine())
         e.setup(); e.run(500)
         snaps.append(cases.snapshot(e, c)); e.close()
     for k in snaps[0]:

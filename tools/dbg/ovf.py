@@ -10,10 +10,10 @@ phi = np.arccos(1.0 - 2.0 * k / nshell); th = np.pi * (1.0 + 5.0 ** 0.5) * k
 u = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
 n = nshell + 1
 c.update(tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32), mask=np.ones(n, np.int32),
-         x=np.vstack([ctr, ctr + (R + rs) * 1.002 * u]), v=np.vstack([np.zeros(3), -0.5 * u]), omega=np.zeros((n, 3)),
+         x=np.vstack([ctr, ctr + (R + rs) * 1.00225 * u]), v=np.vstack([np.zeros(3), -0.5 * u]), omega=np.zeros((n, 3)),
          radius=np.concatenate([[R], np.full(nshell, rs)]), density=np.full(n, c["density"][0]))
 c["hi"][2] = max(c["hi"][2], 0.06)
-c["neigh"] = (1, 0, False)
+c["neigh"] = (2, 0, False)
 e = cases.apply(c, dem_b200.Engine(device=0))
 e.setup()
 for s in range(12):
