@@ -38,6 +38,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,7 +49,7 @@ struct NcclApi {
     for (int k = 0; names[k] && !h; k++) h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
     if (!h) return false;
 #define NCCL_SYM(f) f = (decltype(f))dlsym(h, "nccl" #f); if (!f) return false;
-    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(Send) NCCL_SYM(Recv) NCCL_SYM(AllReduce)
+    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(Send) NCCL_SYM(Recv) NCCL_SYM(AllReduce) NCCL_SYM(AllGather)
     NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
 #undef NCCL_SYM
     return true;
@@ -229,6 +230,9 @@ struct dem_engine {
   DevBuf<int> hsig;       // [0..5] incoming halo serials per swap, [8..13] block counters of my pack kernels
   int cur0 = 0, p2p_ok = 0;
   cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
+  // step flags between ranks over peer memory (k_push / k_wait): my flag box, every rank's box, serial of the last hand-over
+  DevBuf<int> fbox; int *peer_fbox[DEM_MAXRANKS] = {nullptr}; int fbox_ready = 0, fserial = 0, fser_slot[2] = {0, 0}, fpeer[2] = {0, 0};
+  int *hflag_dev = nullptr; int fev_peer[2] = {0, 0};  // slot's flags arrive through k_wait (serial in hflag[16 + slot]) instead of memcpy + event
   int fslot = 0;                            // slot the next step writes
   const int *gate = nullptr; int gate_mask = 0;  // gate of the step being launched (nullptr: not speculative)
   // state
@@ -350,7 +354,7 @@ extern "C" void dem_destroy(dem_engine *e)
   if (e->hflag) host_small_free(e->hflag);
   for (int k = 0; k < 2; k++) if (e->fev[k]) cudaEventDestroy(e->fev[k]);
   for (auto &m : e->ipc) cudaIpcCloseMemHandle(m.ptr);
-  e->hsig.release();
+  e->hsig.release(); e->fbox.release();
   if (e->hcnt) host_small_free(e->hcnt);
   if (e->comm) {
     if (e->comm_bad || getenv("DEM_B200_NO_COMM_CACHE")) g_nccl.CommDestroy(e->comm);
@@ -1306,6 +1310,31 @@ static void halo_p2p_setup(dem_engine *E)
   CK(cudaStreamSynchronize(st));
   E->p2p_ok = E->hcnt[1];
   if (!E->p2p_ok) for (int q = 0; q < E->nswap; q++) E->swaps[q].p2p = 0;
+  if (E->p2p_ok && !E->fbox_ready && E->nranks <= DEM_MAXRANKS && !(E->opt.count("peer_flags") && E->opt["peer_flags"] == 0)) {
+    // flag boxes: every rank maps every rank's box once (the box is never reallocated).  All ranks take the same decision.
+    E->fbox.ensure(E, FBOX_INTS);
+    CK(cudaMemsetAsync(E->fbox.p, 0, FBOX_INTS * sizeof(int), st));
+    cudaIpcMemHandle_t mine; int ok = cudaIpcGetMemHandle(&mine, E->fbox.p) == cudaSuccess ? 1 : 0;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }
+    E->stage.ensure(E, 64 * (size_t)(E->nranks + 1) + 64);
+    CK(cudaMemcpyAsync(E->stage.p, &mine, 64, cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllGather(E->stage.p, E->stage.p + 64, 64, ncclChar, E->comm, st));
+    std::vector<cudaIpcMemHandle_t> all(E->nranks);
+    CK(cudaMemcpyAsync(all.data(), E->stage.p + 64, 64 * (size_t)E->nranks, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int r = 0; r < E->nranks && ok; r++) {
+      if (r == E->rank) { E->peer_fbox[r] = E->fbox.p; continue; }
+      E->peer_fbox[r] = (int *)ipc_open(E, all[r], -1 - r, 0);  // (pseudo rank: the record arrays' generation sweep never closes it)
+      if (!E->peer_fbox[r]) ok = 0;
+    }
+    E->hcnt[0] = ok;
+    CK(cudaMemcpyAsync(E->cnt_dev.p, E->hcnt, sizeof(int), cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllReduce(E->cnt_dev.p, E->cnt_dev.p + 1, 1, ncclInt, ncclMin, E->comm, st));
+    CK(cudaMemcpyAsync(E->hcnt + 1, E->cnt_dev.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    E->fbox_ready = E->hcnt[1] ? 1 : -1;  // -1: tried, not available -> NCCL all-reduce per step
+    if (E->fbox_ready == 1 && !E->hflag_dev) { void *dp = nullptr; if (cudaHostGetDevicePointer(&dp, E->hflag, 0) != cudaSuccess) { cudaGetLastError(); E->fbox_ready = -1; } E->hflag_dev = (int *)dp; }
+  }
 }
 
 // flags -> deterministic compact list; returns the number of set flags
@@ -1327,13 +1356,16 @@ static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &s
 // per-step ghost refresh == CommBrick::forward_comm (comm_brick.cpp:563-645): one pack kernel per swap; periodic
 // images on the same rank are written in place, remote ghosts travel as three NCCL send/recv pairs that land
 // directly in the ghost region of the record arrays.  Swaps run in order so that edge/corner ghosts propagate.
-static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw, bool allow_p2p = false)
+static int *flag_slot(dem_engine *E, int slot);
+static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw, bool allow_p2p = false, bool with_flags = false, int flags_slot = 0)
 {  // nsw = 1, or the two (independent) swaps of one decomposed dimension exchanged in ONE NCCL group
   cudaStream_t st = E->stream;
   const int c = E->cur;
-  if (allow_p2p && E->p2p_ok && !Ws[0].self) {  // peer-memory path (between rebuilds)
+  if (allow_p2p && E->p2p_ok && !Ws[0].self) {  // peer-memory path (between rebuilds): one push launch, one wait launch
     const bool skip = E->opt.count("debug") && ((int)E->opt["debug"] & 8);
-    const volatile int *wsig[2] = {nullptr, nullptr}; int wser[2] = {0, 0};
+    PushP Q; memset(&Q, 0, sizeof Q);
+    WaitP Wt; memset(&Wt, 0, sizeof Wt);
+    Q.nsw = nsw;
     for (int q = 0; q < nsw; q++) {
       dem_engine::Swap &W = Ws[q];
       const int qi = (int)(&W - E->swaps);
@@ -1341,16 +1373,25 @@ static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw, bool allow_p2p
       const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
       if (peer_send >= 0 && !skip) {
         const int pc = W.pcur0 ^ (c ^ E->cur0);  // the receiver's buffer parity moves in lock step with mine
-        SwapP S;
+        SwapP &S = Q.S[q];
         S.n = W.nsend; S.list = W.list.p; S.dim = W.dim; S.shift = W.shift; S.xr = E->xr[c].p; S.vm = E->vm[c].p; S.wt = E->wt[c].p;
         S.ox = W.pbase[0 + pc] + W.pgfirst; S.ov = W.pbase[2 + pc] + W.pgfirst; S.ow = W.pbase[4 + pc] + W.pgfirst;
-        if (W.nsend) k_pack_push<<<GRID(W.nsend, 256), 256, 0, st>>>(S, (unsigned *)E->hsig.p + 8 + qi, W.psig + qi, W.serial);
-        else k_halo_signal<<<1, 1, 0, st>>>(W.psig + qi, W.serial);
-        E->launches++;
+        Q.nb[q] = (int)GRID(W.nsend, 256); Q.done[q] = (unsigned *)E->hsig.p + 8 + qi; Q.sig[q] = W.psig + qi; Q.serial[q] = W.serial;
       }
-      if (peer_recv >= 0 && !skip) { wsig[q] = E->hsig.p + qi; wser[q] = W.serial; }
+      if (peer_recv >= 0 && !skip) { Wt.sig[q] = E->hsig.p + qi; Wt.serial[q] = W.serial; }
     }
-    if (wsig[0] || wsig[1]) { k_halo_wait<<<1, 1, 0, st>>>(wsig[0], wser[0], wsig[1], wser[1], E->hsig.p + 15); E->launches++; }
+    if (with_flags) {
+      E->fserial++;
+      Q.with_flags = 1; Q.myflags = flag_slot(E, flags_slot); Q.me = E->rank; Q.nranks = E->nranks; Q.slot = flags_slot; Q.fserial = E->fserial;
+      for (int r = 0; r < E->nranks; r++) Q.peer_box[r] = E->peer_fbox[r];
+      Wt.with_flags = 1; Wt.box = E->fbox.p; Wt.nranks = E->nranks; Wt.slot = flags_slot; Wt.fserial = E->fserial;
+      Wt.gate_out = flag_slot(E, flags_slot) + 4; Wt.host_out = E->hflag_dev + 4 * flags_slot; Wt.host_serial = E->hflag_dev + 16 + flags_slot;
+      E->fser_slot[flags_slot] = E->fserial;
+    }
+    Wt.timeout_flag = E->hsig.p + 15;
+    k_push<<<(unsigned)(Q.nb[0] + Q.nb[1] + 1), 256, 0, st>>>(Q);
+    k_wait<<<1, 32, 0, st>>>(Wt);
+    E->launches += 2;
     return;
   }
   size_t off[2] = {0, 0}, tot = 0;
@@ -1382,15 +1423,25 @@ static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw, bool allow_p2p
   }
   NK(g_nccl.GroupEnd());
 }
-static void forward_comm(dem_engine *E)
+static bool peer_flags(const dem_engine *E) { return E->nranks > 1 && E->p2p_ok && E->fbox_ready == 1; }
+// ghost refresh of a step; flags_slot >= 0: the step's flags (device slot flags_slot) travel with the last decomposed
+// dimension's push when the peer-memory flag boxes are in use (returns true: post_flags has nothing left to do)
+static bool forward_comm(dem_engine *E, int flags_slot = -1)
 {
   // the two swaps of a dimension never feed each other (comm_brick.cpp:899-905: the candidates of both are the atoms
   // present before the dimension starts), so they travel together; dimensions stay ordered (edge / corner ghosts)
+  int last_remote = -1;
+  for (int q = 0; q < E->nswap; q++) if (!E->swaps[q].self) last_remote = q;
+  const bool pf = flags_slot >= 0 && peer_flags(E) && last_remote >= 0;
+  bool sent = false;
   for (int q = 0; q < E->nswap;) {
     const int n = (q + 1 < E->nswap && E->swaps[q + 1].dim == E->swaps[q].dim) ? 2 : 1;
-    do_swap(E, &E->swaps[q], n, true);
+    const bool wf = pf && last_remote >= q && last_remote < q + n;
+    do_swap(E, &E->swaps[q], n, true, wf, flags_slot);
+    sent = sent || wf;
     q += n;
   }
+  return sent;
 }
 
 static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum, int hslots)
@@ -1813,8 +1864,10 @@ static void clear_flags(dem_engine *E)
   CK(cudaMemsetAsync(E->dflag.p, 0, 16 * sizeof(int), E->stream));
 }
 // after a step: reduce its flags over the ranks, start the copy to the host, mark the point with an event
-static void post_flags(dem_engine *E, int slot)
+static void post_flags(dem_engine *E, int slot, bool sent_with_halo = false)
 {
+  if (sent_with_halo) { E->fev_peer[slot] = 1; return; }  // k_push / k_wait carried the flags: gate words and host block are written by k_wait
+  E->fev_peer[slot] = 0;
   const int dbg = E->opt.count("debug") ? (int)E->opt["debug"] : 0;
   if (E->nranks > 1) {
     if (dbg & 4) CK(cudaMemcpyAsync(flag_slot(E, slot) + 4, flag_slot(E, slot), 4 * sizeof(int), cudaMemcpyDeviceToDevice, E->stream));  // profiling aid: no all-reduce
@@ -1823,6 +1876,24 @@ static void post_flags(dem_engine *E, int slot)
   CK(cudaMemcpyAsync(E->hflag + 4 * slot, gate_slot(E, slot), 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   if (!E->fev[slot]) CK(cudaEventCreateWithFlags(&E->fev[slot], cudaEventDisableTiming));
   CK(cudaEventRecord(E->fev[slot], E->stream));
+}
+
+// the host's view of a slot's flags is complete
+static void wait_flags(dem_engine *E, int slot)
+{
+  if (E->fev_peer[slot]) {  // written by k_wait into the page-locked block; the serial word arrives last
+    const volatile int *ser = (const volatile int *)E->hflag + 16 + slot;
+    const auto t0 = std::chrono::steady_clock::now();
+    long spins = 0;
+    while (*ser != E->fser_slot[slot]) {
+      if ((++spins & 0xfff) == 0) {
+        if (cudaStreamQuery(E->stream) == cudaSuccess && *ser != E->fser_slot[slot]) dem_fail(E, DEM_ERR_CUDA, "step flags did not arrive (stream idle)");
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) { E->comm_bad = 1; dem_fail(E, DEM_ERR_CUDA, "timed out waiting for the step flags of the other ranks"); }
+      }
+    }
+    return;
+  }
+  if (E->fev[slot]) CK(cudaEventSynchronize(E->fev[slot]));
 }
 
 static void collect_timing(dem_engine *E)
@@ -1897,8 +1968,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
     e->launches++;
   }
   e->cur ^= 1;
-  forward_comm(e);
-  post_flags(e, 0);
+  post_flags(e, 0, forward_comm(e, 0));
   const bool moving = e->any_moving && e->mesh_ready;
   int overflow_seen = 0;
   // one step on the device: mesh motion (fix move/mesh initial_integrate, fix_move_mesh.cpp:221-238), the fused step
@@ -1913,8 +1983,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
     }
     launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
     e->cur ^= 1;
-    forward_comm(e);
-    post_flags(e, slot);
+    post_flags(e, slot, forward_comm(e, slot));
   };
   for (long s = 1; s <= nsteps; s++) {
     e->ntimestep++;
@@ -1930,7 +1999,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
       e->gate = mask ? gate_slot(e, prev) : nullptr; e->gate_mask = mask;
       const long ev0 = e->ev_used, l0 = e->launches;
       issue_step(s, slot);
-      CK(cudaEventSynchronize(e->fev[prev]));
+      wait_flags(e, prev);
       const int *hf = e->hflag + 4 * prev;
       overflow_seen |= hf[1];
       if (((mask & 1) && hf[0]) || ((mask & 4) && hf[2])) {  // the queued step returned at its gate: undo the host side
@@ -1941,7 +2010,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
     if (rebuild_now) {
       // (forced rebuild, `check no`: the previous step's flags were not looked at above -- its history-slot overflow must
       // not be wiped by clear_flags)
-      if (e->fev[prev]) { CK(cudaEventSynchronize(e->fev[prev])); overflow_seen |= e->hflag[4 * prev + 1]; }
+      wait_flags(e, prev); overflow_seen |= e->hflag[4 * prev + 1];
       e->gate = nullptr; e->gate_mask = 0;
       if (moving) {  // the mesh moves before the lists are rebuilt
         MeshP M = mesh_params(e);
@@ -1956,8 +2025,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
       e->fslot = slot;
       launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
       e->cur ^= 1;
-      forward_comm(e);
-      post_flags(e, slot);
+      post_flags(e, slot, forward_comm(e, slot));
     }
     if (e->ev_used >= 2048) { CK(cudaStreamSynchronize(st)); collect_timing(e); }
   }

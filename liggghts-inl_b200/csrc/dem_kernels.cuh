@@ -676,6 +676,81 @@ __global__ void __launch_bounds__(256) k_pack_push(const SwapP S, unsigned *done
   if (last && threadIdx.x == 0) { *done_counter = 0; __threadfence_system(); *peer_signal = serial; }
 }
 __global__ void k_halo_signal(volatile int *peer_signal, int serial) { *peer_signal = serial; }  // empty send list
+
+// ---- one launch per decomposed dimension and step: both ghost pushes of the dimension and -- in the same launch -- the
+// hand-over of this rank's step flags to EVERY rank.  The reference reduces the rebuild decision with MPI_Allreduce
+// (neighbor.cpp:1463); here each rank stores its four flag words into its column of every peer's flag box over NVLink peer
+// memory and publishes a serial number; k_wait (below) ORs the columns.  No NCCL call between two rebuilds.
+#define DEM_MAXRANKS 16
+#define FBOX_SERIAL (2 * DEM_MAXRANKS * 4)   // int offset of the serial words in a flag box: [2 slots][DEM_MAXRANKS][4] flags, then [DEM_MAXRANKS] serials
+#define FBOX_INTS (FBOX_SERIAL + DEM_MAXRANKS)
+struct PushP {
+  SwapP S[2]; int nb[2]; unsigned *done[2]; volatile int *sig[2]; int serial[2]; int nsw;
+  const int *myflags; int *peer_box[DEM_MAXRANKS]; int me, nranks, slot, fserial, with_flags;
+};
+__global__ void __launch_bounds__(256) k_push(const PushP Q)
+{
+  int b = blockIdx.x;
+  if (b == (int)gridDim.x - 1) {  // last block: flags to all ranks, and the signal of an empty send list
+    const int r = threadIdx.x;
+    if (Q.with_flags && r < Q.nranks) {
+      int *box = Q.peer_box[r];
+#pragma unroll
+      for (int k = 0; k < 4; k++) box[(Q.slot * DEM_MAXRANKS + Q.me) * 4 + k] = Q.myflags[k];
+      __threadfence_system();
+      ((volatile int *)box)[FBOX_SERIAL + Q.me] = Q.fserial;
+    }
+    if (r >= 32 && r < 32 + Q.nsw && Q.sig[r - 32] && Q.S[r - 32].n == 0) *Q.sig[r - 32] = Q.serial[r - 32];
+    return;
+  }
+  int q = 0;
+  if (b >= Q.nb[0]) { q = 1; b -= Q.nb[0]; }
+  const SwapP &S = Q.S[q];
+  const int e = b * blockDim.x + threadIdx.x;
+  if (e < S.n) {
+    const int s = S.list[e];
+    double4 x = S.xr[s];
+    if (S.dim == 0) x.x += S.shift; else if (S.dim == 1) x.y += S.shift; else x.z += S.shift;
+    st4(S.ox + e, x); st4(S.ov + e, S.vm[s]); st4(S.ow + e, S.wt[s]);
+  }
+  __threadfence_system();  // my peer stores are performed before my block is counted
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(Q.done[q], 1u) == (unsigned)Q.nb[q] - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) { *Q.done[q] = 0; __threadfence_system(); *Q.sig[q] = Q.serial[q]; }
+}
+// receiver side: the ghosts of both swaps have arrived, every rank's flags of this step have arrived; their OR goes to the
+// gate words of the next step (device) and, with the serial, to the host's page-locked flag block
+struct WaitP {
+  const volatile int *sig[2]; int serial[2];
+  const int *box; int nranks, slot, fserial, with_flags;
+  int *gate_out; int *host_out; volatile int *host_serial; int *timeout_flag;
+};
+__global__ void k_wait(const WaitP Q)
+{  // one warp; every wait is bounded (~4 s): a lost peer must not hang the device
+  const int t = threadIdx.x;
+  const long long t0 = clock64(), limit = 8000000000LL;
+  bool ok = true;
+  if (t < 2 && Q.sig[t]) while (*Q.sig[t] < Q.serial[t]) { __nanosleep(64); if (clock64() - t0 > limit) { ok = false; break; } }
+  if (Q.with_flags && t < Q.nranks) {
+    const volatile int *ser = (const volatile int *)Q.box + FBOX_SERIAL + t;
+    while (*ser < Q.fserial) { __nanosleep(64); if (clock64() - t0 > limit) { ok = false; break; } }
+  }
+  if (!ok) *Q.timeout_flag = 1;
+  __syncwarp();
+  __threadfence_system();
+  if (Q.with_flags) {
+    if (t < 4) {
+      int v = 0;
+      for (int r = 0; r < Q.nranks; r++) v = max(v, ((const volatile int *)Q.box)[(Q.slot * DEM_MAXRANKS + r) * 4 + t]);
+      Q.gate_out[t] = v; Q.host_out[t] = v;
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (t == 0) *Q.host_serial = Q.fserial;
+  }
+}
 __global__ void k_halo_wait(const volatile int *sig_a, int serial_a, const volatile int *sig_b, int serial_b, int *timeout_flag)
 {  // bounded (~4 s): a lost peer must not hang the device
   const long long t0 = clock64();
