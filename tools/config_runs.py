@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""Scale runs of the other BASELINE.json configs through the C ABI (supplementary to bench.py, which measures configs[1]):
+"""Throughput of the other BASELINE.json configs at their named sizes through the C ABI (supplementary to bench.py, which
+measures configs[1]); the beds are those of tests/configs.py, i.e. the ones whose first steps are checked against digests
+of the unmodified reference (tests/test_gpu_configs.py):
   C1  10,648 monodisperse spheres settling in a box of primitive planes (hertz/history/cdt)
-  C3  1,000,000 spheres falling into triangle-mesh geometry (box of 2 x 40 x 40 floor triangles + walls, 128-segment
-      funnel = 256 triangles), hertz/history/cdt on `fix wall/gran ... mesh`
-  C4  499,200 bonded spheres (INL bond/nonlinear, bonds created at step 2), hertz/history
-  C5brick  2,252,800 spheres in a rotating 256-segment drum (`fix move/mesh rotate`): one GPU's share of configs[4]
-Each prints one JSON line: particle-steps/s over the timed window, list/contact statistics, rebuilds, and sanity checks
-(no particle lost, finite state).  usage (GPU box): python tools/config_runs.py [C1 C3 C4]"""
+  C3  1,013,189 spheres in a conical hopper STL (16,384 triangles), outlet open: discharge (~50 k particle-triangle rows)
+  C4  499,200 bonded spheres (INL bond/nonlinear, 2.45 M bonds created at step 2) compressed by a moving stress plate
+  C5  2,067,792 spheres in a rotating drum (1,024 triangles): one GPU's share of the 16.8 M-sphere drum of configs[4]
+Each prints one JSON line: particle-steps/s over the timed window (rebuilds included), list/contact statistics, rebuilds,
+mesh contact rows and sanity checks (no particle lost, finite state).  usage (GPU box): python tools/config_runs.py [C1 C3 C4 C5]"""
 import json
 import os
 import sys
@@ -20,28 +21,15 @@ import dem_b200  # noqa: E402
 
 
 def make(name):
-    if name == "C1":
-        return cases.case_box(n3=(22, 22, 22), name="C1"), 20, 2000
-    if name == "C3":
-        c = cases.case_mesh(kind="funnel", n3=(100, 100, 100), name="C3", poly=True)
-        L = c["hi"][0] / 1.25
-        H = c["hi"][2]
-        c["meshes"] = [("cad", 1, cases.mesh_box(L, 0.9 * H, nf=40)), ("fun", 1, cases.mesh_funnel(L, 0.55 * L, 0.2 * L, 0.62 * L, 0.12 * L, nseg=128))]
-        return c, 20, 300
-    if name == "C4":
-        return cases.case_box(n3=(80, 80, 78), model="model hertz tangential history", poly=True, name="C4", bond=dict(kind="bond/nonlinear")), 10, 200
-    if name == "C5brick":  # one GPU's share of the 16M-sphere drum of configs[4]: 2.25M spheres in a rotating 256-segment drum
-        c = cases.case_mesh(kind="drum", n3=(160, 160, 88), name="C5brick", poly=True, move=2.0)
-        L = 160 * 2.05 * 0.003
-        c["x"][:, 2] += 0.62 * L - 0.5 * (c["x"][:, 2].min() + c["x"][:, 2].max())  # bed centred on the drum axis
-        c["meshes"] = [("drum", 1, cases.mesh_drum(0.5 * L, 0.62 * L, 0.62 * L, -0.12 * L, 1.12 * L, nseg=256))]
-        return c, 20, 300
-    raise SystemExit("unknown config " + name)
+    import configs
+    c = configs.CONFIGS[name]()
+    warm, steps = {"C1": (200, 2000), "C3": (200, 1000), "C4": (20, 300), "C5": (200, 1000)}[name]
+    return c, warm, steps
 
 
 def main():
     import torch
-    for name in (sys.argv[1:] or ["C1", "C3", "C4"]):
+    for name in (sys.argv[1:] or ["C1", "C3", "C4", "C5"]):
         c, warm, steps = make(name)
         n = len(c["tag"])
         eng = cases.apply(c, dem_b200.Engine(device=0))
@@ -64,6 +52,8 @@ def main():
         if "cohesion" in c["pair"]:
             p = eng.pairs()
             out["bonds"] = int((p["hist"][:, 0] > 0).sum())
+        for mid in c.get("mesh_stress", []):
+            out["force_on_" + mid] = [float(v) for v in eng.mesh_force(mid)[:3]]
         print(json.dumps(out), flush=True)
         eng.close()
 
