@@ -24,13 +24,13 @@ def _cubic(lo, hi, pitch):
     return g
 
 
-def _finish(c, x, rad, rho=2500.0, v=None, jitter=0.0):
+def _finish(c, x, rad, rho=2500.0, v=None, jitter=0.0, seed=None):
     n = len(x)
     if jitter:
         # a perfect lattice puts every interior sphere in exact force balance: its net force would be rounding noise of
         # contact forces ~50 weights and no relative tolerance could hold.  A seeded jitter of a thousandth of a radius
         # leaves net forces that are small against the contact forces but far above their rounding noise.
-        x = x + np.random.default_rng(cases.SEED).uniform(-jitter, jitter, x.shape)
+        x = x + np.random.default_rng(cases.SEED if seed is None else seed).uniform(-jitter, jitter, x.shape)
     c.update(tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32), mask=np.ones(n, np.int32), x=np.ascontiguousarray(x),
              v=np.zeros((n, 3)) if v is None else v, omega=np.zeros((n, 3)), radius=np.full(n, rad), density=np.full(n, rho))
     return c
@@ -64,9 +64,10 @@ def mesh_hopper(cx, cy, Rc, Ro, zc, ztop, nseg, nz_cone, nz_cyl):
     return np.asarray(t, np.float64)
 
 
-def C3(scale=1.0, nseg=None):
+def C3(scale=1.0, nseg=None, seed=None):
     """configs[2]: hopper discharge.  scale 1 -> ~1.0 M spheres of r = 2 mm filling a hopper of radius 0.2 m (cone half
-    angle 30 deg, outlet radius 40 mm, ~16 k triangles); the outlet is open, the column above it starts to fall at once"""
+    angle 30 deg, outlet radius 40 mm, ~16 k triangles); the outlet is open, the column above it starts to fall at once into
+    a catch box of primitive planes below the hopper (a sphere that left a non-periodic box would be lost)"""
     rad = 0.002
     pitch = 1.995 * rad
     s = scale ** (1.0 / 3.0)
@@ -104,7 +105,11 @@ def C3(scale=1.0, nseg=None):
         shell.append(np.stack([cx + rr_c * np.cos(a), cy + rr_c * np.sin(a), np.full(m, zr)], 1))
     shell = np.concatenate(shell)
     shell = shell[shell[:, 2] >= 0.6 * rad]
-    _finish(c, np.concatenate([g[inside], shell]), rad, jitter=0.001 * rad)
+    _finish(c, np.concatenate([g[inside], shell]), rad, jitter=0.001 * rad, seed=seed)
+    zf = c["lo"][2] + 0.005
+    c["walls"] = [("catch", HERTZ_CDT + " primitive type 1 zplane %.17g" % zf), ("cx0", HERTZ_CDT + " primitive type 1 xplane 0.001"),
+                  ("cx1", HERTZ_CDT + " primitive type 1 xplane %.17g" % (2 * cx - 0.001)), ("cy0", HERTZ_CDT + " primitive type 1 yplane 0.001"),
+                  ("cy1", HERTZ_CDT + " primitive type 1 yplane %.17g" % (2 * cx - 0.001))]
     c["meshes"] = [("hopper", 1, mesh)]
     c["mesh_walls"] = [("mw", HERTZ_CDT + " mesh n_meshes 1 meshes hopper")]
     return c
