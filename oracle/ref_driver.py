@@ -20,8 +20,10 @@ def available():
 
 
 class Ref:
-    def __init__(self, log=None):
-        self.lib = C.CDLL(LIB)
+    def __init__(self, log=None, lib=None, extra_args=()):
+        """lib / extra_args: another build of the reference tree and more command-line switches (the `-suffix b200` shim
+        builds of integration/Makefile)"""
+        self.lib = C.CDLL(lib or LIB)
         L = self.lib
         L.lammps_open_no_mpi.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
         L.lammps_close.argtypes = [C.c_void_p]
@@ -38,7 +40,7 @@ class Ref:
         L.ref_ntimestep.restype = C.c_long
         L.ref_pairlist_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ref_pairlist_dump.argtypes = [C.c_void_p] + [C.c_void_p] * 6
-        args = [b"liggghts", b"-screen", b"/dev/null", b"-log", (log or "none").encode(), b"-echo", b"none"]
+        args = [b"liggghts", b"-screen", b"/dev/null", b"-log", (log or "none").encode(), b"-echo", b"none"] + [a.encode() for a in extra_args]
         argv = (C.c_char_p * len(args))(*args)
         self.h = C.c_void_p()
         L.lammps_open_no_mpi(len(args), argv, C.byref(self.h))

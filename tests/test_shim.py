@@ -1,0 +1,63 @@
+"""The `-suffix b200` binding inside the reference tree (integration/b200_shim.{h,cpp}, built by integration/Makefile into
+oracle/_ref/): an UNMODIFIED input deck, run by the reference binary with `-suffix b200`, hands its timestep loop to the
+engine through the C ABI's input-script front end and must reproduce the plain reference run.
+  CPU (not gpu): the shim bound to the CPU oracle's orc_* entry points (libliggghts_ref_orc.so) -- covers the binding itself;
+  GPU: the shim bound to libdem_b200.so (libliggghts_ref_b200.so)."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+WORKER = r'''
+import sys, os, tempfile
+sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/oracle"); sys.path.insert(0, sys.argv[1] + "/liggghts-inl_b200")
+import numpy as np, cases, ref_driver
+name, lib, out = sys.argv[2], sys.argv[3], sys.argv[4]
+c = cases.make_case(name)
+tmp = tempfile.mkdtemp(); os.chdir(tmp)
+deck, data = cases.to_deck(c, os.path.join(tmp, "case.data")); open(os.path.join(tmp, "case.data"), "w").write(data)
+r = ref_driver.Ref(lib=lib, extra_args=["-suffix", "b200"]) if lib != "plain" else ref_driver.Ref()
+r.cmd(deck)
+done = 0
+for cp in (1, 200, 500):   # three `run` commands: the engine lives across them
+    for line in cases.late_commands(c, cp): r.cmd(line)
+    r.cmd("run %d" % (cp - done)); done = cp
+a = r.atoms()
+np.savez(out, **{k: a[k] for k in ("x", "v", "f", "omega", "torque")})
+'''
+
+
+def run_ref(name, lib, tmp_path):
+    """one reference process per run: the reference keeps global registries (and exit()s on errors)"""
+    out = str(tmp_path / ("%s_%s.npz" % (name, os.path.basename(lib))))
+    r = subprocess.run([sys.executable, "-c", WORKER, ROOT, name, lib, out], capture_output=True, text=True, timeout=600)
+    assert os.path.exists(out), "reference run failed: " + r.stdout[-1500:] + r.stderr[-1500:]
+    return np.load(out)
+
+
+def check(name, lib, tmp_path):
+    a, b = run_ref(name, "plain", tmp_path), run_ref(name, lib, tmp_path)
+    for k in a.files:
+        scale = max(np.abs(a[k]).max(), 1e-300)
+        assert np.abs(a[k] - b[k]).max() <= 1e-6 * scale, "%s: %s differs by %.2e of its scale" % (name, k, np.abs(a[k] - b[k]).max() / scale)
+
+
+@pytest.mark.parametrize("name", ["box_hertz_cdt", "mesh_plate_late_move", "poly_hooke_epsd_cyl"])
+def test_suffix_b200_deck_on_oracle_binding(name, tmp_path):
+    lib = os.path.join(REFDIR, "libliggghts_ref_orc.so")
+    if not (os.path.exists(lib) and os.path.exists(os.path.join(REFDIR, "libliggghts_ref.so"))):
+        pytest.skip("the shim build of the reference tree is not here (make -C integration orc)")
+    check(name, lib, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["box_hertz_cdt", "mesh_plate_late_move", "mesh_drum_rotating", "periodic_epsd2"])
+def test_suffix_b200_deck_on_gpu_engine(name, tmp_path):
+    lib = os.path.join(REFDIR, "libliggghts_ref_b200.so")
+    if not (os.path.exists(lib) and os.path.exists(os.path.join(REFDIR, "libliggghts_ref.so"))):
+        pytest.skip("the shim build of the reference tree is not here (make -C integration)")
+    check(name, lib, tmp_path)
