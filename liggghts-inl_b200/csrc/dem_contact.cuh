@@ -350,6 +350,150 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
 
 
 // ---------------------------------------------------------------------------------------------
+// fp32 mode (option `fp32`; BASELINE.json north_star: forces within 1e-5 of the fp64 reference): the same chain with the
+// contact LAW in single precision.  What stays in fp64: the particle state, the separation r, the unit normal and the
+// overlap radsum - r (the subtraction cancels seven to eight digits -- an overlap formed in fp32 would carry a relative
+// error of ~3e-5 and the Hertz force 1.5 times that), relative velocities (formed in fp64, then rounded), the force / torque
+// sums and the integration.  History values are advanced in fp32 and stored as doubles.  Like pair_chain the expressions are
+// exactly (anti)symmetric under exchange of the bodies, so the two owners of a pair still produce mirror images.
+__device__ __forceinline__ float rsqrt_f32(float x)
+{
+  const float y = rsqrtf(x);
+  return x > 0.f ? y * (1.5f - 0.5f * x * y * y) : 0.f;
+}
+template <int NORMAL, int ROLLING, bool ONE>
+__device__ __forceinline__ void pair_chain_f32(const StepP &P, const ModelP &M, const double4 &xi, const double4 &vi, const double4 &wi,
+                                               const double4 &xj, const double4 &vj, const double4 &wj, int itype, int jtype,
+                                               int imask, int jmask, double dx, double dy, double dz, double rsq,
+                                               double (&shear)[3], double (&ch)[3], bool shearupdate, double *F, double *T, double *Tp)
+{
+  const int tij = itype * P.nt1 + jtype;
+  double r, rinv;
+  sqrt_rsqrt_fast(rsq, r, rinv);
+  const float enx = (float)(dx * rinv), eny = (float)(dy * rinv), enz = (float)(dz * rinv);
+  const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz, frinv = (float)rinv;
+  const float radi = (float)xi.w, radj = (float)xj.w, mi = (float)vi.w, mj = (float)vj.w;
+  const float deltan = (float)((xi.w + xj.w) - r);
+  const float dt = (float)P.dt;
+  const float vr1 = (float)(vi.x - vj.x), vr2 = (float)(vi.y - vj.y), vr3 = (float)(vi.z - vj.z);
+  const float vn = vr1 * enx + vr2 * eny + vr3 * enz;
+  const float vt1 = vr1 - vn * enx, vt2 = vr2 - vn * eny, vt3 = vr3 - vn * enz;
+  const float cri = radi - 0.5f * deltan, crj = radj - 0.5f * deltan;
+  const float wix = (float)wi.x, wiy = (float)wi.y, wiz = (float)wi.z, wjx = (float)wj.x, wjy = (float)wj.y, wjz = (float)wj.z;
+  const float wr1 = __fadd_rn(__fmul_rn(cri, wix), __fmul_rn(crj, wjx)) * frinv;
+  const float wr2 = __fadd_rn(__fmul_rn(cri, wiy), __fmul_rn(crj, wjy)) * frinv;
+  const float wr3 = __fadd_rn(__fmul_rn(cri, wiz), __fmul_rn(crj, wjz)) * frinv;
+  const float vtr1 = vt1 - (fdz * wr2 - fdy * wr3);
+  const float vtr2 = vt2 - (fdx * wr3 - fdz * wr1);
+  const float vtr3 = vt3 - (fdy * wr1 - fdx * wr2);
+  const float reff = radi * radj / (radi + radj);
+  float meff = mi * mj / (mi + mj);
+  if (imask & P.freezebit) meff = mj;
+  if (jmask & P.freezebit) meff = mi;
+  const float nk = (float)P.nktv2p;
+  float kn, kt, inv_kt, gamman, gammat;
+  if (NORMAL == N_HERTZ) {
+    const float Y = (float)tabp<ONE>(P, T_YEFF, tij), G = (float)tabp<ONE>(P, T_GEFF, tij), beta = (float)tabp<ONE>(P, T_BETA, tij);
+    const float rd = reff * deltan;
+    const float inv_s = rsqrt_f32(rd), s = rd * inv_s;
+    const float q = sqrtf(s * meff);
+    kn = 4.f / 3.f * Y * s; kt = 8.f * G * s;
+    inv_kt = (float)tabp<ONE>(P, T_INV8G, tij) * inv_s;
+    const float c2 = -2.f * 0.912870929175276855761616f * beta * q;
+    gamman = c2 * (float)tabp<ONE>(P, T_SQ2Y, tij);
+    gammat = M.tdamp ? c2 * (float)tabp<ONE>(P, T_SQ8G, tij) : 0.f;
+  } else {
+    const float Y = (float)tabp<ONE>(P, T_YEFF, tij), lg = (float)tabp<ONE>(P, T_CORLOG, tij);
+    const float sqrtval = sqrtf(reff), cv = (float)P.charVel;
+    kn = 16.f / 15.f * sqrtval * Y * powf(15.f * meff * cv * cv / (16.f * sqrtval * Y), 0.2f);
+    kt = kn;
+    if (M.ktToKn) kt *= 0.285714286f;
+    const float lgsq = lg * lg;
+    gamman = sqrtf(4.f * meff * kn * lgsq / (lgsq + 9.86960440108935861883f));
+    gammat = M.tdamp ? gamman : 0.f;
+    inv_kt = nk / kt;
+  }
+  if (P.nktv2p != 1.0) { kn /= nk; kt /= nk; if (NORMAL == N_HERTZ) inv_kt *= nk; }
+  float Fn = -gamman * vn + kn * deltan;
+  if (M.limitForce && Fn < 0.f) Fn = 0.f;
+  float F1 = Fn * enx, F2 = Fn * eny, F3 = Fn * enz;
+  float T1 = 0.f, T2 = 0.f, T3 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f;
+  if (M.tangential) {
+    float s0 = (float)shear[0], s1 = (float)shear[1], s2 = (float)shear[2];
+    if (shearupdate) {
+      s0 += vtr1 * dt; s1 += vtr2 * dt; s2 += vtr3 * dt;
+      const float rsht = s0 * enx + s1 * eny + s2 * enz;
+      s0 -= rsht * enx; s1 -= rsht * eny; s2 -= rsht * enz;
+    }
+    const float ssq = s0 * s0 + s1 * s1 + s2 * s2;
+    const float inv_shr = rsqrt_f32(ssq), shrmag = ssq * inv_shr;
+    const float xmu = (float)tabp<ONE>(P, T_MU, tij);
+    float Ft1 = -(kt * s0), Ft2 = -(kt * s1), Ft3 = -(kt * s2);
+    const float Ft_shear = kt * shrmag, Ft_friction = xmu * fabsf(Fn);
+    if (Ft_shear > Ft_friction) {
+      if (shrmag != 0.f) {
+        const float ratio = Ft_friction * (inv_kt * inv_shr);
+        Ft1 *= ratio; Ft2 *= ratio; Ft3 *= ratio;
+        if (shearupdate) { s0 = -Ft1 * inv_kt; s1 = -Ft2 * inv_kt; s2 = -Ft3 * inv_kt; }
+      } else Ft1 = Ft2 = Ft3 = 0.f;
+    } else {
+      Ft1 -= gammat * vtr1; Ft2 -= gammat * vtr2; Ft3 -= gammat * vtr3;
+    }
+    if (shearupdate) { shear[0] = s0; shear[1] = s1; shear[2] = s2; }
+    F1 += Ft1; F2 += Ft2; F3 += Ft3;
+    const float c1 = eny * Ft3 - enz * Ft2, c2 = enz * Ft1 - enx * Ft3, c3 = enx * Ft2 - eny * Ft1;
+    T1 = -cri * c1; T2 = -cri * c2; T3 = -cri * c3;
+    if (Tp) { P1 = -crj * c1; P2 = -crj * c2; P3 = -crj * c3; }
+  }
+  if (ROLLING != R_OFF) {
+    const float a1 = (float)(wi.x - wj.x), a2 = (float)(wi.y - wj.y), a3 = (float)(wi.z - wj.z);
+    const float rmu = (float)tabp<ONE>(P, T_RMU, tij);
+    if (ROLLING == R_CDT) {
+      const float asq = a1 * a1 + a2 * a2 + a3 * a3;
+      if (asq > 0.f) {
+        const float sc = rmu * kn * deltan * reff * rsqrt_f32(asq);
+        float r1 = a1 * sc, r2 = a2 * sc, r3 = a3 * sc;
+        if (!M.torsion) {
+          const float dot = r1 * enx + r2 * eny + r3 * enz;
+          r1 -= enx * dot; r2 -= eny * dot; r3 -= enz * dot;
+        }
+        T1 -= r1; T2 -= r2; T3 -= r3;
+        P1 += r1; P2 += r2; P3 += r3;
+      }
+    } else {
+      float w1 = a1, w2 = a2, w3 = a3;
+      if (!M.torsion) {
+        const float dot = a1 * enx + a2 * eny + a3 * enz;
+        w1 = a1 - enx * dot; w2 = a2 - eny * dot; w3 = a3 - enz * dot;
+      }
+      const float kr = (ROLLING == R_EPSD2) ? kt * reff * reff : 2.25f * kn * rmu * rmu * reff * reff;
+      float r1 = (float)ch[0] + w1 * (dt * kr), r2 = (float)ch[1] + w2 * (dt * kr), r3 = (float)ch[2] + w3 * (dt * kr);
+      const float msq = r1 * r1 + r2 * r2 + r3 * r3;
+      const float inv_mag = rsqrt_f32(msq), mag = msq * inv_mag;
+      const float tmax = fabsf(Fn) * reff * rmu;
+      if (mag > tmax) {
+        const float factor = tmax * inv_mag;
+        r1 *= factor; r2 *= factor; r3 *= factor;
+        if (shearupdate) { ch[0] = r1; ch[1] = r2; ch[2] = r3; }
+      } else {
+        if (shearupdate) { ch[0] = r1; ch[1] = r2; ch[2] = r3; }
+        if (ROLLING == R_EPSD) {
+          const float ri = mi * radi * radi, rj = mj * radj * radj;
+          const float r_inertia = 1.4f * ri * rj / (ri + rj);
+          const float r_coef = (float)tabp<ONE>(P, T_RVISC, tij) * 2.f * sqrtf(r_inertia * kr);
+          r1 += r_coef * w1; r2 += r_coef * w2; r3 += r_coef * w3;
+        }
+      }
+      T1 -= r1; T2 -= r2; T3 -= r3;
+      P1 += r1; P2 += r2; P3 += r3;
+    }
+  }
+  F[0] += (double)F1; F[1] += (double)F2; F[2] += (double)F3;
+  T[0] += (double)T1; T[1] += (double)T2; T[2] += (double)T3;
+  if (Tp) { Tp[0] += (double)P1; Tp[1] += (double)P2; Tp[2] += (double)P3; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bonded-sphere models, sphere-sphere branch:
 //   cohesion bond            cohesion_model_bond.h:491-950 (createBond :1015-1034, breakBond :1036-1070)
 //   cohesion bond/nonlinear  cohesion_model_bond_nonlinear.h:394-940 (:958-995)

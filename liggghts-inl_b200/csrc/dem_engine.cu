@@ -212,7 +212,6 @@ struct dem_engine {
   DevBuf<double4> res;  // owner list: per-contact result records
   long serial = 0;      // step launches so far (stamps the result records)
   DevBuf<int> overflow;
-  DevBuf<double> fa, ta;  // accumulation arrays of the half-list alternative (option "half_list")
   DevBuf<unsigned long long> counters;
   int *hflag = nullptr;  // mapped pinned flags: [0] rebuild trigger, [1] history overflow, [2] moving-mesh trigger
   // triangle-mesh walls (dem_mesh.h)
@@ -347,7 +346,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
-  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->fa.release(); e->ta.release(); e->res.release();
+  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->res.release();
   e->dmforce.release(); e->dmpref.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
@@ -1673,7 +1672,10 @@ static void rebuild(dem_engine *E)
   // full list (k_step, k_step_bond) unless option owner_list asks for the measured alternative of dem_pairs.cuh
   const int fmt = (E->have_pair && !E->pm.cohesion && E->opt.count("owner_list") && E->opt["owner_list"] != 0) ? 1 : 0;
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
-  int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : (fmt ? 12 : 16)));
+  // history rows: by default one per row entry (a particle can never gain more contacts between two rebuilds than it has
+  // list entries, so the step kernels cannot run out of rows and drop a contact's history; rows that are not in use cost
+  // address space, not traffic).  Option histslots lowers it for memory-tight runs; an overflow is then reported by dem_run.
+  int hslots = std::max(Lold.valid ? Lold.hslots : 0, (int)(E->opt.count("histslots") ? E->opt["histslots"] : std::min(maxk, NBR_MAXSLOTS)));
   for (int attempt = 0; attempt < 6; attempt++) {
     ensure_list(E, Lnew, E->cap, maxk, dnum, hslots);
     Lnew.fmt = fmt; Lnew.nlocal = n;
@@ -1698,8 +1700,8 @@ static void rebuild(dem_engine *E)
     CK(cudaStreamSynchronize(st));
     if (ov[0] == 0 && ov[1] == 0) break;
     if (attempt == 5) dem_fail(E, DEM_ERR_OVERFLOW, "neighbour list overflow (%d neighbours, %d history partners)", ov[0], ov[1]);
-    if (ov[0]) maxk = ov[0] + 4;
-    if (ov[1]) hslots = ov[1] + 12;
+    if (ov[0]) { maxk = ov[0] + 4; if (!E->opt.count("histslots")) hslots = std::max(hslots, std::min(maxk, NBR_MAXSLOTS)); }
+    if (ov[1]) hslots = std::max(hslots, ov[1] + 12);
     if (maxk > (fmt ? NN2_MAXK : 0xffff) || hslots > NBR_MAXSLOTS) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d neighbours / %d history partners", ov[0], ov[1]);
   }
   if (fmt && E->res.n < (size_t)Lnew.hslots * 2 * Lnew.cap) { E->res.release(); E->res.ensure(E, (size_t)Lnew.hslots * 2 * Lnew.cap); }
@@ -1785,11 +1787,9 @@ static void launch_pairs_t(dem_engine *E, const StepP &P)
 template <int N, int R>
 static void launch_step_t(dem_engine *E, const StepP &P)
 {
-  if (P.fa) {  // measured half-list alternative (option "half_list"): pair kernel with fp64 reductions + integration kernel
+  if (E->opt.count("fp32") && E->opt["fp32"] != 0) {  // fp32 mode: contact law in single precision (dem_contact.cuh pair_chain_f32)
     if (E->ntypes == 1) k_step<N, R, true, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
     else k_step<N, R, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
-    k_integrate_half<<<GRID(P.nlocal, 256), 256, 0, E->stream>>>(P);
-    E->launches++;
     return;
   }
   if (E->ntypes == 1) k_step<N, R, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
@@ -1803,14 +1803,6 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (tm) {
     if ((long)E->ev.size() < 2 * (E->ev_used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); E->ev.push_back(a); E->ev.push_back(b); }
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
-  }
-  if (E->have_pair && !E->pm.cohesion && E->nranks == 1 && E->opt.count("half_list") && E->opt["half_list"] != 0) {
-    if (E->fa.n < 3 * (size_t)E->cap) {
-      E->fa.release(); E->ta.release(); E->fa.ensure(E, 3 * (size_t)E->cap); E->ta.ensure(E, 3 * (size_t)E->cap);
-      CK(cudaMemsetAsync(E->fa.p, 0, 3 * (size_t)E->cap * sizeof(double), E->stream));
-      CK(cudaMemsetAsync(E->ta.p, 0, 3 * (size_t)E->cap * sizeof(double), E->stream));
-    }
-    P.fa = E->fa.p; P.ta = E->ta.p;
   }
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
   if (have_mesh_walls(E) && E->mesh_ready && E->any_stress) CK(cudaMemsetAsync(E->dmforce.p, 0, 6 * DEM_MAXMESH * sizeof(double), E->stream));  // MeshModuleStress::pre_force

@@ -184,11 +184,10 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 // records are stored in the canonical orientation "lower tag first" (sign flipped on load/store when the partner is the
 // first body).  nh = the particle's count of history slots in use (a shared-memory counter: in the cooperative phase
 // another lane may be serving the particle).
-template <int NORMAL, int ROLLING, bool ONE, bool HALF = false>
+template <int NORMAL, int ROLLING, bool ONE, bool F32 = false>
 __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
                                              const double4 &wi, bool su, int *nh, double *F, double *T)
-{  // HALF (the measured half-list alternative, k_step_half): the pair is evaluated once; the partner's share goes to the
-   // accumulation arrays P.fa / P.ta with fp64 reductions (RED.E.ADD.F64), unless the partner is a ghost
+{  // F32: the contact law in single precision (option fp32, see pair_chain_f32)
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   const int j = (int)(w & NBR_IDX);
   int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
@@ -204,17 +203,10 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
-  if (HALF) {
-    double Fp[3] = {0., 0., 0.}, Tm[3] = {0., 0., 0.}, Tp[3] = {0., 0., 0.};
-    pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, Fp, Tm, Tp);
-#pragma unroll
-    for (int d = 0; d < 3; d++) { F[d] += Fp[d]; T[d] += Tm[d]; }
-    if (j < P.nlocal) {
-#pragma unroll
-      for (int d = 0; d < 3; d++) { atomicAdd(P.fa + (size_t)d * P.cap + j, -Fp[d]); atomicAdd(P.ta + (size_t)d * P.cap + j, Tp[d]); }
-    }
-  } else
-  pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
+  if (F32)
+    pair_chain_f32<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T, nullptr);
+  else
+    pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
   if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
     const int s = atomicAdd(nh, 1);
     if (s < P.hslots) {
@@ -305,12 +297,9 @@ __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const doubl
 // Alternatives that were built, found parity-green and measured slower on the 4.19M bed (git history):
 // partner records from shared memory, one evaluation per in-warp pair, a separate sweep kernel, a software-pipelined
 // contact phase.
-template <int NORMAL, int ROLLING, bool ONE, bool HALF = false>
+template <int NORMAL, int ROLLING, bool ONE, bool F32 = false>
 __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
-{  // HALF = the measured half-list alternative (option "half_list"): only the entries whose partner has
-   // a higher index (or is a ghost) are evaluated, the partner's share travels by fp64 reductions, the owner's sum joins it in
-   // P.fa / P.ta, and k_integrate_half finishes the step.  The mirror copy of a pair's history is NOT maintained: valid
-   // between two rebuilds only -- a measurement vehicle, not a production path.
+{  // F32: option fp32 -- the contact law in single precision (pair_chain_f32); state, geometry, sums and integration stay fp64
   __shared__ unsigned s_w[DEM_CMAX][128];
   __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
   __shared__ double s_res[6][4 * 32 * DEM_RWIN];  // per warp: force / torque of the items of the current window
@@ -357,7 +346,6 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         const double rsq = sq3_rn(xi.x - xv[u].x, xi.y - xv[u].y, xi.z - xv[u].z);
         const double radsum = xi.w + xv[u].w;
         bool t = (k0 + u < nn) && rsq < __dmul_rn(radsum, radsum);
-        if (HALF) t = t && ((int)(wv[u] & NBR_IDX) > i || (int)(wv[u] & NBR_IDX) >= P.nlocal);
         touch |= (unsigned)t << u;
         if (P.cdf > 1.0) close |= (unsigned)((k0 + u < nn) && !t && (wv[u] & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << u;
       }
@@ -369,7 +357,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       while (touch) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
         const int u = __ffs((int)touch) - 1;
         touch &= touch - 1;
-        pair_contact<NORMAL, ROLLING, ONE, HALF>(P, i, P.nbr[(size_t)(k0 + u) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
+        pair_contact<NORMAL, ROLLING, ONE, F32>(P, i, P.nbr[(size_t)(k0 + u) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
       }
       while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
         const int u = __ffs((int)close) - 1;
@@ -398,7 +386,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
     const double4 xo = s_rec[0][tid], vo = s_rec[1][tid], wo = s_rec[2][tid];
 #pragma unroll 1
     for (int r = 0; r < ownr; r++)
-      if (r < nc) pair_contact<NORMAL, ROLLING, ONE, HALF>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T);
+      if (r < nc) pair_contact<NORMAL, ROLLING, ONE, F32>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T);
   }
 #endif
   // (2b) cooperative deal of the remaining items: item t belongs to the last lane whose first item is <= t
@@ -424,7 +412,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
           const int q = wb + p;
           const unsigned w = s_w[ownr + t - s_off[q]][q];
           double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
-          pair_contact<NORMAL, ROLLING, ONE, HALF>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
+          pair_contact<NORMAL, ROLLING, ONE, F32>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
           const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
@@ -443,30 +431,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   // (3) owner epilogue
   if (active) {
     if (P.have_pair) { const int nh = s_nh[tid]; if (nh != nh0) P.numneigh[i] = nn | (nh << 16); }
-    if (HALF) {  // my own sum joins what the lower-index partners sent; k_integrate_half takes it from there
-#pragma unroll
-      for (int d = 0; d < 3; d++) { atomicAdd(P.fa + (size_t)d * P.cap + i, F[d]); atomicAdd(P.ta + (size_t)d * P.cap + i, T[d]); }
-    } else
     trig = step_epilogue(P, i, s_rec[0][tid], s_rec[1][tid], s_rec[2][tid], F, T);
-  }
-  if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
-}
-
-// second kernel of the half-list alternative: pair force sums from P.fa / P.ta (cleared for the next step), then the usual
-// owner epilogue (gravity, wall forces, freeze, integration, rebuild trigger)
-__global__ void __launch_bounds__(256) k_integrate_half(const StepP P)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool trig = false;
-  if (step_gated(P)) return;
-  if (i < P.nlocal) {
-    double F[3], T[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      F[d] = P.fa[(size_t)d * P.cap + i]; T[d] = P.ta[(size_t)d * P.cap + i];
-      P.fa[(size_t)d * P.cap + i] = 0.0; P.ta[(size_t)d * P.cap + i] = 0.0;
-    }
-    trig = step_epilogue(P, i, ldg4(P.xr + i), ldg4(P.vm + i), ldg4(P.wt + i), F, T);
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }

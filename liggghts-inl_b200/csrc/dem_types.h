@@ -63,7 +63,6 @@ struct StepP {
   int hslots;
   double *whist;  // [sum wall dnum][cap]
   double *f, *tq; // [3][cap]
-  double *fa, *ta; // [3][cap] accumulation arrays of the half-list alternative (option "half_list"), else null
   // owner list (option owner_list, dem_pairs.cuh): per-contact result records [hslots][lcap][2], stamped with the launch serial
   double4 *res;
   double serial;

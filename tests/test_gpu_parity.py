@@ -160,6 +160,38 @@ def test_many_contacts_on_one_particle_match_oracle():
     got.close(); ref.close()
 
 
+@pytest.mark.parametrize("kw", [
+    dict(n3=(10, 10, 10), poly=True, model="model hertz tangential history rolling_friction cdt"),
+    dict(n3=(8, 8, 8), poly=True, periodic=(1, 1, 0), ntypes=2, model="model hertz tangential history rolling_friction epsd2"),
+    dict(n3=(8, 8, 8), model="model hooke tangential history rolling_friction epsd", frozen=20),
+])
+def test_fp32_mode_within_1e_5_of_the_fp64_oracle(kw):
+    """option fp32 (BASELINE.json north_star: "1e-5 in fp32 mode"): the contact law in single precision, state / geometry /
+    sums in fp64.  Pair sets and contact flags stay bit-exact (the predicates are fp64), per-particle forces and torques of
+    the first steps agree with the fp64 oracle to 1e-5 (relative, floor 1e-7 of a weight x radius for torques)"""
+    c = cases.case_box(name="fp32", seed=9, **kw)
+    rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
+    got = cases.apply(c, gpu_engine())
+    got.option("fp32", 1)
+    ref = cases.apply(c, parity.oracle_engine())
+    done = 0
+    worst = 0.0
+    for cp in (0, 1, 2, 10, 60):
+        for eng in (got, ref):
+            eng.setup(); eng.run(cp - done)
+        done = cp
+        sg, sr = cases.snapshot(got, c), cases.snapshot(ref, c)
+        parity.compare_bookkeeping(sg, sr, label="fp32@%d" % cp)
+        mg = rmass * 9.81
+        ef = parity.rel_err(sg["f"], sr["f"], 1e-7 * mg)
+        et = parity.rel_err(sg["torque"], sr["torque"], np.maximum(1e-7 * mg * c["radius"], 1e-5 * np.linalg.norm(sr["f"], axis=1) * c["radius"]))
+        worst = max(worst, ef, et)
+        tol = 1e-5 if cp <= 10 else 1e-3   # (after 60 steps the single-precision history has drifted: chaotic growth)
+        assert ef <= tol and et <= tol, "fp32@%d: force %.2e torque %.2e" % (cp, ef, et)
+    print("fp32 mode: worst relative force/torque error over the first 60 steps %.2e" % worst)
+    got.close(); ref.close()
+
+
 def test_settings_changed_between_runs_match_oracle():
     """`neighbor` and `fix property/global` between two runs (the deck front end forwards them and calls setup again): the
     material tables, the neighbour cutoff and the cell grid are derived again -- a doubled skin must not lose pairs beyond
@@ -204,6 +236,7 @@ def test_history_overflow_is_reported_under_check_no():
     c["hi"][2] = max(c["hi"][2], 0.06)
     c["neigh"] = (2, 0, False)
     e = cases.apply(c, gpu_engine())
+    e.option("histslots", 16)   # (the default -- one history row per list entry -- cannot overflow)
     e.setup()
     with pytest.raises(dem_b200.DemError, match="history"):
         e.run(20)
