@@ -154,9 +154,12 @@ def C4(scale=1.0, plate_speed=-0.05):
     return c
 
 
-def C5(scale=1.0, bricks=8, period=2.0, nseg=None):
+def C5(scale=1.0, bricks=8, period=2.0, nseg=None, part=None, yrange=None):
     """configs[4]: rotating drum (axis y), filled to its axis with r = 2.5 mm spheres on a dense lattice clipped by the
-    mantle.  scale 1, bricks 8 -> one GPU's share of the 16.8 M spheres: a drum of radius 0.6 m and 1/8 of its 3.7 m"""
+    mantle.  scale 1, bricks 8 -> one GPU's share of the 16.8 M spheres: a drum of radius 0.6 m and 1/8 of its 3.7 m.
+    bricks 1, part (k, n) -> the FULL drum's geometry with only the spheres of the k-th of n slabs along the axis (what rank k
+    of an n-GPU run holds; tags start at 1 in every part: the caller offsets them); yrange (lo, hi) -> the same for an explicit
+    interval of the axis (a rank's sub-box of the engine's own decomposition)"""
     rad = 0.0025
     pitch = 1.995 * rad
     s = scale ** (1.0 / 3.0)
@@ -166,17 +169,28 @@ def C5(scale=1.0, bricks=8, period=2.0, nseg=None):
     cx, cz = R + 0.02, R + 0.02
     y0, y1 = 0.0, Ly
     c = _base("C5", [0.0, -0.02, 0.0], [2 * cx, Ly + 0.02, 2 * cz])
-    g = _cubic([cx - R, y0 + 0.2 * rad, cz - R], [cx + R, y1 - 0.2 * rad, cz], pitch)   # lower half
+    ya, yb = y0 + 0.2 * rad, y1 - 0.2 * rad
+    ys_all = np.arange(ya + 0.5 * pitch, yb, pitch)
+    ysh_all = np.arange(y0 + 1.0 * rad, y1 - 0.97 * rad, pitch)
+    if part is not None:
+        k, nparts = part
+        lo_p, hi_p = y0 + (y1 - y0) * k / nparts, y0 + (y1 - y0) * (k + 1) / nparts
+        yrange = (lo_p, hi_p)
+    if yrange is not None:
+        ys_all = ys_all[(ys_all >= yrange[0]) & (ys_all < yrange[1])]
+        ysh_all = ysh_all[(ysh_all >= yrange[0]) & (ysh_all < yrange[1])]
+    ax = [np.arange(cx - R + 0.5 * pitch, cx + R, pitch), ys_all, np.arange(cz - R + 0.5 * pitch, cz, pitch)]   # lower half
+    g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
     rho = np.hypot(g[:, 0] - cx, g[:, 2] - cz)
     inside = (R - rho >= 0.98 * rad + pitch) & (g[:, 1] - y0 >= 0.97 * rad) & (y1 - g[:, 1] >= 0.97 * rad)
     # one layer of spheres ON the mantle (lower half), pressed 1 % of a radius into it
     rr_c = R - 0.99 * rad
     m = int(np.pi * rr_c / pitch)
-    ys = np.arange(y0 + 1.0 * rad, y1 - 0.97 * rad, pitch)
+    ys = ysh_all
     a = np.pi + np.pi * (np.arange(m) + 0.5) / m        # angles pi..2pi: below the axis
     A, Y = np.meshgrid(a, ys, indexing="ij")
     shell = np.stack([cx + rr_c * np.cos(A.ravel()), Y.ravel(), cz + rr_c * np.sin(A.ravel())], 1)
-    _finish(c, np.concatenate([g[inside], shell]), rad, jitter=0.001 * rad)
+    _finish(c, np.concatenate([g[inside], shell]), rad, jitter=0.001 * rad, seed=None if yrange is None else cases.SEED + 1 + int(1000 * yrange[0]))
     c["meshes"] = [("drum", 1, cases.mesh_drum(cx, cz, R, y0, y1, nseg=nseg))]
     c["mesh_moves"] = [("drum", "rotate origin %.17g 0. %.17g axis 0. 1. 0. period %s" % (cx, cz, period))]
     c["mesh_walls"] = [("mw", HERTZ_CDT + " mesh n_meshes 1 meshes drum")]

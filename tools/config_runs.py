@@ -27,8 +27,55 @@ def make(name):
     return c, warm, steps
 
 
+def multi_c5():
+    """configs[4] at its full size on all ranks of a torchrun launch: 16.65 M spheres in the rotating drum, slabs along the drum
+    axis (one per GPU); every rank generates and uploads the spheres of its own sub-box"""
+    import torch
+    import torch.distributed as dist
+    import configs
+    dist.init_process_group("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    box = configs.C5(bricks=1, yrange=(0.0, 0.0))
+    lay = dem_b200.brick_layout(world, rank, box["lo"], box["hi"], box["periodic"], procgrid=[1, world, 1])
+    c = configs.C5(bricks=1, yrange=(lay["sublo"][1], lay["subhi"][1]))
+    counts = [None] * world
+    dist.all_gather_object(counts, len(c["tag"]))
+    c["tag"] = (c["tag"].astype(np.int64) + sum(counts[:rank])).astype(np.int32)
+    n = sum(counts)
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(dem_b200.Engine.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    eng = dem_b200.Engine(device=local, rank=rank, nranks=world, nccl_id=buf.cpu().numpy().tobytes())
+    eng.box(c["lo"], c["hi"], c["periodic"]); eng.processors(1, world, 1)
+    eng = cases.apply(c, eng)
+    eng.option("time_kernels", 1)
+    warm, steps = 100, 1000
+    eng.setup(); eng.run(warm)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.run(steps); e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    st = eng.stats()
+    x = eng.download("x")
+    agg = torch.tensor([float(st.nlocal), float(len(eng.mesh_contacts("drum")["tag"])), float(np.isfinite(x).all()), float(st.npairs_full), float(st.ncontacts_full)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"config": "C5 (full, %d GPUs)" % world, "particles": n, "steps": steps, "particle_steps_per_s": n * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                          "step_kernel_ms_rank0": st.step_kernel_ms / max(st.step_kernel_calls, 1), "rebuilds": int(st.nbuilds), "particles_after": int(agg[0].item()),
+                          "mesh_contact_rows": int(agg[1].item()), "state_ok": bool(agg[2].item() == world and int(agg[0].item()) == n),
+                          "halflist_per_particle": agg[3].item() / 2.0 / n, "contacts_per_particle": agg[4].item() / 2.0 / n, "triangles": len(c["meshes"][0][2])}), flush=True)
+    eng.close()
+    dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     import torch
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return multi_c5()
     for name in (sys.argv[1:] or ["C1", "C3", "C4", "C5"]):
         c, warm, steps = make(name)
         n = len(c["tag"])

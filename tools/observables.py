@@ -29,7 +29,7 @@ FIXTURE = os.path.join(ROOT, "tests", "golden", "observables_ref.json")
 SEEDS = (1, 2, 3)
 # statistical tolerances on the mean over the seeds (engine vs reference).  The spread between seeds (the fixture's `std`)
 # is the natural scale: packing ~2e-3, discharge ~2 %, repose ~1 deg.
-TOL = {"packing": 0.01, "discharge": 0.06, "repose": 2.5}   # absolute packing fraction, relative rate, degrees
+TOL = {"packing": 0.01, "discharge": 0.08, "repose": 2.5}   # absolute packing fraction, relative rate, degrees
 
 
 # ------------------------------------------------------------------------------------------------ cases
@@ -40,7 +40,7 @@ def case_packing(seed):
 
 def case_discharge(seed):
     c = configs.C3(configs.MINI["C3"], seed=200 + seed)
-    return c, [("run", 15000), ("mark", "t0"), ("run", 25000), ("mark", "t1")]
+    return c, [("run", 15000), ("mark", "t0"), ("run", 45000), ("mark", "t1")]   # rate over 0.45 s (~700 spheres: counting noise ~4 % per seed)
 
 
 def mesh_tube(cx, cy, R, z0, z1, nseg=24):
@@ -64,7 +64,7 @@ def case_repose(seed):
     g = g[np.hypot(g[:, 0] - cx, g[:, 1] - cy) <= Rt - 1.15 * rad]
     g = g[np.argsort(g[:, 2], kind="stable")][:4000]   # the lowest 4,000 sites: a column of ~48 layers
     g = g + rng.uniform(-0.04 * rad, 0.04 * rad, g.shape)
-    c = configs._base("obs_repose", [0.0, 0.0, 0.0], [L, L, g[:, 2].max() + 0.05])
+    c = configs._base("obs_repose", [0.0, 0.0, 0.0], [L, L, g[:, 2].max() + 0.45])   # (tall enough for the lifted tube: a mesh must stay inside the box)
     configs._finish(c, g, rad, v=np.tile([0.0, 0.0, -0.3], (len(g), 1)) + rng.uniform(-0.05, 0.05, (len(g), 3)))
     c["props"][3] = ("coefficientFriction", "peratomtypepair", [0.6])
     c["props"][4] = ("coefficientRollingFriction", "peratomtypepair", [0.3])
@@ -198,12 +198,14 @@ def main():
                 v = one(name, seed, impl)
             vals[name].append(v)
             print(impl, name, "seed", seed, "->", v, flush=True)
+        if impl == "reference":   # the fixture grows observable by observable (a reference run takes minutes)
+            old = json.load(open(FIXTURE)) if os.path.exists(FIXTURE) else {}
+            old.update(summarize({name: vals[name]}))
+            json.dump(old, open(FIXTURE, "w"), indent=1)
+            print("wrote", name, "to", FIXTURE, flush=True)
     res = summarize(vals)
     if impl == "reference":
-        old = json.load(open(FIXTURE)) if os.path.exists(FIXTURE) else {}
-        old.update(res)
-        json.dump(old, open(FIXTURE, "w"), indent=1)
-        print("wrote", FIXTURE)
+        pass
     else:
         ref = json.load(open(FIXTURE))
         cmp_ = compare(res, {k: ref[k] for k in res})
