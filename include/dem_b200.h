@@ -174,6 +174,16 @@ typedef struct dem_stats {
 } dem_stats;
 int dem_get_stats(dem_engine *e, dem_stats *out);
 
+/* ---- per-contact output -----------------------------------------------------------
+ * replaces: compute ID group pair/gran/local id force torque   src/compute_pair_gran_local.cpp:66-140 (keywords),
+ *           :519-640 (post_force_pp: one row per touching pair with the ids and the force / torque on the first particle)
+ * Needs dem_set_option("contact_output", 1) before dem_setup.  One row per (owned particle, touching partner) of the last
+ * force evaluation that materialised forces (dem_setup, or the last step of dem_run): own tag, partner tag, the force and
+ * the torque the pair applies to the owned particle -- a pair of two owned particles gives two rows, one per particle,
+ * ordered by (own tag, partner tag).  Plain contact models only.                                                        */
+int dem_contact_count(dem_engine *e, long *n);
+int dem_download_contacts(dem_engine *e, int *tag, int *partner, double *force, double *torque);
+
 /* ---- input-script front end (csrc/dem_deck.cpp): the reference's embedding API
  *   void lammps_open_no_mpi(int, char **, void **)   src/library.cpp:85-100   -> dem_create + dem_deck_open
  *   void lammps_file(void *, char *)                 src/library.cpp:130-140  -> dem_deck_file

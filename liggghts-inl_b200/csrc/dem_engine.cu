@@ -210,6 +210,7 @@ struct dem_engine {
   ListSet ls[2];
   int lcur = 0;
   DevBuf<double4> res;  // owner list: per-contact result records
+  DevBuf<double4> cout; long cout_serial = 0;  // option contact_output: per-contact force / torque of the last materialising evaluation
   long serial = 0;      // step launches so far (stamps the result records)
   DevBuf<int> overflow;
   DevBuf<unsigned long long> counters;
@@ -346,7 +347,7 @@ extern "C" void dem_destroy(dem_engine *e)
   e->order.release(); e->order_keys.release(); e->stage.release(); e->valid_tmp.release(); e->wlist.release(); e->fw.release(); e->sbuf.release(); e->sbuf_i.release(); e->gorder.release(); e->gone.release(); e->cnt_dev.release(); e->migs.release(); e->migr.release(); e->dflag.release(); for (auto &sw : e->swaps) sw.list.release();
   e->flo.release(); e->fhi.release(); e->slo.release(); e->shi.release(); e->ocs.release(); e->oce.release();
   e->gcs.release(); e->gce.release(); e->perm.release(); e->vals.release(); e->keys.release(); e->keys2.release();
-  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->res.release();
+  e->cubtmp.release(); e->overflow.release(); e->counters.release(); e->res.release(); e->cout.release();
   e->dmforce.release(); e->dmpref.release();
   e->dtri.release(); e->dcn.release(); e->dcell_start.release(); e->dcell_tri.release(); e->dnodes_last.release();
   for (int s = 0; s < 2; s++) { e->mint[s].release(); e->mhist[s].release(); }
@@ -1705,6 +1706,9 @@ static void rebuild(dem_engine *E)
     if (maxk > (fmt ? NN2_MAXK : 0xffff) || hslots > NBR_MAXSLOTS) dem_fail(E, DEM_ERR_OVERFLOW, "a particle has %d neighbours / %d history partners", ov[0], ov[1]);
   }
   if (fmt && E->res.n < (size_t)Lnew.hslots * 2 * Lnew.cap) { E->res.release(); E->res.ensure(E, (size_t)Lnew.hslots * 2 * Lnew.cap); }
+  if (!fmt && E->opt.count("contact_output") && E->opt["contact_output"] != 0 && E->cout.n < (size_t)Lnew.hslots * 2 * Lnew.cap) {
+    E->cout.release(); E->cout.ensure(E, (size_t)Lnew.hslots * 2 * Lnew.cap);
+  }
   Lnew.valid = 1; Lold.valid = 0;
   E->lcur ^= 1;
   tr.mark("list build + remap");
@@ -1803,6 +1807,9 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (tm) {
     if ((long)E->ev.size() < 2 * (E->ev_used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); E->ev.push_back(a); E->ev.push_back(b); }
     cudaEventRecord(E->ev[2 * E->ev_used], E->stream);
+  }
+  if (mode != MODE_STEP && E->cout.p && E->ls[E->lcur].fmt == 0 && E->have_pair && !E->pm.cohesion) {
+    E->cout_serial = next_serial(); P.cout = E->cout.p; P.serial = (double)E->cout_serial;
   }
   if (P.nwc) { k_walls<<<GRID(P.nwc, 128), 128, 0, E->stream>>>(P); E->launches++; }
   if (have_mesh_walls(E) && E->mesh_ready && E->any_stress) CK(cudaMemsetAsync(E->dmforce.p, 0, 6 * DEM_MAXMESH * sizeof(double), E->stream));  // MeshModuleStress::pre_force
@@ -2198,6 +2205,73 @@ extern "C" int dem_download_pairs(dem_engine *e, int *lo, int *hi, int *flag, do
         if (M.rec_shear >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_shear) * L.cap + i]; hist[r * dn + M.off_shear] = v.x; hist[r * dn + M.off_shear + 1] = v.y; hist[r * dn + M.off_shear + 2] = v.z; }
         if (M.rec_roll >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_roll) * L.cap + i]; hist[r * dn + M.off_roll] = v.x; hist[r * dn + M.off_roll + 1] = v.y; hist[r * dn + M.off_roll + 2] = v.z; }
       }
+    }
+  }
+  API_END
+}
+
+// ---- per-contact output (option contact_output): rows (own tag, partner tag, force on me, torque on me) of the last force
+// evaluation that materialised forces -- dem_setup or the last step of dem_run --, ordered by (own tag, partner tag)
+struct ContactRows { std::vector<int> tags; std::vector<double> v; };
+static void collect_contacts(dem_engine *E, ContactRows &R)
+{
+  R.tags.clear(); R.v.clear();
+  ListSet &L = E->ls[E->lcur];
+  if (!E->have_pair || E->pm.cohesion || L.fmt != 0) dem_fail(E, DEM_ERR_UNSUPPORTED, "per-contact output covers the plain contact models on the default (full) list");
+  if (!(E->opt.count("contact_output") && E->opt["contact_output"] != 0)) dem_fail(E, DEM_ERR_STATE, "per-contact output needs option contact_output 1 (before dem_setup)");
+  if (!E->forces_valid || !L.valid || !E->cout.p) dem_fail(E, DEM_ERR_STATE, "per-contact output is available after dem_setup or dem_run");
+  const int n = (int)E->nlocal;
+  if (!n) return;
+  cudaStream_t st = E->stream;
+  StepP P = step_params(E, MODE_SETUP);
+  P.cout = E->cout.p; P.serial = (double)E->cout_serial;
+  E->flo.ensure(E, n + 1); E->slo.ensure(E, n + 1);
+  ensure_cub(E, (size_t)E->cap);
+  k_contact_count<<<GRID(n, 256), 256, 0, st>>>(P, E->flo.p);
+  size_t tb = E->cubtmp.n;
+  CK(cub::DeviceScan::ExclusiveSum(E->cubtmp.p, tb, E->flo.p, E->slo.p, n, st));
+  int last[2];
+  CK(cudaMemcpyAsync(&last[0], E->flo.p + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&last[1], E->slo.p + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const size_t rows = (size_t)last[0] + last[1];
+  E->launches += 2;
+  if (!rows) return;
+  DevBuf<int> dt; DevBuf<double> dv;
+  dt.ensure(E, 2 * rows); dv.ensure(E, 6 * rows);
+  k_contact_fill<<<GRID(n, 256), 256, 0, st>>>(P, L.ptag.p, E->tag.p, E->slo.p, dt.p, dv.p);
+  E->launches++;
+  std::vector<int> ht(2 * rows); std::vector<double> hv(6 * rows);
+  CK(cudaMemcpyAsync(ht.data(), dt.p, ht.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hv.data(), dv.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  dt.release(); dv.release();
+  std::vector<size_t> o(rows);
+  for (size_t r = 0; r < rows; r++) o[r] = r;
+  std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return ht[2 * a] != ht[2 * b] ? ht[2 * a] < ht[2 * b] : ht[2 * a + 1] < ht[2 * b + 1]; });
+  R.tags.resize(2 * rows); R.v.resize(6 * rows);
+  for (size_t r = 0; r < rows; r++) { R.tags[2 * r] = ht[2 * o[r]]; R.tags[2 * r + 1] = ht[2 * o[r] + 1]; memcpy(&R.v[6 * r], &hv[6 * o[r]], 6 * sizeof(double)); }
+}
+extern "C" int dem_contact_count(dem_engine *e, long *n)
+{
+  API_BEGIN
+  CK(cudaSetDevice(e->device));
+  ContactRows R; collect_contacts(e, R);
+  if (n) *n = (long)(R.tags.size() / 2);
+  API_END
+}
+extern "C" int dem_download_contacts(dem_engine *e, int *tag, int *partner, double *force, double *torque)
+{
+  API_BEGIN
+  CK(cudaSetDevice(e->device));
+  ContactRows R; collect_contacts(e, R);
+  const size_t rows = R.tags.size() / 2;
+  for (size_t r = 0; r < rows; r++) {
+    if (tag) tag[r] = R.tags[2 * r];
+    if (partner) partner[r] = R.tags[2 * r + 1];
+    for (int d = 0; d < 3; d++) {
+      if (force) force[3 * r + d] = R.v[6 * r + d];
+      if (torque) torque[3 * r + d] = R.v[6 * r + 3 + d];
     }
   }
   API_END

@@ -203,10 +203,13 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
   double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
+  double Fc[3] = {0., 0., 0.}, Tc[3] = {0., 0., 0.};  // this contact's share (kept apart for the per-contact output)
   if (F32)
-    pair_chain_f32<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T, nullptr);
+    pair_chain_f32<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, Fc, Tc, nullptr);
   else
-    pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, F, T);
+    pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, Fc, Tc);
+#pragma unroll
+  for (int d = 0; d < 3; d++) { F[d] += Fc[d]; T[d] += Tc[d]; }
   if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
     const int s = atomicAdd(nh, 1);
     if (s < P.hslots) {
@@ -220,6 +223,11 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
     double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
     if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
     if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
+  }
+  if (P.cout && slot >= 0) {  // option contact_output, setup / last step only (null otherwise): see k_contact_fill
+    double4 *cp = P.cout + ((size_t)slot * P.lcap + i) * 2;
+    st4(cp, make_double4(Fc[0], Fc[1], Fc[2], Tc[0]));
+    st4(cp + 1, make_double4(Tc[1], Tc[2], P.serial, 0.));
   }
 }
 

@@ -519,4 +519,45 @@ __global__ void __launch_bounds__(128) k_mig_unpack2(const MigP M, int base)
   }
 }
 
+
+// ---- per-contact output (the reference: compute pair/gran/local, compute_pair_gran_local.cpp:287-303 and
+// post_force_pp :519-640 -- one row per touching pair with the ids and the force / torque the pair loop applied to the
+// first particle).  With option contact_output the step kernel leaves, in the force evaluations that materialise forces
+// (Verlet::setup and the last step of a run), the force and torque of every evaluated contact in the pair's history slot of
+// a side array, stamped with the launch serial (k_step: pair_contact).  These two kernels gather the stamped records into
+// rows (own tag, partner tag, force on me, torque on me) -- both directions of a pair between two owned particles, like the
+// two particles' views of it.
+__global__ void __launch_bounds__(256) k_contact_count(const StepP P, int *cnt)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nlocal) return;
+  const int nn = P.numneigh[i] & 0xffff;
+  int c = 0;
+  for (int k = 0; k < nn; k++) {
+    const unsigned w = P.nbr[(size_t)k * P.lcap + i];
+    if (!(w & NBR_HIST)) continue;
+    const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+    c += P.cout[((size_t)slot * P.lcap + i) * 2 + 1].z == P.serial ? 1 : 0;
+  }
+  cnt[i] = c;
+}
+__global__ void __launch_bounds__(256) k_contact_fill(const StepP P, const int *ptag, const int *tag, const int *off, int *out_tags, double *out6)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nlocal) return;
+  const int nn = P.numneigh[i] & 0xffff;
+  int row = off[i];
+  for (int k = 0; k < nn; k++) {
+    const unsigned w = P.nbr[(size_t)k * P.lcap + i];
+    if (!(w & NBR_HIST)) continue;
+    const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+    const double4 a = P.cout[((size_t)slot * P.lcap + i) * 2], b = P.cout[((size_t)slot * P.lcap + i) * 2 + 1];
+    if (b.z != P.serial) continue;
+    out_tags[2 * row] = tag[i]; out_tags[2 * row + 1] = ptag[(size_t)k * P.lcap + i];
+    double *o = out6 + 6 * (size_t)row;
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+    row++;
+  }
+}
+
 }  // namespace dem

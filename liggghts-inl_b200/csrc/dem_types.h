@@ -66,6 +66,7 @@ struct StepP {
   // owner list (option owner_list, dem_pairs.cuh): per-contact result records [hslots][lcap][2], stamped with the launch serial
   double4 *res;
   double serial;
+  double4 *cout;   // option contact_output: force / torque of every evaluated contact [hslots][lcap][2], stamped like res; else null
   const WallP *walls;
   int nwalls;
   int nwc, nwcap;     // primitive-wall candidates (compact list) and row stride of fw

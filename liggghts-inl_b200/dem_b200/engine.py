@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
-    "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
+    "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
 ]
 
 
@@ -243,6 +243,16 @@ class Engine:
         hist = np.zeros((n, max(d, 1)), np.float64)
         self._call("download_pairs", [C.c_void_p] * 4, lo.ctypes.data, hi.ctypes.data, fl.ctypes.data, hist.ctypes.data)
         return {"lo": lo, "hi": hi, "flag": fl, "hist": hist[:, :d], "dnum": d}
+
+    def contacts(self):
+        """(option contact_output) rows of the last force evaluation: own tag, partner tag, force and torque on the own particle"""
+        n = C.c_long(0)
+        self._call("contact_count", [C.POINTER(C.c_long)], C.byref(n))
+        n = n.value
+        tag = np.zeros(n, np.int32); partner = np.zeros(n, np.int32)
+        f = np.zeros((n, 3)); t = np.zeros((n, 3))
+        self._call("download_contacts", [C.c_void_p] * 4, tag.ctypes.data, partner.ctypes.data, f.ctypes.data, t.ctypes.data)
+        return {"tag": tag, "partner": partner, "force": f, "torque": t}
 
     def wall_history(self, wall_id, dnum):
         n = self.nlocal

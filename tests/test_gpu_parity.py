@@ -1,5 +1,6 @@
 """GPU: the CUDA engine through the C ABI against (a) golden vectors from the unmodified
 reference and (b) the CPU oracle on the same seeded inputs."""
+import os
 import numpy as np
 import pytest
 import cases
@@ -275,3 +276,37 @@ def test_multi_gpu_bricks_match_oracle():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(here, "run_multi.py")], capture_output=True, text=True, timeout=600)
     assert "MULTI-GPU PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["box_hertz_cdt", "periodic_epsd2", "poly_hooke_epsd_cyl"])
+def test_contact_output_matches_reference_compute_pair_gran_local(name):
+    """dem_download_contacts against `compute pair/gran/local id force torque` of the unmodified reference
+    (tests/golden/contacts_*.npz, the values of the last step of a run): the same touching pairs, force and torque on the
+    reference's first particle to 1e-10 -- and the rows of a particle add up to its pair force"""
+    g = np.load(os.path.join(parity.ROOT, "tests", "golden", "contacts_%s.npz" % name))
+    c = cases.make_case(name)
+    e = cases.apply(c, gpu_engine())
+    e.option("contact_output", 1)
+    e.setup(); e.run(int(g["steps"]))
+    ct = e.contacts()
+    key_g = ct["tag"].astype(np.int64) * (1 << 32) + ct["partner"]
+    pos = {k: r for r, k in enumerate(key_g)}
+    key_r = g["id1"].astype(np.int64) * (1 << 32) + g["id2"]
+    # the reference lists a pair once (twice across a periodic face); the engine lists both particles' views
+    und_g = set(zip(np.minimum(ct["tag"], ct["partner"]).tolist(), np.maximum(ct["tag"], ct["partner"]).tolist()))
+    und_r = set(zip(np.minimum(g["id1"], g["id2"]).tolist(), np.maximum(g["id1"], g["id2"]).tolist()))
+    assert und_g == und_r, "touching pair sets differ"
+    worst = 0.0
+    for r in range(len(key_r)):
+        q = pos[key_r[r]]
+        sf = max(np.linalg.norm(g["force"][r]), 1e-300)
+        worst = max(worst, np.linalg.norm(ct["force"][q] - g["force"][r]) / sf,
+                    np.linalg.norm(ct["torque"][q] - g["torque"][r]) / max(np.linalg.norm(g["torque"][r]), 1e-3 * sf * c["radius"].min()))
+    # (the rows follow a run of hundreds of steps: the bound is the one of the per-particle forces at that horizon)
+    tol = parity.tol_for(c, int(g["steps"]), gpu=True)
+    assert worst <= tol, "per-contact force / torque differ from the reference by %.2e (tol %.0e)" % (worst, tol)
+    # Newton's third law between the two views of a pair of owned particles
+    for (a, b) in list(und_g)[:200]:
+        if (a * (1 << 32) + b) in pos and (b * (1 << 32) + a) in pos:
+            assert np.array_equal(ct["force"][pos[a * (1 << 32) + b]], -ct["force"][pos[b * (1 << 32) + a]])
+    e.close()
