@@ -217,12 +217,15 @@ __device__ __forceinline__ void sqrt_rsqrt_fast(double x, double &s, double &rs)
 // forces are equal and opposite to the last bit and the two history copies stay exact negatives,
 // without selecting operands into a canonical order.  shear/ch are in MY orientation.
 // Adds the force / torque acting on me to F / T.
-template <int NORMAL, int ROLLING, bool ONE>
+template <int NORMAL, int ROLLING, bool ONE, bool STD = false>
 __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, const double4 &xi, const double4 &vi, const double4 &wi,
                                            const double4 &xj, const double4 &vj, const double4 &wj, int itype, int jtype,
                                            int imask, int jmask, double dx, double dy, double dz, double rsq,
                                            double (&shear)[3], double (&ch)[3], bool shearupdate, double *F, double *T, double *Tp = nullptr)
-{  // Tp (optional, half-list variant): receives the torque on the PARTNER, -crj (en x Ft) + rolling torque
+{  // Tp (optional, owner list): receives the torque on the PARTNER, -crj (en x Ft) + rolling torque
+  // STD: the reference's default sub-model settings, known at compile time (see pair_item in dem_kernels.cuh)
+  const bool m_tangential = STD ? true : (M.tangential != 0), m_tdamp = STD ? true : (M.tdamp != 0);
+  const bool m_limitForce = STD ? false : (M.limitForce != 0), m_torsion = STD ? false : (M.torsion != 0);
   const int tij = itype * P.nt1 + jtype;
   double r, rinv;
   sqrt_rsqrt_fast(rsq, r, rinv);
@@ -257,7 +260,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
     inv_kt = tabp<ONE>(P, T_INV8G, tij) * inv_s;
     const double c2 = -2. * 0.91287092917527685576161630466800355658790782499663875 * beta * q;
     gamman = c2 * tabp<ONE>(P, T_SQ2Y, tij);          // -2 sqrt(5/6) beta sqrt(Sn meff), Sn = 2 Y s
-    gammat = M.tdamp ? c2 * tabp<ONE>(P, T_SQ8G, tij) : 0.0;  // St = 8 G s
+    gammat = m_tdamp ? c2 * tabp<ONE>(P, T_SQ8G, tij) : 0.0;  // St = 8 G s
   } else {  // normal_model_hooke.h:230-300
     const double Y = tabp<ONE>(P, T_YEFF, tij);
     const double lg = tabp<ONE>(P, T_CORLOG, tij);
@@ -267,15 +270,15 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
     if (M.ktToKn) kt *= 0.285714286;
     const double lgsq = lg * lg;
     gamman = sqrt(4. * meff * kn * lgsq / (lgsq + 3.14159265358979323846 * 3.14159265358979323846));
-    gammat = M.tdamp ? gamman : 0.0;
+    gammat = m_tdamp ? gamman : 0.0;
     inv_kt = P.nktv2p / kt;
   }
-  if (P.nktv2p != 1.0) { kn /= P.nktv2p; kt /= P.nktv2p; if (NORMAL == N_HERTZ) inv_kt *= P.nktv2p; }
+  if (!STD && P.nktv2p != 1.0) { kn /= P.nktv2p; kt /= P.nktv2p; if (NORMAL == N_HERTZ) inv_kt *= P.nktv2p; }
   double Fn = -gamman * vn + kn * deltan;
-  if (M.limitForce && Fn < 0.0) Fn = 0.0;
+  if (m_limitForce && Fn < 0.0) Fn = 0.0;
   double F1 = Fn * enx, F2 = Fn * eny, F3 = Fn * enz;
   double T1 = 0.0, T2 = 0.0, T3 = 0.0, P1 = 0.0, P2 = 0.0, P3 = 0.0;
-  if (M.tangential) {  // tangential_model_history.h:136-240,288-334
+  if (m_tangential) {  // tangential_model_history.h:136-240,288-334
     if (shearupdate) {
       shear[0] += vtr1 * P.dt; shear[1] += vtr2 * P.dt; shear[2] += vtr3 * P.dt;
       const double rsht = shear[0] * enx + shear[1] * eny + shear[2] * enz;
@@ -308,7 +311,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
       if (mag > 0.) {
         const double sc = rmu * kn * deltan * reff * inv_mag;
         double r1 = a1 * sc, r2 = a2 * sc, r3 = a3 * sc;
-        if (!M.torsion) {
+        if (!m_torsion) {
           const double dot = r1 * enx + r2 * eny + r3 * enz;
           r1 -= enx * dot; r2 -= eny * dot; r3 -= enz * dot;
         }
@@ -317,7 +320,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
       }
     } else {  // rolling_model_epsd.h:97-340, rolling_model_epsd2.h:152-205
       double w1 = a1, w2 = a2, w3 = a3;
-      if (!M.torsion) {
+      if (!m_torsion) {
         const double dot = a1 * enx + a2 * eny + a3 * enz;
         w1 = a1 - enx * dot; w2 = a2 - eny * dot; w3 = a3 - enz * dot;
       }

@@ -1796,6 +1796,15 @@ static void launch_step_t(dem_engine *E, const StepP &P)
     else k_step<N, R, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
     return;
   }
+  // the reference's default sub-model settings get the specialised instantiation (see pair_item)
+  const ModelP &m = E->pm;
+  const bool std_deck = E->have_pair && m.tangential && m.tdamp && !m.limitForce && !m.torsion && P.nktv2p == 1.0 && P.cdf == 1.0 && !P.cout && !P.debug &&
+                        !(E->opt.count("generic_step") && E->opt["generic_step"] != 0);
+  if (std_deck) {
+    if (E->ntypes == 1) k_step<N, R, true, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+    else k_step<N, R, false, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
+    return;
+  }
   if (E->ntypes == 1) k_step<N, R, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
   else k_step<N, R, false><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
 }

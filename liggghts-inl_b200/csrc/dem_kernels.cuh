@@ -157,9 +157,6 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #ifndef DEM_CMAX
 #define DEM_CMAX 12  // touching entries per particle staged in shared memory (more: evaluated by the owner on the spot)
 #endif
-#ifndef DEM_RWIN
-#define DEM_RWIN 1   // cooperative rounds of 32 items whose results are parked in shared memory before the owners add them
-#endif
 #ifndef DEM_OWNR
 #define DEM_OWNR 12  // upper limit of contacts per particle evaluated by the particle's own lane before the cooperative deal;
 #endif               // 0 = cooperative deal only (1.252 ms), 12 with the cost rule below 1.125 ms, fixed 5: 1.118 ms, all own: 1.33 ms
@@ -180,51 +177,61 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #define DEM_STEP_WAVE_PREFETCH 200  // blocks ahead whose streaming inputs are pulled towards L2 (0 = off: 1.31 ms)
 #endif
 
-// one touching pair of particle i given its neighbour word w: evaluated in MY orientation (see pair_chain); history
-// records are stored in the canonical orientation "lower tag first" (sign flipped on load/store when the partner is the
-// first body).  nh = the particle's count of history slots in use (a shared-memory counter: in the cooperative phase
-// another lane may be serving the particle).
-template <int NORMAL, int ROLLING, bool ONE, bool F32 = false>
-__device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, const double4 &xi, const double4 &vi,
-                                             const double4 &wi, bool su, int *nh, double *F, double *T)
-{  // F32: the contact law in single precision (option fp32, see pair_chain_f32)
+// one list entry w of particle i (block-local index q, operands from the block's shared-memory records): evaluated in MY
+// orientation (see pair_chain) if the spheres touch; history records are stored in the canonical orientation "lower tag
+// first" (sign bit flipped on load/store when the partner is the first body).  s_nh[q] = the particle's count of history slots
+// in use (a shared-memory counter: in the cooperative phase another lane may be serving the particle).
+// STD (compile-time): the deck uses the reference's default sub-model settings (tangential history with damping, no
+// limitForce, no torsion torque, nktv2p == 1, contact_distance_factor 1, no per-contact output) -- the uniform run-time
+// switches and the generic history-row arithmetic drop out of the hot loop.
+__device__ __forceinline__ double flip_if(double v, unsigned flip)
+{  // v with its sign bit XORed by `flip` (0 or 0x80000000): history sign without a multiplication
+  return __hiloint2double(__double2hiint(v) ^ (int)flip, __double2loint(v));
+}
+template <int NORMAL, int ROLLING, bool ONE, bool F32, bool STD>
+__device__ __forceinline__ void pair_item(const StepP &P, int i, int q, unsigned w, const double4 (*s_rec)[128], int *s_nh, bool su,
+                                          double (&Fc)[3], double (&Tc)[3])
+{
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  const int hrec = STD ? (HAS_ROLL_HIST ? 2 : 1) : P.pm.hrec;
+  const int rec_shear = STD ? 0 : P.pm.rec_shear, rec_roll = STD ? 1 : P.pm.rec_roll;
+  const bool tangential = STD ? true : (P.pm.tangential != 0);
   const int j = (int)(w & NBR_IDX);
   int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   const bool had = slot >= 0;
   const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
   double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
   if (had) {
-    const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-    if (P.pm.tangential) hs = hp[(size_t)P.pm.rec_shear * P.lcap];
-    if (HAS_ROLL_HIST) hr = hp[(size_t)P.pm.rec_roll * P.lcap];
+    const double4 *hp = P.hist + (size_t)(slot * hrec) * P.lcap + i;
+    if (tangential) hs = hp[(size_t)rec_shear * P.lcap];
+    if (HAS_ROLL_HIST) hr = hp[(size_t)rec_roll * P.lcap];
   }
-  const double sgn = (w & NBR_JFIRST) ? -1.0 : 1.0;
-  double h[3] = {sgn * hs.x, sgn * hs.y, sgn * hs.z}, g[3] = {sgn * hr.x, sgn * hr.y, sgn * hr.z};
+  const double4 xi = s_rec[0][q], vi = s_rec[1][q], wi = s_rec[2][q];
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
-  double Fc[3] = {0., 0., 0.}, Tc[3] = {0., 0., 0.};  // this contact's share (kept apart for the per-contact output)
+  const double radsum = xi.w + xj.w;
+  if (!(rsq < __dmul_rn(radsum, radsum))) return;  // pair_gran_base.h:358 (entries that were staged by the sweep always pass)
+  const unsigned flip = w & NBR_JFIRST;
+  double h[3] = {flip_if(hs.x, flip), flip_if(hs.y, flip), flip_if(hs.z, flip)}, g[3] = {flip_if(hr.x, flip), flip_if(hr.y, flip), flip_if(hr.z, flip)};
   if (F32)
     pair_chain_f32<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, Fc, Tc, nullptr);
   else
-    pair_chain<NORMAL, ROLLING, ONE>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, Fc, Tc);
-#pragma unroll
-  for (int d = 0; d < 3; d++) { F[d] += Fc[d]; T[d] += Tc[d]; }
+    pair_chain<NORMAL, ROLLING, ONE, STD>(P, P.pm, xi, vi, wi, xj, vj, wj, rec_type(wi.w), rec_type(wj.w), rec_mask(wi.w), rec_mask(wj.w), dx, dy, dz, rsq, h, g, su, Fc, Tc);
   if (!had) {  // first touch since the last rebuild: the contact flag becomes != 0 and stays
-    const int s = atomicAdd(nh, 1);
+    const int s = atomicAdd(s_nh + q, 1);
     if (s < P.hslots) {
       slot = s;
       const int nn = P.numneigh[i] & 0xffff;
       for (int k = 0; k < nn; k++)  // rare path: find the row entry of this partner and tag it with its slot
         if ((P.nbr[(size_t)k * P.lcap + i] & NBR_IDX) == (unsigned)j) { P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); break; }
-    } else { atomicSub(nh, 1); ((volatile int *)P.flag)[1] = 1; }
+    } else { atomicSub(s_nh + q, 1); ((volatile int *)P.flag)[1] = 1; }
   }
-  if (P.pm.hrec && slot >= 0 && (su || !had)) {
-    double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-    if (P.pm.tangential) st4(hp + (size_t)P.pm.rec_shear * P.lcap, make_double4(sgn * h[0], sgn * h[1], sgn * h[2], 0.));
-    if (HAS_ROLL_HIST) st4(hp + (size_t)P.pm.rec_roll * P.lcap, make_double4(sgn * g[0], sgn * g[1], sgn * g[2], 0.));
+  if (hrec && slot >= 0 && (su || !had)) {
+    double4 *hp = P.hist + (size_t)(slot * hrec) * P.lcap + i;
+    if (tangential) st4(hp + (size_t)rec_shear * P.lcap, make_double4(flip_if(h[0], flip), flip_if(h[1], flip), flip_if(h[2], flip), 0.));
+    if (HAS_ROLL_HIST) st4(hp + (size_t)rec_roll * P.lcap, make_double4(flip_if(g[0], flip), flip_if(g[1], flip), flip_if(g[2], flip), 0.));
   }
-  if (P.cout && slot >= 0) {  // option contact_output, setup / last step only (null otherwise): see k_contact_fill
+  if (!STD && P.cout && slot >= 0) {  // option contact_output, setup / last step only (null otherwise): see k_contact_fill
     double4 *cp = P.cout + ((size_t)slot * P.lcap + i) * 2;
     st4(cp, make_double4(Fc[0], Fc[1], Fc[2], Tc[0]));
     st4(cp + 1, make_double4(Tc[1], Tc[2], P.serial, 0.));
@@ -232,14 +239,16 @@ __device__ __forceinline__ void pair_contact(const StepP &P, int i, unsigned w, 
 }
 
 // start the memory accesses a staged contact will need, without holding registers
+template <bool STD, bool HAS_ROLL_HIST>
 __device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned w)
 {
   const int j = (int)(w & NBR_IDX);
   if (DEM_CPREFETCH >= 2) { prefetch_l2(P.vm + j); prefetch_l2(P.wt + j); }
   const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   if (DEM_CPREFETCH >= 1 && slot >= 0) {
-    const double4 *hp = P.hist + (size_t)(slot * P.pm.hrec) * P.lcap + i;
-    for (int r = 0; r < P.pm.hrec; r++) prefetch_l2(hp + (size_t)r * P.lcap);
+    const int hrec = STD ? (HAS_ROLL_HIST ? 2 : 1) : P.pm.hrec;
+    const double4 *hp = P.hist + (size_t)(slot * hrec) * P.lcap + i;
+    for (int r = 0; r < hrec; r++) prefetch_l2(hp + (size_t)r * P.lcap);
   }
 }
 
@@ -295,22 +304,26 @@ __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const doubl
 //  (1) every lane walks its own row in passes of DEM_SWEEPW entries: the neighbour words, as many independent position gathers in flight,
 //      the touch verdicts; the words of the touching entries go (from registers) into the lane's column of a shared-memory
 //      staging area, and the fetches of what their evaluation will need are started towards L2;
-//  (2a) every lane evaluates the first contacts of its own particle itself -- no owner search, no shared-memory round
-//      trip of operands and results, nearly all lanes busy; how many such rounds is decided per warp by a cost rule;
-//  (2b) the uneven remainder is evaluated COOPERATIVELY: the (particle, contact) items of the 32 particles are dealt out
-//      round-robin to the 32 lanes, each item's force/torque goes through a shared-memory slot back to the owning lane,
-//      which adds its items in list order.  Either way a particle's sum runs in list order and does not depend on which
-//      lane evaluated what: runs are bit reproducible;
+//  (2) ONE loop of contact rounds whose body (pair_item) exists once in the code (the kernel is instruction-fetch sensitive:
+//      with three inlined copies 13 % of the stall samples were "no instruction"):
+//      (a) own rounds: every lane evaluates the first contacts of its own particle -- no owner search, no result round trip,
+//          nearly all lanes busy; how many such rounds is decided per warp by a cost rule;
+//      (b) cooperative rounds: the uneven remainder -- the (particle, contact) items of the 32 particles are dealt out
+//          round-robin to the 32 lanes, each item's force/torque goes through a shared-memory slot back to the owning lane,
+//          which adds its items in list order;
+//      (c) (rare) rounds for the touching entries beyond the DEM_CMAX staged ones, re-read from the row by their owner.
+//      A particle's sum runs in list order and does not depend on which lane evaluated what: runs are bit reproducible;
 //  (3) the owner adds gravity / wall force, integrates, writes its records and votes on the rebuild.
 // Alternatives that were built, found parity-green and measured slower on the 4.19M bed (git history):
 // partner records from shared memory, one evaluation per in-warp pair, a separate sweep kernel, a software-pipelined
-// contact phase.
-template <int NORMAL, int ROLLING, bool ONE, bool F32 = false>
+// contact phase, an owner list in two launches / as a persistent wavefront.
+template <int NORMAL, int ROLLING, bool ONE, bool F32 = false, bool STD = false>
 __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {  // F32: option fp32 -- the contact law in single precision (pair_chain_f32); state, geometry, sums and integration stay fp64
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   __shared__ unsigned s_w[DEM_CMAX][128];
   __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
-  __shared__ double s_res[6][4 * 32 * DEM_RWIN];  // per warp: force / torque of the items of the current window
+  __shared__ double s_res[6][4 * 32];  // per warp: force / torque of the items of the current cooperative round
   __shared__ int s_off[128], s_nh[128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   const bool su = (P.mode != MODE_SETUP);
   bool trig = false;
   double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
-  int nc = 0, nh0 = 0, nn = 0;
+  int nc = 0, nh0 = 0, nn = 0, kov = 0x7fffffff;
 #if DEM_STEP_WAVE_PREFETCH > 0
   {  // pull the streaming inputs of the block that will run one wave later towards L2
     const int ip = i + DEM_STEP_WAVE_PREFETCH * 128;
@@ -340,7 +353,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       nh0 = (nnw >> 16) & 0xffff;
     }
     s_nh[tid] = nh0;
-    for (int k0 = 0; k0 < ((P.debug & 2) ? 0 : nn); k0 += DEM_SWEEPW) {
+    for (int k0 = 0; k0 < ((!STD && (P.debug & 2)) ? 0 : nn); k0 += DEM_SWEEPW) {
       // (1) one pass = DEM_SWEEPW row entries: words, gathers, verdicts -- branch free, then the staging of the touching ones
       unsigned wv[DEM_SWEEPW];
       double4 xv[DEM_SWEEPW];
@@ -355,17 +368,13 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         const double radsum = xi.w + xv[u].w;
         bool t = (k0 + u < nn) && rsq < __dmul_rn(radsum, radsum);
         touch |= (unsigned)t << u;
-        if (P.cdf > 1.0) close |= (unsigned)((k0 + u < nn) && !t && (wv[u] & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << u;
+        if (!STD && P.cdf > 1.0) close |= (unsigned)((k0 + u < nn) && !t && (wv[u] & NBR_HIST) && rsq < P.cdfsq * radsum * radsum) << u;
       }
 #pragma unroll
       for (int u = 0; u < DEM_SWEEPW; u++) {
         if (!((touch >> u) & 1u)) continue;
-        if (nc < DEM_CMAX) { s_w[nc++][tid] = wv[u]; prefetch_contact(P, i, wv[u]); touch &= ~(1u << u); }
-      }
-      while (touch) {  // more than DEM_CMAX contacts (rare): evaluated by the owner on the spot
-        const int u = __ffs((int)touch) - 1;
-        touch &= touch - 1;
-        pair_contact<NORMAL, ROLLING, ONE, F32>(P, i, P.nbr[(size_t)(k0 + u) * P.lcap + i], xi, vi, wi, su, &s_nh[tid], F, T);
+        if (nc < DEM_CMAX) { s_w[nc++][tid] = wv[u]; prefetch_contact<STD, HAS_ROLL_HIST>(P, i, wv[u]); }
+        else kov = min(kov, k0 + u);  // more than DEM_CMAX contacts (rare): rounds (c) re-read the row from here
       }
       while (close) {  // surfacesClose: tangential/rolling history zeroed, flag stays, pair_gran_base.h:420-423
         const int u = __ffs((int)close) - 1;
@@ -375,13 +384,12 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         for (int r = 0; r < P.pm.hrec; r++) st4(P.hist + (size_t)(slot * P.pm.hrec + r) * P.lcap + i, make_double4(0., 0., 0., 0.));
       }
     }
-    if (P.debug & 1) nc = 0;
+    if (!STD && (P.debug & 1)) { nc = 0; kov = 0x7fffffff; }
   }
-  // (2a) own-lane rounds.  Their number minimises (own rounds) x DEM_COST_OWN + (cooperative rounds of 32 items that remain)
-  //      x DEM_COST_COOP for this warp: an own round costs the same whatever the number of busy lanes, a cooperative round
-  //      (owner search, operand and result round trip, owner accumulation) costs more but is always full.
+  // number of own rounds: minimises (own rounds) x DEM_COST_OWN + (cooperative rounds of 32 items that remain) x DEM_COST_COOP
+  // for this warp -- an own round costs the same whatever the number of busy lanes, a cooperative round (owner search,
+  // result round trip, owner accumulation) costs more but is always full.
   int ownr = 0;
-#if DEM_OWNR > 0
   {
     int best = 0x7fffffff;
 #pragma unroll 1
@@ -391,49 +399,55 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       if (cost < best) { best = cost; ownr = r; }
       if (rem == 0) break;
     }
-    const double4 xo = s_rec[0][tid], vo = s_rec[1][tid], wo = s_rec[2][tid];
-#pragma unroll 1
-    for (int r = 0; r < ownr; r++)
-      if (r < nc) pair_contact<NORMAL, ROLLING, ONE, F32>(P, i, s_w[r][tid], xo, vo, wo, su, &s_nh[tid], F, T);
   }
-#endif
-  // (2b) cooperative deal of the remaining items: item t belongs to the last lane whose first item is <= t
-  {
-    const int ncc = max(nc - ownr, 0);
-    int incl = ncc;
+  // cooperative deal of the remaining items: item t belongs to the last lane whose first item is <= t
+  const int ncc = max(nc - ownr, 0);
+  int incl = ncc;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    const int excl = incl - ncc;
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    s_off[tid] = excl;
-    __syncwarp();
-    // rounds of 32 items; results are parked in shared memory and each owner adds its items (in list order) once per
-    // window of DEM_RWIN rounds
-    for (int b0 = 0; b0 < total; b0 += 32 * DEM_RWIN) {
-      const int bend = min(total, b0 + 32 * DEM_RWIN);
-      for (int t0 = b0; t0 < bend; t0 += 32) {
-        const int t = t0 + lane;
-        if (t < total) {
-          int p = 0;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int excl = incl - ncc;
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  s_off[tid] = excl;
+  __syncwarp();
+  const int rcoop = ownr + ((total + 31) >> 5);
+  // (2) the contact rounds
+#pragma unroll 1
+  for (int rnd = 0;; rnd++) {
+    const int phase = rnd < ownr ? 0 : (rnd < rcoop ? 1 : 2);
+    if (phase == 2 && !__any_sync(0xffffffffu, kov < nn)) break;
+    bool valid;
+    int q = tid;
+    unsigned w = 0u;
+    const int t0 = (rnd - ownr) << 5;
+    if (phase == 0) { valid = rnd < nc; if (valid) w = s_w[rnd][tid]; }
+    else if (phase == 1) {
+      const int t = t0 + lane;
+      valid = t < total;
+      if (valid) {
+        int p = 0;
 #pragma unroll
-          for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
-          const int q = wb + p;
-          const unsigned w = s_w[ownr + t - s_off[q]][q];
-          double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
-          pair_contact<NORMAL, ROLLING, ONE, F32>(P, i - tid + q, w, s_rec[0][q], s_rec[1][q], s_rec[2][q], su, &s_nh[q], rF, rT);
-          const int sl = (wb >> 5) * (32 * DEM_RWIN) + (t - b0);
+        for (int s = 16; s; s >>= 1) if (s_off[wb + p + s] <= t) p += s;
+        q = wb + p;
+        w = s_w[ownr + t - s_off[q]][q];
+      }
+    } else { valid = kov < nn; if (valid) { w = P.nbr[(size_t)kov * P.lcap + i]; kov++; } }
+    double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
+    if (valid) pair_item<NORMAL, ROLLING, ONE, F32, STD>(P, i - tid + q, q, w, s_rec, s_nh, su, rF, rT);
+    if (phase == 1) {  // results are parked in shared memory and each owner adds its items (in list order)
+      const int sl = wb + lane;
 #pragma unroll
-          for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
-        }
+      for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
+      __syncwarp();
+      const int qe = min(incl, t0 + 32);
+      for (int k = max(excl, t0); k < qe; k++) {
+        const int so = wb + (k - t0);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { F[d] += s_res[d][so]; T[d] += s_res[3 + d][so]; }
       }
       __syncwarp();
-      const int qe = min(incl, bend);
-      for (int k = max(excl, b0); k < qe; k++) {
-        const int sl = (wb >> 5) * (32 * DEM_RWIN) + (k - b0);
+    } else {
 #pragma unroll
-        for (int d = 0; d < 3; d++) { F[d] += s_res[d][sl]; T[d] += s_res[3 + d][sl]; }
-      }
-      __syncwarp();
+      for (int d = 0; d < 3; d++) { F[d] += rF[d]; T[d] += rT[d]; }
     }
   }
   // (3) owner epilogue
