@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #ifndef DEM_CPREFETCH
 #define DEM_CPREFETCH 2  // L2 prefetch of a staged contact's operands: 0 none, 1 history rows, 2 history + partner v|m, omega|bits
 #endif
+#ifndef DEM_PIPE
+#define DEM_PIPE 0   // contact rounds software pipelined (operands of the next round in flight during the evaluation)
+#endif
 #ifndef DEM_STEP_MINBLOCKS
 #define DEM_STEP_MINBLOCKS 5    // 96 registers; 4 (128 registers) 1.45 ms, 6 (80 registers, spills) 1.42 ms
 #endif
@@ -188,8 +191,43 @@ __device__ __forceinline__ double flip_if(double v, unsigned flip)
 {  // v with its sign bit XORed by `flip` (0 or 0x80000000): history sign without a multiplication
   return __hiloint2double(__double2hiint(v) ^ (int)flip, __double2loint(v));
 }
+__device__ __forceinline__ double4 rec_get(const double2 (*s_rec)[128], int a, int q)
+{
+  const double2 lo = s_rec[2 * a][q], hi = s_rec[2 * a + 1][q];
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void rec_put(double2 (*s_rec)[128], int a, int q, const double4 &v)
+{
+  s_rec[2 * a][q] = make_double2(v.x, v.y); s_rec[2 * a + 1][q] = make_double2(v.z, v.w);
+}
+// operands of one list entry: partner records + the pair's history records (loaded a round ahead, see k_step)
+struct ItemOps { double4 xj, vj, wj, hs, hr; };
+__device__ __forceinline__ double4 ld4(const double4 *p)
+{  // plain (coherent) 256-bit load: history records are rewritten by this kernel
+  double4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+template <int ROLLING, bool STD>
+__device__ __forceinline__ void item_load(const StepP &P, int i, unsigned w, bool valid, ItemOps &o)
+{
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  const int hrec = STD ? (HAS_ROLL_HIST ? 2 : 1) : P.pm.hrec;
+  const int rec_shear = STD ? 0 : P.pm.rec_shear, rec_roll = STD ? 1 : P.pm.rec_roll;
+  const bool tangential = STD ? true : (P.pm.tangential != 0);
+  o.hs = make_double4(0., 0., 0., 0.); o.hr = make_double4(0., 0., 0., 0.);
+  if (!valid) { o.xj = o.vj = o.wj = o.hs; return; }
+  const int j = (int)(w & NBR_IDX);
+  const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+  o.xj = ldg4(P.xr + j); o.vj = ldg4(P.vm + j); o.wj = ldg4(P.wt + j);
+  if (slot >= 0) {
+    const double4 *hp = P.hist + (size_t)(slot * hrec) * P.lcap + i;
+    if (tangential) o.hs = ld4(hp + (size_t)rec_shear * P.lcap);
+    if (HAS_ROLL_HIST) o.hr = ld4(hp + (size_t)rec_roll * P.lcap);
+  }
+}
 template <int NORMAL, int ROLLING, bool ONE, bool F32, bool STD>
-__device__ __forceinline__ void pair_item(const StepP &P, int i, int q, unsigned w, const double4 (*s_rec)[128], int *s_nh, bool su,
+__device__ __forceinline__ void pair_item(const StepP &P, int i, int q, unsigned w, const ItemOps &o, const double2 (*s_rec)[128], int *s_nh, bool su,
                                           double (&Fc)[3], double (&Tc)[3])
 {
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
@@ -199,14 +237,8 @@ __device__ __forceinline__ void pair_item(const StepP &P, int i, int q, unsigned
   const int j = (int)(w & NBR_IDX);
   int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
   const bool had = slot >= 0;
-  const double4 xj = ldg4(P.xr + j), vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
-  double4 hs = make_double4(0., 0., 0., 0.), hr = make_double4(0., 0., 0., 0.);
-  if (had) {
-    const double4 *hp = P.hist + (size_t)(slot * hrec) * P.lcap + i;
-    if (tangential) hs = hp[(size_t)rec_shear * P.lcap];
-    if (HAS_ROLL_HIST) hr = hp[(size_t)rec_roll * P.lcap];
-  }
-  const double4 xi = s_rec[0][q], vi = s_rec[1][q], wi = s_rec[2][q];
+  const double4 &xj = o.xj, &vj = o.vj, &wj = o.wj, &hs = o.hs, &hr = o.hr;
+  const double4 xi = rec_get(s_rec, 0, q), vi = rec_get(s_rec, 1, q), wi = rec_get(s_rec, 2, q);
   const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const double rsq = sq3_rn(dx, dy, dz);
   const double radsum = xi.w + xj.w;
@@ -322,7 +354,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 {  // F32: option fp32 -- the contact law in single precision (pair_chain_f32); state, geometry, sums and integration stay fp64
   constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
   __shared__ unsigned s_w[DEM_CMAX][128];
-  __shared__ double4 s_rec[3][128];   // own records of the block's particles (x|r, v|m, omega|bits)
+  __shared__ double2 s_rec[6][128];   // own records of the block's particles (x|r, v|m, omega|bits) as 16-byte halves: LDS.128 at a 16-byte lane stride is conflict free
   __shared__ double s_res[6][4 * 32];  // per warp: force / torque of the items of the current cooperative round
   __shared__ int s_off[128], s_nh[128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,7 +378,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   {
     double4 xi = make_double4(0., 0., 0., 0.), vi = xi, wi = xi;
     if (active) { xi = ldg4(P.xr + i); vi = ldg4(P.vm + i); wi = ldg4(P.wt + i); }
-    s_rec[0][tid] = xi; s_rec[1][tid] = vi; s_rec[2][tid] = wi;
+    rec_put(s_rec, 0, tid, xi); rec_put(s_rec, 1, tid, vi); rec_put(s_rec, 2, tid, wi);
     if (active && P.have_pair) {
       const int nnw = P.numneigh[i];
       nn = nnw & 0xffff;
@@ -410,18 +442,15 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   s_off[tid] = excl;
   __syncwarp();
   const int rcoop = ownr + ((total + 31) >> 5);
-  // (2) the contact rounds
-#pragma unroll 1
-  for (int rnd = 0;; rnd++) {
-    const int phase = rnd < ownr ? 0 : (rnd < rcoop ? 1 : 2);
-    if (phase == 2 && !__any_sync(0xffffffffu, kov < nn)) break;
+  // (2) the contact rounds, software pipelined: the operands of round r+1 (partner records, history) are loaded while round
+  //     r is evaluated -- a lane's own records come from shared memory when they are used, which is what leaves the registers
+  //     for the second operand set
+  auto select = [&](int rnd, int &q, unsigned &w) -> bool {
     bool valid;
-    int q = tid;
-    unsigned w = 0u;
-    const int t0 = (rnd - ownr) << 5;
-    if (phase == 0) { valid = rnd < nc; if (valid) w = s_w[rnd][tid]; }
-    else if (phase == 1) {
-      const int t = t0 + lane;
+    q = tid; w = 0u;
+    if (rnd < ownr) { valid = rnd < nc; if (valid) w = s_w[rnd][tid]; }
+    else if (rnd < rcoop) {
+      const int t = ((rnd - ownr) << 5) + lane;
       valid = t < total;
       if (valid) {
         int p = 0;
@@ -431,9 +460,25 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         w = s_w[ownr + t - s_off[q]][q];
       }
     } else { valid = kov < nn; if (valid) { w = P.nbr[(size_t)kov * P.lcap + i]; kov++; } }
+    return valid;
+  };
+  int q; unsigned w;
+  bool valid = select(0, q, w);
+  ItemOps oc;
+  item_load<ROLLING, STD>(P, i - tid + q, w, valid, oc);
+#pragma unroll 1
+  for (int rnd = 0;; rnd++) {
+    if (rnd >= rcoop && !__any_sync(0xffffffffu, valid)) break;
+#if DEM_PIPE
+    int qn; unsigned wn;
+    const bool validn = select(rnd + 1, qn, wn);
+    ItemOps on;
+    item_load<ROLLING, STD>(P, i - tid + qn, wn, validn, on);
+#endif
     double rF[3] = {0., 0., 0.}, rT[3] = {0., 0., 0.};
-    if (valid) pair_item<NORMAL, ROLLING, ONE, F32, STD>(P, i - tid + q, q, w, s_rec, s_nh, su, rF, rT);
-    if (phase == 1) {  // results are parked in shared memory and each owner adds its items (in list order)
+    if (valid) pair_item<NORMAL, ROLLING, ONE, F32, STD>(P, i - tid + q, q, w, oc, s_rec, s_nh, su, rF, rT);
+    if (rnd >= ownr && rnd < rcoop) {  // cooperative round: results are parked in shared memory and each owner adds its items (in list order)
+      const int t0 = (rnd - ownr) << 5;
       const int sl = wb + lane;
 #pragma unroll
       for (int d = 0; d < 3; d++) { s_res[d][sl] = rF[d]; s_res[3 + d][sl] = rT[d]; }
@@ -449,11 +494,17 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
 #pragma unroll
       for (int d = 0; d < 3; d++) { F[d] += rF[d]; T[d] += rT[d]; }
     }
+#if DEM_PIPE
+    q = qn; w = wn; valid = validn; oc = on;
+#else
+    valid = select(rnd + 1, q, w);
+    item_load<ROLLING, STD>(P, i - tid + q, w, valid, oc);
+#endif
   }
   // (3) owner epilogue
   if (active) {
     if (P.have_pair) { const int nh = s_nh[tid]; if (nh != nh0) P.numneigh[i] = nn | (nh << 16); }
-    trig = step_epilogue(P, i, s_rec[0][tid], s_rec[1][tid], s_rec[2][tid], F, T);
+    trig = step_epilogue(P, i, rec_get(s_rec, 0, tid), rec_get(s_rec, 1, tid), rec_get(s_rec, 2, tid), F, T);
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }
