@@ -233,6 +233,8 @@ struct dem_engine {
   int cur0 = 0, p2p_ok = 0;
   cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
   // step flags between ranks over peer memory (k_push / k_wait): my flag box, every rank's box, serial of the last hand-over
+  // fused ghost push (fused_halo_setup): image table, block order, device parameter block; fz_on: the next launch_step uses it
+  DevBuf<int> img_first, img_ws, img_in; DevBuf<int4> img_tab; DevBuf<ImgP> imgp; int fz_ready = 0, fz_on = 0, fz_rq[2] = {-1, -1}, slot_zeroed = 0;
   DevBuf<int> fbox; int *peer_fbox[DEM_MAXRANKS] = {nullptr}; int fbox_ready = 0, fserial = 0, fser_slot[2] = {0, 0}, fpeer[2] = {0, 0};
   int *hflag_dev = nullptr; int fev_peer[2] = {0, 0};  // slot's flags arrive through k_wait (serial in hflag[16 + slot]) instead of memcpy + event
   int fslot = 0;                            // slot the next step writes
@@ -355,7 +357,7 @@ extern "C" void dem_destroy(dem_engine *e)
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   if (e->hflag) host_small_free(e->hflag);
   for (int k = 0; k < 2; k++) if (e->fev[k]) cudaEventDestroy(e->fev[k]);
-  e->hsig.release(); e->fbox.release();
+  e->hsig.release(); e->fbox.release(); e->img_first.release(); e->img_tab.release(); e->imgp.release(); e->img_ws.release(); e->img_in.release();
   if (e->hcnt) host_small_free(e->hcnt);
   if (e->comm) {
     if (e->comm_bad || getenv("DEM_B200_NO_COMM_CACHE")) g_nccl.CommDestroy(e->comm);
@@ -1350,6 +1352,125 @@ static void halo_p2p_setup(dem_engine *E)
   }
 }
 
+// developer aid: DEM_B200_TRACE=1 prints the host+device time of each rebuild stage (synchronises at every mark)
+struct StageTrace {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+  explicit StageTrace(cudaStream_t s) : on(getenv("DEM_B200_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what)
+  {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dem trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+// ---- fused ghost push.  After the borders of a rebuild every ghost slot of every rank is a copy of ONE owned particle of
+// this rank or of a neighbour rank (one decomposed dimension: a ghost crosses at most one rank boundary; the periodic images
+// of the other dimensions are made on the rank).  Here every rank learns, per owned particle, all the slots that hold a copy
+// of it -- "direct" ghosts on the two neighbours (entry k of my send list = their slot pgfirst + k), the periodic images the
+// neighbours make of those ghosts (they report them: swap, entry, slot, shift), and its own periodic images -- so that the
+// step kernel can store a particle's new records into all of them from its epilogue (step_epilogue); one k_handshake launch
+// per step then publishes the exchange and the step flags and waits for the neighbours' (k_flags_host on a single rank).
+// comm_brick.cpp:563-645 (forward_comm) is what this replaces between two rebuilds: no pack kernel, no send/recv, no wait
+// launch per swap.  The table is assembled on the device (k_img_chain / k_img_local / k_img_remote, linked entries per
+// particle); any unsupported constellation keeps the k_push path.
+static void fused_halo_setup(dem_engine *E)
+{
+  E->fz_ready = 0;
+  if (E->opt.count("fused_halo") && E->opt["fused_halo"] == 0) return;
+  const bool solo = E->nranks == 1;  // one rank: only its own periodic images (fz_ready = 2)
+  if (!solo && (!E->p2p_ok || E->fbox_ready != 1)) return;
+  int ndec = 0;
+  for (int d = 0; d < 3; d++) if (E->pgrid[d] > 1) ndec++;
+  if (!solo && ndec != 1) return;
+  int rq[2] = {-1, -1};
+  for (int q = 0; q < E->nswap; q++) if (!E->swaps[q].self) rq[E->swaps[q].side] = q;
+  if (!solo && (rq[0] < 0 || rq[1] < 0)) return;
+  if (solo && E->nswap == 0) return;
+  cudaStream_t st = E->stream;
+  const int nl = (int)E->nlocal, ng = (int)E->nghost;
+  auto shiftcode = [](const dem_engine::Swap &W) { return W.shift == 0.0 ? 0 : ((W.shift > 0.0 ? 1 : 2) << (2 * W.dim)); };
+  // work space: gsrc [ng] int4, two report buffers [3 ng] int, counters [4]
+  E->img_ws.ensure(E, (size_t)4 * std::max(ng, 1) + (size_t)6 * std::max(ng, 1) + 16);
+  int4 *gsrc = (int4 *)E->img_ws.p;
+  int *rep[2] = {E->img_ws.p + 4 * (size_t)std::max(ng, 1), E->img_ws.p + 7 * (size_t)std::max(ng, 1)};
+  int *cnt = E->img_ws.p + 10 * (size_t)std::max(ng, 1);
+  CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
+  for (int q = 0; q < E->nswap; q++) {  // origin of every ghost slot, swap after swap
+    const dem_engine::Swap &W = E->swaps[q];
+    if (!W.nrecv) continue;
+    if (W.gfirst < nl || W.gfirst + W.nrecv > nl + ng) return;
+    k_img_chain<<<GRID(W.nrecv, 256), 256, 0, st>>>(W.nrecv, W.list.p, nl, W.gfirst, W.self, W.side, shiftcode(W), gsrc, rep[0], rep[1], cnt);
+    E->launches++;
+  }
+  int hc[4] = {0, 0, 0, 0};
+  if (!solo) { CK(cudaMemcpyAsync(hc, cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+  // the neighbours' reports about the ghosts I sent them
+  int nrep_in[2] = {0, 0};
+  for (int sd = 0; sd < 2 && !solo; sd++) {
+    const dem_engine::Swap &W = E->swaps[rq[sd]];
+    const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+    // my reports about this side's swap go to the rank that sent it to me; I get the reports of the rank I sent it to
+    int sv[1] = {hc[sd]}, rv[1] = {0};
+    xchg_ints(E, peer_recv, sv, peer_send, rv, 1);
+    nrep_in[sd] = rv[0];
+  }
+  const size_t ntab = (size_t)ng + (solo ? 0 : (size_t)E->swaps[rq[0]].nsend + E->swaps[rq[1]].nsend + nrep_in[0] + nrep_in[1]);
+  E->img_first.ensure(E, (size_t)std::max(nl, 1)); E->img_tab.ensure(E, ntab + 1); E->imgp.ensure(E, 1);
+  E->img_in.ensure(E, 3 * (size_t)(nrep_in[0] + nrep_in[1]) + 4);
+  CK(cudaMemsetAsync(E->img_first.p, 0xff, sizeof(int) * (size_t)std::max(nl, 1), st));
+  if (ng) { k_img_local<<<GRID(ng, 256), 256, 0, st>>>(ng, nl, gsrc, E->img_first.p, E->img_tab.p); E->launches++; }
+  size_t base = ng;
+  for (int sd = 0; sd < 2 && !solo; sd++) {
+    dem_engine::Swap &W = E->swaps[rq[sd]];
+    const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+    int *in = E->img_in.p + 3 * (size_t)(sd ? nrep_in[0] : 0);
+    if ((peer_recv >= 0 && hc[sd]) || (peer_send >= 0 && nrep_in[sd])) {
+      NK(g_nccl.GroupStart());
+      if (peer_recv >= 0 && hc[sd]) NK(g_nccl.Send(rep[sd], 3 * (size_t)hc[sd], ncclInt, peer_recv, E->comm, st));
+      if (peer_send >= 0 && nrep_in[sd]) NK(g_nccl.Recv(in, 3 * (size_t)nrep_in[sd], ncclInt, peer_send, E->comm, st));
+      NK(g_nccl.GroupEnd());
+    }
+    if (peer_send >= 0 && W.p2p) {
+      const int sc = shiftcode(W);
+      if (W.nsend) k_img_remote<<<GRID(W.nsend, 256), 256, 0, st>>>(W.nsend, 1, nullptr, W.list.p, W.nsend, nl, gsrc, 1 + sd, W.pgfirst, sc, (int)base, E->img_first.p, E->img_tab.p, cnt);
+      if (nrep_in[sd]) k_img_remote<<<GRID(nrep_in[sd], 256), 256, 0, st>>>(nrep_in[sd], 0, in, W.list.p, W.nsend, nl, gsrc, 1 + sd, W.pgfirst, sc, (int)(base + W.nsend), E->img_first.p, E->img_tab.p, cnt);
+      E->launches += 2;
+    }
+    base += (size_t)W.nsend + nrep_in[sd];
+  }
+  ImgP I; memset(&I, 0, sizeof I);
+  for (int b = 0; b < 2; b++) { I.bx[0][b] = E->xr[b].p; I.bv[0][b] = E->vm[b].p; I.bw[0][b] = E->wt[b].p; }
+  if (solo) E->cur0 = E->cur;
+  I.pcur0[0] = E->cur0;
+  for (int sd = 0; sd < 2 && !solo; sd++) {
+    dem_engine::Swap &W = E->swaps[rq[sd]];
+    const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1);
+    if (peer_send < 0 || !W.p2p) continue;
+    for (int b = 0; b < 2; b++) { I.bx[1 + sd][b] = W.pbase[0 + b]; I.bv[1 + sd][b] = W.pbase[2 + b]; I.bw[1 + sd][b] = W.pbase[4 + b]; }
+    I.pcur0[1 + sd] = W.pcur0;
+  }
+  for (int d = 0; d < 3; d++) I.prd[d] = E->prd[d];
+  CK(cudaMemcpyAsync(E->imgp.p, &I, sizeof I, cudaMemcpyHostToDevice, st));
+  // unsupported constellation anywhere: every rank keeps the pack-kernel path
+  CK(cudaMemcpyAsync(hc, cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int ok = hc[2] ? 0 : 1;
+  if (!solo) {
+    E->hcnt[0] = ok;
+    CK(cudaMemcpyAsync(E->cnt_dev.p, E->hcnt, sizeof(int), cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllReduce(E->cnt_dev.p, E->cnt_dev.p + 1, 1, ncclInt, ncclMin, E->comm, st));
+    CK(cudaMemcpyAsync(E->hcnt + 1, E->cnt_dev.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ok = E->hcnt[1];
+  }
+  if (!ok) return;
+  E->fz_rq[0] = rq[0]; E->fz_rq[1] = rq[1];
+  E->fz_ready = solo ? 2 : 1;
+}
+
 // flags -> deterministic compact list; returns the number of set flags
 static int compact_flags(dem_engine *E, int n, DevBuf<int> &flag, DevBuf<int> &scan, DevBuf<int> &list)
 {
@@ -1402,6 +1523,7 @@ static void do_swap(dem_engine *E, dem_engine::Swap *Ws, int nsw, bool allow_p2p
       E->fser_slot[flags_slot] = E->fserial;
     }
     Wt.timeout_flag = E->hsig.p + 15;
+    if (with_flags) Wt.zero_next = flag_slot(E, flags_slot ^ 1);
     k_push<<<(unsigned)(Q.nb[0] + Q.nb[1] + 1), 256, 0, st>>>(Q);
     k_wait<<<1, 32, 0, st>>>(Wt);
     E->launches += 2;
@@ -1548,20 +1670,6 @@ static int migrate(dem_engine *E, int ncur, int &ngone)
   }
   return ncur;
 }
-
-// developer aid: DEM_B200_TRACE=1 prints the host+device time of each rebuild stage (synchronises at every mark)
-struct StageTrace {
-  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
-  explicit StageTrace(cudaStream_t s) : on(getenv("DEM_B200_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char *what)
-  {
-    if (!on) return;
-    cudaStreamSynchronize(st);
-    const auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[dem trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
 
 // Neighbor rebuild: verlet.cpp:305-328 (pre_exchange .. neighbor->build) re-designed for the GPU.
 static void rebuild(dem_engine *E)
@@ -1740,6 +1848,8 @@ static void rebuild(dem_engine *E)
   tr.mark("mesh + hold + wall index");
   halo_p2p_setup(E);
   tr.mark("halo p2p setup");
+  fused_halo_setup(E);
+  tr.mark("fused halo setup");
   E->ago = 0;
   E->order_valid = 0;
   E->nbuilds++;
@@ -1768,6 +1878,11 @@ static StepP step_params(dem_engine *E, int mode)
   for (int d = 0; d < 3; d++) P.g[d] = E->g[d];
   P.have_g = E->have_g; P.have_pair = E->have_pair; P.freezebit = E->freezebit; P.integbit = E->integbit;
   P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = flag_slot(E, E->fslot); P.gate = E->gate; P.gate_mask = E->gate_mask; P.ncontact = nullptr;
+  P.img = nullptr; P.img_first = nullptr; P.img_tab = nullptr;
+  if (E->fz_on) {  // fused ghost push: this launch writes buffer cur ^ 1
+    P.img = E->imgp.p; P.img_first = E->img_first.p; P.img_tab = E->img_tab.p;
+    P.img_par = (E->cur ^ 1) ^ E->cur0;
+  }
   return P;
 }
 
@@ -1879,10 +1994,11 @@ static int *flag_slot(dem_engine *E, int slot) { return E->dflag.p + 8 * slot; }
 static const int *gate_slot(dem_engine *E, int slot) { return E->nranks > 1 ? E->dflag.p + 8 * slot + 4 : E->dflag.p + 8 * slot; }
 static void clear_flags(dem_engine *E)
 {
-  E->dflag.ensure(E, 16);
+  E->dflag.ensure(E, 24);
   CK(cudaStreamSynchronize(E->stream));
   for (int k = 0; k < 8; k++) E->hflag[k] = 0;
-  CK(cudaMemsetAsync(E->dflag.p, 0, 16 * sizeof(int), E->stream));
+  CK(cudaMemsetAsync(E->dflag.p, 0, 24 * sizeof(int), E->stream));
+  E->slot_zeroed = 1;
 }
 // after a step: reduce its flags over the ranks, start the copy to the host, mark the point with an event
 static void post_flags(dem_engine *E, int slot, bool sent_with_halo = false)
@@ -1915,6 +2031,50 @@ static void wait_flags(dem_engine *E, int slot)
     return;
   }
   if (E->fev[slot]) CK(cudaEventSynchronize(E->fev[slot]));
+}
+
+// fused ghost push: usable for this launch?  (plain step kernel only; decks with mesh walls keep the pack-kernel path)
+static bool fused_on(dem_engine *E, int mode)
+{
+  return E->fz_ready && mode != MODE_SETUP && E->ls[E->lcur].fmt == 0 && !(E->have_pair && E->pm.cohesion) && !have_mesh_walls(E) && E->nlocal > 0;
+}
+// One step on the stream: the step launch, the ghost refresh, the flag hand-over.
+//  * fused ghost push (fz_ready): the step kernel stores every copy of a particle's new records from its epilogue; several
+//    ranks: one k_handshake launch publishes the exchange + this rank's flags and waits for the neighbours' / everybody's;
+//    one rank: one k_flags_host launch hands the flags to the host.
+//  * otherwise: pack kernels / k_push + k_wait (forward_comm) and post_flags.
+static void step_and_comm(dem_engine *E, int mode, int slot)
+{
+  const bool fz = fused_on(E, mode);
+  E->fz_on = fz ? 1 : 0;
+  launch_step(E, mode, true);
+  E->fz_on = 0;
+  E->cur ^= 1;
+  if (!fz) { const bool sent = forward_comm(E, slot); post_flags(E, slot, sent); E->slot_zeroed = sent ? 1 : 0; return; }
+  E->fserial++; E->fser_slot[slot] = E->fserial;
+  if (E->nranks == 1) {
+    if (!E->hflag_dev) { void *dp = nullptr; CK(cudaHostGetDevicePointer(&dp, E->hflag, 0)); E->hflag_dev = (int *)dp; }
+    k_flags_host<<<1, 32, 0, E->stream>>>(flag_slot(E, slot), E->hflag_dev + 4 * slot, E->hflag_dev + 16 + slot, E->fserial, flag_slot(E, slot ^ 1));
+  } else {
+    ShakeP Q; memset(&Q, 0, sizeof Q);
+    WaitP &Wt = Q.W;
+    for (int sd = 0; sd < 2; sd++) {
+      dem_engine::Swap &W = E->swaps[E->fz_rq[sd]];
+      W.serial++;
+      const int peer_send = neighbor_rank(E, W.dim, W.side ? 1 : -1), peer_recv = neighbor_rank(E, W.dim, W.side ? -1 : 1);
+      if (peer_send >= 0) { Q.sig_out[sd] = W.psig + E->fz_rq[sd]; Q.serial_out[sd] = W.serial; }
+      if (peer_recv >= 0) { Wt.sig[sd] = E->hsig.p + E->fz_rq[sd]; Wt.serial[sd] = W.serial; }
+    }
+    Q.myflags = flag_slot(E, slot); Q.me = E->rank;
+    for (int r = 0; r < E->nranks; r++) Q.peer_box[r] = E->peer_fbox[r];
+    Wt.with_flags = 1; Wt.box = E->fbox.p; Wt.nranks = E->nranks; Wt.slot = slot; Wt.fserial = E->fserial;
+    Wt.gate_out = flag_slot(E, slot) + 4; Wt.host_out = E->hflag_dev + 4 * slot; Wt.host_serial = E->hflag_dev + 16 + slot;
+    Wt.timeout_flag = E->hsig.p + 15; Wt.zero_next = flag_slot(E, slot ^ 1);
+    k_handshake<<<1, 32, 0, E->stream>>>(Q);
+  }
+  E->launches++;
+  E->fev_peer[slot] = 1;  // wait_flags spins on the serial word of the page-locked block
+  E->slot_zeroed = 1;
 }
 
 static void collect_timing(dem_engine *E)
@@ -1996,15 +2156,13 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   // kernel(s), the ghost refresh and the flag hand-over
   auto issue_step = [&](long s, int slot) {
     e->fslot = slot;
-    CK(cudaMemsetAsync(flag_slot(e, slot), 0, 8 * sizeof(int), st));
+    if (!e->slot_zeroed) CK(cudaMemsetAsync(flag_slot(e, slot), 0, 8 * sizeof(int), st));  // (else the previous hand-over zeroed it: k_wait / the step kernel's last block)
     if (moving) {
       MeshP M = mesh_params(e);
       for (size_t m = 0; m < e->meshes.size(); m++)
         if (e->meshes[m].moving) { mesh_launch_move(M, (int)m, e->dt, 0.25 * e->skin * e->skin, flag_slot(e, slot), e->gate, e->gate_mask, st); e->launches++; }
     }
-    launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
-    e->cur ^= 1;
-    post_flags(e, slot, forward_comm(e, slot));
+    step_and_comm(e, s == nsteps ? MODE_LAST : MODE_STEP, slot);
   };
   for (long s = 1; s <= nsteps; s++) {
     e->ntimestep++;
@@ -2044,9 +2202,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
       (void)was_moving;
       // the step itself, not gated; its mesh motion has been done above
       e->fslot = slot;
-      launch_step(e, s == nsteps ? MODE_LAST : MODE_STEP, true);
-      e->cur ^= 1;
-      post_flags(e, slot, forward_comm(e, slot));
+      step_and_comm(e, s == nsteps ? MODE_LAST : MODE_STEP, slot);
     }
     if (e->ev_used >= 2048) { CK(cudaStreamSynchronize(st)); collect_timing(e); }
   }

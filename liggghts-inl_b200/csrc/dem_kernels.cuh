@@ -319,6 +319,22 @@ __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const doubl
       }
     }
     st4(P.xr_o + i, xo); st4(P.vm_o + i, vo); st4(P.wt_o + i, wo);
+    if (P.img_first) {  // fused ghost push: every copy of this particle (ghost slots of the neighbour ranks, periodic images here)
+      int k = P.img_first[i];
+      if (k >= 0) {
+        const ImgP &I = *P.img;
+        for (; k >= 0;) {
+          const int4 e = P.img_tab[k];
+          k = e.z;
+          const int t = (e.x >> 28) & 3, slot = e.x & 0x0fffffff, b = I.pcur0[t] ^ P.img_par;
+          double4 xs = xo;
+          if (e.y & 3) xs.x += (e.y & 1) ? I.prd[0] : -I.prd[0];
+          if (e.y & 12) xs.y += (e.y & 4) ? I.prd[1] : -I.prd[1];
+          if (e.y & 48) xs.z += (e.y & 16) ? I.prd[2] : -I.prd[2];
+          st4(I.bx[t][b] + slot, xs); st4(I.bv[t][b] + slot, vo); st4(I.bw[t][b] + slot, wo);
+        }
+      }
+    }
     if (P.mode == MODE_STEP) {
       const double4 xh = P.xh[i];
       trig = sq3_rn(xo.x - xh.x, xo.y - xh.y, xo.z - xh.z) > P.trigsq;
@@ -372,6 +388,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
       prefetch_l2(P.xr + ip); prefetch_l2(P.vm + ip); prefetch_l2(P.wt + ip); prefetch_l2(P.xh + ip);
       if (lane < 12) prefetch_l2(P.nbr + (size_t)lane * P.lcap + (ip - lane));
       else if (lane == 12) prefetch_l2(P.numneigh + (ip - lane));
+      else if (lane == 13 && P.img_first) prefetch_l2(P.img_first + (ip - lane));
     }
   }
 #endif
@@ -719,9 +736,6 @@ __global__ void k_halo_signal(volatile int *peer_signal, int serial) { *peer_sig
 // hand-over of this rank's step flags to EVERY rank.  The reference reduces the rebuild decision with MPI_Allreduce
 // (neighbor.cpp:1463); here each rank stores its four flag words into its column of every peer's flag box over NVLink peer
 // memory and publishes a serial number; k_wait (below) ORs the columns.  No NCCL call between two rebuilds.
-#define DEM_MAXRANKS 16
-#define FBOX_SERIAL (2 * DEM_MAXRANKS * 4)   // int offset of the serial words in a flag box: [2 slots][DEM_MAXRANKS][4] flags, then [DEM_MAXRANKS] serials
-#define FBOX_INTS (FBOX_SERIAL + DEM_MAXRANKS)
 struct PushP {
   SwapP S[2]; int nb[2]; unsigned *done[2]; volatile int *sig[2]; int serial[2]; int nsw;
   const int *myflags; int *peer_box[DEM_MAXRANKS]; int me, nranks, slot, fserial, with_flags;
@@ -764,6 +778,7 @@ struct WaitP {
   const volatile int *sig[2]; int serial[2];
   const int *box; int nranks, slot, fserial, with_flags;
   int *gate_out; int *host_out; volatile int *host_serial; int *timeout_flag;
+  int *zero_next;  // the flag slot the NEXT step will write (8 ints), zeroed here instead of by a memset node per step
 };
 __global__ void k_wait(const WaitP Q)
 {  // one warp; every wait is bounded (~4 s): a lost peer must not hang the device
@@ -776,6 +791,7 @@ __global__ void k_wait(const WaitP Q)
     while (*ser < Q.fserial) { __nanosleep(64); if (clock64() - t0 > limit) { ok = false; break; } }
   }
   if (!ok) *Q.timeout_flag = 1;
+  if (Q.zero_next && t < 8) Q.zero_next[t] = 0;
   __syncwarp();
   __threadfence_system();
   if (Q.with_flags) {
@@ -789,6 +805,55 @@ __global__ void k_wait(const WaitP Q)
     if (t == 0) *Q.host_serial = Q.fserial;
   }
 }
+// Fused ghost push (dem_engine.cu fused_halo_setup): the step kernel has stored the ghost copies from its epilogue and has
+// completed (stream order: its peer stores are performed), so ONE warp publishes the exchange's serial number in both
+// receivers' signal words, hands this rank's step flags to every rank's flag box, and then waits like k_wait.
+struct ShakeP { int *sig_out[2]; int serial_out[2]; const int *myflags; int *peer_box[DEM_MAXRANKS]; int me; WaitP W; };
+__global__ void k_handshake(const ShakeP Q)
+{
+  const int t = threadIdx.x;
+  __threadfence_system();
+  if (t < 2 && Q.sig_out[t]) *(volatile int *)Q.sig_out[t] = Q.serial_out[t];
+  if (t < Q.W.nranks) {
+    int *box = Q.peer_box[t];
+#pragma unroll
+    for (int k = 0; k < 4; k++) box[(Q.W.slot * DEM_MAXRANKS + Q.me) * 4 + k] = Q.myflags[k];
+    __threadfence_system();
+    ((volatile int *)box)[FBOX_SERIAL + Q.me] = Q.W.fserial;
+  }
+  // receiver side (== k_wait)
+  const WaitP &W = Q.W;
+  const long long t0 = clock64(), limit = 8000000000LL;
+  bool ok = true;
+  if (t < 2 && W.sig[t]) while (*W.sig[t] < W.serial[t]) { __nanosleep(64); if (clock64() - t0 > limit) { ok = false; break; } }
+  if (t < W.nranks) {
+    const volatile int *ser = (const volatile int *)W.box + FBOX_SERIAL + t;
+    while (*ser < W.fserial) { __nanosleep(64); if (clock64() - t0 > limit) { ok = false; break; } }
+  }
+  if (!ok) *W.timeout_flag = 1;
+  if (W.zero_next && t < 8) W.zero_next[t] = 0;
+  __syncwarp();
+  __threadfence_system();
+  if (t < 4) {
+    int v = 0;
+    for (int r = 0; r < W.nranks; r++) v = max(v, ((const volatile int *)W.box)[(W.slot * DEM_MAXRANKS + r) * 4 + t]);
+    W.gate_out[t] = v; W.host_out[t] = v;
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (t == 0) *W.host_serial = W.fserial;
+}
+// single rank: the step's flags to the host's page-locked block (flags, then the serial) and the next step's flag slot
+// zeroed -- one tiny launch instead of a memset node, a D2H copy and an event per step
+__global__ void k_flags_host(const int *flags, int *host_out, volatile int *host_serial, int serial, int *zero_next)
+{
+  const int t = threadIdx.x;
+  if (t < 4) host_out[t] = ((const volatile int *)flags)[t];
+  if (t < 8) zero_next[t] = 0;
+  __syncwarp();
+  __threadfence_system();
+  if (t == 0) *host_serial = serial;
+}
 __global__ void k_halo_wait(const volatile int *sig_a, int serial_a, const volatile int *sig_b, int serial_b, int *timeout_flag)
 {  // bounded (~4 s): a lost peer must not hang the device
   const long long t0 = clock64();
@@ -796,6 +861,53 @@ __global__ void k_halo_wait(const volatile int *sig_a, int serial_a, const volat
   if (sig_a) while (*sig_a < serial_a) { __nanosleep(64); if (clock64() - t0 > limit) { *timeout_flag = 1; return; } }
   if (sig_b) while (*sig_b < serial_b) { __nanosleep(64); if (clock64() - t0 > limit) { *timeout_flag = 1; return; } }
   __threadfence_system();
+}
+// ---- image table of the fused ghost push, built on the device at the end of a rebuild (dem_engine.cu fused_halo_setup).
+// gsrc[g] = origin of ghost slot nlocal + g: (kind, a, code) with kind 0: my owned particle a; kind 1 + side: entry a of the
+// remote swap of that side as I received it; code = accumulated periodic shifts (2 bits per dimension: +prd, -prd).
+// Entries of a particle form a linked list headed by img_first[particle] (order irrelevant: independent stores).
+__device__ __forceinline__ void img_link(int *first, int4 *tab, int root, int idx, int slot_t, int code)
+{
+  tab[idx] = make_int4(slot_t, code, atomicExch(first + root, idx), 0);
+}
+__global__ void __launch_bounds__(256) k_img_chain(int n, const int *list, int nl, int gfirst, int self, int side, int shiftcode, int4 *gsrc,
+                                                   int *rep0, int *rep1, int *cnt)
+{  // the new ghosts of one swap (swaps in order); cnt[0..1]: report counters, cnt[2]: unsupported constellation
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int g = gfirst + q - nl;
+  if (!self) { gsrc[g] = make_int4(1 + side, q, 0, 0); return; }
+  const int sidx = list[q];
+  int4 r = sidx < nl ? make_int4(0, sidx, 0, 0) : gsrc[sidx - nl];
+  if (((r.z | (r.z >> 1)) & (shiftcode | (shiftcode >> 1)) & 0x15) != 0) cnt[2] = 1;  // two shifts in one dimension
+  r.z |= shiftcode;
+  gsrc[g] = r;
+  if (r.x) {  // a periodic image of a ghost I received: its owner must learn about this copy
+    int *rep = r.x == 1 ? rep0 : rep1;
+    const int j = atomicAdd(cnt + (r.x - 1), 1);
+    rep[3 * j] = r.y; rep[3 * j + 1] = nl + g; rep[3 * j + 2] = r.z;
+  }
+}
+__global__ void __launch_bounds__(256) k_img_local(int ng, int nl, const int4 *gsrc, int *first, int4 *tab)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const int4 r = gsrc[g];
+  if (r.x == 0) img_link(first, tab, r.y, g, nl + g, r.z);
+}
+__global__ void __launch_bounds__(256) k_img_remote(int n, int direct, const int *rep, const int *list, int nsend, int nl, const int4 *gsrc, int target,
+                                                    int pgfirst, int shiftcode, int base, int *first, int4 *tab, int *cnt)
+{  // direct: entry k of my send list sits in the receiver's slot pgfirst + k; else: the receiver's reports (entry, slot, code)
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int k = direct ? q : rep[3 * q];
+  if (k < 0 || k >= nsend) { cnt[2] = 1; return; }
+  const int sidx = list[k];
+  int root = sidx, code = 0;
+  if (sidx >= nl) { const int4 r = gsrc[sidx - nl]; if (r.x) { cnt[2] = 1; return; } root = r.y; code = r.z; }  // (a ghost forwarded over two rank boundaries: not a slab decomposition)
+  const int extra = direct ? 0 : rep[3 * q + 2];
+  if ((((code | shiftcode) | ((code | shiftcode) >> 1)) & (extra | (extra >> 1)) & 0x15) != 0 || ((code | (code >> 1)) & (shiftcode | (shiftcode >> 1)) & 0x15) != 0) { cnt[2] = 1; return; }
+  img_link(first, tab, root, base + q, (direct ? pgfirst + k : rep[3 * q + 1]) | (target << 28), code | shiftcode | extra);
 }
 __global__ void __launch_bounds__(256) k_pack_int(int n, const int *list, const int *src, int *out)
 {

@@ -50,6 +50,19 @@ struct WallP {
 
 enum { MODE_SETUP = 0, MODE_STEP = 1, MODE_LAST = 2 };
 
+#define DEM_MAXRANKS 16
+#define FBOX_SERIAL (2 * DEM_MAXRANKS * 4)   // int offset of the serial words in a flag box: [2 slots][DEM_MAXRANKS][4] flags, then [DEM_MAXRANKS] serials
+#define FBOX_INTS (FBOX_SERIAL + DEM_MAXRANKS)
+// Fused ghost push (several ranks, one decomposed dimension; dem_engine.cu fused_halo_setup): between two rebuilds the step
+// kernel itself stores every COPY of a particle's new records -- the ghost slots on the neighbour ranks over NVLink peer
+// memory and the periodic images on its own rank -- from its epilogue.  The parameters below are constant between two rebuilds
+// and live in device memory.
+struct ImgP {
+  double4 *bx[3][2], *bv[3][2], *bw[3][2];  // [target][buffer]: 0 this rank, 1 the rank swap 0 sends to, 2 the rank swap 1 sends to
+  int pcur0[3];                              // the target's buffer parity at the rebuild (target 0: cur0)
+  double prd[3];
+};
+
 struct StepP {
   int nlocal, nall, cap, maxk;
   int lcap;  // row stride of the ELLPACK arrays (nbr, hist)
@@ -89,6 +102,10 @@ struct StepP {
   const int *gate;
   int gate_mask;  // bit0: gate[0] (distance check due this step), bit2: gate[2] (a moving mesh forces the rebuild)
   unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
+  // fused ghost push (null / unused otherwise): image table of the owned particles (img_first[i]: first entry or -1; entry =
+  // (slot | target << 28, shift code, next entry or -1, 0)) and this launch's buffer parity
+  const ImgP *img; const int *img_first; const int4 *img_tab;
+  int img_par;
 };
 
 }  // namespace dem
