@@ -181,6 +181,14 @@ int dem_get_stats(dem_engine *e, dem_stats *out);
  * force evaluation that materialised forces (dem_setup, or the last step of dem_run): own tag, partner tag, the force and
  * the torque the pair applies to the owned particle -- a pair of two owned particles gives two rows, one per particle,
  * ordered by (own tag, partner tag).  Plain contact models only.                                                        */
+/* compute bond/counter (compute_bond_counter.cpp:101-138, hooks cohesion_model_bond.h:546,1032,1066) as the reference's
+ * lammps_extract_compute returns its vector between two runs: out6[0] bonds created since the last call, [1] bonds broken since
+ * the last call, [2] "total" = counted + created - broken in unsigned 32-bit arithmetic -- the reference counts existing bonds
+ * only on the step after an invocation inside a run (Modify::init resets invoked_vector at every run start), so between runs
+ * `counted` is 0 and the entry wraps when more bonds broke than formed; the existing bonds are the set flags of
+ * dem_download_pairs.  [3..5] wall bonds: always 0 (out of scope).  Summed over the ranks.  Only the linear bond model feeds
+ * the counter (bond/nonlinear looks for a compute style that does not exist, cohesion_model_bond_nonlinear.h:381). */
+int dem_bond_counter(dem_engine *e, double *out6);
 int dem_contact_count(dem_engine *e, long *n);
 int dem_download_contacts(dem_engine *e, int *tag, int *partner, double *force, double *torque);
 

@@ -133,10 +133,10 @@ __device__ __forceinline__ void contact_chain(const StepP &P, const ModelP &M, c
     if (mag > 0.) {
       double r1, r2, r3;
       if (WALL) {
-        const double FnS = deltan * kn;
+        const double FnS = M.cdtnl2 ? Fn : deltan * kn;  // cdtnonlinear2: rolling_model_cdtnonlinear2.h:127
         r1 = rmu * FnS * a1 / mag * reff; r2 = rmu * FnS * a2 / mag * reff; r3 = rmu * FnS * a3 / mag * reff;
       } else {
-        const double sc = rmu * kn * deltan * reff / mag;
+        const double sc = M.cdtnl2 ? rmu * Fn * reff / mag : rmu * kn * deltan * reff / mag;  // cdtnonlinear2: :157
         r1 = a1 * sc; r2 = a2 * sc; r3 = a3 * sc;
       }
       if (!M.torsion) {
@@ -309,7 +309,7 @@ __device__ __forceinline__ void pair_chain(const StepP &P, const ModelP &M, cons
       double mag, inv_mag;
       sqrt_rsqrt_fast(a1 * a1 + a2 * a2 + a3 * a3, mag, inv_mag);
       if (mag > 0.) {
-        const double sc = rmu * kn * deltan * reff * inv_mag;
+        const double sc = (!STD && M.cdtnl2) ? rmu * Fn * reff * inv_mag : rmu * kn * deltan * reff * inv_mag;  // cdtnonlinear2: rolling_model_cdtnonlinear2.h:157
         double r1 = a1 * sc, r2 = a2 * sc, r3 = a3 * sc;
         if (!m_torsion) {
           const double dot = r1 * enx + r2 * eny + r3 * enz;
@@ -454,7 +454,7 @@ __device__ __forceinline__ void pair_chain_f32(const StepP &P, const ModelP &M, 
     if (ROLLING == R_CDT) {
       const float asq = a1 * a1 + a2 * a2 + a3 * a3;
       if (asq > 0.f) {
-        const float sc = rmu * kn * deltan * reff * rsqrt_f32(asq);
+        const float sc = (M.cdtnl2 ? rmu * Fn * reff : rmu * kn * deltan * reff) * rsqrt_f32(asq);
         float r1 = a1 * sc, r2 = a2 * sc, r3 = a3 * sc;
         if (!M.torsion) {
           const float dot = r1 * enx + r2 * eny + r3 * enz;
@@ -535,8 +535,8 @@ __device__ __forceinline__ double nl_torque_comp(double theta, double &tmax, dou
 template <int COH>
 __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const double *delta, double rsq, double radi, double radj,
                                        const double *xi, const double *vi, const double *vj, const double *omegai, const double *omegaj,
-                                       int it, int jt, bool update_history, double *H, double *F, double *Ti, double *Tj)
-{
+                                       int it, int jt, bool update_history, double *H, double *F, double *Ti, double *Tj, int &events)
+{  // events: bit 0 a bond was created, bit 1 a bond broke (compute bond/counter, cohesion_model_bond.h:1032,1066)
   constexpr bool NL = (COH == C_BONDNL);
   const double lambda = tabv(P, T_B_LAMBDA, it, jt);
   if (lambda < 1.e-15) return false;
@@ -548,10 +548,11 @@ __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const
       H[0] = 1.0; H[1] = r;
       for (int d = 0; d < 3; d++) H[2 + d] = xi[d] - delta[d];
       for (int d = 5; d < 14; d++) H[d] = 0.0;
+      events |= 1;
     }
   } else if (H[0] < 1.e-15) return false;
   double force_tang[3] = {H[5], H[6], H[7]}, tn[3] = {H[8], H[9], H[10]}, tt[3] = {H[11], H[12], H[13]};
-  if (!M.stressBreak && r > tabv(P, T_B_MAXDIST, it, jt) && update_history) { H[0] = 0.; H[1] = 0.; return false; }
+  if (!M.stressBreak && r > tabv(P, T_B_MAXDIST, it, jt) && update_history) { H[0] = 0.; H[1] = 0.; events |= 2; return false; }
   const double rinv = 1. / r;
   const double en[3] = {delta[0] * rinv, delta[1] * rinv, delta[2] * rinv};
   const double rb = lambda * (radi < radj ? radi : radj);
@@ -658,7 +659,7 @@ __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const
     if (M.ratioTC && (NL ? displacement < -1.e-15 : displacement < 1e-16)) maxSigma *= tabv(P, T_B_RATIOTC, it, jt);
     const bool nstress = maxSigma < (nfm / A + ttm * rb / I);
     const bool tstress = tabv(P, T_B_MAXTAU, it, jt) < (tfm / A + ntm * rb / J);
-    if ((nstress || tstress) && update_history) { H[0] = 0.; H[1] = 0.; return false; }
+    if ((nstress || tstress) && update_history) { H[0] = 0.; H[1] = 0.; events |= 2; return false; }
   }
   const double tor[3] = {tforce_d[1] * en[2] - tforce_d[2] * en[1], tforce_d[2] * en[0] - tforce_d[0] * en[2], tforce_d[0] * en[1] - tforce_d[1] * en[0]};
   for (int d = 0; d < 3; d++) { F[d] = nforce_d[d] + tforce_d[d]; Ti[d] = cri * tor[d] + ntorque_d[d] + ttorque_d[d]; Tj[d] = crj * tor[d] - ntorque_d[d] - ttorque_d[d]; }

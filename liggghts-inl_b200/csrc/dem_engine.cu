@@ -234,6 +234,7 @@ struct dem_engine {
   cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
   // step flags between ranks over peer memory (k_push / k_wait): my flag box, every rank's box, serial of the last hand-over
   // fused ghost push (fused_halo_setup): image table, block order, device parameter block; fz_on: the next launch_step uses it
+  DevBuf<unsigned long long> bondc;  // compute bond/counter: created, broken, scratch for the total
   DevBuf<int> img_first, img_ws, img_in; DevBuf<int4> img_tab; DevBuf<ImgP> imgp; int fz_ready = 0, fz_on = 0, fz_rq[2] = {-1, -1}, slot_zeroed = 0;
   DevBuf<int> fbox; int *peer_fbox[DEM_MAXRANKS] = {nullptr}; int fbox_ready = 0, fserial = 0, fser_slot[2] = {0, 0}, fpeer[2] = {0, 0};
   int *hflag_dev = nullptr; int fev_peer[2] = {0, 0};  // slot's flags arrive through k_wait (serial in hflag[16 + slot]) instead of memcpy + event
@@ -357,7 +358,7 @@ extern "C" void dem_destroy(dem_engine *e)
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   if (e->hflag) host_small_free(e->hflag);
   for (int k = 0; k < 2; k++) if (e->fev[k]) cudaEventDestroy(e->fev[k]);
-  e->hsig.release(); e->fbox.release(); e->img_first.release(); e->img_tab.release(); e->imgp.release(); e->img_ws.release(); e->img_in.release();
+  e->hsig.release(); e->fbox.release(); e->bondc.release(); e->img_first.release(); e->img_tab.release(); e->imgp.release(); e->img_ws.release(); e->img_in.release();
   if (e->hcnt) host_small_free(e->hcnt);
   if (e->comm) {
     if (e->comm_bad || getenv("DEM_B200_NO_COMM_CACHE")) g_nccl.CommDestroy(e->comm);
@@ -494,9 +495,9 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
     a += 2; argc -= 2;
   }
   if (argc > 1 && !strcmp(a[0], "rolling_friction")) {
-    if (!strcmp(a[1], "cdt")) m.rolling = R_CDT; else if (!strcmp(a[1], "epsd")) m.rolling = R_EPSD;
+    if (!strcmp(a[1], "cdt")) m.rolling = R_CDT; else if (!strcmp(a[1], "cdtnonlinear2")) { m.rolling = R_CDT; m.cdtnl2 = 1; } else if (!strcmp(a[1], "epsd")) m.rolling = R_EPSD;
     else if (!strcmp(a[1], "epsd2")) m.rolling = R_EPSD2; else if (!strcmp(a[1], "off")) m.rolling = R_OFF;
-    else dem_fail(e, DEM_ERR_UNSUPPORTED, "rolling model '%s' is outside the hot-path scope (cdt, epsd, epsd2)", a[1]);
+    else dem_fail(e, DEM_ERR_UNSUPPORTED, "rolling model '%s' is outside the hot-path scope (cdt, cdtnonlinear2, epsd, epsd2)", a[1]);
     a += 2; argc -= 2;
   }
   if (argc > 1 && !strcmp(a[0], "surface")) {
@@ -1878,6 +1879,7 @@ static StepP step_params(dem_engine *E, int mode)
   for (int d = 0; d < 3; d++) P.g[d] = E->g[d];
   P.have_g = E->have_g; P.have_pair = E->have_pair; P.freezebit = E->freezebit; P.integbit = E->integbit;
   P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = flag_slot(E, E->fslot); P.gate = E->gate; P.gate_mask = E->gate_mask; P.ncontact = nullptr;
+  P.bondc = (E->have_pair && E->pm.cohesion == C_BOND) ? E->bondc.p : nullptr;
   P.img = nullptr; P.img_first = nullptr; P.img_tab = nullptr;
   if (E->fz_on) {  // fused ghost push: this launch writes buffer cur ^ 1
     P.img = E->imgp.p; P.img_first = E->img_first.p; P.img_tab = E->img_tab.p;
@@ -1913,7 +1915,7 @@ static void launch_step_t(dem_engine *E, const StepP &P)
   }
   // the reference's default sub-model settings get the specialised instantiation (see pair_item)
   const ModelP &m = E->pm;
-  const bool std_deck = E->have_pair && m.tangential && m.tdamp && !m.limitForce && !m.torsion && P.nktv2p == 1.0 && P.cdf == 1.0 && !P.cout && !P.debug &&
+  const bool std_deck = E->have_pair && m.tangential && m.tdamp && !m.limitForce && !m.torsion && !m.cdtnl2 && P.nktv2p == 1.0 && P.cdf == 1.0 && !P.cout && !P.debug &&
                         !(E->opt.count("generic_step") && E->opt["generic_step"] != 0);
   if (std_deck) {
     if (E->ntypes == 1) k_step<N, R, true, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
@@ -2121,6 +2123,7 @@ extern "C" int dem_setup(dem_engine *e)
       e->whist_tmp.release(); e->whist_tmp.ensure(e, (size_t)e->nwrows * e->cap);
     }
   }
+  if (e->have_pair && e->pm.cohesion == C_BOND && !e->bondc.p) { e->bondc.ensure(e, 4); CK(cudaMemsetAsync(e->bondc.p, 0, 4 * sizeof(unsigned long long), e->stream)); }
   clear_flags(e);
   rebuild(e);
   e->nbuilds = 0;  // neighbor->ncalls counts the builds of the current run only
@@ -2417,6 +2420,28 @@ static void collect_contacts(dem_engine *E, ContactRows &R)
   R.tags.resize(2 * rows); R.v.resize(6 * rows);
   for (size_t r = 0; r < rows; r++) { R.tags[2 * r] = ht[2 * o[r]]; R.tags[2 * r + 1] = ht[2 * o[r] + 1]; memcpy(&R.v[6 * r], &hv[6 * o[r]], 6 * sizeof(double)); }
 }
+// compute bond/counter (compute_bond_counter.cpp:101-138), see include/dem_b200.h.  Only the linear bond model feeds it in the
+// reference: bond/nonlinear looks for a compute style "bond/nonlinear/counter" that does not exist
+// (cohesion_model_bond_nonlinear.h:381), so its counter stays at zero -- reproduced here.
+extern "C" int dem_bond_counter(dem_engine *e, double *out6)
+{
+  API_BEGIN
+  if (!out6) dem_fail(e, DEM_ERR_ARG, "null output");
+  for (int k = 0; k < 6; k++) out6[k] = 0.0;
+  if (!e->setup_done) dem_fail(e, DEM_ERR_STATE, "dem_bond_counter before dem_setup");
+  if (!(e->have_pair && e->pm.cohesion == C_BOND)) return DEM_OK;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  unsigned long long h[2] = {0, 0};
+  if (e->nranks > 1) NK(g_nccl.AllReduce(e->bondc.p, e->bondc.p, 2, ncclUint64, ncclSum, e->comm, st));
+  CK(cudaMemcpyAsync(h, e->bondc.p, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(e->bondc.p, 0, 2 * sizeof(unsigned long long), st));
+  CK(cudaStreamSynchronize(st));
+  out6[0] = (double)h[0]; out6[1] = (double)h[1];
+  out6[2] = (double)((unsigned int)h[0] - (unsigned int)h[1]);  // counted (0 between runs) + created - broken, unsigned like the reference
+  API_END
+}
+
 extern "C" int dem_contact_count(dem_engine *e, long *n)
 {
   API_BEGIN

@@ -613,7 +613,12 @@ __global__ void __launch_bounds__(128, DEM_BOND_MINBLOCKS) k_step_bond(const Ste
       // cohesion model first (it only needs kinematics + its own history); force on the first body
       double Fb[3] = {0., 0., 0.}, Tbi[3] = {0., 0., 0.}, Tbj[3] = {0., 0., 0.};
       const double xav[3] = {xa.x, xa.y, xa.z}, vav[3] = {va.x, va.y, va.z}, vbv[3] = {vb.x, vb.y, vb.z}, wav[3] = {wa.x, wa.y, wa.z}, wbv[3] = {wb.x, wb.y, wb.z};
-      const bool bonded = bond_eval<COH>(P, M, delta, rsq, xa.w, xb.w, xav, vav, vbv, wav, wbv, ta, tb, su, H, Fb, Tbi, Tbj);
+      int bev = 0;
+      const bool bonded = bond_eval<COH>(P, M, delta, rsq, xa.w, xb.w, xav, vav, vbv, wav, wbv, ta, tb, su, H, Fb, Tbi, Tbj, bev);
+      if (bev && P.bondc && !jfirst) {  // compute bond/counter: the lower-tag particle of a pair counts its events
+        if (bev & 1) atomicAdd(P.bondc, 1ULL);
+        if (bev & 2) atomicAdd(P.bondc + 1, 1ULL);
+      }
       double Fa[3] = {0., 0., 0.}, Ta[3] = {0., 0., 0.}, Tb[3] = {0., 0., 0.};
       if (touch) {
         Contact c;

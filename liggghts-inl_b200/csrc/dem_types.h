@@ -30,6 +30,7 @@ enum { C_OFF = 0, C_BOND = 1, C_BONDNL = 2 };
 struct ModelP {
   int normal, tangential, rolling;
   int tdamp, limitForce, torsion, ktToKn;
+  int cdtnl2;  // rolling_friction cdtnonlinear2 (rolling_model_cdtnonlinear2.h): the CDT law with the full normal force Fn instead of kn*deltan
   int dnum, off_shear, off_roll;  // reference layout of a history row (fix_contact_history)
   int hrec, rec_shear, rec_roll;   // device layout: hrec 32-byte records per contact, one per sub-model
   // cohesion bond | bond/nonlinear: nbond history doubles (14 | 28) in records rec_bond.. , followed by one "sticky flag"
@@ -102,6 +103,7 @@ struct StepP {
   const int *gate;
   int gate_mask;  // bit0: gate[0] (distance check due this step), bit2: gate[2] (a moving mesh forces the rebuild)
   unsigned long long *ncontact;  // optional counter of touching entries (stats), may be null
+  unsigned long long *bondc;     // compute bond/counter: [0] bonds created, [1] bonds broken (each pair counted by its lower-tag particle)
   // fused ghost push (null / unused otherwise): image table of the owned particles (img_first[i]: first entry or -1; entry =
   // (slot | target << 28, shift code, next entry or -1, 0)) and this launch's buffer parity
   const ImgP *img; const int *img_first; const int4 *img_tab;

@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
-    "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
+    "dem_bond_counter", "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
 ]
 
 
@@ -243,6 +243,12 @@ class Engine:
         hist = np.zeros((n, max(d, 1)), np.float64)
         self._call("download_pairs", [C.c_void_p] * 4, lo.ctypes.data, hi.ctypes.data, fl.ctypes.data, hist.ctypes.data)
         return {"lo": lo, "hi": hi, "flag": fl, "hist": hist[:, :d], "dnum": d}
+
+    def bond_counter(self):
+        """compute bond/counter as the reference returns it between two runs (see include/dem_b200.h): [created, broken, created - broken (unsigned), 0, 0, 0]"""
+        out = np.zeros(6, np.float64)
+        self._call("bond_counter", [C.c_void_p], out.ctypes.data)
+        return out
 
     def contacts(self):
         """(option contact_output) rows of the last force evaluation: own tag, partner tag, force and torque on the own particle"""

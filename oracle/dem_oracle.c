@@ -37,6 +37,7 @@ enum { C_OFF = 0, C_BOND = 1, C_BONDNL = 2 };
 typedef struct {
   int normal, tangential, rolling;
   int tangential_damping, limitForce, torsionTorque, ktToKn;
+  int cdtnl2; /* rolling_friction cdtnonlinear2 */
   int dnum, off_shear, off_roll;
   /* cohesion bond / bond/nonlinear: cohesion_model_bond.h:254-276, cohesion_model_bond_nonlinear.h:233-246 */
   int cohesion, off_bond;
@@ -100,6 +101,7 @@ typedef struct orc_engine {
   double *x, *v, *f, *omega, *torque, *radius, *rmass, *density, *xhold;
   /* half list (CSR) + history */
   long *first; int *numneigh; int *jlist; signed char *jshift; int *flag; double *hist; long npairs, cap;
+  long bond_created, bond_broken; /* compute bond/counter (compute_bond_counter.cpp:140-156), linear bond model only */
   long ntimestep, nbuilds; int ago; int setup_done;
 } orc_engine;
 
@@ -203,7 +205,7 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
     a += 2; argc -= 2;
   }
   if (argc > 1 && !strcmp(a[0], "rolling_friction")) {
-    if (!strcmp(a[1], "cdt")) m->rolling = R_CDT; else if (!strcmp(a[1], "epsd")) m->rolling = R_EPSD;
+    if (!strcmp(a[1], "cdt")) m->rolling = R_CDT; else if (!strcmp(a[1], "cdtnonlinear2")) { m->rolling = R_CDT; m->cdtnl2 = 1; } else if (!strcmp(a[1], "epsd")) m->rolling = R_EPSD;
     else if (!strcmp(a[1], "epsd2")) m->rolling = R_EPSD2; else if (!strcmp(a[1], "off")) m->rolling = R_OFF;
     else return fail(e, "rolling model not supported");
     a += 2; argc -= 2;
@@ -465,7 +467,7 @@ static void rolling_cdt(const orc_engine *e, const model_t *m, sid_t *s)
     const double wr1 = s->wr1, wr2 = s->wr2, wr3 = s->wr3;
     const double wrmag = sqrt(wr1 * wr1 + wr2 * wr2 + wr3 * wr3);
     if (wrmag > 0.) {
-      const double Fn = s->deltan * s->kn;
+      const double Fn = m->cdtnl2 ? s->Fn : s->deltan * s->kn; /* rolling_model_cdtnonlinear2.h:127 */
       rt[0] = rmu * Fn * wr1 / wrmag * reff; rt[1] = rmu * Fn * wr2 / wrmag * reff; rt[2] = rmu * Fn * wr3 / wrmag * reff;
       if (!m->torsionTorque) {
         double dot = rt[0] * enx + rt[1] * eny + rt[2] * enz;
@@ -476,7 +478,7 @@ static void rolling_cdt(const orc_engine *e, const model_t *m, sid_t *s)
     double wr[3] = {s->wi[0] - s->wj[0], s->wi[1] - s->wj[1], s->wi[2] - s->wj[2]};
     const double mag = sqrt(wr[0] * wr[0] + wr[1] * wr[1] + wr[2] * wr[2]);
     if (mag > 0.) {
-      const double sc = rmu * s->kn * s->deltan * reff / mag;
+      const double sc = m->cdtnl2 ? rmu * s->Fn * reff / mag : rmu * s->kn * s->deltan * reff / mag; /* rolling_model_cdtnonlinear2.h:157 */
       rt[0] = wr[0] * sc; rt[1] = wr[1] * sc; rt[2] = wr[2] * sc;
       if (!m->torsionTorque) {
         const double dot = rt[0] * enx + rt[1] * eny + rt[2] * enz;
@@ -576,6 +578,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
       H[0] = 1.0; H[1] = r;
       for (int d = 0; d < 3; d++) H[2 + d] = s->xi[d] - s->delta[d];
       for (int d = 5; d < 14; d++) H[d] = 0.0;
+      ((orc_engine *)e)->bond_created++; /* cohesion_model_bond.h:1032 */
     }
   } else if (H[0] < 1.e-15) return;
   double force_tang[3] = {H[5], H[6], H[7]}, tn[3] = {H[8], H[9], H[10]}, tt[3] = {H[11], H[12], H[13]}; /* linear: torques ; nonlinear: angles */
@@ -583,6 +586,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
   const double *delta = s->delta;
   if (!m->stressBreak && r > e->bp[BP_MAXDIST][it][jt] && update_history) { /* breakBond :1036-1070 */
     if (s->flag) *s->flag &= ~CONTACT_COHESION;
+    ((orc_engine *)e)->bond_broken++; /* :1066 */
     H[0] = 0.; H[1] = 0.; return;
   }
   if (s->flag) *s->flag |= CONTACT_COHESION;
@@ -689,7 +693,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
     if (m->ratioTC && (NL ? displacement < -1.e-15 : displacement < 1e-16)) maxSigma *= e->bp[BP_RATIOTC][it][jt];
     const int nstress = maxSigma < (nfm / A + ttm * rb / I);
     const int tstress = e->bp[BP_MAXTAU][it][jt] < (tfm / A + ntm * rb / J);
-    if ((nstress || tstress) && update_history) { if (s->flag) *s->flag &= ~CONTACT_COHESION; H[0] = 0.; H[1] = 0.; return; }
+    if ((nstress || tstress) && update_history) { if (s->flag) *s->flag &= ~CONTACT_COHESION; ((orc_engine *)e)->bond_broken++; H[0] = 0.; H[1] = 0.; return; }
   }
   double tor[3]; tor[0] = tforce_d[1] * en[2] - tforce_d[2] * en[1]; tor[1] = tforce_d[2] * en[0] - tforce_d[0] * en[2]; tor[2] = tforce_d[0] * en[1] - tforce_d[1] * en[0];
   s->has_force_update = 1;
@@ -1594,6 +1598,18 @@ int orc_download_mesh_contacts(orc_engine *e, const char *mesh_id, int *tag, int
   return fail(e, "no such mesh");
 }
 typedef struct { long ntimestep, nbuilds, nlocal, nghost, npairs_full, ncontacts_full, kernel_launches; int maxneigh, dnum; double step_kernel_ms; long step_kernel_calls; } orc_stats;
+/* compute bond/counter (compute_bond_counter.cpp:101-138) as lammps_extract_compute returns it between two runs: bonds created /
+ * broken since the last call, and "total" = counted + created - broken in unsigned 32-bit arithmetic, where `counted` only
+ * moves on the step right after an invocation DURING a run (bond_count, :158-168; Modify::init resets invoked_vector to -1 at
+ * every run start) -- with invocations between runs it is 0.  The three wall entries stay 0 (no bond models on walls). */
+int orc_bond_counter(orc_engine *e, double *out6)
+{
+  const unsigned int total = (unsigned int)e->bond_created - (unsigned int)e->bond_broken;
+  out6[0] = (double)e->bond_created; out6[1] = (double)e->bond_broken; out6[2] = e->pm.cohesion == C_BOND ? (double)total : 0.0; out6[3] = out6[4] = out6[5] = 0.0;
+  if (e->pm.cohesion != C_BOND) out6[0] = out6[1] = 0.0;  /* bond/nonlinear looks for a compute style that does not exist: never fed */
+  e->bond_created = e->bond_broken = 0;
+  return 0;
+}
 int orc_get_stats(orc_engine *e, orc_stats *s)
 { memset(s, 0, sizeof *s); s->ntimestep = e->ntimestep; s->nbuilds = e->nbuilds; s->nlocal = e->n; s->npairs_full = 2 * e->npairs; s->dnum = e->pm.dnum;
   long c = 0; for (long m = 0; m < e->npairs; m++) c += e->flag[m] != 0; s->ncontacts_full = 2 * c; return 0; }

@@ -114,6 +114,15 @@ class Ref:
             self.lib.lammps_free(p)
         return out
 
+    def compute_vector(self, compute_id, n):
+        """global vector of a compute through lammps_extract_compute(style 0, type 1) (invokes Compute::compute_vector when it has
+        not been invoked on this step)"""
+        L = self.lib
+        L.lammps_extract_compute.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.lammps_extract_compute.restype = C.c_void_p
+        p = L.lammps_extract_compute(self.h, compute_id.encode(), 0, 1)
+        return np.array([C.cast(p, C.POINTER(C.c_double))[i] for i in range(n)])
+
     def mesh_geometry(self, mesh_id):
         L = self.lib
         L.ref_mesh_ntri.argtypes = [C.c_void_p, C.c_char_p]

@@ -211,6 +211,8 @@ def to_deck(c, datafile):
         extra = " %d" % c["ntypes"] if kind == "peratomtypepair" else ""
         deck.append("fix m%d all property/global %s %s%s %s" % (k, name, kind, extra, " ".join("%.17g" % v for v in vals)))
     deck += ["pair_style gran " + c["pair"], "pair_coeff * *"]
+    if "cohesion bond " in c["pair"] + " ":  # linear bond model: the reference's bond counter (compute_bond_counter.cpp)
+        deck.append("compute bc all bond/counter")
     if c["gravity"]:
         deck.append("fix grav all gravity %.17g vector %g %g %g" % (c["gravity"][0], *c["gravity"][1]))
     for wid, text in c["walls"]:
@@ -266,6 +268,9 @@ GOLDEN_CASES = {
                                 checkpoints=[0, 1, 2, 10, 400, 2500]),
     "periodic_epsd2": dict(kw=dict(n3=(5, 5, 4), model="model hertz tangential history rolling_friction epsd2", settings="limitForce on",
                                    poly=True, periodic=(1, 1, 0), ntypes=2, shear=True), checkpoints=[0, 1, 2, 10, 400, 2500]),
+    # rolling_friction cdtnonlinear2 (rolling_model_cdtnonlinear2.h): CDT with the full normal force, walls included
+    "box_hertz_cdtnl2": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdtnonlinear2", poly=True,
+                                     cyl=True, shear=True), checkpoints=[0, 1, 2, 10, 400, 2500]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
     # rebuild cadence other than `delay 0 every 1 check yes` (Neighbor::decide, neighbor.cpp:1362-1376)
@@ -329,6 +334,8 @@ def snapshot(eng, c):
     out = dict(eng.atoms(("x", "v", "f", "omega", "torque")))
     p = eng.pairs()
     out.update(pair_lo=p["lo"], pair_hi=p["hi"], pair_flag=(p["flag"] != 0).astype(np.int32), pair_hist=p["hist"])
+    if "cohesion bond " in c["pair"] + " " and hasattr(eng, "bond_counter"):  # compute bond/counter as the reference returns it between runs
+        out["bondcounter"] = eng.bond_counter()
     if "cohesion" in c["pair"]:  # contactPos (history 2..4) is written at bond creation and read for wall bonds only: not compared
         out["pair_hist"] = out["pair_hist"].copy(); out["pair_hist"][:, 2:5] = 0.0
     for wid, text in c["walls"]:

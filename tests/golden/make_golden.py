@@ -48,6 +48,8 @@ def run_case(name):
             out["s%d_mesh_%s_tag" % (cp, mid)] = m["tag"]; out["s%d_mesh_%s_tri" % (cp, mid)] = m["tri"]; out["s%d_mesh_%s_hist" % (cp, mid)] = m["hist"]
         for mid in c.get("mesh_stress", []):
             out["s%d_meshforce_%s" % (cp, mid)] = r.fix_vector(mid, 9)
+        if "cohesion bond " in c["pair"] + " " and cp > 0:  # (at `run 0` the compute has not been invoked: its vector is uninitialised)
+            out["s%d_bondcounter" % cp] = r.compute_vector("bc", 6)
         out["s%d_nbuilds" % cp] = np.array(r.neigh_builds)
     for mid, mtype, nodes in c.get("meshes", []):
         t = r.mesh_topology(mid)
