@@ -21,6 +21,7 @@ struct Contact {
   double meff, mi, mj;
   double vi[3], vj[3], wi[3], wj[3];
   int itype, jtype;
+  double *nh;  // history of the normal model (hysteretic/nonlinear1|2: 12 values), else unused
 };
 
 struct ContactOut {
@@ -38,6 +39,73 @@ template <bool ONE>
 __device__ __forceinline__ double tabp(const StepP &P, int which, int tij)
 {
   return ONE ? P.t1[which] : __ldg(P.tab + which * P.nt1 * P.nt1 + tij);
+}
+
+// INL normal laws hysteretic/nonlinear1 and 2 (normal_model_hysteretic_nonlinear1.h:149-385, normal_model_hysteretic_nonlinear2.h):
+// piecewise loading / unloading / reloading force with plastic overlap, 12 history values per pair (deltaMax, deltaZero, k1,
+// deltaZero_old, k1_old, delta_old, deltaMin, betan, f0, f0_old, kc, fo) that the model rewrites in every force evaluation,
+// the setup one included.  Returns Fn; kn, kt (= k1), gamman, gammat go to the tangential / rolling models.
+template <bool V2>
+__device__ __forceinline__ double hyst_normal(const StepP &P, const ModelP &M, const Contact &c, double deltan, double vn,
+                                              double &kn_o, double &kt_o, double &gamman_o, double &gammat_o)
+{
+  const int it = c.itype, jt = c.jtype;
+  const double PI = 3.14159265358979323846;
+  const double meff = c.meff;
+  const double Alpha = tabv(P, T_H_ALPHA, it, jt), Cin = tabv(P, T_H_CIN, it, jt), A1 = tabv(P, T_H_A1, it, jt), A2 = tabv(P, T_H_A2, it, jt);
+  const double A3 = tabv(P, T_H_A3, it, jt);
+  const double k_c = tabv(P, T_H_KCIN, it, jt) * A2;
+  const double kc = tabv(P, T_H_KN2KC, it, jt) * tabv(P, T_H_KEL, it, jt);
+  const double f_0 = tabv(P, T_H_FADH, it, jt);
+  const double crl = tabv(P, T_CORLOG, it, jt);
+  const double cdamp = 1. + (PI / crl) * (PI / crl);
+  double *h = c.nh;
+  double deltaMax;
+  if (deltan > h[0]) { h[0] = deltan; deltaMax = deltan; } else deltaMax = h[0];
+  double deltaZero = h[1], k1 = h[2], deltaZero_old = h[3];
+  const double k1_old = h[4], delta_old = h[5];
+  double deltaMin = h[6], betan = h[7], f0 = h[8], f0_old = h[9];
+  double k2 = A3 * k1, fHys, gamman;
+  const bool loading = deltan >= delta_old ? (delta_old == 0 ? true : !(vn > 0)) : false;
+  const double dexp = V2 ? 0.5 : 0.25;
+  if (loading) {
+    if (deltaZero == 0) k1 = A2;
+    f0_old = f0;
+    if (deltan <= deltaZero) {
+      if (!V2) fHys = deltan <= deltaMin ? -k_c * deltan : betan * (deltan - deltaZero);
+      else fHys = Cin * k2 * (exp(betan * (deltan - deltaZero)) - 1);
+    } else fHys = Alpha * k1 * pow(deltan - deltaZero, 2.0) + f0;
+    gamman = sqrt(4. * meff * Alpha * k1 / cdamp) * (pow(deltan, dexp) + pow(deltaZero, dexp));  // (sqrt(5/4) is sqrt(1): integer division)
+    h[1] = deltaZero; h[2] = k1; h[3] = deltaZero; h[4] = k1; h[5] = deltan; h[6] = deltaMin; h[7] = betan; h[8] = f0; h[9] = f0_old;
+  } else if (!V2) {
+    k2 = A3 * k1_old;
+    deltaZero = (1 - k1_old / k2) * deltaMax;
+    const double beta = Alpha * k1_old * pow(deltaMax - deltaZero_old, 2.0) / k2 / (deltaMax - deltaZero);
+    deltaMin = beta * (k2 - k1_old) / (beta * k2 + k_c) * deltaMax;
+    k1 = deltaMax * A1 + A2;
+    if (deltan >= deltaMin) {
+      betan = beta * k2;
+      if (deltan >= deltaZero) { fHys = beta * k2 * (deltan - deltaZero) + (deltan - deltaZero) * f0_old / (deltaMax - deltaZero); f0 = fHys - Alpha * k1 * pow(deltan - deltaZero, 2.0); }
+      else { fHys = beta * k2 * (deltan - deltaZero); f0 = 0; }
+    } else { fHys = -k_c * deltan; f0 = 0; }
+    gamman = sqrt(4. * meff * Alpha * k1_old / cdamp) * pow(deltan, 0.25);
+    h[1] = deltaZero; h[2] = k1; h[3] = deltaZero_old; h[4] = k1_old; h[5] = deltan; h[6] = deltaMin; h[7] = betan; h[8] = f0;
+  } else {
+    k2 = A3 * (A1 * deltaMax + A2);
+    deltaZero = (1 - k1_old / k2) * deltaMax;
+    betan = log(Alpha * k1_old / Cin / k2 * pow(deltaMax - deltaZero_old, 2.0) + 1) / (deltaMax - (1 - k1_old / k2) * deltaMax);
+    deltaMin = betan * (k2 - k1_old) / (betan * k2 + k_c) * deltaMax;
+    k1 = deltaMax * A1 + A2;
+    if (deltan >= deltaZero) { fHys = Cin * k2 * (exp(betan * (deltan - deltaZero)) - 1) + (deltan - deltaZero) * f0_old / (deltaMax - deltaZero); f0 = fHys - Alpha * k1 * pow(deltan - deltaZero, 2.0); }
+    else { fHys = Cin * k2 * (exp(betan * (deltan - deltaZero)) - 1); f0 = 0; }
+    gamman = 1 * 0.001 * sqrt(4. * meff * Alpha * k1_old / cdamp) * pow(deltan, -0.25);
+    h[1] = deltaZero; h[2] = k1; h[3] = deltaZero_old; h[4] = k1_old; h[5] = deltan; h[6] = deltaMin; h[7] = betan; h[8] = f0;
+  }
+  double Fn = fHys + (-gamman * vn) + f_0;
+  if (M.limitForce && Fn < 0.0 && kc == 0 && f_0 == 0.0) Fn = 0.0;
+  h[10] = kc; h[11] = f_0;
+  kn_o = k1 / P.nktv2p; kt_o = k1 / P.nktv2p; gamman_o = gamman; gammat_o = gamman;  // (tangential_damping is registered but never applied)
+  return Fn;
 }
 
 // shear / ch: the tangential shear vector and the rolling spring torque of this pair's history row
@@ -79,7 +147,7 @@ __device__ __forceinline__ void contact_chain(const StepP &P, const ModelP &M, c
     const double sqrtFiveOverSix = 0.91287092917527685576161630466800355658790782499663875;
     gamman = -2. * sqrtFiveOverSix * beta * sqrt(Sn * meff);
     gammat = M.tdamp ? -2. * sqrtFiveOverSix * beta * sqrt(St * meff) : 0.0;
-  } else {
+  } else if (NORMAL == N_HOOKE) {
     const double Y = tabv(P, T_YEFF, c.itype, c.jtype);
     const double lg = tabv(P, T_CORLOG, c.itype, c.jtype);
     const double sqrtval = sqrt(reff);
@@ -89,10 +157,14 @@ __device__ __forceinline__ void contact_chain(const StepP &P, const ModelP &M, c
     const double lgsq = lg * lg;
     gamman = sqrt(4. * meff * kn * lgsq / (lgsq + 3.14159265358979323846 * 3.14159265358979323846));
     gammat = M.tdamp ? gamman : 0.0;
+  } else { kn = kt = gamman = gammat = 0.0; }
+  double Fn;
+  if (NORMAL == N_HYST1 || NORMAL == N_HYST2) Fn = hyst_normal<NORMAL == N_HYST2>(P, M, c, deltan, vn, kn, kt, gamman, gammat);
+  else {
+    kn /= P.nktv2p; kt /= P.nktv2p;
+    Fn = -gamman * vn + kn * deltan;
+    if (M.limitForce && Fn < 0.0) Fn = 0.0;
   }
-  kn /= P.nktv2p; kt /= P.nktv2p;
-  double Fn = -gamman * vn + kn * deltan;
-  if (M.limitForce && Fn < 0.0) Fn = 0.0;
   o.F[0] = Fn * enx; o.F[1] = Fn * eny; o.F[2] = Fn * enz;
   if (drop_normal) o.F[0] = o.F[1] = o.F[2] = 0.0;  // cohesion bond/nonlinear assigns the pair force after the normal model
   o.Ti[0] = o.Ti[1] = o.Ti[2] = 0.0; o.Tj[0] = o.Tj[1] = o.Tj[2] = 0.0;

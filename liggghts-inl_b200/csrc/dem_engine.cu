@@ -436,7 +436,11 @@ static int bond_table_of(const std::string &nm)
     {"ratioTensionCompressionBondnonlinear", T_B_RATIOTC}, {"stiffnessPerUnitAreaK_fn1", T_B_K_FN1}, {"stiffnessPerUnitAreaKu_fn1", T_B_KU_FN1},
     {"stiffnessPerUnitAreaKc_fn1", T_B_KC_FN1}, {"stiffnessPerUnitAreaK_fn2", T_B_K_FN2}, {"stiffnessPerUnitAreaKu_fn2", T_B_KU_FN2}, {"stiffnessPerUnitAreaKc_fn2", T_B_KC_FN2},
     {"stiffnessPerUnitAreaK_ft", T_B_K_FT}, {"stiffnessPerUnitAreaK_tn", T_B_K_TN}, {"stiffnessPerUnitAreaKu_tn", T_B_KU_TN}, {"stiffnessPerUnitAreaKc_tn", T_B_KC_TN},
-    {"stiffnessPerUnitAreaK_tt", T_B_K_TT}, {"stiffnessPerUnitAreaKu_tt", T_B_KU_TT}, {"stiffnessPerUnitAreaKc_tt", T_B_KC_TT}};
+    {"stiffnessPerUnitAreaK_tt", T_B_K_TT}, {"stiffnessPerUnitAreaKu_tt", T_B_KU_TT}, {"stiffnessPerUnitAreaKc_tt", T_B_KC_TT},
+    // normal models hysteretic/nonlinear1|2
+    {"LoadingStiffness", T_H_KEL}, {"UnloadingStiffness", T_H_KN2K1}, {"coefficientAdhesionStiffness", T_H_KN2KC}, {"coefficientPlasticityDepth", T_H_PHIF},
+    {"pullOffForce", T_H_FADH}, {"alphaCustom", T_H_ALPHA}, {"cinCustom", T_H_CIN}, {"aoneCustom", T_H_A1}, {"atwoCustom", T_H_A2}, {"athreeCustom", T_H_A3},
+    {"kcinCustom", T_H_KCIN}};
   auto it = m.find(nm);
   return it == m.end() ? -1 : it->second;
 }
@@ -478,7 +482,9 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
   if (argc > 1 && !strcmp(a[0], "model")) {
     if (!strcmp(a[1], "hertz")) m.normal = N_HERTZ;
     else if (!strcmp(a[1], "hooke")) m.normal = N_HOOKE;
-    else dem_fail(e, DEM_ERR_UNSUPPORTED, "normal model '%s' is outside the hot-path scope (hertz, hooke)", a[1]);
+    else if (!strcmp(a[1], "hysteretic/nonlinear1")) { m.normal = N_HYST1; m.limitForce = 1; }  // limitForce defaults to on (normal_model_hysteretic_nonlinear1.h:100)
+    else if (!strcmp(a[1], "hysteretic/nonlinear2")) { m.normal = N_HYST2; m.limitForce = 1; }
+    else dem_fail(e, DEM_ERR_UNSUPPORTED, "normal model '%s' is outside the hot-path scope (hertz, hooke, hysteretic/nonlinear1, hysteretic/nonlinear2)", a[1]);
     a += 2; argc -= 2;
   } else dem_fail(e, DEM_ERR_ARG, "expected 'model <normal model>'");
   if (argc > 1 && !strcmp(a[0], "tangential")) {
@@ -506,7 +512,11 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
   }
   if ((m.rolling == R_EPSD || m.rolling == R_EPSD2) && !m.tangential)
     dem_fail(e, DEM_ERR_ARG, "rolling_friction epsd/epsd2 requires tangential history");
-  m.dnum = 0; m.hrec = 0; m.rec_shear = m.rec_roll = m.rec_bond = -1; m.off_bond = -1;
+  m.dnum = 0; m.hrec = 0; m.rec_shear = m.rec_roll = m.rec_bond = m.rec_norm = -1; m.off_bond = m.off_norm = -1;
+  if (m.normal == N_HYST1 || m.normal == N_HYST2) {  // the normal model's 12 history values come first (model construction order)
+    if (m.cohesion) dem_fail(e, DEM_ERR_UNSUPPORTED, "normal model hysteretic/nonlinear with a bond model is outside the hot-path scope");
+    m.off_norm = m.dnum; m.dnum += 12; m.rec_norm = m.hrec; m.hrec += 3;
+  }
   if (m.cohesion) {  // history slot order = model construction order: cohesion, tangential, rolling (contact_models.h:141-145)
     m.nbond = m.cohesion == C_BOND ? 14 : 28; m.off_bond = 0; m.dnum += m.nbond;
     m.rec_bond = 0; m.nbrec = (m.nbond + 1 + 3) / 4; m.hrec += m.nbrec;
@@ -561,6 +571,7 @@ extern "C" int dem_add_wall_primitive(dem_engine *e, const char *id, int argc, c
   for (auto &w : e->walls) if (w.id == id) dem_fail(e, DEM_ERR_ARG, "fix id %s already in use", id);
   WallHost W; W.id = id; memset(&W.p, 0, sizeof W.p);
   parse_model_select(e, argc, argv, W.p.m);
+  if (W.p.m.normal >= N_HYST1) dem_fail(e, DEM_ERR_UNSUPPORTED, "normal model hysteretic/nonlinear on a wall is outside the hot-path scope (pair style only)");
   if (W.p.m.cohesion) dem_fail(e, DEM_ERR_UNSUPPORTED, "bond models on walls are outside the hot-path scope");
   if (argc < 4 || strcmp(argv[0], "primitive")) {
     if (argc > 0 && !strcmp(argv[0], "mesh")) dem_fail(e, DEM_ERR_UNSUPPORTED, "mesh walls go through dem_add_wall_mesh");
@@ -662,6 +673,7 @@ extern "C" int dem_add_wall_mesh(dem_engine *e, const char *id, int argc, const 
   if (e->setup_done) dem_fail(e, DEM_ERR_STATE, "walls cannot be added after setup");
   dem_engine::MeshWall W; W.id = id;
   parse_model_select(e, argc, argv, W.m);
+  if (W.m.normal >= N_HYST1) dem_fail(e, DEM_ERR_UNSUPPORTED, "normal model hysteretic/nonlinear on a mesh wall is outside the hot-path scope (pair style only)");
   if (W.m.cohesion) dem_fail(e, DEM_ERR_UNSUPPORTED, "bond models on walls are outside the hot-path scope");
   if (argc < 4 || strcmp(argv[0], "mesh")) dem_fail(e, DEM_ERR_ARG, "Need to use define style 'mesh' or 'primitive'");
   if (strcmp(argv[1], "n_meshes")) dem_fail(e, DEM_ERR_ARG, "have to define 'n_meshes' before 'meshes'");
@@ -1113,13 +1125,15 @@ static void derive_tables(dem_engine *E)
   const int T = E->ntypes, n1 = T + 1;
   std::vector<double> t((size_t)T_COUNT * n1 * n1, 0.0);
   auto need = [&](const char *nm) { if (!E->have_prop.count(nm)) dem_fail(E, DEM_ERR_STATE, "property %s required by the selected models was not defined", nm); };
-  bool hertz = false, hooke = false, tang = false, roll = false, epsd = false;
-  auto scan = [&](const ModelP &m) { hertz |= m.normal == N_HERTZ; hooke |= m.normal == N_HOOKE; tang |= m.tangential != 0; roll |= m.rolling != R_OFF; epsd |= m.rolling == R_EPSD; };
+  bool hertz = false, hooke = false, tang = false, roll = false, epsd = false, hyst = false;
+  auto scan = [&](const ModelP &m) { hertz |= m.normal == N_HERTZ; hooke |= m.normal == N_HOOKE; hyst |= m.normal == N_HYST1 || m.normal == N_HYST2; tang |= m.tangential != 0; roll |= m.rolling != R_OFF; epsd |= m.rolling == R_EPSD; };
   if (E->have_pair) scan(E->pm);
   for (auto &w : E->walls) scan(w.p.m);
   for (auto &w : E->mwalls) scan(w.m);
   if (hertz || hooke) { need("youngsModulus"); need("poissonsRatio"); need("coefficientRestitution"); }
   if (hooke) need("characteristicVelocity");
+  if (hyst) for (const char *k : {"coefficientRestitution", "LoadingStiffness", "UnloadingStiffness", "coefficientAdhesionStiffness", "coefficientPlasticityDepth", "pullOffForce",
+                                  "alphaCustom", "cinCustom", "aoneCustom", "atwoCustom", "athreeCustom", "kcinCustom"}) need(k);
   if (tang) need("coefficientFriction");
   if (roll) need("coefficientRollingFriction");
   if (epsd) need("coefficientRollingViscousDamping");
@@ -1133,6 +1147,10 @@ static void derive_tables(dem_engine *E)
       if (cr <= 0.05 || cr > 1) dem_fail(E, DEM_ERR_ARG, "0.05 < coefficientRestitution <= 1 required");
       at(T_CORLOG) = log(cr);
       at(T_BETA) = at(T_CORLOG) / sqrt(pow(at(T_CORLOG), 2.) + pow(3.14159265358979323846, 2.));
+    }
+    if (hyst) {
+      if (!(hertz || hooke)) { const double cr = E->cor[i][j]; if (cr <= 0.05 || cr > 1) dem_fail(E, DEM_ERR_ARG, "0.05 < coefficientRestitution <= 1 required"); at(T_CORLOG) = log(cr); }
+      for (int w = T_H_KEL; w <= T_H_KCIN; w++) at(w) = E->bp[w][i][j];
     }
     at(T_MU) = E->mu[i][j]; at(T_RMU) = E->rmu[i][j]; at(T_RVISC) = E->rvisc[i][j];
     if (hertz || hooke) { at(T_SQ2Y) = sqrt(2. * at(T_YEFF)); at(T_SQ8G) = sqrt(8. * at(T_GEFF)); at(T_INV8G) = 1. / (8. * at(T_GEFF)); }
@@ -1149,7 +1167,7 @@ static void derive_tables(dem_engine *E)
     if (!m.stressBreak) needb("maxDistanceBond"); else { needb("maxSigmaBond"); needb("maxTauBond"); }
     if (!nl) { need("normalBondStiffnessPerUnitArea"); need("tangentialBondStiffnessPerUnitArea"); }
     else for (const char *k : {"K_fn1", "Ku_fn1", "Kc_fn1", "K_fn2", "Ku_fn2", "Kc_fn2", "K_ft", "K_tn", "Ku_tn", "Kc_tn", "K_tt", "Ku_tt", "Kc_tt"}) need((std::string("stiffnessPerUnitArea") + k).c_str());
-    for (int w = T_B_LAMBDA; w < T_COUNT; w++) for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) t[((size_t)w * n1 + i) * n1 + j] = E->bp[w][i][j];
+    for (int w = T_B_LAMBDA; w < T_H_KEL; w++) for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) t[((size_t)w * n1 + i) * n1 + j] = E->bp[w][i][j];
     // neighbor->register_contact_dist_factor: cohesion_model_bond.h:391-475, cohesion_model_bond_nonlinear.h:336-382
     if (!(E->rmin > 0.)) dem_fail(E, DEM_ERR_STATE, "Bond settings: The minimum radius can't be <= 0!");
     double cdf_all = 1.;
@@ -1780,7 +1798,7 @@ static void rebuild(dem_engine *E)
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
   // full list (k_step, k_step_bond) unless option owner_list asks for the measured alternative of dem_pairs.cuh
-  const int fmt = (E->have_pair && !E->pm.cohesion && E->opt.count("owner_list") && E->opt["owner_list"] != 0) ? 1 : 0;
+  const int fmt = (E->have_pair && !E->pm.cohesion && E->pm.normal < N_HYST1 && E->opt.count("owner_list") && E->opt["owner_list"] != 0) ? 1 : 0;
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
   // history rows: by default one per row entry (a particle can never gain more contacts between two rebuilds than it has
   // list entries, so the step kernels cannot run out of rows and drop a contact's history; rows that are not in use cost
@@ -1957,6 +1975,12 @@ static void launch_step(dem_engine *E, int mode, bool timed)
       }
     }
   } else
+  if (E->have_pair && E->pm.normal >= N_HYST1) {  // INL normal laws: general kernel (canonical orientation, 12 more history values per pair)
+    const unsigned g = GRID(P.nlocal, 128);
+#define HYSTK(R) { if (E->pm.normal == N_HYST1) k_step_hyst<N_HYST1, R><<<g, 128, 0, E->stream>>>(P); else k_step_hyst<N_HYST2, R><<<g, 128, 0, E->stream>>>(P); }
+    switch (E->pm.rolling) { case R_OFF: HYSTK(R_OFF) break; case R_CDT: HYSTK(R_CDT) break; case R_EPSD: HYSTK(R_EPSD) break; default: HYSTK(R_EPSD2) break; }
+#undef HYSTK
+  } else
   if (E->have_pair && E->pm.cohesion) {
     const unsigned g = GRID(P.nlocal, 128);
 #define BONDK(N, R) { if (E->pm.cohesion == C_BOND) k_step_bond<N, R, C_BOND><<<g, 128, 0, E->stream>>>(P); else k_step_bond<N, R, C_BONDNL><<<g, 128, 0, E->stream>>>(P); }
@@ -2038,7 +2062,7 @@ static void wait_flags(dem_engine *E, int slot)
 // fused ghost push: usable for this launch?  (plain step kernel only; decks with mesh walls keep the pack-kernel path)
 static bool fused_on(dem_engine *E, int mode)
 {
-  return E->fz_ready && mode != MODE_SETUP && E->ls[E->lcur].fmt == 0 && !(E->have_pair && E->pm.cohesion) && !have_mesh_walls(E) && E->nlocal > 0;
+  return E->fz_ready && mode != MODE_SETUP && E->ls[E->lcur].fmt == 0 && !(E->have_pair && (E->pm.cohesion || E->pm.normal >= N_HYST1)) && !have_mesh_walls(E) && E->nlocal > 0;
 }
 // One step on the stream: the step launch, the ghost refresh, the flag hand-over.
 //  * fused ghost push (fz_ready): the step kernel stores every copy of a particle's new records from its epilogue; several
@@ -2369,6 +2393,10 @@ extern "C" int dem_download_pairs(dem_engine *e, int *lo, int *hi, int *flag, do
         if (M.cohesion) for (int d = 0; d < M.nbond; d++) {
           const double4 v = h[(size_t)(k * nrec + M.rec_bond + d / 4) * L.cap + i];
           hist[r * dn + M.off_bond + d] = (d % 4 == 0) ? v.x : (d % 4 == 1) ? v.y : (d % 4 == 2) ? v.z : v.w;
+        }
+        if (M.rec_norm >= 0) for (int d = 0; d < 12; d++) {
+          const double4 v = h[(size_t)(k * nrec + M.rec_norm + d / 4) * L.cap + i];
+          hist[r * dn + M.off_norm + d] = (d % 4 == 0) ? v.x : (d % 4 == 1) ? v.y : (d % 4 == 2) ? v.z : v.w;
         }
         if (M.rec_shear >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_shear) * L.cap + i]; hist[r * dn + M.off_shear] = v.x; hist[r * dn + M.off_shear + 1] = v.y; hist[r * dn + M.off_shear + 2] = v.z; }
         if (M.rec_roll >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_roll) * L.cap + i]; hist[r * dn + M.off_roll] = v.x; hist[r * dn + M.off_roll + 1] = v.y; hist[r * dn + M.off_roll + 2] = v.z; }

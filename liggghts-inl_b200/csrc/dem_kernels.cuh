@@ -672,6 +672,86 @@ __global__ void __launch_bounds__(128, DEM_BOND_MINBLOCKS) k_step_bond(const Ste
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }
 
+// ----------------------------------------------------------------------------------------
+// Step kernel of the decks whose pair style uses an INL normal law with its own history (hysteretic/nonlinear1|2).  Same
+// contract as k_step; one thread per particle; every pair is evaluated by both owners in the canonical orientation (lower tag =
+// first body), so the two copies of the 12 + 3 (+3) history values stay bit-identical without a symmetric formulation of the
+// law's loading / unloading branches.  contact_distance_factor is 1: entries that do not touch are skipped (history persists
+// until the next rebuild drops the pair, pair_gran_base.h:420-424).
+template <int NORMAL, int ROLLING>
+__global__ void __launch_bounds__(128, 3) k_step_hyst(const StepP P)
+{
+  constexpr bool HAS_ROLL_HIST = (ROLLING == R_EPSD || ROLLING == R_EPSD2);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool trig = false;
+  if (step_gated(P)) return;
+  if (i < P.nlocal) {
+    const ModelP &M = P.pm;
+    const double4 xi = ldg4(P.xr + i), vi = ldg4(P.vm + i), wi = ldg4(P.wt + i);
+    const bool su = (P.mode != MODE_SETUP);
+    double F[3] = {0., 0., 0.}, T[3] = {0., 0., 0.};
+    const int nnw = P.numneigh[i];
+    const int nn = nnw & 0xffff;
+    int nh = (nnw >> 16) & 0xffff;
+    const int nh0 = nh;
+    for (int k = 0; k < nn; k++) {
+      const unsigned w = P.nbr[(size_t)k * P.lcap + i];
+      const int j = (int)(w & NBR_IDX);
+      const double4 xj = ldg4(P.xr + j);
+      const double dxm = xi.x - xj.x, dym = xi.y - xj.y, dzm = xi.z - xj.z;
+      const double rsq = sq3_rn(dxm, dym, dzm);
+      const double radsum = xi.w + xj.w;
+      if (!(rsq < __dmul_rn(radsum, radsum))) continue;  // pair_gran_base.h:358
+      int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+      const bool had = slot >= 0;
+      const double4 vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
+      const bool jfirst = (w & NBR_JFIRST) != 0;
+      const double4 &xa = jfirst ? xj : xi, &xb = jfirst ? xi : xj, &va = jfirst ? vj : vi, &vb = jfirst ? vi : vj, &wa = jfirst ? wj : wi, &wb = jfirst ? wi : wj;
+      double NH[12], h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
+#pragma unroll
+      for (int d = 0; d < 12; d++) NH[d] = 0.0;
+      if (had) {
+        const double4 *hp = P.hist + (size_t)(slot * M.hrec) * P.lcap + i;
+#pragma unroll
+        for (int r = 0; r < 3; r++) { const double4 v = hp[(size_t)(M.rec_norm + r) * P.lcap]; NH[4 * r] = v.x; NH[4 * r + 1] = v.y; NH[4 * r + 2] = v.z; NH[4 * r + 3] = v.w; }
+        if (M.tangential) { const double4 v = hp[(size_t)M.rec_shear * P.lcap]; h[0] = v.x; h[1] = v.y; h[2] = v.z; }
+        if (HAS_ROLL_HIST) { const double4 v = hp[(size_t)M.rec_roll * P.lcap]; g[0] = v.x; g[1] = v.y; g[2] = v.z; }
+      }
+      Contact c;
+      c.dx = xa.x - xb.x; c.dy = xa.y - xb.y; c.dz = xa.z - xb.z;
+      c.r = sqrt(rsq); c.rinv = 1.0 / c.r;
+      c.radi = xa.w; c.radj = xb.w; c.radsum = xa.w + xb.w; c.deltan_in = 0.0;
+      c.mi = va.w; c.mj = vb.w;
+      double meff = va.w * vb.w / (va.w + vb.w);
+      if (rec_mask(wa.w) & P.freezebit) meff = vb.w;
+      if (rec_mask(wb.w) & P.freezebit) meff = va.w;
+      c.meff = meff;
+      c.vi[0] = va.x; c.vi[1] = va.y; c.vi[2] = va.z; c.vj[0] = vb.x; c.vj[1] = vb.y; c.vj[2] = vb.z;
+      c.wi[0] = wa.x; c.wi[1] = wa.y; c.wi[2] = wa.z; c.wj[0] = wb.x; c.wj[1] = wb.y; c.wj[2] = wb.z;
+      c.itype = rec_type(wa.w); c.jtype = rec_type(wb.w);
+      c.nh = NH;
+      ContactOut o;
+      contact_chain<NORMAL, ROLLING, false>(P, M, c, h, g, su, o);
+      if (jfirst) { for (int d = 0; d < 3; d++) { F[d] -= o.F[d]; T[d] += o.Tj[d]; } }
+      else { for (int d = 0; d < 3; d++) { F[d] += o.F[d]; T[d] += o.Ti[d]; } }
+      if (!had) {
+        if (nh < P.hslots) { slot = nh++; P.nbr[(size_t)k * P.lcap + i] = w | ((unsigned)(slot + 1) << NBR_SLOT_SHIFT); }
+        else { ((volatile int *)P.flag)[1] = 1; continue; }
+      }
+      double4 *hp = P.hist + (size_t)(slot * M.hrec) * P.lcap + i;  // the normal law rewrites its values in every evaluation
+#pragma unroll
+      for (int r = 0; r < 3; r++) st4(hp + (size_t)(M.rec_norm + r) * P.lcap, make_double4(NH[4 * r], NH[4 * r + 1], NH[4 * r + 2], NH[4 * r + 3]));
+      if (su || !had) {
+        if (M.tangential) st4(hp + (size_t)M.rec_shear * P.lcap, make_double4(h[0], h[1], h[2], 0.));
+        if (HAS_ROLL_HIST) st4(hp + (size_t)M.rec_roll * P.lcap, make_double4(g[0], g[1], g[2], 0.));
+      }
+    }
+    if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
+    trig = step_epilogue(P, i, xi, vi, wi, F, T);
+  }
+  if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
+}
+
 // first half step of a run from the stored force arrays: fix_nve_sphere.cpp:134-183
 __global__ void __launch_bounds__(256) k_initial_integrate(const StepP P)
 {

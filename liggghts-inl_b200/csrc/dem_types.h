@@ -4,13 +4,15 @@
 
 namespace dem {
 
-enum { N_OFF = 0, N_HERTZ = 1, N_HOOKE = 2 };
+enum { N_OFF = 0, N_HERTZ = 1, N_HOOKE = 2, N_HYST1 = 3, N_HYST2 = 4 };  // N_HYST*: INL laws hysteretic/nonlinear1|2 (pair style only)
 enum { R_OFF = 0, R_CDT = 1, R_EPSD = 2, R_EPSD2 = 3 };
 // per-type-pair tables, each (ntypes+1)^2 doubles, concatenated in this order
 enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_SQ2Y, T_SQ8G, T_INV8G,
        // bond models (cohesion_model_bond.h:76-178, cohesion_model_bond_nonlinear.h:77-147)
        T_B_LAMBDA, T_B_KN, T_B_KT, T_B_DFN, T_B_DFT, T_B_DTN, T_B_DTT, T_B_MAXDIST, T_B_MAXSIGMA, T_B_MAXTAU, T_B_CREATEDIST, T_B_RATIOTC,
        T_B_K_FN1, T_B_KU_FN1, T_B_KC_FN1, T_B_K_FN2, T_B_KU_FN2, T_B_KC_FN2, T_B_K_FT, T_B_K_TN, T_B_KU_TN, T_B_KC_TN, T_B_K_TT, T_B_KU_TT, T_B_KC_TT,
+       // normal models hysteretic/nonlinear1|2 (normal_model_hysteretic_nonlinear1.h:105-133)
+       T_H_KEL, T_H_KN2K1, T_H_KN2KC, T_H_PHIF, T_H_FADH, T_H_ALPHA, T_H_CIN, T_H_A1, T_H_A2, T_H_A3, T_H_KCIN,
        T_COUNT };
 enum { C_OFF = 0, C_BOND = 1, C_BONDNL = 2 };
 
@@ -33,6 +35,7 @@ struct ModelP {
   int cdtnl2;  // rolling_friction cdtnonlinear2 (rolling_model_cdtnonlinear2.h): the CDT law with the full normal force Fn instead of kn*deltan
   int dnum, off_shear, off_roll;  // reference layout of a history row (fix_contact_history)
   int hrec, rec_shear, rec_roll;   // device layout: hrec 32-byte records per contact, one per sub-model
+  int off_norm, rec_norm;          // hysteretic/nonlinear1|2: 12 history doubles of the normal model (3 records), first in the row
   // cohesion bond | bond/nonlinear: nbond history doubles (14 | 28) in records rec_bond.. , followed by one "sticky flag"
   // double (the reference's contact_flags != 0 after a touch or a kept rebuild, see dem_kernels.cuh k_step_bond)
   int cohesion, off_bond, nbond, rec_bond, nbrec;

@@ -29,7 +29,7 @@
 #define M_PI 3.14159265358979323846
 #endif
 
-enum { N_HERTZ = 1, N_HOOKE = 2 };
+enum { N_HERTZ = 1, N_HOOKE = 2, N_HYST1 = 3, N_HYST2 = 4 };
 enum { R_OFF = 0, R_CDT = 1, R_EPSD = 2, R_EPSD2 = 3 };
 enum { CONTACT_NORMAL = 1, CONTACT_COHESION = 2, CONTACT_TANGENTIAL = 4, CONTACT_ROLLING = 8 }; /* contact_model_constants.h:64-69 (values irrelevant: only != 0 is tested) */
 
@@ -38,7 +38,7 @@ typedef struct {
   int normal, tangential, rolling;
   int tangential_damping, limitForce, torsionTorque, ktToKn;
   int cdtnl2; /* rolling_friction cdtnonlinear2 */
-  int dnum, off_shear, off_roll;
+  int dnum, off_shear, off_roll, off_norm; /* off_norm: the 12 history values of normal model hysteretic/nonlinear1|2 */
   /* cohesion bond / bond/nonlinear: cohesion_model_bond.h:254-276, cohesion_model_bond_nonlinear.h:233-246 */
   int cohesion, off_bond;
   int stressBreak, tension, compression, shear, ntorque, ttorque, createAlways, damping, dampingSmooth, ratioTC;
@@ -89,7 +89,7 @@ typedef struct orc_engine {
   /* derived (global_properties.cpp:428-560) */
   double Yeff[MAXT + 1][MAXT + 1], Geff[MAXT + 1][MAXT + 1], betaeff[MAXT + 1][MAXT + 1], corLog[MAXT + 1][MAXT + 1];
   /* bond properties (peratomtypepair unless noted), index = enum BP_* */
-  double bp[32][MAXT + 1][MAXT + 1]; double tsCreateBond; double rmin;
+  double bp[40][MAXT + 1][MAXT + 1]; double tsCreateBond; double rmin;
   model_t pm; int have_pair;
   wall_t walls[MAXW]; int nwalls;
   mesh_t meshes[MAXMESH]; int nmeshes; meshwall_t mwalls[MAXMESH]; int nmwalls;
@@ -140,7 +140,9 @@ int orc_set_timestep(orc_engine *e, double dt) { e->dt = dt; return 0; }
 
 /* peratomtypepair properties of the two bond models (cohesion_model_bond.h:76-178, cohesion_model_bond_nonlinear.h:77-147) */
 enum { BP_LAMBDA = 0, BP_KN, BP_KT, BP_DFN, BP_DFT, BP_DTN, BP_DTT, BP_MAXDIST, BP_MAXSIGMA, BP_MAXTAU, BP_CREATEDIST, BP_RATIOTC,
-       BP_K_FN1, BP_KU_FN1, BP_KC_FN1, BP_K_FN2, BP_KU_FN2, BP_KC_FN2, BP_K_FT, BP_K_TN, BP_KU_TN, BP_KC_TN, BP_K_TT, BP_KU_TT, BP_KC_TT, BP_COUNT };
+       BP_K_FN1, BP_KU_FN1, BP_KC_FN1, BP_K_FN2, BP_KU_FN2, BP_KC_FN2, BP_K_FT, BP_K_TN, BP_KU_TN, BP_KC_TN, BP_K_TT, BP_KU_TT, BP_KC_TT, BP_COUNT,
+       /* normal models hysteretic/nonlinear1|2 (normal_model_hysteretic_nonlinear1.h:105-117) */
+       HP_KEL = BP_COUNT, HP_KN2K1, HP_KN2KC, HP_PHIF, HP_FADH, HP_ALPHA, HP_CIN, HP_A1, HP_A2, HP_A3, HP_KCIN, HP_END };
 static int bond_prop_index(const char *name)
 {
   static const char *lin[] = {"radiusMultiplierBond", "normalBondStiffnessPerUnitArea", "tangentialBondStiffnessPerUnitArea", "dampingNormalForceBond",
@@ -150,6 +152,9 @@ static int bond_prop_index(const char *name)
     "createDistanceBondnonlinear", "ratioTensionCompressionBondnonlinear", "stiffnessPerUnitAreaK_fn1", "stiffnessPerUnitAreaKu_fn1", "stiffnessPerUnitAreaKc_fn1",
     "stiffnessPerUnitAreaK_fn2", "stiffnessPerUnitAreaKu_fn2", "stiffnessPerUnitAreaKc_fn2", "stiffnessPerUnitAreaK_ft", "stiffnessPerUnitAreaK_tn",
     "stiffnessPerUnitAreaKu_tn", "stiffnessPerUnitAreaKc_tn", "stiffnessPerUnitAreaK_tt", "stiffnessPerUnitAreaKu_tt", "stiffnessPerUnitAreaKc_tt"};
+  static const char *hy[] = {"LoadingStiffness", "UnloadingStiffness", "coefficientAdhesionStiffness", "coefficientPlasticityDepth", "pullOffForce",
+    "alphaCustom", "cinCustom", "aoneCustom", "atwoCustom", "athreeCustom", "kcinCustom"};
+  for (int k = 0; k < 11; k++) if (!strcmp(name, hy[k])) return HP_KEL + k;
   for (int k = 0; k < 12; k++) if (!strcmp(name, lin[k])) return k;
   for (int k = 0; k < BP_COUNT; k++) if (nl[k][0] && !strcmp(name, nl[k])) return k;
   return -1;
@@ -191,6 +196,8 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
   memset(m, 0, sizeof *m); m->tangential_damping = 1;
   if (argc > 1 && !strcmp(a[0], "model")) {
     if (!strcmp(a[1], "hertz")) m->normal = N_HERTZ; else if (!strcmp(a[1], "hooke")) m->normal = N_HOOKE;
+    else if (!strcmp(a[1], "hysteretic/nonlinear1")) { m->normal = N_HYST1; m->limitForce = 1; } /* limitForce defaults to on: :100 */
+    else if (!strcmp(a[1], "hysteretic/nonlinear2")) { m->normal = N_HYST2; m->limitForce = 1; }
     else return fail(e, "normal model not supported");
     a += 2; argc -= 2;
   } else return fail(e, "expected 'model'");
@@ -211,7 +218,8 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
     a += 2; argc -= 2;
   }
   /* history slot order = model construction order: cohesion, tangential, rolling (contact_models.h:141-145) */
-  m->dnum = 0; m->off_shear = m->off_roll = m->off_bond = -1;
+  m->dnum = 0; m->off_shear = m->off_roll = m->off_bond = m->off_norm = -1;
+  if (m->normal == N_HYST1 || m->normal == N_HYST2) { m->off_norm = m->dnum; m->nflag[m->dnum + 10] = m->nflag[m->dnum + 11] = 1; m->dnum += 12; } /* deltaMax .. f0_old "0", kc fo "1": :83-94 */
   memset(m->nflag, 0, sizeof m->nflag);
   if (m->cohesion) { /* bondFlag, initial_dist, contactPos[3] (newtonflag 0) ; ft, torque/theta n, t (1) ; nonlinear: 14 more trackers (0) */
     m->off_bond = m->dnum; for (int k = 5; k < 14; k++) m->nflag[m->dnum + k] = 1;
@@ -411,6 +419,98 @@ static void normal_hooke(const orc_engine *e, const model_t *m, sid_t *s)
   double Fn = Fn_damping + Fn_contact;
   if (m->limitForce && Fn < 0.0) Fn = 0.0;
   s->Fn = Fn; s->kn = kn; s->kt = kt; s->gamman = gamman; s->gammat = gammat;
+  normal_apply(s, Fn);
+}
+
+static void normal_hysteretic(const orc_engine *e, const model_t *m, sid_t *s)
+{ /* normal_model_hysteretic_nonlinear1.h:149-385 ; variant 2: normal_model_hysteretic_nonlinear2.h (exponential unloading branch,
+     square-root damping terms, unloading stiffness from deltaMax) */
+  const int V2 = (m->normal == N_HYST2);
+  const int it = s->itype, jt = s->jtype;
+  const double deltan = s->deltan;
+  const double meff = s->meff;
+  double kn = e->bp[HP_KEL][it][jt];
+  const double Alpha_in = e->bp[HP_ALPHA][it][jt], Cin_in = e->bp[HP_CIN][it][jt], A1_in = e->bp[HP_A1][it][jt], A2_in = e->bp[HP_A2][it][jt];
+  const double A3_in = e->bp[HP_A3][it][jt], kcin_in = e->bp[HP_KCIN][it][jt];
+  const double k_c = kcin_in * A2_in;
+  const double kc = e->bp[HP_KN2KC][it][jt] * kn;
+  const double f_0 = e->bp[HP_FADH][it][jt];
+  const double crl = e->corLog[it][jt];
+  double gamman, gammat;
+  if (s->flag) *s->flag |= CONTACT_NORMAL;
+  double *history = &s->hist[m->off_norm];
+  double deltaMax;
+  if (deltan > history[0]) { history[0] = deltan; deltaMax = deltan; } else deltaMax = history[0];
+  double deltaZero = history[1];
+  double k1 = history[2];
+  double deltaZero_old = history[3];
+  double k1_old = history[4];
+  const double delta_old = history[5];
+  double deltaMin = history[6];
+  double betan = history[7];
+  double f0 = history[8];
+  double f0_old = history[9];
+  double k2, fHys;
+  k2 = A3_in * k1;
+  int tag_status; /* loading 1, unloading 2 */
+  if (deltan >= delta_old) {
+    if (delta_old == 0) tag_status = 1;
+    else tag_status = (s->vn > 0) ? 2 : 1;
+  } else tag_status = 2;
+  const double sq54 = sqrt(5 / 4); /* integer division in the reference: sqrt(1) */
+  const double dexp = V2 ? 0.5 : 0.25;
+  const double cdamp = 1. + (M_PI / crl) * (M_PI / crl);
+  if (tag_status == 1) {
+    if (deltaZero == 0) k1 = A2_in; else k1 = history[2];
+    deltaMin = history[6];
+    f0_old = f0;
+    if (deltan <= deltaZero) {
+      if (!V2) { if (deltan <= deltaMin) fHys = -k_c * deltan; else fHys = betan * (deltan - deltaZero); }
+      else fHys = Cin_in * k2 * (exp(betan * (deltan - deltaZero)) - 1);
+    } else fHys = Alpha_in * k1 * pow(deltan - deltaZero, 2) + f0;
+    gamman = sq54 * sqrt(4. * meff * Alpha_in * k1 / cdamp) * (pow(deltan, dexp) + pow(deltaZero, dexp));
+    gammat = gamman;
+    history[1] = deltaZero; history[2] = k1; history[3] = deltaZero; history[4] = k1; history[5] = deltan;
+    history[6] = deltaMin; history[7] = betan; history[8] = f0; history[9] = f0_old;
+  } else if (!V2) {
+    k2 = A3_in * k1_old;
+    deltaZero = (1 - k1_old / k2) * deltaMax;
+    const double beta = Alpha_in * k1_old * pow(deltaMax - deltaZero_old, 2) / k2 / (deltaMax - deltaZero);
+    deltaMin = beta * (k2 - k1_old) / (beta * k2 + k_c) * deltaMax;
+    k1 = deltaMax * A1_in + A2_in;
+    if (deltan >= deltaMin) {
+      betan = beta * k2;
+      if (deltan >= deltaZero) { fHys = beta * k2 * (deltan - deltaZero) + (deltan - deltaZero) * f0_old / (deltaMax - deltaZero); f0 = fHys - Alpha_in * k1 * pow(deltan - deltaZero, 2); }
+      else { fHys = beta * k2 * (deltan - deltaZero); f0 = 0; }
+    } else { fHys = -k_c * deltan; f0 = 0; }
+    gamman = sq54 * sqrt(4. * meff * Alpha_in * k1_old / cdamp) * pow(deltan, 0.25);
+    gammat = gamman;
+    history[1] = deltaZero; history[2] = k1; history[3] = deltaZero_old; history[4] = k1_old; history[5] = deltan;
+    history[6] = deltaMin; history[7] = betan; history[8] = f0;
+  } else {
+    const double fcc = 1.0;
+    k2 = A3_in * (A1_in * deltaMax + A2_in);
+    deltaZero = fcc * (1 - k1_old / k2) * deltaMax;
+    deltaZero_old = history[3];
+    betan = log(Alpha_in * k1_old / Cin_in / k2 * pow(deltaMax - deltaZero_old, 2) + 1) / (deltaMax - fcc * (1 - k1_old / k2) * deltaMax);
+    deltaMin = betan * (k2 - k1_old) / (betan * k2 + k_c) * deltaMax;
+    k1 = deltaMax * A1_in + A2_in;
+    if (deltan >= deltaZero) { fHys = Cin_in * k2 * (exp(betan * (deltan - deltaZero)) - 1) + (deltan - deltaZero) * f0_old / (deltaMax - deltaZero); f0 = fHys - Alpha_in * k1 * pow(deltan - deltaZero, 2); }
+    else { fHys = Cin_in * k2 * (exp(betan * (deltan - deltaZero)) - 1); f0 = 0; }
+    gamman = 1 * 0.001 * sq54 * sqrt(4. * meff * Alpha_in * k1_old / cdamp) * pow(deltan, -0.25);
+    gammat = gamman;
+    history[1] = deltaZero; history[2] = k1; history[3] = deltaZero_old; history[4] = k1_old; history[5] = deltan;
+    history[6] = deltaMin; history[7] = betan; history[8] = f0;
+  }
+  kn = k1;
+  double kt = kn;
+  kn /= e->nktv2p; kt /= e->nktv2p;
+  const double Fn_damping = -gamman * s->vn;
+  double Fn = fHys + Fn_damping + f_0;
+  if (m->limitForce && (Fn < 0.0) && kc == 0 && f_0 == 0.0) Fn = 0.0;
+  /* (the model registers tangential_damping but never applies it: gammat is used as computed, :186-191 are commented out) */
+  s->Fn = Fn; s->kn = kn; s->kt = kt; s->gamman = gamman; s->gammat = gammat;
+  history[10] = kc; history[11] = f_0;
   normal_apply(s, Fn);
 }
 
@@ -708,7 +808,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
 static void chain_intersect(const orc_engine *e, const model_t *m, sid_t *s)
 {
   surface_default(s);
-  if (m->normal == N_HERTZ) normal_hertz(e, m, s); else normal_hooke(e, m, s);
+  if (m->normal == N_HERTZ) normal_hertz(e, m, s); else if (m->normal == N_HOOKE) normal_hooke(e, m, s); else normal_hysteretic(e, m, s);
   if (m->cohesion) cohesion_bond(e, m, s);
   if (m->tangential) tangential_history(e, m, s);
   if (m->rolling == R_CDT) rolling_cdt(e, m, s);

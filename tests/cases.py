@@ -47,6 +47,14 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
     if "epsd2" in model:  # registered by the reference's epsd2 model although unused
         pass
     wmodel = model
+    if "hysteretic/nonlinear" in model:  # INL normal laws on the pair style, hertz on the walls (as in the reference's example decks)
+        wmodel = model.replace("hysteretic/nonlinear1", "hertz").replace("hysteretic/nonlinear2", "hertz")
+        full = lambda v: np.full(T * T, float(v))
+        props += [("LoadingStiffness", "peratomtypepair", full(5e4)), ("UnloadingStiffness", "peratomtypepair", full(2.5)),
+                  ("coefficientAdhesionStiffness", "peratomtypepair", full(0.0)), ("coefficientPlasticityDepth", "peratomtypepair", full(0.1)),
+                  ("pullOffForce", "peratomtypepair", full(0.0)), ("alphaCustom", "peratomtypepair", full(20.0)), ("cinCustom", "peratomtypepair", full(1e-7)),
+                  ("aoneCustom", "peratomtypepair", full(10e8)), ("atwoCustom", "peratomtypepair", full(4e4)), ("athreeCustom", "peratomtypepair", full(8.0)),
+                  ("kcinCustom", "peratomtypepair", full(1e-4))]
     if bond:  # bonded-sphere decks: `cohesion bond|bond/nonlinear` on the pair style, plain contact model on the walls
         kind = bond.get("kind", "bond")
         wmodel = model
@@ -79,10 +87,12 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
     # wall/gran keyword order: model selection, wall keywords, then on/off settings (fix_wall_gran.cpp:150-342)
     st = (" " + settings) if settings else ""
     wst = (" " + " ".join(w for w in [settings] if bond is None)) if (settings and bond is None) else ""
+    hyst = "hysteretic/nonlinear" in model
     pair_model = model
     model = wmodel
     st_pair = st
     st = wst if bond else st
+    if hyst: st = ""  # (the pair style's settings are the INL model's own)
     walls = [("zw", model + " primitive type %d zplane 0.0" % T + (" shear x 0.2" if shear else "") + st)]
     if cyl:
         walls.append(("cw", model + " primitive type 1 zcylinder %.17g %.17g %.17g" % (0.64 * L, 0.5 * L, 0.5 * L)
@@ -271,6 +281,10 @@ GOLDEN_CASES = {
     # rolling_friction cdtnonlinear2 (rolling_model_cdtnonlinear2.h): CDT with the full normal force, walls included
     "box_hertz_cdtnl2": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history rolling_friction cdtnonlinear2", poly=True,
                                      cyl=True, shear=True), checkpoints=[0, 1, 2, 10, 400, 2500]),
+    # INL normal laws hysteretic/nonlinear1 and 2 (12 history values per pair), hertz walls
+    "box_hyst1": dict(kw=dict(n3=(4, 4, 4), model="model hysteretic/nonlinear1 tangential history", poly=True), checkpoints=[0, 1, 2, 10, 400, 1000]),
+    "box_hyst2_cdt": dict(kw=dict(n3=(4, 4, 3), model="model hysteretic/nonlinear2 tangential history rolling_friction cdt", ntypes=2),
+                          checkpoints=[0, 1, 2, 10, 400, 1000]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
     # rebuild cadence other than `delay 0 every 1 check yes` (Neighbor::decide, neighbor.cpp:1362-1376)
