@@ -22,6 +22,7 @@ struct Contact {
   double vi[3], vj[3], wi[3], wj[3];
   int itype, jtype;
   double *nh;  // history of the normal model (hysteretic/nonlinear1|2: 12 values), else unused
+  double *th;  // tangential model hysteretic/nonlinear: [0] = shrmag_0 (history value 3; values 4..6 are read, never written: 0)
 };
 
 struct ContactOut {
@@ -176,8 +177,15 @@ __device__ __forceinline__ void contact_chain(const StepP &P, const ModelP &M, c
       const double rsht = shear[0] * enx + shear[1] * eny + shear[2] * enz;
       shear[0] -= rsht * enx; shear[1] -= rsht * eny; shear[2] -= rsht * enz;
     }
-    const double shrmag = sqrt(shear[0] * shear[0] + shear[1] * shear[1] + shear[2] * shear[2]);
+    double shrmag = sqrt(shear[0] * shear[0] + shear[1] * shear[1] + shear[2] * shear[2]);
     const double xmu = tabv(P, T_MU, c.itype, c.jtype);
+    if ((NORMAL == N_HYST1 || NORMAL == N_HYST2) && M.tangential == 2) {
+      // tangential model hysteretic/nonlinear (tangential_model_hysteretic_nonlinear.h:186-206): while the overlap is inside the
+      // plastic range of the normal law (deltan <= deltaZero) the spring restarts and the magnitude is remembered
+      double shrmag_0 = c.th[0];
+      if (deltan <= c.nh[1]) { shrmag_0 = shrmag; c.th[0] = shrmag_0; shear[0] = 0.0; shear[1] = 0.0; shear[2] = 0.0; }
+      shrmag -= shrmag_0;
+    }
     double Ft1 = -(kt * shear[0]), Ft2 = -(kt * shear[1]), Ft3 = -(kt * shear[2]);
     const double Ft_shear = kt * shrmag, Ft_friction = xmu * fabs(Fn);
     if (Ft_shear > Ft_friction) {

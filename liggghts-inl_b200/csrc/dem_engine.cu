@@ -490,7 +490,11 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
   if (argc > 1 && !strcmp(a[0], "tangential")) {
     if (!strcmp(a[1], "history")) m.tangential = 1;
     else if (!strcmp(a[1], "off")) m.tangential = 0;
-    else dem_fail(e, DEM_ERR_UNSUPPORTED, "tangential model '%s' is outside the hot-path scope (history)", a[1]);
+    else if (!strcmp(a[1], "hysteretic/nonlinear")) {  // reads sidata.deltaZero, which only the hysteretic normal laws set (tangential_model_hysteretic_nonlinear.h:150)
+      if (m.normal < N_HYST1) dem_fail(e, DEM_ERR_UNSUPPORTED, "tangential model hysteretic/nonlinear needs normal model hysteretic/nonlinear1|2");
+      m.tangential = 2;
+    }
+    else dem_fail(e, DEM_ERR_UNSUPPORTED, "tangential model '%s' is outside the hot-path scope (history, hysteretic/nonlinear)", a[1]);
     a += 2; argc -= 2;
   }
   m.tension = m.compression = m.shearf = m.ntorque = m.ttorque = m.damping = 1;
@@ -521,7 +525,7 @@ static void parse_model_select(dem_engine *e, int &argc, const char *const *&a, 
     m.nbond = m.cohesion == C_BOND ? 14 : 28; m.off_bond = 0; m.dnum += m.nbond;
     m.rec_bond = 0; m.nbrec = (m.nbond + 1 + 3) / 4; m.hrec += m.nbrec;
   }
-  if (m.tangential) { m.off_shear = m.dnum; m.dnum += 3; m.rec_shear = m.hrec++; }
+  if (m.tangential) { m.off_shear = m.dnum; m.dnum += m.tangential == 2 ? 7 : 3; m.rec_shear = m.hrec++; }  // (hysteretic/nonlinear: shear xyz | shrmag_0 in one record; values 4..6 stay 0)
   if (m.rolling == R_EPSD || m.rolling == R_EPSD2) { m.off_roll = m.dnum; m.dnum += 3; m.rec_roll = m.hrec++; }
 }
 // trailing `key on|off` settings (Settings::parseArguments)
@@ -2398,7 +2402,8 @@ extern "C" int dem_download_pairs(dem_engine *e, int *lo, int *hi, int *flag, do
           const double4 v = h[(size_t)(k * nrec + M.rec_norm + d / 4) * L.cap + i];
           hist[r * dn + M.off_norm + d] = (d % 4 == 0) ? v.x : (d % 4 == 1) ? v.y : (d % 4 == 2) ? v.z : v.w;
         }
-        if (M.rec_shear >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_shear) * L.cap + i]; hist[r * dn + M.off_shear] = v.x; hist[r * dn + M.off_shear + 1] = v.y; hist[r * dn + M.off_shear + 2] = v.z; }
+        if (M.rec_shear >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_shear) * L.cap + i]; hist[r * dn + M.off_shear] = v.x; hist[r * dn + M.off_shear + 1] = v.y; hist[r * dn + M.off_shear + 2] = v.z;
+          if (M.tangential == 2) hist[r * dn + M.off_shear + 3] = v.w; }
         if (M.rec_roll >= 0) { const double4 v = h[(size_t)(k * nrec + M.rec_roll) * L.cap + i]; hist[r * dn + M.off_roll] = v.x; hist[r * dn + M.off_roll + 1] = v.y; hist[r * dn + M.off_roll + 2] = v.z; }
       }
     }

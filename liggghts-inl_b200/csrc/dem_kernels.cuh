@@ -707,14 +707,14 @@ __global__ void __launch_bounds__(128, 3) k_step_hyst(const StepP P)
       const double4 vj = ldg4(P.vm + j), wj = ldg4(P.wt + j);
       const bool jfirst = (w & NBR_JFIRST) != 0;
       const double4 &xa = jfirst ? xj : xi, &xb = jfirst ? xi : xj, &va = jfirst ? vj : vi, &vb = jfirst ? vi : vj, &wa = jfirst ? wj : wi, &wb = jfirst ? wi : wj;
-      double NH[12], h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.};
+      double NH[12], h[3] = {0., 0., 0.}, g[3] = {0., 0., 0.}, th0 = 0.0;
 #pragma unroll
       for (int d = 0; d < 12; d++) NH[d] = 0.0;
       if (had) {
         const double4 *hp = P.hist + (size_t)(slot * M.hrec) * P.lcap + i;
 #pragma unroll
         for (int r = 0; r < 3; r++) { const double4 v = hp[(size_t)(M.rec_norm + r) * P.lcap]; NH[4 * r] = v.x; NH[4 * r + 1] = v.y; NH[4 * r + 2] = v.z; NH[4 * r + 3] = v.w; }
-        if (M.tangential) { const double4 v = hp[(size_t)M.rec_shear * P.lcap]; h[0] = v.x; h[1] = v.y; h[2] = v.z; }
+        if (M.tangential) { const double4 v = hp[(size_t)M.rec_shear * P.lcap]; h[0] = v.x; h[1] = v.y; h[2] = v.z; th0 = v.w; }
         if (HAS_ROLL_HIST) { const double4 v = hp[(size_t)M.rec_roll * P.lcap]; g[0] = v.x; g[1] = v.y; g[2] = v.z; }
       }
       Contact c;
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(128, 3) k_step_hyst(const StepP P)
       c.vi[0] = va.x; c.vi[1] = va.y; c.vi[2] = va.z; c.vj[0] = vb.x; c.vj[1] = vb.y; c.vj[2] = vb.z;
       c.wi[0] = wa.x; c.wi[1] = wa.y; c.wi[2] = wa.z; c.wj[0] = wb.x; c.wj[1] = wb.y; c.wj[2] = wb.z;
       c.itype = rec_type(wa.w); c.jtype = rec_type(wb.w);
-      c.nh = NH;
+      c.nh = NH; c.th = &th0;
       ContactOut o;
       contact_chain<NORMAL, ROLLING, false>(P, M, c, h, g, su, o);
       if (jfirst) { for (int d = 0; d < 3; d++) { F[d] -= o.F[d]; T[d] += o.Tj[d]; } }
@@ -741,8 +741,8 @@ __global__ void __launch_bounds__(128, 3) k_step_hyst(const StepP P)
       double4 *hp = P.hist + (size_t)(slot * M.hrec) * P.lcap + i;  // the normal law rewrites its values in every evaluation
 #pragma unroll
       for (int r = 0; r < 3; r++) st4(hp + (size_t)(M.rec_norm + r) * P.lcap, make_double4(NH[4 * r], NH[4 * r + 1], NH[4 * r + 2], NH[4 * r + 3]));
-      if (su || !had) {
-        if (M.tangential) st4(hp + (size_t)M.rec_shear * P.lcap, make_double4(h[0], h[1], h[2], 0.));
+      if (su || !had || M.tangential == 2) {  // (the hysteretic tangential law restarts its spring in any evaluation)
+        if (M.tangential) st4(hp + (size_t)M.rec_shear * P.lcap, make_double4(h[0], h[1], h[2], th0));
         if (HAS_ROLL_HIST) st4(hp + (size_t)M.rec_roll * P.lcap, make_double4(g[0], g[1], g[2], 0.));
       }
     }

@@ -202,7 +202,7 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
     a += 2; argc -= 2;
   } else return fail(e, "expected 'model'");
   if (argc > 1 && !strcmp(a[0], "tangential")) {
-    if (!strcmp(a[1], "history")) m->tangential = 1; else return fail(e, "tangential model not supported");
+    if (!strcmp(a[1], "history")) m->tangential = 1; else if (!strcmp(a[1], "hysteretic/nonlinear")) m->tangential = 2; else return fail(e, "tangential model not supported");
     a += 2; argc -= 2;
   }
   m->tension = m->compression = m->shear = m->ntorque = m->ttorque = m->damping = 1;
@@ -225,7 +225,8 @@ static int parse_model(orc_engine *e, int *pargc, const char *const **pargv, mod
     m->off_bond = m->dnum; for (int k = 5; k < 14; k++) m->nflag[m->dnum + k] = 1;
     m->dnum += (m->cohesion == C_BOND) ? 14 : 28;
   }
-  if (m->tangential) { m->off_shear = m->dnum; for (int k = 0; k < 3; k++) m->nflag[m->dnum + k] = 1; m->dnum += 3; }
+  if (m->tangential) { const int nt = m->tangential == 2 ? 7 : 3; /* hysteretic/nonlinear: shear xyz, shrmag_0, sh_0..2, all "1" (tangential_model_hysteretic_nonlinear.h:79-85) */
+    m->off_shear = m->dnum; for (int k = 0; k < nt; k++) m->nflag[m->dnum + k] = 1; m->dnum += nt; }
   if (m->rolling == R_EPSD || m->rolling == R_EPSD2) { m->off_roll = m->dnum; for (int k = 0; k < 3; k++) m->nflag[m->dnum + k] = 1; m->dnum += 3; }
   *pargc = argc; *pargv = a; return 0;
 }
@@ -337,7 +338,7 @@ typedef struct {
   int is_wall, itype, jtype, shearupdate;
   double radi, radj, radsum, r, rinv, en[3], delta[3], deltan, meff, mi, mj;
   const double *vi, *vj, *wi, *wj;
-  double kn, kt, gamman, gammat, Fn, vn, cri, crj, wr1, wr2, wr3, vtr1, vtr2, vtr3;
+  double kn, kt, gamman, gammat, Fn, vn, cri, crj, wr1, wr2, wr3, vtr1, vtr2, vtr3, deltaZero;
   double *hist; int *flag;
   double Fi[3], Ti[3], Fj[3], Tj[3];
   double rsq; int has_force_update; long ntimestep; const double *xi;
@@ -509,7 +510,7 @@ static void normal_hysteretic(const orc_engine *e, const model_t *m, sid_t *s)
   double Fn = fHys + Fn_damping + f_0;
   if (m->limitForce && (Fn < 0.0) && kc == 0 && f_0 == 0.0) Fn = 0.0;
   /* (the model registers tangential_damping but never applies it: gammat is used as computed, :186-191 are commented out) */
-  s->Fn = Fn; s->kn = kn; s->kt = kt; s->gamman = gamman; s->gammat = gammat;
+  s->Fn = Fn; s->kn = kn; s->kt = kt; s->gamman = gamman; s->gammat = gammat; s->deltaZero = deltaZero;
   history[10] = kc; history[11] = f_0;
   normal_apply(s, Fn);
 }
@@ -525,9 +526,15 @@ static void tangential_history(const orc_engine *e, const model_t *m, sid_t *s)
     double rsht = shear[0] * enx + shear[1] * eny + shear[2] * enz;
     shear[0] -= rsht * enx; shear[1] -= rsht * eny; shear[2] -= rsht * enz;
   }
-  const double shrmag = sqrt(shear[0] * shear[0] + shear[1] * shear[1] + shear[2] * shear[2]);
+  double shrmag = sqrt(shear[0] * shear[0] + shear[1] * shear[1] + shear[2] * shear[2]);
   const double kt = s->kt;
   const double xmu = e->mu[s->itype][s->jtype];
+  if (m->tangential == 2) { /* tangential_model_hysteretic_nonlinear.h:186-206: inside the plastic range of the normal law the spring restarts */
+    double shrmag_0 = shear[3], sh_0 = shear[4], sh_1 = shear[5], sh_2 = shear[6];
+    if (s->deltan <= s->deltaZero) { shrmag_0 = shrmag; shear[3] = shrmag_0; sh_0 = shear[0]; sh_1 = shear[1]; sh_2 = shear[2]; }
+    shear[0] -= sh_0; shear[1] -= sh_1; shear[2] -= sh_2;
+    shrmag -= shrmag_0;
+  }
   double Ft1 = -(kt * shear[0]), Ft2 = -(kt * shear[1]), Ft3 = -(kt * shear[2]);
   const double Ft_shear = kt * shrmag;
   const double Ft_friction = xmu * fabs(s->Fn);

@@ -48,7 +48,8 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
         pass
     wmodel = model
     if "hysteretic/nonlinear" in model:  # INL normal laws on the pair style, hertz on the walls (as in the reference's example decks)
-        wmodel = model.replace("hysteretic/nonlinear1", "hertz").replace("hysteretic/nonlinear2", "hertz")
+        wmodel = model.replace("model hysteretic/nonlinear1", "model hertz").replace("model hysteretic/nonlinear2", "model hertz")
+        wmodel = wmodel.replace("tangential hysteretic/nonlinear", "tangential history").replace("cdtnonlinear2", "cdt")
         full = lambda v: np.full(T * T, float(v))
         props += [("LoadingStiffness", "peratomtypepair", full(5e4)), ("UnloadingStiffness", "peratomtypepair", full(2.5)),
                   ("coefficientAdhesionStiffness", "peratomtypepair", full(0.0)), ("coefficientPlasticityDepth", "peratomtypepair", full(0.1)),
@@ -285,6 +286,9 @@ GOLDEN_CASES = {
     "box_hyst1": dict(kw=dict(n3=(4, 4, 4), model="model hysteretic/nonlinear1 tangential history", poly=True), checkpoints=[0, 1, 2, 10, 400, 1000]),
     "box_hyst2_cdt": dict(kw=dict(n3=(4, 4, 3), model="model hysteretic/nonlinear2 tangential history rolling_friction cdt", ntypes=2),
                           checkpoints=[0, 1, 2, 10, 400, 1000]),
+    # all INL laws together: hysteretic normal + hysteretic tangential (7 history values, plastic-range restart) + cdtnonlinear2
+    "box_hyst1_thyst": dict(kw=dict(n3=(4, 4, 3), model="model hysteretic/nonlinear1 tangential hysteretic/nonlinear rolling_friction cdtnonlinear2", poly=True),
+                            checkpoints=[0, 1, 2, 10, 400, 1000]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
     # rebuild cadence other than `delay 0 every 1 check yes` (Neighbor::decide, neighbor.cpp:1362-1376)
