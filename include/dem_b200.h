@@ -125,6 +125,15 @@ int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type,
                          const double *x, const double *v, const double *omega,
                          const double *radius, const double *density);
 
+/* Particles added to a system that already runs: what `create_atoms` and the `fix insert/pack|stream` family do
+ * to the path's state (atom.cpp / atom_vec_sphere.cpp create_atom: appended behind the owned atoms, zero force, no contact
+ * partners, no wall history).  To be called between two runs; the next dem_setup (== the next `run`'s Verlet::setup) rebuilds the
+ * lists and keeps the history of every existing contact.  Several ranks: every rank may pass the whole set, it keeps the
+ * particles inside its brick.  Before the first upload it is dem_upload_particles.  Where the positions come from -- the
+ * reference's insertion fixes draw them from their own random streams -- is the caller's business. */
+int dem_insert_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
+                         const double *v, const double *omega, const double *radius, const double *density);
+
 /* ---- run --------------------------------------------------------------------------------
  * dem_setup  == Verlet::setup  (forces with shearupdate = 0)   src/verlet.cpp:134-199
  * dem_run(n) == Verlet::run(n)                                 src/verlet.cpp:264-391   */

@@ -57,6 +57,8 @@ int API(set_freeze)(dem_engine *e, int groupbit);
 int API(set_integrate)(dem_engine *e, int groupbit);
 int API(upload_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
                           const double *omega, const double *radius, const double *density);
+int API(insert_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
+                          const double *omega, const double *radius, const double *density);
 int API(setup)(dem_engine *e);
 int API(run)(dem_engine *e, long nsteps);
 #endif
@@ -83,6 +85,10 @@ struct Deck {
   double skin = 0.0; int every = 1, delay = 10, check = 1;  // neighbor.cpp:100-130 defaults (delay 10, every 1, check yes)
   std::vector<int> tag, type, mask;
   std::vector<double> x, v, omega, radius, density;
+  // atoms created after the first run (create_atoms single + set atom ...): handed to dem_insert_particles by the next run
+  std::vector<int> ptag, ptype, pmask;
+  std::vector<double> px, pv, pomega, pradius, pdensity;
+  int maxtag = 0;
   long ntimestep = 0;
 };
 
@@ -370,7 +376,14 @@ void mesh_rotate(std::vector<double> &nodes, const double axis[3], double phi_de
 
 int first_run_prepare(Deck *d)
 {
-  if (d->uploaded) return OK;
+  if (d->uploaded) {
+    if (!d->ptag.empty()) {  // atoms created between two runs
+      TRY(API(insert_particles)(d->e, (long)d->ptag.size(), d->ptag.data(), d->ptype.data(), d->pmask.data(), d->px.data(), d->pv.data(), d->pomega.data(),
+                                d->pradius.data(), d->pdensity.data()));
+      d->ptag.clear(); d->ptype.clear(); d->pmask.clear(); d->px.clear(); d->pv.clear(); d->pomega.clear(); d->pradius.clear(); d->pdensity.clear();
+    }
+    return OK;
+  }
   if (!d->have_box) return fail(d, ERR_STATE, "Run command before simulation box is defined");
   if (d->tag.empty()) return fail(d, ERR_UNSUPPORTED, "no particles: initial states come from read_data (particle insertion is outside the hot-path scope)");
   if (!d->newton_off && d->have_pair) return fail(d, ERR_ARG, "Pair granular with shear history requires newton pair off");
@@ -613,6 +626,49 @@ int one(Deck *d, const std::string &raw)
   }
   if (c == "group") return cmd_group(d, w);
   if (c == "timestep") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal timestep command"); double dt; rc = numeric(d, w[1], dt); if (rc) return rc; TRY(API(set_timestep)(d->e, dt)); return OK; }
+  if (c == "create_atoms") {  // create_atoms.cpp (style single): one atom of the given type at a point; radius 0.5, density 1 until `set` (atom_vec_sphere.cpp:167-190)
+    if (w.size() < 6 || w[2] != "single") return fail(d, ERR_UNSUPPORTED, "create_atoms: only style 'single' is on the hot path (lattice / random creation is outside its scope)");
+    if (!d->have_box) return fail(d, ERR_STATE, "Create_atoms command before simulation box is defined");
+    double t, p[3];
+    rc = numeric(d, w[1], t); if (rc) return rc;
+    for (int k = 0; k < 3; k++) { rc = numeric(d, w[3 + k], p[k]); if (rc) return rc; }
+    for (size_t k = 6; k < w.size(); k++) {
+      if (w[k] == "units" && k + 1 < w.size() && w[k + 1] == "box") k++;
+      else return fail(d, ERR_UNSUPPORTED, "create_atoms keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    if ((int)t < 1 || (int)t > d->ntypes) return fail(d, ERR_ARG, "Invalid atom type in create_atoms command");
+    for (int v : d->tag) d->maxtag = std::max(d->maxtag, v);
+    const int id = ++d->maxtag;
+    const bool pend = d->uploaded;
+    (pend ? d->ptag : d->tag).push_back(id); (pend ? d->ptype : d->type).push_back((int)t); (pend ? d->pmask : d->mask).push_back(1);
+    for (int k = 0; k < 3; k++) { (pend ? d->px : d->x).push_back(p[k]); (pend ? d->pv : d->v).push_back(0.0); (pend ? d->pomega : d->omega).push_back(0.0); }
+    (pend ? d->pradius : d->radius).push_back(0.5); (pend ? d->pdensity : d->density).push_back(1.0);
+    return OK;
+  }
+  if (c == "set") {  // set.cpp, style atom: diameter / density / type of atoms that have not reached the engine yet
+    if (w.size() < 5 || w[1] != "atom") return fail(d, ERR_UNSUPPORTED, "set: only style 'atom' is on the hot path");
+    int lo, hi;
+    { const std::string &r = w[2]; const size_t star = r.find('*');
+      if (star == std::string::npos) { double a; rc = numeric(d, r, a); if (rc) return rc; lo = hi = (int)a; }
+      else { lo = star ? atoi(r.substr(0, star).c_str()) : 1; hi = star + 1 < r.size() ? atoi(r.substr(star + 1).c_str()) : 0x7fffffff; } }
+    const bool pend = d->uploaded;
+    std::vector<int> &tg = pend ? d->ptag : d->tag, &ty = pend ? d->ptype : d->type;
+    std::vector<double> &ra = pend ? d->pradius : d->radius, &de = pend ? d->pdensity : d->density;
+    bool any = false;
+    for (size_t i = 0; i < tg.size(); i++) {
+      if (tg[i] < lo || tg[i] > hi) continue;
+      any = true;
+      for (size_t k = 3; k + 1 < w.size(); k += 2) {
+        double val; rc = numeric(d, w[k + 1], val); if (rc) return rc;
+        if (w[k] == "diameter") { if (!(val > 0)) return fail(d, ERR_ARG, "Invalid diameter in set command"); ra[i] = 0.5 * val; }
+        else if (w[k] == "density") { if (!(val > 0)) return fail(d, ERR_ARG, "Invalid density in set command"); de[i] = val; }
+        else if (w[k] == "type") { if ((int)val < 1 || (int)val > d->ntypes) return fail(d, ERR_ARG, "Invalid value in set command"); ty[i] = (int)val; }
+        else return fail(d, ERR_UNSUPPORTED, "set keyword '%s' is outside the hot-path scope", w[k].c_str());
+      }
+    }
+    if (!any) return fail(d, ERR_UNSUPPORTED, "set atom: the atoms are already on the engine (properties of running particles cannot be changed)");
+    return OK;
+  }
   if (c == "run") {  // run.cpp:40-130: every run starts with Verlet::setup
     if (w.size() < 2) return fail(d, ERR_ARG, "Illegal run command");
     double nd; rc = numeric(d, w[1], nd); if (rc) return rc;

@@ -234,6 +234,7 @@ struct dem_engine {
   cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
   // step flags between ranks over peer memory (k_push / k_wait): my flag box, every rank's box, serial of the last hand-over
   // fused ghost push (fused_halo_setup): image table, block order, device parameter block; fz_on: the next launch_step uses it
+  int need_setup = 0;  // particles were inserted: the next dem_run needs a dem_setup first (lists, forces)
   DevBuf<unsigned long long> bondc;  // compute bond/counter: created, broken, scratch for the total
   DevBuf<int> img_first, img_ws, img_in; DevBuf<int4> img_tab; DevBuf<ImgP> imgp; int fz_ready = 0, fz_on = 0, fz_rq[2] = {-1, -1}, slot_zeroed = 0;
   DevBuf<int> fbox; int *peer_fbox[DEM_MAXRANKS] = {nullptr}; int fbox_ready = 0, fserial = 0, fser_slot[2] = {0, 0}, fpeer[2] = {0, 0};
@@ -1612,6 +1613,103 @@ static void ensure_list(dem_engine *E, ListSet &L, int cap, int maxk, int dnum, 
   }
 }
 
+// ---- particle insertion between two runs (what `create_atoms`, `fix insert/pack|stream` do to the path's state:
+// atom.cpp / atom_vec_sphere.cpp create_atom appends the new atoms behind the owned ones with zero force, no partners, no
+// wall history; the next run's Verlet::setup rebuilds the lists and keeps the history of the existing contacts).  The new
+// particles are appended behind the owned ones on the device; the old neighbour list gets empty rows for them so that the
+// rebuild's history remap (by partner tag) carries every existing contact over.
+static void grow_list_rows(dem_engine *E, ListSet &L, int ncap)
+{  // re-stride the [row][cap] arrays of a list to a larger capacity, contents kept
+  if (ncap <= L.cap) return;
+  cudaStream_t st = E->stream;
+  DevBuf<unsigned> nbr; DevBuf<int> ptag, nn; DevBuf<double4> hist;
+  nbr.ensure(E, (size_t)L.maxk * ncap); ptag.ensure(E, (size_t)L.maxk * ncap); nn.ensure(E, ncap);
+  CK(cudaMemsetAsync(nn.p, 0, (size_t)ncap * sizeof(int), st));
+  CK(cudaMemcpy2DAsync(nbr.p, (size_t)ncap * sizeof(unsigned), L.nbr.p, (size_t)L.cap * sizeof(unsigned), (size_t)L.cap * sizeof(unsigned), L.maxk, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpy2DAsync(ptag.p, (size_t)ncap * sizeof(int), L.ptag.p, (size_t)L.cap * sizeof(int), (size_t)L.cap * sizeof(int), L.maxk, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(nn.p, L.numneigh.p, (size_t)L.cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (L.dnum) {
+    hist.ensure(E, (size_t)L.hslots * L.dnum * ncap);
+    CK(cudaMemcpy2DAsync(hist.p, (size_t)ncap * sizeof(double4), L.hist.p, (size_t)L.cap * sizeof(double4), (size_t)L.cap * sizeof(double4), (size_t)L.hslots * L.dnum, cudaMemcpyDeviceToDevice, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  L.nbr.release(); L.ptag.release(); L.numneigh.release(); L.hist.release();
+  L.nbr = nbr; L.ptag = ptag; L.numneigh = nn; L.hist = hist; L.cap = ncap;
+}
+
+extern "C" int dem_insert_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
+                                    const double *v, const double *omega, const double *radius, const double *density)
+{
+  if (e && !e->uploaded) return dem_upload_particles(e, n, tag, type, mask, x, v, omega, radius, density);  // the first particles of the deck
+  API_BEGIN
+  if (n < 0 || (n > 0 && (!tag || !type || !x || !radius || !density))) dem_fail(e, DEM_ERR_ARG, "missing particle arrays");
+  if (n == 0) return DEM_OK;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  // this rank's share (several bricks: ownership test of dem_upload_particles)
+  std::vector<long> mine; mine.reserve(n);
+  const MineP B = brick_params(e);
+  double rmax_all = 0.0, rmin_all = 1e300;
+  for (long i = 0; i < n; i++) {
+    if (type[i] < 1 || type[i] > e->ntypes) dem_fail(e, DEM_ERR_ARG, "Invalid atom type in particle data");
+    if (!(radius[i] > 0.0) || !(density[i] > 0.0)) dem_fail(e, DEM_ERR_ARG, "Invalid radius or density in particle data");
+    if (tag[i] <= 0) dem_fail(e, DEM_ERR_ARG, "Invalid atom ID in particle data");
+    rmax_all = std::max(rmax_all, radius[i]); rmin_all = std::min(rmin_all, radius[i]);
+    if (e->nranks == 1 || brick_owns(B, x + 3 * i)) mine.push_back(i);
+  }
+  const long nm = (long)mine.size(), n0 = e->nlocal, need = n0 + nm;
+  if (need >= (long)NBR_IDX) dem_fail(e, DEM_ERR_OVERFLOW, "more than 2^25 particles on one GPU");
+  if (rmax_all > e->rmax || rmin_all < e->rmin || !(e->rmin > 0.0)) {  // the neighbour cutoff / cell grid follow the extreme radii
+    e->rmax = std::max(e->rmax, rmax_all); e->rmin = e->rmin > 0.0 ? std::min(e->rmin, rmin_all) : rmin_all; e->dirty = 1;
+  }
+  if (nm) {
+    if (need > e->cap) ensure_particle_cap(e, need + need / 4 + 1024, n0);
+    std::vector<double> hx(3 * nm), hv(3 * nm, 0.0), hw(3 * nm, 0.0), hr(nm), hd(nm);
+    std::vector<int> ht(nm), hm(nm, 1), hg(nm);
+    for (long q = 0; q < nm; q++) {
+      const long i = mine[q];
+      for (int d = 0; d < 3; d++) { hx[3 * q + d] = x[3 * i + d]; if (v) hv[3 * q + d] = v[3 * i + d]; if (omega) hw[3 * q + d] = omega[3 * i + d]; }
+      hr[q] = radius[i]; hd[q] = density[i]; ht[q] = type[i]; if (mask) hm[q] = mask[i]; hg[q] = tag[i];
+    }
+    const size_t nd = (size_t)nm;
+    e->stage.ensure(e, nd * 11 * sizeof(double) + nd * 3 * sizeof(int) + 64);
+    double *dx = (double *)e->stage.p, *dv = dx + 3 * nd, *dw = dv + 3 * nd, *dr = dw + 3 * nd, *dd = dr + nd;
+    int *dt = (int *)(dd + nd), *dm = dt + nd, *dg = dm + nd;
+    CK(cudaMemcpyAsync(dx, hx.data(), 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv, hv.data(), 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dw, hw.data(), 3 * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dr, hr.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dd, hd.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dt, ht.data(), nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dm, hm.data(), nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg, hg.data(), nd * sizeof(int), cudaMemcpyHostToDevice, st));
+    e->counters.ensure(e, 4);
+    CK(cudaMemsetAsync(e->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(e->counters.p + 2, 0xFF, sizeof(unsigned long long), st));
+    const int c = e->cur;
+    k_pack_upload<<<GRID(nm, 256), 256, 0, st>>>((int)nm, dx, dv, dw, dr, dd, dt, dm, dg, e->ntypes, e->xr[c].p + n0, e->vm[c].p + n0, e->wt[c].p + n0,
+                                                  (int *)(e->counters.p + 1), e->counters.p);
+    e->launches++;
+    CK(cudaMemcpyAsync(e->tag.p + n0, dg, nd * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(e->density.p + n0, dd, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(e->xh.p + n0, 0, nd * sizeof(double4), st));  // no wall candidate / history-valid bits
+    if (e->f.p) for (int d = 0; d < 3; d++) { CK(cudaMemsetAsync(e->f.p + (size_t)d * e->cap + n0, 0, nd * sizeof(double), st)); CK(cudaMemsetAsync(e->tq.p + (size_t)d * e->cap + n0, 0, nd * sizeof(double), st)); }
+    if (e->whist.p) for (int r = 0; r < e->nwrows; r++) CK(cudaMemsetAsync(e->whist.p + (size_t)r * e->cap + n0, 0, nd * sizeof(double), st));
+    if (e->mesh_ready) for (int b = 0; b < 2; b++) if (e->mint[b].p) CK(cudaMemsetAsync(e->mint[b].p + n0, 0, nd * sizeof(int), st));  // no mesh contact rows
+    for (int b = 0; b < 2; b++) {  // the old list: empty rows for the newcomers
+      ListSet &L = e->ls[b];
+      if (!L.valid) continue;
+      if (need > L.cap) { if (L.dnum) grow_list_rows(e, L, e->cap); else { L.valid = 0; continue; } }
+      CK(cudaMemsetAsync(L.numneigh.p + n0, 0, nd * sizeof(int), st));
+    }
+    CK(cudaStreamSynchronize(st));
+    e->nlocal = need;
+  }
+  e->nghost = 0;
+  e->forces_valid = 0; e->order_valid = 0; e->need_setup = 1;
+  API_END
+}
+
 // particle migration between bricks: CommBrick::exchange (comm_brick.cpp:732-860); runs BEFORE the periodic
 // wrap so that the direction is decided on the unwrapped coordinate (the sender wraps while packing)
 static int migrate(dem_engine *E, int ncur, int &ngone)
@@ -2158,7 +2256,7 @@ extern "C" int dem_setup(dem_engine *e)
   launch_step(e, MODE_SETUP, false);
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaGetLastError());
-  e->setup_done = 1; e->forces_valid = 1;
+  e->setup_done = 1; e->forces_valid = 1; e->need_setup = 0;
   API_END
 }
 
@@ -2166,6 +2264,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
 {
   API_BEGIN
   if (!e->setup_done) dem_fail(e, DEM_ERR_STATE, "dem_run before dem_setup");
+  if (e->need_setup) dem_fail(e, DEM_ERR_STATE, "particles were inserted: dem_setup before dem_run");
   if (nsteps < 0) dem_fail(e, DEM_ERR_ARG, "nsteps < 0");
   if (nsteps == 0) return DEM_OK;
   CK(cudaSetDevice(e->device));

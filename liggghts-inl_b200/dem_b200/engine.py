@@ -10,7 +10,7 @@ ABI_SYMBOLS = [
     "dem_create", "dem_destroy", "dem_nccl_unique_id", "dem_decomposition", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
     "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_property",
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
-    "dem_set_integrate", "dem_upload_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
+    "dem_set_integrate", "dem_upload_particles", "dem_insert_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
     "dem_bond_counter", "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
@@ -202,6 +202,17 @@ class Engine:
                       np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
         ptr = [a.ctypes.data if a is not None else None for a in self._keep]
         self._call("upload_particles", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
+
+    def insert(self, tag, type, x, radius, density, v=None, omega=None, mask=None):
+        """particles added between two runs (create_atoms / fix insert/*): appended, existing contact history kept; call setup() next"""
+        n = len(tag)
+        keep = [np.ascontiguousarray(tag, np.int32), np.ascontiguousarray(type, np.int32),
+                None if mask is None else np.ascontiguousarray(mask, np.int32),
+                np.ascontiguousarray(x, np.float64), None if v is None else np.ascontiguousarray(v, np.float64),
+                None if omega is None else np.ascontiguousarray(omega, np.float64),
+                np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
+        ptr = [a.ctypes.data if a is not None else None for a in keep]
+        self._call("insert_particles", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
 
     def setup(self):
         self._call("setup", [])

@@ -320,6 +320,41 @@ int orc_upload_particles(orc_engine *e, long n, const int *tag, const int *type,
   return 0;
 }
 
+/* particles added between two runs (atom_vec_sphere.cpp create_atom via create_atoms / fix insert/*: appended behind the owned
+ * atoms, zero velocity unless given, zero force, no contact partners, no wall history); the next orc_setup rebuilds the lists */
+int orc_insert_particles(orc_engine *e, long n, const int *tag, const int *type, const int *mask,
+                         const double *x, const double *v, const double *omega, const double *radius, const double *density)
+{
+  if (!e->tag) return orc_upload_particles(e, n, tag, type, mask, x, v, omega, radius, density);
+  if (e->nmwalls) return fail(e, "insertion with mesh walls is not restated in the oracle");
+  const long n0 = e->n, nn = n0 + n;
+#define GROW(p, T, c) do { p = (T *)realloc(p, sizeof(T) * (size_t)(nn ? nn : 1) * (c)); memset(p + (size_t)n0 * (c), 0, sizeof(T) * (size_t)n * (c)); } while (0)
+  GROW(e->tag, int, 1); GROW(e->type, int, 1); GROW(e->mask, int, 1); GROW(e->x, double, 3); GROW(e->v, double, 3);
+  GROW(e->f, double, 3); GROW(e->omega, double, 3); GROW(e->torque, double, 3); GROW(e->radius, double, 1);
+  GROW(e->rmass, double, 1); GROW(e->density, double, 1); GROW(e->xhold, double, 3);
+  for (int w = 0; w < e->nwalls; w++) {
+    wall_t *W = &e->walls[w]; const int dn = W->m.dnum ? W->m.dnum : 1;
+    if (W->hist) GROW(W->hist, double, dn);
+    if (W->cand) W->cand = (int *)realloc(W->cand, sizeof(int) * (size_t)(nn ? nn : 1));
+  }
+  if (e->first) { /* the old half list: no entries for the newcomers */
+    e->first = (long *)realloc(e->first, sizeof(long) * (size_t)(nn + 1));
+    e->numneigh = (int *)realloc(e->numneigh, sizeof(int) * (size_t)(nn ? nn : 1));
+    for (long i = n0; i < nn; i++) { e->first[i] = e->npairs; e->numneigh[i] = 0; }
+    e->first[nn] = e->npairs;
+  }
+#undef GROW
+  for (long q = 0; q < n; q++) {
+    const long i = n0 + q;
+    e->tag[i] = tag[q]; e->type[i] = type[q]; e->mask[i] = mask ? mask[q] : 1;
+    for (int d = 0; d < 3; d++) { e->x[3 * i + d] = x[3 * q + d]; e->v[3 * i + d] = v ? v[3 * q + d] : 0.0; e->omega[3 * i + d] = omega ? omega[3 * q + d] : 0.0; }
+    e->radius[i] = radius[q]; e->density[i] = density[q];
+    e->rmass[i] = 4.0 * M_PI / 3.0 * radius[q] * radius[q] * radius[q] * density[q];
+  }
+  e->n = nn;
+  return 0;
+}
+
 /* ---------------------------------------------------------------- derived material tables */
 static void derive_tables(orc_engine *e)
 { /* global_properties.cpp:428-452 (Yeff), 458-483 (Geff), 519-537 (log e), 542-560 (betaeff) */

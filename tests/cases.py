@@ -289,6 +289,9 @@ GOLDEN_CASES = {
     # all INL laws together: hysteretic normal + hysteretic tangential (7 history values, plastic-range restart) + cdtnonlinear2
     "box_hyst1_thyst": dict(kw=dict(n3=(4, 4, 3), model="model hysteretic/nonlinear1 tangential hysteretic/nonlinear rolling_friction cdtnonlinear2", poly=True),
                             checkpoints=[0, 1, 2, 10, 400, 1000]),
+    # particles added between two runs (create_atoms / fix insert/*): six spheres appear above the settling bed
+    # before step 301; the history of the existing contacts must survive, the newcomers fall in and touch
+    "box_insert": dict(kw=dict(n3=(4, 4, 3), poly=True), insert=dict(at=301, n=6), checkpoints=[0, 1, 10, 300, 301, 310, 900, 2500]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
     # rebuild cadence other than `delay 0 every 1 check yes` (Neighbor::decide, neighbor.cpp:1362-1376)
@@ -330,13 +333,28 @@ def make_case(name):
     c = case_box(name=name, **g["kw"])
     if "neigh" in g:
         c["neigh"] = g["neigh"]
+    if "insert" in g:  # newcomers on a small lattice above the initial bed, numbered behind the existing tags
+        k = g["insert"]["n"]
+        rng = np.random.default_rng(777)
+        L = c["hi"][0] - c["lo"][0]
+        xs = np.array([[c["lo"][0] + L * (0.25 + 0.25 * (q % 3)), c["lo"][1] + L * (0.3 + 0.4 * ((q // 3) % 2)), 0.6 * c["hi"][2] + 0.008 * (q // 6)] for q in range(k)])
+        xs += rng.uniform(-2e-4, 2e-4, xs.shape)
+        n0 = len(c["tag"])
+        c["inserts"] = {g["insert"]["at"]: dict(tag=np.arange(n0 + 1, n0 + k + 1, dtype=np.int32), type=np.ones(k, np.int32), x=xs,
+                                                radius=rng.uniform(0.0015, 0.003, k), density=np.full(k, 2500.0))}
     return c
 
 
 def late_commands(c, cp):
     """deck lines to issue before running on to checkpoint cp (empty for most cases)"""
     at, moves = c.get("late_moves", (None, []))
-    return ["fix mv_%s all move/mesh mesh %s %s" % (mid, mid, text) for mid, text in moves] if cp == at else []
+    lines = ["fix mv_%s all move/mesh mesh %s %s" % (mid, mid, text) for mid, text in moves] if cp == at else []
+    ins = c.get("inserts", {}).get(cp)
+    if ins:  # particles added between two runs: create_atoms single + set (the reference numbers them max tag + 1, ...)
+        for k in range(len(ins["tag"])):
+            lines.append("create_atoms %d single %.17g %.17g %.17g units box" % (ins["type"][k], *ins["x"][k]))
+            lines.append("set atom %d diameter %.17g density %.17g" % (ins["tag"][k], 2.0 * ins["radius"][k], ins["density"][k]))
+    return lines
 
 
 def apply_late(c, eng, cp):
@@ -345,6 +363,9 @@ def apply_late(c, eng, cp):
     if cp == at:
         for mid, text in moves:
             eng.move_mesh(mid, text)
+    ins = c.get("inserts", {}).get(cp)
+    if ins:
+        eng.insert(ins["tag"], ins["type"], ins["x"], ins["radius"], ins["density"])
 
 
 def snapshot(eng, c):

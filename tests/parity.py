@@ -42,6 +42,7 @@ def compare_snapshot(got, ref, rmass, tol=FTOL, tol_state=None, hist_tol=None, l
     which history values are rounding noise (e.g. the tangential spring of a plate that only moves along its normal)"""
     tol_state = tol if tol_state is None else tol_state
     hist_tol = tol if hist_tol is None else hist_tol
+    rmass = np.asarray(rmass)[:len(ref["x"])]  # (cases that insert particles later: the fixture's masses are those of the final set, tag order)
     if "bondcounter" in got and "bondcounter" in ref:  # bonds created / broken since the previous checkpoint: exact
         assert np.array_equal(np.asarray(got["bondcounter"]), np.asarray(ref["bondcounter"])), "%s: bond counter %s != %s" % (label, got["bondcounter"], ref["bondcounter"])
     mg = rmass * 9.81

@@ -86,6 +86,19 @@ def main():
         ref = cases.apply(c, parity.oracle_engine()) if rank == 0 else None
         done = 0
         for cp in steps:
+            if cp == 400 and not mesh and not kw.get("periodic"):
+                # particles added between two runs (dem_insert_particles): a row of newcomers above the bed, spread over all the
+                # bricks; every rank is handed the whole set and keeps its own share
+                k = 6 * world
+                n0 = len(c["tag"])
+                L0 = c["hi"][0] - c["lo"][0]
+                xs = np.stack([c["lo"][0] + L0 * (np.arange(k) + 0.5) / k, np.full(k, 0.5 * (c["lo"][1] + c["hi"][1])), np.full(k, 0.5 * c["hi"][2])], 1)
+                new = dict(tag=np.arange(n0 + 1, n0 + k + 1, dtype=np.int32), type=np.ones(k, np.int32), x=xs, radius=np.full(k, 0.0025), density=np.full(k, 2500.0))
+                eng.insert(new["tag"], new["type"], new["x"], new["radius"], new["density"])
+                if rank == 0:
+                    ref.insert(new["tag"], new["type"], new["x"], new["radius"], new["density"])
+                c["tag"] = np.concatenate([c["tag"], new["tag"]])
+                rmass = np.concatenate([rmass, 4.0 * np.pi / 3.0 * new["radius"] ** 3 * new["density"]])
             eng.setup(); eng.run(cp - done)
             snap = gather_snapshot(eng, c, rank, world)
             nls = [None] * world

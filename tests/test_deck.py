@@ -48,7 +48,8 @@ def follow_golden(name, eng, deck, path, gpu):
 
 
 DECK_CASES = ["box_hertz_cdt", "poly_hooke_epsd_cyl", "periodic_epsd2", "mesh_funnel_hooke", "mesh_plate_moving", "mesh_drum_rotating",
-              "mesh_plate_late_move", "bond_nonlinear", "box_neigh_every2_delay4", "box_neigh_nocheck", "mesh_plate_stress", "mesh_drum_stress"]
+              "mesh_plate_late_move", "bond_nonlinear", "box_neigh_every2_delay4", "box_neigh_nocheck", "mesh_plate_stress", "mesh_drum_stress",
+              "box_insert", "box_hyst1_thyst", "bond_linear"]  # (create_atoms single + set atom between two runs; all INL laws; bond counter)
 
 
 @pytest.mark.parametrize("name", DECK_CASES)

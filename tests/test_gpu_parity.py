@@ -128,6 +128,41 @@ def test_bonded_spheres_match_oracle(kw):
     got.close(); ref.close()
 
 
+def test_insertion_that_outgrows_the_lists_matches_oracle():
+    """dem_insert_particles with more newcomers than the particle arrays and the neighbour rows have room for (48 -> 1,548
+    particles): capacity growth and the re-striding of the old list must keep the history of the contacts that already exist"""
+    c = cases.case_box(n3=(4, 4, 3), name="grow", seed=21, poly=True)
+    c["hi"][2] = 0.75  # room for the column of newcomers
+    got = cases.apply(c, gpu_engine())
+    ref = cases.apply(c, parity.oracle_engine())
+    for eng in (got, ref):
+        eng.setup(); eng.run(400)
+    before = cases.snapshot(got, c)
+    assert int(before["pair_flag"].sum()) > 0, "no contact to preserve"
+    k = 1500
+    L = c["hi"][0] - c["lo"][0]
+    nx = 4
+    q = np.arange(k)
+    xs = np.stack([c["lo"][0] + L * (0.14 + 0.24 * (q % nx)), c["lo"][1] + L * (0.14 + 0.24 * ((q // nx) % nx)), 0.05 + 0.0065 * (q // (nx * nx))], 1)
+    xs += np.random.default_rng(5).uniform(-1e-4, 1e-4, xs.shape)
+    assert xs[:, 2].max() + 0.003 < c["hi"][2]
+    n0 = len(c["tag"])
+    new = dict(tag=np.arange(n0 + 1, n0 + k + 1, dtype=np.int32), type=np.ones(k, np.int32), x=xs, radius=np.full(k, 0.0025), density=np.full(k, 2500.0))
+    rmass = np.concatenate([4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"], 4.0 * np.pi / 3.0 * new["radius"] ** 3 * new["density"]])
+    done = 0
+    for eng in (got, ref):
+        eng.insert(new["tag"], new["type"], new["x"], new["radius"], new["density"])
+    for cp in (0, 1, 10, 300):
+        for eng in (got, ref):
+            eng.setup(); eng.run(cp - done)
+        done = cp
+        sg = cases.snapshot(got, c)
+        assert len(sg["x"]) == n0 + k
+        parity.compare_snapshot(sg, cases.snapshot(ref, c), rmass, tol=tol_at(cp), label="grow@%d" % cp)
+        assert got.stats().nbuilds == ref.stats().nbuilds
+    got.close(); ref.close()
+
+
 def test_many_contacts_on_one_particle_match_oracle():
     """a sphere three times larger than the 40 small ones sitting on its surface: all 40 contacts form in the first step -- far
     more than the 12 contacts the step kernel stages in shared memory and than the default 16 history slots.  Exercises the
