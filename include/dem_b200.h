@@ -85,6 +85,10 @@ int dem_set_processors(dem_engine *e, int px, int py, int pz);
 int dem_set_neighbor(dem_engine *e, double skin, int every, int delay, int check);
 /* `timestep dt`                                                                         */
 int dem_set_timestep(dem_engine *e, double dt);
+/* neigh_modify contact_distance_factor F (neighbor.cpp:1922-1925, F >= 1): list cutoff (r_i + r_j) F + skin, pairs inside the band
+ * that do not touch run the models' surfacesClose (pair_gran_base.h:418-422: tangential / rolling history zeroed); the bond
+ * models raise it themselves (Neighbor::register_contact_dist_factor keeps the larger value). */
+int dem_set_contact_distance_factor(dem_engine *e, double f);
 /* `fix ID all property/global <name> scalar|peratomtype|peratomtypepair v...`
  *                                  src/fix_property_global.cpp, global_properties.cpp   */
 int dem_set_property(dem_engine *e, const char *name, const char *kind, const double *values, int n);

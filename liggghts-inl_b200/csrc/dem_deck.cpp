@@ -46,6 +46,7 @@ int API(set_ntypes)(dem_engine *e, int ntypes);
 int API(set_processors)(dem_engine *e, int px, int py, int pz);
 int API(set_neighbor)(dem_engine *e, double skin, int every, int delay, int check);
 int API(set_timestep)(dem_engine *e, double dt);
+int API(set_contact_distance_factor)(dem_engine *e, double f);
 int API(set_property)(dem_engine *e, const char *name, const char *kind, const double *values, int n);
 int API(set_pair_style)(dem_engine *e, int argc, const char *const *argv);
 int API(add_wall_primitive)(dem_engine *e, const char *id, int argc, const char *const *argv);
@@ -605,7 +606,7 @@ int one(Deck *d, const std::string &raw)
       if (w[k] == "every") { rc = inumeric(d, w[k + 1], d->every); if (rc) return rc; }
       else if (w[k] == "delay") { rc = inumeric(d, w[k + 1], d->delay); if (rc) return rc; }
       else if (w[k] == "check") { if (w[k + 1] != "yes" && w[k + 1] != "no") return fail(d, ERR_ARG, "Illegal neigh_modify command"); d->check = w[k + 1] == "yes"; }
-      else if (w[k] == "contact_distance_factor") { double f; rc = numeric(d, w[k + 1], f); if (rc) return rc; if (f != 1.0) return fail(d, ERR_UNSUPPORTED, "neigh_modify contact_distance_factor != 1 is set by the bond models only"); }
+      else if (w[k] == "contact_distance_factor") { double f; rc = numeric(d, w[k + 1], f); if (rc) return rc; TRY(API(set_contact_distance_factor)(d->e, f)); }
       else if (w[k] == "page" || w[k] == "one" || w[k] == "binsize") continue;
       else return fail(d, ERR_UNSUPPORTED, "neigh_modify keyword '%s' is outside the hot-path scope", w[k].c_str());
     }

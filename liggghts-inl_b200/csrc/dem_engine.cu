@@ -234,6 +234,7 @@ struct dem_engine {
   cudaEvent_t fev[2] = {nullptr, nullptr};  // "flags of slot k are on the host"
   // step flags between ranks over peer memory (k_push / k_wait): my flag box, every rank's box, serial of the last hand-over
   // fused ghost push (fused_halo_setup): image table, block order, device parameter block; fz_on: the next launch_step uses it
+  double cdf_user = 0.0;  // neigh_modify contact_distance_factor, 0 = not given
   int need_setup = 0;  // particles were inserted: the next dem_run needs a dem_setup first (lists, forces)
   DevBuf<unsigned long long> bondc;  // compute bond/counter: created, broken, scratch for the total
   DevBuf<int> img_first, img_ws, img_in; DevBuf<int4> img_tab; DevBuf<ImgP> imgp; int fz_ready = 0, fz_on = 0, fz_rq[2] = {-1, -1}, slot_zeroed = 0;
@@ -444,6 +445,15 @@ static int bond_table_of(const std::string &nm)
     {"kcinCustom", T_H_KCIN}};
   auto it = m.find(nm);
   return it == m.end() ? -1 : it->second;
+}
+
+extern "C" int dem_set_contact_distance_factor(dem_engine *e, double f)
+{
+  API_BEGIN
+  if (!(f >= 1.0)) dem_fail(e, DEM_ERR_ARG, "Illegal neigh_modify command. Please set contact_distance_factor value >=1");
+  if (f >= 10.0) dem_fail(e, DEM_ERR_ARG, "contactDistanceFactor must be < 10");
+  e->cdf_user = f; e->dirty = 1; e->ls[0].valid = e->ls[1].valid = 0;
+  API_END
 }
 
 extern "C" int dem_set_property(dem_engine *e, const char *name, const char *kind, const double *v, int n)
@@ -1160,7 +1170,8 @@ static void derive_tables(dem_engine *E)
     at(T_MU) = E->mu[i][j]; at(T_RMU) = E->rmu[i][j]; at(T_RVISC) = E->rvisc[i][j];
     if (hertz || hooke) { at(T_SQ2Y) = sqrt(2. * at(T_YEFF)); at(T_SQ8G) = sqrt(8. * at(T_GEFF)); at(T_INV8G) = 1. / (8. * at(T_GEFF)); }
   }
-  E->cdf = 1.0;
+  E->cdf = E->cdf_user > 1.0 ? E->cdf_user : 1.0;  // neigh_modify contact_distance_factor (neighbor.cpp:1922-1925)
+  if (E->cdf > 1.0 && E->have_pair && E->pm.normal >= N_HYST1) dem_fail(E, DEM_ERR_UNSUPPORTED, "contact_distance_factor > 1 with the hysteretic/nonlinear laws is outside the hot-path scope");
   if (E->have_pair && E->pm.cohesion) {
     const ModelP &m = E->pm;
     const bool nl = m.cohesion == C_BONDNL;
@@ -1175,7 +1186,7 @@ static void derive_tables(dem_engine *E)
     for (int w = T_B_LAMBDA; w < T_H_KEL; w++) for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) t[((size_t)w * n1 + i) * n1 + j] = E->bp[w][i][j];
     // neighbor->register_contact_dist_factor: cohesion_model_bond.h:391-475, cohesion_model_bond_nonlinear.h:336-382
     if (!(E->rmin > 0.)) dem_fail(E, DEM_ERR_STATE, "Bond settings: The minimum radius can't be <= 0!");
-    double cdf_all = 1.;
+    double cdf_all = E->cdf;  // register_contact_dist_factor keeps the larger one (neighbor.h:142)
     for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) {
       double one;
       if (!m.stressBreak) one = 1.1 * 0.5 * E->bp[T_B_MAXDIST][i][j] / E->rmin;
@@ -1900,7 +1911,7 @@ static void rebuild(dem_engine *E)
   // 5. full Verlet list + history remap
   ListSet &Lold = E->ls[E->lcur], &Lnew = E->ls[E->lcur ^ 1];
   // full list (k_step, k_step_bond) unless option owner_list asks for the measured alternative of dem_pairs.cuh
-  const int fmt = (E->have_pair && !E->pm.cohesion && E->pm.normal < N_HYST1 && E->opt.count("owner_list") && E->opt["owner_list"] != 0) ? 1 : 0;
+  const int fmt = (E->have_pair && !E->pm.cohesion && E->pm.normal < N_HYST1 && E->cdf == 1.0 && E->opt.count("owner_list") && E->opt["owner_list"] != 0) ? 1 : 0;
   int maxk = std::max(Lold.valid ? Lold.maxk : 0, (int)(E->opt.count("maxneigh") ? E->opt["maxneigh"] : 24));
   // history rows: by default one per row entry (a particle can never gain more contacts between two rebuilds than it has
   // list entries, so the step kernels cannot run out of rows and drop a contact's history; rows that are not in use cost

@@ -430,6 +430,8 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
         close &= close - 1;
         const unsigned w = P.nbr[(size_t)(k0 + u) * P.lcap + i];
         const int slot = (int)((w & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
+        // (the hertz / hooke normal models leave their bit of the pair's contact flags set in surfacesClose, normal_model_hertz.h:410-413:
+        //  the pair keeps its row and stays flagged)
         for (int r = 0; r < P.pm.hrec; r++) st4(P.hist + (size_t)(slot * P.pm.hrec + r) * P.lcap + i, make_double4(0., 0., 0., 0.));
       }
     }

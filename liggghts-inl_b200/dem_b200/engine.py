@@ -8,7 +8,7 @@ _ROOT = os.path.dirname(_HERE)
 # every symbol declared in include/dem_b200.h
 ABI_SYMBOLS = [
     "dem_create", "dem_destroy", "dem_nccl_unique_id", "dem_decomposition", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
-    "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_property",
+    "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_contact_distance_factor", "dem_set_property",
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
     "dem_set_integrate", "dem_upload_particles", "dem_insert_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
@@ -202,6 +202,9 @@ class Engine:
                       np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
         ptr = [a.ctypes.data if a is not None else None for a in self._keep]
         self._call("upload_particles", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
+
+    def contact_distance_factor(self, f):
+        self._call("set_contact_distance_factor", [C.c_double], float(f))
 
     def insert(self, tag, type, x, radius, density, v=None, omega=None, mask=None):
         """particles added between two runs (create_atoms / fix insert/*): appended, existing contact history kept; call setup() next"""

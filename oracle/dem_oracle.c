@@ -96,6 +96,7 @@ typedef struct orc_engine {
   double g[3]; int have_gravity;
   int freezebit, integbit;
   double cdf; /* neighbor->contactDistanceFactor (1.0 without bond models) */
+  double cdf_user; /* neigh_modify contact_distance_factor (neighbor.cpp:1922-1925), 0 = not given */
   /* particles */
   long n; int *tag, *type, *mask;
   double *x, *v, *f, *omega, *torque, *radius, *rmass, *density, *xhold;
@@ -137,6 +138,7 @@ int orc_set_processors(orc_engine *e, int a, int b, int c) { (void)e; return (a 
 int orc_set_neighbor(orc_engine *e, double skin, int every, int delay, int check)
 { e->skin = skin; e->every = every; e->delay = delay; e->check = check; return 0; }
 int orc_set_timestep(orc_engine *e, double dt) { e->dt = dt; return 0; }
+int orc_set_contact_distance_factor(orc_engine *e, double f) { if (f < 1.0) return fail(e, "Illegal neigh_modify command. Please set contact_distance_factor value >=1"); e->cdf_user = f; return 0; }
 
 /* peratomtypepair properties of the two bond models (cohesion_model_bond.h:76-178, cohesion_model_bond_nonlinear.h:77-147) */
 enum { BP_LAMBDA = 0, BP_KN, BP_KT, BP_DFN, BP_DFT, BP_DTN, BP_DTT, BP_MAXDIST, BP_MAXSIGMA, BP_MAXTAU, BP_CREATEDIST, BP_RATIOTC,
@@ -1592,10 +1594,10 @@ int orc_setup(orc_engine *e)
 { /* Verlet::setup verlet.cpp:134-199 */
   if (!e->n && !e->tag) return fail(e, "no particles uploaded");
   derive_tables(e);
-  e->cdf = 1.0;
+  e->cdf = e->cdf_user > 1.0 ? e->cdf_user : 1.0;
   if (e->have_pair && e->pm.cohesion) { /* cohesion_model_bond.h:391-475 / cohesion_model_bond_nonlinear.h:336-382: neighbor->register_contact_dist_factor */
     double minrad = 1e99; for (long i = 0; i < e->n; i++) if (e->radius[i] < minrad) minrad = e->radius[i];
-    double cdf_all = 1.;
+    double cdf_all = e->cdf; /* register_contact_dist_factor: max(existing, requested), neighbor.h:142 */
     for (int i = 1; i <= e->ntypes; i++) for (int j = 1; j <= e->ntypes; j++) {
       double one;
       if (!e->pm.stressBreak) one = 1.1 * 0.5 * e->bp[BP_MAXDIST][i][j] / minrad;

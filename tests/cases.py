@@ -217,7 +217,8 @@ def to_deck(c, datafile):
     deck = ["units si", "atom_style sphere", "atom_modify map array sort 0 0", "boundary " + b, "newton off",
             "communicate single vel yes", "read_data " + datafile, "neighbor %.17g bin" % c["skin"],
             "neigh_modify delay %d every %d check %s" % (c.get("neigh", (1, 0, True))[1], c.get("neigh", (1, 0, True))[0],
-                                                         "yes" if c.get("neigh", (1, 0, True))[2] else "no")]
+                                                         "yes" if c.get("neigh", (1, 0, True))[2] else "no")
+            + (" contact_distance_factor %.17g" % c["cdf"] if c.get("cdf") else "")]
     for k, (name, kind, vals) in enumerate(c["props"]):
         extra = " %d" % c["ntypes"] if kind == "peratomtypepair" else ""
         deck.append("fix m%d all property/global %s %s%s %s" % (k, name, kind, extra, " ".join("%.17g" % v for v in vals)))
@@ -251,6 +252,8 @@ def apply(c, eng):
     eng.ntypes(c["ntypes"])
     every, delay, check = c.get("neigh", (1, 0, True))  # neigh_modify every / delay / check
     eng.neighbor(c["skin"], every=every, delay=delay, check=check)
+    if c.get("cdf"):
+        eng.contact_distance_factor(c["cdf"])
     for name, kind, vals in c["props"]:
         eng.property_global(name, kind, vals)
     eng.pair_style(c["pair"])
@@ -292,6 +295,10 @@ GOLDEN_CASES = {
     # particles added between two runs (create_atoms / fix insert/*): six spheres appear above the settling bed
     # before step 301; the history of the existing contacts must survive, the newcomers fall in and touch
     "box_insert": dict(kw=dict(n3=(4, 4, 3), poly=True), insert=dict(at=301, n=6), checkpoints=[0, 1, 10, 300, 301, 310, 900, 2500]),
+    # neigh_modify contact_distance_factor on a plain contact model (neighbor.cpp:1922-1925): pairs inside the band that do not
+    # touch run surfacesClose -- tangential / rolling history zeroed (the flag stays: the normal model keeps its bit)
+    "box_cdf": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history rolling_friction epsd", poly=True), cdf=1.15,
+                    checkpoints=[0, 1, 10, 400, 1500]),
     "hertz_nodamp_notroll": dict(kw=dict(n3=(3, 3, 3), model="model hertz tangential history", settings="tangential_damping off",
                                          poly=True), checkpoints=[0, 1, 300, 1500]),
     # rebuild cadence other than `delay 0 every 1 check yes` (Neighbor::decide, neighbor.cpp:1362-1376)
@@ -333,6 +340,8 @@ def make_case(name):
     c = case_box(name=name, **g["kw"])
     if "neigh" in g:
         c["neigh"] = g["neigh"]
+    if "cdf" in g:
+        c["cdf"] = g["cdf"]
     if "insert" in g:  # newcomers on a small lattice above the initial bed, numbered behind the existing tags
         k = g["insert"]["n"]
         rng = np.random.default_rng(777)
