@@ -662,6 +662,7 @@ __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const
     if (displacement > 0.0) H[27] = 0.0;
   }
   if (M.tension || M.compression) {
+    if (!NL && M.dissipation && update_history) H[1] += (r - H[1]) * fmin(dt * tabv(P, T_D_FN, it, jt), 1.0);  // relax the normal spring (:677-687; the force below uses the displacement formed before)
     if ((M.tension && displacement < -1.e-15) || (M.compression && displacement > 1.e-15)) {
       double frcmag;
       if (!NL) frcmag = tabv(P, T_B_KN, it, jt) * A * displacement;
@@ -688,6 +689,7 @@ __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const
     for (int d = 0; d < 3; d++) dtforce[d] = vtr[d] * (-ktA * A * dt);
     vproject(force_tang, en, tmp1);
     for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] - tmp1[d];
+    if (!NL && M.dissipation) { const double k = 1.0 - fmin(dt * tabv(P, T_D_FT, it, jt), 1.0); for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] * k; }  // :731-732
     for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] + dtforce[d];
     if (M.damping) for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d] - dft * fabs(force_tang[d]) * damp_mult(M, vtr[d], minvel, 0.01 * force_tang[d] * dt);
     else for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d];
@@ -699,6 +701,7 @@ __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const
       double dnt[3];
       for (int d = 0; d < 3; d++) dnt[d] = wn[d] * (-kt_pb * J * dt);
       vproject(torque_normal, en, torque_normal);
+      if (M.dissipation) { const double k = 1.0 - fmin(dt * tabv(P, T_D_TN, it, jt), 1.0); for (int d = 0; d < 3; d++) torque_normal[d] = torque_normal[d] * k; }  // :763-764
       for (int d = 0; d < 3; d++) torque_normal[d] = torque_normal[d] + dnt[d];
       if (M.damping) for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d] - dtn * fabs(torque_normal[d]) * dsgn(wn[d]);
       else for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d];
@@ -709,6 +712,7 @@ __device__ __forceinline__ bool bond_eval(const StepP &P, const ModelP &M, const
         double dtt3[3];
         for (int d = 0; d < 3; d++) dtt3[d] = wt[d] * (-kn_pb * I * dt);
         vproject(torque_tang, wt, torque_tang);
+        if (M.dissipation) { const double k = 1.0 - fmin(dt * tabv(P, T_D_TT, it, jt), 1.0); for (int d = 0; d < 3; d++) torque_tang[d] = torque_tang[d] * k; }  // :798-799
         for (int d = 0; d < 3; d++) torque_tang[d] = torque_tang[d] + dtt3[d];
         if (M.damping) for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d] - dtt * fabs(torque_tang[d]) * dsgn(wt[d]);
         else for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d];

@@ -442,7 +442,8 @@ static int bond_table_of(const std::string &nm)
     // normal models hysteretic/nonlinear1|2
     {"LoadingStiffness", T_H_KEL}, {"UnloadingStiffness", T_H_KN2K1}, {"coefficientAdhesionStiffness", T_H_KN2KC}, {"coefficientPlasticityDepth", T_H_PHIF},
     {"pullOffForce", T_H_FADH}, {"alphaCustom", T_H_ALPHA}, {"cinCustom", T_H_CIN}, {"aoneCustom", T_H_A1}, {"atwoCustom", T_H_A2}, {"athreeCustom", T_H_A3},
-    {"kcinCustom", T_H_KCIN}};
+    {"kcinCustom", T_H_KCIN},
+    {"dissipationNormalForceBond", T_D_FN}, {"dissipationTangentialForceBond", T_D_FT}, {"dissipationNormalTorqueBond", T_D_TN}, {"dissipationTangentialTorqueBond", T_D_TT}};
   auto it = m.find(nm);
   return it == m.end() ? -1 : it->second;
 }
@@ -559,6 +560,7 @@ static void parse_model_settings(dem_engine *e, int argc, const char *const *a, 
     else if (m.cohesion && !strcmp(a[0], "shearTorqueStress")) m.ttorque = on;
     else if (m.cohesion && !strcmp(a[0], "createBondAlways")) m.createAlways = on;
     else if (m.cohesion && !strcmp(a[0], "dampingBond")) m.damping = on;
+    else if (m.cohesion == C_BOND && !strcmp(a[0], "dissipationBond")) m.dissipation = on;
     else if (m.cohesion && !strcmp(a[0], "dampingBondSmooth")) { m.dampingSmooth = on; if (on) m.damping = 1; }
     else if (m.cohesion == C_BOND && !strcmp(a[0], "ratioTensionCompression")) m.ratioTC = on;
     else if (m.cohesion == C_BONDNL && !strcmp(a[0], "ratioTensionCompressionBond")) m.ratioTC = on;
@@ -1179,11 +1181,17 @@ static void derive_tables(dem_engine *E)
     auto needb = [&](const std::string &base) { const std::string nm = base + sfx; need(nm.c_str()); };
     needb("radiusMultiplierBond"); needb("createDistanceBond");
     if (!m.createAlways) needb("tsCreateBond");
+    if (!m.damping && !m.dissipation) dem_fail(E, DEM_ERR_ARG, "Damping or dissipation has to be enabled.");
+    if (m.dissipation) for (const char *k : {"dissipationNormalForceBond", "dissipationTangentialForceBond", "dissipationNormalTorqueBond", "dissipationTangentialTorqueBond"}) need(k);
     if (m.damping) { needb("dampingNormalForceBond"); needb("dampingTangentialForceBond"); needb("dampingNormalTorqueBond"); needb("dampingTangentialTorqueBond"); }
     if (!m.stressBreak) needb("maxDistanceBond"); else { needb("maxSigmaBond"); needb("maxTauBond"); }
     if (!nl) { need("normalBondStiffnessPerUnitArea"); need("tangentialBondStiffnessPerUnitArea"); }
     else for (const char *k : {"K_fn1", "Ku_fn1", "Kc_fn1", "K_fn2", "Ku_fn2", "Kc_fn2", "K_ft", "K_tn", "Ku_tn", "Kc_tn", "K_tt", "Ku_tt", "Kc_tt"}) need((std::string("stiffnessPerUnitArea") + k).c_str());
     for (int w = T_B_LAMBDA; w < T_H_KEL; w++) for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) t[((size_t)w * n1 + i) * n1 + j] = E->bp[w][i][j];
+    if (m.dissipation) for (int w = T_D_FN; w <= T_D_TT; w++) for (int i = 1; i <= T; i++) for (int j = 1; j <= T; j++) {
+      if (E->bp[w][i][j] < E->dt) dem_fail(E, DEM_ERR_ARG, "dissipation time scale > time-step size required");
+      t[((size_t)w * n1 + i) * n1 + j] = 1. / E->bp[w][i][j];  // saved already inverted
+    }
     // neighbor->register_contact_dist_factor: cohesion_model_bond.h:391-475, cohesion_model_bond_nonlinear.h:336-382
     if (!(E->rmin > 0.)) dem_fail(E, DEM_ERR_STATE, "Bond settings: The minimum radius can't be <= 0!");
     double cdf_all = E->cdf;  // register_contact_dist_factor keeps the larger one (neighbor.h:142)

@@ -13,6 +13,8 @@ enum { T_YEFF = 0, T_GEFF, T_BETA, T_CORLOG, T_MU, T_RMU, T_RVISC, T_SQ2Y, T_SQ8
        T_B_K_FN1, T_B_KU_FN1, T_B_KC_FN1, T_B_K_FN2, T_B_KU_FN2, T_B_KC_FN2, T_B_K_FT, T_B_K_TN, T_B_KU_TN, T_B_KC_TN, T_B_K_TT, T_B_KU_TT, T_B_KC_TT,
        // normal models hysteretic/nonlinear1|2 (normal_model_hysteretic_nonlinear1.h:105-133)
        T_H_KEL, T_H_KN2K1, T_H_KN2KC, T_H_PHIF, T_H_FADH, T_H_ALPHA, T_H_CIN, T_H_A1, T_H_A2, T_H_A3, T_H_KCIN,
+       // linear bond, option dissipationBond: 1 / dissipation{Normal,Tangential}{Force,Torque}Bond (inverted like createDissipationMatrix, global_properties.cpp:1138-1163)
+       T_D_FN, T_D_FT, T_D_TN, T_D_TT,
        T_COUNT };
 enum { C_OFF = 0, C_BOND = 1, C_BONDNL = 2 };
 
@@ -40,6 +42,7 @@ struct ModelP {
   // double (the reference's contact_flags != 0 after a touch or a kept rebuild, see dem_kernels.cuh k_step_bond)
   int cohesion, off_bond, nbond, rec_bond, nbrec;
   int stressBreak, tension, compression, shearf, ntorque, ttorque, createAlways, damping, dampingSmooth, ratioTC;
+  int dissipation;  // cohesion bond: dissipationBond on (cohesion_model_bond.h:270,677-687,731,763,798)
 };
 
 struct WallP {

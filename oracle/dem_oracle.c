@@ -38,6 +38,7 @@ typedef struct {
   int normal, tangential, rolling;
   int tangential_damping, limitForce, torsionTorque, ktToKn;
   int cdtnl2; /* rolling_friction cdtnonlinear2 */
+  int dissipation; /* cohesion bond: dissipationBond on (cohesion_model_bond.h:270) */
   int dnum, off_shear, off_roll, off_norm; /* off_norm: the 12 history values of normal model hysteretic/nonlinear1|2 */
   /* cohesion bond / bond/nonlinear: cohesion_model_bond.h:254-276, cohesion_model_bond_nonlinear.h:233-246 */
   int cohesion, off_bond;
@@ -144,7 +145,9 @@ int orc_set_contact_distance_factor(orc_engine *e, double f) { if (f < 1.0) retu
 enum { BP_LAMBDA = 0, BP_KN, BP_KT, BP_DFN, BP_DFT, BP_DTN, BP_DTT, BP_MAXDIST, BP_MAXSIGMA, BP_MAXTAU, BP_CREATEDIST, BP_RATIOTC,
        BP_K_FN1, BP_KU_FN1, BP_KC_FN1, BP_K_FN2, BP_KU_FN2, BP_KC_FN2, BP_K_FT, BP_K_TN, BP_KU_TN, BP_KC_TN, BP_K_TT, BP_KU_TT, BP_KC_TT, BP_COUNT,
        /* normal models hysteretic/nonlinear1|2 (normal_model_hysteretic_nonlinear1.h:105-117) */
-       HP_KEL = BP_COUNT, HP_KN2K1, HP_KN2KC, HP_PHIF, HP_FADH, HP_ALPHA, HP_CIN, HP_A1, HP_A2, HP_A3, HP_KCIN, HP_END };
+       HP_KEL = BP_COUNT, HP_KN2K1, HP_KN2KC, HP_PHIF, HP_FADH, HP_ALPHA, HP_CIN, HP_A1, HP_A2, HP_A3, HP_KCIN,
+       /* linear bond, option dissipationBond (cohesion_model_bond.h:352-362; stored as given, inverted where used) */
+       DP_FN, DP_FT, DP_TN, DP_TT, HP_END };
 static int bond_prop_index(const char *name)
 {
   static const char *lin[] = {"radiusMultiplierBond", "normalBondStiffnessPerUnitArea", "tangentialBondStiffnessPerUnitArea", "dampingNormalForceBond",
@@ -157,6 +160,8 @@ static int bond_prop_index(const char *name)
   static const char *hy[] = {"LoadingStiffness", "UnloadingStiffness", "coefficientAdhesionStiffness", "coefficientPlasticityDepth", "pullOffForce",
     "alphaCustom", "cinCustom", "aoneCustom", "atwoCustom", "athreeCustom", "kcinCustom"};
   for (int k = 0; k < 11; k++) if (!strcmp(name, hy[k])) return HP_KEL + k;
+  static const char *dp[] = {"dissipationNormalForceBond", "dissipationTangentialForceBond", "dissipationNormalTorqueBond", "dissipationTangentialTorqueBond"};
+  for (int k = 0; k < 4; k++) if (!strcmp(name, dp[k])) return DP_FN + k;
   for (int k = 0; k < 12; k++) if (!strcmp(name, lin[k])) return k;
   for (int k = 0; k < BP_COUNT; k++) if (nl[k][0] && !strcmp(name, nl[k])) return k;
   return -1;
@@ -251,6 +256,7 @@ static int parse_settings(orc_engine *e, int argc, const char *const *a, model_t
     else if (m->cohesion && !strcmp(a[0], "shearTorqueStress")) m->ttorque = on;
     else if (m->cohesion && !strcmp(a[0], "createBondAlways")) m->createAlways = on;
     else if (m->cohesion && !strcmp(a[0], "dampingBond")) m->damping = on;
+    else if (m->cohesion == C_BOND && !strcmp(a[0], "dissipationBond")) m->dissipation = on;
     else if (m->cohesion && !strcmp(a[0], "dampingBondSmooth")) m->dampingSmooth = on;
     else if (m->cohesion == C_BOND && !strcmp(a[0], "ratioTensionCompression")) m->ratioTC = on;
     else if (m->cohesion == C_BONDNL && !strcmp(a[0], "ratioTensionCompressionBond")) m->ratioTC = on;
@@ -764,6 +770,10 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
     if (displacement > 0.0) H[27] = 0.0;
   }
   if (m->tension || m->compression) {
+    if (!NL && m->dissipation && update_history) { /* relax the normal spring, cohesion_model_bond.h:677-687 (the force below still uses the displacement formed before) */
+      const double dissipate = fmin(dt * (1. / e->bp[DP_FN][it][jt]), 1.0);
+      H[1] += (r - H[1]) * dissipate;
+    }
     if ((m->tension && displacement < -1.e-15) || (m->compression && displacement > 1.e-15)) {
       double frcmag;
       if (!NL) frcmag = e->bp[BP_KN][it][jt] * A * displacement;
@@ -788,6 +798,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
     double dtforce[3]; for (int d = 0; d < 3; d++) dtforce[d] = vtr[d] * (-ktA * A * dt);
     vproject(force_tang, en, tmp1);
     for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] - tmp1[d];
+    if (!NL && m->dissipation) { const double k = 1.0 - fmin(dt * (1. / e->bp[DP_FT][it][jt]), 1.0); for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] * k; } /* :731-732 */
     for (int d = 0; d < 3; d++) force_tang[d] = force_tang[d] + dtforce[d];
     if (m->damping) for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d] - dft * fabs(force_tang[d]) * damp_mult(m, vtr[d], minvel, 0.01 * force_tang[d] * dt);
     else for (int d = 0; d < 3; d++) tforce_d[d] = force_tang[d];
@@ -798,6 +809,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
     if (m->ntorque) {
       double dnt[3]; for (int d = 0; d < 3; d++) dnt[d] = wn[d] * (-kt_pb * J * dt);
       vproject(torque_normal, en, torque_normal);
+      if (m->dissipation) { const double k = 1.0 - fmin(dt * (1. / e->bp[DP_TN][it][jt]), 1.0); for (int d = 0; d < 3; d++) torque_normal[d] = torque_normal[d] * k; } /* :763-764 */
       for (int d = 0; d < 3; d++) torque_normal[d] = torque_normal[d] + dnt[d];
       if (m->damping) for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d] - dtn * fabs(torque_normal[d]) * isgn(wn[d]);
       else for (int d = 0; d < 3; d++) ntorque_d[d] = torque_normal[d];
@@ -807,6 +819,7 @@ static void cohesion_bond(const orc_engine *e, const model_t *m, sid_t *s)
       if (wtsq > 0) {
         double dtt3[3]; for (int d = 0; d < 3; d++) dtt3[d] = wt[d] * (-kn_pb * I * dt);
         vproject(torque_tang, wt, torque_tang);
+        if (m->dissipation) { const double k = 1.0 - fmin(dt * (1. / e->bp[DP_TT][it][jt]), 1.0); for (int d = 0; d < 3; d++) torque_tang[d] = torque_tang[d] * k; } /* :798-799 */
         for (int d = 0; d < 3; d++) torque_tang[d] = torque_tang[d] + dtt3[d];
         if (m->damping) for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d] - dtt * fabs(torque_tang[d]) * isgn(wt[d]);
         else for (int d = 0; d < 3; d++) ttorque_d[d] = torque_tang[d];

@@ -70,6 +70,9 @@ def case_box(n3=(4, 4, 4), model="model hertz tangential history rolling_frictio
                   ("dampingTangentialTorqueBond" + sfx, "peratomtypepair", full(bond.get("damp", 0.1))),
                   ("tsCreateBond" + sfx, "scalar", [bond.get("ts", 2)]),
                   ("createDistanceBond" + sfx, "peratomtypepair", full(bond.get("create", 2.2 * 0.003 if poly else 2.2 * rad)))]
+        if "dissipationBond on" in settings:  # time scales of the bond's relaxation (cohesion_model_bond.h:352-362)
+            props += [("dissipationNormalForceBond", "peratomtypepair", full(2e-3)), ("dissipationTangentialForceBond", "peratomtypepair", full(1e-3)),
+                      ("dissipationNormalTorqueBond", "peratomtypepair", full(4e-3)), ("dissipationTangentialTorqueBond", "peratomtypepair", full(3e-3))]
         if "stressBreak on" in settings:
             props += [("maxSigmaBond" + sfx, "peratomtypepair", full(bond.get("sigma", 2e5))), ("maxTauBond" + sfx, "peratomtypepair", full(bond.get("tau", 1e5)))]
         else:
@@ -323,6 +326,8 @@ GOLDEN_CASES = {
                         checkpoints=[0, 1, 2, 3, 10, 100]),
     "bond_linear_stress": dict(kw=dict(n3=(4, 4, 3), model="model hertz tangential history rolling_friction cdt", settings="stressBreak on",
                                        bond=dict(kind="bond", sigma=4e4, tau=2e4)), checkpoints=[0, 1, 2, 3, 10, 100]),
+    "bond_linear_dissipation": dict(kw=dict(n3=(4, 4, 3), model="model hertz tangential history", settings="dissipationBond on", poly=True,
+                                            bond=dict(kind="bond", maxdist=2.1 * 0.003)), checkpoints=[0, 1, 2, 3, 10, 100]),
     "bond_nonlinear": dict(kw=dict(n3=(4, 4, 4), model="model hertz tangential history", poly=True, bond=dict(kind="bond/nonlinear")),
                            checkpoints=[0, 1, 2, 3, 10, 100, 400]),
 }
