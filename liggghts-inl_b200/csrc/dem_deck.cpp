@@ -60,6 +60,8 @@ int API(upload_particles)(dem_engine *e, long n, const int *tag, const int *type
                           const double *omega, const double *radius, const double *density);
 int API(insert_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
                           const double *omega, const double *radius, const double *density);
+long API(nlocal)(const dem_engine *e);
+int API(download)(dem_engine *e, const char *field, void *out, long count);
 int API(setup)(dem_engine *e);
 int API(run)(dem_engine *e, long nsteps);
 #endif
@@ -90,6 +92,10 @@ struct Deck {
   std::vector<int> ptag, ptype, pmask;
   std::vector<double> px, pv, pomega, pradius, pdensity;
   int maxtag = 0;
+  // dump custom (dump_custom.cpp): text snapshots every N steps, atoms in ascending id
+  struct Dump { std::string file; long every = 0, last = -1; std::vector<std::string> fields; };
+  std::map<std::string, Dump> dumps;
+  std::string bstr[3] = {"ff", "ff", "ff"};  // Domain::boundary_string
   long ntimestep = 0;
 };
 
@@ -375,6 +381,66 @@ void mesh_rotate(std::vector<double> &nodes, const double axis[3], double phi_de
   }
 }
 
+// dump custom: one snapshot (dump_custom.cpp:380-392 header, :1027-1042 lines: every value "%d " / "%g ", atoms in ascending id)
+int write_dump(Deck *d, Deck::Dump &D)
+{
+  const long n = API(nlocal)(d->e);
+  std::string path = D.file;
+  const size_t star = path.find('*');
+  const bool per_step = star != std::string::npos;
+  if (per_step) path = path.substr(0, star) + std::to_string(d->ntimestep) + path.substr(star + 1);
+  if (!path.empty() && path[0] != '/' && !d->dir.empty()) path = d->dir + "/" + path;
+  FILE *fp = fopen(path.c_str(), (per_step || D.last < 0) ? "w" : "a");
+  if (!fp) return fail(d, ERR_ARG, "Cannot open dump file %s", path.c_str());
+  fprintf(fp, "ITEM: TIMESTEP\n%ld\nITEM: NUMBER OF ATOMS\n%ld\nITEM: BOX BOUNDS %s %s %s\n", d->ntimestep, n, d->bstr[0].c_str(), d->bstr[1].c_str(), d->bstr[2].c_str());
+  for (int k = 0; k < 3; k++) fprintf(fp, "%g %g\n", d->lo[k], d->hi[k]);
+  fprintf(fp, "ITEM: ATOMS");
+  for (auto &f : D.fields) fprintf(fp, " %s", f.c_str());
+  fprintf(fp, " \n");
+  std::map<std::string, std::vector<double>> dv; std::map<std::string, std::vector<int>> iv;
+  auto needd = [&](const char *f, int w) -> int { if (dv.count(f)) return OK; dv[f].resize((size_t)std::max<long>(n, 1) * w); return n ? API(download)(d->e, f, dv[f].data(), n) : OK; };
+  auto needi = [&](const char *f) -> int { if (iv.count(f)) return OK; iv[f].resize((size_t)std::max<long>(n, 1)); return n ? API(download)(d->e, f, iv[f].data(), n) : OK; };
+  struct Col { int kind; const void *p; int w, c; double scale; };  // kind 0 int, 1 double
+  std::vector<Col> cols;
+  for (auto &f : D.fields) {
+    int rc = OK; Col c{1, nullptr, 1, 0, 1.0};
+    auto vec3 = [&](const char *fld, const char *base) -> bool {
+      const std::string b(base);
+      for (int k = 0; k < 3; k++) if (f == b + "xyz"[k]) { rc = needd(fld, 3); c = Col{1, dv[fld].data(), 3, k, 1.0}; return true; }
+      return false;
+    };
+    if (f == "id") { rc = needi("tag"); c = Col{0, iv["tag"].data(), 1, 0, 1.0}; }
+    else if (f == "type") { rc = needi("type"); c = Col{0, iv["type"].data(), 1, 0, 1.0}; }
+    else if (f == "x" || f == "y" || f == "z") { rc = needd("x", 3); c = Col{1, dv["x"].data(), 3, f == "x" ? 0 : f == "y" ? 1 : 2, 1.0}; }
+    else if (vec3("v", "v") || vec3("f", "f") || vec3("omega", "omega") || vec3("torque", "tq")) {}
+    else if (f == "radius") { rc = needd("radius", 1); c = Col{1, dv["radius"].data(), 1, 0, 1.0}; }
+    else if (f == "diameter") { rc = needd("radius", 1); c = Col{1, dv["radius"].data(), 1, 0, 2.0}; }
+    else if (f == "mass") { rc = needd("rmass", 1); c = Col{1, dv["rmass"].data(), 1, 0, 1.0}; }
+    else if (f == "density") { rc = needd("density", 1); c = Col{1, dv["density"].data(), 1, 0, 1.0}; }
+    else { fclose(fp); return fail(d, ERR_UNSUPPORTED, "dump custom field '%s' is outside the hot-path scope", f.c_str()); }
+    if (rc) { fclose(fp); return engine_failed(d, rc); }
+    cols.push_back(c);
+  }
+  for (long i = 0; i < n; i++) {
+    for (auto &c : cols) {
+      if (c.kind == 0) fprintf(fp, "%d ", ((const int *)c.p)[i]);
+      else fprintf(fp, "%g ", c.scale * ((const double *)c.p)[(size_t)i * c.w + c.c]);
+    }
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
+  D.last = d->ntimestep;
+  return OK;
+}
+int write_dumps_due(Deck *d)
+{  // snapshots on the steps that are multiples of N (output.cpp:150-190), once per step
+  for (auto &kv : d->dumps) {
+    Deck::Dump &D = kv.second;
+    if (D.every > 0 && d->ntimestep % D.every == 0 && D.last != d->ntimestep) { const int rc = write_dump(d, D); if (rc) return rc; }
+  }
+  return OK;
+}
+
 int first_run_prepare(Deck *d)
 {
   if (d->uploaded) {
@@ -531,7 +597,7 @@ int one(Deck *d, const std::string &raw)
   const std::vector<std::string> w = split(line);
   if (w.empty()) return OK;
   const std::string &c = w[0];
-  static const char *output_only[] = {"thermo", "thermo_style", "thermo_modify", "compute", "uncompute", "dump", "dump_modify", "undump", "echo", "log",
+  static const char *output_only[] = {"thermo", "thermo_style", "thermo_modify", "compute", "uncompute", "echo", "log",
                                      "print", "restart", "write_restart", "write_data", "info", "reset_timestep_info", nullptr};
   for (int k = 0; output_only[k]; k++) if (c == output_only[k]) { d->warnings += c + " ignored (output only)\n"; return OK; }
   if (c == "variable") {  // styles equal (formula, see Formula) / string / index (variable.cpp:90-330)
@@ -557,6 +623,7 @@ int one(Deck *d, const std::string &raw)
     if (w.size() != 4) return fail(d, ERR_ARG, "Illegal boundary command");
     for (int k = 0; k < 3; k++) {
       const std::string &b = w[1 + k];
+      d->bstr[k] = b.size() == 1 ? b + b : b;
       if (b == "p") d->periodic[k] = 1;
       else if (b == "f" || b == "m" || b == "s" || b == "ff" || b == "mm" || b == "fm" || b == "mf" || b == "ss") d->periodic[k] = 0;
       else return fail(d, ERR_ARG, "Illegal boundary command");
@@ -627,6 +694,22 @@ int one(Deck *d, const std::string &raw)
   }
   if (c == "group") return cmd_group(d, w);
   if (c == "timestep") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal timestep command"); double dt; rc = numeric(d, w[1], dt); if (rc) return rc; TRY(API(set_timestep)(d->e, dt)); return OK; }
+  if (c == "dump") {  // dump ID group custom N file field ...   (dump.cpp:60-110, dump_custom.cpp:95-180)
+    if (w.size() < 6) return fail(d, ERR_ARG, "Illegal dump command");
+    if (w[3] != "custom") { d->warnings += "dump style " + w[3] + " ignored (output only)\n"; return OK; }
+    if (w[2] != "all") return fail(d, ERR_UNSUPPORTED, "dump custom: only group 'all' is on the hot path");
+    if (w.size() == 6) return fail(d, ERR_ARG, "No dump custom arguments specified");
+    double nd; rc = numeric(d, w[4], nd); if (rc) return rc;
+    if ((long)nd <= 0) return fail(d, ERR_ARG, "Invalid dump frequency");
+    Deck::Dump D; D.every = (long)nd; D.file = w[5]; D.fields.assign(w.begin() + 6, w.end());
+    d->dumps[w[1]] = D; return OK;
+  }
+  if (c == "undump") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal undump command"); d->dumps.erase(w[1]); return OK; }
+  if (c == "dump_modify") {  // atoms are always written in ascending id (== `sort id`); other keywords do not change the content
+    if (w.size() < 2) return fail(d, ERR_ARG, "Illegal dump_modify command");
+    for (size_t k = 2; k < w.size(); k++) if (w[k] == "format") return fail(d, ERR_UNSUPPORTED, "dump_modify format is outside the hot-path scope");
+    return OK;
+  }
   if (c == "create_atoms") {  // create_atoms.cpp (style single): one atom of the given type at a point; radius 0.5, density 1 until `set` (atom_vec_sphere.cpp:167-190)
     if (w.size() < 6 || w[2] != "single") return fail(d, ERR_UNSUPPORTED, "create_atoms: only style 'single' is on the hot path (lattice / random creation is outside its scope)");
     if (!d->have_box) return fail(d, ERR_STATE, "Create_atoms command before simulation box is defined");
@@ -681,8 +764,15 @@ int one(Deck *d, const std::string &raw)
     if (n < 0) return fail(d, ERR_ARG, "Invalid run command N value");
     rc = first_run_prepare(d); if (rc) return rc;
     TRY(API(setup)(d->e));
-    TRY(API(run)(d->e, n));
-    d->ntimestep += n; return OK;
+    rc = write_dumps_due(d); if (rc) return rc;
+    while (n > 0) {  // the run in slices that end on the next snapshot step (no setup in between: one run of the reference)
+      long chunk = n;
+      for (auto &kv : d->dumps) if (kv.second.every > 0) chunk = std::min(chunk, (d->ntimestep / kv.second.every + 1) * kv.second.every - d->ntimestep);
+      TRY(API(run)(d->e, chunk));
+      d->ntimestep += chunk; n -= chunk;
+      rc = write_dumps_due(d); if (rc) return rc;
+    }
+    return OK;
   }
   return fail(d, ERR_UNSUPPORTED, "command '%s' is outside the hot-path scope", c.c_str());
 }

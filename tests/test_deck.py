@@ -170,7 +170,8 @@ run\t\t200
     eng, dk = oracle_deck()
     dk.file(str(tmp_path / "in.tut"))
     assert dk.ntimestep == 500
-    assert "dump ignored" in dk.warnings and "check/timestep/gran ignored" in dk.warnings and "fix balance ignored" in dk.warnings
+    assert "check/timestep/gran ignored" in dk.warnings and "fix balance ignored" in dk.warnings
+    assert (tmp_path / "out.0.dump").exists(), "dump custom writes its first snapshot at step 0 (a multiple of N)"
     assert "region factory (cylinder) kept as a name only" in dk.warnings
     # the same through the API calls, step for step
     ref = parity.oracle_engine()
@@ -218,3 +219,53 @@ def test_deck_variable_formulas(tmp_path):
     with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Invalid syntax"):
         deck.command("variable y equal 2*(3"); deck.command("timestep ${y}")
     deck.close(); eng.close(); ref.close()
+
+
+# ---- dump custom: the text snapshots of the deck front end against the reference's own dump file -------------------------------
+DUMP_FIELDS = "id type x y z vx vy vz fx fy fz omegax omegay omegaz radius"
+
+
+def _parse_dump(text):
+    snaps, lines, k = [], text.splitlines(), 0
+    while k < len(lines):
+        assert lines[k] == "ITEM: TIMESTEP"
+        step = int(lines[k + 1]); n = int(lines[k + 3])
+        head = lines[k + 2:k + 9]
+        cols = lines[k + 8].split()[2:]
+        rows = np.array([[float(v) for v in ln.split()] for ln in lines[k + 9:k + 9 + n]])
+        snaps.append((step, head, cols, rows))
+        k += 9 + n
+    return snaps
+
+
+def _follow_dump(eng, deck, tmp_path, tol):
+    c = cases.make_case("box_hertz_cdt")
+    path = write_deck(c, tmp_path)
+    out = os.path.join(str(tmp_path), "dump.txt")
+    deck.file(path)
+    deck.command("dump d1 all custom 100 %s %s" % (out, DUMP_FIELDS))
+    deck.command("dump_modify d1 sort id")
+    deck.command("run 250")
+    got = _parse_dump(open(out).read())
+    ref = _parse_dump(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dump_box_hertz_cdt.txt")).read())
+    assert [s[0] for s in got] == [s[0] for s in ref] == [0, 100, 200]
+    for (gs, gh, gc, gr), (rs, rh, rc, rr) in zip(got, ref):
+        assert gh == rh, "snapshot header differs at step %d: %s != %s" % (gs, gh, rh)
+        assert gc == rc and gr.shape == rr.shape
+        assert np.array_equal(gr[:, :2], rr[:, :2])
+        scale = np.maximum(np.abs(rr[:, 2:]).max(axis=0), 1e-300)
+        assert (np.abs(gr[:, 2:] - rr[:, 2:]) / scale).max() <= tol, "dump values differ at step %d" % gs   # (%g prints six digits)
+    assert deck.ntimestep == 250
+    deck.close(); eng.close()
+
+
+def test_dump_custom_on_oracle_matches_reference_file(tmp_path):
+    eng, deck = oracle_deck()
+    _follow_dump(eng, deck, tmp_path, 2e-6)
+
+
+@pytest.mark.gpu
+def test_dump_custom_on_engine_matches_reference_file(tmp_path):
+    import dem_b200
+    eng = dem_b200.Engine(device=0)
+    _follow_dump(eng, dem_b200.Deck(eng), tmp_path, 2e-6)
