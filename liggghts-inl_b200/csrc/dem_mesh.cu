@@ -45,67 +45,37 @@ __device__ __forceinline__ double calc_dist(const double *cs, const double *cp, 
 __device__ __forceinline__ bool edge_active(const TriRec &T, int k) { return (T.flags >> (2 + k)) & 1; }
 __device__ __forceinline__ bool corner_active(const TriRec &T, int k) { return (T.flags >> (5 + k)) & 1; }
 
-// tri_mesh_I.h:129-170 (skip_inactive = true)
-__device__ double resolve_edge(const TriRec &T, int iEdge, const double *p, double *delta, double *bary)
+// Closest feature of a triangle for a sphere centre, as data instead of as a tree of calls.  The barycentric sign pattern of the
+// centre's projection names a region of the plane (tri_mesh_I.h:65-127): 7 = over the face, 3 / 5 / 6 = beyond one edge,
+// 1 / 2 / 4 = beyond a corner.  Each region resolves to ONE feature -- the face, a point at parameter s on an edge, or a node --
+// through at most two projections onto edge directions (the second only at an obtuse corner, :174-255); the feature is then
+// evaluated by one common tail.  Every arithmetic expression is the reference's (same operands, same order: the region codes
+// and overlaps must be bit-identical); inactive edges / corners answer LARGE_TRIMESH (:141-158, skip_inactive).
+struct TriFeature { int kind, idx, base; double s, sgn; };  // kind 0 node `idx`; 1 point base-node + s * edgeVec[idx], bary[base] = 1 + sgn * s / len
+__device__ __forceinline__ double along(const TriRec &T, const double *p, int node, int edge)
 {
-  const int ip = (iEdge + 1) % 3, ipp = (iEdge + 2) % 3;
-  double nodeToP[3];
-  sub3(p, T.node + 3 * iEdge, nodeToP);
-  const double distFromNode = dot3(nodeToP, T.edgeVec + 3 * iEdge);
-  if (distFromNode < -SMALL_TRIMESH) {
-    if (!corner_active(T, iEdge)) return LARGE_TRIMESH;
-    bary[iEdge] = 1.; bary[ip] = 0.; bary[ipp] = 0.;
-    return calc_dist(p, T.node + 3 * iEdge, delta);
-  } else if (distFromNode > T.edgeLen[iEdge] + SMALL_TRIMESH) {
-    if (!corner_active(T, ip)) return LARGE_TRIMESH;
-    bary[iEdge] = 0.; bary[ip] = 1.; bary[ipp] = 0.;
-    return calc_dist(p, T.node + 3 * ip, delta);
-  }
-  if (!edge_active(T, iEdge)) return LARGE_TRIMESH;
-  double cp[3];
-  for (int d = 0; d < 3; d++) cp[d] = T.node[3 * iEdge + d] + distFromNode * T.edgeVec[3 * iEdge + d];
-  const double dd = calc_dist(p, cp, delta);
-  bary[ipp] = 0.; bary[iEdge] = 1. - distFromNode / T.edgeLen[iEdge]; bary[ip] = 1. - bary[iEdge];
-  return dd;
+  double v[3];
+  sub3(p, T.node + 3 * node, v);
+  return dot3(v, T.edgeVec + 3 * edge);
 }
-// tri_mesh_I.h:174-255
-__device__ double resolve_corner(const TriRec &T, int iNode, bool obtuse, const double *p, double *delta, double *bary)
-{
-  const int ip = (iNode + 1) % 3, ipp = (iNode + 2) % 3;
-  const double *n = T.node + 3 * iNode;
+__device__ __forceinline__ TriFeature feature_beyond_edge(const TriRec &T, int e, const double *p)
+{  // :129-170
+  const int ip = (e + 1) % 3;
+  const double s = along(T, p, e, e);
+  if (s < -SMALL_TRIMESH) return TriFeature{0, e, e, 0., 0.};
+  if (s > T.edgeLen[e] + SMALL_TRIMESH) return TriFeature{0, ip, ip, 0., 0.};
+  return TriFeature{1, e, e, s, -1.};
+}
+__device__ __forceinline__ TriFeature feature_beyond_corner(const TriRec &T, int k, bool obtuse, const double *p)
+{  // :174-255: at an obtuse corner the region reaches over the two adjacent edges
+  const int ip = (k + 1) % 3, ipp = (k + 2) % 3;
   if (obtuse) {
-    double nodeToP[3], cp[3];
-    sub3(p, n, nodeToP);
-    double distFromNode = dot3(nodeToP, T.edgeVec + 3 * ipp);
-    if (distFromNode < SMALL_TRIMESH) {
-      if (distFromNode > -T.edgeLen[ipp]) {
-        if (!edge_active(T, ipp)) return LARGE_TRIMESH;
-        for (int d = 0; d < 3; d++) cp[d] = n[d] + distFromNode * T.edgeVec[3 * ipp + d];
-        bary[ip] = 0.; bary[iNode] = 1. + distFromNode / T.edgeLen[ipp]; bary[ipp] = 1. - bary[iNode];
-        return calc_dist(p, cp, delta);
-      } else {
-        if (!corner_active(T, ipp)) return LARGE_TRIMESH;
-        bary[ipp] = 1.; bary[iNode] = bary[ip] = 0.;
-        return calc_dist(p, T.node + 3 * ipp, delta);
-      }
-    }
-    distFromNode = dot3(nodeToP, T.edgeVec + 3 * iNode);
-    if (distFromNode > -SMALL_TRIMESH) {
-      if (distFromNode < T.edgeLen[iNode]) {
-        if (!edge_active(T, iNode)) return LARGE_TRIMESH;
-        for (int d = 0; d < 3; d++) cp[d] = n[d] + distFromNode * T.edgeVec[3 * iNode + d];
-        bary[ipp] = 0.; bary[iNode] = 1. - distFromNode / T.edgeLen[iNode]; bary[ip] = 1. - bary[iNode];
-        return calc_dist(p, cp, delta);
-      } else {
-        if (!corner_active(T, ip)) return LARGE_TRIMESH;
-        bary[ip] = 1.; bary[iNode] = bary[ipp] = 0.;
-        return calc_dist(p, T.node + 3 * ip, delta);
-      }
-    }
+    const double sb = along(T, p, k, ipp);  // backwards along the edge that ends in this node
+    if (sb < SMALL_TRIMESH) return sb > -T.edgeLen[ipp] ? TriFeature{1, ipp, k, sb, 1.} : TriFeature{0, ipp, ipp, 0., 0.};
+    const double sf = along(T, p, k, k);    // forwards along the edge that starts here
+    if (sf > -SMALL_TRIMESH) return sf < T.edgeLen[k] ? TriFeature{1, k, k, sf, -1.} : TriFeature{0, ip, ip, 0., 0.};
   }
-  if (!corner_active(T, iNode)) return LARGE_TRIMESH;
-  bary[iNode] = 1.; bary[ip] = bary[ipp] = 0.;
-  return calc_dist(p, n, delta);
+  return TriFeature{0, k, k, 0., 0.};
 }
 // TriMesh::resolveTriSphereContactBary  tri_mesh_I.h:65-127 ; returns distance - radius
 __device__ double tri_contact(const TriRec &T, double precision, double rSphere, const double *c, double *delta, double *bary, int &barySign)
@@ -122,25 +92,35 @@ __device__ double tri_contact(const TriRec &T, double precision, double rSphere,
   const double invlen = 1. / (2. * T.rbound);
   const int bs = (bary[0] > -precision * invlen) + 2 * (bary[1] > -precision * invlen) + 4 * (bary[2] > -precision * invlen);
   barySign = bs;
-  const int ob = (T.flags & 3) - 1;
-  double d = 1.;
-  switch (bs) {
-    case 1: d = resolve_corner(T, 0, ob == 0, c, delta, bary); break;
-    case 2: d = resolve_corner(T, 1, ob == 1, c, delta, bary); break;
-    case 3: d = resolve_edge(T, 0, c, delta, bary); break;
-    case 4: d = resolve_corner(T, 2, ob == 2, c, delta, bary); break;
-    case 5: d = resolve_edge(T, 2, c, delta, bary); break;
-    case 6: d = resolve_edge(T, 1, c, delta, bary); break;
-    case 7: {  // resolveFaceContactBary :259-271
-      const double dNorm = dot3(T.surfNorm, n0c);
-      double cs[3];
-      for (int k = 0; k < 3; k++) cs[k] = c[k] - T.surfNorm[k] * dNorm;
-      d = calc_dist(c, cs, delta);
-      break;
-    }
-    default: d = 1.; break;
+  if (bs == 0) return 1. - rSphere;
+  if (bs == 7) {  // over the face (:259-271): foot of the perpendicular, barycentric coordinates as computed above
+    const double dNorm = dot3(T.surfNorm, n0c);
+    double cs[3];
+    for (int k = 0; k < 3; k++) cs[k] = c[k] - T.surfNorm[k] * dNorm;
+    return calc_dist(c, cs, delta) - rSphere;
   }
-  return d - rSphere;
+  // region -> (edge or corner, which): bit patterns with two set bits lie beyond the edge opposite to the cleared bit
+  const int ob = (T.flags & 3) - 1;
+  const int single = (bs & (bs - 1)) == 0;                       // 1, 2, 4: beyond a corner
+  const int which = single ? (bs == 1 ? 0 : bs == 2 ? 1 : 2) : (bs == 3 ? 0 : bs == 6 ? 1 : 2);   // node 0 / 1 / 2 (1, 2, 4) ; edge 0 / 1 / 2 (3, 6, 5)
+  const TriFeature f = single ? feature_beyond_corner(T, which, ob == which, c) : feature_beyond_edge(T, which, c);
+  if (f.kind == 0) {
+    if (!corner_active(T, f.idx)) return LARGE_TRIMESH - rSphere;
+    bary[0] = bary[1] = bary[2] = 0.; bary[f.idx] = 1.;
+    return calc_dist(c, T.node + 3 * f.idx, delta) - rSphere;
+  }
+  if (!edge_active(T, f.idx)) return LARGE_TRIMESH - rSphere;
+  double cp[3];
+  for (int d = 0; d < 3; d++) cp[d] = T.node[3 * f.base + d] + f.s * T.edgeVec[3 * f.idx + d];
+  const double dist = calc_dist(c, cp, delta);
+  // the two nodes of edge idx share the weight; the edge's other node is idx + 1 when the point is measured from the edge's
+  // own start (sgn -1) and idx itself when it is measured backwards from the edge's end node (sgn +1, base = idx + 1)
+  const int other = f.sgn < 0. ? (f.idx + 1) % 3 : f.idx;
+  const int third = 3 - f.base - other;
+  bary[third] = 0.;
+  bary[f.base] = 1. + f.sgn * (f.s / T.edgeLen[f.idx]);
+  bary[other] = 1. - bary[f.base];
+  return dist - rSphere;
 }
 
 // ---------------------------------------------------------------------------------------------
