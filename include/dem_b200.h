@@ -226,6 +226,11 @@ int dem_deck_file(dem_deck *d, const char *path);
 const char *dem_deck_last_error(const dem_deck *d);
 const char *dem_deck_warnings(const dem_deck *d);
 long dem_deck_ntimestep(const dem_deck *d);
+/* thermo output (thermo.cpp:311-330 header, :334-400 lines: one line at the start of a run, on the multiples of `thermo N` and on
+ * the last step; keywords step atoms ke erotate cpu time elapsed, style `one` = step atoms ke cpu) collected so far, and a
+ * switch that also prints it to stdout as it is produced (the reference's screen). */
+const char *dem_deck_output(const dem_deck *d);
+int dem_deck_screen(dem_deck *d, int on);
 
 #ifdef __cplusplus
 }

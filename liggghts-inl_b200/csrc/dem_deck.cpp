@@ -16,6 +16,7 @@
 // named orc_deck_* and drive the CPU oracle's orc_* functions) so that the parser is covered without a GPU.
 #include <cctype>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -96,6 +97,12 @@ struct Deck {
   struct Dump { std::string file; long every = 0, last = -1; std::vector<std::string> fields; };
   std::map<std::string, Dump> dumps;
   std::string bstr[3] = {"ff", "ff", "ff"};  // Domain::boundary_string
+  // thermo (thermo.cpp): one line at the start of a run, on the multiples of N and on the last step
+  long thermo_every = 0; double dt = 0.0;
+  std::vector<std::string> thermo_kw = {"step", "atoms", "ke", "cpu"};  // thermo.cpp:98 (style one)
+  bool screen = false;      // print the lines to stdout as they come (lmp_b200); they are always kept in `out`
+  std::string out;
+  std::chrono::steady_clock::time_point loop0;
   long ntimestep = 0;
 };
 
@@ -381,6 +388,50 @@ void mesh_rotate(std::vector<double> &nodes, const double axis[3], double phi_de
   }
 }
 
+// thermo: header (thermo.cpp:311-330: "%8s " for integers, "%14s " for floats) and one line of values ("%8ld ", "%14.8g ")
+struct ThermoCol { const char *kw, *head; bool is_int; };
+static const ThermoCol thermo_cols[] = {{"step", "Step", true}, {"atoms", "Atoms", true}, {"ke", "KinEng", false}, {"erotate", "RotEng", false},
+                                        {"cpu", "CPU", false}, {"time", "Time", false}, {"elapsed", "Elapsed", true}, {nullptr, nullptr, false}};
+const ThermoCol *thermo_col(const std::string &kw) { for (const ThermoCol *c = thermo_cols; c->kw; c++) if (kw == c->kw) return c; return nullptr; }
+void emit(Deck *d, const std::string &line) { d->out += line; if (d->screen) { fputs(line.c_str(), stdout); fflush(stdout); } }
+int thermo_header(Deck *d)
+{
+  std::string line; char buf[64];
+  for (auto &kw : d->thermo_kw) { const ThermoCol *c = thermo_col(kw); snprintf(buf, sizeof buf, c->is_int ? "%8s " : "%14s ", c->head); line += buf; }
+  emit(d, line + "\n"); return OK;
+}
+int thermo_line(Deck *d, bool first, long run_first)
+{
+  const long n = API(nlocal)(d->e);
+  double ke = 0.0, erot = 0.0;
+  bool need_ke = false, need_er = false;
+  for (auto &kw : d->thermo_kw) { need_ke |= kw == "ke"; need_er |= kw == "erotate"; }
+  if ((need_ke || need_er) && n) {  // compute_ke.cpp:60-80, compute_erotate_sphere.cpp:60-90 (mvv2e = 1 in the supported unit systems)
+    std::vector<double> m(n), v(3 * n);
+    TRY(API(download)(d->e, "rmass", m.data(), n));
+    if (need_ke) { TRY(API(download)(d->e, "v", v.data(), n)); for (long i = 0; i < n; i++) ke += m[i] * (v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]); ke *= 0.5; }
+    if (need_er) {
+      std::vector<double> r(n);
+      TRY(API(download)(d->e, "omega", v.data(), n)); TRY(API(download)(d->e, "radius", r.data(), n));
+      for (long i = 0; i < n; i++) erot += (v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]) * r[i] * r[i] * m[i];
+      erot *= 0.5 * 0.4;
+    }
+  }
+  const double cpu = first ? 0.0 : std::chrono::duration<double>(std::chrono::steady_clock::now() - d->loop0).count();
+  std::string line; char buf[64];
+  for (auto &kw : d->thermo_kw) {
+    if (kw == "step") snprintf(buf, sizeof buf, "%8ld ", d->ntimestep);
+    else if (kw == "atoms") snprintf(buf, sizeof buf, "%8ld ", n);
+    else if (kw == "elapsed") snprintf(buf, sizeof buf, "%8ld ", d->ntimestep - run_first);
+    else if (kw == "ke") snprintf(buf, sizeof buf, "%14.8g ", ke);
+    else if (kw == "erotate") snprintf(buf, sizeof buf, "%14.8g ", erot);
+    else if (kw == "cpu") snprintf(buf, sizeof buf, "%14.8g ", cpu);
+    else if (kw == "time") snprintf(buf, sizeof buf, "%14.8g ", d->ntimestep * d->dt);
+    line += buf;
+  }
+  emit(d, line + "\n"); return OK;
+}
+
 // dump custom: one snapshot (dump_custom.cpp:380-392 header, :1027-1042 lines: every value "%d " / "%g ", atoms in ascending id)
 int write_dump(Deck *d, Deck::Dump &D)
 {
@@ -597,7 +648,7 @@ int one(Deck *d, const std::string &raw)
   const std::vector<std::string> w = split(line);
   if (w.empty()) return OK;
   const std::string &c = w[0];
-  static const char *output_only[] = {"thermo", "thermo_style", "thermo_modify", "compute", "uncompute", "echo", "log",
+  static const char *output_only[] = {"thermo_modify", "compute", "uncompute", "echo", "log",
                                      "print", "restart", "write_restart", "write_data", "info", "reset_timestep_info", nullptr};
   for (int k = 0; output_only[k]; k++) if (c == output_only[k]) { d->warnings += c + " ignored (output only)\n"; return OK; }
   if (c == "variable") {  // styles equal (formula, see Formula) / string / index (variable.cpp:90-330)
@@ -693,7 +744,24 @@ int one(Deck *d, const std::string &raw)
     return fail(d, ERR_UNSUPPORTED, "unfix of a hot-path fix is outside the hot-path scope");
   }
   if (c == "group") return cmd_group(d, w);
-  if (c == "timestep") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal timestep command"); double dt; rc = numeric(d, w[1], dt); if (rc) return rc; TRY(API(set_timestep)(d->e, dt)); return OK; }
+  if (c == "timestep") { if (w.size() != 2) return fail(d, ERR_ARG, "Illegal timestep command"); double dt; rc = numeric(d, w[1], dt); if (rc) return rc; TRY(API(set_timestep)(d->e, dt)); d->dt = dt; return OK; }
+  if (c == "thermo") {  // thermo N (output.cpp:430-460)
+    if (w.size() != 2) return fail(d, ERR_ARG, "Illegal thermo command");
+    double nd; rc = numeric(d, w[1], nd); if (rc) return rc;
+    if ((long)nd < 0) return fail(d, ERR_ARG, "Illegal thermo command");
+    d->thermo_every = (long)nd; return OK;
+  }
+  if (c == "thermo_style") {  // thermo_style one | custom kw ... : columns outside the path's state (computes, variables, fixes) are dropped with a note
+    if (w.size() < 2) return fail(d, ERR_ARG, "Illegal thermo_style command");
+    if (w[1] == "one" || w[1] == "multi") { d->thermo_kw = {"step", "atoms", "ke", "cpu"}; return OK; }
+    if (w[1] != "custom") return fail(d, ERR_ARG, "Illegal thermo style command");
+    d->thermo_kw.clear();
+    for (size_t k = 2; k < w.size(); k++) {
+      if (thermo_col(w[k])) d->thermo_kw.push_back(w[k]);
+      else d->warnings += "thermo keyword " + w[k] + " ignored (output only)\n";
+    }
+    return OK;
+  }
   if (c == "dump") {  // dump ID group custom N file field ...   (dump.cpp:60-110, dump_custom.cpp:95-180)
     if (w.size() < 6) return fail(d, ERR_ARG, "Illegal dump command");
     if (w[3] != "custom") { d->warnings += "dump style " + w[3] + " ignored (output only)\n"; return OK; }
@@ -765,12 +833,18 @@ int one(Deck *d, const std::string &raw)
     rc = first_run_prepare(d); if (rc) return rc;
     TRY(API(setup)(d->e));
     rc = write_dumps_due(d); if (rc) return rc;
-    while (n > 0) {  // the run in slices that end on the next snapshot step (no setup in between: one run of the reference)
+    const long run_first = d->ntimestep;
+    d->loop0 = std::chrono::steady_clock::now();
+    thermo_header(d);
+    rc = thermo_line(d, true, run_first); if (rc) return rc;
+    while (n > 0) {  // the run in slices that end on the next output step (no setup in between: one run of the reference)
       long chunk = n;
       for (auto &kv : d->dumps) if (kv.second.every > 0) chunk = std::min(chunk, (d->ntimestep / kv.second.every + 1) * kv.second.every - d->ntimestep);
+      if (d->thermo_every > 0) chunk = std::min(chunk, (d->ntimestep / d->thermo_every + 1) * d->thermo_every - d->ntimestep);
       TRY(API(run)(d->e, chunk));
       d->ntimestep += chunk; n -= chunk;
       rc = write_dumps_due(d); if (rc) return rc;
+      if (n == 0 || (d->thermo_every > 0 && d->ntimestep % d->thermo_every == 0)) { rc = thermo_line(d, false, run_first); if (rc) return rc; }  // (thermo.cpp: every N steps and on the last step)
     }
     return OK;
   }
@@ -795,6 +869,9 @@ void DECK(close)(DECK(handle) *h) { delete h; }
 const char *DECK(last_error)(const DECK(handle) *h) { return h ? h->d.err.c_str() : "null deck"; }
 const char *DECK(warnings)(const DECK(handle) *h) { return h ? h->d.warnings.c_str() : ""; }
 long DECK(ntimestep)(const DECK(handle) *h) { return h ? h->d.ntimestep : -1; }
+// thermo output (header + lines) collected so far; screen(1): also print it to stdout as it is produced (`lmp_b200`)
+const char *DECK(output)(const DECK(handle) *h) { return h ? h->d.out.c_str() : ""; }
+int DECK(screen)(DECK(handle) *h, int on) { if (!h) return ERR_ARG; h->d.screen = on != 0; return OK; }
 // `lammps_command`: one input-script line (no continuation handling, as Input::one)
 int DECK(command)(DECK(handle) *h, const char *line)
 {

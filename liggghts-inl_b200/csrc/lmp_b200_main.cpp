@@ -26,6 +26,7 @@ int main(int argc, char **argv)
   }
   dem_deck *d = nullptr;
   dem_deck_open(&d, e);
+  dem_deck_screen(d, 1);  // thermo lines as they are produced, like the reference's screen
   printf("%s\n", dem_version());
   const auto t0 = std::chrono::steady_clock::now();
   const int rc = dem_deck_file(d, in);

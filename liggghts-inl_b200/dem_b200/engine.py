@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "dem_set_integrate", "dem_upload_particles", "dem_insert_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
-    "dem_bond_counter", "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep",
+    "dem_bond_counter", "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep", "dem_deck_output", "dem_deck_screen",
 ]
 
 
@@ -364,6 +364,12 @@ class Deck:
     @property
     def warnings(self):
         f = getattr(self._lib, self._p + "warnings"); f.restype = C.c_char_p; f.argtypes = [C.c_void_p]
+        return (f(self._h) or b"").decode()
+
+    @property
+    def output(self):
+        """thermo header and lines produced so far"""
+        f = getattr(self._lib, self._p + "output"); f.restype = C.c_char_p; f.argtypes = [C.c_void_p]
         return (f(self._h) or b"").decode()
 
     @property

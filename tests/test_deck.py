@@ -43,7 +43,7 @@ def follow_golden(name, eng, deck, path, gpu):
         parity.compare_snapshot(cases.snapshot(eng, c), parity.golden_at(g, cp), g["rmass"], tol=parity.tol_for(c, cp, gpu=gpu), label="deck %s@%d" % (name, cp))
         assert eng.stats().nbuilds == int(parity.golden_at(g, cp)["nbuilds"])
     assert deck.ntimestep == done
-    assert "thermo ignored" in deck.warnings
+    assert "compute ignored" in deck.warnings and "Step" in deck.output
     deck.close(); eng.close()
 
 
@@ -245,7 +245,18 @@ def _follow_dump(eng, deck, tmp_path, tol):
     deck.file(path)
     deck.command("dump d1 all custom 100 %s %s" % (out, DUMP_FIELDS))
     deck.command("dump_modify d1 sort id")
+    deck.command("thermo_style custom step atoms ke erotate")
+    deck.command("thermo 100")
+    mark = len(deck.output)
     deck.command("run 250")
+    # thermo lines of the run against the reference's log (header text identical, values printed %14.8g)
+    tg = deck.output[mark:].splitlines()
+    tr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "thermo_box_hertz_cdt.txt")).read().splitlines()
+    assert tg[0] == tr[0], "thermo header %r != %r" % (tg[0], tr[0])
+    assert len(tg) == len(tr)
+    for a, b in zip(tg[1:], tr[1:]):
+        fa, fb = [float(v) for v in a.split()], [float(v) for v in b.split()]
+        assert fa[:2] == fb[:2] and np.allclose(fa[2:], fb[2:], rtol=max(tol, 1e-6), atol=0.0), "thermo line %r != %r" % (a, b)
     got = _parse_dump(open(out).read())
     ref = _parse_dump(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dump_box_hertz_cdt.txt")).read())
     assert [s[0] for s in got] == [s[0] for s in ref] == [0, 100, 200]
