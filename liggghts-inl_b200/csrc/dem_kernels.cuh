@@ -1298,7 +1298,9 @@ __global__ void __launch_bounds__(128) k_build_list(const BuildP B)
       if ((w & NBR_HIST) != NBR_HIST) continue;
       w &= ~NBR_HIST;
       const int tagj = B.ptag[(size_t)k * B.cap + i];
-      for (int m = 0; m < nold; m++) {
+      // (a settled bed: the rows hardly change between two rebuilds, so the old row is searched from this entry's own position)
+      for (int mm = 0; mm < nold; mm++) {
+        int m = (k < nold ? k : 0) + mm; if (m >= nold) m -= nold;  // k, k+1, .., wrapping: a rotation of 0..nold-1
         const unsigned wo = B.nbr_old[(size_t)m * B.cap_old + oi];
         if ((wo & NBR_HIST) && B.ptag_old[(size_t)m * B.cap_old + oi] == tagj) {
           const int so = (int)((wo & NBR_HIST) >> NBR_SLOT_SHIFT) - 1;
