@@ -2180,10 +2180,11 @@ static void wait_flags(dem_engine *E, int slot)
   if (E->fev[slot]) CK(cudaEventSynchronize(E->fev[slot]));
 }
 
-// fused ghost push: usable for this launch?  (plain step kernel only: the bond / hysteretic kernels keep the pack-kernel path)
+// fused ghost push: usable for this launch?  (every step kernel of the full list ends in step_epilogue, which stores the copies;
+// the owner-list option keeps the pack-kernel path)
 static bool fused_on(dem_engine *E, int mode)
 {
-  return E->fz_ready && mode != MODE_SETUP && E->ls[E->lcur].fmt == 0 && !(E->have_pair && (E->pm.cohesion || E->pm.normal >= N_HYST1)) && E->nlocal > 0;
+  return E->fz_ready && mode != MODE_SETUP && E->ls[E->lcur].fmt == 0 && E->nlocal > 0;
 }
 // One step on the stream: the step launch, the ghost refresh, the flag hand-over.
 //  * fused ghost push (fz_ready): the step kernel stores every copy of a particle's new records from its epilogue; several

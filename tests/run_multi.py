@@ -66,6 +66,8 @@ def main():
     ok = True
     for kw, steps in ((dict(n3=(16, 8, 8), poly=True, periodic=(1, 1, 0), model="model hertz tangential history rolling_friction epsd2", ntypes=2), (0, 1, 10, 300, 900)),
                       (dict(n3=(14, 6, 6), model="model hertz tangential history rolling_friction cdt"), (0, 1, 10, 400)),
+                      # bonded spheres across the brick boundary (k_step_bond): bonds form at step 2 between particles of different ranks
+                      (dict(n3=(12, 5, 4), model="model hertz tangential history", poly=True, bond=dict(kind="bond/nonlinear")), (0, 1, 2, 3, 10, 100)),
                       # triangle-mesh walls on several GPUs: triangles replicated, mesh contact rows migrate with their particle
                       (dict(mesh="box", n3=(14, 6, 4)), (0, 1, 10, 400, 1200)),
                       (dict(mesh="plate", n3=(12, 6, 4), model="model hertz tangential history rolling_friction epsd"), (0, 1, 10, 400, 1500)),
@@ -76,7 +78,7 @@ def main():
             kw["n3"] = (kw["n3"][0] * world // 2,) + tuple(kw["n3"][1:])
         c = cases.case_mesh(kind=mesh, name="multi_" + mesh, seed=11, **kw) if mesh else cases.case_box(name="multi", seed=11, **kw)
         # give the particles a drift along x so that they migrate between the bricks
-        c["v"][:, 0] += 2.5 if not mesh else 0.8
+        c["v"][:, 0] += (2.5 if not mesh else 0.8) if "bond" not in kw else 0.3
         rmass = 4.0 * np.pi / 3.0 * c["radius"] ** 3 * c["density"]
         eng = make_engine(rank, world, local)
         eng.box(c["lo"], c["hi"], c["periodic"])
@@ -107,10 +109,11 @@ def main():
             if rank == 0:
                 ref.setup(); ref.run(cp - done)
                 tol = 1e-10 if cp <= 10 else (1e-6 if cp <= 400 else (1e-4 if not mesh else 1e-3))
+                if "bond" in kw: tol = parity.tol_for(c, cp, gpu=True)
                 errs = parity.compare_snapshot(snap, cases.snapshot(ref, c), rmass, tol=tol, label="multi@%d" % cp)
                 print("world %d step %4d ok: nlocal per rank %s f err %.2e" % (world, cp, nls, errs["f"]), flush=True)
             done = cp
-        if not kw.get("periodic") and rank == 0:
+        if not kw.get("periodic") and "bond" not in kw and rank == 0:
             assert nls != nl0, "no particle migrated between the bricks in the drift case"
         if mesh and rank == 0:
             assert sum(len(snap["mesh_%s_tag" % m[0]]) for m in c["meshes"]) > 0, "no mesh contact was exercised"
