@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #define DEM_SWEEPW 5  // row entries per sweep pass = position gathers in flight per thread (4: 1.125 ms, 5: 1.082 ms, 6: 1.215 ms, 8: 1.31 ms -- spills)
 #endif
 #ifndef DEM_CPREFETCH
-#define DEM_CPREFETCH 2  // L2 prefetch of a staged contact's operands: 0 none, 1 history rows, 2 history + partner v|m, omega|bits
+#define DEM_CPREFETCH 1  // L2 prefetch of a staged contact's operands: 0 none (0.900 ms), 1 history rows (0.875), 2 history + partner v|m, omega|bits
+                         // (0.906: since v8 the load/store pipe is the binding unit and every prefetch is one more wavefront per lane)
 #endif
 #ifndef DEM_PIPE
 #define DEM_PIPE 0   // contact rounds software pipelined (operands of the next round in flight during the evaluation)
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(128) k_walls(const StepP P)
 #define DEM_STEP_MINBLOCKS 5    // 96 registers; 4 (128 registers) 1.45 ms, 6 (80 registers, spills) 1.42 ms
 #endif
 #ifndef DEM_STEP_WAVE_PREFETCH
-#define DEM_STEP_WAVE_PREFETCH 200  // blocks ahead whose streaming inputs are pulled towards L2 (0 = off: 1.31 ms)
+#define DEM_STEP_WAVE_PREFETCH 100  // blocks ahead whose streaming inputs are pulled towards L2 (v8: 50 0.870, 100 0.870, 150 0.873, 200 0.875, 400 0.887 ms; 0 = off: 1.31 ms on v7)
 #endif
 
 // one list entry w of particle i (block-local index q, operands from the block's shared-memory records): evaluated in MY
