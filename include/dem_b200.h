@@ -138,6 +138,21 @@ int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type,
 int dem_insert_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
                          const double *v, const double *omega, const double *radius, const double *density);
 
+/* The timestep in which `fix insert/pack` (fix_insert.cpp:672-905 FixInsert::pre_exchange, fix_insert_pack.cpp:474-597) creates
+ * particles, in two halves.  The reference inserts INSIDE a timestep: after the first half step of the existing particles
+ * (verlet.cpp:277-286) and before the rebuild it forces (fix->next_reneighbor, neighbor.cpp:1364-1369); the new particles see
+ * this step's force evaluation and second half step only.
+ *   dem_insert_step_begin: first half step of the particles the engine holds (a no-op while it holds none).  Afterwards
+ *                          dem_download "x" returns the positions the reference's overlap check runs against.
+ *   dem_insert_step_end:   the n new particles appear (arrays as dem_insert_particles; mass = density * volume with the
+ *                          volume rounded as fix_template_sphere.cpp:349-350 forms it), lists are rebuilt, forces evaluated,
+ *                          second half step for all.  n == 0: a timestep with a forced rebuild.  Counts as one timestep.
+ * The random streams, regions and the overlap search of the insertion are host work of the caller (the deck front end,
+ * dem_deck.cpp, restates them). */
+int dem_insert_step_begin(dem_engine *e);
+int dem_insert_step_end(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
+                        const double *v, const double *omega, const double *radius, const double *density);
+
 /* ---- run --------------------------------------------------------------------------------
  * dem_setup  == Verlet::setup  (forces with shearupdate = 0)   src/verlet.cpp:134-199
  * dem_run(n) == Verlet::run(n)                                 src/verlet.cpp:264-391   */

@@ -9,6 +9,8 @@
 //   group id|type                                                      src/group.cpp:90-260
 //   fix mesh/surface file ... [move|rotate|scale]                      src/fix_mesh.cpp:95-240,600-690, input_mesh_tri.cpp:308-591
 //   run N [upto]                                                       src/run.cpp:40-130
+//   fix particletemplate/sphere, particledistribution/discrete,        src/fix_template_sphere.cpp:72-366, fix_particledistribution_discrete.cpp:75-470,
+//   fix insert/pack, region cylinder (host side of SURVEY.md 8f-3)     fix_insert.cpp:79-1030, fix_insert_pack.cpp:74-597, region.cpp:498-700, random_park.cpp
 // Commands that only produce output (thermo, dump, compute, ...) are accepted and listed by dem_deck_warnings();
 // anything else that is valid reference syntax but outside the hot path returns DEM_ERR_UNSUPPORTED.
 //
@@ -61,6 +63,9 @@ int API(upload_particles)(dem_engine *e, long n, const int *tag, const int *type
                           const double *omega, const double *radius, const double *density);
 int API(insert_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
                           const double *omega, const double *radius, const double *density);
+int API(insert_step_begin)(dem_engine *e);
+int API(insert_step_end)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
+                         const double *omega, const double *radius, const double *density);
 long API(nlocal)(const dem_engine *e);
 int API(download)(dem_engine *e, const char *field, void *out, long count);
 int API(setup)(dem_engine *e);
@@ -77,8 +82,44 @@ struct Deck {
   std::string err, warnings, dir;  // dir: directory of the deck file (relative paths in read_data / mesh files)
   std::map<std::string, std::string> vars;
   std::set<std::string> var_is_equal;  // equal-style: the stored text is a formula
-  struct Region { double lo[3], hi[3]; };
+  // Park-Miller minimal standard generator, the stream every insertion object of the reference draws from (random_park.cpp:72-110)
+  struct Park {
+    int seed = 1, save = 0; double second = 0.0;
+    double uniform() { const int k = seed / 127773; seed = 16807 * (seed - k * 127773) - 2836 * k; if (seed < 0) seed += 2147483647; return (1.0 / 2147483647) * seed; }
+    double gaussian() {
+      if (save) { save = 0; return second; }
+      double v1, v2, rsq;
+      do { v1 = 2.0 * uniform() - 1.0; v2 = 2.0 * uniform() - 1.0; rsq = v1 * v1 + v2 * v2; } while (!(rsq < 1.0 && rsq != 0.0));
+      const double fac = std::sqrt(-2.0 * std::log(rsq) / rsq);
+      second = v1 * fac; save = 1; return v2 * fac;
+    }
+    void reset(int s) { seed = s; save = 0; }
+  };
+  struct Region {
+    int kind = 0;  // 0 block (lo, hi), 1 cylinder (axis, c1, c2, rad, clo, chi)
+    double lo[3], hi[3];
+    char axis = 'z'; double c1 = 0, c2 = 0, rad = 0, clo = 0, chi = 0;
+    double ext_lo[3], ext_hi[3];  // bounding box (Region::extent_*)
+    Park random;                  // region.cpp:456-457
+  };
   std::map<std::string, Region> regions;
+  // fix particletemplate/sphere, fix particledistribution/discrete, fix insert/pack (host side of the insertion: where and when;
+  // the particles themselves enter the engine through dem_insert_step_begin / _end)
+  struct Template { int atom_type = 1, groupbit = 1; double radius = 0, density = 0, volexpect = 0, massexpect = 0; };
+  struct Distribution { Park random; int groupbit = 1; std::vector<std::string> templates; std::vector<double> weight; std::vector<int> order; double volexpect = 0, massexpect = 0, maxrbound = 0; };
+  struct Insert {
+    std::string id, dist, region; int groupbit = 1, seed = 0; Park random;
+    int vmode = 0; double v[3] = {0, 0, 0}, vfluct[3] = {0, 0, 0}, omega[3] = {0, 0, 0};
+    long insert_every = -1, next = 0; int maxattempt = 50, check_ol = 1, all_in = 0, exact_number = 1, ntry_mc = 100000;
+    double volumefraction = 0.0, masstotal = 0.0; long ntotal = 0;
+    bool setup_done = false, check_border = true, warn_region = true;
+    double region_volume = 0.0, region_volume_local = 0.0, insertion_ratio = 0.0;
+    long ninserted = 0; double massinserted = 0.0;
+  };
+  std::map<std::string, Template> templates;
+  std::map<std::string, Distribution> distributions;
+  std::vector<Insert> inserts;  // in the order of definition (== the order Modify calls pre_exchange)
+  int nprocs = 1;
   std::set<std::string> opaque_regions;  // regions of other shapes: known by name only
   std::map<std::string, int> groups;  // name -> mask bit
   std::map<std::string, std::string> ignored_fixes;
@@ -492,6 +533,278 @@ int write_dumps_due(Deck *d)
   return OK;
 }
 
+
+// ---- particle insertion (host side): regions, templates, distributions, fix insert/pack --------------------------------
+// The reference draws positions on the host from Park-Miller streams; what reaches the particle hot path is a list of new
+// spheres inside one timestep.  This block restates the drawing so that a deck seeded like a reference deck creates the same
+// spheres: region.cpp:498-700 (random points, Monte-Carlo volume), fix_insert_pack.cpp:337-597 (how many, where),
+// fix_particledistribution_discrete.cpp:383-455 (which template), fix_insert.cpp:672-905 (the insertion step).
+bool is_prime(int n) { if (n < 2) return false; for (long q = 2; q * q <= n; q++) if (n % q == 0) return false; return true; }
+// Random::Random (random.cpp:55-88) + Input::add_and_validate_seed (input.cpp:1920-1953): a seed that is not a prime > 10000
+// would be replaced by one of the reference's built-in seeds -- refused here instead of silently drawing another stream
+int take_seed(Deck *d, const std::string &w, int &seed)
+{
+  int rc = inumeric(d, w, seed); if (rc) return rc;
+  if (atol(w.c_str()) != (long)seed) return fail(d, ERR_ARG, "Seed %s is larger than INT_MAX", w.c_str());
+  if (seed < 10000 || !is_prime(seed)) return fail(d, ERR_UNSUPPORTED, "seed %d: LIGGGHTS requires seeds to be prime numbers > 10000 (the reference would substitute one of its built-in seeds)", seed);
+  return OK;
+}
+bool region_inside(const Deck::Region &R, double x, double y, double z)
+{
+  if (R.kind == 0) return x >= R.lo[0] && x <= R.hi[0] && y >= R.lo[1] && y <= R.hi[1] && z >= R.lo[2] && z <= R.hi[2];  // region_block.cpp:272-277
+  double del1, del2, ax;  // region_cylinder.cpp:213-239
+  if (R.axis == 'x') { del1 = y - R.c1; del2 = z - R.c2; ax = x; } else if (R.axis == 'y') { del1 = x - R.c1; del2 = z - R.c2; ax = y; } else { del1 = x - R.c1; del2 = y - R.c2; ax = z; }
+  const double dist = std::sqrt(del1 * del1 + del2 * del2);
+  return dist <= R.rad && ax >= R.clo && ax <= R.chi;
+}
+// Region::match_cut for an interior region: the point lies within `cut` of the surface (surface_interior() > 0,
+// region_block.cpp:286-345, region_cylinder.cpp:249-359)
+bool region_near_surface(const Deck::Region &R, const double *x, double cut)
+{
+  if (R.kind == 0) {
+    if (x[0] < R.lo[0] || x[0] > R.hi[0] || x[1] < R.lo[1] || x[1] > R.hi[1] || x[2] < R.lo[2] || x[2] > R.hi[2]) return false;
+    for (int k = 0; k < 3; k++) if (x[k] - R.lo[k] < cut || R.hi[k] - x[k] < cut) return true;
+    return false;
+  }
+  double del1, del2, ax;
+  if (R.axis == 'x') { del1 = x[1] - R.c1; del2 = x[2] - R.c2; ax = x[0]; } else if (R.axis == 'y') { del1 = x[0] - R.c1; del2 = x[2] - R.c2; ax = x[1]; } else { del1 = x[0] - R.c1; del2 = x[1] - R.c2; ax = x[2]; }
+  const double r = std::sqrt(del1 * del1 + del2 * del2);
+  if (r > R.rad || ax < R.clo || ax > R.chi) return false;
+  if (R.rad - r < cut && r > 0.0) return true;
+  return ax - R.clo < cut || R.chi - ax < cut;
+}
+bool in_domain(const Deck *d, const double *p) { for (int k = 0; k < 3; k++) if (!(p[k] >= d->lo[k] && p[k] <= d->hi[k])) return false; return true; }  // domain_I.h:51-63
+bool in_subdomain(const Deck *d, const double *p) { for (int k = 0; k < 3; k++) if (!(p[k] >= d->lo[k] - 1.0e-8 && p[k] < d->hi[k] + 1.0e-8)) return false; return true; }  // domain_I.h:65-87, one process
+// Region::volume_mc (region.cpp:633-700), one process
+int region_volume_mc(Deck *d, Deck::Region &R, int n_test, bool cutflag, double cut, double &vol_global, double &vol_local)
+{
+  long n_in_local = 0, n_in_global = 0;
+  for (int i = 0; i < n_test; i++) {
+    double pos[3];
+    for (int k = 0; k < 3; k++) pos[k] = R.ext_lo[k] + R.random.uniform() * (R.ext_hi[k] - R.ext_lo[k]);
+    if (!in_domain(d, pos)) continue;
+    if (region_inside(R, pos[0], pos[1], pos[2])) {
+      n_in_global++;
+      if (in_subdomain(d, pos) && !(cutflag && region_near_surface(R, pos, cut))) n_in_local++;
+    }
+  }
+  const char *msg = "Unable to calculate region volume. Possible sources of error: (a) region volume is too small or out of domain, (b) particles for insertion are too large when using all_in yes, (c) region is 2d, but should be 3d";
+  if (n_in_global == 0) return fail(d, ERR_ARG, "%s", msg);
+  const double vol_bbox = (R.ext_hi[0] - R.ext_lo[0]) * (R.ext_hi[1] - R.ext_lo[1]) * (R.ext_hi[2] - R.ext_lo[2]);
+  vol_global = static_cast<double>(n_in_global) / static_cast<double>(n_test * 1) * vol_bbox;
+  vol_local = static_cast<double>(n_in_local) / static_cast<double>(n_test) * vol_bbox;
+  const double vol_local_all = vol_local;
+  if (vol_local_all < 1.e-10) return fail(d, ERR_ARG, "%s", msg);  // Region::volume_limit_
+  vol_local *= (vol_global / vol_local_all);
+  return OK;
+}
+// Region::generate_random / generate_random_shrinkby_cut with subdomain_flag (region.cpp:505-572)
+int region_random_point(Deck *d, Deck::Region &R, bool shrink, double cut, double *pos)
+{
+  double lo[3], hi[3], diff[3];
+  for (int k = 0; k < 3; k++) { lo[k] = std::max(R.ext_lo[k], d->lo[k]); hi[k] = std::min(R.ext_hi[k], d->hi[k]); diff[k] = hi[k] - lo[k]; }
+  if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) return fail(d, ERR_ARG, "Impossible to generate random points on wrong sub-domain");
+  if (shrink) for (int k = 0; k < 3; k++) if (R.ext_hi[k] - R.ext_lo[k] < 2. * cut)
+    return fail(d, ERR_ARG, "Impossible to generate random points within region - region too small (smaller than twice the particle cutoff)");
+  do {
+    pos[0] = lo[0] + R.random.uniform() * diff[0];
+    pos[1] = lo[1] + R.random.uniform() * diff[1];
+    pos[2] = lo[2] + R.random.uniform() * diff[2];
+  } while (!region_inside(R, pos[0], pos[1], pos[2]) || (shrink && region_near_surface(R, pos, cut)));
+  return OK;
+}
+// FixInsert::setup -> FixInsertPack::calc_insertion_properties (fix_insert.cpp:407-438, fix_insert_pack.cpp:284-327): once, in
+// the setup of the first run after the fix was defined
+int insert_setup(Deck *d, Deck::Insert &I)
+{
+  if (I.setup_done) return OK;
+  I.setup_done = true;
+  Deck::Region &R = d->regions[I.region];
+  R.random.reset(I.seed + 12);  // SEED_OFFSET, Region::reset_random
+  const Deck::Distribution &D = d->distributions[I.dist];
+  int rc = region_volume_mc(d, R, I.ntry_mc, I.all_in != 0, D.maxrbound, I.region_volume, I.region_volume_local); if (rc) return rc;
+  if (I.region_volume <= 0. || I.region_volume_local < 0. || (I.region_volume_local - I.region_volume) / I.region_volume > 1e-3)
+    return fail(d, ERR_ARG, "Fix insert: Region volume calculation with MC failed");
+  char buf[160]; snprintf(buf, sizeof buf, "INFO: Particle insertion %s: inserting every %ld steps\n", I.id.c_str(), I.insert_every);
+  d->out += buf; if (d->screen) fputs(buf, stdout);
+  return OK;
+}
+struct NewSpheres { std::vector<int> type, mask; std::vector<double> x, v, omega, radius, density; long n = 0; };
+// one insertion of one fix insert/pack (FixInsert::pre_exchange, fix_insert.cpp:672-905) against the spheres in ex/er/em
+// (positions after the first half step, radii, masses; spheres created earlier in this step included)
+int insert_pass(Deck *d, Deck::Insert &I, std::vector<double> &ex, std::vector<double> &er, std::vector<double> &em, NewSpheres &out)
+{
+  Deck::Region &R = d->regions[I.region];
+  Deck::Distribution &D = d->distributions[I.dist];
+  const long step = d->ntimestep + 1;
+  // FixInsertPack::calc_ninsert_this (fix_insert_pack.cpp:337-434)
+  if (I.warn_region) {
+    double mn[3], mx[3];
+    for (int k = 0; k < 3; k++) { mn[k] = R.ext_lo[k] + 1e-8; mx[k] = R.ext_hi[k] - 1e-8; }
+    if (!in_domain(d, mn) || !in_domain(d, mx)) for (int k = 0; k < 3; k++) if (d->bstr[k].find('f') != std::string::npos)
+      return fail(d, ERR_ARG, "Insertion region extends outside simulation box and a fixed boundary is used.Please use non-fixed boundaries in this case only");
+  }
+  long np_region = 0; double vol_region = 0., mass_region = 0.;
+  const double _4Pi3 = 4. * M_PI / 3.;
+  for (size_t i = 0; i < er.size(); i++) if (region_inside(R, ex[3 * i], ex[3 * i + 1], ex[3 * i + 2])) { np_region++; vol_region += _4Pi3 * er[i] * er[i] * er[i]; mass_region += em[i]; }
+  int ninsert_this = 0;
+  if (I.volumefraction > 0.) {
+    ninsert_this = static_cast<int>((I.volumefraction * I.region_volume - vol_region) / D.volexpect + I.random.uniform());
+    I.insertion_ratio = vol_region / (I.volumefraction * I.region_volume);
+  } else if (I.ntotal > 0) {
+    ninsert_this = (int)(I.ntotal - np_region);
+    I.insertion_ratio = static_cast<double>(np_region) / static_cast<double>(I.ntotal);
+  } else {
+    ninsert_this = static_cast<int>((I.masstotal - mass_region) / D.massexpect + I.random.uniform());
+    I.insertion_ratio = mass_region / I.masstotal;
+  }
+  if (ninsert_this < -200000) return fail(d, ERR_ARG, "overflow in particle number calculation: inserting too many particles in one step");
+  if (ninsert_this < 0) ninsert_this = 0;
+  if (I.insertion_ratio < 0.) I.insertion_ratio = 0.;
+  if (I.insertion_ratio > 1.) I.insertion_ratio = 1.;
+  // FixInsertPack::insertion_fraction (fix_insert_pack.cpp:438-445): a shrink-wrapped box (boundary m / s) counts as changing,
+  // the Monte-Carlo volume is drawn again before every insertion
+  bool box_change = false;
+  for (int k = 0; k < 3; k++) if (d->bstr[k].find('m') != std::string::npos || d->bstr[k].find('s') != std::string::npos) box_change = true;
+  if (box_change) { const int rc = region_volume_mc(d, R, I.ntry_mc, I.all_in != 0, D.maxrbound, I.region_volume, I.region_volume_local); if (rc) return rc; }
+  // distribute_ninsert_this (fix_insert.cpp:912-987) with one process: everything is mine unless my share of the region is < 2 %
+  if (I.exact_number) { if (I.region_volume_local / I.region_volume < 0.02) return fail(d, ERR_ARG, "Internal error distributing particles to processes"); }
+  else ninsert_this = static_cast<int>(I.region_volume_local / I.region_volume * static_cast<double>(ninsert_this) + I.random.uniform());
+  // FixParticledistributionDiscrete::randomize_list (fix_particledistribution_discrete.cpp:383-455)
+  const int nt = (int)D.templates.size();
+  std::vector<int> parttogen(nt);
+  if (!I.exact_number) for (int i = 0; i < nt; i++) parttogen[i] = static_cast<int>(static_cast<double>(ninsert_this) * D.weight[i] + D.random.uniform());
+  else {
+    int truncated = 0; std::vector<double> remainder(nt);
+    for (int i = 0; i < nt; i++) {
+      parttogen[i] = static_cast<int>(static_cast<double>(ninsert_this) * D.weight[i]);
+      truncated += parttogen[i];
+      remainder[i] = static_cast<double>(ninsert_this) * D.weight[i] - static_cast<double>(parttogen[i]);
+    }
+    const int gap = ninsert_this - truncated;
+    for (int i = 0; i < gap; i++) {
+      const double r = D.random.uniform() * static_cast<double>(gap);
+      int j = 0; double rsum = remainder[0];
+      while (rsum < r && j < nt - 1) { j++; rsum += remainder[j]; }
+      parttogen[j]++;
+    }
+  }
+  std::vector<int> list;  // template index of every sphere to insert, large templates first
+  for (int i = 0; i < nt; i++) for (int j = 0; j < parttogen[D.order[i]]; j++) list.push_back(D.order[i]);
+  const int nlist = (int)list.size();
+  auto schedule = [&](bool some) {
+    if (some) { if (I.insert_every) I.next += I.insert_every; else I.next = 0; }
+    else { if (I.insert_every) I.next += I.insert_every; else I.next = -1; }
+  };
+  if (nlist == 0) { schedule(false); return OK; }
+  // FixInsertPack::x_v_omega (fix_insert_pack.cpp:474-597)
+  const long maxtry = I.insertion_ratio >= 1. ? (long)nlist * I.maxattempt : (long)static_cast<int>(static_cast<double>(nlist * I.maxattempt) / (1. - I.insertion_ratio));
+  long ntry = 0; int ninserted = 0; double mass_inserted = 0.;
+  const size_t ex0 = er.size();
+  auto velocity = [&](double *v) {  // FixInsert::generate_random_velocity (fix_insert.cpp:1023-1036)
+    v[0] = I.v[0]; v[1] = I.v[1]; v[2] = I.v[2];
+    if (I.vmode == 1) for (int k = 0; k < 3; k++) v[k] = I.v[k] + I.vfluct[k] * 2.0 * (I.random.uniform() - 0.50);
+    else if (I.vmode == 2) for (int k = 0; k < 3; k++) v[k] = I.v[k] + I.vfluct[k] * I.random.gaussian();
+  };
+  // overlap search: uniform bins over the region's box, cell >= the largest diameter in play (RegionNeighborList::hasOverlap,
+  // region_neighbor_list_I.h:72-98, tests rsq <= radsum^2 against every sphere that can reach)
+  double rmaxall = D.maxrbound; for (double r : er) rmaxall = std::max(rmaxall, r);
+  const double cell = 2.0 * rmaxall * 1.0001;
+  double blo[3], cs[3]; int nb[3];
+  for (int k = 0; k < 3; k++) {
+    const double span = R.ext_hi[k] - R.ext_lo[k] + 4.0 * cell;
+    cs[k] = std::max(cell, span / 200.0); blo[k] = R.ext_lo[k] - 2.0 * cell; nb[k] = (int)(span / cs[k]) + 1;
+  }
+  std::vector<std::vector<int>> bins((size_t)nb[0] * nb[1] * nb[2]);
+  auto binof = [&](const double *p, int *b) -> bool { for (int k = 0; k < 3; k++) { const double q = (p[k] - blo[k]) / cs[k]; if (!(q >= 0.0) || q >= nb[k]) return false; b[k] = (int)q; } return true; };
+  if (I.check_ol) for (size_t i = 0; i < er.size(); i++) { int b[3]; if (binof(&ex[3 * i], b)) bins[((size_t)b[2] * nb[1] + b[1]) * nb[0] + b[0]].push_back((int)i); }
+  auto overlaps = [&](const double *p, double r) {
+    int b[3]; if (!binof(p, b)) return false;
+    for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+      const int bx = b[0] + dx, by = b[1] + dy, bz = b[2] + dz;
+      if (bx < 0 || by < 0 || bz < 0 || bx >= nb[0] || by >= nb[1] || bz >= nb[2]) continue;
+      for (int j : bins[((size_t)bz * nb[1] + by) * nb[0] + bx]) {
+        const double del[3] = {p[0] - ex[3 * j], p[1] - ex[3 * j + 1], p[2] - ex[3 * j + 2]};
+        const double rsq = del[0] * del[0] + del[1] * del[1] + del[2] * del[2], radsum = r + er[j];
+        if (rsq <= radsum * radsum) return true;
+      }
+    }
+    return false;
+  };
+  auto accept = [&](int t, const double *pos, const double *v) {
+    const Deck::Template &T = d->templates[D.templates[t]];
+    const double volume = T.radius * T.radius * T.radius * 4. * M_PI / 3., mass = T.density * volume;  // fix_template_sphere.cpp:349-350
+    out.type.push_back(T.atom_type); out.mask.push_back(1 | T.groupbit | D.groupbit | I.groupbit);
+    for (int k = 0; k < 3; k++) { out.x.push_back(pos[k]); out.v.push_back(v[k]); out.omega.push_back(I.omega[k]); ex.push_back(pos[k]); }
+    out.radius.push_back(T.radius); out.density.push_back(T.density); out.n++;
+    er.push_back(T.radius); em.push_back(mass);
+    int b[3]; if (I.check_ol && binof(pos, b)) bins[((size_t)b[2] * nb[1] + b[1]) * nb[0] + b[0]].push_back((int)er.size() - 1);
+    mass_inserted += mass; ninserted++;
+  };
+  double pos[3], v[3];
+  if (!I.check_ol) {
+    for (int it = 0; it < nlist; it++) {
+      const double rbound = d->templates[D.templates[list[ninserted]]].radius;
+      int rc = region_random_point(d, R, I.all_in != 0, rbound, pos); if (rc) return rc;
+      velocity(v);
+      if (pos[0] == 0. && pos[1] == 0. && pos[2] == 0.) return fail(d, ERR_ARG, "FixInsertPack::x_v_omega() illegal position");
+      accept(list[ninserted], pos, v);
+    }
+  } else {
+    while (ntry < maxtry && ninserted < nlist) {
+      const int t = list[ninserted];
+      const double rbound = d->templates[D.templates[t]].radius;
+      bool placed = false;
+      while (!placed && ntry < maxtry) {
+        bool clear;
+        do {
+          int rc = region_random_point(d, R, I.all_in != 0, rbound, pos); if (rc) return rc;
+          ntry++;
+          clear = true;  // Domain::check_dist_subbox_borders (domain_I.h:127-149): keep rbound away from the sub-box faces
+          for (int k = 0; k < 3; k++) if (std::fabs(d->lo[k] - pos[k]) < rbound || std::fabs(d->hi[k] - pos[k]) < rbound) clear = false;
+        } while (I.check_border && ntry < maxtry && !clear);
+        if (ntry == maxtry) break;
+        velocity(v);
+        if (!overlaps(pos, rbound)) { accept(t, pos, v); placed = true; }
+      }
+    }
+  }
+  (void)ex0;
+  I.ninserted += ninserted; I.massinserted += mass_inserted;
+  char buf[320];
+  snprintf(buf, sizeof buf, "INFO: Particle insertion %s: inserted %d particle templates (mass %e) at step %ld\n - a total of %ld particle templates (mass %e) inserted so far.\n",
+           I.id.c_str(), ninserted, mass_inserted, step, I.ninserted, I.massinserted);
+  d->out += buf; if (d->screen) fputs(buf, stdout);
+  if (ninserted < nlist) d->warnings += "Particle insertion: Less insertions than requested\n";
+  schedule(true);
+  return OK;
+}
+// the timestep d->ntimestep + 1 with every fix insert/pack that is due on it
+int insertion_step(Deck *d)
+{
+  const long step = d->ntimestep + 1;
+  std::vector<double> ex, er, em;
+  TRY(API(insert_step_begin)(d->e));
+  const long n0 = d->uploaded ? API(nlocal)(d->e) : 0;
+  int maxtag = 0;
+  if (n0) {
+    if (d->nprocs > 1) return fail(d, ERR_UNSUPPORTED, "fix insert/pack into a box that already holds particles needs all of them on one process: several bricks are outside the hot-path scope");
+    ex.resize(3 * n0); er.resize(n0); em.resize(n0);
+    std::vector<int> tg(n0);
+    TRY(API(download)(d->e, "x", ex.data(), n0)); TRY(API(download)(d->e, "radius", er.data(), n0)); TRY(API(download)(d->e, "rmass", em.data(), n0));
+    TRY(API(download)(d->e, "tag", tg.data(), n0));
+    for (int t : tg) maxtag = std::max(maxtag, t);  // Atom::tag_extend continues behind the largest id present
+  }
+  NewSpheres S;
+  for (auto &I : d->inserts) if (I.next == step) { const int rc = insert_pass(d, I, ex, er, em, S); if (rc) return rc; }
+  std::vector<int> tag(S.n);
+  for (long i = 0; i < S.n; i++) tag[i] = maxtag + 1 + (int)i;
+  if (S.n && !d->newton_off && d->have_pair) return fail(d, ERR_ARG, "Pair granular with shear history requires newton pair off");
+  TRY(API(insert_step_end)(d->e, S.n, tag.data(), S.type.data(), S.mask.data(), S.x.data(), S.v.data(), S.omega.data(), S.radius.data(), S.density.data()));
+  if (S.n) { d->uploaded = true; d->maxtag = std::max(d->maxtag, maxtag + (int)S.n); }
+  return OK;
+}
+
 int first_run_prepare(Deck *d)
 {
   if (d->uploaded) {
@@ -503,7 +816,10 @@ int first_run_prepare(Deck *d)
     return OK;
   }
   if (!d->have_box) return fail(d, ERR_STATE, "Run command before simulation box is defined");
-  if (d->tag.empty()) return fail(d, ERR_UNSUPPORTED, "no particles: initial states come from read_data (particle insertion is outside the hot-path scope)");
+  if (d->tag.empty()) {
+    if (!d->inserts.empty()) return OK;  // an empty box that fix insert/pack fills
+    return fail(d, ERR_UNSUPPORTED, "no particles: initial states come from read_data, create_atoms single or fix insert/pack");
+  }
   if (!d->newton_off && d->have_pair) return fail(d, ERR_ARG, "Pair granular with shear history requires newton pair off");
   TRY(API(upload_particles)(d->e, (long)d->tag.size(), d->tag.data(), d->type.data(), d->mask.data(), d->x.data(), d->v.data(), d->omega.data(),
                             d->radius.data(), d->density.data()));
@@ -616,6 +932,127 @@ int cmd_fix(Deck *d, const std::vector<std::string> &w)
   if (style == "balance") {  // dynamic load balancing (fix_balance.cpp) moves brick boundaries, never the physics: bricks stay static here
     d->ignored_fixes[id] = style; d->warnings += "fix balance ignored (bricks are static)\n"; return OK;
   }
+  if (style == "particletemplate/sphere") {  // fix_template_sphere.cpp:72-260 (radius / density: `constant` is the only style the reference has)
+    if (w.size() < 5) return fail(d, ERR_ARG, "Illegal fix particletemplate/sphere command, not enough arguments");
+    Deck::Template T; T.groupbit = bit;
+    int seed; rc = take_seed(d, w[4], seed); if (rc) return rc;
+    bool have_r = false, have_rho = false;
+    for (size_t k = 5; k < w.size();) {
+      if (w[k] == "atom_type" && k + 1 < w.size()) { rc = inumeric(d, w[k + 1], T.atom_type); if (rc) return rc; if (T.atom_type < 1) return fail(d, ERR_ARG, "invalid atom type (must be >=1)"); k += 2; }
+      else if ((w[k] == "radius" || w[k] == "density") && k + 2 < w.size()) {
+        if (w[k + 1] != "constant") return fail(d, ERR_ARG, "invalid %s random style", w[k].c_str());
+        double val; rc = numeric(d, w[k + 2], val); if (rc) return rc;
+        if (val <= 0.) return fail(d, ERR_ARG, "Illegal fix particletemplate/sphere command, %s must be >= 0", w[k].c_str());
+        if (w[k] == "radius") { T.radius = val; have_r = true; } else { T.density = val; have_rho = true; }
+        k += 3;
+      } else if (w[k] == "volume_limit" && k + 1 < w.size()) k += 2;
+      else return fail(d, ERR_UNSUPPORTED, "fix particletemplate/sphere keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    if (!have_rho) return fail(d, ERR_ARG, "have to define 'density'");
+    if (!have_r) return fail(d, ERR_ARG, "have to define 'radius'");
+    if (T.atom_type > d->ntypes) return fail(d, ERR_ARG, "Invalid atom type in fix particletemplate/sphere");
+    T.volexpect = T.radius * T.radius * T.radius * 4. * M_PI / 3.;  // cubic_expectancy * 4 pi / 3 (fix_template_sphere.cpp:256-257)
+    T.massexpect = T.density * T.volexpect;
+    d->templates[id] = T; return OK;
+  }
+  if (style.compare(0, 29, "particledistribution/discrete") == 0) {  // fix_particledistribution_discrete.cpp:75-245
+    if (w.size() < 8) return fail(d, ERR_ARG, "Illegal fix particledistribution/discrete command, not enough arguments");
+    Deck::Distribution D; D.groupbit = bit;
+    const bool mass_based = style.find("numberbased") == std::string::npos;
+    int seed; rc = take_seed(d, w[4], seed); if (rc) return rc;
+    D.random.reset(seed);
+    int nt; rc = inumeric(d, w[5], nt); if (rc) return rc;
+    if (nt < 1) return fail(d, ERR_ARG, "illegal number of templates");
+    if ((int)w.size() != 6 + 2 * nt) return fail(d, ERR_ARG, "# of templates does not match # of arguments");
+    for (int i = 0; i < nt; i++) {
+      const std::string &tid = w[6 + 2 * i];
+      if (!d->templates.count(tid)) return fail(d, ERR_ARG, "invalid ID for fix particletemplate provided");
+      for (auto &o : D.templates) if (o == tid) return fail(d, ERR_ARG, "cannot use the same template twice");
+      double wt; rc = numeric(d, w[7 + 2 * i], wt); if (rc) return rc;
+      if (wt < 0) return fail(d, ERR_ARG, "invalid weight");
+      D.templates.push_back(tid); D.weight.push_back(wt);
+    }
+    double sum = 0; for (double x : D.weight) sum += x;
+    if (std::fabs(sum - 1.) > 0.00001) d->warnings += "particledistribution/discrete: sum of distribution weights != 1, normalizing distribution\n";
+    for (double &x : D.weight) x /= sum;
+    if (mass_based) {  // mass-% to number-%
+      for (int i = 0; i < nt; i++) D.weight[i] = D.weight[i] / d->templates[D.templates[i]].massexpect;
+      sum = 0; for (double x : D.weight) sum += x;
+      for (double &x : D.weight) x /= sum;
+    }
+    for (int i = 0; i < nt; i++) {
+      const Deck::Template &T = d->templates[D.templates[i]];
+      D.volexpect += T.volexpect * D.weight[i]; D.massexpect += T.massexpect * D.weight[i];
+      D.maxrbound = std::max(D.maxrbound, T.radius);
+    }
+    D.order.resize(nt); for (int i = 0; i < nt; i++) D.order[i] = i;  // bubble sort by insertion volume, descending (:213-232)
+    bool swapped; int n = nt;
+    do {
+      swapped = false;
+      for (int i = 0; i < nt - 1; i++)
+        if (d->templates[D.templates[D.order[i]]].volexpect < d->templates[D.templates[D.order[i + 1]]].volexpect) { std::swap(D.order[i], D.order[i + 1]); swapped = true; }
+      n--;
+    } while (swapped && n > 0);
+    d->distributions[id] = D; return OK;
+  }
+  if (style == "insert/pack") {  // fix_insert.cpp:79-395, fix_insert_pack.cpp:74-200
+    if (w.size() < 7) return fail(d, ERR_ARG, "not enough arguments");
+    if (w[4] != "seed") return fail(d, ERR_ARG, "expecting keyword 'seed'");
+    Deck::Insert I; I.id = id; I.groupbit = bit;
+    rc = take_seed(d, w[5], I.seed); if (rc) return rc;
+    I.random.reset(I.seed);
+    I.next = d->ntimestep + 1;  // first insertion on the next timestep
+    auto yesno = [&](const std::string &v, int &out) -> int { if (v == "yes") out = 1; else if (v == "no") out = 0; else return fail(d, ERR_ARG, "expecting 'yes' or 'no'"); return OK; };
+    for (size_t k = 6; k < w.size();) {
+      const std::string &kw = w[k];
+      auto need = [&](size_t n) { return k + n < w.size(); };
+      if (kw == "distributiontemplate" && need(1)) {
+        if (!d->distributions.count(w[k + 1])) return fail(d, ERR_ARG, "Fix insert requires you to define a valid ID for a fix of type particledistribution/discrete");
+        I.dist = w[k + 1]; k += 2;
+      } else if (kw == "maxattempt" && need(1)) { rc = inumeric(d, w[k + 1], I.maxattempt); if (rc) return rc; k += 2; }
+      else if ((kw == "insert_every" || kw == "every") && need(1)) {
+        if (w[k + 1] == "once") I.insert_every = 0;
+        else { int ie; rc = inumeric(d, w[k + 1], ie); if (rc) return rc; if (ie < 0) return fail(d, ERR_ARG, "insert_every must be >= 0"); I.insert_every = ie; }
+        k += 2;
+      } else if (kw == "start" && need(1)) {
+        int st; rc = inumeric(d, w[k + 1], st); if (rc) return rc;
+        if (st < d->ntimestep + 1) return fail(d, ERR_ARG, "'start' step can not be before current step");
+        I.next = st; k += 2;
+      } else if (kw == "overlapcheck" && need(1)) { rc = yesno(w[k + 1], I.check_ol); if (rc) return rc; k += 2; }
+      else if (kw == "all_in" && need(1)) { rc = yesno(w[k + 1], I.all_in); if (rc) return rc; k += 2; }
+      else if (kw == "random_distribute" && need(1)) { if (w[k + 1] == "uncorrelated") I.exact_number = 0; else if (w[k + 1] == "exact") I.exact_number = 1; else return fail(d, ERR_ARG, "Illegal fix insert command"); k += 2; }
+      else if (kw == "verbose" && need(1)) k += 2;
+      else if (kw == "vel" && need(4)) {
+        const std::string &m = w[k + 1];
+        if (m == "constant") { for (int q = 0; q < 3; q++) { rc = numeric(d, w[k + 2 + q], I.v[q]); if (rc) return rc; } k += 5; }
+        else if ((m == "uniform" || m == "gaussian") && need(7)) {
+          I.vmode = m == "uniform" ? 1 : 2;
+          for (int q = 0; q < 3; q++) { rc = numeric(d, w[k + 2 + q], I.v[q]); if (rc) return rc; rc = numeric(d, w[k + 5 + q], I.vfluct[q]); if (rc) return rc; }
+          k += 8;
+        } else return fail(d, ERR_ARG, "expecting keyword 'constant' or 'uniform' or 'gaussian' after keyword 'vel'");
+      } else if (kw == "omega" && need(4)) {
+        if (w[k + 1] != "constant") return fail(d, ERR_ARG, "expecting keyword 'constant' after keyword 'omega'");
+        for (int q = 0; q < 3; q++) { rc = numeric(d, w[k + 2 + q], I.omega[q]); if (rc) return rc; }
+        k += 5;
+      } else if (kw == "region" && need(1)) {
+        if (d->opaque_regions.count(w[k + 1])) return fail(d, ERR_UNSUPPORTED, "fix insert/pack into a region that is neither a block nor a cylinder is outside the hot-path scope");
+        if (!d->regions.count(w[k + 1])) return fail(d, ERR_ARG, "region ID does not exist");
+        I.region = w[k + 1]; k += 2;
+      } else if (kw == "volumefraction_region" && need(1)) { rc = numeric(d, w[k + 1], I.volumefraction); if (rc) return rc; if (I.volumefraction < 0. || I.volumefraction > 1.) return fail(d, ERR_ARG, "Invalid volumefraction"); k += 2; }
+      else if (kw == "particles_in_region" && need(1)) { int nn; rc = inumeric(d, w[k + 1], nn); if (rc) return rc; if (nn <= 0) return fail(d, ERR_ARG, "'ntotal_region' > 0 required"); I.ntotal = nn; k += 2; }
+      else if (kw == "mass_in_region" && need(1)) { rc = numeric(d, w[k + 1], I.masstotal); if (rc) return rc; if (I.masstotal <= 0.) return fail(d, ERR_ARG, "'masstotal_region' > 0 required"); k += 2; }
+      else if (kw == "ntry_mc" && need(1)) { rc = inumeric(d, w[k + 1], I.ntry_mc); if (rc) return rc; if (I.ntry_mc < 1000) return fail(d, ERR_ARG, "ntry_mc must be > 1000"); k += 2; }
+      else if (kw == "warn_region" && need(1)) { int v; rc = yesno(w[k + 1], v); if (rc) return rc; I.warn_region = v != 0; k += 2; }
+      else if (kw == "check_dist_from_subdomain_border" && need(1)) { int v; rc = yesno(w[k + 1], v); if (rc) return rc; I.check_border = v != 0; k += 2; }
+      else return fail(d, ERR_UNSUPPORTED, "fix insert/pack keyword '%s' is outside the hot-path scope", kw.c_str());
+    }
+    if (I.dist.empty()) return fail(d, ERR_ARG, "have to define a 'distributiontemplate'");
+    if (I.region.empty()) return fail(d, ERR_ARG, "must define an insertion region");
+    if (I.insert_every < 0) return fail(d, ERR_ARG, "must define 'insert_every'");
+    if ((I.volumefraction > 0.) + (I.ntotal > 0) + (I.masstotal > 0.) != 1)
+      return fail(d, ERR_ARG, "must define exactly one keyword out of 'volumefraction_region', 'particles_in_region', and 'mass_in_region'");
+    d->inserts.push_back(I); return OK;
+  }
   return fail(d, ERR_UNSUPPORTED, "fix style '%s' is outside the hot-path scope", style.c_str());
 }
 
@@ -690,16 +1127,36 @@ int one(Deck *d, const std::string &raw)
     if (w.size() < 4) return fail(d, ERR_ARG, "Illegal processors command");
     if (w[1] == "*" || w[2] == "*" || w[3] == "*") return OK;  // left to the engine's own choice
     int p[3]; for (int k = 0; k < 3; k++) { rc = inumeric(d, w[1 + k], p[k]); if (rc) return rc; }
-    TRY(API(set_processors)(d->e, p[0], p[1], p[2])); return OK;
+    TRY(API(set_processors)(d->e, p[0], p[1], p[2])); d->nprocs = p[0] * p[1] * p[2]; return OK;
   }
   if (c == "region") {
-    if (w.size() >= 3 && w[2] != "block") {  // other shapes only feed insertion / groups, which are rejected where they are used
-      d->opaque_regions.insert(w[1]); d->warnings += "region " + w[1] + " (" + w[2] + ") kept as a name only\n"; return OK;
-    }
-    if (w.size() < 9) return fail(d, ERR_ARG, "Illegal region command");
     Deck::Region R;
-    for (int k = 0; k < 3; k++) { rc = numeric(d, w[3 + 2 * k], R.lo[k]); if (rc) return rc; rc = numeric(d, w[4 + 2 * k], R.hi[k]); if (rc) return rc; }
-    for (size_t k = 9; k + 1 < w.size(); k++) if (w[k] == "units" && w[k + 1] != "box") return fail(d, ERR_UNSUPPORTED, "region units lattice is outside the hot-path scope");
+    R.random.reset(3012211);  // region.cpp:456-457
+    size_t opt = 9;
+    if (w.size() >= 3 && w[2] == "cylinder") {  // region_cylinder.cpp:64-190
+      if (w.size() < 9) return fail(d, ERR_ARG, "Illegal region cylinder command");
+      if (w[3] != "x" && w[3] != "y" && w[3] != "z") return fail(d, ERR_ARG, "Illegal region cylinder command");
+      R.kind = 1; R.axis = w[3][0];
+      rc = numeric(d, w[4], R.c1); if (rc) return rc; rc = numeric(d, w[5], R.c2); if (rc) return rc; rc = numeric(d, w[6], R.rad); if (rc) return rc;
+      rc = numeric(d, w[7], R.clo); if (rc) return rc; rc = numeric(d, w[8], R.chi); if (rc) return rc;
+      if (R.rad <= 0.0) return fail(d, ERR_ARG, "Illegal region cylinder command");
+      const int a = R.axis == 'x' ? 0 : R.axis == 'y' ? 1 : 2, b1 = a == 0 ? 1 : 0, b2 = a == 2 ? 1 : 2;
+      R.ext_lo[a] = R.clo; R.ext_hi[a] = R.chi; R.ext_lo[b1] = R.c1 - R.rad; R.ext_hi[b1] = R.c1 + R.rad; R.ext_lo[b2] = R.c2 - R.rad; R.ext_hi[b2] = R.c2 + R.rad;
+      for (int k = 0; k < 3; k++) { R.lo[k] = R.ext_lo[k]; R.hi[k] = R.ext_hi[k]; }
+    } else if (w.size() >= 3 && w[2] != "block") {  // other shapes only feed groups / insertion, which are rejected where they are used
+      d->opaque_regions.insert(w[1]); d->warnings += "region " + w[1] + " (" + w[2] + ") kept as a name only\n"; return OK;
+    } else {
+      if (w.size() < 9) return fail(d, ERR_ARG, "Illegal region command");
+      for (int k = 0; k < 3; k++) { rc = numeric(d, w[3 + 2 * k], R.lo[k]); if (rc) return rc; rc = numeric(d, w[4 + 2 * k], R.hi[k]); if (rc) return rc; R.ext_lo[k] = R.lo[k]; R.ext_hi[k] = R.hi[k]; }
+      if (R.lo[0] > R.hi[0] || R.lo[1] > R.hi[1] || R.lo[2] > R.hi[2]) return fail(d, ERR_ARG, "Illegal region block command");
+    }
+    for (size_t k = opt; k < w.size(); k += 2) {  // Region::options (region.cpp:380-460)
+      if (k + 1 >= w.size()) return fail(d, ERR_ARG, "Illegal region command");
+      if (w[k] == "units") { if (w[k + 1] != "box") return fail(d, ERR_UNSUPPORTED, "region units lattice is outside the hot-path scope"); }
+      else if (w[k] == "seed") { int sd; rc = take_seed(d, w[k + 1], sd); if (rc) return rc; R.random.reset(sd); }
+      else if (w[k] == "side" && w[k + 1] == "in") {}
+      else return fail(d, ERR_UNSUPPORTED, "region keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
     d->regions[w[1]] = R; return OK;
   }
   if (c == "create_box") {
@@ -707,6 +1164,7 @@ int one(Deck *d, const std::string &raw)
     if (d->have_box) return fail(d, ERR_ARG, "Cannot create_box after simulation box is defined");
     if (d->opaque_regions.count(w[2])) return fail(d, ERR_UNSUPPORTED, "create_box from a region that is not a block is outside the hot-path scope");
     if (!d->regions.count(w[2])) return fail(d, ERR_ARG, "Create_box region ID does not exist");
+    if (d->regions[w[2]].kind != 0) return fail(d, ERR_UNSUPPORTED, "create_box from a region that is not a block is outside the hot-path scope");
     rc = inumeric(d, w[1], d->ntypes); if (rc) return rc;
     for (int k = 0; k < 3; k++) { d->lo[k] = d->regions[w[2]].lo[k]; d->hi[k] = d->regions[w[2]].hi[k]; }
     d->have_box = true; return send_box(d);
@@ -741,6 +1199,7 @@ int one(Deck *d, const std::string &raw)
   if (c == "unfix") {
     if (w.size() != 2) return fail(d, ERR_ARG, "Illegal unfix command");
     if (d->ignored_fixes.erase(w[1])) return OK;
+    for (size_t k = 0; k < d->inserts.size(); k++) if (d->inserts[k].id == w[1]) { d->inserts.erase(d->inserts.begin() + k); return OK; }
     return fail(d, ERR_UNSUPPORTED, "unfix of a hot-path fix is outside the hot-path scope");
   }
   if (c == "group") return cmd_group(d, w);
@@ -831,7 +1290,8 @@ int one(Deck *d, const std::string &raw)
     }
     if (n < 0) return fail(d, ERR_ARG, "Invalid run command N value");
     rc = first_run_prepare(d); if (rc) return rc;
-    TRY(API(setup)(d->e));
+    if (d->uploaded) TRY(API(setup)(d->e));  // (else the box is still empty: nothing to set up)
+    for (auto &I : d->inserts) { rc = insert_setup(d, I); if (rc) return rc; }  // Modify::setup -> FixInsert::setup
     rc = write_dumps_due(d); if (rc) return rc;
     const long run_first = d->ntimestep;
     d->loop0 = std::chrono::steady_clock::now();
@@ -841,7 +1301,13 @@ int one(Deck *d, const std::string &raw)
       long chunk = n;
       for (auto &kv : d->dumps) if (kv.second.every > 0) chunk = std::min(chunk, (d->ntimestep / kv.second.every + 1) * kv.second.every - d->ntimestep);
       if (d->thermo_every > 0) chunk = std::min(chunk, (d->ntimestep / d->thermo_every + 1) * d->thermo_every - d->ntimestep);
-      TRY(API(run)(d->e, chunk));
+      long next_ins = -1;  // the next timestep a fix insert/pack acts on (fix->next_reneighbor)
+      for (auto &I : d->inserts) if (I.next > d->ntimestep && (next_ins < 0 || I.next < next_ins)) next_ins = I.next;
+      if (next_ins == d->ntimestep + 1) { rc = insertion_step(d); if (rc) return rc; chunk = 1; }
+      else {
+        if (next_ins > 0) chunk = std::min(chunk, next_ins - 1 - d->ntimestep);
+        if (d->uploaded) TRY(API(run)(d->e, chunk));  // (an empty box has nothing to step)
+      }
       d->ntimestep += chunk; n -= chunk;
       rc = write_dumps_due(d); if (rc) return rc;
       if (n == 0 || (d->thermo_every > 0 && d->ntimestep % d->thermo_every == 0)) { rc = thermo_line(d, false, run_first); if (rc) return rc; }  // (thermo.cpp: every N steps and on the last step)

@@ -236,6 +236,8 @@ struct dem_engine {
   // fused ghost push (fused_halo_setup): image table, block order, device parameter block; fz_on: the next launch_step uses it
   double cdf_user = 0.0;  // neigh_modify contact_distance_factor, 0 = not given
   int need_setup = 0;  // particles were inserted: the next dem_run needs a dem_setup first (lists, forces)
+  int ins_mass = 0;    // the upload kernels form the mass like fix insert/* does (set by dem_insert_step_end only)
+  int ins_open = 0;    // dem_insert_step_begin has run: the timestep is half done
   DevBuf<unsigned long long> bondc;  // compute bond/counter: created, broken, scratch for the total
   DevBuf<int> img_first, img_ws, img_in; DevBuf<int4> img_tab; DevBuf<ImgP> imgp; int fz_ready = 0, fz_on = 0, fz_rq[2] = {-1, -1}, slot_zeroed = 0;
   DevBuf<int> fbox; int *peer_fbox[DEM_MAXRANKS] = {nullptr}; int fbox_ready = 0, fserial = 0, fser_slot[2] = {0, 0}, fpeer[2] = {0, 0};
@@ -1031,7 +1033,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     e->cur = 0;
     if (nmine) {
       k_pack_upload_sel<<<GRID(nmine, 256), 256, 0, st>>>(nmine, list.p, dx, v ? dv : nullptr, omega ? dw : nullptr, dr, dd, dt, mask ? dm : nullptr, dg,
-                                                          e->xr[0].p, e->vm[0].p, e->wt[0].p, e->tag.p, e->density.p);
+                                                          e->xr[0].p, e->vm[0].p, e->wt[0].p, e->tag.p, e->density.p, e->ins_mass);
       e->launches++;
     }
     CK(cudaMemsetAsync(e->xh.p, 0, (size_t)e->cap * sizeof(double4), st));
@@ -1074,7 +1076,7 @@ extern "C" int dem_upload_particles(dem_engine *e, long n, const int *tag, const
     CK(cudaMemsetAsync(e->counters.p + 2, 0xFF, sizeof(unsigned long long), st));  // running minimum of the radius bits
     e->cur = 0;
     k_pack_upload<<<GRID(n, 256), 256, 0, st>>>((int)n, dx, v ? dv : nullptr, omega ? dw : nullptr, dr, dd, dt, mask ? dm : nullptr, dg, e->ntypes,
-                                                 e->xr[0].p, e->vm[0].p, e->wt[0].p, (int *)(e->counters.p + 1), e->counters.p);
+                                                 e->xr[0].p, e->vm[0].p, e->wt[0].p, (int *)(e->counters.p + 1), e->counters.p, e->ins_mass);
     e->launches++;
     CK(cudaMemcpyAsync(e->tag.p, dg, nd * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(e->density.p, dd, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1707,7 +1709,7 @@ extern "C" int dem_insert_particles(dem_engine *e, long n, const int *tag, const
     CK(cudaMemsetAsync(e->counters.p + 2, 0xFF, sizeof(unsigned long long), st));
     const int c = e->cur;
     k_pack_upload<<<GRID(nm, 256), 256, 0, st>>>((int)nm, dx, dv, dw, dr, dd, dt, dm, dg, e->ntypes, e->xr[c].p + n0, e->vm[c].p + n0, e->wt[c].p + n0,
-                                                  (int *)(e->counters.p + 1), e->counters.p);
+                                                  (int *)(e->counters.p + 1), e->counters.p, e->ins_mass);
     e->launches++;
     CK(cudaMemcpyAsync(e->tag.p + n0, dg, nd * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(e->density.p + n0, dd, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -2234,9 +2236,10 @@ static void collect_timing(dem_engine *E)
   E->ev_used = 0;
 }
 
-extern "C" int dem_setup(dem_engine *e)
+// what Verlet::setup needs before the lists are built: tables, cutoffs, cell grid, triangle grid, wall history rows
+static void setup_prepare(dem_engine *e)
 {
-  API_BEGIN
+  dem_engine *E = e;  // (CK / NK / dem_fail name the engine E)
   if (!e->uploaded) dem_fail(e, DEM_ERR_STATE, "setup before dem_upload_particles");
   if (!(e->dt > 0)) dem_fail(e, DEM_ERR_STATE, "timestep not set");
   if (!e->have_pair && e->walls.empty() && e->mwalls.empty()) dem_fail(e, DEM_ERR_STATE, "no pair_style and no wall defined");
@@ -2270,6 +2273,13 @@ extern "C" int dem_setup(dem_engine *e)
     }
   }
   if (e->have_pair && e->pm.cohesion == C_BOND && !e->bondc.p) { e->bondc.ensure(e, 4); CK(cudaMemsetAsync(e->bondc.p, 0, 4 * sizeof(unsigned long long), e->stream)); }
+}
+
+extern "C" int dem_setup(dem_engine *e)
+{
+  API_BEGIN
+  if (e->ins_open) dem_fail(e, DEM_ERR_STATE, "dem_setup inside an insertion step");
+  setup_prepare(e);
   clear_flags(e);
   rebuild(e);
   e->nbuilds = 0;  // neighbor->ncalls counts the builds of the current run only
@@ -2285,6 +2295,7 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   API_BEGIN
   if (!e->setup_done) dem_fail(e, DEM_ERR_STATE, "dem_run before dem_setup");
   if (e->need_setup) dem_fail(e, DEM_ERR_STATE, "particles were inserted: dem_setup before dem_run");
+  if (e->ins_open) dem_fail(e, DEM_ERR_STATE, "dem_run inside an insertion step");
   if (nsteps < 0) dem_fail(e, DEM_ERR_ARG, "nsteps < 0");
   if (nsteps == 0) return DEM_OK;
   CK(cudaSetDevice(e->device));
@@ -2367,6 +2378,74 @@ extern "C" int dem_run(dem_engine *e, long nsteps)
   }
   if (overflow_seen || e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
   e->forces_valid = 1;
+  API_END
+}
+
+// The timestep in which fix insert/* creates particles, in two halves (FixInsert::pre_exchange, fix_insert.cpp:672-905, runs
+// between the first half step and the forced rebuild of that timestep, verlet.cpp:277-310).  Between the two calls the
+// caller sees the positions the reference's overlap check sees (dem_download "x").
+//   begin: first half step of the particles the engine holds (nothing to do while it holds none)
+//   end:   the new particles appear (mass = density * volume as FixTemplateSphere forms it), lists are rebuilt, forces
+//          evaluated, second half step for everybody; n == 0 is a step with a forced rebuild and no newcomer
+extern "C" int dem_insert_step_begin(dem_engine *e)
+{
+  API_BEGIN
+  if (e->ins_open) dem_fail(e, DEM_ERR_STATE, "dem_insert_step_begin called twice");
+  if (e->uploaded) {
+    if (!e->setup_done) dem_fail(e, DEM_ERR_STATE, "dem_insert_step_begin before dem_setup");
+    if (e->need_setup) dem_fail(e, DEM_ERR_STATE, "particles were inserted: dem_setup before dem_insert_step_begin");
+    CK(cudaSetDevice(e->device));
+    clear_flags(e);
+    e->fslot = 0; e->gate = nullptr; e->gate_mask = 0;
+    if (e->nlocal) {
+      StepP P = step_params(e, MODE_STEP);
+      k_initial_integrate<<<GRID(P.nlocal, 256), 256, 0, e->stream>>>(P);
+      e->launches++;
+    }
+    e->cur ^= 1;
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  e->ins_open = 1;
+  API_END
+}
+
+extern "C" int dem_insert_step_end(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
+                                   const double *v, const double *omega, const double *radius, const double *density)
+{
+  if (!e) return DEM_ERR_ARG;
+  if (!e->ins_open) { e->err = "dem_insert_step_end without dem_insert_step_begin"; return DEM_ERR_STATE; }
+  if (!e->uploaded && n <= 0) { e->ins_open = 0; e->ntimestep++; return DEM_OK; }  // a step of an empty box
+  e->ins_mass = 1;
+  const int rc = n > 0 ? dem_insert_particles(e, n, tag, type, mask, x, v, omega, radius, density) : DEM_OK;
+  e->ins_mass = 0;
+  if (rc != DEM_OK) return rc;
+  API_BEGIN
+  CK(cudaSetDevice(e->device));
+  if (!(e->dt > 0)) dem_fail(e, DEM_ERR_STATE, "timestep not set");
+  if (!e->have_pair && e->walls.empty() && e->mwalls.empty()) dem_fail(e, DEM_ERR_STATE, "no pair_style and no wall defined");
+  const bool first = !e->setup_done;
+  setup_prepare(e);
+  cudaStream_t st = e->stream;
+  e->step_ms = 0; e->step_calls = 0; e->ev_used = 0;
+  e->ntimestep++;
+  clear_flags(e);
+  e->fslot = 1; e->gate = nullptr; e->gate_mask = 0;
+  if (e->any_moving && e->mesh_ready && !first) {  // the mesh moves before the lists are rebuilt (dem_run)
+    MeshP M = mesh_params(e);
+    for (size_t m = 0; m < e->meshes.size(); m++)
+      if (e->meshes[m].moving) { mesh_launch_move(M, (int)m, e->dt, 0.25 * e->skin * e->skin, flag_slot(e, 1), nullptr, 0, st); e->launches++; }
+  }
+  if (first) e->nbuilds = 0;  // (the run of an empty box had no setup that would have reset the count of builds)
+  rebuild(e);
+  clear_flags(e);
+  e->fslot = 1;
+  step_and_comm(e, MODE_LAST, 1);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  collect_timing(e);
+  e->ins_open = 0;
+  if (e->hflag[1] || e->hflag[5]) { e->hflag[1] = e->hflag[5] = 0; dem_fail(e, DEM_ERR_OVERFLOW, "a particle gained more new contacts between two rebuilds than free history slots; raise option 'histslots'"); }
+  e->setup_done = 1; e->forces_valid = 1; e->need_setup = 0;
   API_END
 }
 

@@ -1395,11 +1395,18 @@ __global__ void __launch_bounds__(256) k_extract_valid(int n, const int *perm, c
   valid[i] = ((unsigned)(__double_as_longlong(xh[perm ? perm[i] : i].w) & 0xffffffffLL)) >> 16;
 }
 
+// mass of a sphere created by fix insert/*: density * volume with the volume rounded the way FixTemplateSphere::randomize_ptilist
+// forms it (fix_template_sphere.cpp:349-350), which is not the rounding of read_data / set (atom_vec_sphere.cpp:1078)
+__device__ __forceinline__ double insert_mass(double r, double rho)
+{
+  const double vol = r * r * r * 4. * 3.14159265358979323846 / 3.;
+  return rho * vol;
+}
 // host-array upload: builds the three 32-byte records on the device from the caller's plain arrays
 // (atom_vec_sphere.cpp:1055-1083: radius = diameter/2 is done by the caller, rmass = 4/3 pi r^3 rho here)
 __global__ void __launch_bounds__(256) k_pack_upload(int n, const double *x, const double *v, const double *omega, const double *radius,
                                                      const double *density, const int *type, const int *mask, const int *tag, int ntypes,
-                                                     double4 *xr, double4 *vm, double4 *wt, int *err, unsigned long long *rmax_bits)
+                                                     double4 *xr, double4 *vm, double4 *wt, int *err, unsigned long long *rmax_bits, int ins_mass)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long b = 0ull, bm = ~0ull;  // running maximum / minimum of the radius bit patterns (rmax_bits[0] / rmax_bits[2])
@@ -1409,7 +1416,7 @@ __global__ void __launch_bounds__(256) k_pack_upload(int n, const double *x, con
     if (t < 1 || t > ntypes) atomicOr(err, 1);
     if (!(r > 0.0) || !(rho > 0.0)) atomicOr(err, 2);
     if (tag[i] <= 0) atomicOr(err, 4);
-    const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;
+    const double m = ins_mass ? insert_mass(r, rho) : 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;
     xr[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
     vm[i] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
     wt[i] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0.,
@@ -1461,13 +1468,13 @@ __global__ void __launch_bounds__(256) k_flag_mine(int n, const double *x, const
 // records of the selected particles (ascending original index, like the host loop it replaces)
 __global__ void __launch_bounds__(256) k_pack_upload_sel(int nsel, const int *list, const double *x, const double *v, const double *omega, const double *radius,
                                                          const double *density, const int *type, const int *mask, const int *tag,
-                                                         double4 *xr, double4 *vm, double4 *wt, int *otag, double *odensity)
+                                                         double4 *xr, double4 *vm, double4 *wt, int *otag, double *odensity, int ins_mass)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nsel) return;
   const int i = list[q];
   const double r = radius[i], rho = density[i];
-  const double m = 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;  // atom_vec_sphere.cpp:1078
+  const double m = ins_mass ? insert_mass(r, rho) : 4.0 * 3.14159265358979323846 / 3.0 * r * r * r * rho;  // atom_vec_sphere.cpp:1078
   xr[q] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], r);
   vm[q] = make_double4(v ? v[3 * i] : 0., v ? v[3 * i + 1] : 0., v ? v[3 * i + 2] : 0., m);
   wt[q] = make_double4(omega ? omega[3 * i] : 0., omega ? omega[3 * i + 1] : 0., omega ? omega[3 * i + 2] : 0.,

@@ -10,7 +10,7 @@ ABI_SYMBOLS = [
     "dem_create", "dem_destroy", "dem_nccl_unique_id", "dem_decomposition", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
     "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_contact_distance_factor", "dem_set_property",
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
-    "dem_set_integrate", "dem_upload_particles", "dem_insert_particles", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
+    "dem_set_integrate", "dem_upload_particles", "dem_insert_particles", "dem_insert_step_begin", "dem_insert_step_end", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
     "dem_bond_counter", "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep", "dem_deck_output", "dem_deck_screen",
@@ -216,6 +216,22 @@ class Engine:
                 np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
         ptr = [a.ctypes.data if a is not None else None for a in keep]
         self._call("insert_particles", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
+
+    def insert_step_begin(self):
+        """first half of the timestep in which fix insert/* creates particles (fix_insert.cpp:672-905): first half step of the
+        existing particles; download('x') then returns the positions the reference's overlap check sees"""
+        self._call("insert_step_begin", [])
+
+    def insert_step_end(self, tag, type, x, radius, density, v=None, omega=None, mask=None):
+        """second half: the particles appear, rebuild, forces, second half step (mass = density * volume as fix insert forms it)"""
+        n = len(tag)
+        keep = [np.ascontiguousarray(tag, np.int32), np.ascontiguousarray(type, np.int32),
+                None if mask is None else np.ascontiguousarray(mask, np.int32),
+                np.ascontiguousarray(x, np.float64), None if v is None else np.ascontiguousarray(v, np.float64),
+                None if omega is None else np.ascontiguousarray(omega, np.float64),
+                np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
+        ptr = [a.ctypes.data if a is not None else None for a in keep]
+        self._call("insert_step_end", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
 
     def setup(self):
         self._call("setup", [])

@@ -105,6 +105,7 @@ typedef struct orc_engine {
   long *first; int *numneigh; int *jlist; signed char *jshift; int *flag; double *hist; long npairs, cap;
   long bond_created, bond_broken; /* compute bond/counter (compute_bond_counter.cpp:140-156), linear bond model only */
   long ntimestep, nbuilds; int ago; int setup_done;
+  int ins_mass, ins_open; /* orc_insert_step_*: mass as fix insert forms it / the timestep is half done */
 } orc_engine;
 
 static int fail(orc_engine *e, const char *msg) { snprintf(e->err, sizeof e->err, "%s", msg); return -1; }
@@ -310,6 +311,10 @@ int orc_set_gravity(orc_engine *e, double mag, const double dir[3])
 int orc_set_freeze(orc_engine *e, int bit) { e->freezebit = bit; return 0; }
 int orc_set_integrate(orc_engine *e, int bit) { e->integbit = bit; return 0; }
 
+/* mass of a sphere created by fix insert/*: fix_template_sphere.cpp:349-350 (volume_ins = r*r*r*4.*M_PI/3., mass_ins = density_ins*volume_ins),
+ * stored by ParticleToInsert::insert particleToInsert.cpp:127 */
+static double insert_mass(double r, double rho) { const double vol = r * r * r * 4. * M_PI / 3.; return rho * vol; }
+
 int orc_upload_particles(orc_engine *e, long n, const int *tag, const int *type, const int *mask,
                          const double *x, const double *v, const double *omega, const double *radius, const double *density)
 {
@@ -323,7 +328,7 @@ int orc_upload_particles(orc_engine *e, long n, const int *tag, const int *type,
     for (int d = 0; d < 3; d++) { e->x[3 * i + d] = x[3 * i + d]; e->v[3 * i + d] = v ? v[3 * i + d] : 0.0; e->omega[3 * i + d] = omega ? omega[3 * i + d] : 0.0; }
     e->radius[i] = radius[i]; e->density[i] = density[i];
     /* atom_vec_sphere.cpp:1078-1079 */
-    e->rmass[i] = 4.0 * M_PI / 3.0 * radius[i] * radius[i] * radius[i] * density[i];
+    e->rmass[i] = e->ins_mass ? insert_mass(radius[i], density[i]) : 4.0 * M_PI / 3.0 * radius[i] * radius[i] * radius[i] * density[i];
   }
   return 0;
 }
@@ -357,7 +362,7 @@ int orc_insert_particles(orc_engine *e, long n, const int *tag, const int *type,
     e->tag[i] = tag[q]; e->type[i] = type[q]; e->mask[i] = mask ? mask[q] : 1;
     for (int d = 0; d < 3; d++) { e->x[3 * i + d] = x[3 * q + d]; e->v[3 * i + d] = v ? v[3 * q + d] : 0.0; e->omega[3 * i + d] = omega ? omega[3 * q + d] : 0.0; }
     e->radius[i] = radius[q]; e->density[i] = density[q];
-    e->rmass[i] = 4.0 * M_PI / 3.0 * radius[q] * radius[q] * radius[q] * density[q];
+    e->rmass[i] = e->ins_mass ? insert_mass(radius[q], density[q]) : 4.0 * M_PI / 3.0 * radius[q] * radius[q] * radius[q] * density[q];
   }
   e->n = nn;
   return 0;
@@ -1603,8 +1608,8 @@ static void compute_forces(orc_engine *e, int shearupdate)
   if (e->freezebit) for (long i = 0; i < e->n; i++) if (e->mask[i] & e->freezebit) for (int d = 0; d < 3; d++) { e->f[3 * i + d] = 0.0; e->torque[3 * i + d] = 0.0; } /* fix_freeze.cpp:132-144 */
 }
 
-int orc_setup(orc_engine *e)
-{ /* Verlet::setup verlet.cpp:134-199 */
+static int setup_prepare(orc_engine *e, int first)
+{
   if (!e->n && !e->tag) return fail(e, "no particles uploaded");
   derive_tables(e);
   e->cdf = e->cdf_user > 1.0 ? e->cdf_user : 1.0;
@@ -1626,25 +1631,80 @@ int orc_setup(orc_engine *e)
     e->cdf = cdf_all;
   }
   for (int w = 0; w < e->nwalls; w++) if (!e->walls[w].hist) { e->walls[w].hist = (double *)calloc((size_t)(e->n ? e->n : 1) * (e->walls[w].m.dnum ? e->walls[w].m.dnum : 1), sizeof(double)); }
-  for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].moving) memset(e->meshes[m].vnode, 0, sizeof(double) * 9 * e->meshes[m].ntri); /* FixMoveMesh::setup fix_move_mesh.cpp:194-217: v = 0 */
+  if (first) for (int m = 0; m < e->nmeshes; m++) if (e->meshes[m].moving) memset(e->meshes[m].vnode, 0, sizeof(double) * 9 * e->meshes[m].ntri); /* FixMoveMesh::setup fix_move_mesh.cpp:194-217: v = 0 */
+  return 0;
+}
+
+int orc_setup(orc_engine *e)
+{ /* Verlet::setup verlet.cpp:134-199 */
+  if (e->ins_open) return fail(e, "setup inside an insertion step");
+  const int rc = setup_prepare(e, 1); if (rc) return rc;
   build(e);
   e->nbuilds = 0; /* neighbor->ncalls counts builds of the current run only (neighbor.cpp init: ncalls = 0) */
   compute_forces(e, 0);
   e->setup_done = 1; return 0;
 }
 
+static void first_half_step(orc_engine *e)
+{
+  const double dtv = e->dt, dtf = 0.5 * e->dt * e->ftm2v, dtfrotate = dtf / 0.4; /* fix_nve.cpp:86, fix_nve_sphere.cpp:69,150 */
+  for (long i = 0; i < e->n; i++) if (e->mask[i] & e->integbit) { /* fix_nve_sphere.cpp:134-183 */
+    const double dtfm = dtf / (e->rmass[i] * (1. + 0.0 / e->density[i]));
+    for (int d = 0; d < 3; d++) { e->v[3 * i + d] += dtfm * e->f[3 * i + d]; e->x[3 * i + d] += dtv * e->v[3 * i + d]; }
+    const double dtirotate = dtfrotate / (e->radius[i] * e->radius[i] * e->rmass[i]);
+    for (int d = 0; d < 3; d++) e->omega[3 * i + d] += dtirotate * e->torque[3 * i + d];
+  }
+}
+static void second_half_step(orc_engine *e)
+{
+  const double dtf = 0.5 * e->dt * e->ftm2v, dtfrotate = dtf / 0.4;
+  for (long i = 0; i < e->n; i++) if (e->mask[i] & e->integbit) { /* fix_nve_sphere.cpp:205-244 */
+    const double dtfm = dtf / (e->rmass[i] * (1. + 0.0 / e->density[i]));
+    for (int d = 0; d < 3; d++) e->v[3 * i + d] += dtfm * e->f[3 * i + d];
+    const double dtirotate = dtfrotate / (e->radius[i] * e->radius[i] * e->rmass[i]);
+    for (int d = 0; d < 3; d++) e->omega[3 * i + d] += dtirotate * e->torque[3 * i + d];
+  }
+}
+
+/* The timestep in which fix insert/* creates particles (FixInsert::pre_exchange fix_insert.cpp:672-905 sits between
+ * initial_integrate and the rebuild it forces, verlet.cpp:277-310), in two halves so that the caller can look at the positions
+ * the overlap check of the reference sees. */
+int orc_insert_step_begin(orc_engine *e)
+{
+  if (e->ins_open) return fail(e, "insert_step_begin called twice");
+  if (e->tag) {
+    if (!e->setup_done) return fail(e, "insert_step_begin before setup");
+    e->ntimestep++;
+    first_half_step(e);
+    mesh_move_step(e);
+  } else e->ntimestep++;
+  e->ins_open = 1; return 0;
+}
+int orc_insert_step_end(orc_engine *e, long n, const int *tag, const int *type, const int *mask,
+                        const double *x, const double *v, const double *omega, const double *radius, const double *density)
+{
+  if (!e->ins_open) return fail(e, "insert_step_end without insert_step_begin");
+  if (!e->tag && n <= 0) { e->ins_open = 0; return 0; } /* a step of an empty box */
+  const int first = !e->setup_done;
+  e->ins_mass = 1;
+  const int rc = n > 0 ? orc_insert_particles(e, n, tag, type, mask, x, v, omega, radius, density) : 0;
+  e->ins_mass = 0;
+  if (rc) return rc;
+  const int rc2 = setup_prepare(e, first); if (rc2) return rc2;
+  if (first) e->nbuilds = 0; /* (the run of an empty box had no setup that would have reset neighbor->ncalls) */
+  build(e); /* fix->next_reneighbor forces the rebuild, neighbor.cpp:1364-1369 */
+  compute_forces(e, 1);
+  second_half_step(e);
+  e->ins_open = 0; e->setup_done = 1; return 0;
+}
+
 int orc_run(orc_engine *e, long nsteps)
 { /* Verlet::run verlet.cpp:264-391 */
   if (!e->setup_done) return fail(e, "run before setup");
-  const double dtv = e->dt, dtf = 0.5 * e->dt * e->ftm2v, dtfrotate = dtf / 0.4; /* fix_nve.cpp:86, fix_nve_sphere.cpp:69,150 */
+  if (e->ins_open) return fail(e, "run inside an insertion step");
   for (long s = 0; s < nsteps; s++) {
     e->ntimestep++;
-    for (long i = 0; i < e->n; i++) if (e->mask[i] & e->integbit) { /* fix_nve_sphere.cpp:134-183 */
-      const double dtfm = dtf / (e->rmass[i] * (1. + 0.0 / e->density[i]));
-      for (int d = 0; d < 3; d++) { e->v[3 * i + d] += dtfm * e->f[3 * i + d]; e->x[3 * i + d] += dtv * e->v[3 * i + d]; }
-      const double dtirotate = dtfrotate / (e->radius[i] * e->radius[i] * e->rmass[i]);
-      for (int d = 0; d < 3; d++) e->omega[3 * i + d] += dtirotate * e->torque[3 * i + d];
-    }
+    first_half_step(e);
     mesh_move_step(e);
     /* Neighbor::decide neighbor.cpp:1362-1376 + check_distance :1425-1466 */
     int nflag = 0, forced = 0;
@@ -1658,12 +1718,7 @@ int orc_run(orc_engine *e, long nsteps)
     }
     if (nflag) build(e); else mesh_decide_rebuild(e);
     compute_forces(e, 1);
-    for (long i = 0; i < e->n; i++) if (e->mask[i] & e->integbit) { /* fix_nve_sphere.cpp:205-244 */
-      const double dtfm = dtf / (e->rmass[i] * (1. + 0.0 / e->density[i]));
-      for (int d = 0; d < 3; d++) e->v[3 * i + d] += dtfm * e->f[3 * i + d];
-      const double dtirotate = dtfrotate / (e->radius[i] * e->radius[i] * e->rmass[i]);
-      for (int d = 0; d < 3; d++) e->omega[3 * i + d] += dtirotate * e->torque[3 * i + d];
-    }
+    second_half_step(e);
   }
   return 0;
 }

@@ -400,3 +400,11 @@ def snapshot(eng, c):
         if mid in c.get("mesh_stress", []):
             out["meshforce_%s" % mid] = eng.mesh_force(mid)
     return out
+
+
+# fix insert/pack decks (tests/golden/in.<name>, goldens by tests/golden/make_golden_insert.py): name -> checkpoints
+#  a: cylinder region, one template, volumefraction_region, insert_every once (the shape of tutorial t01a's insertion)
+#  b: block region, two templates (mass based), all_in yes, particles_in_region topped up every 400 steps against the spheres
+#     already there, vel uniform, omega constant
+#  c: cylinder along x, number based, all_in no, mass_in_region every 300 steps, vel gaussian, maxattempt
+INSERT_DECKS = {"insert_pack_a": [1, 2, 200, 1000], "insert_pack_b": [1, 400, 401, 801, 2500], "insert_pack_c": [1, 301, 601, 2000]}

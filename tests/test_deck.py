@@ -68,6 +68,44 @@ def test_deck_on_engine_matches_reference_golden(name, tmp_path):
     follow_golden(name, eng, dem_b200.Deck(eng), path, gpu=True)
 
 
+def follow_insert_golden(name, eng, deck, gpu):
+    """fix insert/pack decks: the spheres the deck front end draws (Park-Miller streams, Monte-Carlo region volume, overlap search)
+    must be the reference's spheres -- ids, types, radii and masses bit-exact, positions / velocities at the insertion step to
+    1e-10 -- and stay on the reference's trajectory afterwards (tolerances of parity.tol_for)"""
+    g = parity.golden(name)
+    deck.file(os.path.join(parity.ROOT, "tests", "golden", "in." + name))
+    for cp in cases.INSERT_DECKS[name]:
+        deck.command("run %d upto" % cp)
+        ref = parity.golden_at(g, cp)
+        n = len(ref["tag"])
+        assert eng.nlocal == n, "%s@%d: %d spheres, reference %d" % (name, cp, eng.nlocal, n)
+        assert np.array_equal(eng.download("tag"), ref["tag"]) and np.array_equal(eng.download("type"), ref["type"])
+        assert np.array_equal(eng.download("radius"), ref["radius"]) and np.array_equal(eng.download("rmass"), ref["rmass"]), "%s@%d: radius / mass" % (name, cp)
+        tol = (1e-12 if not gpu else 1e-10) if cp <= 10 else parity.tol_for({"pair": "hertz"}, cp, gpu=gpu)
+        mg = ref["rmass"] * 9.81
+        floors = {"x": 1e-3, "v": 1e-3, "omega": 1e-2, "f": 1e-12 * mg, "torque": np.maximum(1e-15 * mg, 1e-9 * np.linalg.norm(ref["f"], axis=1))}
+        for k in ("x", "v", "omega", "f", "torque"):
+            err = parity.rel_err(eng.download(k).reshape(ref[k].shape), ref[k], floors[k])
+            assert err <= tol, "%s@%d: %s rel err %.3e" % (name, cp, k, err)
+        assert eng.stats().nbuilds == int(ref["nbuilds"])
+    assert "Particle insertion ins: inserted" in deck.output
+    deck.close(); eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(cases.INSERT_DECKS))
+def test_insert_pack_deck_on_oracle_matches_reference(name):
+    eng, deck = oracle_deck()
+    follow_insert_golden(name, eng, deck, gpu=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(cases.INSERT_DECKS))
+def test_insert_pack_deck_on_engine_matches_reference(name):
+    import dem_b200
+    eng = dem_b200.Engine(device=0)
+    follow_insert_golden(name, eng, dem_b200.Deck(eng), gpu=True)
+
+
 def test_deck_mesh_load_transforms_and_errors(tmp_path):
     """`fix mesh/surface ... move/rotate/scale` act on the nodes like FixMesh::moveMesh/rotateMesh/scaleMesh; error classes"""
     import dem_b200
@@ -87,7 +125,7 @@ def test_deck_mesh_load_transforms_and_errors(tmp_path):
     assert np.abs(got - want).max() < 1e-15
     # error classes: unsupported (-2) vs bad argument (-1), with the reference's message text where one exists
     with pytest.raises(dem_b200.DemError, match=r"\(-2\).*outside the hot-path scope"):
-        deck.command("fix ins all insert/pack seed 1")
+        deck.command("fix ins all insert/stream seed 1")
     with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Expected floating point parameter"):
         deck.command("timestep abc")
     with pytest.raises(dem_b200.DemError, match=r"\(-1\).*Substitution for illegal variable"):
@@ -107,7 +145,7 @@ def test_lmp_b200_cli_runs_a_deck(tmp_path):
     r = subprocess.run([exe, "-in", path], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "for 300 steps with 64 atoms" in r.stdout, r.stdout
-    bad = tmp_path / "in.bad"; bad.write_text("units si\nfix ins all insert/pack seed 1\n")
+    bad = tmp_path / "in.bad"; bad.write_text("units si\nfix ins all insert/stream seed 1\n")
     r = subprocess.run([exe, "-in", str(bad)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 1 and "outside the hot-path scope" in r.stderr and "line 2" in r.stderr
 
@@ -115,7 +153,7 @@ def test_lmp_b200_cli_runs_a_deck(tmp_path):
 def test_tutorial_style_deck_on_oracle(tmp_path):
     """a deck written the way the INL tutorial decks are (tabs, trailing comments, continuation lines, create_box from a region,
     two atom types with the wall as the last one, a diagnostic fix that is later unfixed, `run N upto`, a mesh that starts to
-    move between two runs) -- particles come from read_data, because insertion is outside the hot path"""
+    move between two runs); particles from read_data here, fix insert/pack has its own tests above"""
     import dem_b200
     c = cases.case_mesh(kind="plate", n3=(4, 4, 3), name="tut")
     _, data = cases.to_deck(c, str(tmp_path / "case.data"))
@@ -172,7 +210,6 @@ run\t\t200
     assert dk.ntimestep == 500
     assert "check/timestep/gran ignored" in dk.warnings and "fix balance ignored" in dk.warnings
     assert not list(tmp_path.glob("out.*.dump")), "the dump is defined at step 1: no multiple of 50000 is reached in 500 steps"
-    assert "region factory (cylinder) kept as a name only" in dk.warnings
     # the same through the API calls, step for step
     ref = parity.oracle_engine()
     ref.units("si"); ref.box(lo, hi, [0, 0, 0]); ref.ntypes(2); ref.neighbor(0.001, every=1, delay=0, check=True)
