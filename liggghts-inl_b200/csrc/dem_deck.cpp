@@ -135,7 +135,7 @@ struct Deck {
   std::vector<double> px, pv, pomega, pradius, pdensity;
   int maxtag = 0;
   // dump custom (dump_custom.cpp): text snapshots every N steps, atoms in ascending id
-  struct Dump { std::string file; long every = 0, last = -1; std::vector<std::string> fields; };
+  struct Dump { std::string file; long every = 0, last = -1; std::vector<std::string> fields; int pad = 0; bool first = false; };  // (dump_modify pad / first, dump.cpp:640-700)
   std::map<std::string, Dump> dumps;
   std::string bstr[3] = {"ff", "ff", "ff"};  // Domain::boundary_string
   // thermo (thermo.cpp): one line at the start of a run, on the multiples of N and on the last step
@@ -480,7 +480,7 @@ int write_dump(Deck *d, Deck::Dump &D)
   std::string path = D.file;
   const size_t star = path.find('*');
   const bool per_step = star != std::string::npos;
-  if (per_step) path = path.substr(0, star) + std::to_string(d->ntimestep) + path.substr(star + 1);
+  if (per_step) { char num[48]; snprintf(num, sizeof num, "%0*ld", D.pad, d->ntimestep); path = path.substr(0, star) + num + path.substr(star + 1); }
   if (!path.empty() && path[0] != '/' && !d->dir.empty()) path = d->dir + "/" + path;
   FILE *fp = fopen(path.c_str(), (per_step || D.last < 0) ? "w" : "a");
   if (!fp) return fail(d, ERR_ARG, "Cannot open dump file %s", path.c_str());
@@ -524,11 +524,11 @@ int write_dump(Deck *d, Deck::Dump &D)
   D.last = d->ntimestep;
   return OK;
 }
-int write_dumps_due(Deck *d)
-{  // snapshots on the steps that are multiples of N (output.cpp:150-190), once per step
+int write_dumps_due(Deck *d, bool run_start = false)
+{  // snapshots on the steps that are multiples of N, and at the start of a run when `dump_modify first yes` (output.cpp:150-190), once per step
   for (auto &kv : d->dumps) {
     Deck::Dump &D = kv.second;
-    if (D.every > 0 && d->ntimestep % D.every == 0 && D.last != d->ntimestep) { const int rc = write_dump(d, D); if (rc) return rc; }
+    if (D.every > 0 && (d->ntimestep % D.every == 0 || (run_start && D.first)) && D.last != d->ntimestep) { const int rc = write_dump(d, D); if (rc) return rc; }
   }
   return OK;
 }
@@ -1235,6 +1235,10 @@ int one(Deck *d, const std::string &raw)
   if (c == "dump_modify") {  // atoms are always written in ascending id (== `sort id`); other keywords do not change the content
     if (w.size() < 2) return fail(d, ERR_ARG, "Illegal dump_modify command");
     for (size_t k = 2; k < w.size(); k++) if (w[k] == "format") return fail(d, ERR_UNSUPPORTED, "dump_modify format is outside the hot-path scope");
+    if (d->dumps.count(w[1])) for (size_t k = 2; k + 1 < w.size(); k++) {
+      if (w[k] == "pad") { rc = inumeric(d, w[k + 1], d->dumps[w[1]].pad); if (rc) return rc; }
+      else if (w[k] == "first") d->dumps[w[1]].first = (w[k + 1] == "yes");
+    }
     return OK;
   }
   if (c == "create_atoms") {  // create_atoms.cpp (style single): one atom of the given type at a point; radius 0.5, density 1 until `set` (atom_vec_sphere.cpp:167-190)
@@ -1292,7 +1296,7 @@ int one(Deck *d, const std::string &raw)
     rc = first_run_prepare(d); if (rc) return rc;
     if (d->uploaded) TRY(API(setup)(d->e));  // (else the box is still empty: nothing to set up)
     for (auto &I : d->inserts) { rc = insert_setup(d, I); if (rc) return rc; }  // Modify::setup -> FixInsert::setup
-    rc = write_dumps_due(d); if (rc) return rc;
+    rc = write_dumps_due(d, true); if (rc) return rc;
     const long run_first = d->ntimestep;
     d->loop0 = std::chrono::steady_clock::now();
     thermo_header(d);

@@ -106,6 +106,39 @@ def test_insert_pack_deck_on_engine_matches_reference(name):
     follow_insert_golden(name, eng, dem_b200.Deck(eng), gpu=True)
 
 
+TUTORIAL = "/root/reference/examples/LIGGGHTS/INL_tutorials/t01a_static_angle_of_repose_monosphere"
+
+
+@pytest.mark.skipif(not os.path.isdir(TUTORIAL), reason="the reference's tutorial deck and STL file exist in the build container only")
+def test_reference_tutorial_t01a_deck_runs_unchanged_on_oracle(tmp_path):
+    """the reference's own tutorial deck t01a (static angle of repose: boundary m m m, cylinder region, fix insert/pack with
+    volumefraction_region 0.6 -> 10,802 spheres, STL tube, primitive floor, thermo / dump / compute lines, the tube lifted by a
+    late fix move/mesh) through the deck front end, only its two long runs shortened; compared with what the unmodified
+    reference makes of the same text (tests/golden/tutorial_t01a.npz: every 16th sphere and the sums over all)"""
+    sys_path = os.path.join(parity.ROOT, "tests", "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_insert", os.path.join(sys_path, "make_golden_insert.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    text = gen.tutorial_text()
+    os.symlink(os.path.join(TUTORIAL, "Cylinder_35cm_7cm.stl"), tmp_path / "Cylinder_35cm_7cm.stl")
+    head, tail = text.split("unfix", 1)
+    (tmp_path / "in.head").write_text(head); (tmp_path / "in.tail").write_text("unfix" + tail)
+    g = parity.golden("tutorial_t01a")
+    eng, dk = oracle_deck()
+    for cp, part, tol in ((1, "in.head", 1e-12), (500, "in.tail", 1e-6)):
+        dk.file(str(tmp_path / part))
+        assert dk.ntimestep == cp and eng.nlocal == int(g["s%d_n" % cp])
+        for k in ("radius", "rmass"):
+            assert np.array_equal(eng.download(k)[::16], g["s%d_%s" % (cp, k)])
+        for k, floor in (("x", 1e-3), ("v", 1e-3), ("f", 1e-12 * 9.81 * g["s%d_rmass" % cp])):
+            got, ref = eng.download(k), g["s%d_%s" % (cp, k)]
+            assert parity.rel_err(got[::16], ref, floor) <= tol, "%s@%d" % (k, cp)
+            assert np.allclose(got.sum(axis=0), g["s%d_sum_%s" % (cp, k)], rtol=1e-6, atol=1e-9 * len(got)), "sum %s@%d" % (k, cp)
+    assert "inserted 10802 particle templates" in dk.output
+    assert list(tmp_path.glob("out.*.dump")), "dump custom with dump_modify first yes"
+    dk.close(); eng.close()
+
+
 def test_deck_mesh_load_transforms_and_errors(tmp_path):
     """`fix mesh/surface ... move/rotate/scale` act on the nodes like FixMesh::moveMesh/rotateMesh/scaleMesh; error classes"""
     import dem_b200
