@@ -34,6 +34,8 @@ int orc_set_ntypes(struct dem_engine *, int); int orc_set_neighbor(struct dem_en
 int orc_set_freeze(struct dem_engine *, int); int orc_set_integrate(struct dem_engine *, int);
 int orc_upload_particles(struct dem_engine *, long, const int *, const int *, const int *, const double *, const double *, const double *, const double *, const double *);
 int orc_setup(struct dem_engine *); int orc_run(struct dem_engine *, long); long orc_nlocal(const struct dem_engine *);
+int orc_insert_step_begin(struct dem_engine *);
+int orc_insert_step_end(struct dem_engine *, long, const int *, const int *, const int *, const double *, const double *, const double *, const double *, const double *);
 int orc_download(struct dem_engine *, const char *, void *, long);
 int orc_deck_open(dem_deck **, struct dem_engine *); void orc_deck_close(dem_deck *); int orc_deck_command(dem_deck *, const char *);
 const char *orc_deck_last_error(const dem_deck *);
@@ -84,7 +86,7 @@ void PairGranB200::settings(int narg, char **arg)
   PairGranProxy::settings(narg, arg);
 }
 
-VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), eng(NULL), deck(NULL), replayed(0), uploaded_step(-1) { DBG("verlet/b200 created"); }
+VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), eng(NULL), deck(NULL), replayed(0), uploaded_step(-1), holds(false) { DBG("verlet/b200 created"); }
 
 VerletB200::~VerletB200()
 {
@@ -128,8 +130,11 @@ void VerletB200::sync_settings()
   }
   // group bits of the fixes that carry no other parameter; every other fix must be one the engine knows, an internal helper
   // of those, or output only -- anything else would silently change the physics
+  // (insert/*, particletemplate/*, particledistribution/*: the reference's own insertion fixes keep drawing the particles;
+  // VerletB200::insertion_step hands what they create to the engine inside the timestep)
   static const char *known[] = {"wall/gran", "mesh/surface", "move/mesh", "gravity", "property/global", "property/atom", "contacthistory",
-                                "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", NULL};
+                                "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", "insert/", "particletemplate/",
+                                "particledistribution/", NULL};
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
     if (strcmp(f->style, "freeze") == 0) { if (DEM(set_freeze)(eng, f->groupbit)) fail("freeze"); continue; }
@@ -146,12 +151,14 @@ void VerletB200::push_state()
   if (DEM(upload_particles)(eng, n, atom->tag, atom->type, atom->mask, n ? &atom->x[0][0] : NULL, n ? &atom->v[0][0] : NULL,
                              n ? &atom->omega[0][0] : NULL, atom->radius, atom->density)) fail("dem_upload_particles");
   uploaded_step = update->ntimestep;
+  holds = true;
 }
 
 // engine -> atom arrays (the engine returns fields ordered by tag; the reference's local order is its own)
-void VerletB200::pull_state()
+void VerletB200::pull_state(bool forces)
 {
   const long n = DEM(nlocal)(eng);
+  if (n == 0 && atom->nlocal == 0) return;
   if (n != atom->nlocal) error->all(FLERR, "verlet/b200: particle count changed");
   std::vector<int> tags(n), order(n);
   if (DEM(download)(eng, "tag", tags.data(), n)) fail("download tag");
@@ -161,6 +168,7 @@ void VerletB200::pull_state()
   std::vector<double> buf(3 * (size_t)n);
   struct { const char *name; double **dst; } fields[] = {{"x", atom->x}, {"v", atom->v}, {"omega", atom->omega}, {"f", atom->f}, {"torque", atom->torque}};
   for (auto &fd : fields) {
+    if (!forces && (fd.dst == atom->f || fd.dst == atom->torque)) continue;
     if (DEM(download)(eng, fd.name, buf.data(), n)) fail(fd.name);
     for (long k = 0; k < n; k++) { double *d = fd.dst[order[k]]; d[0] = buf[3 * k]; d[1] = buf[3 * k + 1]; d[2] = buf[3 * k + 2]; }
   }
@@ -175,9 +183,43 @@ void VerletB200::setup()
   DBG("setup: sync_settings");
   sync_settings();
   DBG("setup: push/setup/pull");
+  if (atom->nlocal == 0 && !holds) return;                // an empty box that an insertion fix will fill: nothing to set up yet
   if (uploaded_step != update->ntimestep) push_state();   // first run, or the deck changed the particles between two runs
   if (DEM(setup)(eng)) fail("dem_setup");
   pull_state();
+}
+
+// the next timestep on which one of the reference's insertion fixes acts (Fix::next_reneighbor, fix_insert.cpp:393-395,897-899)
+static bigint next_insertion(Modify *modify, bigint now)
+{
+  bigint next = -1;
+  for (int i = 0; i < modify->nfix; i++) {
+    Fix *f = modify->fix[i];
+    if (strncmp(f->style, "insert/", 7) == 0 && f->force_reneighbor && f->next_reneighbor > now && (next < 0 || f->next_reneighbor < next)) next = f->next_reneighbor;
+  }
+  return next;
+}
+
+// One timestep in which the reference's OWN insertion fixes create particles (FixInsert::pre_exchange, fix_insert.cpp:672-905,
+// between the first half step and the forced rebuild): the engine does the first half step, the atom arrays receive the
+// positions the fixes check overlaps against, the fixes run unchanged -- their random streams, regions and templates are the
+// reference's -- and whatever they appended to the atom arrays enters the engine for the second half of the step.
+void VerletB200::insertion_step()
+{
+  update->ntimestep++;
+  if (DEM(insert_step_begin)(eng)) fail("dem_insert_step_begin");
+  if (holds) pull_state(false);
+  const int n0 = atom->nlocal;
+  atom->nghost = 0;  // (ghosts of the last build are stale; one process, no periodic images in the overlap check)
+  for (int i = 0; i < modify->nfix; i++)
+    if (strncmp(modify->fix[i]->style, "insert/", 7) == 0) modify->fix[i]->pre_exchange();
+  const int nnew = atom->nlocal - n0;
+  DBG("insertion step %ld: %d new particles", (long)update->ntimestep, nnew);
+  if (DEM(insert_step_end)(eng, nnew, atom->tag + n0, atom->type + n0, atom->mask + n0, nnew ? &atom->x[n0][0] : NULL, nnew ? &atom->v[n0][0] : NULL,
+                           nnew ? &atom->omega[n0][0] : NULL, atom->radius + n0, atom->density + n0)) fail("dem_insert_step_end");
+  if (nnew) holds = true;
+  uploaded_step = update->ntimestep;
+  if (holds) pull_state();
 }
 
 void VerletB200::run(int n)
@@ -186,11 +228,16 @@ void VerletB200::run(int n)
   while (left > 0) {
     bigint m = left;
     if (output->next > update->ntimestep && output->next - update->ntimestep < m) m = output->next - update->ntimestep;
-    if (DEM(run)(eng, (long)m)) fail("dem_run");
-    update->ntimestep += m;
+    const bigint ins = next_insertion(modify, update->ntimestep);
+    if (ins == update->ntimestep + 1) { insertion_step(); m = 1; }
+    else {
+      if (ins > 0 && ins - 1 - update->ntimestep < m) m = ins - 1 - update->ntimestep;
+      if (holds) { if (DEM(run)(eng, (long)m)) fail("dem_run"); }  // (an empty box has nothing to step)
+      update->ntimestep += m;
+      if (holds) pull_state();
+      uploaded_step = update->ntimestep;
+    }
     left -= m;
-    pull_state();
-    uploaded_step = update->ntimestep;
     if (update->ntimestep == output->next) {
       timer->stamp();
       output->write(update->ntimestep);

@@ -87,8 +87,10 @@ class VerletB200 : public Verlet {
   bigint uploaded_step;  // timestep at which the engine received the particle state
   void fail(const char *what);
   void sync_settings();
+  bool holds;            // the engine holds particles (false while an empty box waits for an insertion fix)
   void push_state();
-  void pull_state();
+  void pull_state(bool forces = true);
+  void insertion_step();
 };
 
 }  // namespace LAMMPS_NS

@@ -61,3 +61,56 @@ def test_suffix_b200_deck_on_gpu_engine(name, tmp_path):
     if not (os.path.exists(lib) and os.path.exists(os.path.join(REFDIR, "libliggghts_ref.so"))):
         pytest.skip("the shim build of the reference tree is not here (make -C integration)")
     check(name, lib, tmp_path)
+
+
+# ---- insertion under `-suffix b200`: the reference's own fix insert/pack keeps drawing the spheres (its streams, regions and
+# templates), VerletB200::insertion_step hands them to the engine inside the timestep (dem_insert_step_begin / _end)
+INS_WORKER = r'''
+import sys, os
+sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/oracle")
+import numpy as np, cases, ref_driver
+name, lib, out = sys.argv[2], sys.argv[3], sys.argv[4]
+r = ref_driver.Ref(lib=lib, extra_args=["-suffix", "b200"])
+r.cmd(open(os.path.join(sys.argv[1], "tests", "golden", "in." + name)).read())
+res = {}
+for cp in cases.INSERT_DECKS[name]:
+    r.cmd("run %d upto" % cp)
+    a = r.atoms()
+    for k in ("tag", "radius", "rmass", "x", "v", "omega", "f", "torque"):
+        res["s%d_%s" % (cp, k)] = a[k]
+np.savez(out, **res)
+'''
+
+
+def check_insertion(name, lib, tmp_path, gpu):
+    import parity
+    out = str(tmp_path / (name + ".npz"))
+    r = subprocess.run([sys.executable, "-c", INS_WORKER, ROOT, name, lib, out], capture_output=True, text=True, timeout=600)
+    assert os.path.exists(out), "reference run failed: " + r.stdout[-1500:] + r.stderr[-1500:]
+    a, g = np.load(out), parity.golden(name)
+    for cp in cases.INSERT_DECKS[name]:
+        for k in ("tag", "radius", "rmass"):
+            assert np.array_equal(a["s%d_%s" % (cp, k)], g["s%d_%s" % (cp, k)]), "%s@%d: %s" % (name, cp, k)
+        tol = (1e-10 if gpu else 1e-12) if cp <= 10 else parity.tol_for({"pair": "hertz"}, cp, gpu=gpu)
+        mg = g["s%d_rmass" % cp] * 9.81
+        floors = {"x": 1e-3, "v": 1e-3, "omega": 1e-2, "f": 1e-12 * mg, "torque": np.maximum(1e-15 * mg, 1e-9 * np.linalg.norm(g["s%d_f" % cp], axis=1))}
+        for k in ("x", "v", "omega", "f", "torque"):
+            err = parity.rel_err(a["s%d_%s" % (cp, k)], g["s%d_%s" % (cp, k)], floors[k])
+            assert err <= tol, "%s@%d: %s rel err %.3e" % (name, cp, k, err)
+
+
+@pytest.mark.parametrize("name", sorted(cases.INSERT_DECKS))
+def test_suffix_b200_insertion_deck_on_oracle_binding(name, tmp_path):
+    lib = os.path.join(REFDIR, "libliggghts_ref_orc.so")
+    if not os.path.exists(lib):
+        pytest.skip("the shim build of the reference tree is not here (make -C integration orc)")
+    check_insertion(name, lib, tmp_path, gpu=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["insert_pack_a", "insert_pack_b"])
+def test_suffix_b200_insertion_deck_on_gpu_engine(name, tmp_path):
+    lib = os.path.join(REFDIR, "libliggghts_ref_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("the shim build of the reference tree is not here (make -C integration)")
+    check_insertion(name, lib, tmp_path, gpu=True)
