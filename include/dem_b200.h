@@ -138,6 +138,11 @@ int dem_upload_particles(dem_engine *e, long n, const int *tag, const int *type,
 int dem_insert_particles(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x,
                          const double *v, const double *omega, const double *radius, const double *density);
 
+/* `fix ID G addforce fx fy fz` (fix_addforce.cpp:234-260, constant components: kind 0, 3 values) and `fix ID G viscous gamma`
+ * (fix_viscous.cpp:100-125, one gamma for all types: kind 1, 1 value): per-particle forces added after the pair, gravity and
+ * wall forces of a step, in the order of definition (at most 4).  An existing id is replaced; n < 0 removes the fix (`unfix`). */
+int dem_set_extra_force(dem_engine *e, const char *id, int kind, int groupbit, const double *values, int n);
+
 /* The timestep in which `fix insert/pack` (fix_insert.cpp:672-905 FixInsert::pre_exchange, fix_insert_pack.cpp:474-597) creates
  * particles, in two halves.  The reference inserts INSIDE a timestep: after the first half step of the existing particles
  * (verlet.cpp:277-286) and before the rebuild it forces (fix->next_reneighbor, neighbor.cpp:1364-1369); the new particles see

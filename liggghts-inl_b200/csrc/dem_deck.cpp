@@ -59,6 +59,7 @@ int API(add_wall_mesh)(dem_engine *e, const char *id, int argc, const char *cons
 int API(set_gravity)(dem_engine *e, double magnitude, const double dir[3]);
 int API(set_freeze)(dem_engine *e, int groupbit);
 int API(set_integrate)(dem_engine *e, int groupbit);
+int API(set_extra_force)(dem_engine *e, const char *id, int kind, int groupbit, const double *values, int n);
 int API(upload_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
                           const double *omega, const double *radius, const double *density);
 int API(insert_particles)(dem_engine *e, long n, const int *tag, const int *type, const int *mask, const double *x, const double *v,
@@ -123,6 +124,7 @@ struct Deck {
   std::set<std::string> opaque_regions;  // regions of other shapes: known by name only
   std::map<std::string, int> groups;  // name -> mask bit
   std::map<std::string, std::string> ignored_fixes;
+  std::set<std::string> extra_fixes;  // fix addforce / viscous ids (dem_set_extra_force)
   // box / particles held until the first `run`
   bool have_box = false, box_sent = false, uploaded = false, newton_off = false, have_pair = false;
   double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -925,6 +927,16 @@ int cmd_fix(Deck *d, const std::vector<std::string> &w)
     return OK;
   }
   if (style == "freeze") { TRY(API(set_freeze)(d->e, bit)); return OK; }
+  if (style == "addforce") {  // fix_addforce.cpp:60-130 (constant components; variables / region / energy options are not on the path)
+    if (w.size() != 7) return fail(d, w.size() < 7 ? ERR_ARG : ERR_UNSUPPORTED, w.size() < 7 ? "Illegal fix addforce command" : "fix addforce options are outside the hot-path scope");
+    double f[3]; for (int k = 0; k < 3; k++) { if (w[4 + k].compare(0, 2, "v_") == 0) return fail(d, ERR_UNSUPPORTED, "fix addforce with a variable is outside the hot-path scope"); rc = numeric(d, w[4 + k], f[k]); if (rc) return rc; }
+    TRY(API(set_extra_force)(d->e, id.c_str(), 0, bit, f, 3)); d->extra_fixes.insert(id); return OK;
+  }
+  if (style == "viscous") {  // fix_viscous.cpp:40-95 (one gamma; per-type `scale` is not on the path)
+    if (w.size() != 5) return fail(d, w.size() < 5 ? ERR_ARG : ERR_UNSUPPORTED, w.size() < 5 ? "Illegal fix viscous command" : "fix viscous scale is outside the hot-path scope");
+    double g; rc = numeric(d, w[4], g); if (rc) return rc;
+    TRY(API(set_extra_force)(d->e, id.c_str(), 1, bit, &g, 1)); d->extra_fixes.insert(id); return OK;
+  }
   if (style == "nve/sphere") { TRY(API(set_integrate)(d->e, bit)); return OK; }
   if (style == "check/timestep/gran" || style == "print" || style.compare(0, 4, "ave/") == 0) {
     d->ignored_fixes[id] = style; d->warnings += "fix " + style + " ignored (diagnostic / output only)\n"; return OK;
@@ -1086,7 +1098,7 @@ int one(Deck *d, const std::string &raw)
   if (w.empty()) return OK;
   const std::string &c = w[0];
   static const char *output_only[] = {"thermo_modify", "compute", "uncompute", "echo", "log",
-                                     "print", "restart", "write_restart", "write_data", "info", "reset_timestep_info", nullptr};
+                                     "print", "restart", "write_restart", "write_data", "info", "reset_timestep_info", "thermo_log", nullptr};
   for (int k = 0; output_only[k]; k++) if (c == output_only[k]) { d->warnings += c + " ignored (output only)\n"; return OK; }
   if (c == "variable") {  // styles equal (formula, see Formula) / string / index (variable.cpp:90-330)
     if (w.size() < 4) return fail(d, ERR_ARG, "Illegal variable command");
@@ -1200,6 +1212,7 @@ int one(Deck *d, const std::string &raw)
     if (w.size() != 2) return fail(d, ERR_ARG, "Illegal unfix command");
     if (d->ignored_fixes.erase(w[1])) return OK;
     for (size_t k = 0; k < d->inserts.size(); k++) if (d->inserts[k].id == w[1]) { d->inserts.erase(d->inserts.begin() + k); return OK; }
+    if (d->extra_fixes.count(w[1])) { TRY(API(set_extra_force)(d->e, w[1].c_str(), 0, 0, nullptr, -1)); d->extra_fixes.erase(w[1]); return OK; }
     return fail(d, ERR_UNSUPPORTED, "unfix of a hot-path fix is outside the hot-path scope");
   }
   if (c == "group") return cmd_group(d, w);
@@ -1260,18 +1273,40 @@ int one(Deck *d, const std::string &raw)
     (pend ? d->pradius : d->radius).push_back(0.5); (pend ? d->pdensity : d->density).push_back(1.0);
     return OK;
   }
-  if (c == "set") {  // set.cpp, style atom: diameter / density / type of atoms that have not reached the engine yet
-    if (w.size() < 5 || w[1] != "atom") return fail(d, ERR_UNSUPPORTED, "set: only style 'atom' is on the hot path");
-    int lo, hi;
-    { const std::string &r = w[2]; const size_t star = r.find('*');
+  if (c == "velocity") {  // velocity.cpp:160-260 (style set; LIGGGHTS default `units box`): initial velocity of the atoms of a group
+    if (w.size() < 6 || w[2] != "set") return fail(d, ERR_UNSUPPORTED, "velocity: only style 'set' is on the hot path");
+    if (!d->groups.count(w[1])) return fail(d, ERR_ARG, "Could not find velocity group ID");
+    const int bit = d->groups[w[1]];
+    bool sum = false;
+    for (size_t k = 6; k + 1 < w.size(); k += 2) {
+      if (w[k] == "sum") sum = w[k + 1] == "yes";
+      else if (w[k] == "units") { if (w[k + 1] != "box") return fail(d, ERR_UNSUPPORTED, "velocity units lattice is outside the hot-path scope"); }
+      else return fail(d, ERR_UNSUPPORTED, "velocity keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    const bool pend = d->uploaded;
+    std::vector<int> &mk = pend ? d->pmask : d->mask;
+    std::vector<double> &vv = pend ? d->pv : d->v;
+    if (pend && mk.empty()) return fail(d, ERR_UNSUPPORTED, "velocity set: the atoms are already on the engine (velocities of running particles cannot be changed)");
+    for (int k = 0; k < 3; k++) {
+      if (w[3 + k] == "NULL") continue;
+      double val; rc = numeric(d, w[3 + k], val); if (rc) return rc;
+      for (size_t i = 0; i < mk.size(); i++) if (mk[i] & bit) vv[3 * i + k] = sum ? vv[3 * i + k] + val : val;
+    }
+    return OK;
+  }
+  if (c == "set") {  // set.cpp, styles atom and group: diameter / density / type of atoms that have not reached the engine yet
+    if (w.size() < 5 || (w[1] != "atom" && w[1] != "group")) return fail(d, ERR_UNSUPPORTED, "set: only styles 'atom' and 'group' are on the hot path");
+    int lo = 1, hi = 0x7fffffff, gbit = 0;
+    if (w[1] == "group") { if (!d->groups.count(w[2])) return fail(d, ERR_ARG, "Could not find set group ID"); gbit = d->groups[w[2]]; }
+    else { const std::string &r = w[2]; const size_t star = r.find('*');
       if (star == std::string::npos) { double a; rc = numeric(d, r, a); if (rc) return rc; lo = hi = (int)a; }
       else { lo = star ? atoi(r.substr(0, star).c_str()) : 1; hi = star + 1 < r.size() ? atoi(r.substr(star + 1).c_str()) : 0x7fffffff; } }
     const bool pend = d->uploaded;
-    std::vector<int> &tg = pend ? d->ptag : d->tag, &ty = pend ? d->ptype : d->type;
+    std::vector<int> &tg = pend ? d->ptag : d->tag, &ty = pend ? d->ptype : d->type, &mk = pend ? d->pmask : d->mask;
     std::vector<double> &ra = pend ? d->pradius : d->radius, &de = pend ? d->pdensity : d->density;
     bool any = false;
     for (size_t i = 0; i < tg.size(); i++) {
-      if (tg[i] < lo || tg[i] > hi) continue;
+      if (gbit ? !(mk[i] & gbit) : (tg[i] < lo || tg[i] > hi)) continue;
       any = true;
       for (size_t k = 3; k + 1 < w.size(); k += 2) {
         double val; rc = numeric(d, w[k + 1], val); if (rc) return rc;

@@ -236,6 +236,7 @@ struct dem_engine {
   // fused ghost push (fused_halo_setup): image table, block order, device parameter block; fz_on: the next launch_step uses it
   double cdf_user = 0.0;  // neigh_modify contact_distance_factor, 0 = not given
   int need_setup = 0;  // particles were inserted: the next dem_run needs a dem_setup first (lists, forces)
+  std::vector<std::string> xf_id; std::vector<XForce> xf;  // fix addforce / fix viscous (dem_set_extra_force)
   int ins_mass = 0;    // the upload kernels form the mass like fix insert/* does (set by dem_insert_step_end only)
   int ins_open = 0;    // dem_insert_step_begin has run: the timestep is half done
   DevBuf<unsigned long long> bondc;  // compute bond/counter: created, broken, scratch for the total
@@ -868,6 +869,23 @@ extern "C" int dem_set_gravity(dem_engine *e, double mag, const double dir[3])
   API_END
 }
 extern "C" int dem_set_freeze(dem_engine *e, int bit) { API_BEGIN e->freezebit = bit; API_END }
+// fix addforce (kind 0: constant fx fy fz) / fix viscous (kind 1: gamma) on a group; a fix id that exists is replaced, n < 0 removes it
+extern "C" int dem_set_extra_force(dem_engine *e, const char *id, int kind, int groupbit, const double *values, int n)
+{
+  API_BEGIN
+  if (!id || (kind != 0 && kind != 1)) dem_fail(e, DEM_ERR_ARG, "extra force: kind 0 (addforce) or 1 (viscous)");
+  size_t k = 0;
+  for (; k < e->xf_id.size(); k++) if (e->xf_id[k] == id) break;
+  if (n < 0) { if (k == e->xf_id.size()) dem_fail(e, DEM_ERR_ARG, "Could not find fix ID %s to delete", id); e->xf_id.erase(e->xf_id.begin() + k); e->xf.erase(e->xf.begin() + k); return DEM_OK; }
+  if (n != (kind == 0 ? 3 : 1) || !values) dem_fail(e, DEM_ERR_ARG, "extra force: addforce takes 3 values, viscous 1");
+  XForce X; X.kind = kind; X.bit = groupbit; X.v[0] = values[0]; X.v[1] = n > 1 ? values[1] : 0.0; X.v[2] = n > 2 ? values[2] : 0.0;
+  if (k == e->xf_id.size()) {
+    if (e->xf.size() >= DEM_MAXXF) dem_fail(e, DEM_ERR_UNSUPPORTED, "more than %d fix addforce / viscous", DEM_MAXXF);
+    e->xf_id.push_back(id); e->xf.push_back(X);
+  } else e->xf[k] = X;
+  e->forces_valid = 0;
+  API_END
+}
 extern "C" int dem_set_integrate(dem_engine *e, int bit) { API_BEGIN e->integbit = bit; API_END }
 
 // ------------------------------------------------------------------------------------------------
@@ -2019,6 +2037,7 @@ static StepP step_params(dem_engine *E, int mode)
   P.cutneighmax = E->cutneighmax;
   for (int d = 0; d < 3; d++) P.g[d] = E->g[d];
   P.have_g = E->have_g; P.have_pair = E->have_pair; P.freezebit = E->freezebit; P.integbit = E->integbit;
+  P.nxf = (int)E->xf.size(); for (int q = 0; q < P.nxf; q++) P.xf[q] = E->xf[q];
   P.mode = mode; P.debug = E->opt.count("debug") ? (int)E->opt["debug"] : 0; P.flag = flag_slot(E, E->fslot); P.gate = E->gate; P.gate_mask = E->gate_mask; P.ncontact = nullptr;
   P.bondc = (E->have_pair && E->pm.cohesion == C_BOND) ? E->bondc.p : nullptr;
   P.img = nullptr; P.img_first = nullptr; P.img_tab = nullptr;
@@ -2056,7 +2075,7 @@ static void launch_step_t(dem_engine *E, const StepP &P)
   }
   // the reference's default sub-model settings get the specialised instantiation (see pair_item)
   const ModelP &m = E->pm;
-  const bool std_deck = E->have_pair && m.tangential && m.tdamp && !m.limitForce && !m.torsion && !m.cdtnl2 && P.nktv2p == 1.0 && P.cdf == 1.0 && !P.cout && !P.debug &&
+  const bool std_deck = E->have_pair && m.tangential && m.tdamp && !m.limitForce && !m.torsion && !m.cdtnl2 && P.nktv2p == 1.0 && P.cdf == 1.0 && !P.cout && !P.debug && !P.nxf &&
                         !(E->opt.count("generic_step") && E->opt["generic_step"] != 0);
   if (std_deck) {
     if (E->ntypes == 1) k_step<N, R, true, false, true><<<GRID(P.nlocal, 128), 128, 0, E->stream>>>(P);
@@ -2083,6 +2102,7 @@ static void launch_step(dem_engine *E, int mode, bool timed)
   if (P.nwc && have_mesh_walls(E)) { MeshP M = mesh_params(E); mesh_launch_step(P, M, E->stream); E->launches++; }
   const int key = (E->have_pair ? E->pm.normal : N_HERTZ) * 4 + (E->have_pair ? E->pm.rolling : R_OFF);
   if (E->ls[E->lcur].fmt == 1) {
+    if (P.nxf) dem_fail(E, DEM_ERR_UNSUPPORTED, "fix addforce / viscous with option owner_list");
     E->serial = next_serial(); P.serial = (double)E->serial;
     {
       switch (key) {

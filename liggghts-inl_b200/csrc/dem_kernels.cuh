@@ -305,6 +305,8 @@ __device__ __forceinline__ void prefetch_contact(const StepP &P, int i, unsigned
 // owner epilogue of a step: gravity, primitive/mesh wall force of the pre-pass, freeze, (optional) force output,
 // final_integrate(n) + initial_integrate(n+1), rebuild trigger.  fix_gravity.cpp:331-339, fix_freeze.cpp:132-144,
 // fix_nve_sphere.cpp:134-244, neighbor.cpp:1425-1466
+// XF: the kernel also applies the fix addforce / fix viscous list (never compiled into the specialised hot kernel)
+template <bool XF = false>
 __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const double4 &xi, const double4 &vi, const double4 &wi, double *F, double *T)
 {
   bool trig = false;
@@ -315,6 +317,14 @@ __device__ __forceinline__ bool step_epilogue(const StepP &P, int i, const doubl
     if (widx) {
 #pragma unroll
       for (int d = 0; d < 3; d++) { F[d] += P.fw[(size_t)d * P.nwcap + widx - 1]; T[d] += P.fw[(size_t)(3 + d) * P.nwcap + widx - 1]; }
+    }
+  }
+  if (XF) {
+    for (int q = 0; q < P.nxf; q++) {
+      const XForce &X = P.xf[q];
+      if (!(imask & X.bit)) continue;
+      if (X.kind == 0) { F[0] += X.v[0]; F[1] += X.v[1]; F[2] += X.v[2]; }
+      else { F[0] -= X.v[0] * vi.x; F[1] -= X.v[0] * vi.y; F[2] -= X.v[0] * vi.z; }
     }
   }
   if (imask & P.freezebit) { F[0] = F[1] = F[2] = 0.0; T[0] = T[1] = T[2] = 0.0; }
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(128, DEM_STEP_MINBLOCKS) k_step(const StepP P)
   // (3) owner epilogue
   if (active) {
     if (P.have_pair) { const int nh = s_nh[tid]; if (nh != nh0) P.numneigh[i] = nn | (nh << 16); }
-    trig = step_epilogue(P, i, rec_get(s_rec, 0, tid), rec_get(s_rec, 1, tid), rec_get(s_rec, 2, tid), F, T);
+    trig = step_epilogue<!STD>(P, i, rec_get(s_rec, 0, tid), rec_get(s_rec, 1, tid), rec_get(s_rec, 2, tid), F, T);
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }
@@ -687,7 +697,7 @@ __global__ void __launch_bounds__(128, DEM_BOND_MINBLOCKS) k_step_bond(const Ste
     }
     if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
     (void)itype; (void)imask;
-    trig = step_epilogue(P, i, xi, vi, wi, F, T);
+    trig = step_epilogue<true>(P, i, xi, vi, wi, F, T);
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }
@@ -767,7 +777,7 @@ __global__ void __launch_bounds__(128, 3) k_step_hyst(const StepP P)
       }
     }
     if (nh != nh0) P.numneigh[i] = nn | (nh << 16);
-    trig = step_epilogue(P, i, xi, vi, wi, F, T);
+    trig = step_epilogue<true>(P, i, xi, vi, wi, F, T);
   }
   if (__any_sync(0xffffffffu, trig) && (threadIdx.x & 31) == 0) *((volatile int *)P.flag) = 1;
 }

@@ -70,6 +70,11 @@ struct ImgP {
   double prd[3];
 };
 
+// per-particle forces of two more post_force fixes, applied in the order of their definition after walls and gravity:
+// kind 0 fix addforce (fix_addforce.cpp:234-260, constant components), kind 1 fix viscous (fix_viscous.cpp:100-125, one gamma)
+#define DEM_MAXXF 4
+struct XForce { int kind, bit; double v[3]; };
+
 struct StepP {
   int nlocal, nall, cap, maxk;
   int lcap;  // row stride of the ELLPACK arrays (nbr, hist)
@@ -114,6 +119,7 @@ struct StepP {
   // (slot | target << 28, shift code, next entry or -1, 0)) and this launch's buffer parity
   const ImgP *img; const int *img_first; const int4 *img_tab;
   int img_par;
+  int nxf; XForce xf[DEM_MAXXF];
 };
 
 }  // namespace dem

@@ -10,7 +10,7 @@ ABI_SYMBOLS = [
     "dem_create", "dem_destroy", "dem_nccl_unique_id", "dem_decomposition", "dem_last_error", "dem_version", "dem_set_option", "dem_set_units", "dem_set_box",
     "dem_set_ntypes", "dem_set_processors", "dem_set_neighbor", "dem_set_timestep", "dem_set_contact_distance_factor", "dem_set_property",
     "dem_set_pair_style", "dem_add_wall_primitive", "dem_set_gravity", "dem_set_freeze",
-    "dem_set_integrate", "dem_upload_particles", "dem_insert_particles", "dem_insert_step_begin", "dem_insert_step_end", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
+    "dem_set_integrate", "dem_set_extra_force", "dem_upload_particles", "dem_insert_particles", "dem_insert_step_begin", "dem_insert_step_end", "dem_setup", "dem_run", "dem_nlocal", "dem_download",
     "dem_pair_count", "dem_download_pairs", "dem_download_wall_history", "dem_get_stats",
     "dem_add_mesh", "dem_move_mesh", "dem_add_wall_mesh", "dem_download_mesh", "dem_mesh_force", "dem_mesh_contact_count", "dem_download_mesh_contacts",
     "dem_bond_counter", "dem_contact_count", "dem_download_contacts", "dem_trim_memory", "dem_brick_layout", "dem_deck_open", "dem_deck_close", "dem_deck_command", "dem_deck_file", "dem_deck_last_error", "dem_deck_warnings", "dem_deck_ntimestep", "dem_deck_output", "dem_deck_screen",
@@ -216,6 +216,14 @@ class Engine:
                 np.ascontiguousarray(radius, np.float64), np.ascontiguousarray(density, np.float64)]
         ptr = [a.ctypes.data if a is not None else None for a in keep]
         self._call("insert_particles", [C.c_long] + [C.c_void_p] * 8, n, *ptr)
+
+    def extra_force(self, fix_id, kind, groupbit, values):
+        """fix addforce (kind 0: fx fy fz) / fix viscous (kind 1: gamma) on a group; values=None removes the fix"""
+        if values is None:
+            self._call("set_extra_force", [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int], fix_id.encode(), int(kind), int(groupbit), None, -1)
+            return
+        v = np.ascontiguousarray(values, np.float64)
+        self._call("set_extra_force", [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int], fix_id.encode(), int(kind), int(groupbit), v.ctypes.data, len(v))
 
     def insert_step_begin(self):
         """first half of the timestep in which fix insert/* creates particles (fix_insert.cpp:672-905): first half step of the

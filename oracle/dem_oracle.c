@@ -105,6 +105,7 @@ typedef struct orc_engine {
   long *first; int *numneigh; int *jlist; signed char *jshift; int *flag; double *hist; long npairs, cap;
   long bond_created, bond_broken; /* compute bond/counter (compute_bond_counter.cpp:140-156), linear bond model only */
   long ntimestep, nbuilds; int ago; int setup_done;
+  int nxf; struct { char id[64]; int kind, bit; double v[3]; } xf[4]; /* fix addforce (kind 0) / fix viscous (kind 1), in the order of definition */
   int ins_mass, ins_open; /* orc_insert_step_*: mass as fix insert forms it / the timestep is half done */
 } orc_engine;
 
@@ -309,6 +310,15 @@ int orc_set_gravity(orc_engine *e, double mag, const double dir[3])
   e->have_gravity = 1; return 0;
 }
 int orc_set_freeze(orc_engine *e, int bit) { e->freezebit = bit; return 0; }
+int orc_set_extra_force(orc_engine *e, const char *id, int kind, int bit, const double *v, int n)
+{
+  int k = 0; for (; k < e->nxf; k++) if (!strcmp(e->xf[k].id, id)) break;
+  if (n < 0) { if (k == e->nxf) return fail(e, "Could not find fix ID to delete"); for (; k + 1 < e->nxf; k++) e->xf[k] = e->xf[k + 1]; e->nxf--; return 0; }
+  if ((kind != 0 && kind != 1) || n != (kind == 0 ? 3 : 1)) return fail(e, "extra force arguments");
+  if (k == e->nxf) { if (e->nxf >= 4) return fail(e, "more than 4 fix addforce / viscous"); e->nxf++; snprintf(e->xf[k].id, sizeof e->xf[k].id, "%s", id); }
+  e->xf[k].kind = kind; e->xf[k].bit = bit; e->xf[k].v[0] = v[0]; e->xf[k].v[1] = n > 1 ? v[1] : 0.0; e->xf[k].v[2] = n > 2 ? v[2] : 0.0;
+  return 0;
+}
 int orc_set_integrate(orc_engine *e, int bit) { e->integbit = bit; return 0; }
 
 /* mass of a sphere created by fix insert/*: fix_template_sphere.cpp:349-350 (volume_ins = r*r*r*4.*M_PI/3., mass_ins = density_ins*volume_ins),
@@ -1605,6 +1615,10 @@ static void compute_forces(orc_engine *e, int shearupdate)
     const double m = e->rmass[i]; e->f[3 * i] += m * e->g[0]; e->f[3 * i + 1] += m * e->g[1]; e->f[3 * i + 2] += m * e->g[2]; }
   for (int w = 0; w < e->nwalls; w++) wall_compute(e, &e->walls[w], shearupdate);
   for (int w = 0; w < e->nmwalls; w++) mesh_wall_compute(e, &e->mwalls[w], shearupdate);
+  for (int q = 0; q < e->nxf; q++) for (long i = 0; i < e->n; i++) if (e->mask[i] & e->xf[q].bit) {
+    if (e->xf[q].kind == 0) for (int d = 0; d < 3; d++) e->f[3 * i + d] += e->xf[q].v[d]; /* fix_addforce.cpp:234-260 (constant components) */
+    else { const double drag = e->xf[q].v[0]; for (int d = 0; d < 3; d++) e->f[3 * i + d] -= drag * e->v[3 * i + d]; } /* fix_viscous.cpp:100-125 */
+  }
   if (e->freezebit) for (long i = 0; i < e->n; i++) if (e->mask[i] & e->freezebit) for (int d = 0; d < 3; d++) { e->f[3 * i + d] = 0.0; e->torque[3 * i + d] = 0.0; } /* fix_freeze.cpp:132-144 */
 }
 

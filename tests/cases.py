@@ -3,6 +3,7 @@ engine.  A case is a plain dict; `to_deck` renders it as a LIGGGHTS input script
 file for the unmodified reference, `apply` replays it on an Engine-like object (the CUDA
 engine or, in tests only, the CPU oracle) through the C ABI."""
 import os
+import re
 import numpy as np
 
 SEED = 20261017
@@ -408,3 +409,23 @@ def snapshot(eng, c):
 #     already there, vel uniform, omega constant
 #  c: cylinder along x, number based, all_in no, mass_in_region every 300 steps, vel gaussian, maxattempt
 INSERT_DECKS = {"insert_pack_a": [1, 2, 200, 1000], "insert_pack_b": [1, 400, 401, 801, 2500], "insert_pack_c": [1, 301, 601, 2000]}
+
+# the reference's own INL example decks that the deck front end runs unchanged (read from the reference tree where they lie,
+# build container only; only the length of their `run` is cut): path under examples/LIGGGHTS -> steps.  Goldens:
+# tests/golden/inl_examples.npz (make_golden_insert.py examples)
+INL_EXAMPLES = "/root/reference/examples/LIGGGHTS"
+INL_EXAMPLE_DECKS = {
+    "INL/cohesive_bond/chain_bending_test/in.chain_bending.lmp": 100000,  # (its full length: linear bond, fix addforce, fix viscous, fix freeze)
+    "INL/cohesive_bond_nonlinear_compression/chain_bending_mm_1/in.chain_bending.lmp": 200000,
+    "INL/cohesive_bond_nonlinear_compression/chain_bending_mm_2/in.chain_bending.lmp": 200000,
+    "INL/cohesive_bond_nonlinear_compression/chain_bending_um_1/in.chain_bending.lmp": 200000,
+    "INL/cohesive_bond_nonlinear_compression/chain_bending_um_2/in.chain_bending.lmp": 200000,
+}
+
+
+def example_deck_text(rel, nsteps):
+    """an example deck of the reference with its run length replaced and its dump lines dropped (no files into the read-only tree)"""
+    import re
+    text = re.sub(r"&[ \t]*\n", " ", open(os.path.join(INL_EXAMPLES, rel)).read())
+    text = re.sub(r"^(run\s+)(\d+)", lambda m: m.group(1) + str(nsteps), text, flags=re.M)
+    return "\n".join(l for l in text.splitlines() if not l.strip().startswith(("dump", "fix\t\tprint", "fix print")))

@@ -56,12 +56,29 @@ def tutorial():
     print("tutorial_t01a", int(out["s1_n"]), flush=True)
 
 
+def example(rel):
+    r = ref_driver.Ref()
+    r.cmd(cases.example_deck_text(rel, cases.INL_EXAMPLE_DECKS[rel]))
+    a = r.atoms()
+    path = os.path.join(HERE, "inl_examples.npz")
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    key = rel.replace("/", "|")
+    for k in ("tag", "x", "v", "omega", "f", "torque", "radius", "rmass"):
+        out[key + ":" + k] = a[k]
+    np.savez_compressed(path, **out)
+    print(rel, len(a["tag"]), flush=True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tutorial":
         tutorial()
+    elif len(sys.argv) > 2 and sys.argv[1] == "example":
+        example(sys.argv[2])
     elif len(sys.argv) > 1:
         one(sys.argv[1], cases.INSERT_DECKS[sys.argv[1]])
     else:  # (the reference registers its styles in static tables: one instance per process)
         import subprocess
         for name in list(cases.INSERT_DECKS) + ["tutorial"]:
             subprocess.run([sys.executable, os.path.abspath(__file__), name], check=True)
+        for rel in cases.INL_EXAMPLE_DECKS:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "example", rel], check=True)
