@@ -31,6 +31,8 @@ def build(force=False, verbose=False, out=OUT):
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
         return out
     os.makedirs(OBJDIR, exist_ok=True)
+    import time
+    t0 = time.time()  # (a source edited while the compilers run must make the next call build again: the library is stamped with the start time)
     procs, objs = [], []
     for src, extra in UNITS:
         obj = os.path.join(OBJDIR, os.path.basename(out) + "." + src.replace(".cu", ".o").replace(".cpp", ".o"))
@@ -45,6 +47,7 @@ def build(force=False, verbose=False, out=OUT):
         if verbose:
             print(se)
     _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", out] + objs, verbose)
+    os.utime(out, (t0, t0))
     if out == OUT:  # command-line driver `lmp_b200 -in deck` (the reference's lmp_<machine>), linked against the library next to it
         _run(["g++", "-O2", "-std=c++17", "-o", os.path.join(HERE, "lmp_b200"), os.path.join(CSRC, "lmp_b200_main.cpp"),
               "-L" + HERE, "-ldem_b200", "-Wl,-rpath,$ORIGIN"], verbose)

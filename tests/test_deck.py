@@ -240,6 +240,45 @@ def test_chain_deck_addforce_viscous_velocity_on_engine_matches_oracle(tmp_path)
     assert errs["x"] <= 1e-3, errs
 
 
+def test_insertion_commands_error_classes():
+    """argument errors carry the reference's message text (fix_insert.cpp / fix_insert_pack.cpp / fix_template_sphere.cpp /
+    fix_particledistribution_discrete.cpp `error->fix_error`), requests outside the path are DEM_ERR_UNSUPPORTED"""
+    import dem_b200
+    eng, deck = oracle_deck()
+    for line in ("units si", "boundary f f f", "region dom block 0 1 0 1 0 1 units box", "create_box 1 dom",
+                 "region cyl cylinder z 0.5 0.5 0.2 0.1 0.9 units box", "region ball sphere 0.5 0.5 0.5 0.2 units box"):
+        deck.command(line)
+    bad = [
+        (r"\(-2\).*prime numbers > 10000", "fix t all particletemplate/sphere 1 atom_type 1 density constant 2500 radius constant 0.01"),
+        (r"\(-1\).*have to define 'density'", "fix t all particletemplate/sphere 15485863 atom_type 1 radius constant 0.01"),
+        (r"\(-1\).*invalid radius random style", "fix t all particletemplate/sphere 15485863 atom_type 1 density constant 2500 radius uniform 0.01 0.02"),
+        (r"\(-2\).*outside the hot-path scope", "fix t all particletemplate/multisphere 15485863 atom_type 1 density constant 2500 nspheres 2"),
+        (r"\(-1\).*invalid ID for fix particletemplate", "fix pdd all particledistribution/discrete 15485867 1 nope 1.0"),
+    ]
+    for pat, line in bad:
+        with pytest.raises(dem_b200.DemError, match=pat):
+            deck.command(line)
+    deck.command("fix t all particletemplate/sphere 15485863 atom_type 1 density constant 2500 radius constant 0.01")
+    deck.command("fix pdd all particledistribution/discrete 15485867 1 t 1.0")
+    bad = [
+        (r"\(-1\).*# of templates does not match", "fix p2 all particledistribution/discrete 32452843 2 t 1.0"),
+        (r"\(-1\).*expecting keyword 'seed'", "fix ins all insert/pack distributiontemplate pdd region cyl insert_every once particles_in_region 5"),
+        (r"\(-1\).*must define an insertion region", "fix ins all insert/pack seed 32452843 distributiontemplate pdd insert_every once particles_in_region 5"),
+        (r"\(-1\).*must define 'insert_every'", "fix ins all insert/pack seed 32452843 distributiontemplate pdd region cyl particles_in_region 5"),
+        (r"\(-1\).*must define exactly one keyword", "fix ins all insert/pack seed 32452843 distributiontemplate pdd region cyl insert_every once particles_in_region 5 volumefraction_region 0.1"),
+        (r"\(-1\).*ntry_mc must be > 1000", "fix ins all insert/pack seed 32452843 distributiontemplate pdd region cyl insert_every once particles_in_region 5 ntry_mc 10"),
+        (r"\(-1\).*region ID does not exist", "fix ins all insert/pack seed 32452843 distributiontemplate pdd region nowhere insert_every once particles_in_region 5"),
+        (r"\(-2\).*neither a block nor a cylinder", "fix ins all insert/pack seed 32452843 distributiontemplate pdd region ball insert_every once particles_in_region 5"),
+        (r"\(-2\).*outside the hot-path scope", "fix ins all insert/stream seed 32452843 distributiontemplate pdd nparticles 10"),
+        (r"\(-2\).*outside the hot-path scope", "fix f all addforce 1.0 0.0 v_fz"),
+        (r"\(-1\).*Illegal fix viscous command", "fix v all viscous"),
+    ]
+    for pat, line in bad:
+        with pytest.raises(dem_b200.DemError, match=pat):
+            deck.command(line)
+    deck.close(); eng.close()
+
+
 def test_deck_mesh_load_transforms_and_errors(tmp_path):
     """`fix mesh/surface ... move/rotate/scale` act on the nodes like FixMesh::moveMesh/rotateMesh/scaleMesh; error classes"""
     import dem_b200
