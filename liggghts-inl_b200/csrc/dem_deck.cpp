@@ -1090,6 +1090,8 @@ int cmd_group(Deck *d, const std::vector<std::string> &w)
   return OK;
 }
 
+int run_file(Deck *d, const std::string &path);
+
 int one(Deck *d, const std::string &raw)
 {
   std::string line = raw;
@@ -1208,6 +1210,16 @@ int one(Deck *d, const std::string &raw)
     d->have_pair = true; return OK;
   }
   if (c == "fix") return cmd_fix(d, w);
+  if (c == "include") {  // Input::include (input.cpp:640-670): the named script runs in place; relative to the working directory like
+    // every file name of a deck -- here: to the directory of the deck that is being read
+    if (w.size() != 2) return fail(d, ERR_ARG, "Illegal include command");
+    std::string path = w[1];
+    if (!path.empty() && path[0] != '/' && !d->dir.empty()) path = d->dir + "/" + path;
+    const std::string keep = d->dir;
+    rc = run_file(d, path);
+    d->dir = keep;
+    return rc;
+  }
   if (c == "unfix") {
     if (w.size() != 2) return fail(d, ERR_ARG, "Illegal unfix command");
     if (d->ignored_fixes.erase(w[1])) return OK;
@@ -1356,6 +1368,25 @@ int one(Deck *d, const std::string &raw)
   return fail(d, ERR_UNSUPPORTED, "command '%s' is outside the hot-path scope", c.c_str());
 }
 
+// a whole input script, '&' continuation lines joined (Input::file input.cpp:160-250); stops at the first error.  File names
+// inside the script stay relative to the directory of the outermost script (the reference's working directory).
+int run_file(Deck *d, const std::string &path)
+{
+  std::ifstream f(path);
+  if (!f.good()) return fail(d, ERR_ARG, "Cannot open input script %s", path.c_str());
+  std::string line, acc; int lineno = 0, rc = OK;
+  while (std::getline(f, line)) {
+    lineno++;
+    size_t end = line.find_last_not_of(" \t\r\n");
+    if (end != std::string::npos && line[end] == '&') { acc += line.substr(0, end) + " "; continue; }
+    acc += line;
+    try { rc = one(d, acc); } catch (const std::exception &ex) { d->err = ex.what(); rc = ERR_ARG; }
+    if (rc != OK) { char where[64]; snprintf(where, sizeof where, " (line %d)", lineno); d->err += where; break; }
+    acc.clear();
+  }
+  return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1387,21 +1418,10 @@ int DECK(command)(DECK(handle) *h, const char *line)
 int DECK(file)(DECK(handle) *h, const char *path)
 {
   if (!h || !path) return ERR_ARG;
-  std::ifstream f(path);
-  if (!f.good()) { h->d.err = std::string("Cannot open input script ") + path; return ERR_ARG; }
   const std::string p(path); const size_t sl = p.rfind('/');
   const std::string olddir = h->d.dir;
   h->d.dir = sl == std::string::npos ? "" : p.substr(0, sl);
-  std::string line, acc; int lineno = 0, rc = OK;
-  while (std::getline(f, line)) {
-    lineno++;
-    size_t end = line.find_last_not_of(" \t\r\n");
-    if (end != std::string::npos && line[end] == '&') { acc += line.substr(0, end) + " "; continue; }
-    acc += line;
-    rc = DECK(command)(h, acc.c_str());
-    if (rc != OK) { char where[64]; snprintf(where, sizeof where, " (line %d)", lineno); h->d.err += where; break; }
-    acc.clear();
-  }
+  const int rc = run_file(&h->d, p);
   h->d.dir = olddir;
   return rc;
 }

@@ -21,6 +21,12 @@ def oracle_deck():
 def write_deck(c, tmp_path, lines_extra=()):
     deck, data = cases.to_deck(c, str(tmp_path / "case.data"))
     (tmp_path / "case.data").write_text(data)
+    # the material lines live in a second script (`include`, Input::include)
+    mat = [l for l in deck.splitlines() if " property/global " in l]
+    if mat:
+        (tmp_path / "in.materials").write_text("\n".join(mat) + "\n")
+        first = deck.index(mat[0])
+        deck = deck[:first] + "include in.materials\n" + "\n".join(l for l in deck[first:].splitlines() if l not in mat)
     # exercise the file reader: a comment, a continuation line and a variable
     deck = deck.replace("timestep ", "variable dt equal ").replace("fix integr all nve/sphere", "fix integr all &\n   nve/sphere   # integrator")
     deck += "\ntimestep ${dt}\nthermo 1000\ncompute 1 all erotate\n" + "\n".join(lines_extra) + "\n"
