@@ -117,6 +117,8 @@ struct Deck {
     double region_volume = 0.0, region_volume_local = 0.0, insertion_ratio = 0.0;
     long ninserted = 0; double massinserted = 0.0;
   };
+  // lattice (lattice.cpp:60-300): styles sc | bcc | fcc with the default orientation; scale = lattice constant; optional origin
+  struct Lattice { bool defined = false; double scale = 0.0, origin[3] = {0, 0, 0}; std::vector<double> basis; } lattice;
   std::map<std::string, Template> templates;
   std::map<std::string, Distribution> distributions;
   std::vector<Insert> inserts;  // in the order of definition (== the order Modify calls pre_exchange)
@@ -124,6 +126,7 @@ struct Deck {
   std::set<std::string> opaque_regions;  // regions of other shapes: known by name only
   std::map<std::string, int> groups;  // name -> mask bit
   std::map<std::string, std::string> ignored_fixes;
+  bool have_freeze = false;
   std::set<std::string> extra_fixes;  // fix addforce / viscous ids (dem_set_extra_force)
   // box / particles held until the first `run`
   bool have_box = false, box_sent = false, uploaded = false, newton_off = false, have_pair = false;
@@ -844,6 +847,9 @@ int cmd_fix(Deck *d, const std::vector<std::string> &w)
   if (!d->groups.count(group)) return fail(d, ERR_ARG, "Could not find fix group ID %s", group.c_str());
   const int bit = d->groups[group];
   int rc = send_box(d); if (rc) return rc;
+  // the reference applies its post_force fixes in the order of their definition; here fix freeze always acts last
+  if (d->have_freeze && (style == "gravity" || style == "addforce" || style == "viscous" || style == "wall/gran"))
+    d->warnings += "fix " + style + " defined after fix freeze: the reference would let it act on the frozen group, here frozen particles stay force free\n";
   if (style == "property/global") {  // fix_property_global.cpp:60-200
     if (w.size() < 7) return fail(d, ERR_ARG, "Illegal fix property/global command, not enough arguments");
     const std::string &name = w[4], &kind = w[5];
@@ -926,7 +932,7 @@ int cmd_fix(Deck *d, const std::vector<std::string> &w)
     TRY(API(move_mesh)(d->e, w[5].c_str(), (int)a.size(), a.data()));
     return OK;
   }
-  if (style == "freeze") { TRY(API(set_freeze)(d->e, bit)); return OK; }
+  if (style == "freeze") { TRY(API(set_freeze)(d->e, bit)); d->have_freeze = true; return OK; }
   if (style == "addforce") {  // fix_addforce.cpp:60-130 (constant components; variables / region / energy options are not on the path)
     if (w.size() != 7) return fail(d, w.size() < 7 ? ERR_ARG : ERR_UNSUPPORTED, w.size() < 7 ? "Illegal fix addforce command" : "fix addforce options are outside the hot-path scope");
     double f[3]; for (int k = 0; k < 3; k++) { if (w[4 + k].compare(0, 2, "v_") == 0) return fail(d, ERR_UNSUPPORTED, "fix addforce with a variable is outside the hot-path scope"); rc = numeric(d, w[4 + k], f[k]); if (rc) return rc; }
@@ -1075,6 +1081,26 @@ int cmd_group(Deck *d, const std::vector<std::string> &w)
   int bit;
   if (d->groups.count(w[1])) bit = d->groups[w[1]];
   else { if (d->groups.size() >= 31) return fail(d, ERR_ARG, "Too many groups"); bit = 1 << (int)d->groups.size(); d->groups[w[1]] = bit; }
+  if (w[2] == "region") {  // group.cpp:150-165: the atoms that are inside the region now
+    if (d->opaque_regions.count(w[3])) return fail(d, ERR_UNSUPPORTED, "group region with a region that is neither a block nor a cylinder is outside the hot-path scope");
+    if (!d->regions.count(w[3])) return fail(d, ERR_ARG, "Group region ID does not exist");
+    const Deck::Region &R = d->regions[w[3]];
+    for (size_t i = 0; i < d->tag.size(); i++) if (region_inside(R, d->x[3 * i], d->x[3 * i + 1], d->x[3 * i + 2])) d->mask[i] |= bit;
+    return OK;
+  }
+  if (w[2] == "union" || w[2] == "subtract" || w[2] == "intersect") {  // group.cpp:330-460
+    std::vector<int> bits;
+    for (size_t k = 3; k < w.size(); k++) { if (!d->groups.count(w[k])) return fail(d, ERR_ARG, "Group ID does not exist"); bits.push_back(d->groups[w[k]]); }
+    if (w[2] != "union" && bits.size() < 2) return fail(d, ERR_ARG, "Illegal group command");
+    for (size_t i = 0; i < d->tag.size(); i++) {
+      bool in;
+      if (w[2] == "union") { in = false; for (int b : bits) in |= (d->mask[i] & b) != 0; }
+      else if (w[2] == "subtract") { in = (d->mask[i] & bits[0]) != 0; for (size_t q = 1; q < bits.size(); q++) if (d->mask[i] & bits[q]) in = false; }
+      else { in = true; for (int b : bits) if (!(d->mask[i] & b)) in = false; }
+      if (in) d->mask[i] |= bit;
+    }
+    return OK;
+  }
   if (w[2] != "id" && w[2] != "type") return fail(d, ERR_UNSUPPORTED, "group style '%s' is outside the hot-path scope", w[2].c_str());
   std::vector<std::pair<int, int>> ranges;
   for (size_t k = 3; k < w.size(); k++) {
@@ -1161,7 +1187,15 @@ int one(Deck *d, const std::string &raw)
       d->opaque_regions.insert(w[1]); d->warnings += "region " + w[1] + " (" + w[2] + ") kept as a name only\n"; return OK;
     } else {
       if (w.size() < 9) return fail(d, ERR_ARG, "Illegal region command");
-      for (int k = 0; k < 3; k++) { rc = numeric(d, w[3 + 2 * k], R.lo[k]); if (rc) return rc; rc = numeric(d, w[4 + 2 * k], R.hi[k]); if (rc) return rc; R.ext_lo[k] = R.lo[k]; R.ext_hi[k] = R.hi[k]; }
+      // INF = -/+ 1e20, EDGE = the box bound (region_block.cpp:70-230)
+      auto bound = [&](const std::string &t, int k, bool hi, double &out) -> int {
+        if (t == "INF" || t == "EDGE") {
+          if (!d->have_box) return fail(d, ERR_ARG, "Cannot use region INF or EDGE when box does not exist");
+          out = t == "INF" ? (hi ? 1.0e20 : -1.0e20) : (hi ? d->hi[k] : d->lo[k]); return OK;
+        }
+        return numeric(d, t, out);
+      };
+      for (int k = 0; k < 3; k++) { rc = bound(w[3 + 2 * k], k, false, R.lo[k]); if (rc) return rc; rc = bound(w[4 + 2 * k], k, true, R.hi[k]); if (rc) return rc; R.ext_lo[k] = R.lo[k]; R.ext_hi[k] = R.hi[k]; }
       if (R.lo[0] > R.hi[0] || R.lo[1] > R.hi[1] || R.lo[2] > R.hi[2]) return fail(d, ERR_ARG, "Illegal region block command");
     }
     for (size_t k = opt; k < w.size(); k += 2) {  // Region::options (region.cpp:380-460)
@@ -1266,8 +1300,69 @@ int one(Deck *d, const std::string &raw)
     }
     return OK;
   }
+  if (c == "lattice") {  // lattice.cpp:60-300
+    if (w.size() < 2) return fail(d, ERR_ARG, "Illegal lattice command");
+    Deck::Lattice L;
+    if (w[1] == "none") { d->lattice = L; return OK; }
+    if (w.size() < 3) return fail(d, ERR_ARG, "Illegal lattice command");
+    if (w[1] == "sc") L.basis = {0., 0., 0.};
+    else if (w[1] == "bcc") L.basis = {0., 0., 0., .5, .5, .5};
+    else if (w[1] == "fcc") L.basis = {0., 0., 0., .5, .5, 0., .5, 0., .5, 0., .5, .5};
+    else return fail(d, ERR_UNSUPPORTED, "lattice style '%s' is outside the hot-path scope (sc, bcc, fcc)", w[1].c_str());
+    rc = numeric(d, w[2], L.scale); if (rc) return rc;
+    if (L.scale <= 0.0) return fail(d, ERR_ARG, "Illegal lattice command");
+    for (size_t k = 3; k < w.size();) {
+      if (w[k] == "origin" && k + 3 < w.size()) {
+        for (int q = 0; q < 3; q++) { rc = numeric(d, w[k + 1 + q], L.origin[q]); if (rc) return rc; if (L.origin[q] < 0.0 || L.origin[q] >= 1.0) return fail(d, ERR_ARG, "Illegal lattice command"); }
+        k += 4;
+      } else return fail(d, ERR_UNSUPPORTED, "lattice keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    L.defined = true; d->lattice = L; return OK;
+  }
+  if (c == "create_atoms" && w.size() >= 3 && (w[2] == "box" || w[2] == "region")) {  // create_atoms.cpp:100-300, add_lattice :492-602
+    if (!d->have_box) return fail(d, ERR_STATE, "Create_atoms command before simulation box is defined");
+    if (!d->lattice.defined) return fail(d, ERR_ARG, "Cannot create atoms with undefined lattice");
+    double t; rc = numeric(d, w[1], t); if (rc) return rc;
+    if ((int)t < 1 || (int)t > d->ntypes) return fail(d, ERR_ARG, "Invalid atom type in create_atoms command");
+    const Deck::Region *R = nullptr;
+    size_t opt = 3;
+    if (w[2] == "region") {
+      if (w.size() < 4) return fail(d, ERR_ARG, "Illegal create_atoms command");
+      if (d->opaque_regions.count(w[3])) return fail(d, ERR_UNSUPPORTED, "create_atoms in a region that is neither a block nor a cylinder is outside the hot-path scope");
+      if (!d->regions.count(w[3])) return fail(d, ERR_ARG, "Create_atoms region ID does not exist");
+      R = &d->regions[w[3]]; opt = 4;
+    }
+    for (size_t k = opt; k < w.size(); k += 2) {
+      if (w[k] == "units" && k + 1 < w.size()) continue;  // (only the style single reads it)
+      return fail(d, ERR_UNSUPPORTED, "create_atoms keyword '%s' is outside the hot-path scope", w[k].c_str());
+    }
+    // my sub-box = the whole box; a periodic dimension is shifted down by EPSILON of its length so that exactly one of two
+    // images on the boundary is created (create_atoms.cpp:205-262)
+    double sublo[3], subhi[3];
+    for (int k = 0; k < 3; k++) {
+      sublo[k] = d->lo[k]; subhi[k] = d->hi[k];
+      if (d->periodic[k]) { const double eps = (d->hi[k] - d->lo[k]) * 1.0e-6; sublo[k] -= eps; subhi[k] -= 2.0 * eps; }
+    }
+    const Deck::Lattice &L = d->lattice;
+    int lo[3], hi[3];  // cells that can reach the box (the reference's bounds are tighter; cells outside create nothing)
+    for (int k = 0; k < 3; k++) { lo[k] = (int)std::floor(d->lo[k] / L.scale) - 2; hi[k] = (int)std::ceil(d->hi[k] / L.scale) + 2; }
+    const bool pend = d->uploaded;
+    for (int v : d->tag) d->maxtag = std::max(d->maxtag, v);
+    const int nb = (int)L.basis.size() / 3;
+    for (int k = lo[2]; k <= hi[2]; k++) for (int j = lo[1]; j <= hi[1]; j++) for (int i = lo[0]; i <= hi[0]; i++) for (int m = 0; m < nb; m++) {
+      double x[3] = {i + L.basis[3 * m], j + L.basis[3 * m + 1], k + L.basis[3 * m + 2]};
+      for (int q = 0; q < 3; q++) { x[q] *= L.scale; x[q] = x[q] + L.scale * L.origin[q]; }  // Lattice::lattice2box with unit primitive / rotation matrices
+      if (R && !region_inside(*R, x[0], x[1], x[2])) continue;
+      if (x[0] < sublo[0] || x[0] >= subhi[0] || x[1] < sublo[1] || x[1] >= subhi[1] || x[2] < sublo[2] || x[2] >= subhi[2]) continue;
+      const int id = ++d->maxtag;
+      (pend ? d->ptag : d->tag).push_back(id); (pend ? d->ptype : d->type).push_back((int)t); (pend ? d->pmask : d->mask).push_back(1);
+      for (int q = 0; q < 3; q++) { (pend ? d->px : d->x).push_back(x[q]); (pend ? d->pv : d->v).push_back(0.0); (pend ? d->pomega : d->omega).push_back(0.0); }
+      (pend ? d->pradius : d->radius).push_back(0.5); (pend ? d->pdensity : d->density).push_back(1.0);
+    }
+    return OK;
+  }
   if (c == "create_atoms") {  // create_atoms.cpp (style single): one atom of the given type at a point; radius 0.5, density 1 until `set` (atom_vec_sphere.cpp:167-190)
-    if (w.size() < 6 || w[2] != "single") return fail(d, ERR_UNSUPPORTED, "create_atoms: only style 'single' is on the hot path (lattice / random creation is outside its scope)");
+    if (w.size() < 6 || w[2] != "single") return fail(d, ERR_UNSUPPORTED, "create_atoms: styles 'single', 'box' and 'region' are on the hot path (random creation is outside its scope)");
     if (!d->have_box) return fail(d, ERR_STATE, "Create_atoms command before simulation box is defined");
     double t, p[3];
     rc = numeric(d, w[1], t); if (rc) return rc;

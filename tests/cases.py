@@ -408,7 +408,9 @@ def snapshot(eng, c):
 #  b: block region, two templates (mass based), all_in yes, particles_in_region topped up every 400 steps against the spheres
 #     already there, vel uniform, omega constant
 #  c: cylinder along x, number based, all_in no, mass_in_region every 300 steps, vel gaussian, maxattempt
-INSERT_DECKS = {"insert_pack_a": [1, 2, 200, 1000], "insert_pack_b": [1, 400, 401, 801, 2500], "insert_pack_c": [1, 301, 601, 2000]}
+#  lattice_a / lattice_b: lattice + create_atoms box|region, region INF/EDGE, group region|union|subtract, velocity set (no insertion fix)
+INSERT_DECKS = {"insert_pack_a": [1, 2, 200, 1000], "insert_pack_b": [1, 400, 401, 801, 2500], "insert_pack_c": [1, 301, 601, 2000],
+                "lattice_a": [0, 1, 300, 1500], "lattice_b": [0, 1, 300, 1500]}
 
 # the reference's own INL example decks that the deck front end runs unchanged (read from the reference tree where they lie,
 # build container only; only the length of their `run` is cut): path under examples/LIGGGHTS -> steps.  Goldens:

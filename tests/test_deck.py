@@ -75,7 +75,8 @@ def test_deck_on_engine_matches_reference_golden(name, tmp_path):
 
 
 def follow_insert_golden(name, eng, deck, gpu):
-    """fix insert/pack decks: the spheres the deck front end draws (Park-Miller streams, Monte-Carlo region volume, overlap search)
+    """(also the lattice decks: lattice + create_atoms box|region, region INF / EDGE, group region|union|subtract, velocity set)
+    fix insert/pack decks: the spheres the deck front end draws (Park-Miller streams, Monte-Carlo region volume, overlap search)
     must be the reference's spheres -- ids, types, radii and masses bit-exact, positions / velocities at the insertion step to
     1e-10 -- and stay on the reference's trajectory afterwards (tolerances of parity.tol_for)"""
     g = parity.golden(name)
@@ -94,7 +95,7 @@ def follow_insert_golden(name, eng, deck, gpu):
             err = parity.rel_err(eng.download(k).reshape(ref[k].shape), ref[k], floors[k])
             assert err <= tol, "%s@%d: %s rel err %.3e" % (name, cp, k, err)
         assert eng.stats().nbuilds == int(ref["nbuilds"])
-    assert "Particle insertion ins: inserted" in deck.output
+    assert "Particle insertion ins: inserted" in deck.output or not name.startswith("insert_pack")
     deck.close(); eng.close()
 
 
