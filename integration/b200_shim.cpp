@@ -34,6 +34,7 @@ int orc_set_ntypes(struct dem_engine *, int); int orc_set_neighbor(struct dem_en
 int orc_set_freeze(struct dem_engine *, int); int orc_set_integrate(struct dem_engine *, int);
 int orc_upload_particles(struct dem_engine *, long, const int *, const int *, const int *, const double *, const double *, const double *, const double *, const double *);
 int orc_setup(struct dem_engine *); int orc_run(struct dem_engine *, long); long orc_nlocal(const struct dem_engine *);
+int orc_set_extra_force(struct dem_engine *, const char *, int, int, const double *, int);
 int orc_insert_step_begin(struct dem_engine *);
 int orc_insert_step_end(struct dem_engine *, long, const int *, const int *, const int *, const double *, const double *, const double *, const double *, const double *);
 int orc_download(struct dem_engine *, const char *, void *, long);
@@ -73,6 +74,20 @@ FixNVESphereB200::FixNVESphereB200(LAMMPS *lmp, int narg, char **arg) : FixNVESp
     update->create_integrate(1, a, NULL);
     DBG("nve/sphere/b200: integrate style is now %s", update->integrate_style);
   }
+}
+
+FixAddForceB200::FixAddForceB200(LAMMPS *lmp, int narg, char **arg) : FixAddForce(lmp, narg, arg)
+{
+  if (narg != 6) error->all(FLERR, "fix addforce/b200: options (region, energy, every) are outside the b200 hot path");
+  for (int k = 0; k < 3; k++) {
+    if (strstr(arg[3 + k], "v_") == arg[3 + k]) error->all(FLERR, "fix addforce/b200: variable components are outside the b200 hot path");
+    b200_values[k] = force->numeric(FLERR, arg[3 + k]);
+  }
+}
+FixViscousB200::FixViscousB200(LAMMPS *lmp, int narg, char **arg) : FixViscous(lmp, narg, arg)
+{
+  if (narg != 4) error->all(FLERR, "fix viscous/b200: per-type scale factors are outside the b200 hot path");
+  b200_values[0] = force->numeric(FLERR, arg[3]);
 }
 
 void PairGranB200::settings(int narg, char **arg)
@@ -134,9 +149,15 @@ void VerletB200::sync_settings()
   // VerletB200::insertion_step hands what they create to the engine inside the timestep)
   static const char *known[] = {"wall/gran", "mesh/surface", "move/mesh", "gravity", "property/global", "property/atom", "contacthistory",
                                 "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", "insert/", "particletemplate/",
+
                                 "particledistribution/", NULL};
+  // fix addforce / viscous: drop the ones the deck has unfixed, (re)send the others in the order of their definition
+  for (size_t k = 0; k < sent_xf.size(); k++) if (modify->find_fix(sent_xf[k].c_str()) < 0) DEM(set_extra_force)(eng, sent_xf[k].c_str(), 0, 0, NULL, -1);
+  sent_xf.clear();
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
+    if (FixAddForceB200 *a = dynamic_cast<FixAddForceB200 *>(f)) { if (DEM(set_extra_force)(eng, f->id, 0, f->groupbit, a->b200_values, 3)) fail("addforce"); sent_xf.push_back(f->id); continue; }
+    if (FixViscousB200 *v = dynamic_cast<FixViscousB200 *>(f)) { if (DEM(set_extra_force)(eng, f->id, 1, f->groupbit, v->b200_values, 1)) fail("viscous"); sent_xf.push_back(f->id); continue; }
     if (strcmp(f->style, "freeze") == 0) { if (DEM(set_freeze)(eng, f->groupbit)) fail("freeze"); continue; }
     if (strcmp(f->style, "nve/sphere") == 0) { if (DEM(set_integrate)(eng, f->groupbit)) fail("nve/sphere"); continue; }
     bool ok = false;

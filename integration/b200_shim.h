@@ -19,6 +19,8 @@ FixStyle(move/mesh/b200,FixMoveMeshB200)
 FixStyle(gravity/b200,FixGravityB200)
 FixStyle(property/global/b200,FixPropertyGlobalB200)
 FixStyle(nve/sphere/b200,FixNVESphereB200)
+FixStyle(addforce/b200,FixAddForceB200)
+FixStyle(viscous/b200,FixViscousB200)
 
 #elif defined(PAIR_CLASS)
 
@@ -33,6 +35,8 @@ IntegrateStyle(verlet/b200,VerletB200)
 #ifndef LMP_B200_SHIM_H
 #define LMP_B200_SHIM_H
 
+#include <string>
+#include <vector>
 #include "verlet.h"
 #include "pair_gran_proxy.h"
 #include "fix_wall_gran.h"
@@ -41,6 +45,8 @@ IntegrateStyle(verlet/b200,VerletB200)
 #include "fix_gravity.h"
 #include "fix_property_global.h"
 #include "fix_nve_sphere.h"
+#include "fix_addforce.h"
+#include "fix_viscous.h"
 
 struct dem_engine;        // include/dem_b200.h (opaque)
 struct dem_deck_handle;
@@ -59,6 +65,18 @@ B200_FIX_SHIM(FixMeshSurfaceB200, FixMeshSurface)
 B200_FIX_SHIM(FixMoveMeshB200, FixMoveMesh)
 B200_FIX_SHIM(FixGravityB200, FixGravity)
 B200_FIX_SHIM(FixPropertyGlobalB200, FixPropertyGlobal)
+// fix addforce / fix viscous act on a group of the reference: their b200 variants keep the numbers of their command, which
+// VerletB200::sync_settings hands to dem_set_extra_force together with the group's bit
+class FixAddForceB200 : public FixAddForce {
+ public:
+  FixAddForceB200(class LAMMPS *lmp, int narg, char **arg);
+  double b200_values[3];
+};
+class FixViscousB200 : public FixViscous {
+ public:
+  FixViscousB200(class LAMMPS *lmp, int narg, char **arg);
+  double b200_values[1];
+};
 
 // `fix nve/sphere` is part of every granular deck: its b200 variant also switches the integrator, because the default
 // `verlet` is created before any deck command is read and never sees the suffix (src/update.cpp:103)
@@ -87,6 +105,7 @@ class VerletB200 : public Verlet {
   bigint uploaded_step;  // timestep at which the engine received the particle state
   void fail(const char *what);
   void sync_settings();
+  std::vector<std::string> sent_xf;  // ids of the fix addforce / viscous the engine knows
   bool holds;            // the engine holds particles (false while an empty box waits for an insertion fix)
   void push_state();
   void pull_state(bool forces = true);

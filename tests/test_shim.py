@@ -114,3 +114,34 @@ def test_suffix_b200_insertion_deck_on_gpu_engine(name, tmp_path):
     if not os.path.exists(lib):
         pytest.skip("the shim build of the reference tree is not here (make -C integration)")
     check_insertion(name, lib, tmp_path, gpu=True)
+
+
+EX_WORKER = r'''
+import sys, os
+sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/oracle")
+import numpy as np, cases, ref_driver
+rel, lib, out = sys.argv[2], sys.argv[3], sys.argv[4]
+os.chdir(os.path.dirname(out))
+r = ref_driver.Ref(lib=lib, extra_args=["-suffix", "b200"])
+r.cmd(cases.example_deck_text(rel, cases.INL_EXAMPLE_DECKS[rel]))
+a = r.atoms()
+np.savez(out, **{k: a[k] for k in ("tag", "x", "v", "omega", "f", "torque")})
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(cases.INL_EXAMPLES), reason="the reference's example decks exist in the build container only")
+@pytest.mark.parametrize("rel", sorted(cases.INL_EXAMPLE_DECKS))
+def test_suffix_b200_inl_example_deck_on_oracle_binding(rel, tmp_path):
+    """the reference's INL example decks (bonded chains: fix addforce / viscous / freeze, velocity set, set group) run by the
+    reference binary with `-suffix b200` on the oracle binding: bit-identical to the plain reference (inl_examples.npz)"""
+    import parity
+    lib = os.path.join(REFDIR, "libliggghts_ref_orc.so")
+    if not os.path.exists(lib):
+        pytest.skip("the shim build of the reference tree is not here (make -C integration orc)")
+    out = str(tmp_path / "ex.npz")
+    r = subprocess.run([sys.executable, "-c", EX_WORKER, ROOT, rel, lib, out], capture_output=True, text=True, timeout=600)
+    assert os.path.exists(out), "reference run failed: " + r.stdout[-1500:] + r.stderr[-1500:]
+    a, g = np.load(out), parity.golden("inl_examples")
+    key = rel.replace("/", "|")
+    for k in a.files:
+        assert np.array_equal(a[k], g[key + ":" + k]), "%s: %s" % (rel, k)
