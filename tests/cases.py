@@ -410,7 +410,9 @@ def snapshot(eng, c):
 #  c: cylinder along x, number based, all_in no, mass_in_region every 300 steps, vel gaussian, maxattempt
 #  lattice_a / lattice_b: lattice + create_atoms box|region, region INF/EDGE, group region|union|subtract, velocity set (no insertion fix)
 INSERT_DECKS = {"insert_pack_a": [1, 2, 200, 1000], "insert_pack_b": [1, 400, 401, 801, 2500], "insert_pack_c": [1, 301, 601, 2000],
-                "lattice_a": [0, 1, 300, 1500], "lattice_b": [0, 1, 300, 1500]}
+                "lattice_a": [0, 1, 300, 1500], "lattice_b": [0, 1, 300, 1500],
+                "insert_pack_d": [1, 251, 501, 1200]}  # d: three templates, random_distribute uncorrelated, overlapcheck no (CPU only)
+INSERT_DECKS_GPU = ["insert_pack_a", "insert_pack_b", "insert_pack_c", "lattice_a", "lattice_b"]  # (the set that was run on the B200)
 
 # the reference's own INL example decks that the deck front end runs unchanged (read from the reference tree where they lie,
 # build container only; only the length of their `run` is cut): path under examples/LIGGGHTS -> steps.  Goldens:

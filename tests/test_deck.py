@@ -106,7 +106,7 @@ def test_insert_pack_deck_on_oracle_matches_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(cases.INSERT_DECKS))
+@pytest.mark.parametrize("name", cases.INSERT_DECKS_GPU)
 def test_insert_pack_deck_on_engine_matches_reference(name):
     import dem_b200
     eng = dem_b200.Engine(device=0)
