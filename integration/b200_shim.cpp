@@ -260,6 +260,9 @@ void VerletB200::run(int n)
     }
     left -= m;
     if (update->ntimestep == output->next) {
+      // thermo keywords such as pe check that energies were tallied on this step (compute_pe.cpp:105-106); the granular
+      // styles tally none, Verlet::run would have marked the step through ev_set (integrate.cpp:117-150)
+      update->eflag_global = update->vflag_global = update->ntimestep;
       timer->stamp();
       output->write(update->ntimestep);
       timer->stamp(TIME_OUTPUT);

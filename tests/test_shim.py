@@ -145,3 +145,37 @@ def test_suffix_b200_inl_example_deck_on_oracle_binding(rel, tmp_path):
     key = rel.replace("/", "|")
     for k in a.files:
         assert np.array_equal(a[k], g[key + ":" + k]), "%s: %s" % (rel, k)
+
+
+TUT_WORKER = r'''
+import sys, os, importlib.util
+sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/oracle")
+import numpy as np, ref_driver
+spec = importlib.util.spec_from_file_location("mgi", sys.argv[1] + "/tests/golden/make_golden_insert.py")
+gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+os.chdir(gen.TUTORIAL)  # (the deck names its STL file relative to itself; dump lines dropped: nothing is written there)
+text = "\n".join(l for l in gen.tutorial_text().replace("&\n", " ").splitlines() if not l.strip().startswith("dump"))
+r = ref_driver.Ref(lib=sys.argv[2], extra_args=["-suffix", "b200"])
+r.cmd(text)
+a = r.atoms()
+np.savez(sys.argv[3], n=len(a["tag"]), **{k: a[k][::16] for k in ("x", "v", "f", "radius", "rmass")})
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(cases.INL_EXAMPLES), reason="the reference's tutorial deck exists in the build container only")
+def test_suffix_b200_tutorial_t01a_on_oracle_binding(tmp_path):
+    """the reference binary with `-suffix b200` on its own tutorial deck t01a (runs cut to 500 steps): 10,802 spheres from the
+    reference's fix insert/pack enter the engine inside timestep 1, STL tube, late fix move/mesh, thermo with c_pe -- against the
+    plain reference's result (tutorial_t01a.npz)"""
+    import parity
+    lib = os.path.join(REFDIR, "libliggghts_ref_orc.so")
+    if not os.path.exists(lib):
+        pytest.skip("the shim build of the reference tree is not here (make -C integration orc)")
+    out = str(tmp_path / "tut.npz")
+    r = subprocess.run([sys.executable, "-c", TUT_WORKER, ROOT, lib, out], capture_output=True, text=True, timeout=600)
+    assert os.path.exists(out), "reference run failed: " + r.stdout[-1500:] + r.stderr[-1500:]
+    a, g = np.load(out), parity.golden("tutorial_t01a")
+    assert int(a["n"]) == int(g["s500_n"]) == 10802
+    assert np.array_equal(a["radius"], g["s500_radius"]) and np.array_equal(a["rmass"], g["s500_rmass"])
+    for k, floor in (("x", 1e-3), ("v", 1e-3), ("f", 1e-12 * 9.81 * g["s500_rmass"])):
+        assert parity.rel_err(a[k], g["s500_" + k], floor) <= 1e-9, k
