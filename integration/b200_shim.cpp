@@ -145,10 +145,11 @@ void VerletB200::sync_settings()
   }
   // group bits of the fixes that carry no other parameter; every other fix must be one the engine knows, an internal helper
   // of those, or output only -- anything else would silently change the physics
-  // (insert/*, particletemplate/*, particledistribution/*: the reference's own insertion fixes keep drawing the particles;
-  // VerletB200::insertion_step hands what they create to the engine inside the timestep)
+  // (insert/pack, particletemplate/sphere, particledistribution/*: the reference's own insertion fixes keep drawing the particles;
+  // VerletB200::insertion_step hands what they create to the engine inside the timestep.  insert/stream is NOT in the list: it
+  // moves its particles itself until they have left the insertion face, which the engine does not know)
   static const char *known[] = {"wall/gran", "mesh/surface", "move/mesh", "gravity", "property/global", "property/atom", "contacthistory",
-                                "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", "insert/", "particletemplate/",
+                                "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", "insert/pack", "particletemplate/sphere",
 
                                 "particledistribution/", NULL};
   // fix addforce / viscous: drop the ones the deck has unfixed, (re)send the others in the order of their definition
@@ -216,7 +217,7 @@ static bigint next_insertion(Modify *modify, bigint now)
   bigint next = -1;
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
-    if (strncmp(f->style, "insert/", 7) == 0 && f->force_reneighbor && f->next_reneighbor > now && (next < 0 || f->next_reneighbor < next)) next = f->next_reneighbor;
+    if (strcmp(f->style, "insert/pack") == 0 && f->force_reneighbor && f->next_reneighbor > now && (next < 0 || f->next_reneighbor < next)) next = f->next_reneighbor;
   }
   return next;
 }
@@ -233,7 +234,7 @@ void VerletB200::insertion_step()
   const int n0 = atom->nlocal;
   atom->nghost = 0;  // (ghosts of the last build are stale; one process, no periodic images in the overlap check)
   for (int i = 0; i < modify->nfix; i++)
-    if (strncmp(modify->fix[i]->style, "insert/", 7) == 0) modify->fix[i]->pre_exchange();
+    if (strcmp(modify->fix[i]->style, "insert/pack") == 0) modify->fix[i]->pre_exchange();
   const int nnew = atom->nlocal - n0;
   DBG("insertion step %ld: %d new particles", (long)update->ntimestep, nnew);
   if (DEM(insert_step_end)(eng, nnew, atom->tag + n0, atom->type + n0, atom->mask + n0, nnew ? &atom->x[n0][0] : NULL, nnew ? &atom->v[n0][0] : NULL,

@@ -419,6 +419,7 @@ INSERT_DECKS_GPU = ["insert_pack_a", "insert_pack_b", "insert_pack_c", "lattice_
 # tests/golden/inl_examples.npz (make_golden_insert.py examples)
 INL_EXAMPLES = "/root/reference/examples/LIGGGHTS"
 INL_EXAMPLE_DECKS = {
+    "Tutorials_public/contactModels/in.newModels": 1500,  # (1,800 spheres from fix insert/pack into a cylinder, hertz/history, plane + cylinder walls)
     "INL/cohesive_bond/chain_bending_test/in.chain_bending.lmp": 100000,  # (its full length: linear bond, fix addforce, fix viscous, fix freeze)
     "INL/cohesive_bond_nonlinear_compression/chain_bending_mm_1/in.chain_bending.lmp": 200000,
     "INL/cohesive_bond_nonlinear_compression/chain_bending_mm_2/in.chain_bending.lmp": 200000,

@@ -144,7 +144,11 @@ def test_suffix_b200_inl_example_deck_on_oracle_binding(rel, tmp_path):
     a, g = np.load(out), parity.golden("inl_examples")
     key = rel.replace("/", "|")
     for k in a.files:
-        assert np.array_equal(a[k], g[key + ":" + k]), "%s: %s" % (rel, k)
+        ref = g[key + ":" + k]
+        if len(ref) <= 16 or k == "tag":
+            assert np.array_equal(a[k], ref), "%s: %s" % (rel, k)
+        else:
+            assert parity.rel_err(a[k], ref, 1e-9 * max(np.abs(ref).max(), 1e-300)) <= 1e-9, "%s: %s" % (rel, k)
 
 
 TUT_WORKER = r'''
