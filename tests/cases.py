@@ -419,7 +419,9 @@ INSERT_DECKS_GPU = ["insert_pack_a", "insert_pack_b", "insert_pack_c", "lattice_
 # tests/golden/inl_examples.npz (make_golden_insert.py examples)
 INL_EXAMPLES = "/root/reference/examples/LIGGGHTS"
 INL_EXAMPLE_DECKS = {
-    "Tutorials_public/contactModels/in.newModels": 1500,  # (1,800 spheres from fix insert/pack into a cylinder, hertz/history, plane + cylinder walls)
+    "Tutorials_public/contactModels/in.newModels": 1500,  # (1,800 spheres from fix insert/pack into a cylinder, hertz/history, plane + cylinder walls; 2 runs)
+    "Tutorials_public/cohesion/in.noCohesion": 3000,  # (fix insert/pack every 3000 steps: 3 x 250 spheres, group region, unfix of the insertion; 3 runs)
+    "Tutorials_premium/mesh_force_eval/in.testmeshforce": 1500,  # (500 inserted spheres on an STL plate with mesh/surface/stress; 3 runs)
     "INL/cohesive_bond/chain_bending_test/in.chain_bending.lmp": 100000,  # (its full length: linear bond, fix addforce, fix viscous, fix freeze)
     "INL/cohesive_bond_nonlinear_compression/chain_bending_mm_1/in.chain_bending.lmp": 200000,
     "INL/cohesive_bond_nonlinear_compression/chain_bending_mm_2/in.chain_bending.lmp": 200000,
@@ -432,5 +434,10 @@ def example_deck_text(rel, nsteps):
     """an example deck of the reference with its run length replaced and its dump lines dropped (no files into the read-only tree)"""
     import re
     text = re.sub(r"&[ \t]*\n", " ", open(os.path.join(INL_EXAMPLES, rel)).read())
-    text = re.sub(r"^(run\s+)(\d+)", lambda m: m.group(1) + str(nsteps), text, flags=re.M)
+    total = [0]
+
+    def shorten(m):  # every `run N` becomes `run nsteps`, every `run N upto` ends nsteps later than the run before it
+        total[0] += nsteps
+        return m.group(1) + (str(total[0]) + m.group(3) if m.group(3) else str(nsteps))
+    text = re.sub(r"^(run\s+)(\d+)(\s+upto)?", shorten, text, flags=re.M)
     return "\n".join(l for l in text.splitlines() if not l.strip().startswith(("dump", "fix\t\tprint", "fix print")))

@@ -57,6 +57,7 @@ def tutorial():
 
 
 def example(rel):
+    os.chdir(os.path.dirname(os.path.join(cases.INL_EXAMPLES, rel)))  # (mesh files are named relative to the deck; dump lines are dropped)
     r = ref_driver.Ref()
     r.cmd(cases.example_deck_text(rel, cases.INL_EXAMPLE_DECKS[rel]))
     a = r.atoms()

@@ -121,7 +121,7 @@ import sys, os
 sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/oracle")
 import numpy as np, cases, ref_driver
 rel, lib, out = sys.argv[2], sys.argv[3], sys.argv[4]
-os.chdir(os.path.dirname(out))
+os.chdir(os.path.dirname(os.path.join(cases.INL_EXAMPLES, rel)))  # (mesh files are named relative to the deck; dump lines are dropped)
 r = ref_driver.Ref(lib=lib, extra_args=["-suffix", "b200"])
 r.cmd(cases.example_deck_text(rel, cases.INL_EXAMPLE_DECKS[rel]))
 a = r.atoms()
