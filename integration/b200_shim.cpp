@@ -149,7 +149,7 @@ void VerletB200::sync_settings()
   // VerletB200::insertion_step hands what they create to the engine inside the timestep.  insert/stream is NOT in the list: it
   // moves its particles itself until they have left the insertion face, which the engine does not know)
   static const char *known[] = {"wall/gran", "mesh/surface", "move/mesh", "gravity", "property/global", "property/atom", "contacthistory",
-                                "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", "insert/pack", "particletemplate/sphere",
+                                "neighlist/mesh", "check/timestep/gran", "print", "ave/", "store", "contactproperty", "insert/pack", "particletemplate/sphere", "STORE",
 
                                 "particledistribution/", NULL};
   // fix addforce / viscous: drop the ones the deck has unfixed, (re)send the others in the order of their definition

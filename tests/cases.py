@@ -430,6 +430,12 @@ INL_EXAMPLE_DECKS = {
 }
 
 
+# decks that only run under the `-suffix b200` shim (they use script features the deck front end does not have: `print` of
+# compute-based variables, `compute displace/atom` ...): 5,850 spheres from fix insert/pack (mass_in_region) into a cylinder
+SHIM_ONLY_DECKS = {"Tutorials_premium/dump_custom_vtk/in.dump_custom_vtk": 500}
+ALL_EXAMPLE_DECKS = dict(INL_EXAMPLE_DECKS, **SHIM_ONLY_DECKS)
+
+
 def example_deck_text(rel, nsteps):
     """an example deck of the reference with its run length replaced and its dump lines dropped (no files into the read-only tree)"""
     import re
@@ -440,4 +446,5 @@ def example_deck_text(rel, nsteps):
         total[0] += nsteps
         return m.group(1) + (str(total[0]) + m.group(3) if m.group(3) else str(nsteps))
     text = re.sub(r"^(run\s+)(\d+)(\s+upto)?", shorten, text, flags=re.M)
+    text = re.sub(r"^(run\s+)\$\{\w+\}", lambda m: m.group(1) + str(nsteps), text, flags=re.M)  # (`run ${nDump}`)
     return "\n".join(l for l in text.splitlines() if not l.strip().startswith(("dump", "fix\t\tprint", "fix print")))

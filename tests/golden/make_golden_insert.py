@@ -59,7 +59,7 @@ def tutorial():
 def example(rel):
     os.chdir(os.path.dirname(os.path.join(cases.INL_EXAMPLES, rel)))  # (mesh files are named relative to the deck; dump lines are dropped)
     r = ref_driver.Ref()
-    r.cmd(cases.example_deck_text(rel, cases.INL_EXAMPLE_DECKS[rel]))
+    r.cmd(cases.example_deck_text(rel, cases.ALL_EXAMPLE_DECKS[rel]))
     a = r.atoms()
     path = os.path.join(HERE, "inl_examples.npz")
     out = dict(np.load(path)) if os.path.exists(path) else {}
@@ -81,5 +81,5 @@ if __name__ == "__main__":
         import subprocess
         for name in list(cases.INSERT_DECKS) + ["tutorial"]:
             subprocess.run([sys.executable, os.path.abspath(__file__), name], check=True)
-        for rel in cases.INL_EXAMPLE_DECKS:
+        for rel in cases.ALL_EXAMPLE_DECKS:
             subprocess.run([sys.executable, os.path.abspath(__file__), "example", rel], check=True)

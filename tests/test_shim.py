@@ -123,14 +123,14 @@ import numpy as np, cases, ref_driver
 rel, lib, out = sys.argv[2], sys.argv[3], sys.argv[4]
 os.chdir(os.path.dirname(os.path.join(cases.INL_EXAMPLES, rel)))  # (mesh files are named relative to the deck; dump lines are dropped)
 r = ref_driver.Ref(lib=lib, extra_args=["-suffix", "b200"])
-r.cmd(cases.example_deck_text(rel, cases.INL_EXAMPLE_DECKS[rel]))
+r.cmd(cases.example_deck_text(rel, cases.ALL_EXAMPLE_DECKS[rel]))
 a = r.atoms()
 np.savez(out, **{k: a[k] for k in ("tag", "x", "v", "omega", "f", "torque")})
 '''
 
 
 @pytest.mark.skipif(not os.path.isdir(cases.INL_EXAMPLES), reason="the reference's example decks exist in the build container only")
-@pytest.mark.parametrize("rel", sorted(cases.INL_EXAMPLE_DECKS))
+@pytest.mark.parametrize("rel", sorted(cases.ALL_EXAMPLE_DECKS))
 def test_suffix_b200_inl_example_deck_on_oracle_binding(rel, tmp_path):
     """the reference's INL example decks (bonded chains: fix addforce / viscous / freeze, velocity set, set group) run by the
     reference binary with `-suffix b200` on the oracle binding: bit-identical to the plain reference (inl_examples.npz)"""
